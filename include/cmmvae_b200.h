@@ -1,0 +1,148 @@
+/* cmmvae_b200.h -- C ABI of libcmmvae_b200.so: hand-written sm_100a kernels for the CMMVAE
+ * training step.  Plain pointers + sizes; no torch types.  Every pointer is a DEVICE pointer
+ * unless it says "host".  Every launch is asynchronous on `stream` (a cudaStream_t passed as
+ * void*), performs no hidden synchronisation and allocates nothing: the caller owns all buffers.
+ * Return value: 0 on success, negative on error (message via cmmvae_last_error(), thread local).
+ *
+ * The reference (zdebruine/MMVAE) has no FFI layer: its boundary is the Python module API of
+ * src/cmmvae.  Each entry point below cites the reference code whose arithmetic
+ * it replaces; the Python host side in mmvae_b200/ mirrors the reference's nn.Module /
+ * LightningModule interface and is the only caller (through ctypes).
+ *
+ * dtype enums: CMMVAE_F32 = 0, CMMVAE_BF16 = 1.  Matrices are row-major, leading dimension in
+ * elements.
+ */
+#ifndef CMMVAE_B200_H
+#define CMMVAE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMMVAE_ABI_VERSION 1
+#define CMMVAE_F32 0
+#define CMMVAE_BF16 1
+
+int cmmvae_abi_version(void);
+const char* cmmvae_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py gpu_launches) */
+long long cmmvae_launch_count(void);
+
+/* ---- K1: expert-encoder first layer on a CSR batch ---------------------------------------
+ * replaces nn.Linear applied to torch.sparse_csr input: components.py:276,306 (FCBlock layer 0
+ * of Expert.encoder, components.py:853); batch layout from cellxgene_datapipe.py:178-183.
+ * Y[B,H] (f32) = X_csr[B,G] * Wt[G,H] + bias.  Wt is the TRANSPOSED weight (physical [G,H],
+ * f32 or bf16).  crow int32[B+1], col int32[nnz] sorted & duplicate-free per row, val f32. */
+int cmmvae_csr_linear_fwd(const int32_t* crow, const int32_t* col, const float* val,
+                          int B, int G, int H, const void* Wt, int w_dtype, const float* bias,
+                          float* Y, void* stream);
+
+/* CSR -> CSC of the same batch (needed by the weight gradient).  cptr int32[G+1], ridx int32[nnz],
+ * cval f32[nnz]; `cursor` is an int32[G+1] scratch.  Order inside a column is unspecified. */
+int cmmvae_csr_transpose(const int32_t* crow, const int32_t* col, const float* val,
+                         int B, int G, long long nnz, int32_t* cptr, int32_t* ridx, float* cval,
+                         int32_t* cursor, void* stream);
+
+/* K1b: autograd of the sparse addmm: dWt[G,H] = X^T dY, via the CSC arrays.
+ * Genes absent from the batch get exactly 0.  dY f32 [B,H].  beta=0 overwrites. */
+int cmmvae_csr_linear_bwd_w(const int32_t* cptr, const int32_t* ridx, const float* cval,
+                            int B, int G, int H, const float* dY, float* dWt, void* stream);
+
+/* ---- K2/K3: BatchNorm1d(momentum, eps) + ReLU + Dropout, components.py:279-288 ------------- */
+/* column statistics of Y[B,H]: mean[H], rstd[H] = 1/sqrt(biased var + eps); updates running
+ * stats (unbiased var, momentum) when running_mean != NULL.  `scratch` = 2*H doubles, zeroed by
+ * the call. */
+int cmmvae_bn_stats(const float* Y, int B, int H, float eps, float momentum, float* mean, float* rstd,
+                    float* running_mean, float* running_var, double* scratch, void* stream);
+/* out = drop(act(gamma*(Y-mean)*rstd+beta)); gamma==NULL -> no normalisation (plain act/dropout).
+ * relu: 0/1.  dropout: keep-prob scaling 1/(1-p), Bernoulli mask from a counter-based hash of
+ * (seed, element index) (recomputed in backward), or from `mask` (uint8 [B,H], injected) if
+ * non-NULL.  Writes out_f32 and/or out_bf16 (either may be NULL). */
+int cmmvae_bn_act_drop_fwd(const float* Y, int B, int H, const float* mean, const float* rstd,
+                           const float* gamma, const float* beta, int relu, float p_drop,
+                           unsigned long long seed, const uint8_t* mask,
+                           float* out_f32, void* out_bf16, void* stream);
+/* backward of the above.  dOut f32 [B,H]; `out` = forward output (sign gives the ReLU mask).
+ * Produces dY f32 (+bf16 copy), dgamma, dbeta (if gamma != NULL) and dbias = colsum(dY). */
+int cmmvae_bn_act_drop_bwd(const float* dOut, const float* Y, const float* out, int B, int H,
+                           const float* mean, const float* rstd, const float* gamma,
+                           int relu, float p_drop, unsigned long long seed, const uint8_t* mask,
+                           float* dY, void* dY_bf16, float* dgamma, float* dbeta, float* dbias,
+                           void* stream);
+/* eval-mode BN uses running stats: call bn_act_drop_fwd with mean=running_mean and
+ * rstd computed by this helper. */
+int cmmvae_rstd_from_var(const float* var, int H, float eps, float* rstd, void* stream);
+
+/* ---- dense GEMMs (K4/K12), nn.Linear: components.py:276 ------------------------------------
+ * C[M,N] = act( opA(A) * opB(B) + bias ) (+ C if accumulate).  transA: A stored [K,M];
+ * transB=0: B stored [N,K] (nn.Linear weight layout), transB=1: B stored [K,N].
+ * bias (f32 [N]) may be NULL.  relu: 0/1.  Outputs: C_f32 and/or C_bf16 (either may be NULL). */
+/* fp32 CUDA-core path: any shape; inputs f32. */
+int cmmvae_gemm_f32(const float* A, int lda, int transA, const float* Bm, int ldb, int transB,
+                    int M, int N, int K, const float* bias, int relu, int accumulate,
+                    float* C_f32, void* C_bf16, int ldc, void* stream);
+/* tcgen05/TMEM/TMA path: inputs bf16, fp32 accumulate.  Requires 16-byte aligned bases and
+ * leading dimensions that are multiples of 8 elements; any M, N, K (TMA zero-fills edges). */
+int cmmvae_gemm_bf16_tc(const void* A, int lda, int transA, const void* Bm, int ldb, int transB,
+                        int M, int N, int K, const float* bias, int relu, int accumulate,
+                        float* C_f32, void* C_bf16, int ldc, void* stream);
+/* column sums: out[N] (=|+=) sum_m X[m,n]  (bias gradients) */
+int cmmvae_colsum(const void* X, int x_dtype, int M, int N, int ldx, float* out, int accumulate, void* stream);
+
+/* ---- K8+K9(+Mean/Variance): reparameterisation + KL, components.py:790-801, vae.py:136-138 --
+ * ML f32 [B,2Z] = [mu | logvar];  z = mu + eps*sqrt(exp(lv)+var_eps).
+ * sums (double[3], zeroed by the call): [sum_b KL_b, sum mu, sum var].  z_f32/z_bf16 optional. */
+int cmmvae_reparam_kl_fwd(const float* ML, const float* eps, int B, int Z, float var_eps,
+                          float* z_f32, void* z_bf16, double* sums, void* stream);
+/* dML[B,2Z] from dz (f32 [B,Z]) and the KL term: kl_scale = kl_weight / B. */
+int cmmvae_reparam_kl_bwd(const float* ML, const float* eps, const float* dz, int B, int Z, float var_eps,
+                          float kl_scale, float* dML, void* dML_bf16, void* stream);
+
+/* ---- K5-K7: expert-decoder output + ReLU + sum-MSE against the CSR batch --------------------
+ * replaces Linear(H->G)+ReLU (components.py:840,857), x.to_dense() (cmmvae_model.py:162-163) and
+ * F.mse_loss(reduction='sum') (vae.py:143).
+ * unfused form (f32 logits already materialised, used by the fp32 path and by validation):
+ * xhat = relu(logits) in place (optional), loss_sum (double[1], zeroed by the call) =
+ * sum (xhat - x)^2, dlogits = 2 (xhat - x) 1[logit>0] (f32 and/or bf16 with leading dim ldd). */
+int cmmvae_mse_relu_csr(float* logits, int ldl, int B, int G, const int32_t* crow, const int32_t* col,
+                        const float* val, int write_xhat, float* dlogits_f32, void* dlogits_bf16, int ldd,
+                        double* loss_sum, void* stream);
+/* fused form: logits tile stays in TMEM; epilogue adds bias, applies ReLU, reduces the loss against
+ * the CSR entries of the tile and emits dlogits bf16 [B,ldd]; xhat never reaches HBM.
+ * h bf16 [B,H] (ldh), Wout bf16 [G,H] (ldw), bout f32 [G].  `workspace` (device, size from
+ * cmmvae_decoder_mse_fused_workspace_bytes) receives the per-(cell, gene-tile) CSR pointer table.
+ * loss_sum (double[1]) is zeroed by the call. */
+size_t cmmvae_decoder_mse_fused_workspace_bytes(int B, int G);
+int cmmvae_decoder_mse_fused(const void* h, int ldh, const void* Wout, int ldw, const float* bout,
+                             int B, int G, int H, const int32_t* crow, const int32_t* col, const float* val,
+                             void* dlogits_bf16, int ldd, double* loss_sum, void* workspace, void* stream);
+
+/* ---- K11: adversary heads, CrossEntropyLoss(reduction='sum') (cmmvae_model.py:54,85) --------
+ * logits f32 [B,C] (ldl), labels int64[B]; loss_sum double[1] += ; dlogits = scale*(softmax-onehot). */
+int cmmvae_softmax_ce_sum(const float* logits, int ldl, int B, int C, const long long* labels,
+                          float scale, float* dlogits, int ldd, double* loss_sum, void* stream);
+
+/* ---- K13-K15: grad-norm, clip-by-norm, Adam (base_model.py:111-123, cmmvae_model.py:203-213,
+ * 306-319; torch.optim.Adam with L2 weight decay) --------------------------------------------
+ * norm_sq (double[1]) += sum g^2 over n elements (caller zeroes it). */
+int cmmvae_sumsq(const float* g, long long n, double* norm_sq, void* stream);
+/* coef = max_norm>0 ? min(1, max_norm/(sqrt(*norm_sq)+1e-6)) : 1, read ON DEVICE (no host sync);
+ * g' = coef*grad_scale*g + wd*p; m,v,p updated; bf16 shadow written if non-NULL.
+ * bc1 = 1-beta1^t, bc2 = 1-beta2^t computed by the host. */
+int cmmvae_clip_adam(float* p, const float* g, float* m, float* v, void* p_bf16, long long n,
+                     const double* norm_sq, float max_norm, float grad_scale, float lr, float beta1, float beta2,
+                     float eps, float wd, float bc1, float bc2, void* stream);
+
+/* ---- small utilities ------------------------------------------------------------------------ */
+int cmmvae_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);
+/* dst[c,r] = src[r,c] for a row-major [R,C] f32/bf16 matrix */
+int cmmvae_transpose(const void* src, void* dst, int dtype, int R, int C, int lds, int ldd, void* stream);
+/* a[i] += alpha * b[i] */
+int cmmvae_axpy(float* a, const float* b, float alpha, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,20 @@
+// ABI bookkeeping: version, thread-local error string, launch counter.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace cmmvae {
+static thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+}  // namespace cmmvae
+
+extern "C" int cmmvae_abi_version(void) { return CMMVAE_ABI_VERSION; }
+extern "C" const char* cmmvae_last_error(void) { return cmmvae::g_err; }
+extern "C" long long cmmvae_launch_count(void) { return cmmvae::g_launches.load(); }

@@ -1,0 +1,623 @@
+// Elementwise / reduction kernels of the CMMVAE step: BatchNorm+ReLU+Dropout (K2/K3) forward and
+// backward, reparameterisation + KL (K8/K9), softmax cross-entropy (K11), column sums, the fp32
+// CUDA-core GEMM (exact path + odd shapes), grad-norm / clip / Adam (K13-K15) and small utilities.
+#include "common.cuh"
+
+namespace cmmvae {
+
+// ---------------------------------------------------------------------------------------------
+// column reductions over a row-major [M,N] matrix.  grid (ceil(N/32), row chunks), block (32, 8)
+// ---------------------------------------------------------------------------------------------
+constexpr int kRowsPerChunk = 256;
+
+__global__ void __launch_bounds__(256) bn_stats_reduce_kernel(const float* __restrict__ Y, int B, int H,
+                                                              double* __restrict__ scratch) {
+  __shared__ double s1[8][33], s2[8][33];
+  const int h = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = blockIdx.y * kRowsPerChunk;
+  const int r1 = min(B, r0 + kRowsPerChunk);
+  double a = 0.0, b = 0.0;
+  if (h < H)
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      const double y = Y[(size_t)r * H + h];
+      a += y;
+      b += y * y;
+    }
+  s1[threadIdx.y][threadIdx.x] = a;
+  s2[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && h < H) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      a += s1[i][threadIdx.x];
+      b += s2[i][threadIdx.x];
+    }
+    atomicAdd(&scratch[h], a);
+    atomicAdd(&scratch[H + h], b);
+  }
+}
+
+__global__ void bn_stats_finalize_kernel(const double* __restrict__ scratch, int B, int H, float eps,
+                                         float momentum, float* __restrict__ mean, float* __restrict__ rstd,
+                                         float* __restrict__ rm, float* __restrict__ rv) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  const double m = scratch[h] / B;
+  double var = scratch[H + h] / B - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[h] = (float)m;
+  rstd[h] = (float)(1.0 / sqrt(var + (double)eps));
+  if (rm) {
+    const double unbiased = B > 1 ? var * ((double)B / (double)(B - 1)) : var;
+    rm[h] = (float)((1.0 - (double)momentum) * (double)rm[h] + (double)momentum * m);
+    rv[h] = (float)((1.0 - (double)momentum) * (double)rv[h] + (double)momentum * unbiased);
+  }
+}
+
+__global__ void rstd_from_var_kernel(const float* __restrict__ var, int H, float eps, float* __restrict__ rstd) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h < H) rstd[h] = 1.0f / sqrtf(var[h] + eps);
+}
+
+__global__ void __launch_bounds__(256) bn_act_drop_fwd_kernel(const float* __restrict__ Y, long long n, int H,
+                                                              const float* __restrict__ mean,
+                                                              const float* __restrict__ rstd,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, int relu,
+                                                              float p_drop, unsigned long long seed,
+                                                              const uint8_t* __restrict__ mask,
+                                                              float* __restrict__ o32,
+                                                              __nv_bfloat16* __restrict__ o16) {
+  const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int h = (int)(i % H);
+    float v = Y[i];
+    if (gamma) v = (v - mean[h]) * rstd[h] * gamma[h] + beta[h];
+    if (relu) v = fmaxf(v, 0.f);
+    if (p_drop > 0.f) {
+      const bool keep = mask ? (mask[i] != 0) : dropout_keep(seed, (unsigned long long)i, p_drop);
+      v = keep ? v * keep_scale : 0.f;
+    }
+    if (o32) o32[i] = v;
+    if (o16) o16[i] = __float2bfloat16(v);
+  }
+}
+
+__device__ __forceinline__ float dpre_of(float dout, float out, int relu, float p_drop, float keep_scale,
+                                         unsigned long long seed, const uint8_t* mask, long long i) {
+  float d = dout;
+  if (p_drop > 0.f) {
+    const bool keep = mask ? (mask[i] != 0) : dropout_keep(seed, (unsigned long long)i, p_drop);
+    d = keep ? d * keep_scale : 0.f;
+  }
+  if (relu && !(out > 0.f)) d = 0.f;
+  return d;
+}
+
+// pass A: dbeta[h] = sum dpre, dgamma[h] = sum dpre * yhat     (float atomics into zeroed buffers)
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dOut,
+                                                            const float* __restrict__ Y,
+                                                            const float* __restrict__ out, int B, int H,
+                                                            const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, int relu, float p_drop,
+                                                            unsigned long long seed, const uint8_t* __restrict__ mask,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float s1[8][33], s2[8][33];
+  const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+  const int h = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = blockIdx.y * kRowsPerChunk, r1 = min(B, r0 + kRowsPerChunk);
+  float a = 0.f, b = 0.f;
+  if (h < H) {
+    const float m = mean[h], rs = rstd[h];
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      const long long i = (long long)r * H + h;
+      const float d = dpre_of(dOut[i], relu ? out[i] : 1.f, relu, p_drop, keep_scale, seed, mask, i);
+      a += d;
+      b = fmaf(d, (Y[i] - m) * rs, b);
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = a;
+  s2[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && h < H) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      a += s1[i][threadIdx.x];
+      b += s2[i][threadIdx.x];
+    }
+    atomicAdd(&dbeta[h], a);
+    atomicAdd(&dgamma[h], b);
+  }
+}
+
+// pass B: dY = gamma*rstd*(dpre - dbeta/B - yhat*dgamma/B)  (or dY = dpre without BN); dbias += colsum(dY)
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ dOut,
+                                                           const float* __restrict__ Y,
+                                                           const float* __restrict__ out, int B, int H,
+                                                           const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd,
+                                                           const float* __restrict__ gamma, int relu, float p_drop,
+                                                           unsigned long long seed, const uint8_t* __restrict__ mask,
+                                                           const float* __restrict__ dgamma,
+                                                           const float* __restrict__ dbeta, float* __restrict__ dY,
+                                                           __nv_bfloat16* __restrict__ dY16,
+                                                           float* __restrict__ dbias) {
+  __shared__ float s1[8][33];
+  const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+  const int h = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = blockIdx.y * kRowsPerChunk, r1 = min(B, r0 + kRowsPerChunk);
+  float a = 0.f;
+  if (h < H) {
+    float m = 0.f, rs = 0.f, gm = 0.f, dg = 0.f, db = 0.f;
+    if (gamma) {
+      m = mean[h]; rs = rstd[h]; gm = gamma[h];
+      dg = dgamma[h] / (float)B; db = dbeta[h] / (float)B;
+    }
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      const long long i = (long long)r * H + h;
+      float d = dpre_of(dOut[i], relu ? out[i] : 1.f, relu, p_drop, keep_scale, seed, mask, i);
+      if (gamma) d = gm * rs * (d - db - (Y[i] - m) * rs * dg);
+      if (dY) dY[i] = d;
+      if (dY16) dY16[i] = __float2bfloat16(d);
+      a += d;
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && h < H && dbias) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) a += s1[i][threadIdx.x];
+    atomicAdd(&dbias[h], a);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, int M, int N, int ldx,
+                                                     float* __restrict__ out) {
+  __shared__ float s1[8][33];
+  const int h = blockIdx.x * 32 + threadIdx.x;
+  const int r0 = blockIdx.y * kRowsPerChunk, r1 = min(M, r0 + kRowsPerChunk);
+  float a = 0.f;
+  if (h < N)
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) a += to_f32<T>(X[(size_t)r * ldx + h]);
+  s1[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && h < N) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) a += s1[i][threadIdx.x];
+    atomicAdd(&out[h], a);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// reparameterisation + KL (+ Mean / Variance diagnostics)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) reparam_kl_fwd_kernel(const float* __restrict__ ML,
+                                                             const float* __restrict__ eps, int B, int Z,
+                                                             float var_eps, float* __restrict__ z32,
+                                                             __nv_bfloat16* __restrict__ z16,
+                                                             double* __restrict__ sums) {
+  __shared__ double red[32];
+  const long long n = (long long)B * Z;
+  double kl = 0.0, sm = 0.0, sv = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / Z), k = (int)(i % Z);
+    const float mu = ML[(size_t)b * 2 * Z + k];
+    const float lv = ML[(size_t)b * 2 * Z + Z + k];
+    const float var = expf(lv) + var_eps;
+    const float sigma = sqrtf(var);
+    const float zz = fmaf(eps[i], sigma, mu);
+    if (z32) z32[i] = zz;
+    if (z16) z16[i] = __float2bfloat16(zz);
+    // torch: Normal(mu, sqrt(var)); kl uses scale^2 = (sqrt(var))^2
+    const float var_ratio = sigma * sigma;
+    kl += 0.5 * ((double)var_ratio + (double)mu * mu - 1.0 - (double)logf(var_ratio));
+    sm += mu;
+    sv += var_ratio;
+  }
+  double t;
+  t = block_sum<double>(kl, red);
+  if (threadIdx.x == 0) atomicAdd(&sums[0], t);
+  t = block_sum<double>(sm, red);
+  if (threadIdx.x == 0) atomicAdd(&sums[1], t);
+  t = block_sum<double>(sv, red);
+  if (threadIdx.x == 0) atomicAdd(&sums[2], t);
+}
+
+__global__ void __launch_bounds__(256) reparam_kl_bwd_kernel(const float* __restrict__ ML,
+                                                             const float* __restrict__ eps,
+                                                             const float* __restrict__ dz, int B, int Z,
+                                                             float var_eps, float kl_scale, float* __restrict__ dML,
+                                                             __nv_bfloat16* __restrict__ dML16) {
+  const long long n = (long long)B * Z;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / Z), k = (int)(i % Z);
+    const size_t im = (size_t)b * 2 * Z + k, iv = im + Z;
+    const float mu = ML[im], lv = ML[iv];
+    const float e = expf(lv);
+    const float var = e + var_eps;
+    const float sigma = sqrtf(var);
+    const float g = dz ? dz[i] : 0.f;
+    // d/dmu = g + kl_scale*mu ; d/dlv = [ g*eps/(2 sigma) + kl_scale*0.5*(1 - 1/var) ] * exp(lv)
+    const float dmu = g + kl_scale * mu;
+    const float dlv = (g * eps[i] / (2.f * sigma) + kl_scale * 0.5f * (1.f - 1.f / var)) * e;
+    if (dML) { dML[im] = dmu; dML[iv] = dlv; }
+    if (dML16) { dML16[im] = __float2bfloat16(dmu); dML16[iv] = __float2bfloat16(dlv); }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// softmax cross-entropy, reduction='sum' (one warp per row)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict__ logits, int ldl, int B, int C,
+                                                         const long long* __restrict__ labels, float scale,
+                                                         float* __restrict__ dl, int ldd,
+                                                         double* __restrict__ loss_sum) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  const float* row = logits + (size_t)warp * ldl;
+  float mx = -INFINITY;
+  for (int c = lane; c < C; c += 32) mx = fmaxf(mx, row[c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float se = 0.f;
+  for (int c = lane; c < C; c += 32) se += expf(row[c] - mx);
+  se = warp_sum(se);
+  const int lab = (int)labels[warp];
+  const float lse = mx + logf(se);
+  if (lane == 0) atomicAdd(loss_sum, (double)(lse - row[lab]));
+  if (dl) {
+    const float inv = 1.f / se;
+    for (int c = lane; c < C; c += 32) {
+      const float p = expf(row[c] - mx) * inv;
+      dl[(size_t)warp * ldd + c] = scale * (p - (c == lab ? 1.f : 0.f));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 CUDA-core GEMM: C[M,N] = act(opA(A) opB(B) + bias) (+C).  64x64x16 tiles, 4x4 per thread.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, int lda, int transA,
+                                                       const float* __restrict__ Bm, int ldb, int transB, int M,
+                                                       int N, int K, const float* __restrict__ bias, int relu,
+                                                       int accumulate, float* __restrict__ C32,
+                                                       __nv_bfloat16* __restrict__ C16, int ldc) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    // 64x16 elements each: 1024 / 256 threads = 4 per thread
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int e = threadIdx.x + t * 256;
+      int mm, kk;
+      if (transA) { mm = e % 64; kk = e / 64; } else { kk = e % 16; mm = e / 16; }
+      const int gm = m0 + mm, gk = k0 + kk;
+      float v = 0.f;
+      if (gm < M && gk < K) v = transA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+      As[kk][mm] = v;
+      int nn, kb;
+      if (transB) { nn = e % 64; kb = e / 64; } else { kb = e % 16; nn = e / 16; }
+      const int gn = n0 + nn, gkb = k0 + kb;
+      float w = 0.f;
+      if (gn < N && gkb < K) w = transB ? Bm[(size_t)gkb * ldb + gn] : Bm[(size_t)gn * ldb + gkb];
+      Bs[kb][nn] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j] + (bias ? bias[gn] : 0.f);
+      const size_t o = (size_t)gm * ldc + gn;
+      if (accumulate && C32) v += C32[o];
+      if (relu) v = fmaxf(v, 0.f);
+      if (C32) C32[o] = v;
+      if (C16) C16[o] = __float2bfloat16(v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// grad-norm / clip / Adam
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n,
+                                                    double* __restrict__ out) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  const long long n4 = n / 4;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 t = g4[i];
+    acc += (double)(t.x * t.x + t.y * t.y) + (double)(t.z * t.z + t.w * t.w);
+  }
+  for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    acc += (double)g[i] * g[i];
+  const double t = block_sum<double>(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, t);
+}
+
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float gscale, float lr,
+                                         float b1, float b2, float eps, float wd, float bc1, float inv_sqrt_bc2) {
+  g = g * gscale;
+  g = fmaf(wd, p, g);                 // grad = grad + wd * p
+  m = m + (g - m) * (1.f - b1);       // exp_avg.lerp_(grad, 1-beta1)
+  v = v * b2 + (1.f - b2) * g * g;    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
+  const float denom = sqrtf(v) * inv_sqrt_bc2 + eps;
+  p = p - (lr / bc1) * (m / denom);
+}
+
+__global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v,
+                                                        __nv_bfloat16* __restrict__ p16, long long n,
+                                                        const double* __restrict__ norm_sq, float max_norm,
+                                                        float grad_scale, float lr, float b1, float b2, float eps,
+                                                        float wd, float bc1, float bc2) {
+  float coef = 1.f;
+  if (max_norm > 0.f && norm_sq) {
+    const float total = (float)sqrt(*norm_sq) * fabsf(grad_scale);
+    coef = fminf(1.f, max_norm / (total + 1e-6f));
+  }
+  const float gs = coef * grad_scale;
+  const float isb2 = 1.f / sqrtf(bc2);
+  const long long n4 = n / 4;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 pp = p4[i], mm = m4[i], vv = v4[i];
+    const float4 gg = g4[i];
+    adam_one(pp.x, gg.x, mm.x, vv.x, gs, lr, b1, b2, eps, wd, bc1, isb2);
+    adam_one(pp.y, gg.y, mm.y, vv.y, gs, lr, b1, b2, eps, wd, bc1, isb2);
+    adam_one(pp.z, gg.z, mm.z, vv.z, gs, lr, b1, b2, eps, wd, bc1, isb2);
+    adam_one(pp.w, gg.w, mm.w, vv.w, gs, lr, b1, b2, eps, wd, bc1, isb2);
+    p4[i] = pp; m4[i] = mm; v4[i] = vv;
+    if (p16) {
+      uint2 o;
+      o.x = pack_bf16(pp.x, pp.y);
+      o.y = pack_bf16(pp.z, pp.w);
+      *reinterpret_cast<uint2*>(p16 + i * 4) = o;
+    }
+  }
+  for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float pp = p[i], mm = m[i], vv = v[i];
+    adam_one(pp, g[i], mm, vv, gs, lr, b1, b2, eps, wd, bc1, isb2);
+    p[i] = pp; m[i] = mm; v[i] = vv;
+    if (p16) p16[i] = __float2bfloat16(pp);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// utilities
+// ---------------------------------------------------------------------------------------------
+__global__ void cast_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    d[i] = __float2bfloat16(s[i]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ s, T* __restrict__ d, int R, int C,
+                                                        int lds, int ldd) {
+  __shared__ T tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < R && c < C) tile[i][threadIdx.x] = s[(size_t)r * lds + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < C) d[(size_t)c * ldd + r] = tile[threadIdx.x][i];
+  }
+}
+
+__global__ void axpy_kernel(float* __restrict__ a, const float* __restrict__ b, float alpha, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    a[i] = fmaf(alpha, b[i], a[i]);
+}
+
+static inline int ew_blocks(long long n) {
+  long long b = (n + 255) / 256;
+  return (int)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
+}
+
+}  // namespace cmmvae
+
+using namespace cmmvae;
+
+extern "C" int cmmvae_bn_stats(const float* Y, int B, int H, float eps, float momentum, float* mean, float* rstd,
+                               float* running_mean, float* running_var, double* scratch, void* stream) {
+  CMMVAE_REQUIRE(B > 0 && H > 0 && scratch, "bn_stats: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * (size_t)H, st);
+  dim3 grid((H + 31) / 32, (B + kRowsPerChunk - 1) / kRowsPerChunk), block(32, 8);
+  bn_stats_reduce_kernel<<<grid, block, 0, st>>>(Y, B, H, scratch);
+  if (int rc = check_launch("bn_stats_reduce")) return rc;
+  bn_stats_finalize_kernel<<<(H + 255) / 256, 256, 0, st>>>(scratch, B, H, eps, momentum, mean, rstd,
+                                                            running_mean, running_var);
+  return check_launch("bn_stats_finalize");
+}
+
+extern "C" int cmmvae_rstd_from_var(const float* var, int H, float eps, float* rstd, void* stream) {
+  rstd_from_var_kernel<<<(H + 255) / 256, 256, 0, (cudaStream_t)stream>>>(var, H, eps, rstd);
+  return check_launch("rstd_from_var");
+}
+
+extern "C" int cmmvae_bn_act_drop_fwd(const float* Y, int B, int H, const float* mean, const float* rstd,
+                                      const float* gamma, const float* beta, int relu, float p_drop,
+                                      unsigned long long seed, const uint8_t* mask, float* out_f32,
+                                      void* out_bf16, void* stream) {
+  CMMVAE_REQUIRE(B > 0 && H > 0, "bn_act_drop_fwd: bad shape");
+  CMMVAE_REQUIRE(!gamma || (mean && rstd && beta), "bn_act_drop_fwd: gamma without mean/rstd/beta");
+  CMMVAE_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "bn_act_drop_fwd: p_drop out of range");
+  const long long n = (long long)B * H;
+  bn_act_drop_fwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(
+      Y, n, H, mean, rstd, gamma, beta, relu, p_drop, seed, mask, out_f32, (__nv_bfloat16*)out_bf16);
+  return check_launch("bn_act_drop_fwd");
+}
+
+extern "C" int cmmvae_bn_act_drop_bwd(const float* dOut, const float* Y, const float* out, int B, int H,
+                                      const float* mean, const float* rstd, const float* gamma, int relu,
+                                      float p_drop, unsigned long long seed, const uint8_t* mask, float* dY,
+                                      void* dY_bf16, float* dgamma, float* dbeta, float* dbias, void* stream) {
+  CMMVAE_REQUIRE(B > 0 && H > 0, "bn_act_drop_bwd: bad shape");
+  CMMVAE_REQUIRE(!gamma || (mean && rstd && dgamma && dbeta && Y), "bn_act_drop_bwd: BN needs stats and outputs");
+  CMMVAE_REQUIRE(!relu || out, "bn_act_drop_bwd: relu needs the forward output");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((H + 31) / 32, (B + kRowsPerChunk - 1) / kRowsPerChunk), block(32, 8);
+  if (gamma) {
+    cudaMemsetAsync(dgamma, 0, sizeof(float) * H, st);
+    cudaMemsetAsync(dbeta, 0, sizeof(float) * H, st);
+    bn_bwd_reduce_kernel<<<grid, block, 0, st>>>(dOut, Y, out, B, H, mean, rstd, relu, p_drop, seed, mask,
+                                                 dgamma, dbeta);
+    if (int rc = check_launch("bn_bwd_reduce")) return rc;
+  }
+  if (dbias) cudaMemsetAsync(dbias, 0, sizeof(float) * H, st);
+  bn_bwd_apply_kernel<<<grid, block, 0, st>>>(dOut, Y, out, B, H, mean, rstd, gamma, relu, p_drop, seed, mask,
+                                              dgamma, dbeta, dY, (__nv_bfloat16*)dY_bf16, dbias);
+  return check_launch("bn_bwd_apply");
+}
+
+extern "C" int cmmvae_colsum(const void* X, int x_dtype, int M, int N, int ldx, float* out, int accumulate,
+                             void* stream) {
+  CMMVAE_REQUIRE(M > 0 && N > 0 && ldx >= N, "colsum: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * N, st);
+  dim3 grid((N + 31) / 32, (M + kRowsPerChunk - 1) / kRowsPerChunk), block(32, 8);
+  if (x_dtype == CMMVAE_F32)
+    colsum_kernel<float><<<grid, block, 0, st>>>((const float*)X, M, N, ldx, out);
+  else
+    colsum_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)X, M, N, ldx, out);
+  return check_launch("colsum");
+}
+
+extern "C" int cmmvae_reparam_kl_fwd(const float* ML, const float* eps, int B, int Z, float var_eps, float* z_f32,
+                                     void* z_bf16, double* sums, void* stream) {
+  CMMVAE_REQUIRE(B > 0 && Z > 0 && sums, "reparam_kl_fwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(sums, 0, sizeof(double) * 3, st);
+  const long long n = (long long)B * Z;
+  long long want = (n + 255) / 256; int blocks = (int)(want < 148 * 4 ? want : 148 * 4);
+  reparam_kl_fwd_kernel<<<blocks, 256, 0, st>>>(ML, eps, B, Z, var_eps, z_f32, (__nv_bfloat16*)z_bf16, sums);
+  return check_launch("reparam_kl_fwd");
+}
+
+extern "C" int cmmvae_reparam_kl_bwd(const float* ML, const float* eps, const float* dz, int B, int Z,
+                                     float var_eps, float kl_scale, float* dML, void* dML_bf16, void* stream) {
+  CMMVAE_REQUIRE(B > 0 && Z > 0, "reparam_kl_bwd: bad shape");
+  const long long n = (long long)B * Z;
+  reparam_kl_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(ML, eps, dz, B, Z, var_eps, kl_scale, dML,
+                                                                         (__nv_bfloat16*)dML_bf16);
+  return check_launch("reparam_kl_bwd");
+}
+
+extern "C" int cmmvae_softmax_ce_sum(const float* logits, int ldl, int B, int C, const long long* labels,
+                                     float scale, float* dlogits, int ldd, double* loss_sum, void* stream) {
+  CMMVAE_REQUIRE(B > 0 && C > 0 && ldl >= C, "softmax_ce_sum: bad shape");
+  softmax_ce_kernel<<<(B * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(logits, ldl, B, C, labels, scale,
+                                                                             dlogits, ldd, loss_sum);
+  return check_launch("softmax_ce_sum");
+}
+
+extern "C" int cmmvae_gemm_f32(const float* A, int lda, int transA, const float* Bm, int ldb, int transB, int M,
+                               int N, int K, const float* bias, int relu, int accumulate, float* C_f32,
+                               void* C_bf16, int ldc, void* stream) {
+  CMMVAE_REQUIRE(M > 0 && N > 0 && K > 0 && ldc >= N, "gemm_f32: bad shape M=%d N=%d K=%d", M, N, K);
+  CMMVAE_REQUIRE(C_f32 || C_bf16, "gemm_f32: no output");
+  CMMVAE_REQUIRE(!accumulate || C_f32, "gemm_f32: accumulate needs C_f32");
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  gemm_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, lda, transA, Bm, ldb, transB, M, N, K, bias, relu,
+                                                          accumulate, C_f32, (__nv_bfloat16*)C_bf16, ldc);
+  return check_launch("gemm_f32");
+}
+
+extern "C" int cmmvae_sumsq(const float* g, long long n, double* norm_sq, void* stream) {
+  CMMVAE_REQUIRE(n >= 0 && norm_sq, "sumsq: bad arguments");
+  CMMVAE_REQUIRE(((uintptr_t)g & 15) == 0, "sumsq: g must be 16-byte aligned");
+  if (n == 0) return 0;
+  long long want = (n / 4 + 255) / 256 + 1; int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
+  sumsq_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, n, norm_sq);
+  return check_launch("sumsq");
+}
+
+extern "C" int cmmvae_clip_adam(float* p, const float* g, float* m, float* v, void* p_bf16, long long n,
+                                const double* norm_sq, float max_norm, float grad_scale, float lr, float beta1,
+                                float beta2, float eps, float wd, float bc1, float bc2, void* stream) {
+  CMMVAE_REQUIRE(n >= 0, "clip_adam: bad n");
+  CMMVAE_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0,
+                 "clip_adam: buffers must be 16-byte aligned");
+  CMMVAE_REQUIRE(!p_bf16 || ((uintptr_t)p_bf16 & 7) == 0, "clip_adam: bf16 shadow must be 8-byte aligned");
+  if (n == 0) return 0;
+  long long want = (n / 4 + 255) / 256 + 1; int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
+  clip_adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, n, norm_sq,
+                                                             max_norm, grad_scale, lr, beta1, beta2, eps, wd, bc1,
+                                                             bc2);
+  return check_launch("clip_adam");
+}
+
+extern "C" int cmmvae_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {
+  if (n <= 0) return 0;
+  cast_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+  return check_launch("cast_f32_bf16");
+}
+
+extern "C" int cmmvae_transpose(const void* src, void* dst, int dtype, int R, int C, int lds, int ldd,
+                                void* stream) {
+  CMMVAE_REQUIRE(R > 0 && C > 0 && lds >= C && ldd >= R, "transpose: bad shape");
+  dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+  if (dtype == CMMVAE_F32)
+    transpose_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const float*)src, (float*)dst, R, C, lds, ldd);
+  else
+    transpose_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, R, C, lds, ldd);
+  return check_launch("transpose");
+}
+
+extern "C" int cmmvae_axpy(float* a, const float* b, float alpha, long long n, void* stream) {
+  if (n <= 0) return 0;
+  axpy_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(a, b, alpha, n);
+  return check_launch("axpy");
+}

@@ -1,0 +1,296 @@
+// tcgen05 / TMEM / TMA GEMM for the dense layers of the CMMVAE step (K4, K12) on sm_100a.
+//
+//   C[M,N] = act( opA(A) * opB(B) + bias ) (+ C)        bf16 operands, fp32 accumulation in TMEM
+//
+// One CTA computes one 128 x BN output tile.  Warp roles (192 threads):
+//   warp 0      TMA producer: streams 128x64 (A) and BNx64 (B) bf16 tiles, 128B-swizzled, through a
+//               kStages-deep shared-memory ring guarded by full/empty mbarriers
+//   warp 1      allocates TMEM, then one elected lane issues tcgen05.mma (UMMA 128 x BN x 16) and
+//               releases ring slots with tcgen05.commit
+//   warps 2..5  epilogue: tcgen05.ld the accumulator (lane = output row), bias / ReLU / accumulate,
+//               vectorised stores of f32 and/or bf16
+// Operands may be K-major ("row = M or N index, K contiguous") or MN-major (stored transposed):
+// both are native UMMA layouts, so backward GEMMs (dX = dY W, dW = dY^T X) need no transposed copies.
+#include "tc.cuh"
+
+namespace cmmvae {
+
+using namespace tc;
+
+constexpr int BM = 128;   // UMMA M (cta_group::1)
+constexpr int BK = 64;    // 64 bf16 = 128 bytes = one swizzle span
+constexpr int kGemmThreads = 192;
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN <= 128) ? 6 : 4;
+  static constexpr int kBarrierBytes = 1024;
+  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024 /*alignment slack*/;
+};
+
+struct GemmParams {
+  int M, N, K;
+  const float* bias;
+  int relu, accumulate;
+  float* C32;
+  __nv_bfloat16* C16;
+  int ldc;
+  int vec_ok;  // 16-byte aligned rows for both outputs
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmParams p) {
+  using S = GemmSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
+  uint64_t* empty_bar = full_bar + S::kStages;
+  uint64_t* tmem_full_bar = empty_bar + S::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < S::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sA = smem + stage * S::kStageBytes;
+        uint8_t* sB = sA + S::kABytes;
+        mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+        const int k0 = kb * BK;
+        if (!A_MN) {
+          tma_load_2d(sA, &tmA, &full_bar[stage], k0, m0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[stage], m0 + 64 * j, k0);
+        }
+        if (!B_MN) {
+          tma_load_2d(sB, &tmB, &full_bar[stage], k0, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[stage], n0 + 64 * j, k0);
+        }
+        if (++stage == S::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + stage * S::kStageBytes);
+        const uint32_t sB = sA + S::kABytes;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // K-major: 8-row groups 1024 B apart, +32 B per 16-element K step inside the swizzle span.
+          // MN-major: 64-element MN groups BK*128 B apart (LBO), 8 K-rows = 1024 B (SBO), +2048 B per K step.
+          const uint64_t da = A_MN ? make_desc_sw128(sA + k * 2048, BK * 128, 1024)
+                                   : make_desc_sw128(sA + k * 32, 16, 1024);
+          const uint64_t db = B_MN ? make_desc_sw128(sB + k * 2048, BK * 128, 1024)
+                                   : make_desc_sw128(sB + k * 32, 16, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (kb | k) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == S::kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ===== epilogue (warps 2..5; TMEM lane group = warp % 4) =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int gm = m0 + row;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+      tmem_ld_wait();
+      const int gn0 = n0 + c * 32;
+      if (gm < p.M && gn0 < p.N) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const bool full = (gn0 + 32 <= p.N) && p.vec_ok;
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (gn0 + j < p.N) v[j] += __ldg(p.bias + gn0 + j);
+        }
+        const size_t o = (size_t)gm * p.ldc + gn0;
+        if (full) {
+          if (p.accumulate) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t = *reinterpret_cast<const float4*>(p.C32 + o + j);
+              v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (p.C32) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(p.C32 + o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+          if (p.C16) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 t;
+              t.x = pack_bf16(v[j], v[j + 1]); t.y = pack_bf16(v[j + 2], v[j + 3]);
+              t.z = pack_bf16(v[j + 4], v[j + 5]); t.w = pack_bf16(v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(p.C16 + o + j) = t;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (gn0 + j < p.N) {
+              float x = v[j];
+              if (p.accumulate) x += p.C32[o + j];
+              if (p.relu) x = fmaxf(x, 0.f);
+              if (p.C32) p.C32[o + j] = x;
+              if (p.C16) p.C16[o + j] = __float2bfloat16(x);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<BN>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of pitch `ld` elements
+int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                   uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return -3;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): base=%p inner=%llu outer=%llu ld=%llu box=%ux%u", (int)r, base,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer);
+    return -3;
+  }
+  return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+  using S = GemmSmem<BN>;
+  auto kern = gemm_bf16_tc_kernel<BN, A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    if (e != cudaSuccess) {
+      set_error("gemm_bf16_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return -2;
+    }
+    configured = true;
+  }
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM);
+  kern<<<grid, kGemmThreads, S::kTotal, st>>>(tmA, tmB, p);
+  return check_launch("gemm_bf16_tc");
+}
+
+template <int BN>
+static int dispatch_major(int transA, int transB, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                          const GemmParams& p, cudaStream_t st) {
+  if (!transA && !transB) return launch_gemm<BN, false, false>(tmA, tmB, p, st);
+  if (!transA && transB) return launch_gemm<BN, false, true>(tmA, tmB, p, st);
+  if (transA && !transB) return launch_gemm<BN, true, false>(tmA, tmB, p, st);
+  return launch_gemm<BN, true, true>(tmA, tmB, p, st);
+}
+
+}  // namespace cmmvae
+
+using namespace cmmvae;
+
+extern "C" int cmmvae_gemm_bf16_tc(const void* A, int lda, int transA, const void* Bm, int ldb, int transB, int M,
+                                   int N, int K, const float* bias, int relu, int accumulate, float* C_f32,
+                                   void* C_bf16, int ldc, void* stream) {
+  CMMVAE_REQUIRE(M > 0 && N > 0 && K > 0 && ldc >= N, "gemm_bf16_tc: bad shape M=%d N=%d K=%d ldc=%d", M, N, K, ldc);
+  CMMVAE_REQUIRE(C_f32 || C_bf16, "gemm_bf16_tc: no output");
+  CMMVAE_REQUIRE(!accumulate || C_f32, "gemm_bf16_tc: accumulate needs C_f32");
+  CMMVAE_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)Bm & 15) == 0, "gemm_bf16_tc: operands must be 16-byte aligned");
+  CMMVAE_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm_bf16_tc: lda/ldb must be multiples of 8 (got %d, %d)", lda, ldb);
+  const int BN = (N > 128 && (long long)((M + 127) / 128) * ((N + 255) / 256) >= 148) ? 256 : 128;
+  CUtensorMap tmA, tmB;
+  int rc;
+  // K-major: inner = K, rows = M (or N).  MN-major: inner = M (or N), rows = K, box 64 x 64.
+  if (!transA) rc = make_tmap_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM);
+  else rc = make_tmap_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
+  if (rc) return rc;
+  if (!transB) rc = make_tmap_bf16(&tmB, Bm, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN);
+  else rc = make_tmap_bf16(&tmB, Bm, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
+  if (rc) return rc;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.bias = bias; p.relu = relu; p.accumulate = accumulate;
+  p.C32 = C_f32; p.C16 = (__nv_bfloat16*)C_bf16; p.ldc = ldc;
+  p.vec_ok = (ldc % 8 == 0) && (!C_f32 || ((uintptr_t)C_f32 & 15) == 0) && (!C_bf16 || ((uintptr_t)C_bf16 & 15) == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (BN == 256) return dispatch_major<256>(transA, transB, tmA, tmB, p, st);
+  return dispatch_major<128>(transA, transB, tmA, tmB, p, st);
+}

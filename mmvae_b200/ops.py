@@ -1,0 +1,221 @@
+"""Thin torch-facing wrappers over the C ABI (include/cmmvae_b200.h).
+
+Every function takes CUDA tensors, passes raw device pointers + sizes + the current CUDA stream to
+libcmmvae_b200.so through ctypes and returns tensors.  torch is used for device memory and
+streams only.  CPU tensors are rejected: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+F32, BF16 = 0, 1
+_c = ctypes
+
+
+def lib():
+    return _lib.load()
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"cmmvae_b200.{what} failed ({rc}): {lib().cmmvae_last_error().decode()}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None:
+        return _c.c_void_p(0)
+    if not t.is_cuda:
+        raise RuntimeError("cmmvae_b200 kernels need CUDA tensors (no CPU fallback)")
+    return _c.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return _c.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def launch_count() -> int:
+    return int(lib().cmmvae_launch_count())
+
+
+# ------------------------------------------------------------------------------------------ sparse
+def csr_linear_fwd(crow, col, val, G: int, Wt, bias, out=None):
+    """Y = X_csr @ Wt + bias;  Wt is [G,H] (f32|bf16), contiguous."""
+    B = crow.numel() - 1
+    H = Wt.shape[1]
+    assert Wt.shape[0] == G and Wt.is_contiguous()
+    assert crow.dtype == torch.int32 and col.dtype == torch.int32 and val.dtype == torch.float32
+    if out is None:
+        out = torch.empty(B, H, device=Wt.device, dtype=torch.float32)
+    _check(lib().cmmvae_csr_linear_fwd(_ptr(crow), _ptr(col), _ptr(val), B, G, H, _ptr(Wt), _dt(Wt), _ptr(bias),
+                                       _ptr(out), _stream()), "csr_linear_fwd")
+    return out
+
+
+def csr_transpose(crow, col, val, G: int, nnz: int, cptr=None, ridx=None, cval=None, cursor=None):
+    B = crow.numel() - 1
+    dev = crow.device
+    if cptr is None:
+        cptr = torch.empty(G + 1, device=dev, dtype=torch.int32)
+    if cursor is None:
+        cursor = torch.empty(G + 1, device=dev, dtype=torch.int32)
+    if ridx is None:
+        ridx = torch.empty(max(nnz, 1), device=dev, dtype=torch.int32)
+    if cval is None:
+        cval = torch.empty(max(nnz, 1), device=dev, dtype=torch.float32)
+    _check(lib().cmmvae_csr_transpose(_ptr(crow), _ptr(col), _ptr(val), B, G, _c.c_longlong(nnz), _ptr(cptr),
+                                      _ptr(ridx), _ptr(cval), _ptr(cursor), _stream()), "csr_transpose")
+    return cptr, ridx, cval
+
+
+def csr_linear_bwd_w(cptr, ridx, cval, B: int, G: int, dY, out):
+    H = dY.shape[1]
+    assert dY.dtype == torch.float32 and dY.is_contiguous() and out.is_contiguous() and out.shape == (G, H)
+    _check(lib().cmmvae_csr_linear_bwd_w(_ptr(cptr), _ptr(ridx), _ptr(cval), B, G, H, _ptr(dY), _ptr(out),
+                                         _stream()), "csr_linear_bwd_w")
+    return out
+
+
+def mse_relu_csr(logits, G: int, crow, col, val, write_xhat: bool, dl32, dl16, loss_sum):
+    B = logits.shape[0]
+    ldd = (dl32 if dl32 is not None else dl16).stride(0) if (dl32 is not None or dl16 is not None) else 0
+    _check(lib().cmmvae_mse_relu_csr(_ptr(logits), logits.stride(0), B, G, _ptr(crow), _ptr(col), _ptr(val),
+                                     int(write_xhat), _ptr(dl32), _ptr(dl16), ldd, _ptr(loss_sum), _stream()),
+           "mse_relu_csr")
+
+
+def decoder_mse_fused_workspace_bytes(B: int, G: int) -> int:
+    fn = lib().cmmvae_decoder_mse_fused_workspace_bytes
+    fn.restype = _c.c_size_t
+    return int(fn(B, G))
+
+
+def decoder_mse_fused(h16, Wout16, bout, G: int, crow, col, val, dl16, loss_sum, workspace=None):
+    B, H = h16.shape
+    if workspace is None:
+        workspace = torch.empty(decoder_mse_fused_workspace_bytes(B, G), dtype=torch.uint8, device=h16.device)
+    _check(lib().cmmvae_decoder_mse_fused(_ptr(h16), h16.stride(0), _ptr(Wout16), Wout16.stride(0), _ptr(bout), B, G,
+                                          H, _ptr(crow), _ptr(col), _ptr(val), _ptr(dl16), dl16.stride(0),
+                                          _ptr(loss_sum), _ptr(workspace), _stream()), "decoder_mse_fused")
+
+
+# -------------------------------------------------------------------------------- BN / act / drop
+def bn_stats(Y, eps, momentum, mean, rstd, running_mean, running_var, scratch):
+    B, H = Y.shape
+    _check(lib().cmmvae_bn_stats(_ptr(Y), B, H, _c.c_float(eps), _c.c_float(momentum), _ptr(mean), _ptr(rstd),
+                                 _ptr(running_mean), _ptr(running_var), _ptr(scratch), _stream()), "bn_stats")
+
+
+def rstd_from_var(var, eps, rstd):
+    _check(lib().cmmvae_rstd_from_var(_ptr(var), var.numel(), _c.c_float(eps), _ptr(rstd), _stream()),
+           "rstd_from_var")
+
+
+def bn_act_drop_fwd(Y, mean, rstd, gamma, beta, relu, p_drop, seed, mask, out32, out16):
+    B, H = Y.shape
+    _check(lib().cmmvae_bn_act_drop_fwd(_ptr(Y), B, H, _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta), int(relu),
+                                        _c.c_float(p_drop), _c.c_ulonglong(seed), _ptr(mask), _ptr(out32),
+                                        _ptr(out16), _stream()), "bn_act_drop_fwd")
+
+
+def bn_act_drop_bwd(dOut, Y, out, mean, rstd, gamma, relu, p_drop, seed, mask, dY, dY16, dgamma, dbeta, dbias):
+    B, H = dOut.shape
+    _check(lib().cmmvae_bn_act_drop_bwd(_ptr(dOut), _ptr(Y), _ptr(out), B, H, _ptr(mean), _ptr(rstd), _ptr(gamma),
+                                        int(relu), _c.c_float(p_drop), _c.c_ulonglong(seed), _ptr(mask), _ptr(dY),
+                                        _ptr(dY16), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), _stream()),
+           "bn_act_drop_bwd")
+
+
+# ------------------------------------------------------------------------------------------ GEMMs
+def _ld(t):
+    assert t.dim() == 2 and t.stride(1) == 1
+    return t.stride(0)
+
+
+def gemm(A, transA, Bm, transB, M, N, K, bias=None, relu=False, accumulate=False, C32=None, C16=None,
+         use_tc: Optional[bool] = None):
+    """C[M,N] = act(opA(A) opB(B) + bias) (+C).  A: [M,K] or (transA) [K,M]; B: [N,K] or (transB) [K,N]."""
+    C = C32 if C32 is not None else C16
+    ldc = _ld(C)
+    if C32 is not None and C16 is not None:
+        assert _ld(C32) == _ld(C16)
+    tc = (A.dtype == torch.bfloat16) if use_tc is None else use_tc
+    if tc:
+        assert A.dtype == torch.bfloat16 and Bm.dtype == torch.bfloat16
+        fn, name = lib().cmmvae_gemm_bf16_tc, "gemm_bf16_tc"
+    else:
+        assert A.dtype == torch.float32 and Bm.dtype == torch.float32
+        fn, name = lib().cmmvae_gemm_f32, "gemm_f32"
+    _check(fn(_ptr(A), _ld(A), int(transA), _ptr(Bm), _ld(Bm), int(transB), M, N, K, _ptr(bias), int(relu),
+              int(accumulate), _ptr(C32), _ptr(C16), ldc, _stream()), name)
+    return C
+
+
+def colsum(X, out, accumulate=False, M=None, N=None):
+    M = X.shape[0] if M is None else M
+    N = X.shape[1] if N is None else N
+    _check(lib().cmmvae_colsum(_ptr(X), _dt(X), M, N, _ld(X), _ptr(out), int(accumulate), _stream()), "colsum")
+    return out
+
+
+# --------------------------------------------------------------------------------- latent / losses
+def reparam_kl_fwd(ML, eps, Z, var_eps, z32, z16, sums):
+    B = ML.shape[0]
+    _check(lib().cmmvae_reparam_kl_fwd(_ptr(ML), _ptr(eps), B, Z, _c.c_float(var_eps), _ptr(z32), _ptr(z16),
+                                       _ptr(sums), _stream()), "reparam_kl_fwd")
+
+
+def reparam_kl_bwd(ML, eps, dz, Z, var_eps, kl_scale, dML, dML16):
+    B = ML.shape[0]
+    _check(lib().cmmvae_reparam_kl_bwd(_ptr(ML), _ptr(eps), _ptr(dz), B, Z, _c.c_float(var_eps),
+                                       _c.c_float(kl_scale), _ptr(dML), _ptr(dML16), _stream()), "reparam_kl_bwd")
+
+
+def softmax_ce_sum(logits, C, labels, scale, dlogits, loss_sum):
+    B = logits.shape[0]
+    assert labels.dtype == torch.int64
+    _check(lib().cmmvae_softmax_ce_sum(_ptr(logits), _ld(logits), B, C, _ptr(labels), _c.c_float(scale),
+                                       _ptr(dlogits), _ld(dlogits) if dlogits is not None else 0, _ptr(loss_sum),
+                                       _stream()), "softmax_ce_sum")
+
+
+# --------------------------------------------------------------------------------------- optimiser
+def sumsq(g, norm_sq):
+    _check(lib().cmmvae_sumsq(_ptr(g), _c.c_longlong(g.numel()), _ptr(norm_sq), _stream()), "sumsq")
+
+
+def clip_adam(p, g, m, v, p16, norm_sq, max_norm, grad_scale, lr, beta1, beta2, eps, wd, step):
+    bc1 = 1.0 - beta1 ** step
+    bc2 = 1.0 - beta2 ** step
+    _check(lib().cmmvae_clip_adam(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p16), _c.c_longlong(p.numel()),
+                                  _ptr(norm_sq), _c.c_float(max_norm if max_norm else 0.0), _c.c_float(grad_scale),
+                                  _c.c_float(lr), _c.c_float(beta1), _c.c_float(beta2), _c.c_float(eps),
+                                  _c.c_float(wd), _c.c_float(bc1), _c.c_float(bc2), _stream()), "clip_adam")
+
+
+# --------------------------------------------------------------------------------------- utilities
+def cast_bf16(src, dst):
+    _check(lib().cmmvae_cast_f32_bf16(_ptr(src), _ptr(dst), _c.c_longlong(src.numel()), _stream()), "cast_f32_bf16")
+    return dst
+
+
+def transpose(src, dst):
+    R, C = src.shape
+    _check(lib().cmmvae_transpose(_ptr(src), _ptr(dst), _dt(src), R, C, _ld(src), _ld(dst), _stream()), "transpose")
+    return dst
+
+
+def axpy(a, b, alpha):
+    _check(lib().cmmvae_axpy(_ptr(a), _ptr(b), _c.c_float(alpha), _c.c_longlong(a.numel()), _stream()), "axpy")

@@ -1,0 +1,309 @@
+"""Kernel-level parity: every C-ABI op against the oracle's restatement (or plain fp32 math) on the
+same seeded inputs.  GPU only; calls go through the C ABI (ctypes)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cmmvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from mmvae_b200 import ops as _ops
+    _ops.lib()
+    return _ops
+
+
+def dev(x):
+    return torch.as_tensor(x).cuda()
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("B,G,H,density", [(16, 200, 64, 0.1), (33, 1000, 1024, 0.05), (8, 300, 50, 0.2)])
+@pytest.mark.parametrize("wdtype", [torch.float32, torch.bfloat16])
+def test_csr_linear_fwd(ops, B, G, H, density, wdtype):
+    crow, col, val = O.synth_csr(B, G, density, seed=1)
+    g = torch.Generator().manual_seed(0)
+    W = torch.randn(H, G, generator=g) * 0.05
+    b = torch.randn(H, generator=g) * 0.1
+    Wt = W.t().contiguous().to(wdtype)
+    ref = O.csr_linear(crow, col, val, Wt.float().t(), b)
+    y = ops.csr_linear_fwd(dev(crow), dev(col), dev(val), G, Wt.cuda(), b.cuda())
+    assert rel(y, ref) < 2e-6
+
+
+def test_csr_linear_empty_rows(ops):
+    crow = np.array([0, 0, 3, 3, 5], dtype=np.int32)
+    col = np.array([1, 4, 7, 0, 9], dtype=np.int32)
+    val = np.array([1, 2, 3, 4, 5], dtype=np.float32)
+    W = torch.randn(8, 10)
+    b = torch.randn(8)
+    ref = O.csr_linear(crow, col, val, W, b)
+    y = ops.csr_linear_fwd(dev(crow), dev(col), dev(val), 10, W.t().contiguous().cuda(), b.cuda())
+    assert torch.allclose(y.cpu(), ref, atol=1e-6)
+
+
+@pytest.mark.parametrize("B,G,H", [(24, 264, 64), (64, 2000, 1024), (5, 77, 10)])
+def test_csr_transpose_and_bwd_w(ops, B, G, H):
+    crow, col, val = O.synth_csr(B, G, 0.1, seed=3)
+    nnz = int(crow[-1])
+    cptr, ridx, cval = ops.csr_transpose(dev(crow), dev(col), dev(val), G, nnz)
+    cptr_c, ridx_c, cval_c = cptr.cpu().numpy(), ridx.cpu().numpy(), cval.cpu().numpy()
+    dense = O.csr_to_dense(crow, col, val, G).numpy()
+    # bit-exact: CSC rebuilt to dense equals CSR rebuilt to dense; column pointers are exact counts
+    assert cptr_c[0] == 0 and cptr_c[-1] == nnz
+    assert np.array_equal(np.diff(cptr_c), (dense != 0).sum(0))
+    rebuilt = np.zeros_like(dense)
+    cols = np.repeat(np.arange(G), np.diff(cptr_c))
+    rebuilt[ridx_c[:nnz], cols] = cval_c[:nnz]
+    assert np.array_equal(rebuilt, dense)
+    dY = torch.randn(B, H, generator=torch.Generator().manual_seed(1))
+    out = torch.full((G, H), 7.0).cuda()
+    ops.csr_linear_bwd_w(cptr, ridx, cval, B, G, dY.cuda(), out)
+    ref = torch.from_numpy(dense).t() @ dY
+    assert rel(out, ref) < 2e-6
+    absent = (dense != 0).sum(0) == 0
+    assert absent.any()
+    assert torch.all(out.cpu()[torch.from_numpy(absent)] == 0)
+
+
+@pytest.mark.parametrize("B,H", [(24, 64), (300, 1000), (1024, 512)])
+@pytest.mark.parametrize("relu,p", [(1, 0.0), (1, 0.25), (0, 0.0)])
+def test_bn_act_drop(ops, B, H, relu, p):
+    g = torch.Generator().manual_seed(5)
+    Y = (torch.randn(B, H, generator=g) * 2 + 3).requires_grad_(True)
+    gamma = (1 + 0.1 * torch.randn(H, generator=g)).requires_grad_(True)
+    beta = (0.1 * torch.randn(H, generator=g)).requires_grad_(True)
+    rm, rv = torch.randn(H, generator=g) * 0.1, torch.rand(H, generator=g) + 0.5
+    mask = (torch.rand(B, H, generator=g) >= p)
+    out, nrm, nrv = O.batch_norm_train(Y, gamma, beta, rm, rv)
+    if relu:
+        out = torch.relu(out)
+    if p > 0:
+        out = out * mask / (1 - p)
+    dOut = torch.randn(B, H, generator=g)
+    out.backward(dOut)
+
+    Yc = Y.detach().cuda()
+    mean, rstd = torch.empty(H).cuda(), torch.empty(H).cuda()
+    rmc, rvc = rm.cuda().clone(), rv.cuda().clone()
+    ops.bn_stats(Yc, 1e-3, 0.01, mean, rstd, rmc, rvc, torch.empty(2 * H, dtype=torch.float64).cuda())
+    assert rel(rmc, nrm) < 1e-6 and rel(rvc, nrv) < 1e-6
+    o32 = torch.empty(B, H).cuda()
+    o16 = torch.empty(B, H, dtype=torch.bfloat16).cuda()
+    m8 = mask.to(torch.uint8).cuda() if p > 0 else None
+    ops.bn_act_drop_fwd(Yc, mean, rstd, gamma.detach().cuda(), beta.detach().cuda(), relu, p, 0, m8, o32, o16)
+    assert rel(o32, out.detach()) < 1e-5
+    assert rel(o16.float(), out.detach()) < 1e-2
+    dY, dg, db, dbias = torch.empty(B, H).cuda(), torch.empty(H).cuda(), torch.empty(H).cuda(), torch.empty(H).cuda()
+    ops.bn_act_drop_bwd(dOut.cuda(), Yc, o32, mean, rstd, gamma.detach().cuda(), relu, p, 0, m8, dY, None, dg, db,
+                        dbias)
+    assert rel(dY, Y.grad) < 2e-4
+    assert rel(dg, gamma.grad) < 1e-4 and rel(db, beta.grad) < 1e-4
+    assert float(dbias.abs().max()) < 1e-2 * float(dY.abs().max()) * B ** 0.5
+
+
+def test_dropout_hash_statistics(ops):
+    B, H, p = 512, 1024, 0.1
+    Y = torch.ones(B, H).cuda()
+    o = torch.empty(B, H).cuda()
+    ops.bn_act_drop_fwd(Y, None, None, None, None, 0, p, 1234, None, o, None)
+    keep = (o > 0).float().mean().item()
+    assert abs(keep - 0.9) < 5e-3
+    assert torch.allclose(o[o > 0], torch.tensor(1 / 0.9).cuda())
+    # backward regenerates the same mask from the seed
+    d = torch.empty(B, H).cuda()
+    ops.bn_act_drop_bwd(torch.ones(B, H).cuda(), None, None, None, None, None, 0, p, 1234, None, d, None, None, None,
+                        None)
+    assert torch.equal(d > 0, o > 0)
+    o2 = torch.empty(B, H).cuda()
+    ops.bn_act_drop_fwd(Y, None, None, None, None, 0, p, 99, None, o2, None)
+    assert not torch.equal(o2 > 0, o > 0)
+
+
+SHAPES = [(128, 128, 64), (24, 64, 264), (300, 200, 96), (1024, 512, 1024), (257, 1000, 520), (64, 16, 32)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_gemm_f32(ops, M, N, K, tA, tB):
+    g = torch.Generator().manual_seed(M + N + K)
+    A, Bm = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+    bias = torch.randn(N, generator=g)
+    ref = torch.relu(A.double() @ Bm.double().t() + bias.double()).float()
+    Ad = (A.t().contiguous() if tA else A).cuda()
+    Bd = (Bm.t().contiguous() if tB else Bm).cuda()
+    C = torch.empty(M, N).cuda()
+    ops.gemm(Ad, tA, Bd, tB, M, N, K, bias=bias.cuda(), relu=True, C32=C)
+    assert rel(C, ref) < 1e-5
+
+
+def _pad8(t):
+    """row-major 2-D bf16 with leading dimension rounded up to 8 elements (TMA pitch rule)"""
+    R, C = t.shape
+    ld = (C + 7) // 8 * 8
+    buf = torch.zeros(R, ld, dtype=t.dtype, device=t.device)
+    buf[:, :C] = t
+    return buf[:, :C]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES + [(1024, 2048, 128), (2048, 8192, 256), (130, 60530, 64)])
+@pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_gemm_bf16_tc(ops, M, N, K, tA, tB):
+    g = torch.Generator().manual_seed(M * 3 + N + K)
+    A = torch.randn(M, K, generator=g).bfloat16()
+    Bm = torch.randn(N, K, generator=g).bfloat16()
+    bias = torch.randn(N, generator=g)
+    ref = (A.cuda().float() @ Bm.cuda().float().t() + bias.cuda())
+    Ad = _pad8((A.t().contiguous() if tA else A).cuda())
+    Bd = _pad8((Bm.t().contiguous() if tB else Bm).cuda())
+    C = _pad8(torch.empty(M, N).cuda())
+    C16 = None
+    ops.gemm(Ad, tA, Bd, tB, M, N, K, bias=bias.cuda(), relu=False, C32=C)
+    assert rel(C, ref) < 2e-5, (tA, tB)
+    # relu + accumulate + bf16 output
+    C2 = _pad8(torch.ones(M, N).cuda())
+    ld = C2.stride(0)
+    C16 = torch.zeros(M, ld, dtype=torch.bfloat16).cuda()[:, :N]
+    ops.gemm(Ad, tA, Bd, tB, M, N, K, bias=bias.cuda(), relu=True, accumulate=True, C32=C2, C16=C16)
+    ref2 = torch.relu(ref + 1.0)
+    assert rel(C2, ref2) < 2e-5
+    assert rel(C16.float(), ref2) < 1e-2
+
+
+def test_reparam_kl(ops):
+    B, Z = 48, 32
+    g = torch.Generator().manual_seed(2)
+    ML = (torch.randn(B, 2 * Z, generator=g) * 0.7).requires_grad_(True)
+    eps = torch.randn(B, Z, generator=g)
+    mu, lv = ML[:, :Z], ML[:, Z:]
+    sigma = torch.sqrt(torch.exp(lv) + 1e-4)
+    z = mu + eps * sigma
+    kl = O.kl_normal_std(mu, sigma)
+    dz = torch.randn(B, Z, generator=g)
+    klw = 0.37
+    (klw * kl + (z * dz).sum()).backward()
+    z32 = torch.empty(B, Z).cuda()
+    z16 = torch.empty(B, Z, dtype=torch.bfloat16).cuda()
+    sums = torch.empty(3, dtype=torch.float64).cuda()
+    ops.reparam_kl_fwd(ML.detach().cuda(), eps.cuda(), Z, 1e-4, z32, z16, sums)
+    assert rel(z32, z.detach()) < 1e-6
+    s = sums.cpu()
+    assert abs(s[0].item() / B - kl.item()) < 1e-5 * abs(kl.item())
+    assert abs(s[1].item() / (B * Z) - mu.mean().item()) < 1e-6
+    assert abs(s[2].item() / (B * Z) - (sigma ** 2).mean().item()) < 1e-5
+    dML = torch.empty(B, 2 * Z).cuda()
+    ops.reparam_kl_bwd(ML.detach().cuda(), eps.cuda(), dz.cuda(), Z, 1e-4, klw / B, dML, None)
+    assert rel(dML, ML.grad) < 1e-5
+
+
+@pytest.mark.parametrize("C", [5, 11, 272, 1000])
+def test_softmax_ce(ops, C):
+    B = 37
+    g = torch.Generator().manual_seed(C)
+    logits = (torch.randn(B, C, generator=g) * 3).requires_grad_(True)
+    labels = torch.randint(0, C, (B,), generator=g)
+    loss = O.cross_entropy_sum(logits, labels)
+    (loss * 2.5).backward()
+    dl = torch.empty(B, C).cuda()
+    ls = torch.zeros(1, dtype=torch.float64).cuda()
+    ops.softmax_ce_sum(logits.detach().cuda(), C, labels.cuda(), 2.5, dl, ls)
+    assert abs(ls.item() - loss.item()) < 1e-5 * abs(loss.item())
+    assert rel(dl, logits.grad) < 1e-5
+
+
+@pytest.mark.parametrize("B,G", [(24, 264), (64, 6053)])
+def test_mse_relu_csr(ops, B, G):
+    crow, col, val = O.synth_csr(B, G, 0.08, seed=9)
+    x = O.csr_to_dense(crow, col, val, G)
+    logits = (torch.randn(B, G, generator=torch.Generator().manual_seed(4)) * 2).requires_grad_(True)
+    loss = ((torch.relu(logits) - x) ** 2).sum()
+    loss.backward()
+    ld = (G + 63) // 64 * 64
+    lg = logits.detach().cuda().clone()
+    dl32 = torch.zeros(B, G).cuda()
+    dl16 = torch.zeros(B, ld, dtype=torch.bfloat16).cuda()
+    ls = torch.empty(1, dtype=torch.float64).cuda()
+    ops.mse_relu_csr(lg, G, dev(crow), dev(col), dev(val), True, dl32, None, ls)
+    assert abs(ls.item() - loss.item()) < 1e-5 * loss.item()
+    assert rel(dl32, logits.grad) < 1e-6
+    assert torch.equal(lg.cpu(), torch.relu(logits.detach()))
+    lg2 = logits.detach().cuda().clone()
+    ops.mse_relu_csr(lg2, G, dev(crow), dev(col), dev(val), False, None, dl16, ls)
+    assert rel(dl16[:, :G].float(), logits.grad) < 1e-2
+    assert torch.all(dl16[:, G:] == 0)
+
+
+def test_sumsq_and_clip_adam(ops):
+    n = 100003
+    g_ = torch.Generator().manual_seed(8)
+    p, g = torch.randn(n, generator=g_), torch.randn(n, generator=g_) * 3
+    m, v = torch.randn(n, generator=g_) * 0.1, torch.rand(n, generator=g_) * 0.1
+    nb = (n + 3) // 4 * 4
+
+    def padded(t):
+        b = torch.zeros(nb)
+        b[:n] = t
+        return b.cuda()
+
+    pc, gc, mc, vc = padded(p), padded(g), padded(m), padded(v)
+    ns = torch.zeros(1, dtype=torch.float64).cuda()
+    ops.sumsq(gc[:n], ns)
+    assert abs(ns.item() ** 0.5 - g.double().norm().item()) < 1e-9 * g.double().norm().item() + 1e-9
+    gl, total = O.clip_by_norm([g], 10.0)
+    rp, rm_, rv_ = O.adam_update(p, gl[0], m, v, 3, 5e-3, 1e-6, (0.9, 0.999), 1e-8)
+    p16 = torch.zeros(nb, dtype=torch.bfloat16).cuda()
+    ops.clip_adam(pc[:n], gc[:n], mc[:n], vc[:n], p16[:n], ns, 10.0, 1.0, 5e-3, 0.9, 0.999, 1e-8, 1e-6, 3)
+    assert rel(pc[:n], rp) < 1e-6 and rel(mc[:n], rm_) < 1e-6 and rel(vc[:n], rv_) < 1e-6
+    assert torch.equal(p16[:n].cpu(), pc[:n].cpu().bfloat16())
+
+
+def test_transpose_cast_axpy(ops):
+    a = torch.randn(70, 130).cuda()
+    t = torch.empty(130, 70).cuda()
+    ops.transpose(a, t)
+    assert torch.equal(t, a.t().contiguous())
+    b16 = torch.empty(70, 130, dtype=torch.bfloat16).cuda()
+    ops.cast_bf16(a, b16)
+    assert torch.equal(b16, a.bfloat16())
+    c = torch.randn(70, 130).cuda()
+    ref = a + 0.5 * c
+    ops.axpy(a, c, 0.5)
+    assert torch.allclose(a, ref)
+
+
+def test_cpu_tensor_rejected(ops):
+    with pytest.raises(RuntimeError):
+        ops.cast_bf16(torch.randn(4), torch.empty(4, dtype=torch.bfloat16))
+
+
+@pytest.mark.parametrize("B,G,H,density", [(24, 264, 64, 0.1), (130, 1000, 128, 0.05), (256, 6053, 1024, 0.05),
+                                            (100, 3000, 256, 0.3)])
+def test_decoder_mse_fused(ops, B, G, H, density):
+    """fused tcgen05 GEMM + ReLU + sum-MSE-vs-CSR epilogue against the dense restatement"""
+    crow, col, val = O.synth_csr(B, G, density, seed=11)
+    x = O.csr_to_dense(crow, col, val, G).cuda()
+    g = torch.Generator().manual_seed(6)
+    h = torch.relu(torch.randn(B, H, generator=g)).bfloat16().cuda()
+    W = (torch.randn(G, H, generator=g) * (2.0 / H) ** 0.5).bfloat16().cuda()
+    bout = (torch.randn(G, generator=g) * 0.1).cuda()
+    logits = (h.float() @ W.float().t() + bout).requires_grad_(True)
+    loss = ((torch.relu(logits) - x) ** 2).sum()
+    loss.backward()
+    ldd = (G + 63) // 64 * 64
+    dl16 = torch.full((B, ldd), 3.0, dtype=torch.bfloat16).cuda()
+    ls = torch.empty(1, dtype=torch.float64).cuda()
+    ops.decoder_mse_fused(_pad8(h), _pad8(W), bout, G, dev(crow), dev(col), dev(val), dl16, ls)
+    torch.cuda.synchronize()
+    assert abs(ls.item() - loss.item()) < 2e-5 * loss.item()
+    assert rel(dl16[:, :G].float(), logits.grad) < 6e-3   # bf16 output rounding
+    assert torch.all(dl16[:, G:(G + 7) // 8 * 8] == 0)
+    # exact gene masking: dlogits is exactly 0 wherever logits <= 0 and x == 0
+    dead = (logits.detach() < -1e-3) & (x == 0)
+    assert torch.all(dl16[:, :G][dead] == 0)
