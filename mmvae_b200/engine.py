@@ -1,0 +1,620 @@
+"""Fused CMMVAE training step on the sm_100a kernels (no autograd, no per-parameter host syncs).
+
+``StepEngine`` restates ``CMMVAEModel.training_step`` (reference: src/cmmvae/models/cmmvae_model.py:138-217;
+exact semantics in SURVEY.md Appendix A) as an explicit sequence of C-ABI kernel launches:
+
+  forward   CSR SpMM (K1) -> BN/ReLU/dropout (K2/K3) -> tcgen05 GEMMs (K4) -> fused latent kernel (K8/K9)
+            -> decoder GEMMs -> fused decoder GEMM + ReLU + sum-MSE-vs-CSR epilogue (K5-K7)
+  adversary discriminator pass + clip + Adam, then generator pass through the (folded) GRL (K10/K11)
+  backward  hand-written: dW/dX GEMMs (K12, MN-major operands, no transposed copies), BN/ReLU/dropout
+            backward, CSC gather for the sparse weight gradient (K1b)
+  optimiser one sum-of-squares + one clip+Adam launch per optimizer group over flat buffers (K13-K15),
+            clip coefficient read on the device; bf16 shadows refreshed by the same launch
+  DP        one gradient all-reduce per group over NCCL when torch.distributed is initialised
+
+Parameters of each optimizer group live in one flat fp32 buffer (``FlatGroup``); the nn.Parameters of
+the modules are views into it, so ``state_dict()`` keeps the reference's names and shapes.  The first
+expert-encoder weight is stored physically transposed ([genes, hidden]) for coalesced SpMM row reads
+and exposed as a ``[hidden, genes]`` view.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import layers as L
+from . import ops
+
+
+def _ceil(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+class FlatGroup:
+    """One optimizer group (``experts/<id>``, ``vae`` or ``adversarials/<i>``) as flat buffers."""
+
+    ALIGN = 64
+
+    def __init__(self, name: str, chains: List[List[tuple]], device, lr=5e-3, weight_decay=1e-6,
+                 betas=(0.9, 0.999), eps=1e-8):
+        """``chains``: list of chains; a chain is a list of ``(param, transposed)`` stored back to back
+        (so e.g. mean/var head weights form one contiguous matrix)."""
+        self.name, self.lr, self.wd, self.betas, self.eps = name, lr, weight_decay, betas, eps
+        self.params: List[nn.Parameter] = []
+        self.offset: Dict[int, int] = {}
+        self.transposed: Dict[int, bool] = {}
+        total = 0
+        for chain in chains:
+            total = _ceil(total, self.ALIGN)
+            for p, tr in chain:
+                self.params.append(p)
+                self.offset[id(p)] = total
+                self.transposed[id(p)] = tr
+                total += p.numel()
+        self.n = _ceil(max(total, 4), 4)
+        self.p = torch.zeros(self.n, device=device, dtype=torch.float32)
+        self.g = torch.zeros(self.n, device=device, dtype=torch.float32)
+        self.m = torch.zeros(self.n, device=device, dtype=torch.float32)
+        self.v = torch.zeros(self.n, device=device, dtype=torch.float32)
+        self.p16 = torch.zeros(self.n, device=device, dtype=torch.bfloat16)
+        self.step_count = 0
+        for p in self.params:
+            phys = self.phys(p)
+            src = p.data.to(device)
+            phys.copy_(src.t() if self.transposed[id(p)] else src)
+            p.data = phys.t() if self.transposed[id(p)] else phys
+            gphys = self.phys(p, self.g)
+            p.grad = gphys.t() if self.transposed[id(p)] else gphys
+            L.SHADOWS[id(p)] = self.phys(p, self.p16)
+        self.refresh_shadow()
+
+    def phys(self, p: nn.Parameter, buf: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """physical (row-major, contiguous) view of parameter ``p`` inside ``buf`` (default: values)"""
+        buf = self.p if buf is None else buf
+        o = self.offset[id(p)]
+        shape = tuple(p.shape)
+        if self.transposed[id(p)]:
+            shape = shape[::-1]
+        return buf[o:o + p.numel()].view(shape)
+
+    def refresh_shadow(self):
+        ops.cast_bf16(self.p, self.p16)
+
+    def grad_norm_sq(self, out: torch.Tensor):
+        """out (double[1], pre-zeroed) += ||g||^2 over the whole group (padding is zero)."""
+        ops.sumsq(self.g, out)
+
+    def clip_adam(self, norm_sq: torch.Tensor, max_norm: Optional[float], grad_scale: float = 1.0):
+        self.step_count += 1
+        ops.clip_adam(self.p, self.g, self.m, self.v, self.p16, norm_sq, max_norm or 0.0, grad_scale, self.lr,
+                      self.betas[0], self.betas[1], self.eps, self.wd, self.step_count)
+
+
+class FlatAdam(torch.optim.Optimizer):
+    """``torch.optim.Optimizer`` face of a ``FlatGroup`` (what ``configure_optimizers`` returns, one per
+    reference optimizer: Adam(lr=5e-3, weight_decay=1e-6), cmmvae_model.py:306-319).  ``step`` runs the
+    fused clip+Adam launch; a clip value set through ``set_clip`` is applied inside that launch."""
+
+    def __init__(self, group: FlatGroup):
+        self.flat = group
+        self._max_norm = None
+        super().__init__(group.params, dict(lr=group.lr, weight_decay=group.wd, betas=group.betas, eps=group.eps))
+
+    def set_clip(self, max_norm: Optional[float]):
+        self._max_norm = max_norm
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        ns = torch.zeros(1, dtype=torch.float64, device=self.flat.p.device)
+        self.flat.grad_norm_sq(ns)
+        self.flat.clip_adam(ns, self._max_norm)
+        self._max_norm = None
+
+    def zero_grad(self, set_to_none: bool = True):
+        self.flat.g.zero_()
+
+
+@dataclass
+class LayerPlan:
+    """one lin[/bn][/relu][/dropout] layer bound to its flat-buffer views"""
+    lin: nn.Linear
+    bn: Optional[nn.BatchNorm1d]
+    relu: bool
+    p_drop: float
+    group: FlatGroup
+    sparse: bool = False
+    K: int = 0
+    N: int = 0
+    W32: torch.Tensor = None   # physical: [N,K] dense, [G,H] sparse
+    W16: torch.Tensor = None
+    gW: torch.Tensor = None
+    b: torch.Tensor = None
+    gb: torch.Tensor = None
+    gamma: torch.Tensor = None
+    beta: torch.Tensor = None
+    ggamma: torch.Tensor = None
+    gbeta: torch.Tensor = None
+    return_hidden: bool = False
+
+
+class UnsupportedTopology(NotImplementedError):
+    pass
+
+
+def _plan_block(block, group: FlatGroup, sparse_first=False) -> List[LayerPlan]:
+    plans = []
+    for i, layer in enumerate(block.fc_layers):
+        parts = dict(layer.named_children())
+        if "ln" in parts:
+            raise UnsupportedTopology("LayerNorm layers are outside the fused step")
+        af = parts.get("af")
+        if af is not None and type(af) is not nn.ReLU:
+            raise UnsupportedTopology(f"activation {type(af).__name__} is outside the fused step")
+        lin, bn, dr = parts["lin"], parts.get("bn"), parts.get("dr")
+        lp = LayerPlan(lin=lin, bn=bn, relu=af is not None, p_drop=float(dr.p) if dr is not None else 0.0,
+                       group=group, sparse=(sparse_first and i == 0), K=lin.in_features, N=lin.out_features,
+                       return_hidden=bool(block.config.return_hidden[i]))
+        lp.W32, lp.W16, lp.gW = group.phys(lin.weight), group.phys(lin.weight, group.p16), group.phys(lin.weight, group.g)
+        lp.b, lp.gb = group.phys(lin.bias), group.phys(lin.bias, group.g)
+        if bn is not None:
+            lp.gamma, lp.beta = group.phys(bn.weight), group.phys(bn.bias)
+            lp.ggamma, lp.gbeta = group.phys(bn.weight, group.g), group.phys(bn.bias, group.g)
+        plans.append(lp)
+    return plans
+
+
+def _block_chains(block, sparse_first=False):
+    chains = []
+    for i, layer in enumerate(block.fc_layers):
+        for name, p in layer.named_parameters():
+            chains.append([(p, sparse_first and i == 0 and name == "lin.weight")])
+    return chains
+
+
+@dataclass
+class AdvPlan:
+    enc: List[LayerPlan]
+    conditions: List[str]
+    classes: List[int]
+    Wh32: torch.Tensor = None   # [sumC, K]
+    bh: torch.Tensor = None
+    gWh: torch.Tensor = None
+    gbh: torch.Tensor = None
+    group: FlatGroup = None
+
+
+class StepEngine:
+    def __init__(self, module, adv_weight: float = 1.0, clip: Optional[Dict[str, Optional[float]]] = None,
+                 precision: Optional[str] = None, device=None):
+        self.module = module
+        self.device = torch.device(device or "cuda")
+        if self.device.type != "cuda":
+            raise RuntimeError("StepEngine needs a CUDA device (no CPU fallback)")
+        self.precision = precision or L.get_precision()
+        self.adv_weight = adv_weight
+        self.clip = clip or {"vae": 10.0, "expert": 10.0, "adversarial": 10.0}
+        vae = module.vae
+        if getattr(vae, "conditionals", None):
+            raise UnsupportedTopology("conditional layers are outside the fused step (SURVEY.md 8f-1)")
+        enc = vae.encoder
+        if isinstance(enc.z_transformation, nn.Softmax):
+            raise UnsupportedTopology("distribution='ln' is outside the fused step")
+        module.to(self.device)   # buffers (BN running stats) and not-yet-flattened params
+        dev = self.device
+        # ---- optimizer groups as flat buffers (order mirrors configure_optimizers) ----
+        self.groups: Dict[str, FlatGroup] = {}
+        self.enc_plan: Dict[str, List[LayerPlan]] = {}
+        self.dec_plan: Dict[str, List[LayerPlan]] = {}
+        for eid, expert in module.experts.items():
+            chains = _block_chains(expert.encoder, sparse_first=True) + _block_chains(expert.decoder)
+            g = self.groups[f"experts/{eid}"] = FlatGroup(f"experts/{eid}", chains, dev)
+            self.enc_plan[eid] = _plan_block(expert.encoder, g, sparse_first=True)
+            self.dec_plan[eid] = _plan_block(expert.decoder, g)
+            last = self.dec_plan[eid][-1]
+            if not last.relu or last.bn is not None or last.p_drop > 0:
+                raise UnsupportedTopology("fused decoder loss expects Linear+ReLU as the output layer")
+        chains = _block_chains(enc.fc)
+        chains.append([(enc.mean_encoder.weight, False), (enc.var_encoder.weight, False)])
+        chains.append([(enc.mean_encoder.bias, False), (enc.var_encoder.bias, False)])
+        chains += _block_chains(vae.decoder)
+        listed = {id(p) for c in chains for p, _ in c}
+        extra = [p for p in vae.parameters() if id(p) not in listed]
+        if extra:
+            raise UnsupportedTopology("VAE has parameters outside encoder/decoder")
+        gv = self.groups["vae"] = FlatGroup("vae", chains, dev)
+        self.vaeenc_plan = _plan_block(enc.fc, gv)
+        self.vaedec_plan = _plan_block(vae.decoder, gv)
+        self.Z = enc.mean_encoder.out_features
+        self.Hv = enc.mean_encoder.in_features
+        o = gv.offset[id(enc.mean_encoder.weight)]
+        n = 2 * self.Z * self.Hv
+        self.Wmv32, self.Wmv16, self.gWmv = (b[o:o + n].view(2 * self.Z, self.Hv) for b in (gv.p, gv.p16, gv.g))
+        o = gv.offset[id(enc.mean_encoder.bias)]
+        self.bmv, self.gbmv = gv.p[o:o + 2 * self.Z], gv.g[o:o + 2 * self.Z]
+        self.var_eps = float(enc.var_eps)
+        self.hidden_z = bool(enc.hidden_z)
+        self.n_hidden = sum(1 for lp in self.vaeenc_plan if lp.return_hidden and lp.relu) + int(self.hidden_z)
+        # ---- adversaries ----
+        self.adv: List[AdvPlan] = []
+        for i, adv in enumerate(module.adversarials):
+            conds = list(adv.heads.keys())
+            heads = [adv.heads[c] for c in conds]
+            for h in heads:
+                if len(h.fc_layers) != 1 or len(list(h.fc_layers[0].children())) != 1:
+                    raise UnsupportedTopology("adversary heads must be single Linear layers")
+            chains = _block_chains(adv.encoder)
+            chains.append([(h.fc_layers[0].lin.weight, False) for h in heads])
+            chains.append([(h.fc_layers[0].lin.bias, False) for h in heads])
+            g = self.groups[f"adversarials/{i + 1}"] = FlatGroup(f"adversarials/{i + 1}", chains, dev)
+            ap = AdvPlan(enc=_plan_block(adv.encoder, g), conditions=conds,
+                         classes=[h.fc_layers[0].lin.out_features for h in heads], group=g)
+            K = heads[0].fc_layers[0].lin.in_features
+            sumC = sum(ap.classes)
+            o = g.offset[id(heads[0].fc_layers[0].lin.weight)]
+            ap.Wh32, ap.gWh = g.p[o:o + sumC * K].view(sumC, K), g.g[o:o + sumC * K].view(sumC, K)
+            o = g.offset[id(heads[0].fc_layers[0].lin.bias)]
+            ap.bh, ap.gbh = g.p[o:o + sumC], g.g[o:o + sumC]
+            self.adv.append(ap)
+        self._ws: Dict[tuple, torch.Tensor] = {}
+        self._seed = 0x5EED
+        self.world = 1
+        self.last = None
+
+    # ------------------------------------------------------------------------------------ utilities
+    def ws(self, name: str, shape, dtype=torch.float32, zero=False) -> torch.Tensor:
+        key = (name, tuple(shape), dtype)
+        t = self._ws.get(key)
+        if t is None:
+            t = self._ws[key] = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
+        return t
+
+    def _tc(self, *dims) -> bool:
+        return self.precision == "bf16" and all(d % 8 == 0 for d in dims)
+
+    def _next_seed(self) -> int:
+        self._seed = (self._seed * 6364136223846793005 + 1442695040888963407) & ((1 << 63) - 1)
+        return self._seed
+
+    # ---------------------------------------------------------------------------------- dense layer
+    def _linear(self, tag, lp: LayerPlan, x32, x16, B, fuse_relu):
+        """Y = x W^T + b (optionally ReLU fused in the GEMM epilogue) -> (y32, y16|None)"""
+        y32 = self.ws(tag + ".y32", (B, lp.N))
+        if self._tc(lp.K, lp.N):
+            y16 = self.ws(tag + ".y16", (B, lp.N), torch.bfloat16) if fuse_relu else None
+            ops.gemm(x16, 0, lp.W16, 0, B, lp.N, lp.K, bias=lp.b, relu=fuse_relu, C32=y32, C16=y16)
+            return y32, y16
+        ops.gemm(x32, 0, lp.W32, 0, B, lp.N, lp.K, bias=lp.b, relu=fuse_relu, C32=y32, use_tc=False)
+        return y32, None
+
+    def _layer_fwd(self, tag, lp: LayerPlan, x32, x16, B, csr=None, training=True, masks=None):
+        """full layer; returns (out32, out16, cache)"""
+        want16 = self.precision == "bf16"
+        plain = lp.bn is None and lp.p_drop == 0.0
+        if lp.sparse:
+            crow, col, val, G = csr
+            Wt = lp.W16 if self.precision == "bf16" else lp.W32
+            Y = ops.csr_linear_fwd(crow, col, val, G, Wt, lp.b, out=self.ws(tag + ".y32", (B, lp.N)))
+            y16 = None
+            fused_relu = False
+        else:
+            fused_relu = plain and lp.relu
+            Y, y16 = self._linear(tag, lp, x32, x16, B, fused_relu)
+        cache = dict(x32=x32, x16=x16, Y=Y, mean=None, rstd=None, seed=0, mask=None, p=0.0)
+        if plain and (fused_relu or not lp.relu):
+            out32, out16 = Y, y16
+            if want16 and out16 is None:
+                out16 = ops.cast_bf16(out32, self.ws(tag + ".o16", (B, lp.N), torch.bfloat16))
+        else:
+            mean = rstd = None
+            if lp.bn is not None:
+                mean, rstd = self.ws(tag + ".mean", (lp.N,)), self.ws(tag + ".rstd", (lp.N,))
+                if training:
+                    ops.bn_stats(Y, lp.bn.eps, lp.bn.momentum, mean, rstd, lp.bn.running_mean, lp.bn.running_var,
+                                 self.ws("bn.scratch", (2 * lp.N,), torch.float64))
+                    lp.bn.num_batches_tracked += 1
+                else:
+                    mean = lp.bn.running_mean
+                    ops.rstd_from_var(lp.bn.running_var, lp.bn.eps, rstd)
+            p = lp.p_drop if training else 0.0
+            mask = masks.get(tag) if (masks and p > 0) else None
+            seed = self._next_seed() if (p > 0 and mask is None) else 0
+            out32 = self.ws(tag + ".o32", (B, lp.N))
+            out16 = self.ws(tag + ".o16", (B, lp.N), torch.bfloat16) if want16 else None
+            ops.bn_act_drop_fwd(Y, mean, rstd, lp.gamma if lp.bn is not None else None,
+                                lp.beta if lp.bn is not None else None, lp.relu, p, seed, mask, out32, out16)
+            cache.update(mean=mean, rstd=rstd, seed=seed, mask=mask, p=p)
+        cache.update(out32=out32, out16=out16)
+        return out32, out16, cache
+
+    def _layer_bwd(self, tag, lp: LayerPlan, cache, dOut32, B, need_dx=True, csc=None):
+        """backward of one layer: parameter grads go to the flat grad buffer; returns dX32 (or None)"""
+        want16 = self.precision == "bf16"
+        has_tail = lp.bn is not None or lp.relu or cache["p"] > 0
+        if has_tail:
+            dY = self.ws(tag + ".dY", (B, lp.N))
+            dY16 = self.ws(tag + ".dY16", (B, lp.N), torch.bfloat16) if want16 else None
+            ops.bn_act_drop_bwd(dOut32, cache["Y"], cache["out32"], cache["mean"], cache["rstd"],
+                                lp.gamma if lp.bn is not None else None, lp.relu, cache["p"], cache["seed"],
+                                cache["mask"], dY, dY16, lp.ggamma, lp.gbeta, lp.gb)
+        else:
+            dY = dOut32
+            dY16 = ops.cast_bf16(dY, self.ws(tag + ".dY16", (B, lp.N), torch.bfloat16)) if want16 else None
+            ops.colsum(dY, lp.gb)
+        if lp.sparse:
+            cptr, ridx, cval, G = csc
+            ops.csr_linear_bwd_w(cptr, ridx, cval, B, G, dY, lp.gW)
+            return None
+        dX = self.ws(tag + ".dX", (B, lp.K)) if need_dx else None
+        if self._tc(lp.K, lp.N):
+            ops.gemm(dY16, 1, cache["x16"], 1, lp.N, lp.K, B, C32=lp.gW)
+            if need_dx:
+                ops.gemm(dY16, 0, lp.W16, 1, B, lp.K, lp.N, C32=dX)
+        else:
+            ops.gemm(dY, 1, cache["x32"], 1, lp.N, lp.K, B, C32=lp.gW, use_tc=False)
+            if need_dx:
+                ops.gemm(dY, 0, lp.W32, 1, B, lp.K, lp.N, C32=dX, use_tc=False)
+        return dX
+
+    # ------------------------------------------------------------------------------------ adversary
+    def _adv_fwd(self, tag, ap: AdvPlan, hid32, B):
+        x, caches = hid32, []
+        saved_precision, self.precision = self.precision, "fp32"   # tiny GEMMs: exact CUDA-core path
+        try:
+            for j, lp in enumerate(ap.enc):
+                x, _, c = self._layer_fwd(f"{tag}.e{j}", lp, x, None, B)
+                caches.append(c)
+            sumC = sum(ap.classes)
+            logits = self.ws(tag + ".logits", (B, sumC))
+            ops.gemm(x, 0, ap.Wh32, 0, B, sumC, ap.Wh32.shape[1], bias=ap.bh, C32=logits, use_tc=False)
+        finally:
+            self.precision = saved_precision
+        return x, caches, logits
+
+    def _adv_loss(self, tag, ap: AdvPlan, logits, labels, scale, B, ce_slots):
+        dl = self.ws(tag + ".dlogits", logits.shape)
+        o = 0
+        for c, C, slot in zip(ap.conditions, ap.classes, ce_slots):
+            ops.softmax_ce_sum(logits[:, o:o + C], C, labels[c], scale, dl[:, o:o + C], slot)
+            o += C
+        return dl
+
+    def _adv_bwd(self, tag, ap: AdvPlan, code, caches, dl, B, need_dx):
+        saved_precision, self.precision = self.precision, "fp32"
+        try:
+            sumC, K = ap.Wh32.shape
+            ops.gemm(dl, 1, code, 1, sumC, K, B, C32=ap.gWh, use_tc=False)
+            ops.colsum(dl, ap.gbh)
+            d = self.ws(tag + ".dcode", (B, K))
+            ops.gemm(dl, 0, ap.Wh32, 1, B, K, sumC, C32=d, use_tc=False)
+            for j in reversed(range(len(ap.enc))):
+                d = self._layer_bwd(f"{tag}.e{j}", ap.enc[j], caches[j], d, B, need_dx=(need_dx or j > 0))
+        finally:
+            self.precision = saved_precision
+        return d
+
+    # ----------------------------------------------------------------------------------------- step
+    def _allreduce(self, group: FlatGroup):
+        if self.world > 1:
+            torch.distributed.all_reduce(group.g)
+
+    def train_step(self, expert_id: str, crow, col, val, nnz: int, kl_weight: float, eps=None,
+                   labels: Optional[Dict[str, torch.Tensor]] = None, masks=None):
+        """One optimisation step on a CSR batch already resident on the device.
+        Returns a dict of 0-dim device tensors (no host sync)."""
+        dev = self.device
+        enc, dec = self.enc_plan[expert_id], self.dec_plan[expert_id]
+        B = crow.numel() - 1
+        G = enc[0].K
+        Z = self.Z
+        self.world = torch.distributed.get_world_size() if (
+            torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
+        gscale = 1.0 / self.world
+        bf = self.precision == "bf16"
+        n_adv = min(len(self.adv), self.n_hidden)   # zip(hidden, adversarials) truncates (cmmvae_model.py:67-70)
+        # scalar slots (double): 0 recon | 1..3 kl,sum mu,sum var | then norms | then CE sums
+        n_ce = sum(len(a.conditions) for a in self.adv[:n_adv])
+        sc = torch.zeros(4 + 2 + 2 * n_adv + 2 * n_ce, dtype=torch.float64, device=dev)
+        s_norm = lambda k: sc[4 + k:5 + k]  # noqa: E731   0 vae, 1 expert, 2.. disc_i, then gen_i
+        ce_base = 4 + 2 + 2 * n_adv
+
+        # ---------------- forward ----------------
+        caches = {}
+        x32 = x16 = None
+        for j, lp in enumerate(enc):
+            x32, x16, caches[("enc", j)] = self._layer_fwd(f"enc{j}", lp, x32, x16, B,
+                                                            csr=(crow, col, val, G) if j == 0 else None, masks=masks)
+        hidden = []
+        for j, lp in enumerate(self.vaeenc_plan):
+            x32, x16, caches[("venc", j)] = self._layer_fwd(f"venc{j}", lp, x32, x16, B, masks=masks)
+            if lp.return_hidden and lp.relu:
+                hidden.append(("venc", j, x32))
+        q32, q16 = x32, x16
+        ML = self.ws("ML", (B, 2 * Z))
+        if self._tc(self.Hv, 2 * Z):
+            ops.gemm(q16, 0, self.Wmv16, 0, B, 2 * Z, self.Hv, bias=self.bmv, C32=ML)
+        else:
+            ops.gemm(q32, 0, self.Wmv32, 0, B, 2 * Z, self.Hv, bias=self.bmv, C32=ML, use_tc=False)
+        if eps is None:
+            eps = L.draw_noise(B, Z, dev)
+        z32 = self.ws("z32", (B, Z))
+        z16 = self.ws("z16", (B, Z), torch.bfloat16) if bf else None
+        ops.reparam_kl_fwd(ML, eps, Z, self.var_eps, z32, z16, sc[1:4])
+        if self.hidden_z:
+            hidden.append(("z", 0, z32))
+        x32, x16 = z32, z16
+        for j, lp in enumerate(self.vaedec_plan):
+            x32, x16, caches[("vdec", j)] = self._layer_fwd(f"vdec{j}", lp, x32, x16, B, masks=masks)
+        for j, lp in enumerate(dec[:-1]):
+            x32, x16, caches[("dec", j)] = self._layer_fwd(f"dec{j}", lp, x32, x16, B, masks=masks)
+        h32, h16 = x32, x16
+        out = dec[-1]
+        fused = self._tc(out.K) and bf
+        if fused:
+            ldd = _ceil(G, 64)
+            dl = self.ws("dlogits16", (B, ldd), torch.bfloat16, zero=True)
+            wsb = self.ws("tileptr", (ops.decoder_mse_fused_workspace_bytes(B, G),), torch.uint8)
+            ops.decoder_mse_fused(h16, out.W16, out.b, G, crow, col, val, dl, sc[0:1], wsb)
+        else:
+            logits = self.ws("logits32", (B, G))
+            ops.gemm(h32, 0, out.W32, 0, B, G, out.K, bias=out.b, C32=logits, use_tc=False)
+            dl = self.ws("dlogits32", (B, G))
+            ops.mse_relu_csr(logits, G, crow, col, val, False, dl, None, sc[0:1])
+
+        # ---------------- adversaries: discriminator update, then generator pass ----------------
+        d_hidden = {}
+        slot = ce_base
+        if n_adv:
+            assert labels is not None, "adversaries need labels"
+            for i in range(n_adv):
+                ap = self.adv[i]
+                hid = hidden[i][2]
+                code, ac, logits_a = self._adv_fwd(f"adv{i}", ap, hid, B)
+                slots = [sc[slot + k:slot + k + 1] for k in range(len(ap.conditions))]
+                slot += len(ap.conditions)
+                dla = self._adv_loss(f"adv{i}", ap, logits_a, labels, 1.0, B, slots)
+                self._adv_bwd(f"adv{i}", ap, code, ac, dla, B, need_dx=False)
+                self._allreduce(ap.group)
+                ap.group.grad_norm_sq(s_norm(2 + i))
+                ap.group.clip_adam(s_norm(2 + i), self.clip.get("adversarial"), gscale)
+            for i in range(n_adv):
+                ap = self.adv[i]
+                hid = hidden[i][2]
+                code, ac, logits_a = self._adv_fwd(f"adv{i}", ap, hid, B)
+                slots = [sc[slot + k:slot + k + 1] for k in range(len(ap.conditions))]
+                slot += len(ap.conditions)
+                dla = self._adv_loss(f"adv{i}", ap, logits_a, labels, float(self.adv_weight), B, slots)
+                d_hidden[i] = self._adv_bwd(f"adv{i}", ap, code, ac, dla, B, need_dx=True)
+                ap.group.grad_norm_sq(s_norm(2 + n_adv + i))   # "generator_i" norm: logged, never applied
+
+        # ---------------- backward ----------------
+        gexp, gvae = self.groups[f"experts/{expert_id}"], self.groups["vae"]
+        H1 = out.K
+        dh = self.ws("dh", (B, H1))
+        if fused:
+            ops.gemm(dl, 1, h16, 1, G, H1, B, C32=out.gW)                 # dWout = dlogits^T h
+            ops.colsum(dl, out.gb, M=B, N=G)
+            ops.gemm(dl, 0, out.W16, 1, B, H1, G, C32=dh)                 # dh = dlogits Wout
+        else:
+            ops.gemm(dl, 1, h32, 1, G, H1, B, C32=out.gW, use_tc=False)
+            ops.colsum(dl, out.gb)
+            ops.gemm(dl, 0, out.W32, 1, B, H1, G, C32=dh, use_tc=False)
+        d = dh
+        for j in reversed(range(len(dec) - 1)):
+            d = self._layer_bwd(f"dec{j}", dec[j], caches[("dec", j)], d, B)
+        for j in reversed(range(len(self.vaedec_plan))):
+            d = self._layer_bwd(f"vdec{j}", self.vaedec_plan[j], caches[("vdec", j)], d, B)
+        dz = d
+        for i in range(n_adv):
+            if hidden[i][0] == "z":
+                ops.axpy(dz, d_hidden[i], -1.0)                            # GRL: -alpha * grad, alpha = 1
+        dML = self.ws("dML", (B, 2 * Z))
+        dML16 = self.ws("dML16", (B, 2 * Z), torch.bfloat16) if bf else None
+        ops.reparam_kl_bwd(ML, eps, dz, Z, self.var_eps, float(kl_weight) / B, dML, dML16)
+        dq = self.ws("dq", (B, self.Hv))
+        ops.colsum(dML, self.gbmv)
+        if self._tc(self.Hv, 2 * Z):
+            ops.gemm(dML16, 1, q16, 1, 2 * Z, self.Hv, B, C32=self.gWmv)
+            ops.gemm(dML16, 0, self.Wmv16, 1, B, self.Hv, 2 * Z, C32=dq)
+        else:
+            ops.gemm(dML, 1, q32, 1, 2 * Z, self.Hv, B, C32=self.gWmv, use_tc=False)
+            ops.gemm(dML, 0, self.Wmv32, 1, B, self.Hv, 2 * Z, C32=dq, use_tc=False)
+        d = dq
+        for j in reversed(range(len(self.vaeenc_plan))):
+            for i in range(n_adv):
+                if hidden[i][0] == "venc" and hidden[i][1] == j:
+                    ops.axpy(d, d_hidden[i], -1.0)
+            d = self._layer_bwd(f"venc{j}", self.vaeenc_plan[j], caches[("venc", j)], d, B)
+        cptr, ridx, cval = ops.csr_transpose(crow, col, val, G, nnz, self.ws("cptr", (G + 1,), torch.int32),
+                                             self.ws("ridx", (max(nnz, 1),), torch.int32),
+                                             self.ws("cval", (max(nnz, 1),)), self.ws("cursor", (G + 1,), torch.int32))
+        for j in reversed(range(len(enc))):
+            d = self._layer_bwd(f"enc{j}", enc[j], caches[("enc", j)], d, B, need_dx=(j > 0),
+                                csc=(cptr, ridx, cval, G) if j == 0 else None)
+
+        # ---------------- grad norms, clip, Adam ----------------
+        self._allreduce(gvae)
+        self._allreduce(gexp)
+        gvae.grad_norm_sq(s_norm(0))
+        gexp.grad_norm_sq(s_norm(1))
+        gvae.clip_adam(s_norm(0), self.clip.get("vae"), gscale)
+        gexp.clip_adam(s_norm(1), self.clip.get("expert"), gscale)
+
+        self.last = dict(sc=sc, B=B, Z=Z, kl_weight=float(kl_weight), expert_id=expert_id, n_adv=n_adv,
+                         gscale=gscale, ce_base=ce_base, z=z32, dl=dl)
+        return self.last
+
+    # ---------------------------------------------------------------------------------------- logs
+    def scalars(self, rec=None) -> Dict[str, float]:
+        """Host copy (one sync) of every value the reference logs for the step, untagged keys."""
+        rec = rec or self.last
+        sc = rec["sc"].cpu().tolist()
+        B, Z, n_adv = rec["B"], rec["Z"], rec["n_adv"]
+        out = {"recon_loss": sc[0], "kl_loss": sc[1] / B, "kl_weight": rec["kl_weight"],
+               "Mean": sc[2] / (B * Z), "Variance": sc[3] / (B * Z)}
+        total = out["recon_loss"] + rec["kl_weight"] * out["kl_loss"]
+        out["grad_norms/vae"] = math.sqrt(sc[4]) * rec["gscale"]
+        out[f"grad_norms/expert_{rec['expert_id']}"] = math.sqrt(sc[5]) * rec["gscale"]
+        slot = rec["ce_base"]
+        for tag_i, tag in enumerate(("discriminator", "generator")):
+            for i in range(n_adv):
+                ap = self.adv[i]
+                summed = 0.0
+                for c in ap.conditions:
+                    out[f"{tag}_{i + 1}/adversarial_loss/{c}"] = sc[slot]
+                    summed += sc[slot]
+                    slot += 1
+                out[f"{tag}_{i + 1}/adversarial_loss/summed"] = summed
+                out[f"grad_norms/{tag}_{i + 1}"] = math.sqrt(sc[6 + tag_i * n_adv + i]) * (
+                    rec["gscale"] if tag == "discriminator" else 1.0)
+                if tag == "generator":
+                    total += self.adv_weight * summed
+        out["loss"] = total
+        return out
+
+    # ------------------------------------------------------------------------------- eval forward
+    @torch.no_grad()
+    def eval_step(self, expert_id: str, crow, col, val, eps=None, kl_weight: float = 1.0):
+        """validation_step arithmetic (cmmvae_model.py:219-245): eval-mode forward + ELBO on the fused
+        decoder path.  Returns the scalar record (use ``scalars``-like host read via ``eval_scalars``)."""
+        enc, dec = self.enc_plan[expert_id], self.dec_plan[expert_id]
+        B, G, Z = crow.numel() - 1, enc[0].K, self.Z
+        bf = self.precision == "bf16"
+        sc = torch.zeros(4, dtype=torch.float64, device=self.device)
+        x32 = x16 = None
+        for j, lp in enumerate(enc):
+            x32, x16, _ = self._layer_fwd(f"enc{j}", lp, x32, x16, B, csr=(crow, col, val, G) if j == 0 else None,
+                                          training=False)
+        for j, lp in enumerate(self.vaeenc_plan):
+            x32, x16, _ = self._layer_fwd(f"venc{j}", lp, x32, x16, B, training=False)
+        ML = self.ws("ML", (B, 2 * Z))
+        if self._tc(self.Hv, 2 * Z):
+            ops.gemm(x16, 0, self.Wmv16, 0, B, 2 * Z, self.Hv, bias=self.bmv, C32=ML)
+        else:
+            ops.gemm(x32, 0, self.Wmv32, 0, B, 2 * Z, self.Hv, bias=self.bmv, C32=ML, use_tc=False)
+        if eps is None:
+            eps = L.draw_noise(B, Z, self.device)
+        z32 = self.ws("z32", (B, Z))
+        z16 = self.ws("z16", (B, Z), torch.bfloat16) if bf else None
+        ops.reparam_kl_fwd(ML, eps, Z, self.var_eps, z32, z16, sc[1:4])
+        x32, x16 = z32, z16
+        for j, lp in enumerate(self.vaedec_plan):
+            x32, x16, _ = self._layer_fwd(f"vdec{j}", lp, x32, x16, B, training=False)
+        for j, lp in enumerate(dec[:-1]):
+            x32, x16, _ = self._layer_fwd(f"dec{j}", lp, x32, x16, B, training=False)
+        out = dec[-1]
+        if self._tc(out.K) and bf:
+            dl = self.ws("dlogits16", (B, _ceil(G, 64)), torch.bfloat16, zero=True)
+            wsb = self.ws("tileptr", (ops.decoder_mse_fused_workspace_bytes(B, G),), torch.uint8)
+            ops.decoder_mse_fused(x16, out.W16, out.b, G, crow, col, val, dl, sc[0:1], wsb)
+        else:
+            logits = self.ws("logits32", (B, G))
+            ops.gemm(x32, 0, out.W32, 0, B, G, out.K, bias=out.b, C32=logits, use_tc=False)
+            ops.mse_relu_csr(logits, G, crow, col, val, False, None, None, sc[0:1])
+        s = sc.cpu().tolist()
+        kl = s[1] / B
+        return {"loss": s[0] + kl_weight * kl, "recon_loss": s[0], "kl_loss": kl, "kl_weight": kl_weight,
+                "z": z32}

@@ -1,0 +1,150 @@
+"""``CMMVAEModel``: the LightningModule whose ``training_step`` is the accelerated hot path (mirror of
+``cmmvae.models.cmmvae_model``; reference: src/cmmvae/models/cmmvae_model.py -- ``__init__`` 40-57,
+``training_step`` 138-217, ``validation_step`` 219-248, ``predict_step`` 250-264, ``get_optimizers``
+267-297, ``configure_optimizers`` 299-324, ``convert_to_flat_list_and_map`` 327-351).
+
+Same constructor, same optimizer list / ``optimizer_map``, same logged keys.  ``training_step`` hands
+the CSR batch to ``mmvae_b200.engine.StepEngine`` (one fused sequence of sm_100a kernel launches, no
+autograd graph, no per-parameter host syncs) and logs the reference's keys from one small host read.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import pandas as pd
+import torch
+
+from mmvae_b200 import layers as L
+from mmvae_b200.config import AutogradConfig
+from mmvae_b200.constants import REGISTRY_KEYS as RK
+from mmvae_b200.engine import FlatAdam, StepEngine
+from mmvae_b200.models.base_model import BaseModel
+from mmvae_b200.modules import CMMVAE
+from mmvae_b200.modules.base.components import Adversarial
+
+
+def convert_to_flat_list_and_map(d: dict, flat_list: Optional[list] = None) -> dict:
+    """Flatten a nested dict of values into ``flat_list`` (depth first, insertion order) and return the
+    same nesting with list indices in place of the values."""
+    if flat_list is None:
+        flat_list = []
+    mapping = {}
+    for key, value in d.items():
+        if isinstance(value, dict):
+            mapping[key] = convert_to_flat_list_and_map(value, flat_list)
+        else:
+            mapping[key] = len(flat_list)
+            flat_list.append(value)
+    return mapping
+
+
+class CMMVAEModel(BaseModel):
+    def __init__(self, module: CMMVAE, adv_weight: Optional[float] = None,
+                 autograd_config: Optional[AutogradConfig] = None, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.module = module
+        self.automatic_optimization = False
+        self.adversarial_criterion = torch.nn.CrossEntropyLoss(reduction="sum")
+        self.init_weights()
+        self.adv_weight = adv_weight if adv_weight else 1.0   # 0/None -> 1.0, as in the reference
+        self.autograd_config = autograd_config or AutogradConfig()
+        self._engine: Optional[StepEngine] = None
+        self.sync_logging = True   # read the step's scalars back and log python floats every step
+
+    # ------------------------------------------------------------------------------------ engine
+    @staticmethod
+    def _clip_val(cfg):
+        if not cfg:
+            return None
+        val, algorithm = tuple(cfg)
+        if val is None:
+            return None
+        if algorithm not in (None, "norm"):
+            raise NotImplementedError("only clip-by-norm is implemented in the fused step")
+        return float(val)
+
+    def engine(self) -> StepEngine:
+        if self._engine is None:
+            ac = self.autograd_config
+            clip = {"vae": self._clip_val(ac.vae_gradient_clip), "expert": self._clip_val(ac.expert_gradient_clip),
+                    "adversarial": self._clip_val(ac.adversarial_gradient_clip)}
+            self._engine = StepEngine(self.module, adv_weight=self.adv_weight, clip=clip)
+        return self._engine
+
+    def configure_optimizers(self, optim_cls="Adam"):
+        """``[Adam(expert_0), ..., Adam(vae), Adam(adv_1), ...]`` + ``self.optimizer_map`` with the
+        reference's nesting; each optimizer is the flat-buffer fused Adam of its group."""
+        if optim_cls != "Adam":
+            raise NotImplementedError("the fused optimizer implements torch.optim.Adam semantics only")
+        eng = self.engine()
+        optim_dict = {"experts": {eid: FlatAdam(eng.groups[f"experts/{eid}"]) for eid in self.module.experts.keys()},
+                      "vae": FlatAdam(eng.groups["vae"])}
+        if len(self.module.adversarials):
+            optim_dict["adversarials"] = {i: FlatAdam(eng.groups[f"adversarials/{i}"])
+                                          for i in range(1, len(self.module.adversarials) + 1)}
+        optimizers = []
+        self.optimizer_map = convert_to_flat_list_and_map(optim_dict, optimizers)
+        return optimizers
+
+    def get_optimizers(self, zero_all: bool = False):
+        optimizers = self.optimizers()
+        if zero_all:
+            for opt in optimizers:
+                opt.zero_grad()
+
+        def resolve(node):
+            return {k: resolve(v) for k, v in node.items()} if isinstance(node, dict) else optimizers[node]
+
+        return resolve(self.optimizer_map)
+
+    # ------------------------------------------------------------------------------------- steps
+    def _labels(self, metadata: pd.DataFrame, device):
+        """int64 class ids per condition: row index of each value in the human csv (class-level
+        ``Adversarial.labels``), one H2D copy per condition."""
+        return {c: torch.tensor([table[v] for v in metadata[c].values], dtype=torch.int64).to(device, non_blocking=True)
+                for c, table in Adversarial.labels.items()}
+
+    @staticmethod
+    def _csr(x: torch.Tensor):
+        if x.layout != torch.sparse_csr:
+            raise NotImplementedError(
+                "the fused step consumes torch.sparse_csr batches (reference datapipe default, "
+                "cellxgene_manager.py:44); densified input is outside the hot path")
+        return L.csr_parts(x)
+
+    def training_step(self, batch, batch_idx: int) -> None:
+        x, metadata, expert_id = batch
+        metadata["species"] = expert_id
+        eng = self.engine()
+        crow, col, val, nnz = self._csr(x)
+        labels = self._labels(metadata, x.device) if len(self.module.adversarials) else None
+        rec = eng.train_step(expert_id, crow, col, val, nnz, self.kl_annealing_fn.kl_weight, labels=labels)
+        self.kl_annealing_fn.step()
+        if self.sync_logging:
+            self._log_step(eng.scalars(rec), expert_id)
+
+    def _log_step(self, s: dict, expert_id: str):
+        stage = self.stage_name
+        main = {k: s[k] for k in (RK.LOSS, RK.RECON_LOSS, RK.KL_LOSS, RK.KL_WEIGHT, "Mean", "Variance")}
+        for key, v in s.items():
+            if key.startswith("grad_norms/"):
+                self.log(key, v)
+            elif "/adversarial_loss/" in key:
+                tag, _, cond = key.split("/")
+                self.auto_log({cond: v}, tags=[tag, stage, expert_id, RK.ADV_LOSS], key_pos="last")
+        self.auto_log(main, tags=[stage, expert_id])
+
+    def validation_step(self, batch):
+        x, metadata, expert_id = batch
+        crow, col, val, _ = self._csr(x)
+        out = self.engine().eval_step(expert_id, crow, col, val, kl_weight=self.kl_annealing_fn.kl_weight)
+        loss_dict = {k: out[k] for k in (RK.LOSS, RK.RECON_LOSS, RK.KL_LOSS, RK.KL_WEIGHT)}
+        self.auto_log(loss_dict, tags=[self.stage_name, expert_id])
+        if self.trainer.validating:
+            self.log("val_loss", loss_dict[RK.LOSS], logger=False, on_epoch=True)
+
+    test_step = validation_step
+
+    def predict_step(self, batch, batch_idx: int):
+        x, metadata, species = batch
+        return self.module.get_latent_embeddings(x, metadata, species)

@@ -87,3 +87,49 @@ def rel_l2(a, b):
     b = np.asarray(b, dtype=np.float64)
     den = np.linalg.norm(b)
     return float(np.linalg.norm(a - b) / den) if den > 0 else float(np.linalg.norm(a - b))
+
+
+def build_b200_model(gc: "GoldenCase", tmpdir, kl_fn=None, dropout=0.0):
+    """mmvae_b200 CMMVAEModel with the golden case's topology (constructor calls read like the
+    reference's: same class names and keyword arguments)."""
+    import pandas as pd
+    from mmvae_b200.config import AutogradConfig, GradientClipConfig
+    from mmvae_b200.models import CMMVAEModel
+    from mmvae_b200.modules import CLVAE, CMMVAE
+    from mmvae_b200.modules.base import Adversarial, Expert, Experts, FCBlockConfig, KLAnnealingFn
+
+    d = gc.dims
+    os.makedirs(os.path.join(tmpdir, "human"), exist_ok=True)
+    for cond, n in CONDITIONS.items():
+        pd.DataFrame([f"{cond}_{i}" for i in range(n)]).to_csv(
+            os.path.join(tmpdir, "human", f"unique_expression_{cond}.csv"), header=False, index=False)
+    experts = Experts([
+        Expert(id=s,
+               encoder_config=FCBlockConfig(layers=[gc.genes[s], d["H1"], d["H2"]], dropout_rate=dropout,
+                                            use_batch_norm=True, activation_fn=torch.nn.ReLU),
+               decoder_config=FCBlockConfig(layers=[d["H2"], d["H1"], gc.genes[s]], dropout_rate=0.0,
+                                            activation_fn=torch.nn.ReLU))
+        for s in gc.species_present()])
+    vae = CLVAE(encoder_config=FCBlockConfig(layers=[d["H2"], d["Hv"]], use_batch_norm=True,
+                                             activation_fn=torch.nn.ReLU, return_hidden=True),
+                decoder_config=FCBlockConfig(layers=[d["Z"], d["Hv"], d["H2"]], activation_fn=torch.nn.ReLU),
+                latent_dim=d["Z"], hidden_z=gc.with_adv)
+    advs = []
+    if gc.with_adv:
+        Adversarial.labels.clear()
+        for enc_layers in ([d["Hv"], 24, 16], [d["Z"], 16]):
+            advs.append(Adversarial(encoder=FCBlockConfig(layers=enc_layers, activation_fn=torch.nn.ReLU),
+                                    heads=FCBlockConfig(layers=[16], activation_fn=None),
+                                    conditions=list(CONDITIONS), labels_dir=str(tmpdir)))
+    clip = lambda: GradientClipConfig(val=10, algorithm="norm")  # noqa: E731
+    model = CMMVAEModel(module=CMMVAE(vae=vae, experts=experts, adversarials=advs), adv_weight=gc.adv_weight,
+                        autograd_config=AutogradConfig(adversarial_gradient_clip=clip(), vae_gradient_clip=clip(),
+                                                       expert_gradient_clip=clip()),
+                        kl_annealing_fn=kl_fn or KLAnnealingFn(1.0))
+    return model
+
+
+def csr_batch(crow, col, val, n_genes, device="cuda"):
+    """the reference batch format: torch.sparse_csr (cellxgene_datapipe.py:178-183)"""
+    return torch.sparse_csr_tensor(torch.from_numpy(np.asarray(crow)), torch.from_numpy(np.asarray(col)),
+                                   torch.from_numpy(np.asarray(val)), size=(len(crow) - 1, n_genes)).to(device)
