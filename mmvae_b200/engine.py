@@ -260,6 +260,7 @@ class StepEngine:
             ap.bh, ap.gbh = g.p[o:o + sumC], g.g[o:o + sumC]
             self.adv.append(ap)
         self._ws: Dict[tuple, torch.Tensor] = {}
+        self.timers: Optional[Dict[str, list]] = None   # name -> [(start_event, end_event)] when profiling
         self._seed = 0x5EED
         self.world = 1
         self.last = None
@@ -271,6 +272,24 @@ class StepEngine:
         if t is None:
             t = self._ws[key] = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
         return t
+
+    def _t0(self, name):
+        if self.timers is None:
+            return None
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+        self.timers.setdefault(name, []).append(ev)
+        return ev
+
+    @staticmethod
+    def _t1(ev):
+        if ev is not None:
+            ev[1].record()
+
+    def timer_ms(self, name) -> float:
+        """mean duration (ms) of the events recorded under ``name`` (call after a synchronize)"""
+        evs = (self.timers or {}).get(name, [])
+        return sum(a.elapsed_time(b) for a, b in evs) / max(len(evs), 1)
 
     def _tc(self, *dims) -> bool:
         return self.precision == "bf16" and all(d % 8 == 0 for d in dims)
@@ -297,7 +316,9 @@ class StepEngine:
         if lp.sparse:
             crow, col, val, G = csr
             Wt = lp.W16 if self.precision == "bf16" else lp.W32
+            ev = self._t0("csr_linear_fwd")
             Y = ops.csr_linear_fwd(crow, col, val, G, Wt, lp.b, out=self.ws(tag + ".y32", (B, lp.N)))
+            self._t1(ev)
             y16 = None
             fused_relu = False
         else:
@@ -457,7 +478,9 @@ class StepEngine:
             ldd = _ceil(G, 64)
             dl = self.ws("dlogits16", (B, ldd), torch.bfloat16, zero=True)
             wsb = self.ws("tileptr", (ops.decoder_mse_fused_workspace_bytes(B, G),), torch.uint8)
+            ev = self._t0("decoder_mse_fused")
             ops.decoder_mse_fused(h16, out.W16, out.b, G, crow, col, val, dl, sc[0:1], wsb)
+            self._t1(ev)
         else:
             logits = self.ws("logits32", (B, G))
             ops.gemm(h32, 0, out.W32, 0, B, G, out.K, bias=out.b, C32=logits, use_tc=False)
@@ -495,9 +518,13 @@ class StepEngine:
         H1 = out.K
         dh = self.ws("dh", (B, H1))
         if fused:
+            ev = self._t0("dWout_gemm")
             ops.gemm(dl, 1, h16, 1, G, H1, B, C32=out.gW)                 # dWout = dlogits^T h
+            self._t1(ev)
             ops.colsum(dl, out.gb, M=B, N=G)
+            ev = self._t0("dh_gemm")
             ops.gemm(dl, 0, out.W16, 1, B, H1, G, C32=dh)                 # dh = dlogits Wout
+            self._t1(ev)
         else:
             ops.gemm(dl, 1, h32, 1, G, H1, B, C32=out.gW, use_tc=False)
             ops.colsum(dl, out.gb)
@@ -532,16 +559,20 @@ class StepEngine:
                                              self.ws("ridx", (max(nnz, 1),), torch.int32),
                                              self.ws("cval", (max(nnz, 1),)), self.ws("cursor", (G + 1,), torch.int32))
         for j in reversed(range(len(enc))):
+            ev = self._t0("csr_linear_bwd_w+bn") if j == 0 else None
             d = self._layer_bwd(f"enc{j}", enc[j], caches[("enc", j)], d, B, need_dx=(j > 0),
                                 csc=(cptr, ridx, cval, G) if j == 0 else None)
+            self._t1(ev)
 
         # ---------------- grad norms, clip, Adam ----------------
         self._allreduce(gvae)
         self._allreduce(gexp)
+        ev = self._t0("norm+clip_adam")
         gvae.grad_norm_sq(s_norm(0))
         gexp.grad_norm_sq(s_norm(1))
         gvae.clip_adam(s_norm(0), self.clip.get("vae"), gscale)
         gexp.clip_adam(s_norm(1), self.clip.get("expert"), gscale)
+        self._t1(ev)
 
         self.last = dict(sc=sc, B=B, Z=Z, kl_weight=float(kl_weight), expert_id=expert_id, n_adv=n_adv,
                          gscale=gscale, ce_base=ce_base, z=z32, dl=dl)

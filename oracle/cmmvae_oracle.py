@@ -117,11 +117,21 @@ def csr_to_dense(crow, col, val, n_cols):
     return torch.from_numpy(out)
 
 
+FAST_CSR = False  # set by bench.py's CPU legs: use torch's sparse-CSR addmm (what the reference executes)
+
+
 def csr_linear(crow, col, val, weight, bias):
     """First expert-encoder layer on a CSR batch: Y = X W^T + b (components.py:276,306).
 
     Restated as an explicit per-nonzero accumulation so that CSR indexing is exercised by the
-    oracle itself (not by torch's sparse addmm)."""
+    oracle itself (not by torch's sparse addmm).  With FAST_CSR the same product goes through
+    ``F.linear`` on a ``torch.sparse_csr`` tensor, i.e. exactly the ATen call the reference makes
+    (used for full-size CPU timing; tests check both forms agree)."""
+    if FAST_CSR:
+        x = torch.sparse_csr_tensor(torch.as_tensor(np.asarray(crow)), torch.as_tensor(np.asarray(col)),
+                                    torch.as_tensor(np.asarray(val, dtype=np.float32)),
+                                    size=(len(crow) - 1, weight.shape[1]))
+        return F.linear(x, weight, bias)
     crow = torch.as_tensor(np.asarray(crow, dtype=np.int64))
     col = torch.as_tensor(np.asarray(col, dtype=np.int64))
     val = torch.as_tensor(np.asarray(val, dtype=np.float32))

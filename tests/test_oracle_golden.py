@@ -91,3 +91,20 @@ def test_other_species_untouched():
     for k, v in before.items():
         assert torch.equal(P[k], v), k
     assert "experts/mouse" not in opt
+
+
+def test_oracle_fast_csr_path_agrees():
+    """the full-size CPU-timing path (torch sparse addmm, as the reference executes it) equals the
+    explicit per-nonzero restatement, forward and weight gradient"""
+    crow, col, val = O.synth_csr(16, 300, 0.1, seed=4)
+    W = torch.randn(32, 300, requires_grad=True)
+    b = torch.randn(32)
+    y0 = O.csr_linear(crow, col, val, W, b)
+    g0, = torch.autograd.grad(y0.square().sum(), W)
+    O.FAST_CSR = True
+    try:
+        y1 = O.csr_linear(crow, col, val, W, b)
+        g1, = torch.autograd.grad(y1.square().sum(), W)
+    finally:
+        O.FAST_CSR = False
+    assert torch.allclose(y0, y1, atol=1e-5) and torch.allclose(g0, g1, atol=1e-4)
