@@ -197,6 +197,36 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, in
   }
 }
 
+// bf16, 8 columns (16 bytes) per thread: a warp reads 512 contiguous bytes of each row
+__global__ void __launch_bounds__(256) colsum_bf16x8_kernel(const __nv_bfloat16* __restrict__ X, int M, int N,
+                                                            int ldx, float* __restrict__ out) {
+  __shared__ float s1[8][32][9];
+  const int c0 = (blockIdx.x * 32 + threadIdx.x) * 8;
+  const int r0 = blockIdx.y * 128, r1 = min(M, r0 + 128);
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
+  if (c0 < N) {
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      const uint4 t = __ldg(reinterpret_cast<const uint4*>(X + (size_t)r * ldx + c0));
+      a[0] += bf16_lo(t.x); a[1] += bf16_hi(t.x); a[2] += bf16_lo(t.y); a[3] += bf16_hi(t.y);
+      a[4] += bf16_lo(t.z); a[5] += bf16_hi(t.z); a[6] += bf16_lo(t.w); a[7] += bf16_hi(t.w);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[threadIdx.y][threadIdx.x][j] = a[j];
+  __syncthreads();
+  if (threadIdx.y == 0 && c0 < N) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = a[j];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) v += s1[i][threadIdx.x][j];
+      if (c0 + j < N) atomicAdd(&out[c0 + j], v);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // reparameterisation + KL (+ Mean / Variance diagnostics)
 // ---------------------------------------------------------------------------------------------
@@ -527,10 +557,15 @@ extern "C" int cmmvae_colsum(const void* X, int x_dtype, int M, int N, int ldx, 
   cudaStream_t st = (cudaStream_t)stream;
   if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * N, st);
   dim3 grid((N + 31) / 32, (M + kRowsPerChunk - 1) / kRowsPerChunk), block(32, 8);
-  if (x_dtype == CMMVAE_F32)
+  if (x_dtype == CMMVAE_F32) {
     colsum_kernel<float><<<grid, block, 0, st>>>((const float*)X, M, N, ldx, out);
-  else
+  } else if (ldx % 8 == 0 && ((uintptr_t)X & 15) == 0 && ((N + 7) / 8 * 8) <= ldx) {
+    // rows are padded to a multiple of 8 columns (padding holds zeros or is never summed into out)
+    dim3 g8((N + 255) / 256, (M + 127) / 128);
+    colsum_bf16x8_kernel<<<g8, block, 0, st>>>((const __nv_bfloat16*)X, M, N, ldx, out);
+  } else {
     colsum_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)X, M, N, ldx, out);
+  }
   return check_launch("colsum");
 }
 

@@ -39,6 +39,7 @@ struct GemmParams {
   __nv_bfloat16* C16;
   int ldc;
   int vec_ok;  // 16-byte aligned rows for both outputs
+  int splits;  // split-K factor (gridDim.z); > 1: partial products are atomically added into a zeroed C32
 };
 
 template <int BN, bool A_MN, bool B_MN>
@@ -55,7 +56,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int num_kb = (p.K + BK - 1) / BK;
+  const int total_kb = (p.K + BK - 1) / BK;
+  const int kb_per = (total_kb + p.splits - 1) / p.splits;
+  const int kb0 = blockIdx.z * kb_per;
+  const int num_kb = max(0, min(total_kb, kb0 + kb_per) - kb0);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -83,7 +87,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint8_t* sA = smem + stage * S::kStageBytes;
         uint8_t* sB = sA + S::kABytes;
         mbar_expect_tx(&full_bar[stage], S::kStageBytes);
-        const int k0 = kb * BK;
+        const int k0 = (kb0 + kb) * BK;
         if (!A_MN) {
           tma_load_2d(sA, &tmA, &full_bar[stage], k0, m0);
         } else {
@@ -123,17 +127,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         umma_commit(&empty_bar[stage]);
         if (++stage == S::kStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tmem_full_bar);
+      if (num_kb > 0) umma_commit(tmem_full_bar);
     }
   } else {
     // ===== epilogue (warps 2..5; TMEM lane group = warp % 4) =====
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int gm = m0 + row;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
+    if (num_kb > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = 0; c < BN / 32 && num_kb > 0; ++c) {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
       tmem_ld_wait();
@@ -143,6 +149,25 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         const bool full = (gn0 + 32 <= p.N) && p.vec_ok;
+        if (p.splits > 1) {
+          // split-K: this CTA holds a partial product; split 0 also contributes the bias
+          float* crow = p.C32 + (size_t)gm * p.ldc + gn0;
+          if (p.bias && blockIdx.z == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (gn0 + j < p.N) v[j] += __ldg(p.bias + gn0 + j);
+          }
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              atomicAdd(reinterpret_cast<float4*>(crow + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (gn0 + j < p.N) atomicAdd(crow + j, v[j]);
+          }
+          continue;
+        }
         if (p.bias) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -250,7 +275,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     }
     configured = true;
   }
-  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM);
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.splits);
   kern<<<grid, kGemmThreads, S::kTotal, st>>>(tmA, tmB, p);
   return check_launch("gemm_bf16_tc");
 }
@@ -276,7 +301,16 @@ extern "C" int cmmvae_gemm_bf16_tc(const void* A, int lda, int transA, const voi
   CMMVAE_REQUIRE(!accumulate || C_f32, "gemm_bf16_tc: accumulate needs C_f32");
   CMMVAE_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)Bm & 15) == 0, "gemm_bf16_tc: operands must be 16-byte aligned");
   CMMVAE_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm_bf16_tc: lda/ldb must be multiples of 8 (got %d, %d)", lda, ldb);
-  const int BN = (N > 128 && (long long)((M + 127) / 128) * ((N + 255) / 256) >= 148) ? 256 : 128;
+  const long long tiles256 = (long long)((M + 127) / 128) * ((N + 255) / 256);
+  const int total_kb = (K + BK - 1) / BK;
+  // long-K, few-tile products (dh = dlogits Wout: K = genes) are split along K to fill the 148 SMs
+  int splits = 1;
+  if (!relu && !C_bf16 && !accumulate && C_f32 && total_kb >= 64 && tiles256 * 2 <= kNumSMs && N > 128) {
+    splits = (int)(kNumSMs / tiles256);
+    if (splits > total_kb / 16) splits = total_kb / 16;
+    if (splits < 1) splits = 1;
+  }
+  const int BN = (N > 128 && (tiles256 >= 148 || splits > 1)) ? 256 : 128;
   CUtensorMap tmA, tmB;
   int rc;
   // K-major: inner = K, rows = M (or N).  MN-major: inner = M (or N), rows = K, box 64 x 64.
@@ -290,7 +324,15 @@ extern "C" int cmmvae_gemm_bf16_tc(const void* A, int lda, int transA, const voi
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.relu = relu; p.accumulate = accumulate;
   p.C32 = C_f32; p.C16 = (__nv_bfloat16*)C_bf16; p.ldc = ldc;
   p.vec_ok = (ldc % 8 == 0) && (!C_f32 || ((uintptr_t)C_f32 & 15) == 0) && (!C_bf16 || ((uintptr_t)C_bf16 & 15) == 0);
+  p.splits = splits;
   cudaStream_t st = (cudaStream_t)stream;
+  if (splits > 1) {
+    cudaError_t e = cudaMemset2DAsync(C_f32, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st);
+    if (e != cudaSuccess) {
+      set_error("gemm_bf16_tc: split-K memset: %s", cudaGetErrorString(e));
+      return -2;
+    }
+  }
   if (BN == 256) return dispatch_major<256>(transA, transB, tmA, tmB, p, st);
   return dispatch_major<128>(transA, transB, tmA, tmB, p, st);
 }

@@ -114,27 +114,43 @@ __global__ void csc_hist_kernel(const int32_t* __restrict__ col, long long nnz, 
     atomicAdd(&cptr[col[i] + 1], 1);
 }
 
-// single-CTA in-place inclusive scan of a[0..n) (a[0] == 0 on entry => exclusive pointers)
+// single-CTA in-place inclusive scan of a[0..n) (a[0] == 0 on entry => exclusive pointers);
+// coalesced: 1024 consecutive elements per iteration, warp-shuffle scan + carried offset
 __global__ void __launch_bounds__(1024) scan_kernel(int32_t* __restrict__ a, int n, int32_t* __restrict__ copy) {
-  __shared__ int32_t part[1024];
-  const int t = threadIdx.x;
-  const int per = (n + 1023) / 1024;
-  const int lo = min(n, t * per), hi = min(n, lo + per);
-  int32_t s = 0;
-  for (int i = lo; i < hi; ++i) s += a[i];
-  part[t] = s;
+  __shared__ int32_t warp_tot[32];
+  __shared__ int32_t carry_s;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  if (t == 0) carry_s = 0;
   __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {
-    int32_t v = (t >= off) ? part[t - off] : 0;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + t;
+    int32_t v = (i < n) ? a[i] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    if (lane == 31) warp_tot[w] = v;
     __syncthreads();
-    part[t] += v;
+    if (w == 0) {
+      int32_t x = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t u = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += u;
+      }
+      warp_tot[lane] = x;
+    }
     __syncthreads();
-  }
-  int32_t run = (t == 0) ? 0 : part[t - 1];
-  for (int i = lo; i < hi; ++i) {
-    run += a[i];
-    a[i] = run;
-    copy[i] = run;
+    const int32_t carry = carry_s;
+    v += carry + (w > 0 ? warp_tot[w - 1] : 0);
+    if (i < n) {
+      a[i] = v;
+      copy[i] = v;
+    }
+    __syncthreads();
+    if (t == 1023) carry_s = v;
+    __syncthreads();
   }
 }
 

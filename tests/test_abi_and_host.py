@@ -1,0 +1,199 @@
+"""CPU-side checks: the C-ABI library builds for sm_100a, loads and exports every symbol that
+include/cmmvae_b200.h declares (no compute calls without a GPU); host logic of the module mirror
+(config validation, log tagging, KL annealing, optimizer map, YAML class_path loading).  The shape /
+key tests follow the reference's own tests (tests/test_components.py, tests/test_tag_log_dict.py)."""
+import ctypes
+import os
+
+import pandas as pd
+import pytest
+import torch
+import torch.nn as nn
+
+import mmvae_b200.compat as compat
+from mmvae_b200 import _lib
+from mmvae_b200.models import CMMVAEModel, tag_log_dict
+from mmvae_b200.models.cmmvae_model import convert_to_flat_list_and_map
+from mmvae_b200.modules import CLVAE, CMMVAE
+from mmvae_b200.modules.base import (ConditionalLayer, Encoder, Expert, Experts, FCBlock, FCBlockConfig,
+                                     KLAnnealingFn, LinearKLAnnealingFn)
+from mmvae_b200.modules.base.components import collect_species_files, is_iterable
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---------------------------------------------------------------------------------------- C ABI
+def test_library_builds_and_exports_every_declared_symbol():
+    path = _lib.build_library()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    names = _lib.exported_symbols_in_header()
+    assert len(names) >= 20 and "cmmvae_decoder_mse_fused" in names and "cmmvae_csr_linear_fwd" in names
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.cmmvae_abi_version() == 1
+    lib.cmmvae_last_error.restype = ctypes.c_char_p
+    assert isinstance(lib.cmmvae_last_error(), bytes)
+
+
+def test_argument_validation_happens_before_any_launch():
+    lib = _lib.load()
+    lib.cmmvae_last_error.restype = ctypes.c_char_p
+    rc = lib.cmmvae_csr_linear_fwd(None, None, None, 0, 10, 8, None, 0, None, None, None)
+    assert rc == -1 and b"bad shape" in lib.cmmvae_last_error()
+    rc = lib.cmmvae_gemm_bf16_tc(ctypes.c_void_p(16), 7, 0, ctypes.c_void_p(32), 8, 0, 4, 4, 4, None, 0, 0,
+                                 ctypes.c_void_p(64), None, 4, None)
+    assert rc == -1 and b"multiples of 8" in lib.cmmvae_last_error()
+
+
+def test_sass_contains_tcgen05_and_tma():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in out and "UTMALDG" in out and "LDTM" in out
+
+
+def test_forward_on_cpu_tensors_fails_loudly():
+    block = FCBlock(FCBlockConfig(layers=[10, 20, 30], dropout_rate=0.5))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        block(torch.randn(5, 10))
+
+
+# ------------------------------------------------------------------- reference unit tests, host side
+@pytest.mark.parametrize("obj,expect", [([1, 2, 3], True), ("string", True), (123, False), ({"k": "v"}, True),
+                                        (None, False)])
+def test_is_iterable(obj, expect):
+    assert is_iterable(obj) is expect
+
+
+def test_fc_block_config_and_block_properties():
+    cfg = FCBlockConfig(layers=[10, 20, 30], dropout_rate=0.5)
+    block = FCBlock(cfg)
+    assert cfg.n_layers == 2 and block.input_dim == 10 and block.output_dim == 30
+    assert FCBlock(FCBlockConfig(layers=[10, 20, 30], return_hidden=False)).can_bypass
+    assert not FCBlock(FCBlockConfig(layers=[10, 20, 30], return_hidden=True)).can_bypass
+    cfg = FCBlockConfig(layers=[10, 20, 30], dropout_rate=[0.5, 0.3], use_batch_norm=True)
+    assert cfg.layers == [10, 20, 30] and cfg.dropout_rate == [0.5, 0.3] and cfg.use_batch_norm == [True, True]
+    assert all(issubclass(a, nn.ReLU) for a in FCBlockConfig(layers=[10, 20], activation_fn=nn.ReLU).activation_fn)
+    assert FCBlockConfig(layers=[7]).layers == [7, 7]
+    names = [n for n, _ in FCBlock(FCBlockConfig([4, 5], use_batch_norm=True, use_layer_norm=True,
+                                                 activation_fn=nn.ReLU, dropout_rate=0.1)).fc_layers[0].named_children()]
+    assert names == ["lin", "bn", "ln", "af", "dr"]
+
+
+@pytest.mark.parametrize("kwargs", [dict(layers=[-10, 20]), dict(layers=[10, 20, 30], dropout_rate=[0.5]),
+                                    dict(layers=(10, 20)), dict(layers=[10, 20], use_batch_norm=[1]),
+                                    dict(layers=[10, 20], activation_fn=[int])])
+def test_fc_block_config_validation_errors(kwargs):
+    with pytest.raises(ValueError):
+        FCBlockConfig(**kwargs)
+
+
+def test_conditional_layer_and_species_files(tmp_path):
+    csv = tmp_path / "unique_assays.csv"
+    pd.DataFrame(["10x 5' v1", "10x 3' v3", "microwell-seq", "a.b"]).to_csv(csv, header=False, index=False)
+    layer = ConditionalLayer(batch_key="assay", conditions_path=str(csv), fc_block_config=FCBlockConfig(layers=[10]))
+    assert layer.batch_key == "assay" and len(layer.conditions) == 4 and "a_b" in layer.conditions
+    (tmp_path / "d" / "shared").mkdir(parents=True)
+    (tmp_path / "d" / "human").mkdir()
+    (tmp_path / "d" / "shared" / "unique_expression_assay.csv").write_text("x\n")
+    (tmp_path / "d" / "human" / "unique_expression_assay.csv").write_text("x\n")
+    (tmp_path / "d" / "human" / "unique_expression_sex.csv").write_text("x\n")
+    found = collect_species_files(str(tmp_path / "d"), ["assay", "sex"])
+    assert set(found["shared"]) == {"assay"} and set(found["human"]) == {"sex"}
+
+
+def test_encoder_expert_experts_construction():
+    enc = Encoder(latent_dim=5, fc_block_config=FCBlockConfig(layers=[10]))
+    assert enc.n_layers == 1 and enc.var_eps == 1e-4
+    cfg = FCBlockConfig(layers=[10, 20])
+    e1, e2 = Expert("expert1", cfg, cfg), Expert("expert2", cfg, cfg)
+    assert e1.id == "expert1" and e1.encoder is not None and e1.decoder is not None
+    with pytest.raises(NotImplementedError):
+        e1()
+    experts = Experts([e1, e2])
+    assert len(experts) == 2 and "expert1" in experts and experts.labels == {"expert1": 0, "expert2": 1}
+
+
+def test_tag_log_dict():
+    d = {"loss": torch.tensor(1.0), "accuracy": torch.tensor(0.9)}
+    assert tag_log_dict(d) == d
+    assert set(tag_log_dict(d, tags=["modelA", "experiment1"], sep="_", key_pos="first")) == {
+        "loss_modelA_experiment1", "accuracy_modelA_experiment1"}
+    assert set(tag_log_dict(d, tags=["modelA", "experiment1"], sep="_", key_pos="last")) == {
+        "modelA_experiment1_loss", "modelA_experiment1_accuracy"}
+    assert tag_log_dict({}) == {}
+    with pytest.raises(ValueError):
+        tag_log_dict({"loss": 1.0}, key_pos="invalid")
+
+
+def test_kl_annealing_matches_reference_schedule():
+    fn = LinearKLAnnealingFn(min_kl_weight=0.1, max_kl_weight=1.0, warmup_steps=1, climax_steps=4)
+    seen = []
+    for _ in range(7):
+        seen.append(fn.kl_weight)
+        fn.step()
+    assert seen == pytest.approx([0.1, 0.1, 0.325, 0.55, 0.775, 1.0, 1.0])
+    const = KLAnnealingFn(0.5)
+    const.step()
+    assert const.kl_weight == 0.5
+
+
+def test_flat_list_and_map():
+    flat = []
+    m = convert_to_flat_list_and_map({"experts": {"human": "a", "mouse": "b"}, "vae": "c", "adversarials": {1: "d"}}, flat)
+    assert flat == ["a", "b", "c", "d"]
+    assert m == {"experts": {"human": 0, "mouse": 1}, "vae": 2, "adversarials": {1: 3}}
+
+
+def test_yaml_class_path_tree_instantiates_under_cmmvae_names():
+    """the reference's jsonargparse trees (configs/model/*.yaml) load against this package"""
+    compat.install_as_cmmvae()
+    import cmmvae.models  # noqa: F401  (alias)
+    tree = {
+        "class_path": "cmmvae.models.CMMVAEModel",
+        "init_args": {
+            "kl_annealing_fn": {"class_path": "cmmvae.modules.base.KLAnnealingFn", "init_args": {"kl_weight": 1.0}},
+            "adv_weight": 0,
+            "autograd_config": {"class_path": "cmmvae.config.AutogradConfig", "init_args": {
+                "vae_gradient_clip": {"class_path": "cmmvae.config.GradientClipConfig",
+                                      "init_args": {"val": 10, "algorithm": "norm"}}}},
+            "module": {"class_path": "cmmvae.modules.CMMVAE", "init_args": {
+                "vae": {"class_path": "cmmvae.modules.CLVAE", "init_args": {
+                    "latent_dim": 16,
+                    "encoder_config": {"class_path": "cmmvae.modules.base.FCBlockConfig", "init_args": {
+                        "layers": [32, 24], "use_batch_norm": True, "activation_fn": "torch.nn.ReLU",
+                        "return_hidden": True}},
+                    "decoder_config": {"class_path": "cmmvae.modules.base.FCBlockConfig", "init_args": {
+                        "layers": [16, 24, 32], "activation_fn": "torch.nn.ReLU"}}}},
+                "experts": {"class_path": "cmmvae.modules.base.Experts", "init_args": {"experts": [
+                    {"class_path": "cmmvae.modules.base.Expert", "init_args": {
+                        "id": "human",
+                        "encoder_config": {"class_path": "cmmvae.modules.base.FCBlockConfig", "init_args": {
+                            "layers": [200, 64, 32], "dropout_rate": [0.1, 0.1], "use_batch_norm": True,
+                            "activation_fn": "torch.nn.ReLU"}},
+                        "decoder_config": {"class_path": "cmmvae.modules.base.FCBlockConfig", "init_args": {
+                            "layers": [32, 64, 200], "activation_fn": "torch.nn.ReLU"}}}}]}},
+                "adversarials": None}}}}
+    model = compat.instantiate(tree)
+    assert isinstance(model, CMMVAEModel) and model.adv_weight == 1.0   # 0 -> 1.0, reference quirk
+    assert len(model.module.adversarials) == 0                            # attribute always exists
+    keys = set(model.state_dict())
+    assert "module.experts.human.encoder.fc_layers.0.lin.weight" in keys
+    assert "module.vae.encoder.mean_encoder.weight" in keys
+    assert "module.experts.human.encoder.fc_layers.1.bn.running_mean" in keys
+    assert tuple(model.state_dict()["module.experts.human.decoder.fc_layers.1.lin.weight"].shape) == (200, 64)
+    # He init: zero biases, fan_out-scaled weights
+    w = model.module.experts["human"].encoder.fc_layers[0].lin
+    assert float(w.bias.abs().max()) == 0.0
+    assert float(w.weight.std()) == pytest.approx((2.0 / 64) ** 0.5, rel=0.1)
+
+
+def test_reference_state_dict_loads_by_name():
+    """golden init state (from the unmodified reference) loads strictly: identical names and shapes"""
+    from helpers import GoldenCase, build_b200_model
+    import tempfile
+    gc = GoldenCase("two_species_adv")
+    with tempfile.TemporaryDirectory() as tmp:
+        model = build_b200_model(gc, tmp)
+    res = model.load_state_dict({f"module.{k}": v for k, v in gc.state("init").items()}, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys

@@ -153,7 +153,8 @@ def _pad8(t):
     return buf[:, :C]
 
 
-@pytest.mark.parametrize("M,N,K", SHAPES + [(1024, 2048, 128), (2048, 8192, 256), (130, 60530, 64)])
+@pytest.mark.parametrize("M,N,K", SHAPES + [(1024, 2048, 128), (2048, 8192, 256), (130, 60530, 64),
+                                             (256, 1024, 8192), (1024, 1024, 60530)])  # last two: split-K
 @pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
 def test_gemm_bf16_tc(ops, M, N, K, tA, tB):
     g = torch.Generator().manual_seed(M * 3 + N + K)
@@ -166,7 +167,9 @@ def test_gemm_bf16_tc(ops, M, N, K, tA, tB):
     C = _pad8(torch.empty(M, N).cuda())
     C16 = None
     ops.gemm(Ad, tA, Bd, tB, M, N, K, bias=bias.cuda(), relu=False, C32=C)
-    assert rel(C, ref) < 2e-5, (tA, tB)
+    assert rel(C, ref) < (2e-5 if K < 8192 else 2e-4), (tA, tB)   # long K: fp32 summation-order noise
+    if K >= 8192 and (tA, tB) != (0, 1):
+        return  # the long-K shapes exist for the split-K path; one epilogue variant is enough
     # relu + accumulate + bf16 output
     C2 = _pad8(torch.ones(M, N).cuda())
     ld = C2.stride(0)
