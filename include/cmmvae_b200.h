@@ -50,6 +50,24 @@ int cmmvae_csr_transpose(const int32_t* crow, const int32_t* col, const float* v
 int cmmvae_csr_linear_bwd_w(const int32_t* cptr, const int32_t* ridx, const float* cval,
                             int B, int G, int H, const float* dY, float* dWt, void* stream);
 
+/* Tensor-pipe form of K1/K1b (bf16 policy): the CSR batch is densified tile by tile inside shared memory,
+ * directly in the tcgen05 operand layout, and multiplied on the tensor cores; HBM sees only the CSR
+ * arrays, the bf16 weight (or dY) and the output.  `tile_ptr` (device, cmmvae_csr_tile_ptr_bytes) is
+ * the per-(cell, 64-gene window) CSR pointer table built by cmmvae_csr_tile_ptr, bit-exact with
+ * crow/col.  Wt_bf16 [G,H], dY_bf16 [B,H], H % 8 == 0.  Faster than the gather kernels above
+ * ~1.5 % density; identical contract otherwise (fwd: Y = X Wt + bias; bwd: dWt = X^T dY, genes
+ * absent from the batch get exactly 0). */
+size_t cmmvae_csr_tile_ptr_bytes(int B, int G);
+size_t cmmvae_csr_packed_bytes(long long nnz);
+/* builds tile_ptr ([G/64+1][B], window-major) and `packed` (one 4-byte record per non-zero: 16-bit gene id |
+ * bf16 value, CSR order; needs G <= 65536) */
+int cmmvae_csr_tile_ptr(const int32_t* crow, const int32_t* col, const float* val, int B, int G, long long nnz,
+                        int32_t* tile_ptr, void* packed, void* stream);
+int cmmvae_csr_linear_fwd_tc(const void* packed, const int32_t* tile_ptr, int B, int G, int H,
+                             const void* Wt_bf16, const float* bias, float* Y, void* stream);
+int cmmvae_csr_linear_bwd_w_tc(const void* packed, const int32_t* tile_ptr, int B, int G, int H,
+                               const void* dY_bf16, float* dWt, void* stream);
+
 /* ---- K2/K3: BatchNorm1d(momentum, eps) + ReLU + Dropout, components.py:279-288 ------------- */
 /* column statistics of Y[B,H]: mean[H], rstd[H] = 1/sqrt(biased var + eps); updates running
  * stats (unbiased var, momentum) when running_mean != NULL.  `scratch` = 2*H doubles, zeroed by

@@ -8,7 +8,7 @@
 //
 // Persistent kernel, one CTA per SM, 128 x 256 output tiles, static round-robin tile order with the
 // cell-block index fastest (so CTAs running concurrently share the same Wout tiles in L2).
-//   warp 0      TMA producer (3-stage ring of 128x64 h tiles + 256x64 Wout tiles, 128B swizzle)
+//   warp 0      TMA producer (4-stage ring of 128x64 h tiles + 256x64 Wout tiles, 128B swizzle)
 //   warp 1      tcgen05.mma issuer; two 256-column TMEM accumulators ping-pong with the epilogue
 //   warps 2..5  epilogue: thread = cell.  The cell's CSR entries inside the gene window are located
 //               through a per-(cell, gene-tile) pointer table (built once per batch by
@@ -21,8 +21,8 @@ namespace cmmvae {
 
 using namespace tc;
 
-constexpr int DBM = 128, DBN = 256, DBK = 64, DSTAGES = 3;
-constexpr int DCAP = 48;  // CSR entries per (cell, gene tile) staged in smem; the rest stream from global
+constexpr int DBM = 128, DBN = 256, DBK = 64, DSTAGES = 4;
+constexpr int DCAP = 24;  // CSR entries per (cell, gene tile) staged in smem; the rest stream from global
 constexpr int kDecThreads = 192;
 
 struct DecSmem {
@@ -75,8 +75,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __global__ void __launch_bounds__(kDecThreads, 1)
 decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW,
                          const DecParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];   // 128B-swizzled tiles need 1024-byte alignment
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   float* staging = reinterpret_cast<float*>(smem + DecSmem::kStagingOff);
   float* ent_val = reinterpret_cast<float*>(smem + DecSmem::kEntValOff);
   uint8_t* ent_col = smem + DecSmem::kEntColOff;

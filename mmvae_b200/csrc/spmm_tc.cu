@@ -1,0 +1,360 @@
+// K1 / K1b on the tensor pipe: the CSR batch is densified tile by tile INSIDE shared memory (never in
+// HBM) straight into the UMMA operand layout, and multiplied with tcgen05.
+//
+//   forward   Y[B,H]   = X[B,G]   * Wt[G,H]  (+bias)     A = X tile   (K-major,  K = genes)
+//   backward  dWt[G,H] = X^T[G,B] * dY[B,H]              A = X^T tile (MN-major, K = cells)
+//
+// Why: the per-nonzero gather kernel (sparse.cu) moves 2 KB of weight row per non-zero through L1/L2
+// (6.3 GB per step at B=1024, d=5%) and is L1/L2-bandwidth bound at ~6% of the HBM roofline of the
+// algorithmic bytes.  Above ~1.5% density the dense tile product on the tensor pipe is faster even though
+// it multiplies zeros; HBM traffic is the algorithmic minimum: CSR once (per N tile),
+// the bf16 weight once, Y once.  Values are rounded to bf16 when staged (the bf16 precision policy).
+//
+// CTA = 128 x 256 output tile, 320 threads:
+//   warp 0      TMA: B-operand tiles (Wt or dY, MN-major, 4 boxes of 64x64 per stage)
+//   warp 1      tcgen05.mma issue, accumulator in TMEM (256 columns)
+//   warps 2..9  two producer groups of 4 warps; group g builds the A tile of k-blocks kb = g (mod 2):
+//               zero the 16 KB tile, then scatter the CSR entries of the tile (located through the
+//               per-(cell, 64-gene window) pointer table) into the 128B-swizzled layout,
+//               fence.proxy.async, arrive on the stage's full barrier.  After the K loop the same warps
+//               run the epilogue.
+#include "tc.cuh"
+
+namespace cmmvae {
+
+using namespace tc;
+
+constexpr int SBM = 128, SBN = 256, SBK = 64, SSTAGES = 4;
+constexpr int kSpThreads = 320;
+constexpr int kSpABytes = SBM * SBK * 2;   // 16 KB
+constexpr int kSpBBytes = SBN * SBK * 2;   // 32 KB
+constexpr int kSpStage = kSpABytes + kSpBBytes;
+constexpr int kSpSmem = SSTAGES * kSpStage + 1024 + 1024;
+
+struct SpParams {
+  int B, G, H;
+  const uint32_t* packed;  // per non-zero: column (low 16 bits) | bf16 value (high 16 bits), CSR order
+  const int32_t* tp;       // [ntp][B] (window-major) first CSR position of row b with column >= 64*w
+  int ntp;
+  const float* bias;   // forward only
+  float* out;          // forward: Y[B,H]; backward: dWt[G,H]
+  int splits;          // forward split-K over genes
+};
+
+// tp[w][b] = first position p in row b with col[p] >= 64*w, w = 0..NW (NW = ceil(G/64)); window-major so
+// that the producers' reads (consecutive lanes = consecutive cells) coalesce
+__global__ void tile_ptr64_kernel(const int32_t* __restrict__ crow, const int32_t* __restrict__ col, int B, int ntp,
+                                  int32_t* __restrict__ tp) {
+  const long long n = (long long)B * ntp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i / B), b = (int)(i % B);
+    int lo = crow[b], hi = crow[b + 1];
+    const int key = w * 64;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(col + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    tp[i] = lo;
+  }
+}
+
+// packed[i] = col[i] | bf16(val[i]) << 16   (G <= 65536); one 4-byte record per non-zero
+__global__ void csr_pack_kernel(const int32_t* __restrict__ col, const float* __restrict__ val, long long nnz,
+                                long long padded, uint32_t* __restrict__ packed) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < padded;
+       i += (long long)gridDim.x * blockDim.x) {
+    uint32_t r = 0;
+    if (i < nnz) {
+      const __nv_bfloat16 h = __float2bfloat16(val[i]);
+      r = (uint32_t)(col[i] & 0xFFFF) | ((uint32_t)(*reinterpret_cast<const uint16_t*>(&h)) << 16);
+    }
+    packed[i] = r;
+  }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(kSpThreads, 1)
+spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const SpParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];   // 128B-swizzled tiles need 1024-byte alignment
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SSTAGES * kSpStage);
+  uint64_t* empty_bar = full_bar + SSTAGES;
+  uint64_t* tmem_full_bar = empty_bar + SSTAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * SBN, m0 = blockIdx.y * SBM;
+  const int Kdim = BWD ? p.B : p.G;
+  const int total_kb = (Kdim + SBK - 1) / SBK;
+  const int kb_per = (total_kb + p.splits - 1) / p.splits;
+  const int kb0 = blockIdx.z * kb_per;
+  const int num_kb = max(0, min(total_kb, kb0 + kb_per) - kb0);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < SSTAGES; ++s) {
+      mbar_init(&full_bar[s], 5);   // 1 TMA arrive.expect_tx + 4 producer warps
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<SBN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sB = smem + stage * kSpStage + kSpABytes;
+        mbar_expect_tx(&full_bar[stage], kSpBBytes);
+#pragma unroll
+        for (int j = 0; j < SBN / 64; ++j)
+          tma_load_2d(sB + j * (SBK * 128), &tmB, &full_bar[stage], n0 + 64 * j, (kb0 + kb) * SBK);
+        if (++stage == SSTAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(SBM, SBN, BWD ? 1 : 0, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + stage * kSpStage);
+        const uint32_t sB = sA + kSpABytes;
+#pragma unroll
+        for (int k = 0; k < SBK / 16; ++k) {
+          const uint64_t da = BWD ? make_desc_sw128(sA + k * 2048, SBK * 128, 1024)
+                                  : make_desc_sw128(sA + k * 32, 16, 1024);
+          const uint64_t db = make_desc_sw128(sB + k * 2048, SBK * 128, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (kb | k) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == SSTAGES) { stage = 0; phase ^= 1; }
+      }
+      if (num_kb > 0) umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ===== A-tile producers (two groups), then epilogue =====
+    const int group = (warp - 2) >> 2;                 // 0 or 1
+    const int t = (warp - 2 - group * 4) * 32 + lane;  // 0..127 inside the group
+    // this thread's 128-byte line of the tile, its swizzle phase, its CSR row and window index
+    int line_off, swz;
+    if (!BWD) {                       // thread = cell row of the tile; window advances with kb
+      line_off = (t >> 3) * 1024 + (t & 7) * 128;
+      swz = t & 7;
+    } else {                          // thread = (cell kk inside the k-block, gene half h)
+      const int kk = t & 63, h = t >> 6;
+      line_off = h * (SBK * 128) + (kk >> 3) * 1024 + (kk & 7) * 128;
+      swz = kk & 7;
+    }
+    auto window_ptrs = [&](int kb, int& q0, int& q1, int& win_start) {
+      // CSR range [q0,q1) of the entries this thread stages for k-block kb (coalesced table reads)
+      q0 = q1 = 0;
+      win_start = 0;
+      if (kb >= num_kb) return;
+      const int kbg = kb0 + kb;
+      int b, w;
+      if (!BWD) { b = m0 + t; w = kbg; } else { b = kbg * 64 + (t & 63); w = (m0 >> 6) + (t >> 6); }
+      if (b < p.B && w < p.ntp - 1) {
+        q0 = __ldg(p.tp + (size_t)w * p.B + b);
+        q1 = __ldg(p.tp + (size_t)(w + 1) * p.B + b);
+      }
+      win_start = w * 64;
+    };
+    constexpr int E = 8;   // packed records prefetched into registers per (thread, window)
+    auto load_entries = [&](int q0, int q1, uint32_t (&rec)[E]) {
+      const int n = q1 - q0;
+      const uint32_t* src = p.packed + q0;
+#pragma unroll
+      for (int u = 0; u < E; ++u) rec[u] = (u < n) ? __ldg(src + u) : 0u;
+    };
+    // Software pipeline per group, iteration i <-> k-block kb = group + 2 i:
+    //   pointers P(i+2) and entries E(i+1) are requested while tile i is built, so every global load has a
+    //   full iteration to land.  Three pointer slots and two entry slots rotate by NAME (the body is
+    //   instantiated six times per trip) so no register moves touch in-flight loads.
+    struct Ptr { int q0, q1, win; };
+    Ptr P0, P1, P2;
+    uint32_t E0[E], E1[E];
+    window_ptrs(group, P0.q0, P0.q1, P0.win);
+    window_ptrs(group + 2, P1.q0, P1.q1, P1.win);
+    load_entries(P0.q0, P0.q1, E0);
+    const int bar_id = 1 + group;
+    const uint32_t smem_base = smem_u32(smem);
+    auto body = [&](int kb, const Ptr& cur, const Ptr& nxt, Ptr& fut, const uint32_t (&ec)[E], uint32_t (&en)[E]) {
+      if (kb >= num_kb) return;
+      const int stage = kb % SSTAGES;
+      const uint32_t phase = (kb / SSTAGES) & 1;
+      window_ptrs(kb + 4, fut.q0, fut.q1, fut.win);
+      load_entries(nxt.q0, nxt.q1, en);
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      const uint32_t tile = smem_base + stage * kSpStage;
+      // zero the 16 KB tile cooperatively (consecutive threads -> consecutive 16-byte chunks: conflict free)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) st_shared_zero16(tile + (c * 128 + t) * 16);
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      const uint32_t line = tile + line_off;
+      const int a0 = cur.q0, a1 = cur.q1, aw = cur.win;
+      const int n = a1 - a0;
+#pragma unroll
+      for (int u = 0; u < E; ++u) {
+        const int c = (int)(ec[u] & 0xFFFFu) - aw;
+        st_shared_u16_if(line + ((((c >> 3) ^ swz) << 4) | ((c & 7) << 1)), ec[u] >> 16, u < n);
+      }
+      for (int q = a0 + E; q < a1; ++q) {   // windows with more than E entries (dense batches)
+        const uint32_t r = __ldg(p.packed + q);
+        const int c = (int)(r & 0xFFFFu) - aw;
+        st_shared_u16_if(line + ((((c >> 3) ^ swz) << 4) | ((c & 7) << 1)), r >> 16, true);
+      }
+      fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[stage]);
+    };
+    for (int kb = group; kb < num_kb; kb += 12) {
+      body(kb, P0, P1, P2, E0, E1);
+      body(kb + 2, P1, P2, P0, E1, E0);
+      body(kb + 4, P2, P0, P1, E0, E1);
+      body(kb + 6, P0, P1, P2, E1, E0);
+      body(kb + 8, P1, P2, P0, E0, E1);
+      body(kb + 10, P2, P0, P1, E1, E0);
+    }
+
+    // ----- epilogue: group g drains accumulator columns [128 g, 128 g + 128) -----
+    if (num_kb > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+      const int qd = warp & 3;
+      const int row = qd * 32 + lane;
+      const int gm = m0 + row;
+      const int Mdim = BWD ? p.G : p.B;
+#pragma unroll 1
+      for (int c = group * 4; c < group * 4 + 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        const int gn0 = n0 + c * 32;
+        if (gm < Mdim && gn0 < p.H) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          float* orow = p.out + (size_t)gm * p.H + gn0;
+          const bool full = gn0 + 32 <= p.H;
+          if (!BWD && p.bias && blockIdx.z == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (gn0 + j < p.H) v[j] += __ldg(p.bias + gn0 + j);
+          }
+          if (!BWD && p.splits > 1) {
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                atomicAdd(reinterpret_cast<float4*>(orow + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (gn0 + j < p.H) atomicAdd(orow + j, v[j]);
+            }
+          } else if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(orow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (gn0 + j < p.H) orow[j] = v[j];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<SBN>(tmem_base);
+}
+
+int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                   uint32_t box_outer);
+
+template <bool BWD>
+static int launch_spmm_tc(const CUtensorMap& tm, const SpParams& p, dim3 grid, cudaStream_t st) {
+  auto kern = spmm_tc_kernel<BWD>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSpSmem);
+    if (e != cudaSuccess) {
+      set_error("spmm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return -2;
+    }
+    configured = true;
+  }
+  kern<<<grid, kSpThreads, kSpSmem, st>>>(tm, p);
+  return check_launch(BWD ? "csr_linear_bwd_w_tc" : "csr_linear_fwd_tc");
+}
+
+}  // namespace cmmvae
+
+using namespace cmmvae;
+
+extern "C" size_t cmmvae_csr_tile_ptr_bytes(int B, int G) {
+  return sizeof(int32_t) * (size_t)B * (size_t)((G + 63) / 64 + 1);
+}
+extern "C" size_t cmmvae_csr_packed_bytes(long long nnz) { return sizeof(uint32_t) * (size_t)((nnz + 3) / 4 * 4 + 4); }
+
+extern "C" int cmmvae_csr_tile_ptr(const int32_t* crow, const int32_t* col, const float* val, int B, int G,
+                                   long long nnz, int32_t* tile_ptr, void* packed, void* stream) {
+  CMMVAE_REQUIRE(B > 0 && G > 0 && tile_ptr && packed, "csr_tile_ptr: bad arguments");
+  CMMVAE_REQUIRE(G <= 65536, "csr_tile_ptr: packed records hold 16-bit gene ids (G=%d)", G);
+  CMMVAE_REQUIRE(((uintptr_t)packed & 15) == 0, "csr_tile_ptr: packed must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ntp = (G + 63) / 64 + 1;
+  const long long n = (long long)B * ntp;
+  long long want = (n + 255) / 256;
+  int blocks = (int)(want < 148 * 16 ? want : 148 * 16);
+  tile_ptr64_kernel<<<blocks, 256, 0, st>>>(crow, col, B, ntp, tile_ptr);
+  if (int rc = check_launch("csr_tile_ptr")) return rc;
+  const long long padded = (nnz + 3) / 4 * 4 + 4;
+  want = (padded + 255) / 256;
+  blocks = (int)(want < 148 * 16 ? want : 148 * 16);
+  csr_pack_kernel<<<blocks, 256, 0, st>>>(col, val, nnz, padded, (uint32_t*)packed);
+  return check_launch("csr_pack");
+}
+
+extern "C" int cmmvae_csr_linear_fwd_tc(const void* packed, const int32_t* tile_ptr, int B, int G, int H,
+                                        const void* Wt_bf16, const float* bias, float* Y, void* stream) {
+  CMMVAE_REQUIRE(B > 0 && G > 0 && H > 0 && H % 8 == 0, "csr_linear_fwd_tc: bad shape (H must be a multiple of 8)");
+  CMMVAE_REQUIRE(((uintptr_t)Wt_bf16 & 15) == 0 && ((uintptr_t)Y & 15) == 0, "csr_linear_fwd_tc: alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  SpParams p;
+  p.B = B; p.G = G; p.H = H; p.packed = (const uint32_t*)packed; p.tp = tile_ptr; p.ntp = (G + 63) / 64 + 1;
+  p.bias = bias; p.out = Y;
+  const int tiles = ((B + SBM - 1) / SBM) * ((H + SBN - 1) / SBN);
+  const int total_kb = (G + SBK - 1) / SBK;
+  int splits = tiles >= kNumSMs ? 1 : kNumSMs / tiles;
+  if (splits > total_kb / 8) splits = total_kb / 8;
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+  CUtensorMap tm;
+  if (int rc = make_tmap_bf16(&tm, Wt_bf16, (uint64_t)H, (uint64_t)G, (uint64_t)H, 64, SBK)) return rc;
+  if (splits > 1) cudaMemsetAsync(Y, 0, sizeof(float) * (size_t)B * H, st);
+  dim3 grid((H + SBN - 1) / SBN, (B + SBM - 1) / SBM, splits);
+  return launch_spmm_tc<false>(tm, p, grid, st);
+}
+
+extern "C" int cmmvae_csr_linear_bwd_w_tc(const void* packed, const int32_t* tile_ptr, int B, int G, int H,
+                                          const void* dY_bf16, float* dWt, void* stream) {
+  CMMVAE_REQUIRE(B > 0 && G > 0 && H > 0 && H % 8 == 0, "csr_linear_bwd_w_tc: bad shape (H must be a multiple of 8)");
+  CMMVAE_REQUIRE(((uintptr_t)dY_bf16 & 15) == 0 && ((uintptr_t)dWt & 15) == 0, "csr_linear_bwd_w_tc: alignment");
+  SpParams p;
+  p.B = B; p.G = G; p.H = H; p.packed = (const uint32_t*)packed; p.tp = tile_ptr; p.ntp = (G + 63) / 64 + 1;
+  p.bias = nullptr; p.out = dWt; p.splits = 1;
+  CUtensorMap tm;
+  if (int rc = make_tmap_bf16(&tm, dY_bf16, (uint64_t)H, (uint64_t)B, (uint64_t)H, 64, SBK)) return rc;
+  dim3 grid((H + SBN - 1) / SBN, (G + SBM - 1) / SBM, 1);
+  return launch_spmm_tc<true>(tm, p, grid, (cudaStream_t)stream);
+}

@@ -18,6 +18,16 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// predicated 2-byte shared store (branch free)
+__device__ __forceinline__ void st_shared_u16_if(uint32_t addr, uint32_t v, bool pred) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.shared.u16 [%0], %1;\n\t}\n" ::"r"(addr),
+               "h"((uint16_t)v), "r"((uint32_t)pred)
+               : "memory");
+}
+__device__ __forceinline__ void st_shared_zero16(uint32_t addr) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
+}
+
 // ---- mbarrier ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

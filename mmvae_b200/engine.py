@@ -262,6 +262,8 @@ class StepEngine:
         self._ws: Dict[tuple, torch.Tensor] = {}
         self.timers: Optional[Dict[str, list]] = None   # name -> [(start_event, end_event)] when profiling
         self._seed = 0x5EED
+        self.spmm_tc = True                 # bf16 policy: expert-encoder SpMM on the tensor pipe ...
+        self.spmm_tc_min_density = 0.015    # ... when the batch is at least this dense (else gather kernel)
         self.world = 1
         self.last = None
 
@@ -314,10 +316,13 @@ class StepEngine:
         want16 = self.precision == "bf16"
         plain = lp.bn is None and lp.p_drop == 0.0
         if lp.sparse:
-            crow, col, val, G = csr
+            crow, col, val, G, tp = csr
             Wt = lp.W16 if self.precision == "bf16" else lp.W32
             ev = self._t0("csr_linear_fwd")
-            Y = ops.csr_linear_fwd(crow, col, val, G, Wt, lp.b, out=self.ws(tag + ".y32", (B, lp.N)))
+            if tp is not None:
+                Y = ops.csr_linear_fwd_tc(tp[1], tp[0], B, G, lp.W16, lp.b, out=self.ws(tag + ".y32", (B, lp.N)))
+            else:
+                Y = ops.csr_linear_fwd(crow, col, val, G, Wt, lp.b, out=self.ws(tag + ".y32", (B, lp.N)))
             self._t1(ev)
             y16 = None
             fused_relu = False
@@ -366,8 +371,12 @@ class StepEngine:
             dY16 = ops.cast_bf16(dY, self.ws(tag + ".dY16", (B, lp.N), torch.bfloat16)) if want16 else None
             ops.colsum(dY, lp.gb)
         if lp.sparse:
-            cptr, ridx, cval, G = csc
-            ops.csr_linear_bwd_w(cptr, ridx, cval, B, G, dY, lp.gW)
+            if csc[0] == "tc":
+                _, tp, G = csc
+                ops.csr_linear_bwd_w_tc(tp[1], tp[0], B, G, dY16, lp.gW)
+            else:
+                _, cptr, ridx, cval, G = csc
+                ops.csr_linear_bwd_w(cptr, ridx, cval, B, G, dY, lp.gW)
             return None
         dX = self.ws(tag + ".dX", (B, lp.K)) if need_dx else None
         if self._tc(lp.K, lp.N):
@@ -445,9 +454,17 @@ class StepEngine:
         # ---------------- forward ----------------
         caches = {}
         x32 = x16 = None
+        # tensor-pipe SpMM (tile densified in smem) above the density where it beats the gather kernel
+        use_tc_spmm = (bf and self.spmm_tc and enc[0].N % 8 == 0 and G <= 65536 and
+                       nnz >= self.spmm_tc_min_density * B * G)
+        tp = None
+        if use_tc_spmm:
+            tp = ops.csr_tile_ptr(crow, col, val, G, nnz, self.ws("tp64", (B * ((G + 63) // 64 + 1),), torch.int32),
+                                  self.ws("packed", ((nnz + 3) // 4 * 4 + 4,), torch.int32))
         for j, lp in enumerate(enc):
             x32, x16, caches[("enc", j)] = self._layer_fwd(f"enc{j}", lp, x32, x16, B,
-                                                            csr=(crow, col, val, G) if j == 0 else None, masks=masks)
+                                                            csr=(crow, col, val, G, tp) if j == 0 else None,
+                                                            masks=masks)
         hidden = []
         for j, lp in enumerate(self.vaeenc_plan):
             x32, x16, caches[("venc", j)] = self._layer_fwd(f"venc{j}", lp, x32, x16, B, masks=masks)
@@ -555,13 +572,18 @@ class StepEngine:
                 if hidden[i][0] == "venc" and hidden[i][1] == j:
                     ops.axpy(d, d_hidden[i], -1.0)
             d = self._layer_bwd(f"venc{j}", self.vaeenc_plan[j], caches[("venc", j)], d, B)
-        cptr, ridx, cval = ops.csr_transpose(crow, col, val, G, nnz, self.ws("cptr", (G + 1,), torch.int32),
-                                             self.ws("ridx", (max(nnz, 1),), torch.int32),
-                                             self.ws("cval", (max(nnz, 1),)), self.ws("cursor", (G + 1,), torch.int32))
+        if use_tc_spmm:
+            csc = ("tc", tp, G)
+        else:
+            cptr, ridx, cval = ops.csr_transpose(crow, col, val, G, nnz, self.ws("cptr", (G + 1,), torch.int32),
+                                                 self.ws("ridx", (max(nnz, 1),), torch.int32),
+                                                 self.ws("cval", (max(nnz, 1),)),
+                                                 self.ws("cursor", (G + 1,), torch.int32))
+            csc = ("gather", cptr, ridx, cval, G)
         for j in reversed(range(len(enc))):
             ev = self._t0("csr_linear_bwd_w+bn") if j == 0 else None
             d = self._layer_bwd(f"enc{j}", enc[j], caches[("enc", j)], d, B, need_dx=(j > 0),
-                                csc=(cptr, ridx, cval, G) if j == 0 else None)
+                                csc=csc if j == 0 else None)
             self._t1(ev)
 
         # ---------------- grad norms, clip, Adam ----------------
@@ -617,8 +639,8 @@ class StepEngine:
         sc = torch.zeros(4, dtype=torch.float64, device=self.device)
         x32 = x16 = None
         for j, lp in enumerate(enc):
-            x32, x16, _ = self._layer_fwd(f"enc{j}", lp, x32, x16, B, csr=(crow, col, val, G) if j == 0 else None,
-                                          training=False)
+            x32, x16, _ = self._layer_fwd(f"enc{j}", lp, x32, x16, B,
+                                          csr=(crow, col, val, G, None) if j == 0 else None, training=False)
         for j, lp in enumerate(self.vaeenc_plan):
             x32, x16, _ = self._layer_fwd(f"venc{j}", lp, x32, x16, B, training=False)
         ML = self.ws("ML", (B, 2 * Z))

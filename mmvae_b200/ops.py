@@ -88,6 +88,43 @@ def csr_linear_bwd_w(cptr, ridx, cval, B: int, G: int, dY, out):
     return out
 
 
+def csr_tile_ptr(crow, col, val, G: int, nnz: int, tp=None, packed=None):
+    """(tile_ptr int32 [G/64+1, B] window-major, packed uint32-as-int32 [nnz padded]) for the tensor-pipe SpMM"""
+    B = crow.numel() - 1
+    fn = lib().cmmvae_csr_tile_ptr_bytes
+    fn.restype = _c.c_size_t
+    n = int(fn(B, G)) // 4
+    fp = lib().cmmvae_csr_packed_bytes
+    fp.restype = _c.c_size_t
+    m = int(fp(_c.c_longlong(nnz))) // 4
+    if tp is None:
+        tp = torch.empty(n, dtype=torch.int32, device=crow.device)
+    if packed is None:
+        packed = torch.empty(m, dtype=torch.int32, device=crow.device)
+    assert tp.numel() >= n and packed.numel() >= m
+    _check(lib().cmmvae_csr_tile_ptr(_ptr(crow), _ptr(col), _ptr(val), B, G, _c.c_longlong(nnz), _ptr(tp),
+                                     _ptr(packed), _stream()), "csr_tile_ptr")
+    return tp, packed
+
+
+def csr_linear_fwd_tc(packed, tile_ptr, B: int, G: int, Wt16, bias, out=None):
+    H = Wt16.shape[1]
+    assert Wt16.dtype == torch.bfloat16 and Wt16.is_contiguous() and Wt16.shape[0] == G
+    if out is None:
+        out = torch.empty(B, H, device=Wt16.device, dtype=torch.float32)
+    _check(lib().cmmvae_csr_linear_fwd_tc(_ptr(packed), _ptr(tile_ptr), B, G, H, _ptr(Wt16), _ptr(bias),
+                                          _ptr(out), _stream()), "csr_linear_fwd_tc")
+    return out
+
+
+def csr_linear_bwd_w_tc(packed, tile_ptr, B: int, G: int, dY16, out):
+    H = dY16.shape[1]
+    assert dY16.dtype == torch.bfloat16 and dY16.is_contiguous() and out.is_contiguous() and out.shape == (G, H)
+    _check(lib().cmmvae_csr_linear_bwd_w_tc(_ptr(packed), _ptr(tile_ptr), B, G, H, _ptr(dY16), _ptr(out),
+                                            _stream()), "csr_linear_bwd_w_tc")
+    return out
+
+
 def mse_relu_csr(logits, G: int, crow, col, val, write_xhat: bool, dl32, dl16, loss_sum):
     B = logits.shape[0]
     ldd = (dl32 if dl32 is not None else dl16).stride(0) if (dl32 is not None or dl16 is not None) else 0

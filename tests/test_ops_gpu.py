@@ -310,3 +310,40 @@ def test_decoder_mse_fused(ops, B, G, H, density):
     # exact gene masking: dlogits is exactly 0 wherever logits <= 0 and x == 0
     dead = (logits.detach() < -1e-3) & (x == 0)
     assert torch.all(dl16[:, :G][dead] == 0)
+
+
+@pytest.mark.parametrize("B,G,H,density", [(24, 264, 64, 0.1), (300, 3000, 512, 0.05), (130, 1000, 1024, 0.2),
+                                            (1024, 6053, 1024, 0.05), (64, 777, 256, 0.5)])
+def test_csr_linear_tc_fwd_bwd(ops, B, G, H, density):
+    """tensor-pipe SpMM (tile densified in smem): forward and weight gradient against the oracle with
+    x rounded to bf16 (the staged operand precision); exact zeros for absent genes; pointer table exact."""
+    crow, col, val = O.synth_csr(B, G, density, seed=21)
+    g = torch.Generator().manual_seed(2)
+    Wt16 = (torch.randn(G, H, generator=g) * 0.05).bfloat16()
+    b = torch.randn(H, generator=g) * 0.1
+    crow_d, col_d, val_d = dev(crow), dev(col), dev(val)
+    nnz = int(crow[-1])
+    tp, packed = ops.csr_tile_ptr(crow_d, col_d, val_d, G, nnz)
+    ntp = (G + 63) // 64 + 1
+    tp_c = tp.cpu().numpy()[:ntp * B].reshape(ntp, B)
+    for r in (0, B // 2, B - 1):   # bit-exact pointer table (lower bounds of 64-gene windows)
+        cols = col[crow[r]:crow[r + 1]]
+        want = crow[r] + np.searchsorted(cols, np.arange(ntp) * 64, side="left")
+        assert np.array_equal(tp_c[:, r], want)
+    pk = packed.cpu().numpy().view(np.uint32)[:nnz]   # bit-exact gene ids, bf16-rounded values
+    assert np.array_equal(pk & 0xFFFF, col.astype(np.uint32))
+    assert np.array_equal((pk >> 16).astype(np.uint16),
+                          torch.from_numpy(val).bfloat16().view(torch.int16).numpy().view(np.uint16))
+    val16 = torch.from_numpy(val).bfloat16().float().numpy()
+    ref = O.csr_linear(crow, col, val16, Wt16.float().t(), b)
+    y = ops.csr_linear_fwd_tc(packed, tp, B, G, Wt16.cuda(), b.cuda())
+    assert rel(y, ref) < 2e-5
+    dY16 = torch.randn(B, H, generator=g).bfloat16()
+    dense16 = O.csr_to_dense(crow, col, val16, G)
+    want_dw = dense16.t() @ dY16.float()
+    dWt = torch.full((G, H), 5.0).cuda()
+    ops.csr_linear_bwd_w_tc(packed, tp, B, G, dY16.cuda(), dWt)
+    assert rel(dWt, want_dw) < 2e-5
+    absent = (dense16 != 0).sum(0) == 0
+    if absent.any():
+        assert torch.all(dWt.cpu()[absent] == 0)
