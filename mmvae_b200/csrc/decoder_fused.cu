@@ -8,7 +8,7 @@
 //
 // Persistent kernel, one CTA per SM, 128 x 256 output tiles, static round-robin tile order with the
 // cell-block index fastest (so CTAs running concurrently share the same Wout tiles in L2).
-//   warp 0      TMA producer (4-stage ring of 128x64 h tiles + 256x64 Wout tiles, 128B swizzle)
+//   warp 0      TMA producer (3-stage ring of 128x64 h tiles + 256x64 Wout tiles, 128B swizzle)
 //   warp 1      tcgen05.mma issuer; two 256-column TMEM accumulators ping-pong with the epilogue
 //   warps 2..5  epilogue: thread = cell.  The cell's CSR entries inside the gene window are located
 //               through a per-(cell, gene-tile) pointer table (built once per batch by
@@ -21,8 +21,8 @@ namespace cmmvae {
 
 using namespace tc;
 
-constexpr int DBM = 128, DBN = 256, DBK = 64, DSTAGES = 4;
-constexpr int DCAP = 24;  // CSR entries per (cell, gene tile) staged in smem; the rest stream from global
+constexpr int DBM = 128, DBN = 256, DBK = 64, DSTAGES = 3;
+constexpr int DCAP = 48;  // CSR entries per (cell, gene tile) staged in smem; the rest stream from global
 constexpr int kDecThreads = 192;
 
 struct DecSmem {

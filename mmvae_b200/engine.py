@@ -26,6 +26,7 @@ from typing import Dict, List, Optional
 import torch
 import torch.nn as nn
 
+from . import dp
 from . import layers as L
 from . import ops
 
@@ -427,9 +428,11 @@ class StepEngine:
         return d
 
     # ----------------------------------------------------------------------------------------- step
-    def _allreduce(self, group: FlatGroup):
+    def _allreduce(self, group: FlatGroup, lo: int = 0, hi: Optional[int] = None, async_op: bool = False):
+        """SUM all-reduce of (a slice of) a group's flat gradient buffer; mean is folded into clip/Adam"""
         if self.world > 1:
-            torch.distributed.all_reduce(group.g)
+            return dp.allreduce_sum_(group.g[lo:hi if hi is not None else group.n], async_op=async_op)
+        return None
 
     def train_step(self, expert_id: str, crow, col, val, nnz: int, kl_weight: float, eps=None,
                    labels: Optional[Dict[str, torch.Tensor]] = None, masks=None):
@@ -440,8 +443,7 @@ class StepEngine:
         B = crow.numel() - 1
         G = enc[0].K
         Z = self.Z
-        self.world = torch.distributed.get_world_size() if (
-            torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
+        self.world = dp.world_size()
         gscale = 1.0 / self.world
         bf = self.precision == "bf16"
         n_adv = min(len(self.adv), self.n_hidden)   # zip(hidden, adversarials) truncates (cmmvae_model.py:67-70)
@@ -539,12 +541,18 @@ class StepEngine:
             ops.gemm(dl, 1, h16, 1, G, H1, B, C32=out.gW)                 # dWout = dlogits^T h
             self._t1(ev)
             ops.colsum(dl, out.gb, M=B, N=G)
+            # the output layer's gradient (half of the expert group) is final: start exchanging it now so
+            # the transfer overlaps the rest of the backward pass
+            o_out = gexp.offset[id(out.lin.weight)]
+            pending = [self._allreduce(gexp, o_out, None, async_op=True)]
             ev = self._t0("dh_gemm")
             ops.gemm(dl, 0, out.W16, 1, B, H1, G, C32=dh)                 # dh = dlogits Wout
             self._t1(ev)
         else:
             ops.gemm(dl, 1, h32, 1, G, H1, B, C32=out.gW, use_tc=False)
             ops.colsum(dl, out.gb)
+            o_out = gexp.offset[id(out.lin.weight)]
+            pending = [self._allreduce(gexp, o_out, None, async_op=True)]
             ops.gemm(dl, 0, out.W32, 1, B, H1, G, C32=dh, use_tc=False)
         d = dh
         for j in reversed(range(len(dec) - 1)):
@@ -587,8 +595,11 @@ class StepEngine:
             self._t1(ev)
 
         # ---------------- grad norms, clip, Adam ----------------
-        self._allreduce(gvae)
-        self._allreduce(gexp)
+        pending.append(self._allreduce(gexp, 0, o_out, async_op=True))
+        pending.append(self._allreduce(gvae, async_op=True))
+        for w in pending:
+            if w is not None:
+                w.wait()
         ev = self._t0("norm+clip_adam")
         gvae.grad_norm_sq(s_norm(0))
         gexp.grad_norm_sq(s_norm(1))

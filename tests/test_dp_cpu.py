@@ -1,0 +1,69 @@
+"""N>1 host logic on CPU: two gloo ranks.  DDP semantics of the fused step = SUM all-reduce of the flat
+gradient buffers + 1/world folded into clip/Adam: must equal averaging the per-rank gradients, clipping
+the average and stepping (what Lightning DDP gives the reference)."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mmvae_b200 import dp
+from oracle import cmmvae_oracle as O
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(100 + rank)
+        n = 1000
+        p0 = torch.randn(n, generator=torch.Generator().manual_seed(7))
+        grad = torch.randn(n, generator=g) * 5
+        flat = grad.clone()
+        # chunked reduction (what overlapping the exchange with backward does) == one-shot reduction
+        for lo, hi in dp.chunk_bounds(n, [300, 300, 640]):
+            dp.allreduce_sum_(flat[lo:hi])
+        gathered = [torch.empty(n) for _ in range(world)]
+        dist.all_gather(gathered, grad)
+        mean = torch.stack(gathered).mean(0)
+        assert torch.allclose(flat / world, mean, atol=1e-6)
+        # norm of the averaged gradient from the summed buffer
+        assert dp.reduced_norm(float(flat.double().pow(2).sum())) == pytest.approx(float(mean.norm()), rel=1e-6)
+        # fused semantics: coef from the averaged norm, gradient scale 1/world -> same update as clip(mean)+Adam
+        total = float(flat.norm()) / world
+        coef = min(1.0, 10.0 / (total + 1e-6))
+        mine, _, _ = O.adam_update(p0, flat * (coef / world), torch.zeros(n), torch.zeros(n), 1, 5e-3, 1e-6,
+                                   (0.9, 0.999), 1e-8)
+        clipped, _ = O.clip_by_norm([mean], 10.0)
+        ref, _, _ = O.adam_update(p0, clipped[0], torch.zeros(n), torch.zeros(n), 1, 5e-3, 1e-6, (0.9, 0.999), 1e-8)
+        assert torch.allclose(mine, ref, atol=1e-7)
+        # every rank picks the same species for every step
+        sched = [dp.species_for_step(t, ["human", "mouse"], seed=3) for t in range(50)]
+        objs = [None] * world
+        dist.all_gather_object(objs, sched)
+        assert all(o == sched for o in objs) and {"human", "mouse"} <= set(sched)
+        out.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        out.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_dp_semantics_two_gloo_ranks():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_single_process_helpers():
+    assert dp.world_size() == 1 and dp.rank() == 0
+    assert dp.allreduce_sum_(torch.ones(3)) is None
+    assert dp.chunk_bounds(10, [0, 4, 4, 10, 12]) == [(0, 4), (4, 10)]
