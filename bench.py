@@ -231,6 +231,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout clean: the only stdout line is the JSON result
         torch.distributed.init_process_group("nccl", device_id=dev)
     from mmvae_b200 import layers as L, ops
     import pandas as pd

@@ -24,7 +24,8 @@ def _worker(rank, world, port, tmp, out):
         from mmvae_b200 import layers as L
         L.set_precision("fp32")
         gc = GoldenCase("core_human")
-        model = build_b200_model(gc, os.path.join(tmp, str(rank)))
+        from mmvae_b200.modules.base import KLAnnealingFn
+        model = build_b200_model(gc, os.path.join(tmp, str(rank)), kl_fn=KLAnnealingFn(0.5))
         model.load_state_dict({f"module.{k}": v for k, v in gc.state("init").items()})
         model.cuda().train()
         model.configure_optimizers()
