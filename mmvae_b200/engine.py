@@ -36,33 +36,75 @@ def _ceil(a: int, b: int) -> int:
 
 
 class FlatGroup:
-    """One optimizer group (``experts/<id>``, ``vae`` or ``adversarials/<i>``) as flat buffers."""
+    """One optimizer group (``experts/<id>``, ``vae`` or ``adversarials/<i>``) as flat buffers.
+
+    Layout: ``[segment 0 | segment 1 | ... | tail]``.  With one process the distinction is moot (one range).
+    With ``world`` > 1 ranks each *segment* (the big weight matrices) is ZeRO-1 sharded: gradients are
+    reduce-scattered, every rank runs clip+Adam on its 1/world shard only (Adam state exists only for the
+    shard) and the refreshed bf16 shadow is all-gathered; the fp32 master copy of a segment is current
+    only inside the owner's shard until ``sync_master()``.  The *tail* (biases, BatchNorm affine, small
+    matrices) is replicated: all-reduced gradients, identical Adam on every rank."""
 
     ALIGN = 64
 
     def __init__(self, name: str, chains: List[List[tuple]], device, lr=5e-3, weight_decay=1e-6,
-                 betas=(0.9, 0.999), eps=1e-8):
-        """``chains``: list of chains; a chain is a list of ``(param, transposed)`` stored back to back
-        (so e.g. mean/var head weights form one contiguous matrix)."""
+                 betas=(0.9, 0.999), eps=1e-8, segments: Optional[List[List[List[tuple]]]] = None):
+        """``chains`` (tail) / ``segments[i]`` (sharded when world > 1): lists of chains; a chain is a list
+        of ``(param, transposed)`` stored back to back (e.g. mean/var head weights = one matrix)."""
         self.name, self.lr, self.wd, self.betas, self.eps = name, lr, weight_decay, betas, eps
+        self.world, self.rank = dp.world_size(), dp.rank()
         self.params: List[nn.Parameter] = []
         self.offset: Dict[int, int] = {}
         self.transposed: Dict[int, bool] = {}
+        segments = segments or []
+        seg_align = self.world * 256
         total = 0
-        for chain in chains:
-            total = _ceil(total, self.ALIGN)
-            for p, tr in chain:
-                self.params.append(p)
-                self.offset[id(p)] = total
-                self.transposed[id(p)] = tr
-                total += p.numel()
+        self.seg_bounds: List[tuple] = []
+
+        def place(chain_list):
+            nonlocal total
+            for chain in chain_list:
+                total = _ceil(total, self.ALIGN)
+                for p, tr in chain:
+                    self.params.append(p)
+                    self.offset[id(p)] = total
+                    self.transposed[id(p)] = tr
+                    total += p.numel()
+
+        for seg in segments:
+            total = _ceil(total, seg_align)
+            lo = total
+            place(seg)
+            total = _ceil(total, seg_align)
+            self.seg_bounds.append((lo, total))
+        self.tail_lo = total
+        place(chains)
         self.n = _ceil(max(total, 4), 4)
+        self.sharded = self.world > 1 and len(self.seg_bounds) > 0
+        # ranges the optimizer walks: (flat lo, flat hi, grad buffer, offset into m/v)
         self.p = torch.zeros(self.n, device=device, dtype=torch.float32)
         self.g = torch.zeros(self.n, device=device, dtype=torch.float32)
-        self.m = torch.zeros(self.n, device=device, dtype=torch.float32)
-        self.v = torch.zeros(self.n, device=device, dtype=torch.float32)
         self.p16 = torch.zeros(self.n, device=device, dtype=torch.bfloat16)
+        self.gs: List[torch.Tensor] = []       # reduce-scatter outputs (one per segment)
+        self.ranges: List[tuple] = []
+        mv = 0
+        if self.sharded:
+            for lo, hi in self.seg_bounds:
+                ns = (hi - lo) // self.world
+                gs = torch.zeros(ns, device=device, dtype=torch.float32)
+                self.gs.append(gs)
+                own = lo + self.rank * ns
+                self.ranges.append((own, own + ns, gs, mv))
+                mv += ns
+            self.ranges.append((self.tail_lo, self.n, self.g[self.tail_lo:self.n], mv))
+            mv += self.n - self.tail_lo
+        else:
+            self.ranges.append((0, self.n, self.g, 0))
+            mv = self.n
+        self.m = torch.zeros(mv, device=device, dtype=torch.float32)
+        self.v = torch.zeros(mv, device=device, dtype=torch.float32)
         self.step_count = 0
+        self._ag_pending: List = []
         for p in self.params:
             phys = self.phys(p)
             src = p.data.to(device)
@@ -85,14 +127,58 @@ class FlatGroup:
     def refresh_shadow(self):
         ops.cast_bf16(self.p, self.p16)
 
+    # ---- gradient exchange (world > 1) ----
+    def exchange_segment_async(self, i: int):
+        """reduce-scatter (SUM) of segment i's gradient into this rank's shard buffer"""
+        if not self.sharded:
+            return None
+        lo, hi = self.seg_bounds[i]
+        return torch.distributed.reduce_scatter_tensor(self.gs[i], self.g[lo:hi], async_op=True)
+
+    def exchange_rest_async(self):
+        """all-reduce (SUM) of everything that is not sharded"""
+        if self.world == 1:
+            return None
+        lo = self.tail_lo if self.sharded else 0
+        return dp.allreduce_sum_(self.g[lo:self.n], async_op=True)
+
     def grad_norm_sq(self, out: torch.Tensor):
-        """out (double[1], pre-zeroed) += ||g||^2 over the whole group (padding is zero)."""
-        ops.sumsq(self.g, out)
+        """out (double[1], pre-zeroed) += || sum_r g_r ||^2 over the whole group (padding is zero)."""
+        if self.sharded:
+            for gs in self.gs:
+                ops.sumsq(gs, out)
+            torch.distributed.all_reduce(out)
+            ops.sumsq(self.g[self.tail_lo:self.n], out)
+        else:
+            ops.sumsq(self.g, out)
 
     def clip_adam(self, norm_sq: torch.Tensor, max_norm: Optional[float], grad_scale: float = 1.0):
         self.step_count += 1
-        ops.clip_adam(self.p, self.g, self.m, self.v, self.p16, norm_sq, max_norm or 0.0, grad_scale, self.lr,
-                      self.betas[0], self.betas[1], self.eps, self.wd, self.step_count)
+        for lo, hi, g, mv in self.ranges:
+            n = hi - lo
+            ops.clip_adam(self.p[lo:hi], g, self.m[mv:mv + n], self.v[mv:mv + n], self.p16[lo:hi], norm_sq,
+                          max_norm or 0.0, grad_scale, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                          self.step_count)
+        if self.sharded:   # publish the refreshed bf16 shards; consumers wait just before they read them
+            self._ag_pending = []
+            for (lo, hi), (own_lo, own_hi, _, _) in zip(self.seg_bounds, self.ranges):
+                self._ag_pending.append(torch.distributed.all_gather_into_tensor(
+                    self.p16[lo:hi], self.p16[own_lo:own_hi], async_op=True))
+
+    def wait_shadow(self, i: Optional[int] = None):
+        """make the current stream wait for the all-gather of segment i's bf16 shadow (all if None)"""
+        for j, w in enumerate(self._ag_pending):
+            if w is not None and (i is None or i == j):
+                w.wait()
+                self._ag_pending[j] = None
+
+    def sync_master(self):
+        """all-gather the fp32 master copy of the sharded segments (before state_dict / fp32 evaluation)"""
+        if not self.sharded:
+            return
+        self.wait_shadow()
+        for (lo, hi), (own_lo, own_hi, _, _) in zip(self.seg_bounds, self.ranges):
+            torch.distributed.all_gather_into_tensor(self.p[lo:hi], self.p[own_lo:own_hi])
 
 
 class FlatAdam(torch.optim.Optimizer):
@@ -110,6 +196,8 @@ class FlatAdam(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None):
+        if self.flat.world > 1:
+            raise NotImplementedError("with torch.distributed the exchange + step run inside training_step")
         ns = torch.zeros(1, dtype=torch.float64, device=self.flat.p.device)
         self.flat.grad_norm_sq(ns)
         self.flat.clip_adam(ns, self._max_norm)
@@ -168,10 +256,13 @@ def _plan_block(block, group: FlatGroup, sparse_first=False) -> List[LayerPlan]:
     return plans
 
 
-def _block_chains(block, sparse_first=False):
+def _block_chains(block, sparse_first=False, kind="all"):
+    """chains of a block; kind: "all", "matrix" (>= 2-D params) or "vector" (1-D params)"""
     chains = []
     for i, layer in enumerate(block.fc_layers):
         for name, p in layer.named_parameters():
+            if kind == "matrix" and p.dim() < 2 or kind == "vector" and p.dim() >= 2:
+                continue
             chains.append([(p, sparse_first and i == 0 and name == "lin.weight")])
     return chains
 
@@ -211,8 +302,12 @@ class StepEngine:
         self.enc_plan: Dict[str, List[LayerPlan]] = {}
         self.dec_plan: Dict[str, List[LayerPlan]] = {}
         for eid, expert in module.experts.items():
-            chains = _block_chains(expert.encoder, sparse_first=True) + _block_chains(expert.decoder)
-            g = self.groups[f"experts/{eid}"] = FlatGroup(f"experts/{eid}", chains, dev)
+            # big matrices: segment 0 = everything but the output layer, segment 1 = the output layer (its
+            # gradient is final first, so its exchange overlaps the rest of the backward pass); vectors: tail
+            mats = _block_chains(expert.encoder, sparse_first=True, kind="matrix") + \
+                _block_chains(expert.decoder, kind="matrix")
+            vecs = _block_chains(expert.encoder, kind="vector") + _block_chains(expert.decoder, kind="vector")
+            g = self.groups[f"experts/{eid}"] = FlatGroup(f"experts/{eid}", vecs, dev, segments=[mats[:-1], mats[-1:]])
             self.enc_plan[eid] = _plan_block(expert.encoder, g, sparse_first=True)
             self.dec_plan[eid] = _plan_block(expert.decoder, g)
             last = self.dec_plan[eid][-1]
@@ -428,12 +523,6 @@ class StepEngine:
         return d
 
     # ----------------------------------------------------------------------------------------- step
-    def _allreduce(self, group: FlatGroup, lo: int = 0, hi: Optional[int] = None, async_op: bool = False):
-        """SUM all-reduce of (a slice of) a group's flat gradient buffer; mean is folded into clip/Adam"""
-        if self.world > 1:
-            return dp.allreduce_sum_(group.g[lo:hi if hi is not None else group.n], async_op=async_op)
-        return None
-
     def train_step(self, expert_id: str, crow, col, val, nnz: int, kl_weight: float, eps=None,
                    labels: Optional[Dict[str, torch.Tensor]] = None, masks=None):
         """One optimisation step on a CSR batch already resident on the device.
@@ -454,6 +543,8 @@ class StepEngine:
         ce_base = 4 + 2 + 2 * n_adv
 
         # ---------------- forward ----------------
+        gexp, gvae = self.groups[f"experts/{expert_id}"], self.groups["vae"]
+        gexp.wait_shadow(0)     # bf16 shards published by the previous step's optimizer (world > 1)
         caches = {}
         x32 = x16 = None
         # tensor-pipe SpMM (tile densified in smem) above the density where it beats the gather kernel
@@ -492,6 +583,7 @@ class StepEngine:
             x32, x16, caches[("dec", j)] = self._layer_fwd(f"dec{j}", lp, x32, x16, B, masks=masks)
         h32, h16 = x32, x16
         out = dec[-1]
+        gexp.wait_shadow(1)
         fused = self._tc(out.K) and bf
         if fused:
             ldd = _ceil(G, 64)
@@ -519,7 +611,9 @@ class StepEngine:
                 slot += len(ap.conditions)
                 dla = self._adv_loss(f"adv{i}", ap, logits_a, labels, 1.0, B, slots)
                 self._adv_bwd(f"adv{i}", ap, code, ac, dla, B, need_dx=False)
-                self._allreduce(ap.group)
+                w = ap.group.exchange_rest_async()
+                if w is not None:
+                    w.wait()
                 ap.group.grad_norm_sq(s_norm(2 + i))
                 ap.group.clip_adam(s_norm(2 + i), self.clip.get("adversarial"), gscale)
             for i in range(n_adv):
@@ -533,7 +627,6 @@ class StepEngine:
                 ap.group.grad_norm_sq(s_norm(2 + n_adv + i))   # "generator_i" norm: logged, never applied
 
         # ---------------- backward ----------------
-        gexp, gvae = self.groups[f"experts/{expert_id}"], self.groups["vae"]
         H1 = out.K
         dh = self.ws("dh", (B, H1))
         if fused:
@@ -543,16 +636,14 @@ class StepEngine:
             ops.colsum(dl, out.gb, M=B, N=G)
             # the output layer's gradient (half of the expert group) is final: start exchanging it now so
             # the transfer overlaps the rest of the backward pass
-            o_out = gexp.offset[id(out.lin.weight)]
-            pending = [self._allreduce(gexp, o_out, None, async_op=True)]
+            pending = [gexp.exchange_segment_async(1)]
             ev = self._t0("dh_gemm")
             ops.gemm(dl, 0, out.W16, 1, B, H1, G, C32=dh)                 # dh = dlogits Wout
             self._t1(ev)
         else:
             ops.gemm(dl, 1, h32, 1, G, H1, B, C32=out.gW, use_tc=False)
             ops.colsum(dl, out.gb)
-            o_out = gexp.offset[id(out.lin.weight)]
-            pending = [self._allreduce(gexp, o_out, None, async_op=True)]
+            pending = [gexp.exchange_segment_async(1)]
             ops.gemm(dl, 0, out.W32, 1, B, H1, G, C32=dh, use_tc=False)
         d = dh
         for j in reversed(range(len(dec) - 1)):
@@ -595,8 +686,9 @@ class StepEngine:
             self._t1(ev)
 
         # ---------------- grad norms, clip, Adam ----------------
-        pending.append(self._allreduce(gexp, 0, o_out, async_op=True))
-        pending.append(self._allreduce(gvae, async_op=True))
+        pending.append(gexp.exchange_segment_async(0))
+        pending.append(gexp.exchange_rest_async())
+        pending.append(gvae.exchange_rest_async())
         for w in pending:
             if w is not None:
                 w.wait()
@@ -647,6 +739,10 @@ class StepEngine:
         enc, dec = self.enc_plan[expert_id], self.dec_plan[expert_id]
         B, G, Z = crow.numel() - 1, enc[0].K, self.Z
         bf = self.precision == "bf16"
+        if bf:
+            self.groups[f"experts/{expert_id}"].wait_shadow()
+        else:
+            self.groups[f"experts/{expert_id}"].sync_master()
         sc = torch.zeros(4, dtype=torch.float64, device=self.device)
         x32 = x16 = None
         for j, lp in enumerate(enc):

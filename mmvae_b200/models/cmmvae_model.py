@@ -97,6 +97,12 @@ class CMMVAEModel(BaseModel):
 
         return resolve(self.optimizer_map)
 
+    def state_dict(self, *args, **kwargs):
+        if self._engine is not None:     # ZeRO-1 sharded fp32 master copies are gathered before export
+            for g in self._engine.groups.values():
+                g.sync_master()
+        return super().state_dict(*args, **kwargs)
+
     # ------------------------------------------------------------------------------------- steps
     def _labels(self, metadata: pd.DataFrame, device):
         """int64 class ids per condition: row index of each value in the human csv (class-level

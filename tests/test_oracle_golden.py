@@ -107,4 +107,4 @@ def test_oracle_fast_csr_path_agrees():
         g1, = torch.autograd.grad(y1.square().sum(), W)
     finally:
         O.FAST_CSR = False
-    assert torch.allclose(y0, y1, atol=1e-5) and torch.allclose(g0, g1, atol=1e-4)
+    assert torch.allclose(y0, y1, rtol=1e-5, atol=1e-5) and torch.allclose(g0, g1, rtol=1e-5, atol=1e-4)
