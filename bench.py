@@ -304,9 +304,13 @@ def main():
         s, (crow, col, val), ev = staged
         torch.cuda.current_stream().wait_event(ev)
         x = torch.sparse_csr_tensor(crow, col, val, size=(B, species[s]))
-        model.training_step((x, metas[t % NB], s), t)   # logs python floats: D2H read of the step's scalars
-        return float(model.logged_metrics[f"loss/training/{s}"])
+        # every step ends with a D2H copy of its scalar block (loss, KL, norms) into pinned memory; with
+        # sync_logging off the host reads it one step later, so the copy never stalls the launch queue
+        model.training_step((x, metas[t % NB], s), t)
+        v = model.logged_metrics.get(f"loss/training/{s}")
+        return float(v) if v is not None else None
 
+    model.sync_logging = False
     nxt = stage(0)
     for t in range(max(args.warmup, 3)):
         cur, nxt = nxt, stage(t + 1)
@@ -318,6 +322,7 @@ def main():
     for t in range(args.steps):
         cur, nxt = nxt, stage(t + 1 + max(args.warmup, 3))
         loss = api_step(t, cur)
+    model.flush_logs()
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)

@@ -66,7 +66,7 @@ int cmmvae_csr_tile_ptr(const int32_t* crow, const int32_t* col, const float* va
 int cmmvae_csr_linear_fwd_tc(const void* packed, const int32_t* tile_ptr, int B, int G, int H,
                              const void* Wt_bf16, const float* bias, float* Y, void* stream);
 int cmmvae_csr_linear_bwd_w_tc(const void* packed, const int32_t* tile_ptr, int B, int G, int H,
-                               const void* dY_bf16, float* dWt, void* stream);
+                               const void* dY_bf16, float* dWt, double* sumsq_out, void* stream);
 
 /* ---- K2/K3: BatchNorm1d(momentum, eps) + ReLU + Dropout, components.py:279-288 ------------- */
 /* column statistics of Y[B,H]: mean[H], rstd[H] = 1/sqrt(biased var + eps); updates running
@@ -102,10 +102,12 @@ int cmmvae_gemm_f32(const float* A, int lda, int transA, const float* Bm, int ld
                     int M, int N, int K, const float* bias, int relu, int accumulate,
                     float* C_f32, void* C_bf16, int ldc, void* stream);
 /* tcgen05/TMEM/TMA path: inputs bf16, fp32 accumulate.  Requires 16-byte aligned bases and
- * leading dimensions that are multiples of 8 elements; any M, N, K (TMA zero-fills edges). */
+ * leading dimensions that are multiples of 8 elements; any M, N, K (TMA zero-fills edges).
+ * sumsq_out (double[1], optional): += sum of squares of the stored C, so a weight-gradient GEMM also
+ * yields its contribution to the clip norm (log_gradient_norms, base_model.py:111-123). */
 int cmmvae_gemm_bf16_tc(const void* A, int lda, int transA, const void* Bm, int ldb, int transB,
                         int M, int N, int K, const float* bias, int relu, int accumulate,
-                        float* C_f32, void* C_bf16, int ldc, void* stream);
+                        float* C_f32, void* C_bf16, int ldc, double* sumsq_out, void* stream);
 /* column sums: out[N] (=|+=) sum_m X[m,n]  (bias gradients) */
 int cmmvae_colsum(const void* X, int x_dtype, int M, int N, int ldx, float* out, int accumulate, void* stream);
 
@@ -130,12 +132,14 @@ int cmmvae_mse_relu_csr(float* logits, int ldl, int B, int G, const int32_t* cro
 /* fused form: logits tile stays in TMEM; epilogue adds bias, applies ReLU, reduces the loss against
  * the CSR entries of the tile and emits dlogits bf16 [B,ldd]; xhat never reaches HBM.
  * h bf16 [B,H] (ldh), Wout bf16 [G,H] (ldw), bout f32 [G].  `workspace` (device, size from
- * cmmvae_decoder_mse_fused_workspace_bytes) receives the per-(cell, gene-tile) CSR pointer table.
+ * cmmvae_decoder_mse_fused_workspace_bytes) receives the per-(cell, 64-gene window) CSR pointer table when
+ * `tile_ptr` is NULL; pass the table built by cmmvae_csr_tile_ptr as `tile_ptr` to share it.
  * loss_sum (double[1]) is zeroed by the call. */
 size_t cmmvae_decoder_mse_fused_workspace_bytes(int B, int G);
 int cmmvae_decoder_mse_fused(const void* h, int ldh, const void* Wout, int ldw, const float* bout,
                              int B, int G, int H, const int32_t* crow, const int32_t* col, const float* val,
-                             void* dlogits_bf16, int ldd, double* loss_sum, void* workspace, void* stream);
+                             const int32_t* tile_ptr, void* dlogits_bf16, int ldd, double* loss_sum,
+                             void* workspace, void* stream);
 
 /* ---- K11: adversary heads, CrossEntropyLoss(reduction='sum') (cmmvae_model.py:54,85) --------
  * logits f32 [B,C] (ldl), labels int64[B]; loss_sum double[1] += ; dlogits = scale*(softmax-onehot). */

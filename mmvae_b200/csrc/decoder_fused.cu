@@ -7,70 +7,47 @@
 //   dlogits     = 2 (xhat - x) 1[logits > 0]
 //
 // Persistent kernel, one CTA per SM, 128 x 256 output tiles, static round-robin tile order with the
-// cell-block index fastest (so CTAs running concurrently share the same Wout tiles in L2).
-//   warp 0      TMA producer (3-stage ring of 128x64 h tiles + 256x64 Wout tiles, 128B swizzle)
-//   warp 1      tcgen05.mma issuer; two 256-column TMEM accumulators ping-pong with the epilogue
-//   warps 2..5  epilogue: thread = cell.  The cell's CSR entries inside the gene window are located
-//               through a per-(cell, gene-tile) pointer table (built once per batch by
-//               tile_ptr_kernel, bit-exact with crow/col) and staged in shared memory while the MMA
-//               runs; accumulator chunks go TMEM -> registers -> per-thread smem column, where the
-//               sparse entries are patched in, then out as bf16.
+// cell-block index fastest (so CTAs running concurrently share the same Wout tiles in L2).  576 threads:
+//   warp 0       TMA producer (4-stage ring of 128x64 h tiles + 256x64 Wout tiles, 128B swizzle)
+//   warp 1       tcgen05.mma issuer; two 256-column TMEM accumulators ping-pong with the epilogue
+//   warps 2..17  epilogue, 16 warps so that draining a tile takes less time than computing the next one:
+//                thread = (cell, 64-gene window).  The cell's CSR entries of the window are found through
+//                the per-(cell, 64-gene window) pointer table (window-major, shared with the tensor-pipe
+//                SpMM; bit-exact with crow/col) and prefetched into registers while the MMA runs;
+//                accumulator sub-chunks go TMEM -> registers -> a per-thread shared-memory column where
+//                the sparse entries are patched in, then out as bf16 (32 contiguous bytes per store pair).
 #include "tc.cuh"
 
 namespace cmmvae {
 
 using namespace tc;
 
-constexpr int DBM = 128, DBN = 256, DBK = 64, DSTAGES = 3;
-constexpr int DCAP = 48;  // CSR entries per (cell, gene tile) staged in smem; the rest stream from global
-constexpr int kDecThreads = 192;
+constexpr int DBM = 128, DBN = 256, DBK = 64, DSTAGES = 4;
+constexpr int kDecEpiWarps = 16;
+constexpr int kDecThreads = 64 + 32 * kDecEpiWarps;   // 576
+constexpr int DE = 8;   // CSR entries per (cell, window) prefetched into registers; the rest stream from global
 
 struct DecSmem {
   static constexpr int kABytes = DBM * DBK * 2;           // 16 KB
   static constexpr int kBBytes = DBN * DBK * 2;           // 32 KB
   static constexpr int kStageBytes = kABytes + kBBytes;   // 48 KB
-  static constexpr int kStageOff = 0;
-  static constexpr int kStagingOff = DSTAGES * kStageBytes;          // float [32][128]
-  static constexpr int kEntValOff = kStagingOff + 32 * 128 * 4;      // float [DCAP][128]
-  static constexpr int kEntColOff = kEntValOff + DCAP * 128 * 4;     // uint8 [DCAP][128]
-  static constexpr int kBiasOff = kEntColOff + DCAP * 128;           // float [256]
-  static constexpr int kBarOff = kBiasOff + DBN * 4;
-  static constexpr int kTotal = kBarOff + 256 + 1024;
+  static constexpr int kStagingOff = DSTAGES * kStageBytes;                 // float [16][512]
+  static constexpr int kBarOff = kStagingOff + 16 * 32 * kDecEpiWarps * 4;  // + 32 KB
+  static constexpr int kTotal = kBarOff + 256;
 };
 
 struct DecParams {
   int B, G, H;
   const float* bout;
-  const int32_t* crow;
   const int32_t* col;
   const float* val;
-  const int32_t* tile_ptr;  // [B][num_n + 1]
+  const int32_t* tp;   // [ntp][B] window-major pointer table (64-gene windows)
+  int ntp;
   __nv_bfloat16* dl;
   int ldd;
   double* loss_sum;
   int num_m, num_n;
 };
-
-// tile_ptr[b][t] = first CSR position of row b whose column is >= t * DBN   (t = 0..num_n)
-__global__ void tile_ptr_kernel(const int32_t* __restrict__ crow, const int32_t* __restrict__ col, int B, int num_n,
-                                int32_t* __restrict__ tp) {
-  const long long n = (long long)B * (num_n + 1);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(i / (num_n + 1)), t = (int)(i % (num_n + 1));
-    int lo = crow[b], hi = crow[b + 1];
-    const int key = t * DBN;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (col[mid] < key) lo = mid + 1; else hi = mid;
-    }
-    tp[i] = lo;
-  }
-}
-
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 
 __global__ void __launch_bounds__(kDecThreads, 1)
 decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW,
@@ -78,9 +55,6 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
   extern __shared__ __align__(1024) uint8_t smem[];   // 128B-swizzled tiles need 1024-byte alignment
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   float* staging = reinterpret_cast<float*>(smem + DecSmem::kStagingOff);
-  float* ent_val = reinterpret_cast<float*>(smem + DecSmem::kEntValOff);
-  uint8_t* ent_col = smem + DecSmem::kEntColOff;
-  float* s_bias = reinterpret_cast<float*>(smem + DecSmem::kBiasOff);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + DecSmem::kBarOff);
   uint64_t* empty_bar = full_bar + DSTAGES;
   uint64_t* tmem_full = empty_bar + DSTAGES;   // [2]
@@ -100,7 +74,7 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty[a], kDecEpiWarps);  // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -154,11 +128,43 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
       }
     }
   } else {
-    // ===== epilogue =====
-    const int q = warp & 3;
+    // ===== epilogue: thread = (cell row, 64-gene window) =====
+    const int e = warp - 2;                  // 0..15
+    const int q = warp & 3;                  // TMEM lane group this warp may read
+    const int w = e >> 2;                    // 64-gene window of the tile: consecutive warps cover all lane groups
     const int row = q * 32 + lane;           // TMEM lane == row inside the tile
-    const int et = threadIdx.x - 64;         // 0..127 among epilogue threads
+    const int et = e * 32 + lane;            // 0..511
+    float* st = staging + et;                // element j of this thread's column: st[j * 512]
+    constexpr int SS = 32 * kDecEpiWarps;
     double loss_acc = 0.0;
+    // CSR entries of (this thread's cell, this thread's window) for a tile, fetched one tile ahead so the
+    // two dependent L2 round trips (pointer table, then entries) hide behind the previous tile's drain
+    auto fetch = [&](int t, int& p0, int& cnt, int (&ecol)[DE], float (&eval)[DE]) {
+      p0 = 0;
+      int p1 = 0;
+      if (t < num_tiles) {
+        const int b = (t % p.num_m) * DBM + row;
+        const int g0 = (t / p.num_m) * DBN + w * 64;
+        const int win = g0 >> 6;
+        if (b < p.B && win < p.ntp - 1) {
+          p0 = __ldg(p.tp + (size_t)win * p.B + b);
+          p1 = __ldg(p.tp + (size_t)(win + 1) * p.B + b);
+        }
+        cnt = p1 - p0;
+#pragma unroll
+        for (int u = 0; u < DE; ++u) {
+          const bool ok = u < cnt;
+          ecol[u] = ok ? __ldg(p.col + p0 + u) - g0 : 1 << 20;
+          eval[u] = ok ? __ldg(p.val + p0 + u) : 0.f;
+        }
+      } else {
+        cnt = 0;
+      }
+    };
+    int p0, cnt, np0, ncnt;
+    int ecol[DE], necol[DE];
+    float eval[DE], neval[DE];
+    fetch(blockIdx.x, p0, cnt, ecol, eval);
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -167,72 +173,68 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
       const int m0 = m_blk * DBM, n0 = n_blk * DBN;
       const int b = m0 + row;
       const bool row_ok = b < p.B;
-
-      // bias tile -> smem (zero beyond G so padded columns give xhat = 0)
-      named_bar_sync(1, 128);
-      for (int j = et; j < DBN; j += 128) s_bias[j] = (n0 + j < p.G) ? __ldg(p.bout + n0 + j) : 0.f;
-      // this cell's CSR entries inside [n0, n0 + DBN): stage up to DCAP of them while the MMA runs
-      int p0 = 0, p1 = 0;
-      if (row_ok) {
-        const int32_t* tp = p.tile_ptr + (size_t)b * (p.num_n + 1) + n_blk;
-        p0 = __ldg(tp);
-        p1 = __ldg(tp + 1);
-      }
-      const int cnt = p1 - p0;
-      const int staged = min(cnt, DCAP);
-#pragma unroll 4
-      for (int k = 0; k < staged; ++k) {
-        ent_col[k * 128 + row] = (uint8_t)(__ldg(p.col + p0 + k) - n0);
-        ent_val[k * 128 + row] = __ldg(p.val + p0 + k);
-      }
-      named_bar_sync(1, 128);
+      const int g0 = n0 + w * 64;            // first gene of this thread's window
+      fetch(t + gridDim.x, np0, ncnt, necol, neval);
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       float part = 0.f;
-      int ek = 0;  // next entry of this row
 #pragma unroll 1
-      for (int c = 0; c < DBN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * DBN + c * 32), r);
-        tmem_ld_wait();
-        // dense part: xhat = relu(acc + bias); staged column-major per thread (conflict free)
+      for (int c = 0; c < 4; ++c) {          // four 16-column sub-chunks of the window
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * DBN + w * 64 + c * 16), r);
+        const int gc = g0 + c * 16;
+        float bias[16];
+        if (gc + 16 <= p.G) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float xh = fmaxf(__uint_as_float(r[j]) + s_bias[c * 32 + j], 0.f);
-          part = fmaf(xh, xh, part);
-          staging[j * 128 + row] = xh;
-        }
-        // sparse part: patch the entries of this 32-gene chunk
-        const int chunk_end = (c + 1) * 32;
-        while (ek < cnt) {
-          int cj;
-          float x;
-          if (ek < DCAP) {
-            cj = ent_col[ek * 128 + row];
-            x = ent_val[ek * 128 + row];
-          } else {
-            cj = __ldg(p.col + p0 + ek) - n0;
-            x = __ldg(p.val + p0 + ek);
+          for (int j = 0; j < 16; j += 2) {   // G is only guaranteed even-aligned here: 8-byte loads
+            const float2 t2 = __ldg(reinterpret_cast<const float2*>(p.bout + gc + j));
+            bias[j] = t2.x; bias[j + 1] = t2.y;
           }
-          if (cj >= chunk_end) break;
-          const int j = cj - c * 32;
-          const float xh = staging[j * 128 + row];
-          part += x * x - 2.f * x * xh;
-          staging[j * 128 + row] = xh > 0.f ? xh - x : 0.f;
-          ++ek;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) bias[j] = (gc + j < p.G) ? __ldg(p.bout + gc + j) : 0.f;
+        }
+        tmem_ld_wait();
+        // dense part: xhat = relu(acc + bias), staged in this thread's smem column (conflict free)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float xh = fmaxf(__uint_as_float(r[j]) + bias[j], 0.f);
+          part = fmaf(xh, xh, part);
+          st[j * SS] = xh;
+        }
+        // sparse part: patch the entries of this 16-gene sub-chunk
+        const int lo = c * 16;
+#pragma unroll
+        for (int u = 0; u < DE; ++u) {
+          const int j = ecol[u] - lo;
+          if (j >= 0 && j < 16) {
+            const float x = eval[u];
+            const float xh = st[j * SS];
+            part += x * x - 2.f * x * xh;
+            st[j * SS] = xh > 0.f ? xh - x : 0.f;
+          }
+        }
+        for (int k = DE; k < cnt; ++k) {     // windows with more than DE entries (dense batches)
+          const int j = __ldg(p.col + p0 + k) - g0 - lo;
+          if (j >= 0 && j < 16) {
+            const float x = __ldg(p.val + p0 + k);
+            const float xh = st[j * SS];
+            part += x * x - 2.f * x * xh;
+            st[j * SS] = xh > 0.f ? xh - x : 0.f;
+          }
         }
         // out: dlogits = 2 * staged, bf16, 8 columns (16 bytes) per store
         if (row_ok) {
-          __nv_bfloat16* drow = p.dl + (size_t)b * p.ldd + n0 + c * 32;
+          __nv_bfloat16* drow = p.dl + (size_t)b * p.ldd + gc;
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (n0 + c * 32 + j + 8 <= p.ldd) {
+          for (int j = 0; j < 16; j += 8) {
+            if (gc + j + 8 <= p.ldd) {
               uint4 o;
-              o.x = pack_bf16(2.f * staging[(j + 0) * 128 + row], 2.f * staging[(j + 1) * 128 + row]);
-              o.y = pack_bf16(2.f * staging[(j + 2) * 128 + row], 2.f * staging[(j + 3) * 128 + row]);
-              o.z = pack_bf16(2.f * staging[(j + 4) * 128 + row], 2.f * staging[(j + 5) * 128 + row]);
-              o.w = pack_bf16(2.f * staging[(j + 6) * 128 + row], 2.f * staging[(j + 7) * 128 + row]);
+              o.x = pack_bf16(2.f * st[(j + 0) * SS], 2.f * st[(j + 1) * SS]);
+              o.y = pack_bf16(2.f * st[(j + 2) * SS], 2.f * st[(j + 3) * SS]);
+              o.z = pack_bf16(2.f * st[(j + 4) * SS], 2.f * st[(j + 5) * SS]);
+              o.w = pack_bf16(2.f * st[(j + 6) * SS], 2.f * st[(j + 7) * SS]);
               *reinterpret_cast<uint4*>(drow + j) = o;
             }
           }
@@ -243,6 +245,9 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      p0 = np0; cnt = ncnt;
+#pragma unroll
+      for (int u = 0; u < DE; ++u) { ecol[u] = necol[u]; eval[u] = neval[u]; }
     }
     // one atomic per warp
     loss_acc = warp_sum(loss_acc);
@@ -255,30 +260,32 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
 
 int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
                    uint32_t box_outer);
+__global__ void tile_ptr64_kernel(const int32_t* __restrict__ crow, const int32_t* __restrict__ col, int B, int ntp,
+                                  int32_t* __restrict__ tp);
 
 }  // namespace cmmvae
 
 using namespace cmmvae;
 
 extern "C" size_t cmmvae_decoder_mse_fused_workspace_bytes(int B, int G) {
-  const int num_n = (G + DBN - 1) / DBN;
-  return sizeof(int32_t) * (size_t)B * (size_t)(num_n + 1);
+  return sizeof(int32_t) * (size_t)B * (size_t)((G + 63) / 64 + 1);
 }
 
 extern "C" int cmmvae_decoder_mse_fused(const void* h, int ldh, const void* Wout, int ldw, const float* bout, int B,
                                         int G, int H, const int32_t* crow, const int32_t* col, const float* val,
-                                        void* dlogits_bf16, int ldd, double* loss_sum, void* workspace,
-                                        void* stream) {
+                                        const int32_t* tile_ptr, void* dlogits_bf16, int ldd, double* loss_sum,
+                                        void* workspace, void* stream) {
   CMMVAE_REQUIRE(B > 0 && G > 0 && H > 0, "decoder_mse_fused: bad shape");
   CMMVAE_REQUIRE(ldh % 8 == 0 && ldw % 8 == 0 && ldd % 8 == 0 && ldd >= G,
                  "decoder_mse_fused: ldh/ldw/ldd must be multiples of 8 and ldd >= G");
   CMMVAE_REQUIRE((((uintptr_t)h | (uintptr_t)Wout | (uintptr_t)dlogits_bf16) & 15) == 0,
                  "decoder_mse_fused: pointers must be 16-byte aligned");
-  CMMVAE_REQUIRE(workspace && loss_sum, "decoder_mse_fused: workspace/loss_sum missing");
+  CMMVAE_REQUIRE(((uintptr_t)bout & 7) == 0, "decoder_mse_fused: bout must be 8-byte aligned");
+  CMMVAE_REQUIRE((tile_ptr || workspace) && loss_sum, "decoder_mse_fused: tile_ptr/workspace or loss_sum missing");
   cudaStream_t st = (cudaStream_t)stream;
   DecParams p;
-  p.B = B; p.G = G; p.H = H; p.bout = bout; p.crow = crow; p.col = col; p.val = val;
-  p.tile_ptr = (const int32_t*)workspace;
+  p.B = B; p.G = G; p.H = H; p.bout = bout; p.col = col; p.val = val;
+  p.ntp = (G + 63) / 64 + 1;
   p.dl = (__nv_bfloat16*)dlogits_bf16; p.ldd = ldd; p.loss_sum = loss_sum;
   p.num_m = (B + DBM - 1) / DBM;
   p.num_n = (G + DBN - 1) / DBN;
@@ -296,13 +303,13 @@ extern "C" int cmmvae_decoder_mse_fused(const void* h, int ldh, const void* Wout
     configured = true;
   }
   cudaMemsetAsync(loss_sum, 0, sizeof(double), st);
-  {
-    const long long n = (long long)B * (p.num_n + 1);
-    long long want = (n + 255) / 256;
-    int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
-    tile_ptr_kernel<<<blocks, 256, 0, st>>>(crow, col, B, p.num_n, (int32_t*)workspace);
-    if (int rc = check_launch("tile_ptr")) return rc;
+  if (!tile_ptr) {   // build the 64-gene-window pointer table (the tensor-pipe SpMM shares it when it ran)
+    int blocks = (B + 7) / 8 < 148 * 8 ? (B + 7) / 8 : 148 * 8;   // one warp per row
+    tile_ptr64_kernel<<<blocks, 256, 0, st>>>(crow, col, B, p.ntp, (int32_t*)workspace);
+    if (int rc = check_launch("tile_ptr64")) return rc;
+    tile_ptr = (const int32_t*)workspace;
   }
+  p.tp = tile_ptr;
   const int num_tiles = p.num_m * p.num_n;
   const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
   decoder_mse_fused_kernel<<<grid, kDecThreads, DecSmem::kTotal, st>>>(tmH, tmW, p);

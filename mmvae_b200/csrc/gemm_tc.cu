@@ -40,6 +40,7 @@ struct GemmParams {
   int ldc;
   int vec_ok;  // 16-byte aligned rows for both outputs
   int splits;  // split-K factor (gridDim.z); > 1: partial products are atomically added into a zeroed C32
+  double* sumsq;  // optional: += sum of squares of the stored C (gradient-norm fused into the dW GEMM)
 };
 
 template <int BN, bool A_MN, bool B_MN>
@@ -138,6 +139,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
     }
+    float ssq = 0.f;
 #pragma unroll 1
     for (int c = 0; c < BN / 32 && num_kb > 0; ++c) {
       uint32_t r[32];
@@ -186,6 +188,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
+          if (p.sumsq) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) ssq = fmaf(v[j], v[j], ssq);
+          }
           if (p.C32) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
@@ -207,12 +213,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               float x = v[j];
               if (p.accumulate) x += p.C32[o + j];
               if (p.relu) x = fmaxf(x, 0.f);
+              if (p.sumsq) ssq = fmaf(x, x, ssq);
               if (p.C32) p.C32[o + j] = x;
               if (p.C16) p.C16[o + j] = __float2bfloat16(x);
             }
           }
         }
       }
+    }
+    if (p.sumsq) {
+      const double tot = warp_sum((double)ssq);
+      if (lane == 0 && tot != 0.0) atomicAdd(p.sumsq, tot);
     }
   }
   tc_fence_before();
@@ -295,7 +306,7 @@ using namespace cmmvae;
 
 extern "C" int cmmvae_gemm_bf16_tc(const void* A, int lda, int transA, const void* Bm, int ldb, int transB, int M,
                                    int N, int K, const float* bias, int relu, int accumulate, float* C_f32,
-                                   void* C_bf16, int ldc, void* stream) {
+                                   void* C_bf16, int ldc, double* sumsq_out, void* stream) {
   CMMVAE_REQUIRE(M > 0 && N > 0 && K > 0 && ldc >= N, "gemm_bf16_tc: bad shape M=%d N=%d K=%d ldc=%d", M, N, K, ldc);
   CMMVAE_REQUIRE(C_f32 || C_bf16, "gemm_bf16_tc: no output");
   CMMVAE_REQUIRE(!accumulate || C_f32, "gemm_bf16_tc: accumulate needs C_f32");
@@ -325,6 +336,8 @@ extern "C" int cmmvae_gemm_bf16_tc(const void* A, int lda, int transA, const voi
   p.C32 = C_f32; p.C16 = (__nv_bfloat16*)C_bf16; p.ldc = ldc;
   p.vec_ok = (ldc % 8 == 0) && (!C_f32 || ((uintptr_t)C_f32 & 15) == 0) && (!C_bf16 || ((uintptr_t)C_bf16 & 15) == 0);
   p.splits = splits;
+  p.sumsq = sumsq_out;
+  CMMVAE_REQUIRE(!sumsq_out || splits == 1, "gemm_bf16_tc: sumsq_out is not available on the split-K path");
   cudaStream_t st = (cudaStream_t)stream;
   if (splits > 1) {
     cudaError_t e = cudaMemset2DAsync(C_f32, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st);

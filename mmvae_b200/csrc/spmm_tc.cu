@@ -39,23 +39,31 @@ struct SpParams {
   const float* bias;   // forward only
   float* out;          // forward: Y[B,H]; backward: dWt[G,H]
   int splits;          // forward split-K over genes
+  double* sumsq;       // backward only, optional: += sum of squares of dWt (fused gradient norm)
 };
 
 // tp[w][b] = first position p in row b with col[p] >= 64*w, w = 0..NW (NW = ceil(G/64)); window-major so
-// that the producers' reads (consecutive lanes = consecutive cells) coalesce
+// that the producers' reads (consecutive lanes = consecutive cells) coalesce.
+// One thread per non-zero: entry i of row b opens every window in (window(i-1), window(i)] (all windows up
+// to window(i) when it is the row's first entry); the row's last entry also closes the windows after it.
+// Every table cell is written exactly once; rows without entries are filled by tile_ptr64_empty_rows.
 __global__ void tile_ptr64_kernel(const int32_t* __restrict__ crow, const int32_t* __restrict__ col, int B, int ntp,
                                   int32_t* __restrict__ tp) {
-  const long long n = (long long)B * ntp;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int w = (int)(i / B), b = (int)(i % B);
-    int lo = crow[b], hi = crow[b + 1];
-    const int key = w * 64;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (__ldg(col + mid) < key) lo = mid + 1; else hi = mid;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int b = warp; b < B; b += nwarps) {
+    const int s = crow[b], e = crow[b + 1];
+    if (s == e) {
+      for (int w = lane; w < ntp; w += 32) tp[(size_t)w * B + b] = s;
+      continue;
     }
-    tp[i] = lo;
+    for (int i = s + lane; i < e; i += 32) {
+      const int wi = __ldg(col + i) >> 6;
+      const int wprev = (i == s) ? -1 : (__ldg(col + i - 1) >> 6);
+      for (int w = wprev + 1; w <= wi; ++w) tp[(size_t)w * B + b] = i;
+      if (i == e - 1)
+        for (int w = wi + 1; w < ntp; ++w) tp[(size_t)w * B + b] = e;
+    }
   }
 }
 
@@ -235,6 +243,7 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const SpParams p) {
       const int row = qd * 32 + lane;
       const int gm = m0 + row;
       const int Mdim = BWD ? p.G : p.B;
+      float ssq = 0.f;
 #pragma unroll 1
       for (int c = group * 4; c < group * 4 + 4; ++c) {
         uint32_t r[32];
@@ -265,11 +274,22 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const SpParams p) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               *reinterpret_cast<float4*>(orow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (BWD && p.sumsq) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) ssq = fmaf(v[j], v[j], ssq);
+            }
           } else {
             for (int j = 0; j < 32; ++j)
-              if (gn0 + j < p.H) orow[j] = v[j];
+              if (gn0 + j < p.H) {
+                orow[j] = v[j];
+                if (BWD && p.sumsq) ssq = fmaf(v[j], v[j], ssq);
+              }
           }
         }
+      }
+      if (BWD && p.sumsq) {
+        const double tot = warp_sum((double)ssq);
+        if (lane == 0 && tot != 0.0) atomicAdd(p.sumsq, tot);
       }
     }
   }
@@ -313,11 +333,10 @@ extern "C" int cmmvae_csr_tile_ptr(const int32_t* crow, const int32_t* col, cons
   CMMVAE_REQUIRE(((uintptr_t)packed & 15) == 0, "csr_tile_ptr: packed must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const int ntp = (G + 63) / 64 + 1;
-  const long long n = (long long)B * ntp;
-  long long want = (n + 255) / 256;
-  int blocks = (int)(want < 148 * 16 ? want : 148 * 16);
+  int blocks = (B + 7) / 8 < 148 * 8 ? (B + 7) / 8 : 148 * 8;   // one warp per row
   tile_ptr64_kernel<<<blocks, 256, 0, st>>>(crow, col, B, ntp, tile_ptr);
   if (int rc = check_launch("csr_tile_ptr")) return rc;
+  long long want;
   const long long padded = (nnz + 3) / 4 * 4 + 4;
   want = (padded + 255) / 256;
   blocks = (int)(want < 148 * 16 ? want : 148 * 16);
@@ -332,7 +351,7 @@ extern "C" int cmmvae_csr_linear_fwd_tc(const void* packed, const int32_t* tile_
   cudaStream_t st = (cudaStream_t)stream;
   SpParams p;
   p.B = B; p.G = G; p.H = H; p.packed = (const uint32_t*)packed; p.tp = tile_ptr; p.ntp = (G + 63) / 64 + 1;
-  p.bias = bias; p.out = Y;
+  p.bias = bias; p.out = Y; p.sumsq = nullptr;
   const int tiles = ((B + SBM - 1) / SBM) * ((H + SBN - 1) / SBN);
   const int total_kb = (G + SBK - 1) / SBK;
   int splits = tiles >= kNumSMs ? 1 : kNumSMs / tiles;
@@ -347,12 +366,12 @@ extern "C" int cmmvae_csr_linear_fwd_tc(const void* packed, const int32_t* tile_
 }
 
 extern "C" int cmmvae_csr_linear_bwd_w_tc(const void* packed, const int32_t* tile_ptr, int B, int G, int H,
-                                          const void* dY_bf16, float* dWt, void* stream) {
+                                          const void* dY_bf16, float* dWt, double* sumsq_out, void* stream) {
   CMMVAE_REQUIRE(B > 0 && G > 0 && H > 0 && H % 8 == 0, "csr_linear_bwd_w_tc: bad shape (H must be a multiple of 8)");
   CMMVAE_REQUIRE(((uintptr_t)dY_bf16 & 15) == 0 && ((uintptr_t)dWt & 15) == 0, "csr_linear_bwd_w_tc: alignment");
   SpParams p;
   p.B = B; p.G = G; p.H = H; p.packed = (const uint32_t*)packed; p.tp = tile_ptr; p.ntp = (G + 63) / 64 + 1;
-  p.bias = nullptr; p.out = dWt; p.splits = 1;
+  p.bias = nullptr; p.out = dWt; p.splits = 1; p.sumsq = sumsq_out;
   CUtensorMap tm;
   if (int rc = make_tmap_bf16(&tm, dY_bf16, (uint64_t)H, (uint64_t)B, (uint64_t)H, 64, SBK)) return rc;
   dim3 grid((H + SBN - 1) / SBN, (G + SBM - 1) / SBM, 1);

@@ -142,8 +142,18 @@ class FlatGroup:
         lo = self.tail_lo if self.sharded else 0
         return dp.allreduce_sum_(self.g[lo:self.n], async_op=True)
 
-    def grad_norm_sq(self, out: torch.Tensor):
-        """out (double[1], pre-zeroed) += || sum_r g_r ||^2 over the whole group (padding is zero)."""
+    def grad_norm_sq(self, out: torch.Tensor, skip: Optional[List[nn.Parameter]] = None):
+        """out (double[1], pre-zeroed) += || sum_r g_r ||^2 over the whole group (padding is zero).
+        ``skip``: parameters whose contribution a producer kernel already added to ``out`` (single process)."""
+        if skip and not self.sharded and self.world == 1:
+            cuts = sorted((self.offset[id(p)], self.offset[id(p)] + p.numel()) for p in skip)
+            lo = 0
+            for a, b in cuts + [(self.n, self.n)]:
+                a4, lo4 = a // 4 * 4, _ceil(lo, 4)   # ranges start/stop on parameter boundaries (64-aligned)
+                if a4 > lo4:
+                    ops.sumsq(self.g[lo4:a4], out)
+                lo = b
+            return
         if self.sharded:
             for gs in self.gs:
                 ops.sumsq(gs, out)
@@ -468,8 +478,8 @@ class StepEngine:
             ops.colsum(dY, lp.gb)
         if lp.sparse:
             if csc[0] == "tc":
-                _, tp, G = csc
-                ops.csr_linear_bwd_w_tc(tp[1], tp[0], B, G, dY16, lp.gW)
+                _, tp, G, ssq = csc
+                ops.csr_linear_bwd_w_tc(tp[1], tp[0], B, G, dY16, lp.gW, sumsq_out=ssq)
             else:
                 _, cptr, ridx, cval, G = csc
                 ops.csr_linear_bwd_w(cptr, ridx, cval, B, G, dY, lp.gW)
@@ -590,7 +600,8 @@ class StepEngine:
             dl = self.ws("dlogits16", (B, ldd), torch.bfloat16, zero=True)
             wsb = self.ws("tileptr", (ops.decoder_mse_fused_workspace_bytes(B, G),), torch.uint8)
             ev = self._t0("decoder_mse_fused")
-            ops.decoder_mse_fused(h16, out.W16, out.b, G, crow, col, val, dl, sc[0:1], wsb)
+            ops.decoder_mse_fused(h16, out.W16, out.b, G, crow, col, val, dl, sc[0:1], wsb,
+                                  tile_ptr=tp[0] if tp is not None else None)
             self._t1(ev)
         else:
             logits = self.ws("logits32", (B, G))
@@ -627,11 +638,14 @@ class StepEngine:
                 ap.group.grad_norm_sq(s_norm(2 + n_adv + i))   # "generator_i" norm: logged, never applied
 
         # ---------------- backward ----------------
+        # single process: the two big weight-gradient kernels add their own sum of squares to the clip norm
+        fuse_norm = self.world == 1 and fused and use_tc_spmm
         H1 = out.K
         dh = self.ws("dh", (B, H1))
         if fused:
             ev = self._t0("dWout_gemm")
-            ops.gemm(dl, 1, h16, 1, G, H1, B, C32=out.gW)                 # dWout = dlogits^T h
+            ops.gemm(dl, 1, h16, 1, G, H1, B, C32=out.gW,                 # dWout = dlogits^T h (+ its ||.||^2)
+                     sumsq_out=s_norm(1) if fuse_norm else None)
             self._t1(ev)
             ops.colsum(dl, out.gb, M=B, N=G)
             # the output layer's gradient (half of the expert group) is final: start exchanging it now so
@@ -672,7 +686,7 @@ class StepEngine:
                     ops.axpy(d, d_hidden[i], -1.0)
             d = self._layer_bwd(f"venc{j}", self.vaeenc_plan[j], caches[("venc", j)], d, B)
         if use_tc_spmm:
-            csc = ("tc", tp, G)
+            csc = ("tc", tp, G, s_norm(1) if fuse_norm else None)
         else:
             cptr, ridx, cval = ops.csr_transpose(crow, col, val, G, nnz, self.ws("cptr", (G + 1,), torch.int32),
                                                  self.ws("ridx", (max(nnz, 1),), torch.int32),
@@ -694,7 +708,7 @@ class StepEngine:
                 w.wait()
         ev = self._t0("norm+clip_adam")
         gvae.grad_norm_sq(s_norm(0))
-        gexp.grad_norm_sq(s_norm(1))
+        gexp.grad_norm_sq(s_norm(1), skip=[enc[0].lin.weight, out.lin.weight] if fuse_norm else None)
         gvae.clip_adam(s_norm(0), self.clip.get("vae"), gscale)
         gexp.clip_adam(s_norm(1), self.clip.get("expert"), gscale)
         self._t1(ev)
@@ -704,10 +718,24 @@ class StepEngine:
         return self.last
 
     # ---------------------------------------------------------------------------------------- logs
-    def scalars(self, rec=None) -> Dict[str, float]:
+    def scalars_async(self, rec=None):
+        """start a non-blocking copy of the step's scalar block into pinned host memory; returns
+        (pinned tensor, event) to pass to ``scalars(host=...)`` later"""
+        rec = rec or self.last
+        host = torch.empty(rec["sc"].shape, dtype=torch.float64, pin_memory=True)
+        host.copy_(rec["sc"], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return host, ev
+
+    def scalars(self, rec=None, host=None) -> Dict[str, float]:
         """Host copy (one sync) of every value the reference logs for the step, untagged keys."""
         rec = rec or self.last
-        sc = rec["sc"].cpu().tolist()
+        if host is not None:
+            host[1].synchronize()
+            sc = host[0].tolist()
+        else:
+            sc = rec["sc"].cpu().tolist()
         B, Z, n_adv = rec["B"], rec["Z"], rec["n_adv"]
         out = {"recon_loss": sc[0], "kl_loss": sc[1] / B, "kl_weight": rec["kl_weight"],
                "Mean": sc[2] / (B * Z), "Variance": sc[3] / (B * Z)}

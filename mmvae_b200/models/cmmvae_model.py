@@ -49,7 +49,11 @@ class CMMVAEModel(BaseModel):
         self.adv_weight = adv_weight if adv_weight else 1.0   # 0/None -> 1.0, as in the reference
         self.autograd_config = autograd_config or AutogradConfig()
         self._engine: Optional[StepEngine] = None
-        self.sync_logging = True   # read the step's scalars back and log python floats every step
+        # True: read the step's scalars back and log them inside the same training_step (one host sync per
+        # step, the reference's timing).  False: the scalars are copied to pinned host memory asynchronously
+        # and logged at the NEXT training_step (or flush_logs()), so the host never waits for the GPU.
+        self.sync_logging = True
+        self._pending_log = None
 
     # ------------------------------------------------------------------------------------ engine
     @staticmethod
@@ -128,6 +132,17 @@ class CMMVAEModel(BaseModel):
         self.kl_annealing_fn.step()
         if self.sync_logging:
             self._log_step(eng.scalars(rec), expert_id)
+        else:
+            prev, self._pending_log = self._pending_log, (eng.scalars_async(rec), rec, expert_id)
+            if prev is not None:
+                self._log_step(eng.scalars(prev[1], host=prev[0]), prev[2])
+
+    def flush_logs(self):
+        """log the scalars of the last step when ``sync_logging`` is off"""
+        if self._pending_log is not None:
+            host, rec, expert_id = self._pending_log
+            self._pending_log = None
+            self._log_step(self.engine().scalars(rec, host=host), expert_id)
 
     def _log_step(self, s: dict, expert_id: str):
         stage = self.stage_name

@@ -117,11 +117,11 @@ def csr_linear_fwd_tc(packed, tile_ptr, B: int, G: int, Wt16, bias, out=None):
     return out
 
 
-def csr_linear_bwd_w_tc(packed, tile_ptr, B: int, G: int, dY16, out):
+def csr_linear_bwd_w_tc(packed, tile_ptr, B: int, G: int, dY16, out, sumsq_out=None):
     H = dY16.shape[1]
     assert dY16.dtype == torch.bfloat16 and dY16.is_contiguous() and out.is_contiguous() and out.shape == (G, H)
     _check(lib().cmmvae_csr_linear_bwd_w_tc(_ptr(packed), _ptr(tile_ptr), B, G, H, _ptr(dY16), _ptr(out),
-                                            _stream()), "csr_linear_bwd_w_tc")
+                                            _ptr(sumsq_out), _stream()), "csr_linear_bwd_w_tc")
     return out
 
 
@@ -139,13 +139,14 @@ def decoder_mse_fused_workspace_bytes(B: int, G: int) -> int:
     return int(fn(B, G))
 
 
-def decoder_mse_fused(h16, Wout16, bout, G: int, crow, col, val, dl16, loss_sum, workspace=None):
+def decoder_mse_fused(h16, Wout16, bout, G: int, crow, col, val, dl16, loss_sum, workspace=None, tile_ptr=None):
     B, H = h16.shape
-    if workspace is None:
+    if workspace is None and tile_ptr is None:
         workspace = torch.empty(decoder_mse_fused_workspace_bytes(B, G), dtype=torch.uint8, device=h16.device)
     _check(lib().cmmvae_decoder_mse_fused(_ptr(h16), h16.stride(0), _ptr(Wout16), Wout16.stride(0), _ptr(bout), B, G,
-                                          H, _ptr(crow), _ptr(col), _ptr(val), _ptr(dl16), dl16.stride(0),
-                                          _ptr(loss_sum), _ptr(workspace), _stream()), "decoder_mse_fused")
+                                          H, _ptr(crow), _ptr(col), _ptr(val), _ptr(tile_ptr), _ptr(dl16),
+                                          dl16.stride(0), _ptr(loss_sum), _ptr(workspace), _stream()),
+           "decoder_mse_fused")
 
 
 # -------------------------------------------------------------------------------- BN / act / drop
@@ -182,7 +183,7 @@ def _ld(t):
 
 
 def gemm(A, transA, Bm, transB, M, N, K, bias=None, relu=False, accumulate=False, C32=None, C16=None,
-         use_tc: Optional[bool] = None):
+         use_tc: Optional[bool] = None, sumsq_out=None):
     """C[M,N] = act(opA(A) opB(B) + bias) (+C).  A: [M,K] or (transA) [K,M]; B: [N,K] or (transB) [K,N]."""
     C = C32 if C32 is not None else C16
     ldc = _ld(C)
@@ -191,12 +192,13 @@ def gemm(A, transA, Bm, transB, M, N, K, bias=None, relu=False, accumulate=False
     tc = (A.dtype == torch.bfloat16) if use_tc is None else use_tc
     if tc:
         assert A.dtype == torch.bfloat16 and Bm.dtype == torch.bfloat16
-        fn, name = lib().cmmvae_gemm_bf16_tc, "gemm_bf16_tc"
-    else:
-        assert A.dtype == torch.float32 and Bm.dtype == torch.float32
-        fn, name = lib().cmmvae_gemm_f32, "gemm_f32"
-    _check(fn(_ptr(A), _ld(A), int(transA), _ptr(Bm), _ld(Bm), int(transB), M, N, K, _ptr(bias), int(relu),
-              int(accumulate), _ptr(C32), _ptr(C16), ldc, _stream()), name)
+        _check(lib().cmmvae_gemm_bf16_tc(_ptr(A), _ld(A), int(transA), _ptr(Bm), _ld(Bm), int(transB), M, N, K,
+                                         _ptr(bias), int(relu), int(accumulate), _ptr(C32), _ptr(C16), ldc,
+                                         _ptr(sumsq_out), _stream()), "gemm_bf16_tc")
+        return C
+    assert A.dtype == torch.float32 and Bm.dtype == torch.float32 and sumsq_out is None
+    _check(lib().cmmvae_gemm_f32(_ptr(A), _ld(A), int(transA), _ptr(Bm), _ld(Bm), int(transB), M, N, K, _ptr(bias),
+                                 int(relu), int(accumulate), _ptr(C32), _ptr(C16), ldc, _stream()), "gemm_f32")
     return C
 
 

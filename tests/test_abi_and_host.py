@@ -42,7 +42,7 @@ def test_argument_validation_happens_before_any_launch():
     rc = lib.cmmvae_csr_linear_fwd(None, None, None, 0, 10, 8, None, 0, None, None, None)
     assert rc == -1 and b"bad shape" in lib.cmmvae_last_error()
     rc = lib.cmmvae_gemm_bf16_tc(ctypes.c_void_p(16), 7, 0, ctypes.c_void_p(32), 8, 0, 4, 4, 4, None, 0, 0,
-                                 ctypes.c_void_p(64), None, 4, None)
+                                 ctypes.c_void_p(64), None, 4, None, None)
     assert rc == -1 and b"multiples of 8" in lib.cmmvae_last_error()
 
 
