@@ -29,6 +29,9 @@ int cmmvae_abi_version(void);
 const char* cmmvae_last_error(void);
 /* number of kernels this library has launched in the calling process (bench.py gpu_launches) */
 long long cmmvae_launch_count(void);
+/* SMs the persistent tensor kernels plan their grids / split-K factors for (default 148).  Lower it while
+ * communication kernels (NCCL) share the GPU so that all planned CTAs are co-resident. */
+int cmmvae_set_sm_budget(int sms);
 
 /* ---- K1: expert-encoder first layer on a CSR batch ---------------------------------------
  * replaces nn.Linear applied to torch.sparse_csr input: components.py:276,306 (FCBlock layer 0

@@ -6,6 +6,8 @@
 namespace cmmvae {
 static thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+static std::atomic<int> g_sm_budget{kNumSMs};
+int sm_budget() { return g_sm_budget.load(std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -18,3 +20,11 @@ void set_error(const char* fmt, ...) {
 extern "C" int cmmvae_abi_version(void) { return CMMVAE_ABI_VERSION; }
 extern "C" const char* cmmvae_last_error(void) { return cmmvae::g_err; }
 extern "C" long long cmmvae_launch_count(void) { return cmmvae::g_launches.load(); }
+extern "C" int cmmvae_set_sm_budget(int sms) {
+  if (sms < 1 || sms > cmmvae::kNumSMs) {
+    cmmvae::set_error("set_sm_budget: %d outside [1, %d]", sms, cmmvae::kNumSMs);
+    return -1;
+  }
+  cmmvae::g_sm_budget.store(sms);
+  return 0;
+}

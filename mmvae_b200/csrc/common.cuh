@@ -33,6 +33,9 @@ inline int check_launch(const char* what) {
   } while (0)
 
 constexpr int kNumSMs = 148;
+// SMs the persistent kernels may plan for (grid sizes, split-K factors).  148 by default; the host lowers it
+// while NCCL kernels share the GPU so that every planned CTA is resident at once (cmmvae_set_sm_budget).
+int sm_budget();
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -8,9 +8,10 @@
 //
 // Persistent kernel, one CTA per SM, 128 x 256 output tiles, static round-robin tile order with the
 // cell-block index fastest (so CTAs running concurrently share the same Wout tiles in L2).  576 threads:
-//   warp 0       TMA producer (4-stage ring of 128x64 h tiles + 256x64 Wout tiles, 128B swizzle)
-//   warp 1       tcgen05.mma issuer; two 256-column TMEM accumulators ping-pong with the epilogue
-//   warps 2..17  epilogue, 16 warps so that draining a tile takes less time than computing the next one:
+//   warp 16      TMA producer (4-stage ring of 128x64 h tiles + 256x64 Wout tiles, 128B swizzle)
+//   warp 17      tcgen05.mma issuer (highest warp id = issue priority); two 256-column TMEM accumulators
+//                ping-pong with the epilogue
+//   warps 0..15  epilogue, 16 warps so that draining a tile takes less time than computing the next one:
 //                thread = (cell, 64-gene window).  The cell's CSR entries of the window are found through
 //                the per-(cell, 64-gene window) pointer table (window-major, shared with the tensor-pipe
 //                SpMM; bit-exact with crow/col) and prefetched into registers while the MMA runs;
@@ -65,7 +66,8 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
   const int num_kb = (p.H + DBK - 1) / DBK;
   const int num_tiles = p.num_m * p.num_n;
 
-  if (warp == 0 && lane == 0) {
+  constexpr int kTmaWarp = kDecEpiWarps, kMmaWarp = kDecEpiWarps + 1;   // MMA issuer = highest warp id (priority)
+  if (warp == kTmaWarp && lane == 0) {
     prefetch_tmap(&tmH);
     prefetch_tmap(&tmW);
     for (int s = 0; s < DSTAGES; ++s) {
@@ -78,13 +80,13 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == kMmaWarp) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == kTmaWarp) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -100,7 +102,7 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(DBM, DBN, 0, 0);
       int stage = 0;
@@ -129,7 +131,7 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
     }
   } else {
     // ===== epilogue: thread = (cell row, 64-gene window) =====
-    const int e = warp - 2;                  // 0..15
+    const int e = warp;                      // 0..15
     const int q = warp & 3;                  // TMEM lane group this warp may read
     const int w = e >> 2;                    // 64-gene window of the tile: consecutive warps cover all lane groups
     const int row = q * 32 + lane;           // TMEM lane == row inside the tile
@@ -176,7 +178,7 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
       const int g0 = n0 + w * 64;            // first gene of this thread's window
       fetch(t + gridDim.x, np0, ncnt, necol, neval);
 
-      mbar_wait(&tmem_full[acc], acc_phase);
+      mbar_wait_relaxed(&tmem_full[acc], acc_phase);
       tc_fence_after();
       float part = 0.f;
 #pragma unroll 1
@@ -255,7 +257,7 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
 }
 
 int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
@@ -311,7 +313,7 @@ extern "C" int cmmvae_decoder_mse_fused(const void* h, int ldh, const void* Wout
   }
   p.tp = tile_ptr;
   const int num_tiles = p.num_m * p.num_n;
-  const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+  const int grid = num_tiles < sm_budget() ? num_tiles : sm_budget();
   decoder_mse_fused_kernel<<<grid, kDecThreads, DecSmem::kTotal, st>>>(tmH, tmW, p);
   return check_launch("decoder_mse_fused");
 }

@@ -2,13 +2,13 @@
 //
 //   C[M,N] = act( opA(A) * opB(B) + bias ) (+ C)        bf16 operands, fp32 accumulation in TMEM
 //
-// One CTA computes one 128 x BN output tile.  Warp roles (192 threads):
-//   warp 0      TMA producer: streams 128x64 (A) and BNx64 (B) bf16 tiles, 128B-swizzled, through a
+// Persistent CTAs walk 128 x BN output tiles (optionally split along K).  Warp roles (192 threads):
+//   warps 0..3  epilogue: tcgen05.ld the accumulator (lane = output row), bias / ReLU / accumulate,
+//               vectorised stores of f32 and/or bf16 (drains accumulator i while tile i+1 is multiplied)
+//   warp 4      TMA producer: streams 128x64 (A) and BNx64 (B) bf16 tiles, 128B-swizzled, through a
 //               kStages-deep shared-memory ring guarded by full/empty mbarriers
-//   warp 1      allocates TMEM, then one elected lane issues tcgen05.mma (UMMA 128 x BN x 16) and
-//               releases ring slots with tcgen05.commit
-//   warps 2..5  epilogue: tcgen05.ld the accumulator (lane = output row), bias / ReLU / accumulate,
-//               vectorised stores of f32 and/or bf16
+//   warp 5      allocates TMEM (two accumulators), then one lane issues tcgen05.mma (UMMA 128 x BN x 16) and
+//               releases ring slots with tcgen05.commit; it is the highest warp id on purpose (issue priority)
 // Operands may be K-major ("row = M or N index, K contiguous") or MN-major (stored transposed):
 // both are native UMMA layouts, so backward GEMMs (dX = dY W, dW = dY^T X) need no transposed copies.
 #include "tc.cuh"
@@ -52,174 +52,212 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
   uint64_t* empty_bar = full_bar + S::kStages;
-  uint64_t* tmem_full_bar = empty_bar + S::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full = empty_bar + S::kStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  // persistent: work units (n tile fastest, then m tile, then K split) are dealt round-robin to the CTAs;
+  // two TMEM accumulators let the epilogue of unit i overlap the main loop of unit i+1
+  const int tiles_n = (p.N + BN - 1) / BN, tiles_m = (p.M + BM - 1) / BM;
+  const int num_units = tiles_n * tiles_m * p.splits;
   const int total_kb = (p.K + BK - 1) / BK;
   const int kb_per = (total_kb + p.splits - 1) / p.splits;
-  const int kb0 = blockIdx.z * kb_per;
-  const int num_kb = max(0, min(total_kb, kb0 + kb_per) - kb0);
+  auto unit_coords = [&](int u, int& m0, int& n0, int& z, int& kb0, int& num_kb) {
+    n0 = (u % tiles_n) * BN;
+    m0 = ((u / tiles_n) % tiles_m) * BM;
+    z = u / (tiles_n * tiles_m);
+    kb0 = z * kb_per;
+    num_kb = max(0, min(total_kb, kb0 + kb_per) - kb0);
+  };
 
-  if (warp == 0 && lane == 0) {
+  // warp roles: the MMA issuer is the LAST warp (the scheduler favours higher warp ids, and the one issuing
+  // thread must never wait behind polling warps), TMA producer next, epilogue warps 0..3
+  constexpr int kTmaWarp = 4, kMmaWarp = 5;
+  if (warp == kTmaWarp && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < S::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);   // one arrival per epilogue warp
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  if (warp == kMmaWarp) tmem_alloc<2 * BN>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == kTmaWarp) {
     // ===== TMA producer =====
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sA = smem + stage * S::kStageBytes;
-        uint8_t* sB = sA + S::kABytes;
-        mbar_expect_tx(&full_bar[stage], S::kStageBytes);
-        const int k0 = (kb0 + kb) * BK;
-        if (!A_MN) {
-          tma_load_2d(sA, &tmA, &full_bar[stage], k0, m0);
-        } else {
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        int m0, n0, z, kb0, num_kb;
+        unit_coords(u, m0, n0, z, kb0, num_kb);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * S::kStageBytes;
+          uint8_t* sB = sA + S::kABytes;
+          mbar_expect_tx(&full_bar[stage], S::kStageBytes);
+          const int k0 = (kb0 + kb) * BK;
+          if (!A_MN) {
+            tma_load_2d(sA, &tmA, &full_bar[stage], k0, m0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[stage], m0 + 64 * j, k0);
-        }
-        if (!B_MN) {
-          tma_load_2d(sB, &tmB, &full_bar[stage], k0, n0);
-        } else {
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[stage], m0 + 64 * j, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d(sB, &tmB, &full_bar[stage], k0, n0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[stage], n0 + 64 * j, k0);
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[stage], n0 + 64 * j, k0);
+          }
+          if (++stage == S::kStages) { stage = 0; phase ^= 1; }
         }
-        if (++stage == S::kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+      int it = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
+        int m0, n0, z, kb0, num_kb;
+        unit_coords(u, m0, n0, z, kb0, num_kb);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t sA = smem_u32(smem + stage * S::kStageBytes);
-        const uint32_t sB = sA + S::kABytes;
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * S::kStageBytes);
+          const uint32_t sB = sA + S::kABytes;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // K-major: 8-row groups 1024 B apart, +32 B per 16-element K step inside the swizzle span.
-          // MN-major: 64-element MN groups BK*128 B apart (LBO), 8 K-rows = 1024 B (SBO), +2048 B per K step.
-          const uint64_t da = A_MN ? make_desc_sw128(sA + k * 2048, BK * 128, 1024)
-                                   : make_desc_sw128(sA + k * 32, 16, 1024);
-          const uint64_t db = B_MN ? make_desc_sw128(sB + k * 2048, BK * 128, 1024)
-                                   : make_desc_sw128(sB + k * 32, 16, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: 8-row groups 1024 B apart, +32 B per 16-element K step inside the swizzle span.
+            // MN-major: 64-element MN groups BK*128 B apart (LBO), 8 K-rows = 1024 B (SBO), +2048 B per K step.
+            const uint64_t da = A_MN ? make_desc_sw128(sA + k * 2048, BK * 128, 1024)
+                                     : make_desc_sw128(sA + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_desc_sw128(sB + k * 2048, BK * 128, 1024)
+                                     : make_desc_sw128(sB + k * 32, 16, 1024);
+            umma_bf16(tmem_d, da, db, idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == S::kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&empty_bar[stage]);
-        if (++stage == S::kStages) { stage = 0; phase ^= 1; }
+        umma_commit(&tmem_full[acc]);   // with num_kb == 0 this arrives immediately (nothing outstanding)
       }
-      if (num_kb > 0) umma_commit(tmem_full_bar);
     }
   } else {
-    // ===== epilogue (warps 2..5; TMEM lane group = warp % 4) =====
+    // ===== epilogue (warps 0..3; TMEM lane group = warp % 4) =====
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int gm = m0 + row;
-    if (num_kb > 0) {
-      mbar_wait(tmem_full_bar, 0);
-      tc_fence_after();
-    }
     float ssq = 0.f;
+    int it = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
+      int m0, n0, z, kb0, num_kb;
+      unit_coords(u, m0, n0, z, kb0, num_kb);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int gm = m0 + row;
+      mbar_wait_relaxed(&tmem_full[acc], acc_phase);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < BN / 32 && num_kb > 0; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-      tmem_ld_wait();
-      const int gn0 = n0 + c * 32;
-      if (gm < p.M && gn0 < p.N) {
-        float v[32];
+      for (int c = 0; c < BN / 32 && num_kb > 0; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+        tmem_ld_wait();
+        const int gn0 = n0 + c * 32;
+        if (gm < p.M && gn0 < p.N) {
+          float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        const bool full = (gn0 + 32 <= p.N) && p.vec_ok;
-        if (p.splits > 1) {
-          // split-K: this CTA holds a partial product; split 0 also contributes the bias
-          float* crow = p.C32 + (size_t)gm * p.ldc + gn0;
-          if (p.bias && blockIdx.z == 0) {
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          const bool full = (gn0 + 32 <= p.N) && p.vec_ok;
+          if (p.splits > 1) {
+            // split-K: this unit holds a partial product; split 0 also contributes the bias
+            float* crow = p.C32 + (size_t)gm * p.ldc + gn0;
+            if (p.bias && z == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (gn0 + j < p.N) v[j] += __ldg(p.bias + gn0 + j);
+            }
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                atomicAdd(reinterpret_cast<float4*>(crow + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (gn0 + j < p.N) atomicAdd(crow + j, v[j]);
+            }
+            continue;
+          }
+          if (p.bias) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (gn0 + j < p.N) v[j] += __ldg(p.bias + gn0 + j);
           }
+          const size_t o = (size_t)gm * p.ldc + gn0;
           if (full) {
+            if (p.accumulate) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              atomicAdd(reinterpret_cast<float4*>(crow + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+              for (int j = 0; j < 32; j += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(p.C32 + o + j);
+                v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (p.sumsq) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) ssq = fmaf(v[j], v[j], ssq);
+            }
+            if (p.C32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(p.C32 + o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            if (p.C16) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 t;
+                t.x = pack_bf16(v[j], v[j + 1]); t.y = pack_bf16(v[j + 2], v[j + 3]);
+                t.z = pack_bf16(v[j + 4], v[j + 5]); t.w = pack_bf16(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(p.C16 + o + j) = t;
+              }
+            }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (gn0 + j < p.N) atomicAdd(crow + j, v[j]);
-          }
-          continue;
-        }
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (gn0 + j < p.N) v[j] += __ldg(p.bias + gn0 + j);
-        }
-        const size_t o = (size_t)gm * p.ldc + gn0;
-        if (full) {
-          if (p.accumulate) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 t = *reinterpret_cast<const float4*>(p.C32 + o + j);
-              v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (p.sumsq) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) ssq = fmaf(v[j], v[j], ssq);
-          }
-          if (p.C32) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(p.C32 + o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          }
-          if (p.C16) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 t;
-              t.x = pack_bf16(v[j], v[j + 1]); t.y = pack_bf16(v[j + 2], v[j + 3]);
-              t.z = pack_bf16(v[j + 4], v[j + 5]); t.w = pack_bf16(v[j + 6], v[j + 7]);
-              *reinterpret_cast<uint4*>(p.C16 + o + j) = t;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (gn0 + j < p.N) {
-              float x = v[j];
-              if (p.accumulate) x += p.C32[o + j];
-              if (p.relu) x = fmaxf(x, 0.f);
-              if (p.sumsq) ssq = fmaf(x, x, ssq);
-              if (p.C32) p.C32[o + j] = x;
-              if (p.C16) p.C16[o + j] = __float2bfloat16(x);
+            for (int j = 0; j < 32; ++j) {
+              if (gn0 + j < p.N) {
+                float x = v[j];
+                if (p.accumulate) x += p.C32[o + j];
+                if (p.relu) x = fmaxf(x, 0.f);
+                if (p.sumsq) ssq = fmaf(x, x, ssq);
+                if (p.C32) p.C32[o + j] = x;
+                if (p.C16) p.C16[o + j] = __float2bfloat16(x);
+              }
             }
           }
         }
       }
+      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
     if (p.sumsq) {
       const double tot = warp_sum((double)ssq);
@@ -228,7 +266,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<BN>(tmem_base);
+  if (warp == kMmaWarp) tmem_dealloc<2 * BN>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -286,7 +324,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     }
     configured = true;
   }
-  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.splits);
+  const long long units = (long long)((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM) * p.splits;
+  const int grid = (int)(units < sm_budget() ? units : sm_budget());
   kern<<<grid, kGemmThreads, S::kTotal, st>>>(tmA, tmB, p);
   return check_launch("gemm_bf16_tc");
 }
@@ -316,12 +355,13 @@ extern "C" int cmmvae_gemm_bf16_tc(const void* A, int lda, int transA, const voi
   const int total_kb = (K + BK - 1) / BK;
   // long-K, few-tile products (dh = dlogits Wout: K = genes) are split along K to fill the 148 SMs
   int splits = 1;
-  if (!relu && !C_bf16 && !accumulate && C_f32 && total_kb >= 64 && tiles256 * 2 <= kNumSMs && N > 128) {
-    splits = (int)(kNumSMs / tiles256);
+  const int sms = sm_budget();
+  if (!relu && !C_bf16 && !accumulate && C_f32 && total_kb >= 64 && tiles256 * 2 <= sms && N > 128) {
+    splits = (int)(sms / tiles256);
     if (splits > total_kb / 16) splits = total_kb / 16;
     if (splits < 1) splits = 1;
   }
-  const int BN = (N > 128 && (tiles256 >= 148 || splits > 1)) ? 256 : 128;
+  const int BN = (N > 128 && (tiles256 >= sms || splits > 1)) ? 256 : 128;
   CUtensorMap tmA, tmB;
   int rc;
   // K-major: inner = K, rows = M (or N).  MN-major: inner = M (or N), rows = K, box 64 x 64.

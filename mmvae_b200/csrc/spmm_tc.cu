@@ -10,14 +10,14 @@
 // it multiplies zeros; HBM traffic is the algorithmic minimum: CSR once (per N tile),
 // the bf16 weight once, Y once.  Values are rounded to bf16 when staged (the bf16 precision policy).
 //
-// CTA = 128 x 256 output tile, 320 threads:
-//   warp 0      TMA: B-operand tiles (Wt or dY, MN-major, 4 boxes of 64x64 per stage)
-//   warp 1      tcgen05.mma issue, accumulator in TMEM (256 columns)
-//   warps 2..9  two producer groups of 4 warps; group g builds the A tile of k-blocks kb = g (mod 2):
-//               zero the 16 KB tile, then scatter the CSR entries of the tile (located through the
-//               per-(cell, 64-gene window) pointer table) into the 128B-swizzled layout,
-//               fence.proxy.async, arrive on the stage's full barrier.  After the K loop the same warps
-//               run the epilogue.
+// Persistent CTAs (one per SM) walk 128 x 256 output tiles; 704 threads:
+//   warp 20       TMA: B-operand tiles (Wt or dY, MN-major, 4 boxes of 64x64 per stage)
+//   warp 21       tcgen05.mma issue (highest warp id = issue priority), two 256-column TMEM accumulators
+//   warps 0..15   four producer groups of 4 warps; group g builds the A tile of flat k-blocks f = g (mod 4),
+//                 i.e. owns ring stage g: zero the 16 KB tile, scatter the CSR entries of the tile (located
+//                 through the per-(cell, 64-gene window) pointer table, prefetched two tiles ahead) into the
+//                 128B-swizzled layout, fence.proxy.async, arrive on the stage's full barrier
+//   warps 16..19  epilogue: drain accumulator i while tile i+1 is being multiplied
 #include "tc.cuh"
 
 namespace cmmvae {
@@ -25,7 +25,8 @@ namespace cmmvae {
 using namespace tc;
 
 constexpr int SBM = 128, SBN = 256, SBK = 64, SSTAGES = 4;
-constexpr int kSpThreads = 320;
+constexpr int SNG = 4;             // producer groups (4 warps each); group g builds flat k-blocks f = g (mod SNG)
+constexpr int kSpThreads = 64 + 128 * SNG + 128;   // TMA + MMA + producer warps + 4 epilogue warps
 constexpr int kSpABytes = SBM * SBK * 2;   // 16 KB
 constexpr int kSpBBytes = SBN * SBK * 2;   // 32 KB
 constexpr int kSpStage = kSpABytes + kSpBBytes;
@@ -88,73 +89,100 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const SpParams p) {
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SSTAGES * kSpStage);
   uint64_t* empty_bar = full_bar + SSTAGES;
-  uint64_t* tmem_full_bar = empty_bar + SSTAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full = empty_bar + SSTAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * SBN, m0 = blockIdx.y * SBM;
+  // persistent: units (n tile fastest, then m tile, then K split) are dealt round-robin to the CTAs
   const int Kdim = BWD ? p.B : p.G;
+  const int Mdim = BWD ? p.G : p.B;
+  const int tiles_n = (p.H + SBN - 1) / SBN, tiles_m = (Mdim + SBM - 1) / SBM;
+  const int num_units = tiles_n * tiles_m * p.splits;
   const int total_kb = (Kdim + SBK - 1) / SBK;
   const int kb_per = (total_kb + p.splits - 1) / p.splits;
-  const int kb0 = blockIdx.z * kb_per;
-  const int num_kb = max(0, min(total_kb, kb0 + kb_per) - kb0);
+  auto unit_coords = [&](int u, int& m0, int& n0, int& z, int& kb0, int& num_kb) {
+    n0 = (u % tiles_n) * SBN;
+    m0 = ((u / tiles_n) % tiles_m) * SBM;
+    z = u / (tiles_n * tiles_m);
+    kb0 = z * kb_per;
+    num_kb = max(0, min(total_kb, kb0 + kb_per) - kb0);
+  };
 
-  if (warp == 0 && lane == 0) {
+  constexpr int kEpiWarp0 = 4 * SNG, kTmaWarp = 4 * SNG + 4, kMmaWarp = 4 * SNG + 5;   // MMA = highest id
+  if (warp == kTmaWarp && lane == 0) {
     prefetch_tmap(&tmB);
     for (int s = 0; s < SSTAGES; ++s) {
       mbar_init(&full_bar[s], 5);   // 1 TMA arrive.expect_tx + 4 producer warps
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<SBN>(tmem_slot);
+  if (warp == kMmaWarp) tmem_alloc<2 * SBN>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == kTmaWarp) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sB = smem + stage * kSpStage + kSpABytes;
-        mbar_expect_tx(&full_bar[stage], kSpBBytes);
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        int m0, n0, z, kb0, num_kb;
+        unit_coords(u, m0, n0, z, kb0, num_kb);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sB = smem + stage * kSpStage + kSpABytes;
+          mbar_expect_tx(&full_bar[stage], kSpBBytes);
 #pragma unroll
-        for (int j = 0; j < SBN / 64; ++j)
-          tma_load_2d(sB + j * (SBK * 128), &tmB, &full_bar[stage], n0 + 64 * j, (kb0 + kb) * SBK);
-        if (++stage == SSTAGES) { stage = 0; phase ^= 1; }
+          for (int j = 0; j < SBN / 64; ++j)
+            tma_load_2d(sB + j * (SBK * 128), &tmB, &full_bar[stage], n0 + 64 * j, (kb0 + kb) * SBK);
+          if (++stage == SSTAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(SBM, SBN, BWD ? 1 : 0, 1);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+      int it = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
+        int m0, n0, z, kb0, num_kb;
+        unit_coords(u, m0, n0, z, kb0, num_kb);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t sA = smem_u32(smem + stage * kSpStage);
-        const uint32_t sB = sA + kSpABytes;
+        const uint32_t tmem_d = tmem_base + acc * SBN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * kSpStage);
+          const uint32_t sB = sA + kSpABytes;
 #pragma unroll
-        for (int k = 0; k < SBK / 16; ++k) {
-          const uint64_t da = BWD ? make_desc_sw128(sA + k * 2048, SBK * 128, 1024)
-                                  : make_desc_sw128(sA + k * 32, 16, 1024);
-          const uint64_t db = make_desc_sw128(sB + k * 2048, SBK * 128, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < SBK / 16; ++k) {
+            const uint64_t da = BWD ? make_desc_sw128(sA + k * 2048, SBK * 128, 1024)
+                                    : make_desc_sw128(sA + k * 32, 16, 1024);
+            const uint64_t db = make_desc_sw128(sB + k * 2048, SBK * 128, 1024);
+            umma_bf16(tmem_d, da, db, idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == SSTAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&empty_bar[stage]);
-        if (++stage == SSTAGES) { stage = 0; phase ^= 1; }
+        umma_commit(&tmem_full[acc]);
       }
-      if (num_kb > 0) umma_commit(tmem_full_bar);
     }
-  } else {
-    // ===== A-tile producers (two groups), then epilogue =====
-    const int group = (warp - 2) >> 2;                 // 0 or 1
-    const int t = (warp - 2 - group * 4) * 32 + lane;  // 0..127 inside the group
-    // this thread's 128-byte line of the tile, its swizzle phase, its CSR row and window index
+  } else if (warp < kEpiWarp0) {
+    // ===== A-tile producers: SNG groups of 4 warps; group g builds flat k-blocks f = g (mod SNG) =====
+    const int group = warp >> 2;                       // 0 .. SNG-1
+    const int t = (warp - group * 4) * 32 + lane;      // 0..127 inside the group
+    // this thread's 128-byte line of the tile and its swizzle phase
     int line_off, swz;
     if (!BWD) {                       // thread = cell row of the tile; window advances with kb
       line_off = (t >> 3) * 1024 + (t & 7) * 128;
@@ -164,46 +192,77 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const SpParams p) {
       line_off = h * (SBK * 128) + (kk >> 3) * 1024 + (kk & 7) * 128;
       swz = kk & 7;
     }
-    auto window_ptrs = [&](int kb, int& q0, int& q1, int& win_start) {
-      // CSR range [q0,q1) of the entries this thread stages for k-block kb (coalesced table reads)
-      q0 = q1 = 0;
-      win_start = 0;
-      if (kb >= num_kb) return;
-      const int kbg = kb0 + kb;
-      int b, w;
-      if (!BWD) { b = m0 + t; w = kbg; } else { b = kbg * 64 + (t & 63); w = (m0 >> 6) + (t >> 6); }
-      if (b < p.B && w < p.ntp - 1) {
-        q0 = __ldg(p.tp + (size_t)w * p.B + b);
-        q1 = __ldg(p.tp + (size_t)(w + 1) * p.B + b);
+    // cursor over this CTA's flattened (unit, k-block) sequence
+    struct Seq { int u, kb, nkb, m0, kb0; };
+    auto seq_load = [&](Seq& s) {
+      if (s.u < num_units) {
+        int n0, z;
+        unit_coords(s.u, s.m0, n0, z, s.kb0, s.nkb);
+      } else {
+        s.nkb = 0; s.m0 = 0; s.kb0 = 0;
       }
-      win_start = w * 64;
+    };
+    auto seq_advance = [&](Seq& s, int steps) {
+      while (steps > 0 && s.u < num_units) {
+        const int room = s.nkb - s.kb;
+        if (steps < room) { s.kb += steps; return; }
+        steps -= room;
+        s.u += gridDim.x; s.kb = 0;
+        seq_load(s);
+      }
+    };
+    struct Ptr { int q0, q1, win; };
+    auto window_ptrs = [&](const Seq& s, Ptr& o) {
+      // CSR range [q0,q1) of the entries this thread stages for the k-block at cursor s (coalesced reads)
+      o.q0 = o.q1 = 0;
+      o.win = 0;
+      if (s.u >= num_units) return;
+      const int kbg = s.kb0 + s.kb;
+      int b, w;
+      if (!BWD) { b = s.m0 + t; w = kbg; } else { b = kbg * 64 + (t & 63); w = (s.m0 >> 6) + (t >> 6); }
+      if (b < p.B && w < p.ntp - 1) {
+        o.q0 = __ldg(p.tp + (size_t)w * p.B + b);
+        o.q1 = __ldg(p.tp + (size_t)(w + 1) * p.B + b);
+      }
+      o.win = w * 64;
     };
     constexpr int E = 8;   // packed records prefetched into registers per (thread, window)
-    auto load_entries = [&](int q0, int q1, uint32_t (&rec)[E]) {
-      const int n = q1 - q0;
-      const uint32_t* src = p.packed + q0;
+    auto load_entries = [&](const Ptr& q, uint32_t (&rec)[E]) {
+      const int n = q.q1 - q.q0;
+      const uint32_t* src = p.packed + q.q0;
 #pragma unroll
       for (int u = 0; u < E; ++u) rec[u] = (u < n) ? __ldg(src + u) : 0u;
     };
-    // Software pipeline per group, iteration i <-> k-block kb = group + 2 i:
-    //   pointers P(i+2) and entries E(i+1) are requested while tile i is built, so every global load has a
-    //   full iteration to land.  Three pointer slots and two entry slots rotate by NAME (the body is
-    //   instantiated six times per trip) so no register moves touch in-flight loads.
-    struct Ptr { int q0, q1, win; };
+    // Software pipeline per group over its flat indices f = group, group+2, ...: pointers for f+4 and
+    // entries for f+2 are requested while tile f is built, so every global load has a full iteration to
+    // land.  Three pointer slots and two entry slots rotate by NAME (six body instances per trip) so no
+    // register moves touch in-flight loads.
+    int total_f = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      int m0, n0, z, kb0, nkb;
+      unit_coords(u, m0, n0, z, kb0, nkb);
+      total_f += nkb;
+    }
+    Seq cur_s{(int)blockIdx.x, 0, 0, 0, 0};
+    seq_load(cur_s);
+    seq_advance(cur_s, group);            // cursor at flat index f = group
+    Seq fut_s = cur_s;                    // will run 4 flat steps (two group iterations) ahead
     Ptr P0, P1, P2;
     uint32_t E0[E], E1[E];
-    window_ptrs(group, P0.q0, P0.q1, P0.win);
-    window_ptrs(group + 2, P1.q0, P1.q1, P1.win);
-    load_entries(P0.q0, P0.q1, E0);
+    window_ptrs(fut_s, P0);
+    seq_advance(fut_s, SNG);
+    window_ptrs(fut_s, P1);
+    load_entries(P0, E0);
     const int bar_id = 1 + group;
     const uint32_t smem_base = smem_u32(smem);
-    auto body = [&](int kb, const Ptr& cur, const Ptr& nxt, Ptr& fut, const uint32_t (&ec)[E], uint32_t (&en)[E]) {
-      if (kb >= num_kb) return;
-      const int stage = kb % SSTAGES;
-      const uint32_t phase = (kb / SSTAGES) & 1;
-      window_ptrs(kb + 4, fut.q0, fut.q1, fut.win);
-      load_entries(nxt.q0, nxt.q1, en);
-      mbar_wait(&empty_bar[stage], phase ^ 1);
+    auto body = [&](int f, const Ptr& cur, const Ptr& nxt, Ptr& fut, const uint32_t (&ec)[E], uint32_t (&en)[E]) {
+      if (f >= total_f) return;
+      const int stage = f % SSTAGES;
+      const uint32_t phase = (f / SSTAGES) & 1;
+      seq_advance(fut_s, SNG);
+      window_ptrs(fut_s, fut);
+      load_entries(nxt, en);
+      mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
       const uint32_t tile = smem_base + stage * kSpStage;
       // zero the 16 KB tile cooperatively (consecutive threads -> consecutive 16-byte chunks: conflict free)
 #pragma unroll
@@ -226,28 +285,32 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const SpParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[stage]);
     };
-    for (int kb = group; kb < num_kb; kb += 12) {
-      body(kb, P0, P1, P2, E0, E1);
-      body(kb + 2, P1, P2, P0, E1, E0);
-      body(kb + 4, P2, P0, P1, E0, E1);
-      body(kb + 6, P0, P1, P2, E1, E0);
-      body(kb + 8, P1, P2, P0, E0, E1);
-      body(kb + 10, P2, P0, P1, E1, E0);
+    for (int f = group; f < total_f; f += 6 * SNG) {
+      body(f, P0, P1, P2, E0, E1);
+      body(f + SNG, P1, P2, P0, E1, E0);
+      body(f + 2 * SNG, P2, P0, P1, E0, E1);
+      body(f + 3 * SNG, P0, P1, P2, E1, E0);
+      body(f + 4 * SNG, P1, P2, P0, E0, E1);
+      body(f + 5 * SNG, P2, P0, P1, E1, E0);
     }
-
-    // ----- epilogue: group g drains accumulator columns [128 g, 128 g + 128) -----
-    if (num_kb > 0) {
-      mbar_wait(tmem_full_bar, 0);
-      tc_fence_after();
-      const int qd = warp & 3;
-      const int row = qd * 32 + lane;
+  } else {
+    // ===== the last 4 warps: epilogue (TMEM lane group = warp % 4): drain unit i while unit i+1 is computed =====
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    float ssq = 0.f;
+    int it = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
+      int m0, n0, z, kb0, num_kb;
+      unit_coords(u, m0, n0, z, kb0, num_kb);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
       const int gm = m0 + row;
-      const int Mdim = BWD ? p.G : p.B;
-      float ssq = 0.f;
+      mbar_wait_relaxed(&tmem_full[acc], acc_phase);
+      tc_fence_after();
 #pragma unroll 1
-      for (int c = group * 4; c < group * 4 + 4; ++c) {
+      for (int c = 0; c < SBN / 32 && num_kb > 0; ++c) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(c * 32), r);
+        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * SBN + c * 32), r);
         tmem_ld_wait();
         const int gn0 = n0 + c * 32;
         if (gm < Mdim && gn0 < p.H) {
@@ -256,7 +319,7 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const SpParams p) {
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           float* orow = p.out + (size_t)gm * p.H + gn0;
           const bool full = gn0 + 32 <= p.H;
-          if (!BWD && p.bias && blockIdx.z == 0) {
+          if (!BWD && p.bias && z == 0) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (gn0 + j < p.H) v[j] += __ldg(p.bias + gn0 + j);
@@ -287,15 +350,18 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const SpParams p) {
           }
         }
       }
-      if (BWD && p.sumsq) {
-        const double tot = warp_sum((double)ssq);
-        if (lane == 0 && tot != 0.0) atomicAdd(p.sumsq, tot);
-      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+    if (BWD && p.sumsq) {
+      const double tot = warp_sum((double)ssq);
+      if (lane == 0 && tot != 0.0) atomicAdd(p.sumsq, tot);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<SBN>(tmem_base);
+  if (warp == kMmaWarp) tmem_dealloc<2 * SBN>(tmem_base);
 }
 
 int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
@@ -354,14 +420,16 @@ extern "C" int cmmvae_csr_linear_fwd_tc(const void* packed, const int32_t* tile_
   p.bias = bias; p.out = Y; p.sumsq = nullptr;
   const int tiles = ((B + SBM - 1) / SBM) * ((H + SBN - 1) / SBN);
   const int total_kb = (G + SBK - 1) / SBK;
-  int splits = tiles >= kNumSMs ? 1 : kNumSMs / tiles;
+  const int sms = sm_budget();
+  int splits = tiles >= sms ? 1 : sms / tiles;
   if (splits > total_kb / 8) splits = total_kb / 8;
   if (splits < 1) splits = 1;
   p.splits = splits;
   CUtensorMap tm;
   if (int rc = make_tmap_bf16(&tm, Wt_bf16, (uint64_t)H, (uint64_t)G, (uint64_t)H, 64, SBK)) return rc;
   if (splits > 1) cudaMemsetAsync(Y, 0, sizeof(float) * (size_t)B * H, st);
-  dim3 grid((H + SBN - 1) / SBN, (B + SBM - 1) / SBM, splits);
+  const int units = tiles * splits;
+  dim3 grid(units < sms ? units : sms);
   return launch_spmm_tc<false>(tm, p, grid, st);
 }
 
@@ -374,6 +442,7 @@ extern "C" int cmmvae_csr_linear_bwd_w_tc(const void* packed, const int32_t* til
   p.bias = nullptr; p.out = dWt; p.splits = 1; p.sumsq = sumsq_out;
   CUtensorMap tm;
   if (int rc = make_tmap_bf16(&tm, dY_bf16, (uint64_t)H, (uint64_t)B, (uint64_t)H, 64, SBK)) return rc;
-  dim3 grid((H + SBN - 1) / SBN, (G + SBM - 1) / SBM, 1);
+  const int units = ((H + SBN - 1) / SBN) * ((G + SBM - 1) / SBM);
+  dim3 grid(units < sm_budget() ? units : sm_budget());
   return launch_spmm_tc<true>(tm, p, grid, (cudaStream_t)stream);
 }

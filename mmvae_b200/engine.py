@@ -164,16 +164,18 @@ class FlatGroup:
 
     def clip_adam(self, norm_sq: torch.Tensor, max_norm: Optional[float], grad_scale: float = 1.0):
         self.step_count += 1
-        for lo, hi, g, mv in self.ranges:
+        self._ag_pending = []
+        for i, (lo, hi, g, mv) in enumerate(self.ranges):
             n = hi - lo
             ops.clip_adam(self.p[lo:hi], g, self.m[mv:mv + n], self.v[mv:mv + n], self.p16[lo:hi], norm_sq,
                           max_norm or 0.0, grad_scale, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
                           self.step_count)
-        if self.sharded:   # publish the refreshed bf16 shards; consumers wait just before they read them
-            self._ag_pending = []
-            for (lo, hi), (own_lo, own_hi, _, _) in zip(self.seg_bounds, self.ranges):
+            if self.sharded and i < len(self.seg_bounds):
+                # publish the refreshed bf16 shard right away (segment 0 = first-layer weight is needed first by
+                # the next forward); consumers wait just before they read it
+                slo, shi = self.seg_bounds[i]
                 self._ag_pending.append(torch.distributed.all_gather_into_tensor(
-                    self.p16[lo:hi], self.p16[own_lo:own_hi], async_op=True))
+                    self.p16[slo:shi], self.p16[lo:hi], async_op=True))
 
     def wait_shadow(self, i: Optional[int] = None):
         """make the current stream wait for the all-gather of segment i's bf16 shadow (all if None)"""
@@ -368,6 +370,7 @@ class StepEngine:
         self._ws: Dict[tuple, torch.Tensor] = {}
         self.timers: Optional[Dict[str, list]] = None   # name -> [(start_event, end_event)] when profiling
         self._seed = 0x5EED
+        self.nccl_sms = 24                  # SMs left to communication kernels when world > 1
         self.spmm_tc = True                 # bf16 policy: expert-encoder SpMM on the tensor pipe ...
         self.spmm_tc_min_density = 0.015    # ... when the batch is at least this dense (else gather kernel)
         self.world = 1
@@ -543,6 +546,12 @@ class StepEngine:
         G = enc[0].K
         Z = self.Z
         self.world = dp.world_size()
+        # NCCL's all-gather (start of the forward) and reduce-scatter (backward after dWout) kernels hold some
+        # SMs while they run: during those windows the persistent kernels plan for the remaining SMs so that
+        # no planned CTA has to wait for a free SM; elsewhere they use all 148
+        comm_budget = (lambda on: ops.set_sm_budget(148 - self.nccl_sms if on else 148)) if self.world > 1 \
+            else (lambda on: None)
+        comm_budget(True)
         gscale = 1.0 / self.world
         bf = self.precision == "bf16"
         n_adv = min(len(self.adv), self.n_hidden)   # zip(hidden, adversarials) truncates (cmmvae_model.py:67-70)
@@ -594,6 +603,7 @@ class StepEngine:
         h32, h16 = x32, x16
         out = dec[-1]
         gexp.wait_shadow(1)
+        comm_budget(False)      # all-gathers are done: decoder + dWout run on every SM
         fused = self._tc(out.K) and bf
         if fused:
             ldd = _ceil(G, 64)
@@ -651,6 +661,7 @@ class StepEngine:
             # the output layer's gradient (half of the expert group) is final: start exchanging it now so
             # the transfer overlaps the rest of the backward pass
             pending = [gexp.exchange_segment_async(1)]
+            comm_budget(True)
             ev = self._t0("dh_gemm")
             ops.gemm(dl, 0, out.W16, 1, B, H1, G, C32=dh)                 # dh = dlogits Wout
             self._t1(ev)
@@ -706,6 +717,7 @@ class StepEngine:
         for w in pending:
             if w is not None:
                 w.wait()
+        comm_budget(False)
         ev = self._t0("norm+clip_adam")
         gvae.grad_norm_sq(s_norm(0))
         gexp.grad_norm_sq(s_norm(1), skip=[enc[0].lin.weight, out.lin.weight] if fuse_norm else None)

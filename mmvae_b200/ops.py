@@ -50,6 +50,10 @@ def launch_count() -> int:
     return int(lib().cmmvae_launch_count())
 
 
+def set_sm_budget(sms: int) -> None:
+    _check(lib().cmmvae_set_sm_budget(int(sms)), "set_sm_budget")
+
+
 # ------------------------------------------------------------------------------------------ sparse
 def csr_linear_fwd(crow, col, val, G: int, Wt, bias, out=None):
     """Y = X_csr @ Wt + bias;  Wt is [G,H] (f32|bf16), contiguous."""
