@@ -192,7 +192,7 @@ def cpu_reference_leg(config, B, steps, warmup, threads=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=[2, 3])
@@ -340,6 +340,12 @@ def main():
             torch.distributed.destroy_process_group()
         return
     pk, pk_kind = peaks()
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this shape (ncu --set full)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_topk_dram_bytes.json")))
+        traffic = tj.get("decoder_mse_fused_kernel") if (B == 1024 and args.config == 2) else None
+    except Exception:  # noqa: BLE001
+        pass
     flops = 2.0 * B * G_HUMAN * H1
     ach = flops / (t_dec * 1e-3) / 1e12 if t_dec > 0 else 0.0
     peak = pk["bf16_tflops_sustained"]
@@ -354,7 +360,7 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"kernel": "decoder_mse_fused_kernel (K5-K7: tcgen05 GEMM + ReLU + sum-MSE-vs-CSR epilogue)",
                      "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                     "traffic": None, "peak_source": f"{pk_kind} bf16_tflops_sustained (kernel timed inside a step)",
+                     "traffic": traffic, "peak_source": f"{pk_kind} bf16_tflops_sustained (kernel timed inside a step)",
                      "ms_per_launch": t_dec, "flops_per_launch": flops},
         "kernels_ms": {"decoder_mse_fused": t_dec, "dWout_gemm": t_dw, "dh_gemm": t_dh, "csr_linear_fwd": t_spmm,
                        "csr_linear_bwd_w+bn_bwd": t_spbw, "norm+clip_adam": t_adam},

@@ -17,7 +17,7 @@ import torch
 from mmvae_b200 import layers as L
 from mmvae_b200.config import AutogradConfig
 from mmvae_b200.constants import REGISTRY_KEYS as RK
-from mmvae_b200.engine import FlatAdam, StepEngine
+from mmvae_b200.engine import FlatAdam, StepEngine, UnsupportedTopology
 from mmvae_b200.models.base_model import BaseModel
 from mmvae_b200.modules import CMMVAE
 from mmvae_b200.modules.base.components import Adversarial
@@ -67,13 +67,19 @@ class CMMVAEModel(BaseModel):
             raise NotImplementedError("only clip-by-norm is implemented in the fused step")
         return float(val)
 
-    def engine(self) -> StepEngine:
+    def engine(self) -> Optional[StepEngine]:
+        """The fused step engine, or None when the topology is outside it (conditional layers, LayerNorm,
+        non-ReLU activations): those models train through the module route (same kernels under autograd)."""
         if self._engine is None:
             ac = self.autograd_config
             clip = {"vae": self._clip_val(ac.vae_gradient_clip), "expert": self._clip_val(ac.expert_gradient_clip),
                     "adversarial": self._clip_val(ac.adversarial_gradient_clip)}
-            self._engine = StepEngine(self.module, adv_weight=self.adv_weight, clip=clip)
-        return self._engine
+            try:
+                self._engine = StepEngine(self.module, adv_weight=self.adv_weight, clip=clip)
+            except UnsupportedTopology as why:
+                self._engine = False
+                self._module_route_reason = str(why)
+        return self._engine or None
 
     def configure_optimizers(self, optim_cls="Adam"):
         """``[Adam(expert_0), ..., Adam(vae), Adam(adv_1), ...]`` + ``self.optimizer_map`` with the
@@ -81,11 +87,25 @@ class CMMVAEModel(BaseModel):
         if optim_cls != "Adam":
             raise NotImplementedError("the fused optimizer implements torch.optim.Adam semantics only")
         eng = self.engine()
+        if eng is None:
+            return self._configure_optimizers_module_route()
         optim_dict = {"experts": {eid: FlatAdam(eng.groups[f"experts/{eid}"]) for eid in self.module.experts.keys()},
                       "vae": FlatAdam(eng.groups["vae"])}
         if len(self.module.adversarials):
             optim_dict["adversarials"] = {i: FlatAdam(eng.groups[f"adversarials/{i}"])
                                           for i in range(1, len(self.module.adversarials) + 1)}
+        optimizers = []
+        self.optimizer_map = convert_to_flat_list_and_map(optim_dict, optimizers)
+        return optimizers
+
+    def _configure_optimizers_module_route(self):
+        """same optimizer list / map, stock Adam objects (lr 5e-3, wd 1e-6) over ordinary parameters"""
+        adam = lambda params: torch.optim.Adam(params, lr=5e-3, weight_decay=1e-6)  # noqa: E731
+        optim_dict = {"experts": {eid: adam(m.parameters()) for eid, m in self.module.experts.items()},
+                      "vae": adam(self.module.vae.parameters())}
+        if len(self.module.adversarials):
+            optim_dict["adversarials"] = {i: adam(m.parameters())
+                                          for i, m in enumerate(self.module.adversarials, start=1)}
         optimizers = []
         self.optimizer_map = convert_to_flat_list_and_map(optim_dict, optimizers)
         return optimizers
@@ -102,7 +122,7 @@ class CMMVAEModel(BaseModel):
         return resolve(self.optimizer_map)
 
     def state_dict(self, *args, **kwargs):
-        if self._engine is not None:     # ZeRO-1 sharded fp32 master copies are gathered before export
+        if self._engine:     # ZeRO-1 sharded fp32 master copies are gathered before export
             for g in self._engine.groups.values():
                 g.sync_master()
         return super().state_dict(*args, **kwargs)
@@ -122,10 +142,70 @@ class CMMVAEModel(BaseModel):
                 "cellxgene_manager.py:44); densified input is outside the hot path")
         return L.csr_parts(x)
 
+    def _adversary_losses(self, hidden, labels, expert_id, through_grl: bool):
+        """sum over conditions of CE(sum) per (hidden representation, adversary) pair; logs every term"""
+        from mmvae_b200.modules.base.components import GradientReversalFunction
+        tag = "generator" if through_grl else "discriminator"
+        losses = []
+        for i, (h, adversary) in enumerate(zip(hidden, self.module.adversarials), start=1):
+            h = GradientReversalFunction.apply(h, 1) if through_grl else h.detach()
+            code = adversary.encoder(h)
+            terms = {c: self.adversarial_criterion(adversary.heads[c](code), y) for c, y in labels.items()}
+            for c, v in terms.items():
+                self.auto_log({c: v}, tags=[f"{tag}_{i}", self.stage_name, expert_id, RK.ADV_LOSS], key_pos="last")
+            total = torch.stack(list(terms.values())).sum()
+            self.auto_log({"summed": total}, tags=[f"{tag}_{i}", self.stage_name, expert_id, RK.ADV_LOSS],
+                          key_pos="last")
+            losses.append(total)
+        return losses
+
+    def _training_step_module_route(self, batch) -> None:
+        """training_step for topologies outside the fused engine: the nn.Modules run on the same CUDA kernels
+        through autograd Functions, optimisers are stock Adam; order of operations as in the reference
+        (cmmvae_model.py:138-217): discriminator update first, then the generator loss through the GRL."""
+        x, metadata, expert_id = batch
+        opts = self.get_optimizers()
+        vae_opt, expert_opt = opts["vae"], opts["experts"][expert_id]
+        adv_opts = opts.get("adversarials") or {}
+        for o in [vae_opt, expert_opt, *adv_opts.values()]:
+            o.zero_grad()
+        qz, pz, z, xhats, hidden = self.module(x=x, metadata=metadata, expert_id=expert_id)
+        ld = self.module.vae.elbo(qz, pz, x, xhats[expert_id], self.kl_annealing_fn.kl_weight)
+        ld["Mean"], ld["Variance"] = qz.mean.mean(), qz.variance.mean()
+        total = ld[RK.LOSS]
+        ac = self.autograd_config
+        if len(self.module.adversarials):
+            labels = self._labels(metadata, z.device)
+            for i, (loss_i, opt_i) in enumerate(zip(self._adversary_losses(hidden, labels, expert_id, False),
+                                                    adv_opts.values()), start=1):
+                self.manual_backward(loss_i)
+                self.log_gradient_norms({f"discriminator_{i}": opt_i}, tag_prefix="grad_norms")
+                if ac.adversarial_gradient_clip:
+                    self.clip_gradients(opt_i, *ac.adversarial_gradient_clip)
+                opt_i.step()
+                opt_i.zero_grad()
+            for loss_i in self._adversary_losses(hidden, labels, expert_id, True):
+                total = total + loss_i * self.adv_weight
+        self.manual_backward(total)
+        ld[RK.LOSS] = total
+        self.log_gradient_norms({"vae": vae_opt, f"expert_{expert_id}": expert_opt}, tag_prefix="grad_norms")
+        for key, o in adv_opts.items():
+            self.log_gradient_norms({f"generator_{key}": o}, tag_prefix="grad_norms")
+        if ac.vae_gradient_clip:
+            self.clip_gradients(vae_opt, *ac.vae_gradient_clip)
+        if ac.expert_gradient_clip:
+            self.clip_gradients(expert_opt, *ac.expert_gradient_clip)
+        vae_opt.step()
+        expert_opt.step()
+        self.kl_annealing_fn.step()
+        self.auto_log(ld, tags=[self.stage_name, expert_id])
+
     def training_step(self, batch, batch_idx: int) -> None:
         x, metadata, expert_id = batch
         metadata["species"] = expert_id
         eng = self.engine()
+        if eng is None:
+            return self._training_step_module_route(batch)
         crow, col, val, nnz = self._csr(x)
         labels = self._labels(metadata, x.device) if len(self.module.adversarials) else None
         rec = eng.train_step(expert_id, crow, col, val, nnz, self.kl_annealing_fn.kl_weight, labels=labels)
@@ -157,9 +237,14 @@ class CMMVAEModel(BaseModel):
 
     def validation_step(self, batch):
         x, metadata, expert_id = batch
-        crow, col, val, _ = self._csr(x)
-        out = self.engine().eval_step(expert_id, crow, col, val, kl_weight=self.kl_annealing_fn.kl_weight)
-        loss_dict = {k: out[k] for k in (RK.LOSS, RK.RECON_LOSS, RK.KL_LOSS, RK.KL_WEIGHT)}
+        if self.engine() is None:
+            with torch.no_grad():
+                qz, pz, z, xhats, _ = self.module(x, metadata, expert_id)
+                loss_dict = self.module.vae.elbo(qz, pz, x, xhats[expert_id], self.kl_annealing_fn.kl_weight)
+        else:
+            crow, col, val, _ = self._csr(x)
+            out = self.engine().eval_step(expert_id, crow, col, val, kl_weight=self.kl_annealing_fn.kl_weight)
+            loss_dict = {k: out[k] for k in (RK.LOSS, RK.RECON_LOSS, RK.KL_LOSS, RK.KL_WEIGHT)}
         self.auto_log(loss_dict, tags=[self.stage_name, expert_id])
         if self.trainer.validating:
             self.log("val_loss", loss_dict[RK.LOSS], logger=False, on_epoch=True)

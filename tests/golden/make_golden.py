@@ -49,7 +49,7 @@ class _Eps:
         return self.next.to(dtype=dtype, device=device)
 
 
-def build(species, with_adv, labels_dir, kl_fn, adv_weight):
+def build(species, with_adv, labels_dir, kl_fn, adv_weight, conditional=False):
     d = DIMS
     torch.manual_seed(0)
     experts = Experts([
@@ -60,11 +60,19 @@ def build(species, with_adv, labels_dir, kl_fn, adv_weight):
             decoder_config=FCBlockConfig(layers=[d["H2"], d["H1"], d["G"][s]], dropout_rate=0.0,
                                          activation_fn=torch.nn.ReLU),
         ) for s in species])
+    cond_kwargs = {}
+    if conditional:   # the topology of configs/model/human_only.yaml:53-79 (parallel conditionals + concat layer)
+        from cmmvae.modules.base import ConcatBlockConfig
+        cond_kwargs = dict(
+            conditional_config=FCBlockConfig(layers=[d["Z"]], use_layer_norm=True, activation_fn=None),
+            concat_config=ConcatBlockConfig(activation_fn=torch.nn.ReLU),
+            conditionals_directory=labels_dir, conditionals=["assay", "dataset_id", "species"],
+            selection_order=["parallel"])
     vae = CLVAE(
         encoder_config=FCBlockConfig(layers=[d["H2"], d["Hv"]], use_batch_norm=True,
                                      activation_fn=torch.nn.ReLU, return_hidden=True),
         decoder_config=FCBlockConfig(layers=[d["Z"], d["Hv"], d["H2"]], activation_fn=torch.nn.ReLU),
-        latent_dim=d["Z"], hidden_z=with_adv)
+        latent_dim=d["Z"], hidden_z=with_adv, **cond_kwargs)
     advs = []
     if with_adv:
         Adversarial.labels.clear()
@@ -91,15 +99,19 @@ def build(species, with_adv, labels_dir, kl_fn, adv_weight):
     return model
 
 
-def run_case(name, species_schedule, with_adv, kl_fn, adv_weight, density=0.10):
+def run_case(name, species_schedule, with_adv, kl_fn, adv_weight, density=0.10, conditional=False):
+    import random
     d = DIMS
     out = {}
     with tempfile.TemporaryDirectory() as tmp:
         os.makedirs(os.path.join(tmp, "human"))
+        os.makedirs(os.path.join(tmp, "shared"))
         for cond, n in CONDITIONS.items():
             pd.DataFrame([f"{cond}_{i}" for i in range(n)]).to_csv(
                 os.path.join(tmp, "human", f"unique_expression_{cond}.csv"), header=False, index=False)
-        model = build(sorted(set(species_schedule)), with_adv, tmp, kl_fn, adv_weight)
+        pd.DataFrame([f"assay_{i}" for i in range(CONDITIONS["assay"])]).to_csv(
+            os.path.join(tmp, "shared", "unique_expression_assay.csv"), header=False, index=False)
+        model = build(sorted(set(species_schedule)), with_adv, tmp, kl_fn, adv_weight, conditional)
     model.train()
     eps_src = _Eps()
     _tdn._standard_normal = eps_src
@@ -121,6 +133,7 @@ def run_case(name, species_schedule, with_adv, kl_fn, adv_weight, density=0.10):
         out[f"step{t}/kl_weight_in"] = np.float64(model.kl_annealing_fn.kl_weight)
         model.logged.clear()
         model.pre_clip_grads.clear()
+        random.seed(4242 + t)   # ConditionalLayers shuffles its (parallel) order with python's random
         model.training_step((x, meta, sp), t)
         out[f"step{t}/species"] = np.array(sp)
         out[f"step{t}/crow"], out[f"step{t}/col"], out[f"step{t}/val"] = crow, col, val
@@ -147,7 +160,10 @@ def run_case(name, species_schedule, with_adv, kl_fn, adv_weight, density=0.10):
     meta = pd.DataFrame({c: [f"{c}_0"] * d["B"] for c in CONDITIONS})
     model.logged.clear()
     with torch.no_grad():
+        random.seed(777)
         model.validation_step((x, meta, sp))
+        eps_src.next = eps
+        random.seed(777)
         qz, pz, z, xhats, hid = model.module(x, meta, sp)
     out["val/species"] = np.array(sp)
     out["val/crow"], out["val/col"], out["val/val"], out["val/eps"] = crow, col, val, eps.numpy()
@@ -159,6 +175,7 @@ def run_case(name, species_schedule, with_adv, kl_fn, adv_weight, density=0.10):
     out["meta/genes_keys"] = np.array(list(d["G"].keys()))
     out["meta/genes_vals"] = np.array(list(d["G"].values()))
     out["meta/with_adv"] = np.array(with_adv)
+    out["meta/conditional"] = np.array(conditional)
     out["meta/adv_weight"] = np.float64(adv_weight if adv_weight else 1.0)
     out["meta/n_steps"] = np.array(n_steps)
     out["meta/torch_version"] = np.array(torch.__version__)
@@ -171,3 +188,4 @@ if __name__ == "__main__":
     run_case("core_human", ["human", "human", "human"], False, KLAnnealingFn(0.5), None)
     run_case("two_species_adv", ["human", "mouse", "human", "mouse"], True,
              LinearKLAnnealingFn(min_kl_weight=0.1, max_kl_weight=1.0, warmup_steps=1, climax_steps=4), 2.0)
+    run_case("human_conditional", ["human", "human", "human"], True, KLAnnealingFn(0.5), 1.0, conditional=True)

@@ -18,6 +18,7 @@ class GoldenCase:
         self.dims = dict(H1=H1, H2=H2, Hv=Hv, Z=Z, B=B)
         self.genes = {str(k): int(v) for k, v in zip(self.z["meta/genes_keys"], self.z["meta/genes_vals"])}
         self.with_adv = bool(self.z["meta/with_adv"])
+        self.conditional = bool(self.z["meta/conditional"]) if "meta/conditional" in self.z.files else False
         self.adv_weight = float(self.z["meta/adv_weight"])
         self.n_steps = int(self.z["meta/n_steps"])
 
@@ -100,9 +101,12 @@ def build_b200_model(gc: "GoldenCase", tmpdir, kl_fn=None, dropout=0.0):
 
     d = gc.dims
     os.makedirs(os.path.join(tmpdir, "human"), exist_ok=True)
+    os.makedirs(os.path.join(tmpdir, "shared"), exist_ok=True)
     for cond, n in CONDITIONS.items():
         pd.DataFrame([f"{cond}_{i}" for i in range(n)]).to_csv(
             os.path.join(tmpdir, "human", f"unique_expression_{cond}.csv"), header=False, index=False)
+    pd.DataFrame([f"assay_{i}" for i in range(CONDITIONS["assay"])]).to_csv(
+        os.path.join(tmpdir, "shared", "unique_expression_assay.csv"), header=False, index=False)
     experts = Experts([
         Expert(id=s,
                encoder_config=FCBlockConfig(layers=[gc.genes[s], d["H1"], d["H2"]], dropout_rate=dropout,
@@ -110,10 +114,18 @@ def build_b200_model(gc: "GoldenCase", tmpdir, kl_fn=None, dropout=0.0):
                decoder_config=FCBlockConfig(layers=[d["H2"], d["H1"], gc.genes[s]], dropout_rate=0.0,
                                             activation_fn=torch.nn.ReLU))
         for s in gc.species_present()])
+    cond_kwargs = {}
+    if gc.conditional:   # topology of configs/model/human_only.yaml:53-79
+        from mmvae_b200.modules.base import ConcatBlockConfig
+        cond_kwargs = dict(
+            conditional_config=FCBlockConfig(layers=[d["Z"]], use_layer_norm=True, activation_fn=None),
+            concat_config=ConcatBlockConfig(activation_fn=torch.nn.ReLU),
+            conditionals_directory=str(tmpdir), conditionals=["assay", "dataset_id", "species"],
+            selection_order=["parallel"])
     vae = CLVAE(encoder_config=FCBlockConfig(layers=[d["H2"], d["Hv"]], use_batch_norm=True,
                                              activation_fn=torch.nn.ReLU, return_hidden=True),
                 decoder_config=FCBlockConfig(layers=[d["Z"], d["Hv"], d["H2"]], activation_fn=torch.nn.ReLU),
-                latent_dim=d["Z"], hidden_z=gc.with_adv)
+                latent_dim=d["Z"], hidden_z=gc.with_adv, **cond_kwargs)
     advs = []
     if gc.with_adv:
         Adversarial.labels.clear()

@@ -254,3 +254,47 @@ def test_bf16_step_matches_oracle_midsize(with_adv, tmp_path):
         model.load_state_dict({f"module.{k}": v for k, v in P.items()})
         for g in model.engine().groups.values():
             g.refresh_shadow()
+
+
+def test_conditional_layers_module_route_matches_reference(tmp_path):
+    """the topology of configs/model/human_only.yaml (parallel conditional layers on z, concat
+    layer, two GRL adversaries) is outside the fused engine; it trains through the module route (same
+    kernels under autograd, LayerNorm as a stock module).  Checked against the unmodified reference's
+    training_step / validation_step outputs (fp32 path)."""
+    import random
+    from mmvae_b200 import layers as L
+    from mmvae_b200.modules.base import KLAnnealingFn
+    L.set_precision("fp32")
+    try:
+        gc = GoldenCase("human_conditional")
+        assert gc.conditional
+        model = build_b200_model(gc, tmp_path, kl_fn=KLAnnealingFn(0.5))
+        model.load_state_dict({f"module.{k}": v for k, v in gc.state("init").items()}, strict=True)
+        model.cuda().train()
+        assert model.engine() is None and "conditional" in model._module_route_reason
+        for t in range(gc.n_steps):
+            s = gc.step(t)
+            L.inject_noise(s["eps"].cuda())
+            meta = pd.DataFrame({c: [f"{c}_{int(i)}" for i in s["labels"][c]] for c in CONDITIONS})
+            model.logged_metrics.clear()
+            random.seed(4242 + t)
+            model.training_step((csr_batch(s["crow"], s["col"], s["val"], gc.genes["human"]), meta, "human"), t)
+            got = {k: float(v) for k, v in model.logged_metrics.items()}
+            assert set(got) == set(s["logs"])
+            for k, v in s["logs"].items():
+                assert got[k] == pytest.approx(v, rel=5e-4, abs=1e-5), (t, k)
+        final = gc.state("final")
+        mine = {k[len("module."):]: v for k, v in model.state_dict().items()}
+        assert set(mine) == set(final)
+        for k, v in final.items():
+            a = mine[k].detach().cpu().numpy()
+            if k.endswith("num_batches_tracked"):
+                assert int(a) == int(v)
+            elif bias_feeds_batchnorm(k, final) or k.endswith("bn.running_mean"):
+                continue
+            elif ".conditions." in k and k.endswith(".lin.bias"):
+                continue   # bias feeding LayerNorm(no affine): shift-invariant, gradient is rounding noise too
+            else:
+                assert rel_l2(a, v.numpy()) < 2e-3, (k, rel_l2(a, v.numpy()))
+    finally:
+        L.set_precision("bf16")

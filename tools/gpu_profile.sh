@@ -3,7 +3,6 @@ mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -s 260 -c 130 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 5 --no-cpu-baseline > gpurun_out/ncu_bench1.log 2>&1
 ncu --set full --clock-control none --import-source on \
-    -k regex:"decoder_mse_fused_kernel|csr_linear_fwd_kernel|csr_linear_bwd_w_kernel|gemm_bf16_tc_kernel|clip_adam_kernel" \
-    -s 60 -c 14 -f -o gpurun_out/prof python bench.py --steps 2 --warmup 5 --no-cpu-baseline > gpurun_out/ncu_bench2.log 2>&1
-ls -la gpurun_out/
-tail -3 gpurun_out/ncu_bench1.log gpurun_out/ncu_bench2.log
+    -k regex:"decoder_mse_fused_kernel|spmm_tc_kernel|gemm_bf16_tc_kernel|clip_adam_kernel|csr_linear_fwd_kernel" \
+    -s 14 -c 7 -f -o gpurun_out/topk python tools/prof_kernels.py > gpurun_out/ncu_topk.log 2>&1
+tail -2 gpurun_out/ncu_topk.log

@@ -46,6 +46,15 @@ def raw(rep, dst, title):
             "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct"]
     idx = [hdr.index(w) for w in want if w in hdr]
     ki = hdr.index("Kernel Name")
+    import json
+    traffic = {}
+    ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    for r in data:
+        def mb(i):
+            v = float(r[i].replace(",", ""))
+            return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[units[i]]
+        traffic[r[ki].split("(")[0].replace("void ", "").replace("cmmvae::", "")] = mb(ir) + mb(iw)
+    json.dump(traffic, open(dst.replace(".md", "_dram_bytes.json"), "w"), indent=1)
     with open(dst, "w") as f:
         f.write(f"# {title}\n\n`ncu --set full --clock-control none --import-source on` (per launch; never a bench value)\n\n")
         f.write("| kernel | " + " | ".join(f"{hdr[i]} [{units[i]}]" for i in idx) + " |\n")
@@ -58,8 +67,7 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if os.path.exists(os.path.join(GP, "launches.csv")):
         launches(os.path.join(GP, "launches.csv"), os.path.join(OUT, f"{tag}_launch_list.md"))
-    for name, title in (("prof2.ncu-rep", "top tensor kernels at the bench shape (B=1024, G=60530, H=1024, 5%)"),
-                        ("prof.ncu-rep", "full captures inside a bench step")):
+    for name, title in (("topk.ncu-rep", "top kernels at the bench shape (B=1024, G=60530, H=1024, 5% nnz)"),):
         p = os.path.join(GP, name)
         if os.path.exists(p):
             raw(p, os.path.join(OUT, f"{tag}_ncu_{name.split('.')[0]}.md"), title)
