@@ -8,7 +8,7 @@
 //
 // Persistent kernel, one CTA per SM, 128 x 256 output tiles, static round-robin tile order with the
 // cell-block index fastest (so CTAs running concurrently share the same Wout tiles in L2).  576 threads:
-//   warp 16      TMA producer (4-stage ring of 128x64 h tiles + 256x64 Wout tiles, 128B swizzle)
+//   warp 16      TMA producer (3-stage ring of 128x64 h tiles + 256x64 Wout tiles, 128B swizzle)
 //   warp 17      tcgen05.mma issuer (highest warp id = issue priority); two 256-column TMEM accumulators
 //                ping-pong with the epilogue
 //   warps 0..15  epilogue, 16 warps so that draining a tile takes less time than computing the next one:
@@ -16,14 +16,16 @@
 //                the per-(cell, 64-gene window) pointer table (window-major, shared with the tensor-pipe
 //                SpMM; bit-exact with crow/col) and prefetched into registers while the MMA runs;
 //                accumulator sub-chunks go TMEM -> registers -> a per-thread shared-memory column where
-//                the sparse entries are patched in, then out as bf16 (32 contiguous bytes per store pair).
+//                the sparse entries are patched in, then as bf16 into a 128B-swizzled [128 x 64] output tile
+//                per window that one thread hands to a TMA bulk store (full-line writes, edges clipped by
+//                the tensor map) -- per-thread 32-byte global stores cost 0.05 ms of L1 wavefronts here.
 #include "tc.cuh"
 
 namespace cmmvae {
 
 using namespace tc;
 
-constexpr int DBM = 128, DBN = 256, DBK = 64, DSTAGES = 4;
+constexpr int DBM = 128, DBN = 256, DBK = 64, DSTAGES = 3;
 constexpr int kDecEpiWarps = 16;
 constexpr int kDecThreads = 64 + 32 * kDecEpiWarps;   // 576
 constexpr int DE = 8;   // CSR entries per (cell, window) prefetched into registers; the rest stream from global
@@ -32,8 +34,9 @@ struct DecSmem {
   static constexpr int kABytes = DBM * DBK * 2;           // 16 KB
   static constexpr int kBBytes = DBN * DBK * 2;           // 32 KB
   static constexpr int kStageBytes = kABytes + kBBytes;   // 48 KB
-  static constexpr int kStagingOff = DSTAGES * kStageBytes;                 // float [16][512]
-  static constexpr int kBarOff = kStagingOff + 16 * 32 * kDecEpiWarps * 4;  // + 32 KB
+  static constexpr int kOutOff = DSTAGES * kStageBytes;                     // 4 x [128 rows][128 B] bf16, SW128
+  static constexpr int kStagingOff = kOutOff + 4 * DBM * 128;               // float [8][512]
+  static constexpr int kBarOff = kStagingOff + 8 * 32 * kDecEpiWarps * 4;   // + 16 KB
   static constexpr int kTotal = kBarOff + 256;
 };
 
@@ -52,7 +55,7 @@ struct DecParams {
 
 __global__ void __launch_bounds__(kDecThreads, 1)
 decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW,
-                         const DecParams p) {
+                         const __grid_constant__ CUtensorMap tmD, const DecParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];   // 128B-swizzled tiles need 1024-byte alignment
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   float* staging = reinterpret_cast<float*>(smem + DecSmem::kStagingOff);
@@ -137,6 +140,8 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
     const int row = q * 32 + lane;           // TMEM lane == row inside the tile
     const int et = e * 32 + lane;            // 0..511
     float* st = staging + et;                // element j of this thread's column: st[j * 512]
+    uint8_t* out_tile = smem + DecSmem::kOutOff + w * (DBM * 128);   // this window's [128][64] bf16 tile
+    const int gt = (e & 3) * 32 + lane;      // 0..127 inside the window's 4-warp group
     constexpr int SS = 32 * kDecEpiWarps;
     double loss_acc = 0.0;
     // CSR entries of (this thread's cell, this thread's window) for a tile, fetched one tile ahead so the
@@ -178,39 +183,43 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
       const int g0 = n0 + w * 64;            // first gene of this thread's window
       fetch(t + gridDim.x, np0, ncnt, necol, neval);
 
+      // the window's output tile (shared by the 4 warps of this window) must have been read by the previous
+      // tile's TMA store before it is overwritten
+      if (gt == 0) tma_store_wait_read();
+      named_bar_sync(1 + w, 128);
       mbar_wait_relaxed(&tmem_full[acc], acc_phase);
       tc_fence_after();
       float part = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {          // four 16-column sub-chunks of the window
-        uint32_t r[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * DBN + w * 64 + c * 16), r);
-        const int gc = g0 + c * 16;
-        float bias[16];
-        if (gc + 16 <= p.G) {
+      for (int c = 0; c < 8; ++c) {          // eight 8-column sub-chunks of the window (one 16-byte bf16 chunk each)
+        uint32_t r[8];
+        tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * DBN + w * 64 + c * 8), r);
+        const int gc = g0 + c * 8;
+        float bias[8];
+        if (gc + 8 <= p.G) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {   // G is only guaranteed even-aligned here: 8-byte loads
+          for (int j = 0; j < 8; j += 2) {   // G is only guaranteed even-aligned here: 8-byte loads
             const float2 t2 = __ldg(reinterpret_cast<const float2*>(p.bout + gc + j));
             bias[j] = t2.x; bias[j + 1] = t2.y;
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) bias[j] = (gc + j < p.G) ? __ldg(p.bout + gc + j) : 0.f;
+          for (int j = 0; j < 8; ++j) bias[j] = (gc + j < p.G) ? __ldg(p.bout + gc + j) : 0.f;
         }
         tmem_ld_wait();
         // dense part: xhat = relu(acc + bias), staged in this thread's smem column (conflict free)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 8; ++j) {
           const float xh = fmaxf(__uint_as_float(r[j]) + bias[j], 0.f);
           part = fmaf(xh, xh, part);
           st[j * SS] = xh;
         }
-        // sparse part: patch the entries of this 16-gene sub-chunk
-        const int lo = c * 16;
+        // sparse part: patch the entries of this 8-gene sub-chunk
+        const int lo = c * 8;
 #pragma unroll
         for (int u = 0; u < DE; ++u) {
           const int j = ecol[u] - lo;
-          if (j >= 0 && j < 16) {
+          if (j >= 0 && j < 8) {
             const float x = eval[u];
             const float xh = st[j * SS];
             part += x * x - 2.f * x * xh;
@@ -219,28 +228,28 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
         }
         for (int k = DE; k < cnt; ++k) {     // windows with more than DE entries (dense batches)
           const int j = __ldg(p.col + p0 + k) - g0 - lo;
-          if (j >= 0 && j < 16) {
+          if (j >= 0 && j < 8) {
             const float x = __ldg(p.val + p0 + k);
             const float xh = st[j * SS];
             part += x * x - 2.f * x * xh;
             st[j * SS] = xh > 0.f ? xh - x : 0.f;
           }
         }
-        // out: dlogits = 2 * staged, bf16, 8 columns (16 bytes) per store
-        if (row_ok) {
-          __nv_bfloat16* drow = p.dl + (size_t)b * p.ldd + gc;
-#pragma unroll
-          for (int j = 0; j < 16; j += 8) {
-            if (gc + j + 8 <= p.ldd) {
-              uint4 o;
-              o.x = pack_bf16(2.f * st[(j + 0) * SS], 2.f * st[(j + 1) * SS]);
-              o.y = pack_bf16(2.f * st[(j + 2) * SS], 2.f * st[(j + 3) * SS]);
-              o.z = pack_bf16(2.f * st[(j + 4) * SS], 2.f * st[(j + 5) * SS]);
-              o.w = pack_bf16(2.f * st[(j + 6) * SS], 2.f * st[(j + 7) * SS]);
-              *reinterpret_cast<uint4*>(drow + j) = o;
-            }
-          }
-        }
+        // out: dlogits = 2 * staged as bf16 -> chunk c of this row in the 128B-swizzled output tile
+        uint4 o;
+        o.x = pack_bf16(2.f * st[0 * SS], 2.f * st[1 * SS]);
+        o.y = pack_bf16(2.f * st[2 * SS], 2.f * st[3 * SS]);
+        o.z = pack_bf16(2.f * st[4 * SS], 2.f * st[5 * SS]);
+        o.w = pack_bf16(2.f * st[6 * SS], 2.f * st[7 * SS]);
+        *reinterpret_cast<uint4*>(out_tile + row * 128 + ((c ^ (row & 7)) << 4)) = o;
+      }
+      // publish the window: generic-proxy writes -> async proxy, then one thread stores the 128 x 64 box
+      // (rows beyond B and columns beyond ldd are clipped by the tensor map)
+      fence_proxy_async();
+      named_bar_sync(1 + w, 128);
+      if (gt == 0) {
+        tma_store_2d(&tmD, out_tile, g0, m0);
+        tma_store_commit();
       }
       if (row_ok) loss_acc += (double)part;
       // accumulator drained: hand the TMEM buffer back to the MMA warp
@@ -251,6 +260,7 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
 #pragma unroll
       for (int u = 0; u < DE; ++u) { ecol[u] = necol[u]; eval[u] = neval[u]; }
     }
+    if (gt == 0) tma_store_wait_all();       // smem must outlive the last bulk store
     // one atomic per warp
     loss_acc = warp_sum(loss_acc);
     if (lane == 0 && loss_acc != 0.0) atomicAdd(p.loss_sum, loss_acc);
@@ -291,9 +301,10 @@ extern "C" int cmmvae_decoder_mse_fused(const void* h, int ldh, const void* Wout
   p.dl = (__nv_bfloat16*)dlogits_bf16; p.ldd = ldd; p.loss_sum = loss_sum;
   p.num_m = (B + DBM - 1) / DBM;
   p.num_n = (G + DBN - 1) / DBN;
-  CUtensorMap tmH, tmW;
+  CUtensorMap tmH, tmW, tmD;
   if (int rc = make_tmap_bf16(&tmH, h, (uint64_t)H, (uint64_t)B, (uint64_t)ldh, DBK, DBM)) return rc;
   if (int rc = make_tmap_bf16(&tmW, Wout, (uint64_t)H, (uint64_t)G, (uint64_t)ldw, DBK, DBN)) return rc;
+  if (int rc = make_tmap_bf16(&tmD, dlogits_bf16, (uint64_t)ldd, (uint64_t)B, (uint64_t)ldd, 64, DBM)) return rc;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(decoder_mse_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -306,7 +317,7 @@ extern "C" int cmmvae_decoder_mse_fused(const void* h, int ldh, const void* Wout
   }
   cudaMemsetAsync(loss_sum, 0, sizeof(double), st);
   if (!tile_ptr) {   // build the 64-gene-window pointer table (the tensor-pipe SpMM shares it when it ran)
-    int blocks = (B + 7) / 8 < 148 * 8 ? (B + 7) / 8 : 148 * 8;   // one warp per row
+    int blocks = B < 148 * 16 ? B : 148 * 16;   // one CTA per row
     tile_ptr64_kernel<<<blocks, 256, 0, st>>>(crow, col, B, p.ntp, (int32_t*)workspace);
     if (int rc = check_launch("tile_ptr64")) return rc;
     tile_ptr = (const int32_t*)workspace;
@@ -314,6 +325,6 @@ extern "C" int cmmvae_decoder_mse_fused(const void* h, int ldh, const void* Wout
   p.tp = tile_ptr;
   const int num_tiles = p.num_m * p.num_n;
   const int grid = num_tiles < sm_budget() ? num_tiles : sm_budget();
-  decoder_mse_fused_kernel<<<grid, kDecThreads, DecSmem::kTotal, st>>>(tmH, tmW, p);
+  decoder_mse_fused_kernel<<<grid, kDecThreads, DecSmem::kTotal, st>>>(tmH, tmW, tmD, p);
   return check_launch("decoder_mse_fused");
 }

@@ -48,17 +48,16 @@ struct SpParams {
 // One thread per non-zero: entry i of row b opens every window in (window(i-1), window(i)] (all windows up
 // to window(i) when it is the row's first entry); the row's last entry also closes the windows after it.
 // Every table cell is written exactly once; rows without entries are filled by tile_ptr64_empty_rows.
-__global__ void tile_ptr64_kernel(const int32_t* __restrict__ crow, const int32_t* __restrict__ col, int B, int ntp,
-                                  int32_t* __restrict__ tp) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int b = warp; b < B; b += nwarps) {
+__global__ void __launch_bounds__(256) tile_ptr64_kernel(const int32_t* __restrict__ crow,
+                                                         const int32_t* __restrict__ col, int B, int ntp,
+                                                         int32_t* __restrict__ tp) {
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {      // one CTA per row
     const int s = crow[b], e = crow[b + 1];
     if (s == e) {
-      for (int w = lane; w < ntp; w += 32) tp[(size_t)w * B + b] = s;
+      for (int w = threadIdx.x; w < ntp; w += blockDim.x) tp[(size_t)w * B + b] = s;
       continue;
     }
-    for (int i = s + lane; i < e; i += 32) {
+    for (int i = s + threadIdx.x; i < e; i += blockDim.x) {
       const int wi = __ldg(col + i) >> 6;
       const int wprev = (i == s) ? -1 : (__ldg(col + i - 1) >> 6);
       for (int w = wprev + 1; w <= wi; ++w) tp[(size_t)w * B + b] = i;
@@ -399,7 +398,7 @@ extern "C" int cmmvae_csr_tile_ptr(const int32_t* crow, const int32_t* col, cons
   CMMVAE_REQUIRE(((uintptr_t)packed & 15) == 0, "csr_tile_ptr: packed must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const int ntp = (G + 63) / 64 + 1;
-  int blocks = (B + 7) / 8 < 148 * 8 ? (B + 7) / 8 : 148 * 8;   // one warp per row
+  int blocks = B < 148 * 16 ? B : 148 * 16;   // one CTA per row
   tile_ptr64_kernel<<<blocks, 256, 0, st>>>(crow, col, B, ntp, tile_ptr);
   if (int rc = check_launch("csr_tile_ptr")) return rc;
   long long want;
