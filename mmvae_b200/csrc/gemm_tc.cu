@@ -27,8 +27,10 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN <= 128) ? 6 : 4;
-  static constexpr int kBarrierBytes = 1024;
-  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024 /*alignment slack*/;
+  static constexpr int kOutOff = kStages * kStageBytes;        // 2 x [128 rows][128 B] f32 chunks, SW128
+  static constexpr int kOutBytes = 2 * BM * 128;
+  static constexpr int kBarOff = kOutOff + kOutBytes;
+  static constexpr int kTotal = kBarOff + 256;
 };
 
 struct GemmParams {
@@ -41,16 +43,17 @@ struct GemmParams {
   int vec_ok;  // 16-byte aligned rows for both outputs
   int splits;  // split-K factor (gridDim.z); > 1: partial products are atomically added into a zeroed C32
   double* sumsq;  // optional: += sum of squares of the stored C (gradient-norm fused into the dW GEMM)
+  int tma_out;    // f32 output leaves through 128B-swizzled smem chunks + TMA bulk stores (full-line writes)
 };
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   using S = GemmSmem<BN>;
   extern __shared__ __align__(1024) uint8_t smem[];   // 128B-swizzled tiles need 1024-byte alignment
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
   uint64_t* empty_bar = full_bar + S::kStages;
   uint64_t* tmem_full = empty_bar + S::kStages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;           // [2]
@@ -165,6 +168,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int row = q * 32 + lane;
     float ssq = 0.f;
     int it = 0;
+    int chunk_no = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
       int m0, n0, z, kb0, num_kb;
       unit_coords(u, m0, n0, z, kb0, num_kb);
@@ -179,6 +183,42 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
         tmem_ld_wait();
         const int gn0 = n0 + c * 32;
+        if (p.tma_out) {
+          // f32 chunk [128 rows x 32 cols] -> 128B-swizzled smem (double buffered) -> TMA bulk store; rows and
+          // columns outside C are clipped by the tensor map
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (gn0 + j < p.N) v[j] += __ldg(p.bias + gn0 + j);
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (p.sumsq && gm < p.M) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (gn0 + j < p.N) ssq = fmaf(v[j], v[j], ssq);
+          }
+          uint8_t* obuf = smem + S::kOutOff + (chunk_no & 1) * (BM * 128);
+          if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          named_bar_sync(1, 128);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<float4*>(obuf + row * 128 + ((k ^ (row & 7)) << 4)) =
+                make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          fence_proxy_async();
+          named_bar_sync(1, 128);
+          if (threadIdx.x == 0) {
+            tma_store_2d(&tmC, obuf, gn0, m0);
+            tma_store_commit();
+          }
+          ++chunk_no;
+          continue;
+        }
         if (gm < p.M && gn0 < p.N) {
           float v[32];
 #pragma unroll
@@ -259,6 +299,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
+    if (p.tma_out && threadIdx.x == 0) tma_store_wait_all();   // smem must outlive the last bulk store
     if (p.sumsq) {
       const double tot = warp_sum((double)ssq);
       if (lane == 0 && tot != 0.0) atomicAdd(p.sumsq, tot);
@@ -288,19 +329,31 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+static int make_tmap(CUtensorMap* m, CUtensorMapDataType dt, int esize, const void* base, uint64_t inner,
+                    uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer);
+
 // 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of pitch `ld` elements
 int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
                    uint32_t box_outer) {
+  return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, inner, outer, ld, box_inner, box_outer);
+}
+int make_tmap_f32(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                  uint32_t box_outer) {
+  return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, inner, outer, ld, box_inner, box_outer);
+}
+
+static int make_tmap(CUtensorMap* m, CUtensorMapDataType dt, int esize, const void* base, uint64_t inner,
+                    uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     return -3;
   }
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {ld * 2};
+  cuuint64_t strides[1] = {ld * (uint64_t)esize};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -312,7 +365,8 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t ou
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
+                       cudaStream_t st) {
   using S = GemmSmem<BN>;
   auto kern = gemm_bf16_tc_kernel<BN, A_MN, B_MN>;
   static bool configured = false;
@@ -326,17 +380,17 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   const long long units = (long long)((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM) * p.splits;
   const int grid = (int)(units < sm_budget() ? units : sm_budget());
-  kern<<<grid, kGemmThreads, S::kTotal, st>>>(tmA, tmB, p);
+  kern<<<grid, kGemmThreads, S::kTotal, st>>>(tmA, tmB, tmC, p);
   return check_launch("gemm_bf16_tc");
 }
 
 template <int BN>
 static int dispatch_major(int transA, int transB, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                          const GemmParams& p, cudaStream_t st) {
-  if (!transA && !transB) return launch_gemm<BN, false, false>(tmA, tmB, p, st);
-  if (!transA && transB) return launch_gemm<BN, false, true>(tmA, tmB, p, st);
-  if (transA && !transB) return launch_gemm<BN, true, false>(tmA, tmB, p, st);
-  return launch_gemm<BN, true, true>(tmA, tmB, p, st);
+                          const CUtensorMap& tmC, const GemmParams& p, cudaStream_t st) {
+  if (!transA && !transB) return launch_gemm<BN, false, false>(tmA, tmB, tmC, p, st);
+  if (!transA && transB) return launch_gemm<BN, false, true>(tmA, tmB, tmC, p, st);
+  if (transA && !transB) return launch_gemm<BN, true, false>(tmA, tmB, tmC, p, st);
+  return launch_gemm<BN, true, true>(tmA, tmB, tmC, p, st);
 }
 
 }  // namespace cmmvae
@@ -386,6 +440,12 @@ extern "C" int cmmvae_gemm_bf16_tc(const void* A, int lda, int transA, const voi
       return -2;
     }
   }
-  if (BN == 256) return dispatch_major<256>(transA, transB, tmA, tmB, p, st);
-  return dispatch_major<128>(transA, transB, tmA, tmB, p, st);
+  // big f32-only outputs (weight gradients) leave through TMA bulk stores
+  CUtensorMap tmC = tmA;
+  p.tma_out = (C_f32 && !C_bf16 && !accumulate && splits == 1 && ldc % 4 == 0 && ((uintptr_t)C_f32 & 15) == 0 &&
+               (long long)M * N >= (1 << 20)) ? 1 : 0;
+  if (p.tma_out)
+    if (int rc2 = make_tmap_f32(&tmC, C_f32, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, BM)) return rc2;
+  if (BN == 256) return dispatch_major<256>(transA, transB, tmA, tmB, tmC, p, st);
+  return dispatch_major<128>(transA, transB, tmA, tmB, tmC, p, st);
 }

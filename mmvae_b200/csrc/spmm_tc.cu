@@ -30,7 +30,9 @@ constexpr int kSpThreads = 64 + 128 * SNG + 128;   // TMA + MMA + producer warps
 constexpr int kSpABytes = SBM * SBK * 2;   // 16 KB
 constexpr int kSpBBytes = SBN * SBK * 2;   // 32 KB
 constexpr int kSpStage = kSpABytes + kSpBBytes;
-constexpr int kSpSmem = SSTAGES * kSpStage + 1024 + 1024;
+constexpr int kSpOutOff = SSTAGES * kSpStage;              // 2 x [128 rows][128 B] f32 chunks, SW128 (backward)
+constexpr int kSpBarOff = kSpOutOff + 2 * SBM * 128;
+constexpr int kSpSmem = kSpBarOff + 256;
 
 struct SpParams {
   int B, G, H;
@@ -83,10 +85,10 @@ __global__ void csr_pack_kernel(const int32_t* __restrict__ col, const float* __
 
 template <bool BWD>
 __global__ void __launch_bounds__(kSpThreads, 1)
-spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const SpParams p) {
+spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const SpParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];   // 128B-swizzled tiles need 1024-byte alignment
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SSTAGES * kSpStage);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kSpBarOff);
   uint64_t* empty_bar = full_bar + SSTAGES;
   uint64_t* tmem_full = empty_bar + SSTAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
@@ -298,6 +300,8 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const SpParams p) {
     const int row = qd * 32 + lane;
     float ssq = 0.f;
     int it = 0;
+    int chunk_no = 0;
+    const int et = (warp - kEpiWarp0) * 32 + lane;   // 0..127 among the epilogue threads
     for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++it) {
       int m0, n0, z, kb0, num_kb;
       unit_coords(u, m0, n0, z, kb0, num_kb);
@@ -312,6 +316,30 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const SpParams p) {
         tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * SBN + c * 32), r);
         tmem_ld_wait();
         const int gn0 = n0 + c * 32;
+        if (BWD) {
+          // dWt chunk [128 genes x 32 cols] f32 -> 128B-swizzled smem (double buffered) -> TMA bulk store;
+          // gene rows beyond G / columns beyond H are clipped by the tensor map
+          if (p.sumsq && gm < Mdim) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (gn0 + j < p.H) ssq = fmaf(__uint_as_float(r[j]), __uint_as_float(r[j]), ssq);
+          }
+          uint8_t* obuf = smem + kSpOutOff + (chunk_no & 1) * (SBM * 128);
+          if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          named_bar_sync(15, 128);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<uint4*>(obuf + row * 128 + ((k ^ (row & 7)) << 4)) =
+                make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+          fence_proxy_async();
+          named_bar_sync(15, 128);
+          if (et == 0) {
+            tma_store_2d(&tmC, obuf, gn0, m0);
+            tma_store_commit();
+          }
+          ++chunk_no;
+          continue;
+        }
         if (gm < Mdim && gn0 < p.H) {
           float v[32];
 #pragma unroll
@@ -353,6 +381,7 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const SpParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
+    if (BWD && et == 0) tma_store_wait_all();   // smem must outlive the last bulk store
     if (BWD && p.sumsq) {
       const double tot = warp_sum((double)ssq);
       if (lane == 0 && tot != 0.0) atomicAdd(p.sumsq, tot);
@@ -365,9 +394,12 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const SpParams p) {
 
 int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
                    uint32_t box_outer);
+int make_tmap_f32(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                  uint32_t box_outer);
 
 template <bool BWD>
-static int launch_spmm_tc(const CUtensorMap& tm, const SpParams& p, dim3 grid, cudaStream_t st) {
+static int launch_spmm_tc(const CUtensorMap& tm, const CUtensorMap& tmC, const SpParams& p, dim3 grid,
+                          cudaStream_t st) {
   auto kern = spmm_tc_kernel<BWD>;
   static bool configured = false;
   if (!configured) {
@@ -378,7 +410,7 @@ static int launch_spmm_tc(const CUtensorMap& tm, const SpParams& p, dim3 grid, c
     }
     configured = true;
   }
-  kern<<<grid, kSpThreads, kSpSmem, st>>>(tm, p);
+  kern<<<grid, kSpThreads, kSpSmem, st>>>(tm, tmC, p);
   return check_launch(BWD ? "csr_linear_bwd_w_tc" : "csr_linear_fwd_tc");
 }
 
@@ -429,7 +461,7 @@ extern "C" int cmmvae_csr_linear_fwd_tc(const void* packed, const int32_t* tile_
   if (splits > 1) cudaMemsetAsync(Y, 0, sizeof(float) * (size_t)B * H, st);
   const int units = tiles * splits;
   dim3 grid(units < sms ? units : sms);
-  return launch_spmm_tc<false>(tm, p, grid, st);
+  return launch_spmm_tc<false>(tm, tm, p, grid, st);
 }
 
 extern "C" int cmmvae_csr_linear_bwd_w_tc(const void* packed, const int32_t* tile_ptr, int B, int G, int H,
@@ -443,5 +475,7 @@ extern "C" int cmmvae_csr_linear_bwd_w_tc(const void* packed, const int32_t* til
   if (int rc = make_tmap_bf16(&tm, dY_bf16, (uint64_t)H, (uint64_t)B, (uint64_t)H, 64, SBK)) return rc;
   const int units = ((H + SBN - 1) / SBN) * ((G + SBM - 1) / SBM);
   dim3 grid(units < sm_budget() ? units : sm_budget());
-  return launch_spmm_tc<true>(tm, p, grid, (cudaStream_t)stream);
+  CUtensorMap tmC;
+  if (int rc = make_tmap_f32(&tmC, dWt, (uint64_t)H, (uint64_t)G, (uint64_t)H, 32, SBM)) return rc;
+  return launch_spmm_tc<true>(tm, tmC, p, grid, (cudaStream_t)stream);
 }
