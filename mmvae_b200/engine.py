@@ -368,6 +368,10 @@ class StepEngine:
             ap.bh, ap.gbh = g.p[o:o + sumC], g.g[o:o + sumC]
             self.adv.append(ap)
         self._ws: Dict[tuple, torch.Tensor] = {}
+        # small weight-gradient GEMMs are off the critical path (only the optimizer needs them): they run on a
+        # side stream, concurrently with the dX chain of the main stream
+        self.side = torch.cuda.Stream(device=self.device)
+        self._side_used = False
         self.timers: Optional[Dict[str, list]] = None   # name -> [(start_event, end_event)] when profiling
         self._seed = 0x5EED
         self.nccl_sms = 24                  # SMs left to communication kernels when world > 1
@@ -401,6 +405,20 @@ class StepEngine:
         """mean duration (ms) of the events recorded under ``name`` (call after a synchronize)"""
         evs = (self.timers or {}).get(name, [])
         return sum(a.elapsed_time(b) for a, b in evs) / max(len(evs), 1)
+
+    def _on_side(self, fn):
+        """run ``fn`` (kernel launches reading tensors the main stream has produced so far) on the side stream"""
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ev)
+            fn()
+        self._side_used = True
+
+    def _join_side(self):
+        if self._side_used:
+            torch.cuda.current_stream().wait_stream(self.side)
+            self._side_used = False
 
     def _tc(self, *dims) -> bool:
         return self.precision == "bf16" and all(d % 8 == 0 for d in dims)
@@ -489,11 +507,13 @@ class StepEngine:
             return None
         dX = self.ws(tag + ".dX", (B, lp.K)) if need_dx else None
         if self._tc(lp.K, lp.N):
-            ops.gemm(dY16, 1, cache["x16"], 1, lp.N, lp.K, B, C32=lp.gW)
+            x16 = cache["x16"]
+            self._on_side(lambda: ops.gemm(dY16, 1, x16, 1, lp.N, lp.K, B, C32=lp.gW))
             if need_dx:
                 ops.gemm(dY16, 0, lp.W16, 1, B, lp.K, lp.N, C32=dX)
         else:
-            ops.gemm(dY, 1, cache["x32"], 1, lp.N, lp.K, B, C32=lp.gW, use_tc=False)
+            x32 = cache["x32"]
+            self._on_side(lambda: ops.gemm(dY, 1, x32, 1, lp.N, lp.K, B, C32=lp.gW, use_tc=False))
             if need_dx:
                 ops.gemm(dY, 0, lp.W32, 1, B, lp.K, lp.N, C32=dX, use_tc=False)
         return dX
@@ -533,6 +553,7 @@ class StepEngine:
                 d = self._layer_bwd(f"{tag}.e{j}", ap.enc[j], caches[j], d, B, need_dx=(need_dx or j > 0))
         finally:
             self.precision = saved_precision
+        self._join_side()
         return d
 
     # ----------------------------------------------------------------------------------------- step
@@ -683,12 +704,13 @@ class StepEngine:
         dML16 = self.ws("dML16", (B, 2 * Z), torch.bfloat16) if bf else None
         ops.reparam_kl_bwd(ML, eps, dz, Z, self.var_eps, float(kl_weight) / B, dML, dML16)
         dq = self.ws("dq", (B, self.Hv))
-        ops.colsum(dML, self.gbmv)
         if self._tc(self.Hv, 2 * Z):
-            ops.gemm(dML16, 1, q16, 1, 2 * Z, self.Hv, B, C32=self.gWmv)
+            self._on_side(lambda: (ops.colsum(dML, self.gbmv),
+                                   ops.gemm(dML16, 1, q16, 1, 2 * Z, self.Hv, B, C32=self.gWmv)))
             ops.gemm(dML16, 0, self.Wmv16, 1, B, self.Hv, 2 * Z, C32=dq)
         else:
-            ops.gemm(dML, 1, q32, 1, 2 * Z, self.Hv, B, C32=self.gWmv, use_tc=False)
+            self._on_side(lambda: (ops.colsum(dML, self.gbmv),
+                                   ops.gemm(dML, 1, q32, 1, 2 * Z, self.Hv, B, C32=self.gWmv, use_tc=False)))
             ops.gemm(dML, 0, self.Wmv32, 1, B, self.Hv, 2 * Z, C32=dq, use_tc=False)
         d = dq
         for j in reversed(range(len(self.vaeenc_plan))):
@@ -711,6 +733,7 @@ class StepEngine:
             self._t1(ev)
 
         # ---------------- grad norms, clip, Adam ----------------
+        self._join_side()
         pending.append(gexp.exchange_segment_async(0))
         pending.append(gexp.exchange_rest_async())
         pending.append(gvae.exchange_rest_async())
