@@ -231,6 +231,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        torch.set_num_threads(max(1, (os.cpu_count() or 8) // world))   # one launch thread per rank matters
         os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout clean: the only stdout line is the JSON result
         torch.distributed.init_process_group("nccl", device_id=dev)
     from mmvae_b200 import layers as L, ops
@@ -281,6 +282,7 @@ def main():
     t_dec, t_spmm = eng.timer_ms("decoder_mse_fused"), eng.timer_ms("csr_linear_fwd")
     t_dw, t_dh, t_adam = eng.timer_ms("dWout_gemm"), eng.timer_ms("dh_gemm"), eng.timer_ms("norm+clip_adam")
     t_spbw = eng.timer_ms("csr_linear_bwd_w+bn")
+    t_dp = {k: eng.timer_ms(k) for k in ("dp_wait_shadow_first", "dp_wait_shadow_rest", "dp_wait_grads")}
     eng.timers = None
     if world > 1:
         tt = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -363,7 +365,7 @@ def main():
                      "traffic": traffic, "peak_source": f"{pk_kind} bf16_tflops_sustained (kernel timed inside a step)",
                      "ms_per_launch": t_dec, "flops_per_launch": flops},
         "kernels_ms": {"decoder_mse_fused": t_dec, "dWout_gemm": t_dw, "dh_gemm": t_dh, "csr_linear_fwd": t_spmm,
-                       "csr_linear_bwd_w+bn_bwd": t_spbw, "norm+clip_adam": t_adam},
+                       "csr_linear_bwd_w+bn_bwd": t_spbw, "norm+clip_adam": t_adam, **t_dp},
         "spmm": {"algorithmic_bytes": spmm_bytes, "ms": t_spmm,
                  "achieved_gbs": spmm_bytes / (t_spmm * 1e-3) / 1e9 if t_spmm > 0 else 0.0,
                  "peak_gbs": pk["hbm_gbs"], "frac": (spmm_bytes / (t_spmm * 1e-3) / 1e9 / pk["hbm_gbs"]) if t_spmm > 0 else 0.0,

@@ -68,8 +68,11 @@ int cmmvae_csr_tile_ptr(const int32_t* crow, const int32_t* col, const float* va
                         int32_t* tile_ptr, void* packed, void* stream);
 int cmmvae_csr_linear_fwd_tc(const void* packed, const int32_t* tile_ptr, int B, int G, int H,
                              const void* Wt_bf16, const float* bias, float* Y, void* stream);
+/* [g_begin, g_end): gene rows of dWt computed by this launch (128-aligned; g_end <= 0 means G), so a caller
+ * can hand finished row ranges to a collective while the rest is still being computed */
 int cmmvae_csr_linear_bwd_w_tc(const void* packed, const int32_t* tile_ptr, int B, int G, int H,
-                               const void* dY_bf16, float* dWt, double* sumsq_out, void* stream);
+                               const void* dY_bf16, float* dWt, int g_begin, int g_end, double* sumsq_out,
+                               void* stream);
 
 /* ---- K2/K3: BatchNorm1d(momentum, eps) + ReLU + Dropout, components.py:279-288 ------------- */
 /* column statistics of Y[B,H]: mean[H], rstd[H] = 1/sqrt(biased var + eps); updates running

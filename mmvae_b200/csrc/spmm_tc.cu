@@ -43,6 +43,7 @@ struct SpParams {
   float* out;          // forward: Y[B,H]; backward: dWt[G,H]
   int splits;          // forward split-K over genes
   double* sumsq;       // backward only, optional: += sum of squares of dWt (fused gradient norm)
+  int m_begin, m_end;  // backward only: gene range [m_begin, m_end) computed by this launch (m_begin % 128 == 0)
 };
 
 // tp[w][b] = first position p in row b with col[p] >= 64*w, w = 0..NW (NW = ceil(G/64)); window-major so
@@ -97,14 +98,15 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // persistent: units (n tile fastest, then m tile, then K split) are dealt round-robin to the CTAs
   const int Kdim = BWD ? p.B : p.G;
-  const int Mdim = BWD ? p.G : p.B;
-  const int tiles_n = (p.H + SBN - 1) / SBN, tiles_m = (Mdim + SBM - 1) / SBM;
+  const int Mdim = BWD ? p.m_end : p.B;
+  const int m_base = BWD ? p.m_begin : 0;
+  const int tiles_n = (p.H + SBN - 1) / SBN, tiles_m = (Mdim - m_base + SBM - 1) / SBM;
   const int num_units = tiles_n * tiles_m * p.splits;
   const int total_kb = (Kdim + SBK - 1) / SBK;
   const int kb_per = (total_kb + p.splits - 1) / p.splits;
   auto unit_coords = [&](int u, int& m0, int& n0, int& z, int& kb0, int& num_kb) {
     n0 = (u % tiles_n) * SBN;
-    m0 = ((u / tiles_n) % tiles_m) * SBM;
+    m0 = m_base + ((u / tiles_n) % tiles_m) * SBM;
     z = u / (tiles_n * tiles_m);
     kb0 = z * kb_per;
     num_kb = max(0, min(total_kb, kb0 + kb_per) - kb0);
@@ -448,7 +450,7 @@ extern "C" int cmmvae_csr_linear_fwd_tc(const void* packed, const int32_t* tile_
   cudaStream_t st = (cudaStream_t)stream;
   SpParams p;
   p.B = B; p.G = G; p.H = H; p.packed = (const uint32_t*)packed; p.tp = tile_ptr; p.ntp = (G + 63) / 64 + 1;
-  p.bias = bias; p.out = Y; p.sumsq = nullptr;
+  p.bias = bias; p.out = Y; p.sumsq = nullptr; p.m_begin = 0; p.m_end = B;
   const int tiles = ((B + SBM - 1) / SBM) * ((H + SBN - 1) / SBN);
   const int total_kb = (G + SBK - 1) / SBK;
   const int sms = sm_budget();
@@ -465,15 +467,19 @@ extern "C" int cmmvae_csr_linear_fwd_tc(const void* packed, const int32_t* tile_
 }
 
 extern "C" int cmmvae_csr_linear_bwd_w_tc(const void* packed, const int32_t* tile_ptr, int B, int G, int H,
-                                          const void* dY_bf16, float* dWt, double* sumsq_out, void* stream) {
+                                          const void* dY_bf16, float* dWt, int g_begin, int g_end,
+                                          double* sumsq_out, void* stream) {
   CMMVAE_REQUIRE(B > 0 && G > 0 && H > 0 && H % 8 == 0, "csr_linear_bwd_w_tc: bad shape (H must be a multiple of 8)");
   CMMVAE_REQUIRE(((uintptr_t)dY_bf16 & 15) == 0 && ((uintptr_t)dWt & 15) == 0, "csr_linear_bwd_w_tc: alignment");
   SpParams p;
   p.B = B; p.G = G; p.H = H; p.packed = (const uint32_t*)packed; p.tp = tile_ptr; p.ntp = (G + 63) / 64 + 1;
-  p.bias = nullptr; p.out = dWt; p.splits = 1; p.sumsq = sumsq_out;
+  if (g_end <= 0 || g_end > G) g_end = G;
+  CMMVAE_REQUIRE(g_begin >= 0 && g_begin < g_end && g_begin % SBM == 0 && (g_end == G || g_end % SBM == 0),
+                 "csr_linear_bwd_w_tc: gene range [%d,%d) must be 128-aligned", g_begin, g_end);
+  p.bias = nullptr; p.out = dWt; p.splits = 1; p.sumsq = sumsq_out; p.m_begin = g_begin; p.m_end = g_end;
   CUtensorMap tm;
   if (int rc = make_tmap_bf16(&tm, dY_bf16, (uint64_t)H, (uint64_t)B, (uint64_t)H, 64, SBK)) return rc;
-  const int units = ((H + SBN - 1) / SBN) * ((G + SBM - 1) / SBM);
+  const int units = ((H + SBN - 1) / SBN) * ((g_end - g_begin + SBM - 1) / SBM);
   dim3 grid(units < sm_budget() ? units : sm_budget());
   CUtensorMap tmC;
   if (int rc = make_tmap_f32(&tmC, dWt, (uint64_t)H, (uint64_t)G, (uint64_t)H, 32, SBM)) return rc;

@@ -20,6 +20,7 @@ and exposed as a ``[hidden, genes]`` view.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
@@ -48,7 +49,8 @@ class FlatGroup:
     ALIGN = 64
 
     def __init__(self, name: str, chains: List[List[tuple]], device, lr=5e-3, weight_decay=1e-6,
-                 betas=(0.9, 0.999), eps=1e-8, segments: Optional[List[List[List[tuple]]]] = None):
+                 betas=(0.9, 0.999), eps=1e-8, segments: Optional[List[List[List[tuple]]]] = None,
+                 split_first: int = 1):
         """``chains`` (tail) / ``segments[i]`` (sharded when world > 1): lists of chains; a chain is a list
         of ``(param, transposed)`` stored back to back (e.g. mean/var head weights = one matrix)."""
         self.name, self.lr, self.wd, self.betas, self.eps = name, lr, weight_decay, betas, eps
@@ -71,12 +73,30 @@ class FlatGroup:
                     self.transposed[id(p)] = tr
                     total += p.numel()
 
-        for seg in segments:
+        self.first_rows: List[tuple] = []      # row ranges of the first parameter covered by segments 0..k-1
+        for si, seg in enumerate(segments):
             total = _ceil(total, seg_align)
             lo = total
             place(seg)
             total = _ceil(total, seg_align)
+            if si == 0 and split_first > 1 and self.world > 1:
+                # cut segment 0 inside its first (big, row-major) parameter at 128-row boundaries so that
+                # finished row ranges of its gradient can be exchanged while the rest is still computed
+                p0, tr0 = seg[0][0]
+                rows, width = (p0.shape[1], p0.shape[0]) if tr0 else (p0.shape[0], p0.shape[1])
+                per = _ceil((rows + split_first - 1) // split_first, 128)
+                cuts = [r for r in range(per, rows, per)]
+                if all((r * width) % seg_align == 0 for r in cuts) and self.offset[id(p0)] == lo:
+                    edges = [0] + cuts + [rows]
+                    starts = [lo + r * width for r in edges[:-1]]
+                    ends = starts[1:] + [total]
+                    self.seg_bounds += list(zip(starts, ends))
+                    self.first_rows = list(zip(edges[:-1], edges[1:]))
+                    continue
             self.seg_bounds.append((lo, total))
+            if si == 0:
+                self.first_rows = [(0, 0)]
+        self.n_first = max(len(self.first_rows), 1)   # segments 0..n_first-1 = pieces of the original segment 0
         self.tail_lo = total
         place(chains)
         self.n = _ceil(max(total, 4), 4)
@@ -177,10 +197,12 @@ class FlatGroup:
                 self._ag_pending.append(torch.distributed.all_gather_into_tensor(
                     self.p16[slo:shi], self.p16[lo:hi], async_op=True))
 
-    def wait_shadow(self, i: Optional[int] = None):
-        """make the current stream wait for the all-gather of segment i's bf16 shadow (all if None)"""
+    def wait_shadow(self, which: Optional[str] = None):
+        """make the current stream wait for the all-gather of bf16 shadows: "first" = the pieces of the original
+        segment 0 (first-layer weight), "rest" = the other segments, None = all"""
         for j, w in enumerate(self._ag_pending):
-            if w is not None and (i is None or i == j):
+            hit = which is None or (which == "first") == (j < self.n_first)
+            if w is not None and hit:
                 w.wait()
                 self._ag_pending[j] = None
 
@@ -285,6 +307,7 @@ class AdvPlan:
     conditions: List[str]
     classes: List[int]
     Wh32: torch.Tensor = None   # [sumC, K]
+    Wh16: torch.Tensor = None
     bh: torch.Tensor = None
     gWh: torch.Tensor = None
     gbh: torch.Tensor = None
@@ -299,6 +322,7 @@ class StepEngine:
         if self.device.type != "cuda":
             raise RuntimeError("StepEngine needs a CUDA device (no CPU fallback)")
         self.precision = precision or L.get_precision()
+        self.dp_chunks = 2     # world > 1: pieces the first-layer weight gradient is exchanged in (overlap)
         self.adv_weight = adv_weight
         self.clip = clip or {"vae": 10.0, "expert": 10.0, "adversarial": 10.0}
         vae = module.vae
@@ -319,7 +343,8 @@ class StepEngine:
             mats = _block_chains(expert.encoder, sparse_first=True, kind="matrix") + \
                 _block_chains(expert.decoder, kind="matrix")
             vecs = _block_chains(expert.encoder, kind="vector") + _block_chains(expert.decoder, kind="vector")
-            g = self.groups[f"experts/{eid}"] = FlatGroup(f"experts/{eid}", vecs, dev, segments=[mats[:-1], mats[-1:]])
+            g = self.groups[f"experts/{eid}"] = FlatGroup(f"experts/{eid}", vecs, dev, segments=[mats[:-1], mats[-1:]],
+                                                          split_first=self.dp_chunks)
             self.enc_plan[eid] = _plan_block(expert.encoder, g, sparse_first=True)
             self.dec_plan[eid] = _plan_block(expert.decoder, g)
             last = self.dec_plan[eid][-1]
@@ -364,6 +389,7 @@ class StepEngine:
             sumC = sum(ap.classes)
             o = g.offset[id(heads[0].fc_layers[0].lin.weight)]
             ap.Wh32, ap.gWh = g.p[o:o + sumC * K].view(sumC, K), g.g[o:o + sumC * K].view(sumC, K)
+            ap.Wh16 = g.p16[o:o + sumC * K].view(sumC, K)
             o = g.offset[id(heads[0].fc_layers[0].lin.bias)]
             ap.bh, ap.gbh = g.p[o:o + sumC], g.g[o:o + sumC]
             self.adv.append(ap)
@@ -374,7 +400,7 @@ class StepEngine:
         self._side_used = False
         self.timers: Optional[Dict[str, list]] = None   # name -> [(start_event, end_event)] when profiling
         self._seed = 0x5EED
-        self.nccl_sms = 24                  # SMs left to communication kernels when world > 1
+        self.nccl_sms = int(os.environ.get("CMMVAE_NCCL_SMS", "32"))                  # SMs left to communication kernels when world > 1
         self.spmm_tc = True                 # bf16 policy: expert-encoder SpMM on the tensor pipe ...
         self.spmm_tc_min_density = 0.015    # ... when the batch is at least this dense (else gather kernel)
         self.world = 1
@@ -410,7 +436,7 @@ class StepEngine:
         """run ``fn`` (kernel launches reading tensors the main stream has produced so far) on the side stream"""
         ev = torch.cuda.Event()
         ev.record()
-        with torch.cuda.stream(self.side):
+        with torch.cuda.stream(self.side), ops.stream_scope(self.side):
             self.side.wait_event(ev)
             fn()
         self._side_used = True
@@ -499,8 +525,12 @@ class StepEngine:
             ops.colsum(dY, lp.gb)
         if lp.sparse:
             if csc[0] == "tc":
-                _, tp, G, ssq = csc
-                ops.csr_linear_bwd_w_tc(tp[1], tp[0], B, G, dY16, lp.gW, sumsq_out=ssq)
+                _, tp, G, ssq, pending = csc
+                pieces = lp.group.first_rows if (lp.group.sharded and lp.group.n_first > 1) else [(0, G)]
+                for i, (g0, g1) in enumerate(pieces):
+                    ops.csr_linear_bwd_w_tc(tp[1], tp[0], B, G, dY16, lp.gW, sumsq_out=ssq, g_begin=g0, g_end=g1)
+                    if i + 1 < len(pieces):   # this row range is final: exchange it while the next one is computed
+                        pending.append(lp.group.exchange_segment_async(i))
             else:
                 _, cptr, ridx, cval, G = csc
                 ops.csr_linear_bwd_w(cptr, ridx, cval, B, G, dY, lp.gW)
@@ -519,19 +549,30 @@ class StepEngine:
         return dX
 
     # ------------------------------------------------------------------------------------ adversary
-    def _adv_fwd(self, tag, ap: AdvPlan, hid32, B):
-        x, caches = hid32, []
-        saved_precision, self.precision = self.precision, "fp32"   # tiny GEMMs: exact CUDA-core path
+    def _adv_tc(self, ap: AdvPlan) -> bool:
+        """adversary GEMMs go to the tensor pipe when every dimension is TMA-addressable (else CUDA-core fp32)"""
+        dims = [d for lp in ap.enc for d in (lp.K, lp.N)] + [sum(ap.classes), ap.Wh32.shape[1]]
+        return self.precision == "bf16" and all(d % 8 == 0 for d in dims)
+
+    def _adv_fwd(self, tag, ap: AdvPlan, hid32, hid16, B):
+        x, x16, caches = hid32, hid16, []
+        tc = self._adv_tc(ap)
+        saved_precision, self.precision = self.precision, ("bf16" if tc else "fp32")
         try:
+            if tc and x16 is None:
+                x16 = ops.cast_bf16(x, self.ws(tag + ".in16", tuple(x.shape), torch.bfloat16))
             for j, lp in enumerate(ap.enc):
-                x, _, c = self._layer_fwd(f"{tag}.e{j}", lp, x, None, B)
+                x, x16, c = self._layer_fwd(f"{tag}.e{j}", lp, x, x16, B)
                 caches.append(c)
-            sumC = sum(ap.classes)
+            sumC, K = ap.Wh32.shape
             logits = self.ws(tag + ".logits", (B, sumC))
-            ops.gemm(x, 0, ap.Wh32, 0, B, sumC, ap.Wh32.shape[1], bias=ap.bh, C32=logits, use_tc=False)
+            if tc:
+                ops.gemm(x16, 0, ap.Wh16, 0, B, sumC, K, bias=ap.bh, C32=logits)
+            else:
+                ops.gemm(x, 0, ap.Wh32, 0, B, sumC, K, bias=ap.bh, C32=logits, use_tc=False)
         finally:
             self.precision = saved_precision
-        return x, caches, logits
+        return (x, x16), caches, logits
 
     def _adv_loss(self, tag, ap: AdvPlan, logits, labels, scale, B, ce_slots):
         dl = self.ws(tag + ".dlogits", logits.shape)
@@ -542,13 +583,20 @@ class StepEngine:
         return dl
 
     def _adv_bwd(self, tag, ap: AdvPlan, code, caches, dl, B, need_dx):
-        saved_precision, self.precision = self.precision, "fp32"
+        code32, code16 = code
+        tc = self._adv_tc(ap)
+        saved_precision, self.precision = self.precision, ("bf16" if tc else "fp32")
         try:
             sumC, K = ap.Wh32.shape
-            ops.gemm(dl, 1, code, 1, sumC, K, B, C32=ap.gWh, use_tc=False)
             ops.colsum(dl, ap.gbh)
             d = self.ws(tag + ".dcode", (B, K))
-            ops.gemm(dl, 0, ap.Wh32, 1, B, K, sumC, C32=d, use_tc=False)
+            if tc:
+                dl16 = ops.cast_bf16(dl, self.ws(tag + ".dl16", tuple(dl.shape), torch.bfloat16))
+                self._on_side(lambda: ops.gemm(dl16, 1, code16, 1, sumC, K, B, C32=ap.gWh))
+                ops.gemm(dl16, 0, ap.Wh16, 1, B, K, sumC, C32=d)
+            else:
+                ops.gemm(dl, 1, code32, 1, sumC, K, B, C32=ap.gWh, use_tc=False)
+                ops.gemm(dl, 0, ap.Wh32, 1, B, K, sumC, C32=d, use_tc=False)
             for j in reversed(range(len(ap.enc))):
                 d = self._layer_bwd(f"{tag}.e{j}", ap.enc[j], caches[j], d, B, need_dx=(need_dx or j > 0))
         finally:
@@ -559,8 +607,12 @@ class StepEngine:
     # ----------------------------------------------------------------------------------------- step
     def train_step(self, expert_id: str, crow, col, val, nnz: int, kl_weight: float, eps=None,
                    labels: Optional[Dict[str, torch.Tensor]] = None, masks=None):
-        """One optimisation step on a CSR batch already resident on the device.
-        Returns a dict of 0-dim device tensors (no host sync)."""
+        """One optimisation step on a CSR batch already resident on the device (no host sync).
+        Returns the step record (device scalar block etc.) for ``scalars()``."""
+        with ops.stream_scope(torch.cuda.current_stream()):
+            return self._train_step(expert_id, crow, col, val, nnz, kl_weight, eps, labels, masks)
+
+    def _train_step(self, expert_id, crow, col, val, nnz, kl_weight, eps, labels, masks):
         dev = self.device
         enc, dec = self.enc_plan[expert_id], self.dec_plan[expert_id]
         B = crow.numel() - 1
@@ -584,7 +636,9 @@ class StepEngine:
 
         # ---------------- forward ----------------
         gexp, gvae = self.groups[f"experts/{expert_id}"], self.groups["vae"]
-        gexp.wait_shadow(0)     # bf16 shards published by the previous step's optimizer (world > 1)
+        ev = self._t0("dp_wait_shadow_first")
+        gexp.wait_shadow("first")   # bf16 shards published by the previous step's optimizer (world > 1)
+        self._t1(ev)
         caches = {}
         x32 = x16 = None
         # tensor-pipe SpMM (tile densified in smem) above the density where it beats the gather kernel
@@ -602,7 +656,7 @@ class StepEngine:
         for j, lp in enumerate(self.vaeenc_plan):
             x32, x16, caches[("venc", j)] = self._layer_fwd(f"venc{j}", lp, x32, x16, B, masks=masks)
             if lp.return_hidden and lp.relu:
-                hidden.append(("venc", j, x32))
+                hidden.append(("venc", j, x32, x16))
         q32, q16 = x32, x16
         ML = self.ws("ML", (B, 2 * Z))
         if self._tc(self.Hv, 2 * Z):
@@ -615,7 +669,7 @@ class StepEngine:
         z16 = self.ws("z16", (B, Z), torch.bfloat16) if bf else None
         ops.reparam_kl_fwd(ML, eps, Z, self.var_eps, z32, z16, sc[1:4])
         if self.hidden_z:
-            hidden.append(("z", 0, z32))
+            hidden.append(("z", 0, z32, z16))
         x32, x16 = z32, z16
         for j, lp in enumerate(self.vaedec_plan):
             x32, x16, caches[("vdec", j)] = self._layer_fwd(f"vdec{j}", lp, x32, x16, B, masks=masks)
@@ -623,7 +677,9 @@ class StepEngine:
             x32, x16, caches[("dec", j)] = self._layer_fwd(f"dec{j}", lp, x32, x16, B, masks=masks)
         h32, h16 = x32, x16
         out = dec[-1]
-        gexp.wait_shadow(1)
+        ev = self._t0("dp_wait_shadow_rest")
+        gexp.wait_shadow("rest")
+        self._t1(ev)
         comm_budget(False)      # all-gathers are done: decoder + dWout run on every SM
         fused = self._tc(out.K) and bf
         if fused:
@@ -647,8 +703,8 @@ class StepEngine:
             assert labels is not None, "adversaries need labels"
             for i in range(n_adv):
                 ap = self.adv[i]
-                hid = hidden[i][2]
-                code, ac, logits_a = self._adv_fwd(f"adv{i}", ap, hid, B)
+                hid, hid16 = hidden[i][2], hidden[i][3]
+                code, ac, logits_a = self._adv_fwd(f"adv{i}", ap, hid, hid16, B)
                 slots = [sc[slot + k:slot + k + 1] for k in range(len(ap.conditions))]
                 slot += len(ap.conditions)
                 dla = self._adv_loss(f"adv{i}", ap, logits_a, labels, 1.0, B, slots)
@@ -660,8 +716,8 @@ class StepEngine:
                 ap.group.clip_adam(s_norm(2 + i), self.clip.get("adversarial"), gscale)
             for i in range(n_adv):
                 ap = self.adv[i]
-                hid = hidden[i][2]
-                code, ac, logits_a = self._adv_fwd(f"adv{i}", ap, hid, B)
+                hid, hid16 = hidden[i][2], hidden[i][3]
+                code, ac, logits_a = self._adv_fwd(f"adv{i}", ap, hid, hid16, B)
                 slots = [sc[slot + k:slot + k + 1] for k in range(len(ap.conditions))]
                 slot += len(ap.conditions)
                 dla = self._adv_loss(f"adv{i}", ap, logits_a, labels, float(self.adv_weight), B, slots)
@@ -681,7 +737,7 @@ class StepEngine:
             ops.colsum(dl, out.gb, M=B, N=G)
             # the output layer's gradient (half of the expert group) is final: start exchanging it now so
             # the transfer overlaps the rest of the backward pass
-            pending = [gexp.exchange_segment_async(1)]
+            pending = [gexp.exchange_segment_async(gexp.n_first)]
             comm_budget(True)
             ev = self._t0("dh_gemm")
             ops.gemm(dl, 0, out.W16, 1, B, H1, G, C32=dh)                 # dh = dlogits Wout
@@ -689,7 +745,7 @@ class StepEngine:
         else:
             ops.gemm(dl, 1, h32, 1, G, H1, B, C32=out.gW, use_tc=False)
             ops.colsum(dl, out.gb)
-            pending = [gexp.exchange_segment_async(1)]
+            pending = [gexp.exchange_segment_async(gexp.n_first)]
             ops.gemm(dl, 0, out.W32, 1, B, H1, G, C32=dh, use_tc=False)
         d = dh
         for j in reversed(range(len(dec) - 1)):
@@ -719,7 +775,7 @@ class StepEngine:
                     ops.axpy(d, d_hidden[i], -1.0)
             d = self._layer_bwd(f"venc{j}", self.vaeenc_plan[j], caches[("venc", j)], d, B)
         if use_tc_spmm:
-            csc = ("tc", tp, G, s_norm(1) if fuse_norm else None)
+            csc = ("tc", tp, G, s_norm(1) if fuse_norm else None, pending)
         else:
             cptr, ridx, cval = ops.csr_transpose(crow, col, val, G, nnz, self.ws("cptr", (G + 1,), torch.int32),
                                                  self.ws("ridx", (max(nnz, 1),), torch.int32),
@@ -734,12 +790,17 @@ class StepEngine:
 
         # ---------------- grad norms, clip, Adam ----------------
         self._join_side()
-        pending.append(gexp.exchange_segment_async(0))
+        pending.append(gexp.exchange_segment_async(gexp.n_first - 1))   # last piece of W1 + the small matrices
+        if not (use_tc_spmm and gexp.n_first > 1):
+            for i in range(gexp.n_first - 1):
+                pending.append(gexp.exchange_segment_async(i))
         pending.append(gexp.exchange_rest_async())
         pending.append(gvae.exchange_rest_async())
+        ev = self._t0("dp_wait_grads")
         for w in pending:
             if w is not None:
                 w.wait()
+        self._t1(ev)
         comm_budget(False)
         ev = self._t0("norm+clip_adam")
         gvae.grad_norm_sq(s_norm(0))
@@ -803,7 +864,7 @@ class StepEngine:
         B, G, Z = crow.numel() - 1, enc[0].K, self.Z
         bf = self.precision == "bf16"
         if bf:
-            self.groups[f"experts/{expert_id}"].wait_shadow()
+            self.groups[f"experts/{expert_id}"].wait_shadow(None)
         else:
             self.groups[f"experts/{expert_id}"].sync_master()
         sc = torch.zeros(4, dtype=torch.float64, device=self.device)

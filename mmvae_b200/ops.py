@@ -34,8 +34,31 @@ def _ptr(t: Optional[torch.Tensor]):
     return _c.c_void_p(t.data_ptr())
 
 
+_stream_override = None   # set by the step engine for the duration of a step (avoids ~1 us per launch)
+
+
 def _stream():
+    if _stream_override is not None:
+        return _stream_override
     return _c.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class stream_scope:
+    """``with ops.stream_scope(torch_stream):`` every op launches on that stream without asking torch for the
+    current stream on each call.  The caller guarantees it IS torch's current stream inside the scope."""
+
+    def __init__(self, stream):
+        self.handle = _c.c_void_p(stream.cuda_stream)
+
+    def __enter__(self):
+        global _stream_override
+        self.prev, _stream_override = _stream_override, self.handle
+        return self
+
+    def __exit__(self, *exc):
+        global _stream_override
+        _stream_override = self.prev
+        return False
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -121,11 +144,12 @@ def csr_linear_fwd_tc(packed, tile_ptr, B: int, G: int, Wt16, bias, out=None):
     return out
 
 
-def csr_linear_bwd_w_tc(packed, tile_ptr, B: int, G: int, dY16, out, sumsq_out=None):
+def csr_linear_bwd_w_tc(packed, tile_ptr, B: int, G: int, dY16, out, sumsq_out=None, g_begin=0, g_end=0):
     H = dY16.shape[1]
     assert dY16.dtype == torch.bfloat16 and dY16.is_contiguous() and out.is_contiguous() and out.shape == (G, H)
     _check(lib().cmmvae_csr_linear_bwd_w_tc(_ptr(packed), _ptr(tile_ptr), B, G, H, _ptr(dY16), _ptr(out),
-                                            _ptr(sumsq_out), _stream()), "csr_linear_bwd_w_tc")
+                                            int(g_begin), int(g_end), _ptr(sumsq_out), _stream()),
+           "csr_linear_bwd_w_tc")
     return out
 
 

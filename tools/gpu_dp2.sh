@@ -1,6 +1,10 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --timeout 400 2>&1 | grep -E "^E   |passed|failed|skipped" | cut -c1-250 | head
-for n in 1 2; do
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29711 bench.py --gpus $n --steps 50 --warmup 5 --no-cpu-baseline 2>gpurun_out/dp_err_$n.log | tee gpurun_out/scale_$n.json | python -c "
-import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['n_gpus'], {k:d[k] for k in ('value','ms_per_step')}, d['e2e']['value'], d['kernels_ms'])"
-done
+run() {
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29711 bench.py --gpus 2 --steps 50 --warmup 5 --no-cpu-baseline 2>gpurun_out/dp_err_2.log | python -c "
+import json,sys,os; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); k=d['kernels_ms']; print(os.environ.get('TAG'), round(d['ms_per_step'],3), {x: round(k[x],3) for x in ('dh_gemm','csr_linear_fwd','norm+clip_adam','dp_wait_shadow_first','dp_wait_grads')})"
+}
+TAG=default run
+TAG=min32 NCCL_MIN_NCHANNELS=32 run
+TAG=min32_sms40 NCCL_MIN_NCHANNELS=32 CMMVAE_NCCL_SMS=40 run
+TAG=sms8 CMMVAE_NCCL_SMS=8 run
+TAG=max8_sms8 NCCL_MAX_NCHANNELS=8 CMMVAE_NCCL_SMS=8 run

@@ -1,0 +1,5 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_step_gpu.py -q --timeout 300 2>&1 | grep -E "^E   |passed|failed" | cut -c1-250 | head
+timeout 900 python bench.py --config 3 --steps 20 --warmup 4 --no-cpu-baseline 2>gpurun_out/c3_err.log | tee gpurun_out/bench_config3.json | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['config']['workload']); print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}); print(d['e2e']); print(d['kernels_ms']); print(d['roofline']['frac'])"
+tail -3 gpurun_out/c3_err.log | cut -c1-300
