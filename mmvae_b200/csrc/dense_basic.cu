@@ -433,20 +433,29 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, c
   const float4* g4 = reinterpret_cast<const float4*>(g);
   float4* m4 = reinterpret_cast<float4*>(m);
   float4* v4 = reinterpret_cast<float4*>(v);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
-       i += (long long)gridDim.x * blockDim.x) {
-    float4 pp = p4[i], mm = m4[i], vv = v4[i];
-    const float4 gg = g4[i];
-    adam_one(pp.x, gg.x, mm.x, vv.x, gs, lr, b1, b2, eps, wd, bc1, isb2);
-    adam_one(pp.y, gg.y, mm.y, vv.y, gs, lr, b1, b2, eps, wd, bc1, isb2);
-    adam_one(pp.z, gg.z, mm.z, vv.z, gs, lr, b1, b2, eps, wd, bc1, isb2);
-    adam_one(pp.w, gg.w, mm.w, vv.w, gs, lr, b1, b2, eps, wd, bc1, isb2);
-    p4[i] = pp; m4[i] = mm; v4[i] = vv;
-    if (p16) {
-      uint2 o;
-      o.x = pack_bf16(pp.x, pp.y);
-      o.y = pack_bf16(pp.z, pp.w);
-      *reinterpret_cast<uint2*>(p16 + i * 4) = o;
+  // two independent float4 quads per trip: all eight loads are issued before the first use, so one resident
+  // wave of CTAs (grid = occupancy x SMs, see cmmvae_clip_adam) keeps enough bytes in flight to fill HBM
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += 2 * stride) {
+    const long long j = i + stride;
+    const bool two = j < n4;
+    float4 pa = p4[i], ma = m4[i], va = v4[i];
+    const float4 ga = __ldcs(g4 + i);
+    float4 pb = pa, mb = ma, vb = va, gb = ga;
+    if (two) { pb = p4[j]; mb = m4[j]; vb = v4[j]; gb = __ldcs(g4 + j); }
+    adam_one(pa.x, ga.x, ma.x, va.x, gs, lr, b1, b2, eps, wd, bc1, isb2);
+    adam_one(pa.y, ga.y, ma.y, va.y, gs, lr, b1, b2, eps, wd, bc1, isb2);
+    adam_one(pa.z, ga.z, ma.z, va.z, gs, lr, b1, b2, eps, wd, bc1, isb2);
+    adam_one(pa.w, ga.w, ma.w, va.w, gs, lr, b1, b2, eps, wd, bc1, isb2);
+    p4[i] = pa; m4[i] = ma; v4[i] = va;
+    if (p16) *reinterpret_cast<uint2*>(p16 + i * 4) = make_uint2(pack_bf16(pa.x, pa.y), pack_bf16(pa.z, pa.w));
+    if (two) {
+      adam_one(pb.x, gb.x, mb.x, vb.x, gs, lr, b1, b2, eps, wd, bc1, isb2);
+      adam_one(pb.y, gb.y, mb.y, vb.y, gs, lr, b1, b2, eps, wd, bc1, isb2);
+      adam_one(pb.z, gb.z, mb.z, vb.z, gs, lr, b1, b2, eps, wd, bc1, isb2);
+      adam_one(pb.w, gb.w, mb.w, vb.w, gs, lr, b1, b2, eps, wd, bc1, isb2);
+      p4[j] = pb; m4[j] = mb; v4[j] = vb;
+      if (p16) *reinterpret_cast<uint2*>(p16 + j * 4) = make_uint2(pack_bf16(pb.x, pb.y), pack_bf16(pb.z, pb.w));
     }
   }
   for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
@@ -626,7 +635,17 @@ extern "C" int cmmvae_clip_adam(float* p, const float* g, float* m, float* v, vo
                  "clip_adam: buffers must be 16-byte aligned");
   CMMVAE_REQUIRE(!p_bf16 || ((uintptr_t)p_bf16 & 7) == 0, "clip_adam: bf16 shadow must be 8-byte aligned");
   if (n == 0) return 0;
-  long long want = (n / 4 + 255) / 256 + 1; int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
+  // exactly one resident wave: a grid-stride loop launched wider than the occupancy leaves a second, thinly
+  // populated wave that doubles the run time of an HBM-bound kernel
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, clip_adam_kernel, 256, 0);
+    per_sm = occ > 0 ? occ : 1;
+  }
+  long long want = (n / 8 + 255) / 256 + 1;
+  const long long cap = (long long)sm_budget() * per_sm;
+  int blocks = (int)(want < cap ? want : cap);
   clip_adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, n, norm_sq,
                                                              max_norm, grad_scale, lr, beta1, beta2, eps, wd, bc1,
                                                              bc2);

@@ -1,0 +1,169 @@
+"""Host -> HBM feed for CSR minibatches.
+
+The reference hands ``training_step`` a ``torch.sparse_csr_tensor`` built on the host by
+``SparseCSRMatrixBatcherDataPipe`` (data/local/cellxgene_datapipe.py:169-193: scipy row slice ->
+``torch.sparse_csr_tensor(crow, col, val)``) and lets Lightning move it to the GPU with three separate
+pageable copies (sparse tensors cannot be pinned, cellxgene_datamodule.py:95-103).  ``CSRStager`` is the
+B200 side of that hand-off: the three arrays of a batch are packed back to back into ONE pinned block
+(``crow | col | val``, each 16-byte aligned), shipped with ONE async copy on a dedicated copy stream into a
+rotating set of HBM blocks, and handed to the step as views of that block -- indices and values reach the
+device bit-identical, int32 / fp32 exactly as scipy emitted them.
+
+    stager = CSRStager(max_cells=B, max_nnz=nnz_cap, device="cuda", depth=3)
+    blk = stager.reserve(n_cells, nnz)               # numpy views into the next pinned block
+    slice_rows(indptr, indices, data, lo, hi, out=blk)   # the batcher writes the rows in place
+    ticket = stager.commit(blk, n_genes)             # async H2D, returns immediately
+    x = stager.get(ticket)                           # torch.sparse_csr tensor on the device; the current
+                                                     # stream waits for the copy, the host does not
+    model.training_step((x, metadata, species), i);  stager.release(ticket)
+(``put(crow, col, val, n_genes)`` = reserve + copy in + commit, for producers that already hold arrays.)
+
+A slot is reused ``depth`` puts later; ``put`` first waits (host side) for the event recorded by the
+consumer of that slot's previous occupant, so an in-flight step never sees its input overwritten.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+
+def _align(n: int, a: int = 16) -> int:
+    return (n + a - 1) // a * a
+
+
+def block_layout(n_cells: int, nnz: int):
+    """byte offsets of (crow, col, val) inside one staged block and the block's size"""
+    o_crow = 0
+    o_col = _align(o_crow + 4 * (n_cells + 1))
+    o_val = _align(o_col + 4 * nnz)
+    return o_crow, o_col, o_val, _align(o_val + 4 * nnz)
+
+
+def slice_rows(indptr: np.ndarray, indices: np.ndarray, data: np.ndarray, lo: int, hi: int, out=None):
+    """rows [lo, hi) of a CSR chunk as (crow int32 rebased to 0, col int32, val fp32) -- what scipy's
+    ``chunk[lo:hi]`` yields (cellxgene_datapipe.py:173-183), without building a scipy object.  With
+    ``out`` (a ``Block`` from ``CSRStager.reserve(hi - lo, indptr[hi] - indptr[lo])``) the rows are written
+    straight into pinned memory."""
+    a, b = int(indptr[lo]), int(indptr[hi])
+    if out is not None:
+        np.subtract(indptr[lo:hi + 1], indptr[lo], out=out.crow, casting="unsafe")
+        out.col[:], out.val[:] = indices[a:b], data[a:b]
+        return out.crow, out.col, out.val
+    crow = (indptr[lo:hi + 1] - indptr[lo]).astype(np.int32, copy=False)
+    return crow, indices[a:b].astype(np.int32, copy=False), data[a:b].astype(np.float32, copy=False)
+
+
+@dataclass
+class Ticket:
+    slot: int
+    n_cells: int
+    n_genes: int
+    nnz: int
+    ready: Optional[torch.cuda.Event]
+
+
+@dataclass
+class Block:
+    slot: int
+    n_cells: int
+    nnz: int
+    crow: np.ndarray
+    col: np.ndarray
+    val: np.ndarray
+
+
+class CSRStager:
+    def __init__(self, max_cells: int, max_nnz: int, device="cuda", depth: int = 3):
+        if depth < 2:
+            raise ValueError("CSRStager needs depth >= 2 (one block in flight, one being filled)")
+        self.device = torch.device(device)
+        self.max_cells, self.max_nnz, self.depth = int(max_cells), int(max_nnz), int(depth)
+        self.nbytes = block_layout(self.max_cells, self.max_nnz)[3]
+        self.on_gpu = self.device.type == "cuda"
+        if self.on_gpu and not torch.cuda.is_available():
+            raise RuntimeError("CSRStager(device='cuda') needs a CUDA device")
+        self.host = [torch.empty(self.nbytes, dtype=torch.uint8, pin_memory=self.on_gpu) for _ in range(depth)]
+        self.dev = [torch.empty(self.nbytes, dtype=torch.uint8, device=self.device) for _ in range(depth)]
+        self.stream = torch.cuda.Stream(self.device) if self.on_gpu else None
+        self._consumed = [None] * depth     # event: the step that read this slot has been enqueued and finished
+        self._copied = [None] * depth       # event: the H2D copy out of the pinned block has finished
+        self._n = 0
+        self.bytes_staged = 0
+
+    # ------------------------------------------------------------------------------------------ put
+    def reserve(self, n_cells: int, nnz: int) -> "Block":
+        """next pinned block, as numpy views (crow int32 [n_cells+1], col int32 [nnz], val fp32 [nnz]) the
+        batcher fills IN PLACE (``slice_rows(..., out=block)``) -- no intermediate host copy"""
+        if n_cells < 0 or n_cells > self.max_cells or nnz < 0 or nnz > self.max_nnz:
+            raise ValueError(f"batch of {n_cells} cells / {nnz} nnz exceeds the stager's "
+                             f"{self.max_cells} cells / {self.max_nnz} nnz")
+        slot = self._n % self.depth
+        self._n += 1
+        if self._copied[slot] is not None:
+            self._copied[slot].synchronize()      # the pinned block is free once its copy has left
+        o_crow, o_col, o_val, _ = block_layout(n_cells, nnz)
+        h = self.host[slot].numpy()
+        return Block(slot, n_cells, nnz,
+                     h[o_crow:o_crow + 4 * (n_cells + 1)].view(np.int32), h[o_col:o_col + 4 * nnz].view(np.int32),
+                     h[o_val:o_val + 4 * nnz].view(np.float32))
+
+    def commit(self, b: "Block", n_genes: int) -> Ticket:
+        """ship a filled block: one async H2D copy on the copy stream.  A block may be committed again
+        (unchanged) as long as it has not been handed out by a later ``reserve``"""
+        if b.n_cells >= 0 and (int(b.crow[0]) != 0 or int(b.crow[-1]) != b.nnz):
+            raise ValueError("inconsistent CSR arrays (crow[0] must be 0, crow[-1] == len(col) == len(val))")
+        used = block_layout(b.n_cells, b.nnz)[3]
+        self.bytes_staged = used
+        slot = b.slot
+        if not self.on_gpu:
+            self.dev[slot][:used].copy_(self.host[slot][:used])
+            return Ticket(slot, b.n_cells, int(n_genes), b.nnz, None)
+        with torch.cuda.stream(self.stream):
+            if self._consumed[slot] is not None:
+                self.stream.wait_event(self._consumed[slot])    # do not overwrite a block a step still reads
+            self.dev[slot][:used].copy_(self.host[slot][:used], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self._copied[slot] = ev
+        return Ticket(slot, b.n_cells, int(n_genes), b.nnz, ev)
+
+    def put(self, crow, col, val, n_genes: int) -> Ticket:
+        """reserve + copy the three arrays in + commit (for producers that already hold numpy arrays)"""
+        crow, col, val = (np.asarray(a) for a in (crow, col, val))
+        n_cells, nnz = int(crow.shape[0]) - 1, int(col.shape[0])
+        if val.shape[0] != nnz or (n_cells >= 0 and (int(crow[-1]) != nnz or int(crow[0]) != 0)):
+            raise ValueError("inconsistent CSR arrays (crow[0] must be 0, crow[-1] == len(col) == len(val))")
+        if nnz and int(col.max()) >= 2 ** 31:
+            raise ValueError("CSR indices do not fit int32")
+        b = self.reserve(n_cells, nnz)
+        b.crow[:], b.col[:], b.val[:] = crow, col, val      # casts int64 -> int32 / f64 -> f32 on the way in
+        return self.commit(b, n_genes)
+
+    # ------------------------------------------------------------------------------------------ get
+    def arrays(self, t: Ticket):
+        """device views (crow int32 [n_cells+1], col int32 [nnz], val fp32 [nnz]) of a staged batch; the
+        current stream waits for the copy"""
+        if t.ready is not None:
+            torch.cuda.current_stream(self.device).wait_event(t.ready)
+        o_crow, o_col, o_val, _ = block_layout(t.n_cells, t.nnz)
+        d = self.dev[t.slot]
+        crow = d[o_crow:o_crow + 4 * (t.n_cells + 1)].view(torch.int32)
+        col = d[o_col:o_col + 4 * t.nnz].view(torch.int32)
+        val = d[o_val:o_val + 4 * t.nnz].view(torch.float32)
+        return crow, col, val
+
+    def get(self, t: Ticket) -> torch.Tensor:
+        """the staged batch as the ``torch.sparse_csr_tensor`` the reference's ``training_step`` receives"""
+        crow, col, val = self.arrays(t)
+        return torch.sparse_csr_tensor(crow, col, val, size=(t.n_cells, t.n_genes))
+
+    def release(self, t: Ticket):
+        """call after the step that consumes ``t`` has been enqueued: its slot may be refilled once that
+        step has finished on the device"""
+        if self.on_gpu:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._consumed[t.slot] = ev

@@ -1,0 +1,153 @@
+"""CSR batch feed: the staged block must hand the step the arrays scipy emitted, bit for bit."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+from mmvae_b200.feed import CSRStager, block_layout, slice_rows
+from oracle.cmmvae_oracle import synth_csr
+
+
+def _ragged(seed, B=37, G=501):
+    rng = np.random.default_rng(seed)
+    m = sp.random(B, G, density=0.07, format="csr", dtype=np.float32, random_state=rng)
+    m[3] = 0            # an empty cell
+    m[B - 1] = 0        # empty last row
+    m.eliminate_zeros()
+    m.sort_indices()
+    return m
+
+
+def test_block_layout_is_aligned_and_disjoint():
+    for B, nnz in [(0, 0), (1, 1), (37, 1234), (1024, 3_099_136)]:
+        o_crow, o_col, o_val, size = block_layout(B, nnz)
+        assert o_crow == 0 and o_col % 16 == 0 and o_val % 16 == 0 and size % 16 == 0
+        assert o_col >= 4 * (B + 1) and o_val >= o_col + 4 * nnz and size >= o_val + 4 * nnz
+
+
+def test_slice_rows_matches_scipy_row_slicing():
+    m = _ragged(0)
+    for lo, hi in [(0, 37), (2, 5), (3, 4), (30, 37), (5, 5)]:
+        crow, col, val = slice_rows(m.indptr, m.indices, m.data, lo, hi)
+        ref = m[lo:hi]
+        assert crow.dtype == np.int32 and col.dtype == np.int32 and val.dtype == np.float32
+        np.testing.assert_array_equal(crow, ref.indptr)
+        np.testing.assert_array_equal(col, ref.indices)
+        np.testing.assert_array_equal(val, ref.data)
+
+
+def test_stager_cpu_round_trip_and_rotation():
+    st = CSRStager(max_cells=64, max_nnz=4096, device="cpu", depth=2)
+    kept = []
+    for seed in range(5):
+        m = _ragged(seed)
+        t = st.put(m.indptr, m.indices, m.data, m.shape[1])
+        crow, col, val = st.arrays(t)
+        assert crow.dtype == torch.int32 and col.dtype == torch.int32 and val.dtype == torch.float32
+        np.testing.assert_array_equal(crow.numpy(), m.indptr)
+        np.testing.assert_array_equal(col.numpy(), m.indices)
+        np.testing.assert_array_equal(val.numpy().view(np.uint32), m.data.view(np.uint32))
+        x = st.get(t)
+        assert x.layout == torch.sparse_csr and tuple(x.shape) == m.shape
+        kept.append(t)
+    assert kept[0].slot == kept[2].slot == kept[4].slot and kept[1].slot == kept[3].slot
+
+
+def test_reserve_fill_in_place_commit_and_recommit():
+    m = _ragged(11)
+    st = CSRStager(max_cells=64, max_nnz=4096, device="cpu", depth=2)
+    lo, hi = 4, 29
+    blk = st.reserve(hi - lo, int(m.indptr[hi] - m.indptr[lo]))
+    slice_rows(m.indptr, m.indices, m.data, lo, hi, out=blk)
+    ref = m[lo:hi]
+    for _ in range(2):      # an unchanged block may be shipped again
+        crow, col, val = st.arrays(st.commit(blk, m.shape[1]))
+        np.testing.assert_array_equal(crow.numpy(), ref.indptr)
+        np.testing.assert_array_equal(col.numpy(), ref.indices)
+        np.testing.assert_array_equal(val.numpy(), ref.data)
+    blk.crow[-1] += 1
+    with pytest.raises(ValueError, match="inconsistent"):
+        st.commit(blk, m.shape[1])
+
+
+def test_stager_accepts_int64_indices_and_empty_batches():
+    st = CSRStager(max_cells=8, max_nnz=16, device="cpu")
+    t = st.put(np.array([0, 2, 2, 3], dtype=np.int64), np.array([5, 9, 1], dtype=np.int64),
+               np.array([1.5, 2.5, 3.5], dtype=np.float64), 10)
+    crow, col, val = st.arrays(t)
+    assert crow.tolist() == [0, 2, 2, 3] and col.tolist() == [5, 9, 1] and val.tolist() == [1.5, 2.5, 3.5]
+    t = st.put(np.zeros(4, dtype=np.int32), np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.float32), 10)
+    crow, col, val = st.arrays(t)
+    assert crow.tolist() == [0, 0, 0, 0] and col.numel() == 0 and val.numel() == 0
+
+
+def test_stager_rejects_oversize_and_inconsistent_input():
+    st = CSRStager(max_cells=4, max_nnz=8, device="cpu")
+    with pytest.raises(ValueError, match="exceeds"):
+        st.put(np.arange(7, dtype=np.int32), np.zeros(6, np.int32), np.zeros(6, np.float32), 10)
+    with pytest.raises(ValueError, match="exceeds"):
+        st.put(np.array([0, 9], np.int32), np.zeros(9, np.int32), np.zeros(9, np.float32), 10)
+    with pytest.raises(ValueError, match="inconsistent"):
+        st.put(np.array([0, 3], np.int32), np.zeros(2, np.int32), np.zeros(2, np.float32), 10)
+    with pytest.raises(ValueError, match="depth"):
+        CSRStager(4, 8, device="cpu", depth=1)
+
+
+@pytest.mark.gpu
+def test_stager_gpu_bit_identical_over_many_rotations():
+    B, G = 256, 60530
+    st = CSRStager(max_cells=B, max_nnz=int(B * G * 0.06), device="cuda", depth=3)
+    tickets, srcs = [], []
+    for seed in range(7):
+        crow, col, val = synth_csr(B, G, 0.05, seed)
+        t = st.put(crow, col, val, G)
+        dcrow, dcol, dval = st.arrays(t)
+        # consume on the current stream (a reduction stands in for the step), then release the slot
+        got = (dcrow.clone(), dcol.clone(), dval.clone())
+        st.release(t)
+        tickets.append(got)
+        srcs.append((crow, col, val))
+    torch.cuda.synchronize()
+    for (dcrow, dcol, dval), (crow, col, val) in zip(tickets, srcs):
+        np.testing.assert_array_equal(dcrow.cpu().numpy(), crow)
+        np.testing.assert_array_equal(dcol.cpu().numpy(), col)
+        np.testing.assert_array_equal(dval.cpu().numpy().view(np.uint32), val.view(np.uint32))
+    assert st.host[0].is_pinned()
+
+
+@pytest.mark.gpu
+def test_training_step_through_the_stager_matches_direct_feed(tmp_path):
+    import pandas as pd
+    from helpers import CONDITIONS, GoldenCase, build_b200_model, csr_batch
+    from mmvae_b200 import layers as L
+    from mmvae_b200.modules.base import KLAnnealingFn
+    gc = GoldenCase("core_human")
+    L.set_precision("fp32")
+    try:
+        logs = []
+        for staged in (False, True):
+            model = build_b200_model(gc, tmp_path, kl_fn=KLAnnealingFn(0.5))
+            model.load_state_dict({f"module.{k}": v for k, v in gc.state("init").items()}, strict=True)
+            model.cuda().train()
+            model.configure_optimizers()
+            st = CSRStager(64, 4096, device="cuda", depth=2)
+            rec = {}
+            for t in range(gc.n_steps):
+                s = gc.step(t)
+                L.inject_noise(s["eps"].cuda())
+                meta = pd.DataFrame({c: [f"{c}_{int(i)}" for i in s["labels"][c]] for c in CONDITIONS})
+                if staged:
+                    tk = st.put(s["crow"], s["col"], s["val"], gc.genes["human"])
+                    x = st.get(tk)
+                else:
+                    x = csr_batch(s["crow"], s["col"], s["val"], gc.genes["human"])
+                model.training_step((x, meta, "human"), t)
+                if staged:
+                    st.release(tk)
+                rec.update({f"{t}/{k}": float(v) for k, v in model.logged_metrics.items()})
+            logs.append(rec)
+        assert logs[0].keys() == logs[1].keys() and len(logs[0]) > 0
+        for k in logs[0]:
+            assert logs[0][k] == pytest.approx(logs[1][k], rel=1e-6), k
+    finally:
+        L.set_precision("bf16")

@@ -159,8 +159,10 @@ def _midsize_spec(G, H1, H2, Hv, Z, with_adv):
         adv_weight=1.0)
 
 
+@pytest.mark.parametrize("dims", [(3000, 512, 256, 128, 64, 300), (2777, 384, 192, 128, 64, 320)],
+                         ids=["config2-like", "config4-like-odd-G"])
 @pytest.mark.parametrize("with_adv", [False, True])
-def test_bf16_step_matches_oracle_midsize(with_adv, tmp_path):
+def test_bf16_step_matches_oracle_midsize(with_adv, dims, tmp_path):
     """bf16 tcgen05 path (fused decoder loss, TMA GEMMs) against the oracle at a size where every
     tile/edge path is exercised: G not a multiple of the tile, several cell blocks.
     Stated tolerances (bf16 operands, fp32 accumulation): loss 5e-4, KL 5e-3, grads 6e-2 rel-L2 per
@@ -175,7 +177,7 @@ def test_bf16_step_matches_oracle_midsize(with_adv, tmp_path):
     import os
 
     L.set_precision("bf16")
-    G, H1, H2, Hv, Z, B = 3000, 512, 256, 128, 64, 300
+    G, H1, H2, Hv, Z, B = dims   # second shape: BASELINE config 4's 1024-768|768-512-Z256 proportions, odd G
     os.makedirs(tmp_path / "human", exist_ok=True)
     for cond, n in CONDITIONS.items():
         pd.DataFrame([f"{cond}_{i}" for i in range(n)]).to_csv(tmp_path / "human" / f"unique_expression_{cond}.csv",
