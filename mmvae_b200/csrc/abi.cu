@@ -1,5 +1,7 @@
 // ABI bookkeeping: version, thread-local error string, launch counter.
 #include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -8,6 +10,13 @@ static thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 static std::atomic<int> g_sm_budget{kNumSMs};
 int sm_budget() { return g_sm_budget.load(std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("CMMVAE_PDL");
+    return !(e && strcmp(e, "0") == 0);
+  }();
+  return on;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;

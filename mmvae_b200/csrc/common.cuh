@@ -32,6 +32,31 @@ inline int check_launch(const char* what) {
     }                              \
   } while (0)
 
+// Programmatic dependent launch: a kernel launched through launch_pdl may be scheduled while its predecessor in
+// the stream is still running; it must execute pdl_sync() before it touches global memory (the call returns
+// once the predecessor grid has completed and its writes are visible).  Everything before pdl_sync() -- barrier
+// init, TMEM allocation, tensor-map prefetch, block scheduling itself -- overlaps the predecessor's tail.
+// pdl_sync() also lets this grid's own successor start its prologue.  CMMVAE_PDL=0 turns the attribute off.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 constexpr int kNumSMs = 148;
 // SMs the persistent kernels may plan for (grid sizes, split-K factors).  148 by default; the host lowers it
 // while NCCL kernels share the GPU so that every planned CTA is resident at once (cmmvae_set_sm_budget).

@@ -88,6 +88,7 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // prologue overlapped the previous kernel; its results are visible from here on
 
   if (warp == kTmaWarp) {
     if (lane == 0) {
@@ -318,13 +319,13 @@ extern "C" int cmmvae_decoder_mse_fused(const void* h, int ldh, const void* Wout
   cudaMemsetAsync(loss_sum, 0, sizeof(double), st);
   if (!tile_ptr) {   // build the 64-gene-window pointer table (the tensor-pipe SpMM shares it when it ran)
     int blocks = B < 148 * 16 ? B : 148 * 16;   // one CTA per row
-    tile_ptr64_kernel<<<blocks, 256, 0, st>>>(crow, col, B, p.ntp, (int32_t*)workspace);
+    launch_pdl(tile_ptr64_kernel, dim3(blocks), dim3(256), 0, st, crow, col, B, p.ntp, (int32_t*)workspace);
     if (int rc = check_launch("tile_ptr64")) return rc;
     tile_ptr = (const int32_t*)workspace;
   }
   p.tp = tile_ptr;
   const int num_tiles = p.num_m * p.num_n;
   const int grid = num_tiles < sm_budget() ? num_tiles : sm_budget();
-  decoder_mse_fused_kernel<<<grid, kDecThreads, DecSmem::kTotal, st>>>(tmH, tmW, tmD, p);
+  launch_pdl(decoder_mse_fused_kernel, dim3(grid), dim3(kDecThreads), DecSmem::kTotal, st, tmH, tmW, tmD, p);
   return check_launch("decoder_mse_fused");
 }

@@ -12,6 +12,7 @@ constexpr int kRowsPerChunk = 256;
 
 __global__ void __launch_bounds__(256) bn_stats_reduce_kernel(const float* __restrict__ Y, int B, int H,
                                                               double* __restrict__ scratch) {
+  pdl_sync();
   __shared__ double s1[8][33], s2[8][33];
   const int h = blockIdx.x * 32 + threadIdx.x;
   const int r0 = blockIdx.y * kRowsPerChunk;
@@ -40,6 +41,7 @@ __global__ void __launch_bounds__(256) bn_stats_reduce_kernel(const float* __res
 __global__ void bn_stats_finalize_kernel(const double* __restrict__ scratch, int B, int H, float eps,
                                          float momentum, float* __restrict__ mean, float* __restrict__ rstd,
                                          float* __restrict__ rm, float* __restrict__ rv) {
+  pdl_sync();
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= H) return;
   const double m = scratch[h] / B;
@@ -68,6 +70,7 @@ __global__ void __launch_bounds__(256) bn_act_drop_fwd_kernel(const float* __res
                                                               const uint8_t* __restrict__ mask,
                                                               float* __restrict__ o32,
                                                               __nv_bfloat16* __restrict__ o16) {
+  pdl_sync();
   const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -103,6 +106,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
                                                             const float* __restrict__ rstd, int relu, float p_drop,
                                                             unsigned long long seed, const uint8_t* __restrict__ mask,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_sync();
   __shared__ float s1[8][33], s2[8][33];
   const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
   const int h = blockIdx.x * 32 + threadIdx.x;
@@ -143,6 +147,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            const float* __restrict__ dbeta, float* __restrict__ dY,
                                                            __nv_bfloat16* __restrict__ dY16,
                                                            float* __restrict__ dbias) {
+  pdl_sync();
   __shared__ float s1[8][33];
   const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
   const int h = blockIdx.x * 32 + threadIdx.x;
@@ -182,6 +187,7 @@ __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, int M, int N, int ldx,
                                                      float* __restrict__ out) {
+  pdl_sync();
   __shared__ float s1[8][33];
   const int h = blockIdx.x * 32 + threadIdx.x;
   const int r0 = blockIdx.y * kRowsPerChunk, r1 = min(M, r0 + kRowsPerChunk);
@@ -200,6 +206,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ X, in
 // bf16, 8 columns (16 bytes) per thread: a warp reads 512 contiguous bytes of each row
 __global__ void __launch_bounds__(256) colsum_bf16x8_kernel(const __nv_bfloat16* __restrict__ X, int M, int N,
                                                             int ldx, float* __restrict__ out) {
+  pdl_sync();
   __shared__ float s1[8][32][9];
   const int c0 = (blockIdx.x * 32 + threadIdx.x) * 8;
   const int r0 = blockIdx.y * 128, r1 = min(M, r0 + 128);
@@ -235,6 +242,7 @@ __global__ void __launch_bounds__(256) reparam_kl_fwd_kernel(const float* __rest
                                                              float var_eps, float* __restrict__ z32,
                                                              __nv_bfloat16* __restrict__ z16,
                                                              double* __restrict__ sums) {
+  pdl_sync();
   __shared__ double red[32];
   const long long n = (long long)B * Z;
   double kl = 0.0, sm = 0.0, sv = 0.0;
@@ -268,6 +276,7 @@ __global__ void __launch_bounds__(256) reparam_kl_bwd_kernel(const float* __rest
                                                              const float* __restrict__ dz, int B, int Z,
                                                              float var_eps, float kl_scale, float* __restrict__ dML,
                                                              __nv_bfloat16* __restrict__ dML16) {
+  pdl_sync();
   const long long n = (long long)B * Z;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -293,6 +302,7 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const float* __restrict
                                                          const long long* __restrict__ labels, float scale,
                                                          float* __restrict__ dl, int ldd,
                                                          double* __restrict__ loss_sum) {
+  pdl_sync();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= B) return;
   const float* row = logits + (size_t)warp * ldl;
@@ -323,6 +333,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
                                                        int N, int K, const float* __restrict__ bias, int relu,
                                                        int accumulate, float* __restrict__ C32,
                                                        __nv_bfloat16* __restrict__ C16, int ldc) {
+  pdl_sync();
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
@@ -389,6 +400,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n,
                                                     double* __restrict__ out) {
+  pdl_sync();
   __shared__ double red[32];
   double acc = 0.0;
   const long long n4 = n / 4;
@@ -421,6 +433,7 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, c
                                                         const double* __restrict__ norm_sq, float max_norm,
                                                         float grad_scale, float lr, float b1, float b2, float eps,
                                                         float wd, float bc1, float bc2) {
+  pdl_sync();
   float coef = 1.f;
   if (max_norm > 0.f && norm_sq) {
     const float total = (float)sqrt(*norm_sq) * fabsf(grad_scale);
@@ -471,6 +484,7 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, c
 // utilities
 // ---------------------------------------------------------------------------------------------
 __global__ void cast_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, long long n) {
+  pdl_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     d[i] = __float2bfloat16(s[i]);
@@ -493,6 +507,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ s,
 }
 
 __global__ void axpy_kernel(float* __restrict__ a, const float* __restrict__ b, float alpha, long long n) {
+  pdl_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     a[i] = fmaf(alpha, b[i], a[i]);
@@ -513,9 +528,9 @@ extern "C" int cmmvae_bn_stats(const float* Y, int B, int H, float eps, float mo
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * (size_t)H, st);
   dim3 grid((H + 31) / 32, (B + kRowsPerChunk - 1) / kRowsPerChunk), block(32, 8);
-  bn_stats_reduce_kernel<<<grid, block, 0, st>>>(Y, B, H, scratch);
+  launch_pdl(bn_stats_reduce_kernel, dim3(grid), dim3(block), 0, st, Y, B, H, scratch);
   if (int rc = check_launch("bn_stats_reduce")) return rc;
-  bn_stats_finalize_kernel<<<(H + 255) / 256, 256, 0, st>>>(scratch, B, H, eps, momentum, mean, rstd,
+  launch_pdl(bn_stats_finalize_kernel, dim3((H + 255) / 256), dim3(256), 0, st, scratch, B, H, eps, momentum, mean, rstd,
                                                             running_mean, running_var);
   return check_launch("bn_stats_finalize");
 }
@@ -533,8 +548,7 @@ extern "C" int cmmvae_bn_act_drop_fwd(const float* Y, int B, int H, const float*
   CMMVAE_REQUIRE(!gamma || (mean && rstd && beta), "bn_act_drop_fwd: gamma without mean/rstd/beta");
   CMMVAE_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "bn_act_drop_fwd: p_drop out of range");
   const long long n = (long long)B * H;
-  bn_act_drop_fwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(
-      Y, n, H, mean, rstd, gamma, beta, relu, p_drop, seed, mask, out_f32, (__nv_bfloat16*)out_bf16);
+  launch_pdl(bn_act_drop_fwd_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, Y, n, H, mean, rstd, gamma, beta, relu, p_drop, seed, mask, out_f32, (__nv_bfloat16*)out_bf16);
   return check_launch("bn_act_drop_fwd");
 }
 
@@ -550,12 +564,12 @@ extern "C" int cmmvae_bn_act_drop_bwd(const float* dOut, const float* Y, const f
   if (gamma) {
     cudaMemsetAsync(dgamma, 0, sizeof(float) * H, st);
     cudaMemsetAsync(dbeta, 0, sizeof(float) * H, st);
-    bn_bwd_reduce_kernel<<<grid, block, 0, st>>>(dOut, Y, out, B, H, mean, rstd, relu, p_drop, seed, mask,
+    launch_pdl(bn_bwd_reduce_kernel, dim3(grid), dim3(block), 0, st, dOut, Y, out, B, H, mean, rstd, relu, p_drop, seed, mask,
                                                  dgamma, dbeta);
     if (int rc = check_launch("bn_bwd_reduce")) return rc;
   }
   if (dbias) cudaMemsetAsync(dbias, 0, sizeof(float) * H, st);
-  bn_bwd_apply_kernel<<<grid, block, 0, st>>>(dOut, Y, out, B, H, mean, rstd, gamma, relu, p_drop, seed, mask,
+  launch_pdl(bn_bwd_apply_kernel, dim3(grid), dim3(block), 0, st, dOut, Y, out, B, H, mean, rstd, gamma, relu, p_drop, seed, mask,
                                               dgamma, dbeta, dY, (__nv_bfloat16*)dY_bf16, dbias);
   return check_launch("bn_bwd_apply");
 }
@@ -567,13 +581,13 @@ extern "C" int cmmvae_colsum(const void* X, int x_dtype, int M, int N, int ldx, 
   if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * N, st);
   dim3 grid((N + 31) / 32, (M + kRowsPerChunk - 1) / kRowsPerChunk), block(32, 8);
   if (x_dtype == CMMVAE_F32) {
-    colsum_kernel<float><<<grid, block, 0, st>>>((const float*)X, M, N, ldx, out);
+    launch_pdl(colsum_kernel<float>, dim3(grid), dim3(block), 0, st, (const float*)X, M, N, ldx, out);
   } else if (ldx % 8 == 0 && ((uintptr_t)X & 15) == 0 && ((N + 7) / 8 * 8) <= ldx) {
     // rows are padded to a multiple of 8 columns (padding holds zeros or is never summed into out)
     dim3 g8((N + 255) / 256, (M + 127) / 128);
-    colsum_bf16x8_kernel<<<g8, block, 0, st>>>((const __nv_bfloat16*)X, M, N, ldx, out);
+    launch_pdl(colsum_bf16x8_kernel, dim3(g8), dim3(block), 0, st, (const __nv_bfloat16*)X, M, N, ldx, out);
   } else {
-    colsum_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)X, M, N, ldx, out);
+    launch_pdl(colsum_kernel<__nv_bfloat16>, dim3(grid), dim3(block), 0, st, (const __nv_bfloat16*)X, M, N, ldx, out);
   }
   return check_launch("colsum");
 }
@@ -585,7 +599,7 @@ extern "C" int cmmvae_reparam_kl_fwd(const float* ML, const float* eps, int B, i
   cudaMemsetAsync(sums, 0, sizeof(double) * 3, st);
   const long long n = (long long)B * Z;
   long long want = (n + 255) / 256; int blocks = (int)(want < 148 * 4 ? want : 148 * 4);
-  reparam_kl_fwd_kernel<<<blocks, 256, 0, st>>>(ML, eps, B, Z, var_eps, z_f32, (__nv_bfloat16*)z_bf16, sums);
+  launch_pdl(reparam_kl_fwd_kernel, dim3(blocks), dim3(256), 0, st, ML, eps, B, Z, var_eps, z_f32, (__nv_bfloat16*)z_bf16, sums);
   return check_launch("reparam_kl_fwd");
 }
 
@@ -593,7 +607,7 @@ extern "C" int cmmvae_reparam_kl_bwd(const float* ML, const float* eps, const fl
                                      float var_eps, float kl_scale, float* dML, void* dML_bf16, void* stream) {
   CMMVAE_REQUIRE(B > 0 && Z > 0, "reparam_kl_bwd: bad shape");
   const long long n = (long long)B * Z;
-  reparam_kl_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(ML, eps, dz, B, Z, var_eps, kl_scale, dML,
+  launch_pdl(reparam_kl_bwd_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, ML, eps, dz, B, Z, var_eps, kl_scale, dML,
                                                                          (__nv_bfloat16*)dML_bf16);
   return check_launch("reparam_kl_bwd");
 }
@@ -601,7 +615,7 @@ extern "C" int cmmvae_reparam_kl_bwd(const float* ML, const float* eps, const fl
 extern "C" int cmmvae_softmax_ce_sum(const float* logits, int ldl, int B, int C, const long long* labels,
                                      float scale, float* dlogits, int ldd, double* loss_sum, void* stream) {
   CMMVAE_REQUIRE(B > 0 && C > 0 && ldl >= C, "softmax_ce_sum: bad shape");
-  softmax_ce_kernel<<<(B * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(logits, ldl, B, C, labels, scale,
+  launch_pdl(softmax_ce_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, (cudaStream_t)stream, logits, ldl, B, C, labels, scale,
                                                                              dlogits, ldd, loss_sum);
   return check_launch("softmax_ce_sum");
 }
@@ -613,7 +627,7 @@ extern "C" int cmmvae_gemm_f32(const float* A, int lda, int transA, const float*
   CMMVAE_REQUIRE(C_f32 || C_bf16, "gemm_f32: no output");
   CMMVAE_REQUIRE(!accumulate || C_f32, "gemm_f32: accumulate needs C_f32");
   dim3 grid((N + 63) / 64, (M + 63) / 64);
-  gemm_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, lda, transA, Bm, ldb, transB, M, N, K, bias, relu,
+  launch_pdl(gemm_f32_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, A, lda, transA, Bm, ldb, transB, M, N, K, bias, relu,
                                                           accumulate, C_f32, (__nv_bfloat16*)C_bf16, ldc);
   return check_launch("gemm_f32");
 }
@@ -623,7 +637,7 @@ extern "C" int cmmvae_sumsq(const float* g, long long n, double* norm_sq, void* 
   CMMVAE_REQUIRE(((uintptr_t)g & 15) == 0, "sumsq: g must be 16-byte aligned");
   if (n == 0) return 0;
   long long want = (n / 4 + 255) / 256 + 1; int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
-  sumsq_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, n, norm_sq);
+  launch_pdl(sumsq_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, g, n, norm_sq);
   return check_launch("sumsq");
 }
 
@@ -646,7 +660,7 @@ extern "C" int cmmvae_clip_adam(float* p, const float* g, float* m, float* v, vo
   long long want = (n / 8 + 255) / 256 + 1;
   const long long cap = (long long)sm_budget() * per_sm;
   int blocks = (int)(want < cap ? want : cap);
-  clip_adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, n, norm_sq,
+  launch_pdl(clip_adam_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, (__nv_bfloat16*)p_bf16, n, norm_sq,
                                                              max_norm, grad_scale, lr, beta1, beta2, eps, wd, bc1,
                                                              bc2);
   return check_launch("clip_adam");
@@ -654,7 +668,7 @@ extern "C" int cmmvae_clip_adam(float* p, const float* g, float* m, float* v, vo
 
 extern "C" int cmmvae_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {
   if (n <= 0) return 0;
-  cast_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+  launch_pdl(cast_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, src, (__nv_bfloat16*)dst, n);
   return check_launch("cast_f32_bf16");
 }
 
@@ -672,6 +686,6 @@ extern "C" int cmmvae_transpose(const void* src, void* dst, int dtype, int R, in
 
 extern "C" int cmmvae_axpy(float* a, const float* b, float alpha, long long n, void* stream) {
   if (n <= 0) return 0;
-  axpy_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(a, b, alpha, n);
+  launch_pdl(axpy_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, a, b, alpha, n);
   return check_launch("axpy");
 }

@@ -95,6 +95,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // the prologue above overlapped the previous kernel; its results are visible from here on
 
   if (warp == kTmaWarp) {
     // ===== TMA producer =====
@@ -380,7 +381,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   }
   const long long units = (long long)((p.N + BN - 1) / BN) * ((p.M + BM - 1) / BM) * p.splits;
   const int grid = (int)(units < sm_budget() ? units : sm_budget());
-  kern<<<grid, kGemmThreads, S::kTotal, st>>>(tmA, tmB, tmC, p);
+  launch_pdl(kern, dim3(grid), dim3(kGemmThreads), S::kTotal, st, tmA, tmB, tmC, p);
   return check_launch("gemm_bf16_tc");
 }
 

@@ -54,6 +54,7 @@ struct SpParams {
 __global__ void __launch_bounds__(256) tile_ptr64_kernel(const int32_t* __restrict__ crow,
                                                          const int32_t* __restrict__ col, int B, int ntp,
                                                          int32_t* __restrict__ tp) {
+  pdl_sync();
   for (int b = blockIdx.x; b < B; b += gridDim.x) {      // one CTA per row
     const int s = crow[b], e = crow[b + 1];
     if (s == e) {
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(256) tile_ptr64_kernel(const int32_t* __restri
 // packed[i] = col[i] | bf16(val[i]) << 16   (G <= 65536); one 4-byte record per non-zero
 __global__ void csr_pack_kernel(const int32_t* __restrict__ col, const float* __restrict__ val, long long nnz,
                                 long long padded, uint32_t* __restrict__ packed) {
+  pdl_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < padded;
        i += (long long)gridDim.x * blockDim.x) {
     uint32_t r = 0;
@@ -130,6 +132,7 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // prologue overlapped the previous kernel; its results are visible from here on
 
   if (warp == kTmaWarp) {
     if (lane == 0) {
@@ -412,7 +415,7 @@ static int launch_spmm_tc(const CUtensorMap& tm, const CUtensorMap& tmC, const S
     }
     configured = true;
   }
-  kern<<<grid, kSpThreads, kSpSmem, st>>>(tm, tmC, p);
+  launch_pdl(kern, dim3(grid), dim3(kSpThreads), kSpSmem, st, tm, tmC, p);
   return check_launch(BWD ? "csr_linear_bwd_w_tc" : "csr_linear_fwd_tc");
 }
 
@@ -433,13 +436,13 @@ extern "C" int cmmvae_csr_tile_ptr(const int32_t* crow, const int32_t* col, cons
   cudaStream_t st = (cudaStream_t)stream;
   const int ntp = (G + 63) / 64 + 1;
   int blocks = B < 148 * 16 ? B : 148 * 16;   // one CTA per row
-  tile_ptr64_kernel<<<blocks, 256, 0, st>>>(crow, col, B, ntp, tile_ptr);
+  launch_pdl(tile_ptr64_kernel, dim3(blocks), dim3(256), 0, st, crow, col, B, ntp, tile_ptr);
   if (int rc = check_launch("csr_tile_ptr")) return rc;
   long long want;
   const long long padded = (nnz + 3) / 4 * 4 + 4;
   want = (padded + 255) / 256;
   blocks = (int)(want < 148 * 16 ? want : 148 * 16);
-  csr_pack_kernel<<<blocks, 256, 0, st>>>(col, val, nnz, padded, (uint32_t*)packed);
+  launch_pdl(csr_pack_kernel, dim3(blocks), dim3(256), 0, st, col, val, nnz, padded, (uint32_t*)packed);
   return check_launch("csr_pack");
 }
 

@@ -399,6 +399,7 @@ class StepEngine:
         self.side = torch.cuda.Stream(device=self.device)
         self._side_used = False
         self.timers: Optional[Dict[str, list]] = None   # name -> [(start_event, end_event)] when profiling
+        self.timer_filter = None   # optional set of section names to time (an event record ends a PDL chain)
         self._seed = 0x5EED
         self.nccl_sms = int(os.environ.get("CMMVAE_NCCL_SMS", "32"))                  # SMs left to communication kernels when world > 1
         self.spmm_tc = True                 # bf16 policy: expert-encoder SpMM on the tensor pipe ...
@@ -415,7 +416,7 @@ class StepEngine:
         return t
 
     def _t0(self, name):
-        if self.timers is None:
+        if self.timers is None or (self.timer_filter is not None and name not in self.timer_filter):
             return None
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
@@ -645,13 +646,18 @@ class StepEngine:
         use_tc_spmm = (bf and self.spmm_tc and enc[0].N % 8 == 0 and G <= 65536 and
                        nnz >= self.spmm_tc_min_density * B * G)
         tp = None
+        ev = self._t0("csr_prep")
         if use_tc_spmm:
             tp = ops.csr_tile_ptr(crow, col, val, G, nnz, self.ws("tp64", (B * ((G + 63) // 64 + 1),), torch.int32),
                                   self.ws("packed", ((nnz + 3) // 4 * 4 + 4,), torch.int32))
+        self._t1(ev)
+        ev_mid = None
         for j, lp in enumerate(enc):
             x32, x16, caches[("enc", j)] = self._layer_fwd(f"enc{j}", lp, x32, x16, B,
                                                             csr=(crow, col, val, G, tp) if j == 0 else None,
                                                             masks=masks)
+            if j == 0:
+                ev_mid = self._t0("mid_fwd")     # everything between the two gene-sized layers
         hidden = []
         for j, lp in enumerate(self.vaeenc_plan):
             x32, x16, caches[("venc", j)] = self._layer_fwd(f"venc{j}", lp, x32, x16, B, masks=masks)
@@ -677,6 +683,7 @@ class StepEngine:
             x32, x16, caches[("dec", j)] = self._layer_fwd(f"dec{j}", lp, x32, x16, B, masks=masks)
         h32, h16 = x32, x16
         out = dec[-1]
+        self._t1(ev_mid)
         ev = self._t0("dp_wait_shadow_rest")
         gexp.wait_shadow("rest")
         self._t1(ev)
@@ -748,6 +755,7 @@ class StepEngine:
             pending = [gexp.exchange_segment_async(gexp.n_first)]
             ops.gemm(dl, 0, out.W32, 1, B, H1, G, C32=dh, use_tc=False)
         d = dh
+        ev_mid = self._t0("mid_bwd")
         for j in reversed(range(len(dec) - 1)):
             d = self._layer_bwd(f"dec{j}", dec[j], caches[("dec", j)], d, B)
         for j in reversed(range(len(self.vaedec_plan))):
@@ -783,6 +791,8 @@ class StepEngine:
                                                  self.ws("cursor", (G + 1,), torch.int32))
             csc = ("gather", cptr, ridx, cval, G)
         for j in reversed(range(len(enc))):
+            if j == 0:
+                self._t1(ev_mid)
             ev = self._t0("csr_linear_bwd_w+bn") if j == 0 else None
             d = self._layer_bwd(f"enc{j}", enc[j], caches[("enc", j)], d, B, need_dx=(j > 0),
                                 csc=csc if j == 0 else None)
