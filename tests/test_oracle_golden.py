@@ -97,8 +97,9 @@ def test_oracle_fast_csr_path_agrees():
     """the full-size CPU-timing path (torch sparse addmm, as the reference executes it) equals the
     explicit per-nonzero restatement, forward and weight gradient"""
     crow, col, val = O.synth_csr(16, 300, 0.1, seed=4)
-    W = torch.randn(32, 300, requires_grad=True)
-    b = torch.randn(32)
+    gen = torch.Generator().manual_seed(4)
+    W = torch.randn(32, 300, generator=gen).requires_grad_()
+    b = torch.randn(32, generator=gen)
     y0 = O.csr_linear(crow, col, val, W, b)
     g0, = torch.autograd.grad(y0.square().sum(), W)
     O.FAST_CSR = True
@@ -107,4 +108,6 @@ def test_oracle_fast_csr_path_agrees():
         g1, = torch.autograd.grad(y1.square().sum(), W)
     finally:
         O.FAST_CSR = False
-    assert torch.allclose(y0, y1, rtol=1e-5, atol=1e-5) and torch.allclose(g0, g1, rtol=1e-5, atol=1e-4)
+    # fp32 summation order differs between the two: compare against the tensor's scale
+    assert (y0 - y1).abs().max() <= 1e-5 * y0.abs().max()
+    assert (g0 - g1).abs().max() <= 1e-5 * g0.abs().max()
