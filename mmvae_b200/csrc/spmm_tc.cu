@@ -19,6 +19,7 @@
 //                 128B-swizzled layout, fence.proxy.async, arrive on the stage's full barrier
 //   warps 16..19  epilogue: drain accumulator i while tile i+1 is being multiplied
 #include "tc.cuh"
+#include <stdlib.h>
 
 namespace cmmvae {
 
@@ -43,6 +44,7 @@ struct SpParams {
   float* out;          // forward: Y[B,H]; backward: dWt[G,H]
   int splits;          // forward split-K over genes
   double* sumsq;       // backward only, optional: += sum of squares of dWt (fused gradient norm)
+  int dbg;
   int m_begin, m_end;  // backward only: gene range [m_begin, m_end) computed by this launch (m_begin % 128 == 0)
 };
 
@@ -267,22 +269,24 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
       const uint32_t phase = (f / SSTAGES) & 1;
       seq_advance(fut_s, SNG);
       window_ptrs(fut_s, fut);
-      load_entries(nxt, en);
+      if (!(p.dbg & 4)) load_entries(nxt, en);
       mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
       const uint32_t tile = smem_base + stage * kSpStage;
       // zero the 16 KB tile cooperatively (consecutive threads -> consecutive 16-byte chunks: conflict free)
+      if (!(p.dbg & 2)) {
 #pragma unroll
       for (int c = 0; c < 8; ++c) st_shared_zero16(tile + (c * 128 + t) * 16);
       asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      }
       const uint32_t line = tile + line_off;
       const int a0 = cur.q0, a1 = cur.q1, aw = cur.win;
-      const int n = a1 - a0;
+      const int n = (p.dbg & 1) ? 0 : a1 - a0;
 #pragma unroll
       for (int u = 0; u < E; ++u) {
         const int c = (int)(ec[u] & 0xFFFFu) - aw;
         st_shared_u16_if(line + ((((c >> 3) ^ swz) << 4) | ((c & 7) << 1)), ec[u] >> 16, u < n);
       }
-      for (int q = a0 + E; q < a1; ++q) {   // windows with more than E entries (dense batches)
+      for (int q = a0 + E; q < a0 + n; ++q) {   // windows with more than E entries (dense batches)
         const uint32_t r = __ldg(p.packed + q);
         const int c = (int)(r & 0xFFFFu) - aw;
         st_shared_u16_if(line + ((((c >> 3) ^ swz) << 4) | ((c & 7) << 1)), r >> 16, true);
@@ -454,6 +458,7 @@ extern "C" int cmmvae_csr_linear_fwd_tc(const void* packed, const int32_t* tile_
   SpParams p;
   p.B = B; p.G = G; p.H = H; p.packed = (const uint32_t*)packed; p.tp = tile_ptr; p.ntp = (G + 63) / 64 + 1;
   p.bias = bias; p.out = Y; p.sumsq = nullptr; p.m_begin = 0; p.m_end = B;
+  { const char* e = getenv("CMMVAE_SPMM_DBG"); p.dbg = e ? atoi(e) : 0; }
   const int tiles = ((B + SBM - 1) / SBM) * ((H + SBN - 1) / SBN);
   const int total_kb = (G + SBK - 1) / SBK;
   const int sms = sm_budget();
@@ -479,6 +484,7 @@ extern "C" int cmmvae_csr_linear_bwd_w_tc(const void* packed, const int32_t* til
   if (g_end <= 0 || g_end > G) g_end = G;
   CMMVAE_REQUIRE(g_begin >= 0 && g_begin < g_end && g_begin % SBM == 0 && (g_end == G || g_end % SBM == 0),
                  "csr_linear_bwd_w_tc: gene range [%d,%d) must be 128-aligned", g_begin, g_end);
+  { const char* e = getenv("CMMVAE_SPMM_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.bias = nullptr; p.out = dWt; p.splits = 1; p.sumsq = sumsq_out; p.m_begin = g_begin; p.m_end = g_end;
   CUtensorMap tm;
   if (int rc = make_tmap_bf16(&tm, dY_bf16, (uint64_t)H, (uint64_t)B, (uint64_t)H, 64, SBK)) return rc;
