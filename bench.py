@@ -201,6 +201,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-diag", action="store_true", help="extra legs that split the end-to-end time")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -353,6 +354,38 @@ def main():
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
         e2e_ms = float(tt.item())
     clocks = sampler.stop() if rank == 0 else None
+    diag = None
+    if args.e2e_diag:
+        # where does the end-to-end leg lose time?  (a) the same API calls on batches already in HBM (no H2D);
+        # (b) the H2D copies alone (no compute)
+        def api_resident(t):
+            s = names[t % len(names)]
+            crow, col, val = resident[s][t % NB]
+            model.training_step((torch.sparse_csr_tensor(crow, col, val, size=(B, species[s])), metas[t % NB], s), t)
+        for t in range(3):
+            api_resident(t)
+        barrier()
+        e0.record()
+        for t in range(args.steps):
+            api_resident(t)
+        model.flush_logs()
+        e1.record()
+        barrier()
+        a_ms = e0.elapsed_time(e1) / args.steps
+        barrier()
+        e0.record()
+        for t in range(args.steps):
+            _, tk = stage(t)
+            stager.arrays(tk)
+            stager.release(tk)
+        e1.record()
+        barrier()
+        c_ms = e0.elapsed_time(e1) / args.steps
+        tt = torch.tensor([a_ms, c_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+        diag = {"api_resident_ms_per_step": float(tt[0]), "h2d_only_ms_per_step": float(tt[1]),
+                "h2d_only_gbs_per_gpu": stager.bytes_staged / (float(tt[1]) * 1e-3) / 1e9}
     nnz = int(host[names[0]][0][1].size)
     h2d = int(stager.bytes_staged)
     d2h = int(eng.last["sc"].numel()) * 8
@@ -392,6 +425,8 @@ def main():
                  "fma_tflops": 2.0 * nnz * H1 / (t_spmm * 1e-3) / 1e12 if t_spmm > 0 else 0.0},
         "clocks": clocks,
     }
+    if diag:
+        line["e2e_diag"] = diag
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_leg(args.config, min(B, 1024), 2, 1)
     print(json.dumps(line))

@@ -26,6 +26,9 @@ namespace cmmvae {
 using namespace tc;
 
 constexpr int SBM = 128, SBN = 256, SBK = 64, SSTAGES = 4;
+#ifndef SP_E
+#define SP_E 8
+#endif
 constexpr int SNG = 4;             // producer groups (4 warps each); group g builds flat k-blocks f = g (mod SNG)
 constexpr int kSpThreads = 64 + 128 * SNG + 128;   // TMA + MMA + producer warps + 4 epilogue warps
 constexpr int kSpABytes = SBM * SBK * 2;   // 16 KB
@@ -130,6 +133,10 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc<2 * SBN>(tmem_slot);
+  // the A tiles start out all zero; the producers keep them that way between occupants (see below)
+  for (int i = threadIdx.x; i < SSTAGES * (kSpABytes / 16); i += kSpThreads)
+    st_shared_zero16(smem_u32(smem) + (i / (kSpABytes / 16)) * kSpStage + (i % (kSpABytes / 16)) * 16);
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -234,7 +241,7 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
       }
       o.win = w * 64;
     };
-    constexpr int E = 8;   // packed records prefetched into registers per (thread, window)
+    constexpr int E = SP_E;   // packed records prefetched into registers per (thread, window)
     auto load_entries = [&](const Ptr& q, uint32_t (&rec)[E]) {
       const int n = q.q1 - q.q0;
       const uint32_t* src = p.packed + q.q0;
@@ -261,7 +268,12 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
     seq_advance(fut_s, SNG);
     window_ptrs(fut_s, P1);
     load_entries(P0, E0);
-    const int bar_id = 1 + group;
+    static_assert(SNG == SSTAGES, "group g must own ring stage g (its threads keep the stage's un-scatter state)");
+    constexpr int EW = (SP_E + 3) / 4;   // entry byte offsets, four per register
+    uint32_t prev_off[EW];
+#pragma unroll
+    for (int i = 0; i < EW; ++i) prev_off[i] = 0;
+    int prev_n = 0, prev_a0 = 0, prev_aw = 0;
     const uint32_t smem_base = smem_u32(smem);
     auto body = [&](int f, const Ptr& cur, const Ptr& nxt, Ptr& fut, const uint32_t (&ec)[E], uint32_t (&en)[E]) {
       if (f >= total_f) return;
@@ -271,26 +283,37 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
       window_ptrs(fut_s, fut);
       if (!(p.dbg & 4)) load_entries(nxt, en);
       mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
-      const uint32_t tile = smem_base + stage * kSpStage;
-      // zero the 16 KB tile cooperatively (consecutive threads -> consecutive 16-byte chunks: conflict free)
-      if (!(p.dbg & 2)) {
+      const uint32_t line = smem_base + stage * kSpStage + line_off;
+      // The tile is all zeros except the entries this group scattered for the stage's previous occupant, and a
+      // thread only ever writes its own 128-byte line: take the previous entries back out (byte offsets kept
+      // packed in two registers), then put the new ones in.  No 16 KB re-zeroing, no barrier inside the group.
 #pragma unroll
-      for (int c = 0; c < 8; ++c) st_shared_zero16(tile + (c * 128 + t) * 16);
-      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      for (int u = 0; u < E; ++u)
+        st_shared_u16_if(line + ((prev_off[u >> 2] >> (8 * (u & 3))) & 0xFFu), 0u, u < prev_n);
+      for (int q = prev_a0 + E; q < prev_a0 + prev_n; ++q) {   // previous window had more than E entries
+        const int c = (int)(__ldg(p.packed + q) & 0xFFFFu) - prev_aw;
+        st_shared_u16_if(line + ((((c >> 3) ^ swz) << 4) | ((c & 7) << 1)), 0u, true);
       }
-      const uint32_t line = tile + line_off;
-      const int a0 = cur.q0, a1 = cur.q1, aw = cur.win;
-      const int n = (p.dbg & 1) ? 0 : a1 - a0;
+      const int a0 = cur.q0, aw = cur.win;
+      const int n = (p.dbg & 1) ? 0 : cur.q1 - cur.q0;
+      uint32_t offs[EW];
+#pragma unroll
+      for (int i = 0; i < EW; ++i) offs[i] = 0;
 #pragma unroll
       for (int u = 0; u < E; ++u) {
         const int c = (int)(ec[u] & 0xFFFFu) - aw;
-        st_shared_u16_if(line + ((((c >> 3) ^ swz) << 4) | ((c & 7) << 1)), ec[u] >> 16, u < n);
+        const uint32_t off = (uint32_t)((((c >> 3) ^ swz) << 4) | ((c & 7) << 1)) & 0x7Fu;
+        st_shared_u16_if(line + off, ec[u] >> 16, u < n);
+        offs[u >> 2] |= off << (8 * (u & 3));
       }
       for (int q = a0 + E; q < a0 + n; ++q) {   // windows with more than E entries (dense batches)
         const uint32_t r = __ldg(p.packed + q);
         const int c = (int)(r & 0xFFFFu) - aw;
         st_shared_u16_if(line + ((((c >> 3) ^ swz) << 4) | ((c & 7) << 1)), r >> 16, true);
       }
+#pragma unroll
+      for (int i = 0; i < EW; ++i) prev_off[i] = offs[i];
+      prev_n = n; prev_a0 = a0; prev_aw = aw;
       fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[stage]);

@@ -322,7 +322,7 @@ class StepEngine:
         if self.device.type != "cuda":
             raise RuntimeError("StepEngine needs a CUDA device (no CPU fallback)")
         self.precision = precision or L.get_precision()
-        self.dp_chunks = 2     # world > 1: pieces the first-layer weight gradient is exchanged in (overlap)
+        self.dp_chunks = int(os.environ.get("CMMVAE_DP_CHUNKS", "2"))     # world > 1: pieces the first-layer weight gradient is exchanged in (overlap)
         self.adv_weight = adv_weight
         self.clip = clip or {"vae": 10.0, "expert": 10.0, "adversarial": 10.0}
         vae = module.vae

@@ -2,6 +2,8 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
+import mmvae_b200._lib as _L
+if os.environ.get('CMMVAE_LIB_PATH'): _L.LIB_PATH = os.environ['CMMVAE_LIB_PATH']; _L.needs_build = lambda: False
 from mmvae_b200 import ops
 from oracle.cmmvae_oracle import synth_csr
 B, G, H = int(os.environ.get("PB", 1024)), 60530, 1024
@@ -30,4 +32,4 @@ def timeit(fn, n=20):
 r = {"fwd": timeit(lambda: ops.csr_linear_fwd_tc(packed, tp, B, G, Wt16, bias, out=Y)),
      "bwd": timeit(lambda: ops.csr_linear_bwd_w_tc(packed, tp, B, G, dY16, dWt)),
      "dec": timeit(lambda: ops.decoder_mse_fused(h16, Wout16, bout, G, crow, col, val, dl, ls, tile_ptr=tp))}
-print(os.environ.get("CMMVAE_SPMM_DBG", "0"), os.environ.get("CMMVAE_DEC_DBG", "0"), {k: round(v, 4) for k, v in r.items()})
+print(os.environ.get("CMMVAE_LIB_PATH", "default")[-12:], os.environ.get("CMMVAE_SPMM_DBG", "0"), os.environ.get("CMMVAE_DEC_DBG", "0"), {k: round(v, 4) for k, v in r.items()})
