@@ -239,7 +239,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         torch.set_num_threads(max(1, (os.cpu_count() or 8) // world))   # one launch thread per rank matters
-        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout clean: the only stdout line is the JSON result
+        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")   # keep stdout clean: the only stdout line is the JSON result
         torch.distributed.init_process_group("nccl", device_id=dev)
     from mmvae_b200 import layers as L, ops
     import pandas as pd

@@ -73,6 +73,14 @@ int cmmvae_csr_linear_fwd_tc(const void* packed, const int32_t* tile_ptr, int B,
 int cmmvae_csr_linear_bwd_w_tc(const void* packed, const int32_t* tile_ptr, int B, int G, int H,
                                const void* dY_bf16, float* dWt, int g_begin, int g_end, double* sumsq_out,
                                void* stream);
+/* Same product for ONE gene shard [g_begin, g_end) of a data-parallel job (DDP gradient mean of
+ * cmmvae_model.py:191-213, taken on the inputs instead of the outputs): `packed` / `dY_bf16` hold the cells of
+ * ALL ranks (B = global cells), `tile_ptr_shard` holds only the windows of the shard (first row = window
+ * g_begin/64, plus the closing row) and `dWt_shard` only the shard's rows (first row = gene g_begin).  The
+ * result is the shard of the SUMMED gradient; no reduce-scatter of dWt is needed. */
+int cmmvae_csr_linear_bwd_w_tc_shard(const void* packed, const int32_t* tile_ptr_shard, int B, int G, int H,
+                                     const void* dY_bf16, float* dWt_shard, int g_begin, int g_end,
+                                     double* sumsq_out, void* stream);
 
 /* ---- K2/K3: BatchNorm1d(momentum, eps) + ReLU + Dropout, components.py:279-288 ------------- */
 /* column statistics of Y[B,H]: mean[H], rstd[H] = 1/sqrt(biased var + eps); updates running

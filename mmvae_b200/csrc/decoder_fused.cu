@@ -20,7 +20,6 @@
 //                per window that one thread hands to a TMA bulk store (full-line writes, edges clipped by
 //                the tensor map) -- per-thread 32-byte global stores cost 0.05 ms of L1 wavefronts here.
 #include "tc.cuh"
-#include <stdlib.h>
 
 namespace cmmvae {
 
@@ -52,7 +51,6 @@ struct DecParams {
   int ldd;
   double* loss_sum;
   int num_m, num_n;
-  int dbg;
 };
 
 __global__ void __launch_bounds__(kDecThreads, 1)
@@ -184,7 +182,7 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
       const int b = m0 + row;
       const bool row_ok = b < p.B;
       const int g0 = n0 + w * 64;            // first gene of this thread's window
-      if (!(p.dbg & 4)) fetch(t + gridDim.x, np0, ncnt, necol, neval); else ncnt = 0;
+      fetch(t + gridDim.x, np0, ncnt, necol, neval);
 
       // the window's output tile (shared by the 4 warps of this window) must have been read by the previous
       // tile's TMA store before it is overwritten
@@ -194,7 +192,7 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
       tc_fence_after();
       float part = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < ((p.dbg & 2) ? 0 : 8); ++c) {          // eight 8-column sub-chunks of the window (one 16-byte bf16 chunk each)
+      for (int c = 0; c < 8; ++c) {          // eight 8-column sub-chunks of the window (one 16-byte bf16 chunk each)
         uint32_t r[8];
         tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * DBN + w * 64 + c * 8), r);
         const int gc = g0 + c * 8;
@@ -219,7 +217,6 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
         }
         // sparse part: patch the entries of this 8-gene sub-chunk
         const int lo = c * 8;
-        if (!(p.dbg & 1))
 #pragma unroll
         for (int u = 0; u < DE; ++u) {
           const int j = ecol[u] - lo;
@@ -303,7 +300,6 @@ extern "C" int cmmvae_decoder_mse_fused(const void* h, int ldh, const void* Wout
   p.B = B; p.G = G; p.H = H; p.bout = bout; p.col = col; p.val = val;
   p.ntp = (G + 63) / 64 + 1;
   p.dl = (__nv_bfloat16*)dlogits_bf16; p.ldd = ldd; p.loss_sum = loss_sum;
-  { const char* e = getenv("CMMVAE_DEC_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.num_m = (B + DBM - 1) / DBM;
   p.num_n = (G + DBN - 1) / DBN;
   CUtensorMap tmH, tmW, tmD;

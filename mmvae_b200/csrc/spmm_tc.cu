@@ -19,7 +19,6 @@
 //                 128B-swizzled layout, fence.proxy.async, arrive on the stage's full barrier
 //   warps 16..19  epilogue: drain accumulator i while tile i+1 is being multiplied
 #include "tc.cuh"
-#include <stdlib.h>
 
 namespace cmmvae {
 
@@ -47,7 +46,7 @@ struct SpParams {
   float* out;          // forward: Y[B,H]; backward: dWt[G,H]
   int splits;          // forward split-K over genes
   double* sumsq;       // backward only, optional: += sum of squares of dWt (fused gradient norm)
-  int dbg;
+  int win0, row0;      // backward only: window index of tp's first row / gene index of out's first row (shard views)
   int m_begin, m_end;  // backward only: gene range [m_begin, m_end) computed by this launch (m_begin % 128 == 0)
 };
 
@@ -236,8 +235,9 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
       int b, w;
       if (!BWD) { b = s.m0 + t; w = kbg; } else { b = kbg * 64 + (t & 63); w = (s.m0 >> 6) + (t >> 6); }
       if (b < p.B && w < p.ntp - 1) {
-        o.q0 = __ldg(p.tp + (size_t)w * p.B + b);
-        o.q1 = __ldg(p.tp + (size_t)(w + 1) * p.B + b);
+        const int wl = BWD ? w - p.win0 : w;
+        o.q0 = __ldg(p.tp + (size_t)wl * p.B + b);
+        o.q1 = __ldg(p.tp + (size_t)(wl + 1) * p.B + b);
       }
       o.win = w * 64;
     };
@@ -281,7 +281,7 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
       const uint32_t phase = (f / SSTAGES) & 1;
       seq_advance(fut_s, SNG);
       window_ptrs(fut_s, fut);
-      if (!(p.dbg & 4)) load_entries(nxt, en);
+      load_entries(nxt, en);
       mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
       const uint32_t line = smem_base + stage * kSpStage + line_off;
       // The tile is all zeros except the entries this group scattered for the stage's previous occupant, and a
@@ -295,7 +295,7 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
         st_shared_u16_if(line + ((((c >> 3) ^ swz) << 4) | ((c & 7) << 1)), 0u, true);
       }
       const int a0 = cur.q0, aw = cur.win;
-      const int n = (p.dbg & 1) ? 0 : cur.q1 - cur.q0;
+      const int n = cur.q1 - cur.q0;
       uint32_t offs[EW];
 #pragma unroll
       for (int i = 0; i < EW; ++i) offs[i] = 0;
@@ -366,7 +366,7 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
           fence_proxy_async();
           named_bar_sync(15, 128);
           if (et == 0) {
-            tma_store_2d(&tmC, obuf, gn0, m0);
+            tma_store_2d(&tmC, obuf, gn0, m0 - p.row0);
             tma_store_commit();
           }
           ++chunk_no;
@@ -480,8 +480,7 @@ extern "C" int cmmvae_csr_linear_fwd_tc(const void* packed, const int32_t* tile_
   cudaStream_t st = (cudaStream_t)stream;
   SpParams p;
   p.B = B; p.G = G; p.H = H; p.packed = (const uint32_t*)packed; p.tp = tile_ptr; p.ntp = (G + 63) / 64 + 1;
-  p.bias = bias; p.out = Y; p.sumsq = nullptr; p.m_begin = 0; p.m_end = B;
-  { const char* e = getenv("CMMVAE_SPMM_DBG"); p.dbg = e ? atoi(e) : 0; }
+  p.bias = bias; p.out = Y; p.sumsq = nullptr; p.m_begin = 0; p.m_end = B; p.win0 = 0; p.row0 = 0;
   const int tiles = ((B + SBM - 1) / SBM) * ((H + SBN - 1) / SBN);
   const int total_kb = (G + SBK - 1) / SBK;
   const int sms = sm_budget();
@@ -497,9 +496,8 @@ extern "C" int cmmvae_csr_linear_fwd_tc(const void* packed, const int32_t* tile_
   return launch_spmm_tc<false>(tm, tm, p, grid, st);
 }
 
-extern "C" int cmmvae_csr_linear_bwd_w_tc(const void* packed, const int32_t* tile_ptr, int B, int G, int H,
-                                          const void* dY_bf16, float* dWt, int g_begin, int g_end,
-                                          double* sumsq_out, void* stream) {
+static int spmm_bwd_w(const void* packed, const int32_t* tile_ptr, int B, int G, int H, const void* dY_bf16,
+                      float* dWt, int g_begin, int g_end, bool shard_view, double* sumsq_out, void* stream) {
   CMMVAE_REQUIRE(B > 0 && G > 0 && H > 0 && H % 8 == 0, "csr_linear_bwd_w_tc: bad shape (H must be a multiple of 8)");
   CMMVAE_REQUIRE(((uintptr_t)dY_bf16 & 15) == 0 && ((uintptr_t)dWt & 15) == 0, "csr_linear_bwd_w_tc: alignment");
   SpParams p;
@@ -507,13 +505,26 @@ extern "C" int cmmvae_csr_linear_bwd_w_tc(const void* packed, const int32_t* til
   if (g_end <= 0 || g_end > G) g_end = G;
   CMMVAE_REQUIRE(g_begin >= 0 && g_begin < g_end && g_begin % SBM == 0 && (g_end == G || g_end % SBM == 0),
                  "csr_linear_bwd_w_tc: gene range [%d,%d) must be 128-aligned", g_begin, g_end);
-  { const char* e = getenv("CMMVAE_SPMM_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.bias = nullptr; p.out = dWt; p.splits = 1; p.sumsq = sumsq_out; p.m_begin = g_begin; p.m_end = g_end;
+  p.win0 = shard_view ? g_begin / 64 : 0;
+  p.row0 = shard_view ? g_begin : 0;
   CUtensorMap tm;
   if (int rc = make_tmap_bf16(&tm, dY_bf16, (uint64_t)H, (uint64_t)B, (uint64_t)H, 64, SBK)) return rc;
   const int units = ((H + SBN - 1) / SBN) * ((g_end - g_begin + SBM - 1) / SBM);
   dim3 grid(units < sm_budget() ? units : sm_budget());
   CUtensorMap tmC;
-  if (int rc = make_tmap_f32(&tmC, dWt, (uint64_t)H, (uint64_t)G, (uint64_t)H, 32, SBM)) return rc;
+  if (int rc = make_tmap_f32(&tmC, dWt, (uint64_t)H, (uint64_t)(g_end - p.row0), (uint64_t)H, 32, SBM)) return rc;
   return launch_spmm_tc<true>(tm, tmC, p, grid, (cudaStream_t)stream);
+}
+
+extern "C" int cmmvae_csr_linear_bwd_w_tc(const void* packed, const int32_t* tile_ptr, int B, int G, int H,
+                                          const void* dY_bf16, float* dWt, int g_begin, int g_end,
+                                          double* sumsq_out, void* stream) {
+  return spmm_bwd_w(packed, tile_ptr, B, G, H, dY_bf16, dWt, g_begin, g_end, false, sumsq_out, stream);
+}
+
+extern "C" int cmmvae_csr_linear_bwd_w_tc_shard(const void* packed, const int32_t* tile_ptr_shard, int B, int G,
+                                                int H, const void* dY_bf16, float* dWt_shard, int g_begin,
+                                                int g_end, double* sumsq_out, void* stream) {
+  return spmm_bwd_w(packed, tile_ptr_shard, B, G, H, dY_bf16, dWt_shard, g_begin, g_end, true, sumsq_out, stream);
 }

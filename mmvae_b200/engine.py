@@ -50,7 +50,7 @@ class FlatGroup:
 
     def __init__(self, name: str, chains: List[List[tuple]], device, lr=5e-3, weight_decay=1e-6,
                  betas=(0.9, 0.999), eps=1e-8, segments: Optional[List[List[List[tuple]]]] = None,
-                 split_first: int = 1):
+                 split_first: int = 1, row_shard_first: bool = False):
         """``chains`` (tail) / ``segments[i]`` (sharded when world > 1): lists of chains; a chain is a list
         of ``(param, transposed)`` stored back to back (e.g. mean/var head weights = one matrix)."""
         self.name, self.lr, self.wd, self.betas, self.eps = name, lr, weight_decay, betas, eps
@@ -74,10 +74,25 @@ class FlatGroup:
                     total += p.numel()
 
         self.first_rows: List[tuple] = []      # row ranges of the first parameter covered by segments 0..k-1
+        # row_shard_first (world > 1): segment 0 holds ONE row-major matrix and is padded to world * Rs rows
+        # (Rs a multiple of 128) so that rank r's ZeRO shard is exactly rows [r*Rs, (r+1)*Rs): the rank can then
+        # COMPUTE its shard of the summed gradient from all-gathered inputs instead of reduce-scattering it
+        self.row_shard: Optional[tuple] = None   # (rows per rank, width, padded rows)
         for si, seg in enumerate(segments):
             total = _ceil(total, seg_align)
             lo = total
             place(seg)
+            if si == 0 and row_shard_first and self.world > 1:
+                assert len(seg) == 1 and len(seg[0]) == 1, "row-sharded segment = one matrix"
+                p0, tr0 = seg[0][0]
+                rows, width = (p0.shape[1], p0.shape[0]) if tr0 else (p0.shape[0], p0.shape[1])
+                per = _ceil((rows + self.world - 1) // self.world, 128)
+                assert (per * width) % 256 == 0
+                total = lo + self.world * per * width
+                self.row_shard = (per, width, self.world * per)
+                self.seg_bounds.append((lo, total))
+                self.first_rows = [(0, 0)]
+                continue
             total = _ceil(total, seg_align)
             if si == 0 and split_first > 1 and self.world > 1:
                 # cut segment 0 inside its first (big, row-major) parameter at 128-row boundaries so that
@@ -124,6 +139,7 @@ class FlatGroup:
         self.m = torch.zeros(mv, device=device, dtype=torch.float32)
         self.v = torch.zeros(mv, device=device, dtype=torch.float32)
         self.step_count = 0
+        self.first_by_inputs = False   # set per step by the engine when gs[0] was produced from gathered inputs
         self._ag_pending: List = []
         for p in self.params:
             phys = self.phys(p)
@@ -152,6 +168,8 @@ class FlatGroup:
         """reduce-scatter (SUM) of segment i's gradient into this rank's shard buffer"""
         if not self.sharded:
             return None
+        if i == 0 and self.first_by_inputs:
+            return None    # the shard of the summed gradient was computed in place (StepEngine._first_layer_grad_shard)
         lo, hi = self.seg_bounds[i]
         return torch.distributed.reduce_scatter_tensor(self.gs[i], self.g[lo:hi], async_op=True)
 
@@ -322,6 +340,10 @@ class StepEngine:
         if self.device.type != "cuda":
             raise RuntimeError("StepEngine needs a CUDA device (no CPU fallback)")
         self.precision = precision or L.get_precision()
+        # world > 1: the first-layer weight gradient shard is computed from all-gathered inputs (packed CSR, window
+        # pointers, dY) instead of reduce-scattering 4*G*H1 bytes of output; CMMVAE_DP_BY_INPUTS=0 -> reduce-scatter
+        self.dp_by_inputs = os.environ.get("CMMVAE_DP_BY_INPUTS", "1") != "0" and self.precision == "bf16"
+        self._dp_cap = None
         self.dp_chunks = int(os.environ.get("CMMVAE_DP_CHUNKS", "2"))     # world > 1: pieces the first-layer weight gradient is exchanged in (overlap)
         self.adv_weight = adv_weight
         self.clip = clip or {"vae": 10.0, "expert": 10.0, "adversarial": 10.0}
@@ -343,8 +365,15 @@ class StepEngine:
             mats = _block_chains(expert.encoder, sparse_first=True, kind="matrix") + \
                 _block_chains(expert.decoder, kind="matrix")
             vecs = _block_chains(expert.encoder, kind="vector") + _block_chains(expert.decoder, kind="vector")
-            g = self.groups[f"experts/{eid}"] = FlatGroup(f"experts/{eid}", vecs, dev, segments=[mats[:-1], mats[-1:]],
-                                                          split_first=self.dp_chunks)
+            if dp.world_size() > 1 and self.dp_by_inputs:
+                # first-layer weight alone in segment 0 with row-aligned shards (its gradient shard is computed
+                # from all-gathered inputs); the two small matrices join the replicated tail
+                g = FlatGroup(f"experts/{eid}", vecs + mats[1:-1], dev, segments=[mats[:1], mats[-1:]],
+                              row_shard_first=True)
+            else:
+                g = FlatGroup(f"experts/{eid}", vecs, dev, segments=[mats[:-1], mats[-1:]],
+                              split_first=self.dp_chunks)
+            self.groups[f"experts/{eid}"] = g
             self.enc_plan[eid] = _plan_block(expert.encoder, g, sparse_first=True)
             self.dec_plan[eid] = _plan_block(expert.decoder, g)
             last = self.dec_plan[eid][-1]
@@ -526,7 +555,10 @@ class StepEngine:
             ops.colsum(dY, lp.gb)
         if lp.sparse:
             if csc[0] == "tc":
-                _, tp, G, ssq, pending = csc
+                _, tp, G, ssq, pending, gathered = csc
+                if gathered is not None:
+                    self._first_layer_grad_shard(lp.group, gathered, dY16, B)
+                    return None
                 pieces = lp.group.first_rows if (lp.group.sharded and lp.group.n_first > 1) else [(0, G)]
                 for i, (g0, g1) in enumerate(pieces):
                     ops.csr_linear_bwd_w_tc(tp[1], tp[0], B, G, dY16, lp.gW, sumsq_out=ssq, g_begin=g0, g_end=g1)
@@ -605,6 +637,55 @@ class StepEngine:
         self._join_side()
         return d
 
+    # ------------------------------------------------------------- data parallel: first layer by inputs
+    def _dp_capacity(self, n_packed: int, B: int) -> int:
+        """records per rank in the all-gathered packed CSR (identical on every rank; agreed once, with headroom)"""
+        if self._dp_cap is None:
+            t = torch.tensor([n_packed, B, -B], dtype=torch.int64, device=self.device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            mx, bmax, bmin = (int(v) for v in t.tolist())
+            if bmax != -bmin:
+                raise RuntimeError("data-parallel step needs the same number of cells on every rank")
+            self._dp_cap = _ceil(int(mx * 1.15) + 1024, 1024)
+        if n_packed > self._dp_cap:
+            raise RuntimeError(f"batch with {n_packed} non-zero records exceeds the data-parallel CSR capacity "
+                               f"{self._dp_cap} agreed on the first step; set engine._dp_cap (same value on every "
+                               "rank) before training on batches of very different density")
+        return self._dp_cap
+
+    def _dp_gather_csr(self, gexp: FlatGroup, tp, B: int, cap: int):
+        """start the exchange that lets every rank compute ITS gene shard of the summed first-layer weight
+        gradient: all-gather of the packed CSR records (4 B per non-zero) and all-to-all of the window pointers
+        (rank r receives, from every rank, the pointer rows of r's windows, rebased into the gathered array).
+        Runs on the NCCL stream under the forward pass; consumed by ``_first_layer_grad_shard``."""
+        per, width, _ = gexp.row_shard
+        world, rank, WS = self.world, dp.rank(), gexp.row_shard[0] // 64
+        table, packed = tp
+        packed_all = self.ws("dp.packed_all", (world * cap,), torch.int32)
+        w_pk = torch.distributed.all_gather_into_tensor(packed_all, packed[:cap], async_op=True)
+        tp2d = table.view(-1, B)                                # [world * WS + 1, B]
+        send = self.ws("dp.tp_send", (world, WS + 1, B), torch.int32)
+        send[:, :WS].copy_(tp2d[:world * WS].view(world, WS, B))
+        send[:, WS].copy_(tp2d[WS::WS][:world])                 # closing row of every shard
+        send += rank * cap
+        recv = self.ws("dp.tp_recv", (world, WS + 1, B), torch.int32)
+        w_tp = torch.distributed.all_to_all_single(recv.view(-1), send.view(-1), async_op=True)
+        return dict(packed_all=packed_all, recv=recv, waits=[w_pk, w_tp], WS=WS)
+
+    def _first_layer_grad_shard(self, gexp: FlatGroup, gathered, dY16, B: int):
+        """dW1^T[shard] = X_all^T[shard] . dY_all  -- the shard of the SUM over ranks, written straight into the
+        ZeRO gradient shard (no 4*G*H1-byte reduce-scatter; only dY, 2*B*H1 bytes per rank, is exchanged here)"""
+        per, width, rows_pad = gexp.row_shard
+        world, rank, WS = self.world, dp.rank(), gathered["WS"]
+        for w in gathered["waits"]:
+            w.wait()
+        tp_shard = self.ws("dp.tp_shard", (WS + 1, world * B), torch.int32)
+        tp_shard.view(WS + 1, world, B).copy_(gathered["recv"].permute(1, 0, 2))
+        dY_all = self.ws("dp.dY_all", (world * B, width), torch.bfloat16)
+        torch.distributed.all_gather_into_tensor(dY_all, dY16)
+        ops.csr_linear_bwd_w_tc_shard(gathered["packed_all"], tp_shard, world * B, rows_pad, dY_all,
+                                      gexp.gs[0].view(per, width), rank * per, (rank + 1) * per)
+
     # ----------------------------------------------------------------------------------------- step
     def train_step(self, expert_id: str, crow, col, val, nnz: int, kl_weight: float, eps=None,
                    labels: Optional[Dict[str, torch.Tensor]] = None, masks=None):
@@ -637,19 +718,32 @@ class StepEngine:
 
         # ---------------- forward ----------------
         gexp, gvae = self.groups[f"experts/{expert_id}"], self.groups["vae"]
-        ev = self._t0("dp_wait_shadow_first")
-        gexp.wait_shadow("first")   # bf16 shards published by the previous step's optimizer (world > 1)
-        self._t1(ev)
         caches = {}
         x32 = x16 = None
         # tensor-pipe SpMM (tile densified in smem) above the density where it beats the gather kernel
-        use_tc_spmm = (bf and self.spmm_tc and enc[0].N % 8 == 0 and G <= 65536 and
-                       nnz >= self.spmm_tc_min_density * B * G)
+        tc_ok = bf and self.spmm_tc and enc[0].N % 8 == 0 and G <= 65536
+        # data parallel: every rank must take the same route (it decides which collectives run), so the
+        # density test is dropped there
+        by_inputs = tc_ok and self.world > 1 and gexp.row_shard is not None
+        use_tc_spmm = tc_ok and (by_inputs or nnz >= self.spmm_tc_min_density * B * G)
+        gexp.first_by_inputs = by_inputs
+        G_tp = gexp.row_shard[2] if by_inputs else G     # window table padded to world * rows-per-rank genes
         tp = None
+        gathered = None
         ev = self._t0("csr_prep")
         if use_tc_spmm:
-            tp = ops.csr_tile_ptr(crow, col, val, G, nnz, self.ws("tp64", (B * ((G + 63) // 64 + 1),), torch.int32),
-                                  self.ws("packed", ((nnz + 3) // 4 * 4 + 4,), torch.int32))
+            n_packed = (nnz + 3) // 4 * 4 + 4
+            if by_inputs:
+                n_packed = self._dp_capacity(n_packed, B)
+            tp = ops.csr_tile_ptr(crow, col, val, G_tp, nnz,
+                                  self.ws("tp64", (B * ((G_tp + 63) // 64 + 1),), torch.int32),
+                                  self.ws("packed", (n_packed,), torch.int32))
+            if by_inputs:
+                gathered = self._dp_gather_csr(gexp, tp, B, n_packed)
+        self._t1(ev)
+        # index preparation needs no weights: it runs while the previous step's shadow all-gather finishes
+        ev = self._t0("dp_wait_shadow_first")
+        gexp.wait_shadow("first")   # bf16 shards published by the previous step's optimizer (world > 1)
         self._t1(ev)
         ev_mid = None
         for j, lp in enumerate(enc):
@@ -783,7 +877,7 @@ class StepEngine:
                     ops.axpy(d, d_hidden[i], -1.0)
             d = self._layer_bwd(f"venc{j}", self.vaeenc_plan[j], caches[("venc", j)], d, B)
         if use_tc_spmm:
-            csc = ("tc", tp, G, s_norm(1) if fuse_norm else None, pending)
+            csc = ("tc", tp, G, s_norm(1) if fuse_norm else None, pending, gathered)
         else:
             cptr, ridx, cval = ops.csr_transpose(crow, col, val, G, nnz, self.ws("cptr", (G + 1,), torch.int32),
                                                  self.ws("ridx", (max(nnz, 1),), torch.int32),

@@ -153,6 +153,19 @@ def csr_linear_bwd_w_tc(packed, tile_ptr, B: int, G: int, dY16, out, sumsq_out=N
     return out
 
 
+def csr_linear_bwd_w_tc_shard(packed_all, tp_shard, B_all: int, G_pad: int, dY16_all, out_shard, g_begin: int,
+                              g_end: int, sumsq_out=None):
+    """gene shard [g_begin, g_end) of X_all^T . dY_all (all ranks' cells); ``tp_shard``/``out_shard`` hold only
+    the shard's windows / rows"""
+    H = dY16_all.shape[1]
+    assert dY16_all.dtype == torch.bfloat16 and dY16_all.is_contiguous() and out_shard.is_contiguous()
+    assert out_shard.shape == (g_end - g_begin, H) and tp_shard.numel() >= ((g_end - g_begin) // 64 + 1) * B_all
+    _check(lib().cmmvae_csr_linear_bwd_w_tc_shard(_ptr(packed_all), _ptr(tp_shard), B_all, G_pad, H, _ptr(dY16_all),
+                                                  _ptr(out_shard), int(g_begin), int(g_end), _ptr(sumsq_out),
+                                                  _stream()), "csr_linear_bwd_w_tc_shard")
+    return out_shard
+
+
 def mse_relu_csr(logits, G: int, crow, col, val, write_xhat: bool, dl32, dl16, loss_sum):
     B = logits.shape[0]
     ldd = (dl32 if dl32 is not None else dl16).stride(0) if (dl32 is not None or dl16 is not None) else 0
