@@ -170,6 +170,11 @@ int cmmvae_sumsq(const float* g, long long n, double* norm_sq, void* stream);
 int cmmvae_clip_adam(float* p, const float* g, float* m, float* v, void* p_bf16, long long n,
                      const double* norm_sq, float max_norm, float grad_scale, float lr, float beta1, float beta2,
                      float eps, float wd, float bc1, float bc2, void* stream);
+/* Same update launched as many short-lived 128-thread CTAs: meant for a low-priority stream that runs the
+ * output-layer update underneath the next step's forward pass (engine.pipeline_optimizer). */
+int cmmvae_clip_adam_bg(float* p, const float* g, float* m, float* v, void* p_bf16, long long n,
+                        const double* norm_sq, float max_norm, float grad_scale, float lr, float beta1, float beta2,
+                        float eps, float wd, float bc1, float bc2, void* stream);
 
 /* ---- small utilities ------------------------------------------------------------------------ */
 int cmmvae_cast_f32_bf16(const float* src, void* dst, long long n, void* stream);

@@ -480,6 +480,58 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, c
   }
 }
 
+// Background variant: many short-lived 128-thread CTAs (1024 elements each) instead of one resident wave, so
+// that kernels of a higher-priority stream get SM slots within microseconds and a CTA (64 registers x 128
+// threads) still fits next to a resident tensor-pipe CTA.  Same arithmetic per element as clip_adam_kernel.
+__global__ void __launch_bounds__(128) clip_adam_bg_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                           float* __restrict__ m, float* __restrict__ v,
+                                                           __nv_bfloat16* __restrict__ p16, long long n,
+                                                           const double* __restrict__ norm_sq, float max_norm,
+                                                           float grad_scale, float lr, float b1, float b2,
+                                                           float eps, float wd, float bc1, float bc2) {
+  pdl_sync();
+  float coef = 1.f;
+  if (max_norm > 0.f && norm_sq) {
+    const float total = (float)sqrt(*norm_sq) * fabsf(grad_scale);
+    coef = fminf(1.f, max_norm / (total + 1e-6f));
+  }
+  const float gs = coef * grad_scale;
+  const float isb2 = 1.f / sqrtf(bc2);
+  const long long n4 = n / 4;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x, j = i + 128;
+  const bool one = i < n4, two = j < n4;
+  float4 pa, ma, va, ga, pb, mb, vb, gb;
+  if (one) { pa = p4[i]; ma = m4[i]; va = v4[i]; ga = __ldcs(g4 + i); }
+  if (two) { pb = p4[j]; mb = m4[j]; vb = v4[j]; gb = __ldcs(g4 + j); }
+  if (one) {
+    adam_one(pa.x, ga.x, ma.x, va.x, gs, lr, b1, b2, eps, wd, bc1, isb2);
+    adam_one(pa.y, ga.y, ma.y, va.y, gs, lr, b1, b2, eps, wd, bc1, isb2);
+    adam_one(pa.z, ga.z, ma.z, va.z, gs, lr, b1, b2, eps, wd, bc1, isb2);
+    adam_one(pa.w, ga.w, ma.w, va.w, gs, lr, b1, b2, eps, wd, bc1, isb2);
+    p4[i] = pa; m4[i] = ma; v4[i] = va;
+    if (p16) *reinterpret_cast<uint2*>(p16 + i * 4) = make_uint2(pack_bf16(pa.x, pa.y), pack_bf16(pa.z, pa.w));
+  }
+  if (two) {
+    adam_one(pb.x, gb.x, mb.x, vb.x, gs, lr, b1, b2, eps, wd, bc1, isb2);
+    adam_one(pb.y, gb.y, mb.y, vb.y, gs, lr, b1, b2, eps, wd, bc1, isb2);
+    adam_one(pb.z, gb.z, mb.z, vb.z, gs, lr, b1, b2, eps, wd, bc1, isb2);
+    adam_one(pb.w, gb.w, mb.w, vb.w, gs, lr, b1, b2, eps, wd, bc1, isb2);
+    p4[j] = pb; m4[j] = mb; v4[j] = vb;
+    if (p16) *reinterpret_cast<uint2*>(p16 + j * 4) = make_uint2(pack_bf16(pb.x, pb.y), pack_bf16(pb.z, pb.w));
+  }
+  if (blockIdx.x == 0)   // scalar tail (n not a multiple of 4)
+    for (long long k = n4 * 4 + threadIdx.x; k < n; k += 128) {
+      float pp = p[k], mm = m[k], vv = v[k];
+      adam_one(pp, g[k], mm, vv, gs, lr, b1, b2, eps, wd, bc1, isb2);
+      p[k] = pp; m[k] = mm; v[k] = vv;
+      if (p16) p16[k] = __float2bfloat16(pp);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // utilities
 // ---------------------------------------------------------------------------------------------
@@ -664,6 +716,20 @@ extern "C" int cmmvae_clip_adam(float* p, const float* g, float* m, float* v, vo
                                                              max_norm, grad_scale, lr, beta1, beta2, eps, wd, bc1,
                                                              bc2);
   return check_launch("clip_adam");
+}
+
+extern "C" int cmmvae_clip_adam_bg(float* p, const float* g, float* m, float* v, void* p_bf16, long long n,
+                                   const double* norm_sq, float max_norm, float grad_scale, float lr, float beta1,
+                                   float beta2, float eps, float wd, float bc1, float bc2, void* stream) {
+  CMMVAE_REQUIRE(n >= 0 && n / 1024 < 2147483647LL, "clip_adam_bg: bad n");
+  CMMVAE_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0,
+                 "clip_adam_bg: buffers must be 16-byte aligned");
+  CMMVAE_REQUIRE(!p_bf16 || ((uintptr_t)p_bf16 & 7) == 0, "clip_adam_bg: bf16 shadow must be 8-byte aligned");
+  if (n == 0) return 0;
+  const long long blocks = (n / 4 + 255) / 256 + 1;
+  launch_pdl(clip_adam_bg_kernel, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)stream, p, g, m, v,
+             (__nv_bfloat16*)p_bf16, n, norm_sq, max_norm, grad_scale, lr, beta1, beta2, eps, wd, bc1, bc2);
+  return check_launch("clip_adam_bg");
 }
 
 extern "C" int cmmvae_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {

@@ -139,6 +139,7 @@ class FlatGroup:
         self.m = torch.zeros(mv, device=device, dtype=torch.float32)
         self.v = torch.zeros(mv, device=device, dtype=torch.float32)
         self.step_count = 0
+        self._deferred: Optional[torch.cuda.Event] = None   # output-layer update in flight on the background stream
         self.first_by_inputs = False   # set per step by the engine when gs[0] was produced from gathered inputs
         self._ag_pending: List = []
         for p in self.params:
@@ -200,14 +201,33 @@ class FlatGroup:
         else:
             ops.sumsq(self.g, out)
 
-    def clip_adam(self, norm_sq: torch.Tensor, max_norm: Optional[float], grad_scale: float = 1.0):
+    def clip_adam(self, norm_sq: torch.Tensor, max_norm: Optional[float], grad_scale: float = 1.0,
+                  background: Optional[torch.cuda.Stream] = None):
+        """fused clip + Adam over the group.  ``background`` (single process only): the LAST segment (the output
+        layer, which the next forward pass reads last) is updated on that low-priority stream, after everything
+        else, so the update runs underneath the next step's forward; ``wait_shadow("rest")`` joins it."""
         self.step_count += 1
         self._ag_pending = []
+        hyper = (self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.step_count)
+        if background is not None and not self.sharded and len(self.seg_bounds) >= 2:
+            lo1, hi1 = self.seg_bounds[-1]
+            for lo, hi in ((0, lo1), (hi1, self.n)):
+                if hi > lo:
+                    ops.clip_adam(self.p[lo:hi], self.g[lo:hi], self.m[lo:hi], self.v[lo:hi], self.p16[lo:hi],
+                                  norm_sq, max_norm or 0.0, grad_scale, *hyper)
+            first_done = torch.cuda.Event()
+            first_done.record()
+            with torch.cuda.stream(background), ops.stream_scope(background):
+                background.wait_event(first_done)
+                ops.clip_adam(self.p[lo1:hi1], self.g[lo1:hi1], self.m[lo1:hi1], self.v[lo1:hi1], self.p16[lo1:hi1],
+                              norm_sq, max_norm or 0.0, grad_scale, *hyper, background=True)
+                self._deferred = torch.cuda.Event()
+                self._deferred.record(background)
+            return
         for i, (lo, hi, g, mv) in enumerate(self.ranges):
             n = hi - lo
             ops.clip_adam(self.p[lo:hi], g, self.m[mv:mv + n], self.v[mv:mv + n], self.p16[lo:hi], norm_sq,
-                          max_norm or 0.0, grad_scale, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
-                          self.step_count)
+                          max_norm or 0.0, grad_scale, *hyper)
             if self.sharded and i < len(self.seg_bounds):
                 # publish the refreshed bf16 shard right away (segment 0 = first-layer weight is needed first by
                 # the next forward); consumers wait just before they read it
@@ -217,16 +237,21 @@ class FlatGroup:
 
     def wait_shadow(self, which: Optional[str] = None):
         """make the current stream wait for the all-gather of bf16 shadows: "first" = the pieces of the original
-        segment 0 (first-layer weight), "rest" = the other segments, None = all"""
+        segment 0 (first-layer weight), "rest" = the other segments, None = all; "rest"/None also join an
+        output-layer update still running on the background stream"""
         for j, w in enumerate(self._ag_pending):
             hit = which is None or (which == "first") == (j < self.n_first)
             if w is not None and hit:
                 w.wait()
                 self._ag_pending[j] = None
+        if which != "first" and self._deferred is not None:
+            torch.cuda.current_stream().wait_event(self._deferred)
+            self._deferred = None
 
     def sync_master(self):
         """all-gather the fp32 master copy of the sharded segments (before state_dict / fp32 evaluation)"""
         if not self.sharded:
+            self.wait_shadow()
             return
         self.wait_shadow()
         for (lo, hi), (own_lo, own_hi, _, _) in zip(self.seg_bounds, self.ranges):
@@ -344,6 +369,13 @@ class StepEngine:
         # pointers, dY) instead of reduce-scattering 4*G*H1 bytes of output; CMMVAE_DP_BY_INPUTS=0 -> reduce-scatter
         self.dp_by_inputs = os.environ.get("CMMVAE_DP_BY_INPUTS", "1") != "0" and self.precision == "bf16"
         self._dp_cap = None
+        # single process: run the step on a high-priority stream and the output layer's clip+Adam on a
+        # low-priority one, underneath the next step's forward pass (37 % of a B=1024 step is optimizer HBM
+        # traffic, half of it the output layer whose new value is only needed by the decoder kernel).  Weights
+        # read outside the engine need ``finish()`` first, hence opt-in (training_step turns it on in its
+        # pipelined mode, sync_logging=False)
+        self.pipeline_optimizer = False
+        self._hp = self._bg = None
         self.dp_chunks = int(os.environ.get("CMMVAE_DP_CHUNKS", "2"))     # world > 1: pieces the first-layer weight gradient is exchanged in (overlap)
         self.adv_weight = adv_weight
         self.clip = clip or {"vae": 10.0, "expert": 10.0, "adversarial": 10.0}
@@ -691,8 +723,25 @@ class StepEngine:
                    labels: Optional[Dict[str, torch.Tensor]] = None, masks=None):
         """One optimisation step on a CSR batch already resident on the device (no host sync).
         Returns the step record (device scalar block etc.) for ``scalars()``."""
+        if self.pipeline_optimizer and dp.world_size() == 1:
+            if self._hp is None:
+                lo_pri, hi_pri = torch.cuda.Stream.priority_range()
+                self._hp = torch.cuda.Stream(self.device, priority=hi_pri)
+                self._bg = torch.cuda.Stream(self.device, priority=lo_pri)
+            cur = torch.cuda.current_stream()
+            self._hp.wait_stream(cur)
+            with torch.cuda.stream(self._hp), ops.stream_scope(self._hp):
+                rec = self._train_step(expert_id, crow, col, val, nnz, kl_weight, eps, labels, masks)
+            cur.wait_stream(self._hp)
+            return rec
         with ops.stream_scope(torch.cuda.current_stream()):
             return self._train_step(expert_id, crow, col, val, nnz, kl_weight, eps, labels, masks)
+
+    def finish(self):
+        """join optimizer work still in flight on the background stream (call before reading weights outside
+        the engine when ``pipeline_optimizer`` is on; ``state_dict``/evaluation do it themselves)"""
+        for g in self.groups.values():
+            g.wait_shadow()
 
     def _train_step(self, expert_id, crow, col, val, nnz, kl_weight, eps, labels, masks):
         dev = self.device
@@ -910,7 +959,8 @@ class StepEngine:
         gvae.grad_norm_sq(s_norm(0))
         gexp.grad_norm_sq(s_norm(1), skip=[enc[0].lin.weight, out.lin.weight] if fuse_norm else None)
         gvae.clip_adam(s_norm(0), self.clip.get("vae"), gscale)
-        gexp.clip_adam(s_norm(1), self.clip.get("expert"), gscale)
+        gexp.clip_adam(s_norm(1), self.clip.get("expert"), gscale,
+                       background=self._bg if (self.pipeline_optimizer and self.world == 1) else None)
         self._t1(ev)
 
         self.last = dict(sc=sc, B=B, Z=Z, kl_weight=float(kl_weight), expert_id=expert_id, n_adv=n_adv,

@@ -208,6 +208,7 @@ class CMMVAEModel(BaseModel):
             return self._training_step_module_route(batch)
         crow, col, val, nnz = self._csr(x)
         labels = self._labels(metadata, x.device) if len(self.module.adversarials) else None
+        eng.pipeline_optimizer = not self.sync_logging    # pipelined mode: results (logs, output-layer update) trail
         rec = eng.train_step(expert_id, crow, col, val, nnz, self.kl_annealing_fn.kl_weight, labels=labels)
         self.kl_annealing_fn.step()
         if self.sync_logging:
@@ -223,6 +224,8 @@ class CMMVAEModel(BaseModel):
             host, rec, expert_id = self._pending_log
             self._pending_log = None
             self._log_step(self.engine().scalars(rec, host=host), expert_id)
+        if self._engine:
+            self._engine.finish()
 
     def _log_step(self, s: dict, expert_id: str):
         stage = self.stage_name
@@ -237,6 +240,8 @@ class CMMVAEModel(BaseModel):
 
     def validation_step(self, batch):
         x, metadata, expert_id = batch
+        if self._engine:
+            self._engine.finish()
         if self.engine() is None:
             with torch.no_grad():
                 qz, pz, z, xhats, _ = self.module(x, metadata, expert_id)
@@ -253,4 +258,6 @@ class CMMVAEModel(BaseModel):
 
     def predict_step(self, batch, batch_idx: int):
         x, metadata, species = batch
+        if self._engine:
+            self._engine.finish()
         return self.module.get_latent_embeddings(x, metadata, species)

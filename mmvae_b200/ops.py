@@ -276,10 +276,11 @@ def sumsq(g, norm_sq):
     _check(lib().cmmvae_sumsq(_ptr(g), _c.c_longlong(g.numel()), _ptr(norm_sq), _stream()), "sumsq")
 
 
-def clip_adam(p, g, m, v, p16, norm_sq, max_norm, grad_scale, lr, beta1, beta2, eps, wd, step):
+def clip_adam(p, g, m, v, p16, norm_sq, max_norm, grad_scale, lr, beta1, beta2, eps, wd, step, background=False):
     bc1 = 1.0 - beta1 ** step
     bc2 = 1.0 - beta2 ** step
-    _check(lib().cmmvae_clip_adam(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p16), _c.c_longlong(p.numel()),
+    fn = lib().cmmvae_clip_adam_bg if background else lib().cmmvae_clip_adam
+    _check(fn(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p16), _c.c_longlong(p.numel()),
                                   _ptr(norm_sq), _c.c_float(max_norm if max_norm else 0.0), _c.c_float(grad_scale),
                                   _c.c_float(lr), _c.c_float(beta1), _c.c_float(beta2), _c.c_float(eps),
                                   _c.c_float(wd), _c.c_float(bc1), _c.c_float(bc2), _stream()), "clip_adam")

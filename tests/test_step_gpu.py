@@ -300,3 +300,49 @@ def test_conditional_layers_module_route_matches_reference(tmp_path):
                 assert rel_l2(a, v.numpy()) < 2e-3, (k, rel_l2(a, v.numpy()))
     finally:
         L.set_precision("bf16")
+
+
+def test_pipelined_optimizer_gives_the_same_training_run(tmp_path):
+    """sync_logging=False turns on the pipelined mode: the step runs on a high-priority stream, the output
+    layer's clip+Adam on a background stream underneath the next forward pass, logs arrive one step late.
+    Four steps alternating species (each expert's deferred update must be joined by ITS next step, by
+    state_dict and by validation) must end in the same weights and the same logged scalars."""
+    from mmvae_b200 import layers as L
+    L.set_precision("fp32")
+    gc = GoldenCase("two_species_adv")
+    finals, logs = [], []
+    for pipelined in (False, True):
+        model = build_b200_model(gc, tmp_path / str(pipelined), kl_fn=_kl_fn("two_species_adv"))
+        model.load_state_dict({f"module.{k}": v for k, v in gc.state("init").items()}, strict=True)
+        model.cuda().train()
+        model.configure_optimizers()
+        model.sync_logging = not pipelined
+        seen = {}
+        for t in range(gc.n_steps):
+            s = gc.step(t)
+            L.inject_noise(s["eps"].cuda())
+            meta = pd.DataFrame({c: [f"{c}_{int(i)}" for i in s["labels"][c]] for c in CONDITIONS})
+            model.training_step((csr_batch(s["crow"], s["col"], s["val"], gc.genes[s["species"]]), meta, s["species"]), t)
+            seen.update({f"{k}": float(v) for k, v in model.logged_metrics.items()})
+        model.flush_logs()
+        seen.update({f"{k}": float(v) for k, v in model.logged_metrics.items()})
+        assert (model.engine().pipeline_optimizer is True) == pipelined
+        finals.append({k: v.detach().cpu() for k, v in model.state_dict().items()})
+        logs.append(seen)
+    L.set_precision("bf16")
+    assert logs[0].keys() == logs[1].keys()
+    for k in logs[0]:
+        assert logs[1][k] == pytest.approx(logs[0][k], rel=1e-6, abs=1e-9), k
+    init = gc.state("init")
+    bad = []
+    for k, v in finals[0].items():
+        name = k[len("module."):]
+        if bias_feeds_batchnorm(name, init) or name.endswith("running_mean"):
+            continue   # zero-gradient biases random-walk on rounding noise (see module docstring of the golden tests)
+        if v.dtype.is_floating_point:
+            err = rel_l2(finals[1][k].numpy(), v.numpy())
+            if err > 1e-5:
+                bad.append((k, err))
+        else:
+            assert torch.equal(finals[1][k], v), k
+    assert not bad, bad

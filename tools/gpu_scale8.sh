@@ -3,10 +3,7 @@ run() { # n extra-env tag flags
 n=$1; tag=$3
 env $2 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29711 bench.py --gpus $n --steps 60 --warmup 5 --no-cpu-baseline $4 2>gpurun_out/dp_err_$tag.log | tee gpurun_out/scale_$tag.json | python -c "
 import json,sys,os; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$tag N', d['n_gpus'], {k:round(d[k],3) for k in ('value','ms_per_step')}, round(d['e2e']['value']), d.get('e2e_diag'), {k:round(v,3) for k,v in d['kernels_ms'].items()})"
-tail -2 gpurun_out/dp_err_$tag.log | cut -c1-200
+grep -E "Error|Traceback" -A3 gpurun_out/dp_err_$tag.log | head -10
 }
-nproc
-run 8 "X=1" 8 "--e2e-diag"
-run 8 "CMMVAE_DP_CHUNKS=4" 8c4 ""
+run 8 "X=1" 8 ""
 run 4 "X=1" 4 ""
-run 2 "X=1" 2 ""
