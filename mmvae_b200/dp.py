@@ -49,3 +49,11 @@ def species_for_step(step: int, species: Sequence[str], seed: int = 0) -> str:
     ``random.choice`` on identically seeded ranks (multi_modal_loader.py:57-61); here the choice is a
     pure function of (seed, step) so ranks cannot drift apart."""
     return random.Random(seed * 1000003 + step).choice(list(species))
+
+
+def shard_rows(rows: int, world: int, align: int = 128) -> int:
+    """rows of a row-sharded matrix owned by each rank: ceil(rows / world) rounded up to ``align`` (the tile
+    height of the tensor-pipe SpMM), so rank r owns rows [r * n, (r + 1) * n) of the matrix padded to
+    world * n rows.  The last ranks may own only padding."""
+    per = (rows + world - 1) // world
+    return (per + align - 1) // align * align

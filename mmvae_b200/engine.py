@@ -86,7 +86,7 @@ class FlatGroup:
                 assert len(seg) == 1 and len(seg[0]) == 1, "row-sharded segment = one matrix"
                 p0, tr0 = seg[0][0]
                 rows, width = (p0.shape[1], p0.shape[0]) if tr0 else (p0.shape[0], p0.shape[1])
-                per = _ceil((rows + self.world - 1) // self.world, 128)
+                per = dp.shard_rows(rows, self.world)
                 assert (per * width) % 256 == 0
                 total = lo + self.world * per * width
                 self.row_shard = (per, width, self.world * per)

@@ -50,6 +50,55 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
+def _worker_by_inputs(rank, world, port, out):
+    """the identity the data-parallel first-layer gradient relies on: rank r's gene shard of the SUMMED
+    gradient  sum_s X_s^T dY_s  equals  X_all^T dY_all  restricted to the shard, so exchanging the inputs
+    (CSR + dY, all-gather) replaces exchanging the outputs (reduce-scatter of a [G, H] matrix)"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        B, G, H = 24, 300, 16
+        crow, col, val = O.synth_csr(B, G, 0.1, seed=40 + rank)
+        X = torch.sparse_csr_tensor(torch.from_numpy(crow), torch.from_numpy(col), torch.from_numpy(val),
+                                    size=(B, G)).to_dense()
+        dY = torch.randn(B, H, generator=torch.Generator().manual_seed(90 + rank))
+        # outputs route: full per-rank gradient, summed over ranks (what DDP all-reduces), then sliced
+        full = X.t() @ dY
+        dist.all_reduce(full)
+        per = dp.shard_rows(G, world)
+        assert per % 128 == 0 and per * world >= G and per * (world - 1) < G + per
+        lo, hi = rank * per, min((rank + 1) * per, G)
+        # inputs route: gather every rank's cells and dY, multiply only this rank's gene rows
+        Xs, dYs = [torch.empty_like(X) for _ in range(world)], [torch.empty_like(dY) for _ in range(world)]
+        dist.all_gather(Xs, X)
+        dist.all_gather(dYs, dY)
+        shard = torch.cat(Xs)[:, lo:hi].t() @ torch.cat(dYs)
+        assert torch.allclose(shard, full[lo:hi], rtol=1e-5, atol=1e-5)
+        out.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        out.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_first_layer_gradient_by_inputs_identity_two_gloo_ranks():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29500 + (os.getpid() + 501) % 2000
+    procs = [ctx.Process(target=_worker_by_inputs, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    assert all(r[1] == "ok" for r in res), res
+
+
+def test_shard_rows():
+    assert dp.shard_rows(60530, 8) == 7680 and dp.shard_rows(60530, 2) == 30336 and dp.shard_rows(264, 2) == 256
+    assert dp.shard_rows(128, 1) == 128 and dp.shard_rows(129, 1) == 256
+
+
 def test_dp_semantics_two_gloo_ranks():
     ctx = mp.get_context("spawn")
     out = ctx.Queue()

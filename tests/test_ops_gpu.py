@@ -347,3 +347,39 @@ def test_csr_linear_tc_fwd_bwd(ops, B, G, H, density):
     absent = (dense16 != 0).sum(0) == 0
     if absent.any():
         assert torch.all(dWt.cpu()[absent] == 0)
+
+
+def test_csr_linear_bwd_w_tc_shard_equals_sum_of_full_gradients(ops):
+    """data-parallel first layer (2 simulated ranks on one GPU): each rank's gene shard computed from the
+    concatenated inputs == the same rows of the sum of the per-rank full gradients.  The inputs are laid out
+    exactly as StepEngine._dp_gather_csr leaves them (packed records back to back at a fixed capacity, window
+    pointers rebased per source rank, shard windows + closing row)."""
+    from mmvae_b200 import dp
+    world, B, G, H = 2, 96, 1000, 64
+    per = dp.shard_rows(G, world)          # 512
+    G_pad, WS = world * per, per // 64
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    batches, dYs, fulls, tps, packs = [], [], [], [], []
+    for r in range(world):
+        crow, col, val = O.synth_csr(B, G, 0.06, seed=70 + r)
+        crow, col, val = (torch.from_numpy(a).cuda() for a in (crow, col, val))
+        nnz = int(col.numel())
+        dY = torch.randn(B, H, device="cuda", generator=gen).bfloat16()
+        tp, packed = ops.csr_tile_ptr(crow, col, val, G_pad, nnz)
+        full = torch.zeros(G_pad, H, device="cuda")
+        ops.csr_linear_bwd_w_tc(packed, tp, B, G_pad, dY, full)
+        batches.append((crow, col, val)); dYs.append(dY); fulls.append(full); tps.append(tp.view(-1, B)); packs.append(packed)
+    cap = max(int(p.numel()) for p in packs) + 64
+    packed_all = torch.zeros(world * cap, dtype=torch.int32, device="cuda")
+    for r in range(world):
+        packed_all[r * cap:r * cap + packs[r].numel()] = packs[r]
+    dY_all = torch.cat(dYs).contiguous()
+    total = fulls[0] + fulls[1]
+    for r in range(world):
+        tp_shard = torch.cat([tps[s][r * WS:r * WS + WS + 1] + s * cap for s in range(world)], dim=1).contiguous()
+        out = torch.full((per, H), float("nan"), device="cuda")
+        ops.csr_linear_bwd_w_tc_shard(packed_all, tp_shard, world * B, G_pad, dY_all, out, r * per, (r + 1) * per)
+        ref = total[r * per:(r + 1) * per]
+        assert torch.isfinite(out).all()
+        assert (out - ref).abs().max().item() <= 1e-5 * ref.abs().max().item() + 1e-6
+        assert torch.equal(out[max(0, G - r * per):], torch.zeros_like(out[max(0, G - r * per):]))   # padding rows
