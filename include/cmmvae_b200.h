@@ -84,8 +84,10 @@ int cmmvae_csr_linear_bwd_w_tc_shard(const void* packed, const int32_t* tile_ptr
 
 /* ---- K2/K3: BatchNorm1d(momentum, eps) + ReLU + Dropout, components.py:279-288 ------------- */
 /* column statistics of Y[B,H]: mean[H], rstd[H] = 1/sqrt(biased var + eps); updates running
- * stats (unbiased var, momentum) when running_mean != NULL.  `scratch` = 2*H doubles, zeroed by
- * the call. */
+ * stats (unbiased var, momentum) when running_mean != NULL.  One launch: the last row-chunk block
+ * of each column group finishes the statistics.  `scratch` = cmmvae_bn_stats_scratch_bytes(H) bytes that are
+ * ZERO on entry; the call leaves them zero again (allocate + zero once, reuse for every call). */
+size_t cmmvae_bn_stats_scratch_bytes(int H);
 int cmmvae_bn_stats(const float* Y, int B, int H, float eps, float momentum, float* mean, float* rstd,
                     float* running_mean, float* running_var, double* scratch, void* stream);
 /* out = drop(act(gamma*(Y-mean)*rstd+beta)); gamma==NULL -> no normalisation (plain act/dropout).
@@ -97,12 +99,14 @@ int cmmvae_bn_act_drop_fwd(const float* Y, int B, int H, const float* mean, cons
                            unsigned long long seed, const uint8_t* mask,
                            float* out_f32, void* out_bf16, void* stream);
 /* backward of the above.  dOut f32 [B,H]; `out` = forward output (sign gives the ReLU mask).
- * Produces dY f32 (+bf16 copy), dgamma, dbeta (if gamma != NULL) and dbias = colsum(dY). */
+ * Produces dY f32 (+bf16 copy), dgamma, dbeta (if gamma != NULL) and dbias = colsum(dY).
+ * accumulate != 0: the three vector gradients are added to (the caller zeroed them: one fill per step
+ * instead of three memsets per layer). */
 int cmmvae_bn_act_drop_bwd(const float* dOut, const float* Y, const float* out, int B, int H,
                            const float* mean, const float* rstd, const float* gamma,
                            int relu, float p_drop, unsigned long long seed, const uint8_t* mask,
                            float* dY, void* dY_bf16, float* dgamma, float* dbeta, float* dbias,
-                           void* stream);
+                           int accumulate, void* stream);
 /* eval-mode BN uses running stats: call bn_act_drop_fwd with mean=running_mean and
  * rstd computed by this helper. */
 int cmmvae_rstd_from_var(const float* var, int H, float eps, float* rstd, void* stream);

@@ -38,9 +38,14 @@ inline int check_launch(const char* what) {
 // init, TMEM allocation, tensor-map prefetch, block scheduling itself -- overlaps the predecessor's tail.
 // pdl_sync() also lets this grid's own successor start its prologue.  CMMVAE_PDL=0 turns the attribute off.
 bool pdl_enabled();
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// short kernels: let the successor in right away.  The long persistent tensor-pipe kernels instead call
+// pdl_wait() after their prologue and pdl_trigger() once their last unit's MMAs are issued, so a successor's
+// CTAs do not sit on the SMs for the whole run
 __device__ __forceinline__ void pdl_sync() {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  pdl_trigger();
+  pdl_wait();
 }
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {

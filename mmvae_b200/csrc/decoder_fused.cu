@@ -88,7 +88,7 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_sync();   // prologue overlapped the previous kernel; its results are visible from here on
+  pdl_wait();   // prologue overlapped the previous kernel; its results are visible from here on
 
   if (warp == kTmaWarp) {
     if (lane == 0) {
@@ -132,6 +132,7 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
         }
         umma_commit(&tmem_full[acc]);
       }
+      pdl_trigger();   // every MMA of this CTA is issued: the next kernel in the stream may move in
     }
   } else {
     // ===== epilogue: thread = (cell row, 64-gene window) =====

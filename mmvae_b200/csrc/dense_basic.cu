@@ -10,10 +10,16 @@ namespace cmmvae {
 // ---------------------------------------------------------------------------------------------
 constexpr int kRowsPerChunk = 256;
 
-__global__ void __launch_bounds__(256) bn_stats_reduce_kernel(const float* __restrict__ Y, int B, int H,
-                                                              double* __restrict__ scratch) {
+// Column sums / sums of squares of Y[B,H] in double (atomics into `scratch`), finished by the LAST row-chunk
+// block of every 32-column group (ticket counter behind the sums): mean, rstd, running statistics -- one launch.
+// `scratch` = 2*H doubles + ceil(H/32) counters, zero on entry; the finishing block leaves it zero again.
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ Y, int B, int H,
+                                                       double* __restrict__ scratch, float eps, float momentum,
+                                                       float* __restrict__ mean, float* __restrict__ rstd,
+                                                       float* __restrict__ rm, float* __restrict__ rv) {
   pdl_sync();
   __shared__ double s1[8][33], s2[8][33];
+  __shared__ int is_last;
   const int h = blockIdx.x * 32 + threadIdx.x;
   const int r0 = blockIdx.y * kRowsPerChunk;
   const int r1 = min(B, r0 + kRowsPerChunk);
@@ -35,24 +41,28 @@ __global__ void __launch_bounds__(256) bn_stats_reduce_kernel(const float* __res
     }
     atomicAdd(&scratch[h], a);
     atomicAdd(&scratch[H + h], b);
+    __threadfence();
   }
-}
-
-__global__ void bn_stats_finalize_kernel(const double* __restrict__ scratch, int B, int H, float eps,
-                                         float momentum, float* __restrict__ mean, float* __restrict__ rstd,
-                                         float* __restrict__ rm, float* __restrict__ rv) {
-  pdl_sync();
-  const int h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h >= H) return;
-  const double m = scratch[h] / B;
-  double var = scratch[H + h] / B - m * m;
-  if (var < 0.0) var = 0.0;
-  mean[h] = (float)m;
-  rstd[h] = (float)(1.0 / sqrt(var + (double)eps));
-  if (rm) {
-    const double unbiased = B > 1 ? var * ((double)B / (double)(B - 1)) : var;
-    rm[h] = (float)((1.0 - (double)momentum) * (double)rm[h] + (double)momentum * m);
-    rv[h] = (float)((1.0 - (double)momentum) * (double)rv[h] + (double)momentum * unbiased);
+  __syncthreads();
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(scratch + 2 * (size_t)H);
+  if (threadIdx.x == 0 && threadIdx.y == 0) is_last = atomicAdd(&tickets[blockIdx.x], 1u) == gridDim.y - 1;
+  __syncthreads();
+  if (!is_last) return;
+  if (threadIdx.y == 0 && h < H) {
+    __threadfence();
+    const double m = __ldcg(&scratch[h]) / B;
+    double var = __ldcg(&scratch[H + h]) / B - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[h] = (float)m;
+    rstd[h] = (float)(1.0 / sqrt(var + (double)eps));
+    if (rm) {
+      const double unbiased = B > 1 ? var * ((double)B / (double)(B - 1)) : var;
+      rm[h] = (float)((1.0 - (double)momentum) * (double)rm[h] + (double)momentum * m);
+      rv[h] = (float)((1.0 - (double)momentum) * (double)rv[h] + (double)momentum * unbiased);
+    }
+    scratch[h] = 0.0;
+    scratch[H + h] = 0.0;
+    if (threadIdx.x == 0) tickets[blockIdx.x] = 0u;
   }
 }
 
@@ -578,13 +588,14 @@ extern "C" int cmmvae_bn_stats(const float* Y, int B, int H, float eps, float mo
                                float* running_mean, float* running_var, double* scratch, void* stream) {
   CMMVAE_REQUIRE(B > 0 && H > 0 && scratch, "bn_stats: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  cudaMemsetAsync(scratch, 0, sizeof(double) * 2 * (size_t)H, st);
   dim3 grid((H + 31) / 32, (B + kRowsPerChunk - 1) / kRowsPerChunk), block(32, 8);
-  launch_pdl(bn_stats_reduce_kernel, dim3(grid), dim3(block), 0, st, Y, B, H, scratch);
-  if (int rc = check_launch("bn_stats_reduce")) return rc;
-  launch_pdl(bn_stats_finalize_kernel, dim3((H + 255) / 256), dim3(256), 0, st, scratch, B, H, eps, momentum, mean, rstd,
-                                                            running_mean, running_var);
-  return check_launch("bn_stats_finalize");
+  launch_pdl(bn_stats_kernel, dim3(grid), dim3(block), 0, st, Y, B, H, scratch, eps, momentum, mean, rstd,
+             running_mean, running_var);
+  return check_launch("bn_stats");
+}
+
+extern "C" size_t cmmvae_bn_stats_scratch_bytes(int H) {
+  return sizeof(double) * (2 * (size_t)H + ((size_t)H + 31) / 32 / 2 + 1);
 }
 
 extern "C" int cmmvae_rstd_from_var(const float* var, int H, float eps, float* rstd, void* stream) {
@@ -607,20 +618,25 @@ extern "C" int cmmvae_bn_act_drop_fwd(const float* Y, int B, int H, const float*
 extern "C" int cmmvae_bn_act_drop_bwd(const float* dOut, const float* Y, const float* out, int B, int H,
                                       const float* mean, const float* rstd, const float* gamma, int relu,
                                       float p_drop, unsigned long long seed, const uint8_t* mask, float* dY,
-                                      void* dY_bf16, float* dgamma, float* dbeta, float* dbias, void* stream) {
+                                      void* dY_bf16, float* dgamma, float* dbeta, float* dbias, int accumulate,
+                                      void* stream) {
   CMMVAE_REQUIRE(B > 0 && H > 0, "bn_act_drop_bwd: bad shape");
   CMMVAE_REQUIRE(!gamma || (mean && rstd && dgamma && dbeta && Y), "bn_act_drop_bwd: BN needs stats and outputs");
   CMMVAE_REQUIRE(!relu || out, "bn_act_drop_bwd: relu needs the forward output");
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((H + 31) / 32, (B + kRowsPerChunk - 1) / kRowsPerChunk), block(32, 8);
+  if (!accumulate) {   // accumulate: the caller zeroed (or wants to add to) the three vector gradients
+    if (gamma) {
+      cudaMemsetAsync(dgamma, 0, sizeof(float) * H, st);
+      cudaMemsetAsync(dbeta, 0, sizeof(float) * H, st);
+    }
+    if (dbias) cudaMemsetAsync(dbias, 0, sizeof(float) * H, st);
+  }
   if (gamma) {
-    cudaMemsetAsync(dgamma, 0, sizeof(float) * H, st);
-    cudaMemsetAsync(dbeta, 0, sizeof(float) * H, st);
     launch_pdl(bn_bwd_reduce_kernel, dim3(grid), dim3(block), 0, st, dOut, Y, out, B, H, mean, rstd, relu, p_drop, seed, mask,
                                                  dgamma, dbeta);
     if (int rc = check_launch("bn_bwd_reduce")) return rc;
   }
-  if (dbias) cudaMemsetAsync(dbias, 0, sizeof(float) * H, st);
   launch_pdl(bn_bwd_apply_kernel, dim3(grid), dim3(block), 0, st, dOut, Y, out, B, H, mean, rstd, gamma, relu, p_drop, seed, mask,
                                               dgamma, dbeta, dY, (__nv_bfloat16*)dY_bf16, dbias);
   return check_launch("bn_bwd_apply");

@@ -95,7 +95,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_sync();   // the prologue above overlapped the previous kernel; its results are visible from here on
+  pdl_wait();   // the prologue above overlapped the previous kernel; its results are visible from here on
 
   if (warp == kTmaWarp) {
     // ===== TMA producer =====
@@ -162,6 +162,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         umma_commit(&tmem_full[acc]);   // with num_kb == 0 this arrives immediately (nothing outstanding)
       }
+      pdl_trigger();   // every MMA of this CTA is issued: the next kernel in the stream may move in
     }
   } else {
     // ===== epilogue (warps 0..3; TMEM lane group = warp % 4) =====

@@ -140,7 +140,7 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_sync();   // prologue overlapped the previous kernel; its results are visible from here on
+  pdl_wait();   // prologue overlapped the previous kernel; its results are visible from here on
 
   if (warp == kTmaWarp) {
     if (lane == 0) {
@@ -191,6 +191,7 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
         }
         umma_commit(&tmem_full[acc]);
       }
+      pdl_trigger();   // every MMA of this CTA is issued: the next kernel in the stream may move in
     }
   } else if (warp < kEpiWarp0) {
     // ===== A-tile producers: SNG groups of 4 warps; group g builds flat k-blocks f = g (mod SNG) =====

@@ -139,6 +139,7 @@ class FlatGroup:
         self.m = torch.zeros(mv, device=device, dtype=torch.float32)
         self.v = torch.zeros(mv, device=device, dtype=torch.float32)
         self.step_count = 0
+        self._vec_range: Optional[tuple] = None
         self._deferred: Optional[torch.cuda.Event] = None   # output-layer update in flight on the background stream
         self.first_by_inputs = False   # set per step by the engine when gs[0] was produced from gathered inputs
         self._ag_pending: List = []
@@ -151,6 +152,22 @@ class FlatGroup:
             p.grad = gphys.t() if self.transposed[id(p)] else gphys
             L.SHADOWS[id(p)] = self.phys(p, self.p16)
         self.refresh_shadow()
+
+    def zero_vector_grads(self):
+        """one fill per step over the gradients of the 1-D parameters (biases, BatchNorm affine): the kernels
+        that produce them accumulate, instead of each issuing its own memsets in the middle of the backward
+        pass.  Matrix gradients are overwritten by their GEMMs and need no zeroing."""
+        if self._vec_range is None:
+            vec = [(self.offset[id(p)], self.offset[id(p)] + p.numel()) for p in self.params if p.dim() == 1]
+            if not vec:
+                self._vec_range = (0, 0)
+            elif self.seg_bounds:       # tail = vectors first, then (data parallel) the small matrices
+                self._vec_range = (min(a for a, _ in vec), max(b for _, b in vec))
+            else:                       # small group with interleaved layout: clear everything
+                self._vec_range = (0, self.n)
+        lo, hi = self._vec_range
+        if hi > lo:
+            self.g[lo:hi].zero_()
 
     def phys(self, p: nn.Parameter, buf: Optional[torch.Tensor] = None) -> torch.Tensor:
         """physical (row-major, contiguous) view of parameter ``p`` inside ``buf`` (default: values)"""
@@ -554,8 +571,7 @@ class StepEngine:
             if lp.bn is not None:
                 mean, rstd = self.ws(tag + ".mean", (lp.N,)), self.ws(tag + ".rstd", (lp.N,))
                 if training:
-                    ops.bn_stats(Y, lp.bn.eps, lp.bn.momentum, mean, rstd, lp.bn.running_mean, lp.bn.running_var,
-                                 self.ws("bn.scratch", (2 * lp.N,), torch.float64))
+                    ops.bn_stats(Y, lp.bn.eps, lp.bn.momentum, mean, rstd, lp.bn.running_mean, lp.bn.running_var)
                     lp.bn.num_batches_tracked += 1
                 else:
                     mean = lp.bn.running_mean
@@ -580,11 +596,11 @@ class StepEngine:
             dY16 = self.ws(tag + ".dY16", (B, lp.N), torch.bfloat16) if want16 else None
             ops.bn_act_drop_bwd(dOut32, cache["Y"], cache["out32"], cache["mean"], cache["rstd"],
                                 lp.gamma if lp.bn is not None else None, lp.relu, cache["p"], cache["seed"],
-                                cache["mask"], dY, dY16, lp.ggamma, lp.gbeta, lp.gb)
+                                cache["mask"], dY, dY16, lp.ggamma, lp.gbeta, lp.gb, accumulate=True)
         else:
             dY = dOut32
             dY16 = ops.cast_bf16(dY, self.ws(tag + ".dY16", (B, lp.N), torch.bfloat16)) if want16 else None
-            ops.colsum(dY, lp.gb)
+            ops.colsum(dY, lp.gb, accumulate=True)
         if lp.sparse:
             if csc[0] == "tc":
                 _, tp, G, ssq, pending, gathered = csc
@@ -653,7 +669,8 @@ class StepEngine:
         saved_precision, self.precision = self.precision, ("bf16" if tc else "fp32")
         try:
             sumC, K = ap.Wh32.shape
-            ops.colsum(dl, ap.gbh)
+            ap.group.zero_vector_grads()
+            ops.colsum(dl, ap.gbh, accumulate=True)
             d = self.ws(tag + ".dcode", (B, K))
             if tc:
                 dl16 = ops.cast_bf16(dl, self.ws(tag + ".dl16", tuple(dl.shape), torch.bfloat16))
@@ -767,6 +784,8 @@ class StepEngine:
 
         # ---------------- forward ----------------
         gexp, gvae = self.groups[f"experts/{expert_id}"], self.groups["vae"]
+        gexp.zero_vector_grads()
+        gvae.zero_vector_grads()
         caches = {}
         x32 = x16 = None
         # tensor-pipe SpMM (tile densified in smem) above the density where it beats the gather kernel
@@ -884,7 +903,7 @@ class StepEngine:
             ops.gemm(dl, 1, h16, 1, G, H1, B, C32=out.gW,                 # dWout = dlogits^T h (+ its ||.||^2)
                      sumsq_out=s_norm(1) if fuse_norm else None)
             self._t1(ev)
-            ops.colsum(dl, out.gb, M=B, N=G)
+            ops.colsum(dl, out.gb, M=B, N=G, accumulate=True)
             # the output layer's gradient (half of the expert group) is final: start exchanging it now so
             # the transfer overlaps the rest of the backward pass
             pending = [gexp.exchange_segment_async(gexp.n_first)]
@@ -894,7 +913,7 @@ class StepEngine:
             self._t1(ev)
         else:
             ops.gemm(dl, 1, h32, 1, G, H1, B, C32=out.gW, use_tc=False)
-            ops.colsum(dl, out.gb)
+            ops.colsum(dl, out.gb, accumulate=True)
             pending = [gexp.exchange_segment_async(gexp.n_first)]
             ops.gemm(dl, 0, out.W32, 1, B, H1, G, C32=dh, use_tc=False)
         d = dh
@@ -912,11 +931,11 @@ class StepEngine:
         ops.reparam_kl_bwd(ML, eps, dz, Z, self.var_eps, float(kl_weight) / B, dML, dML16)
         dq = self.ws("dq", (B, self.Hv))
         if self._tc(self.Hv, 2 * Z):
-            self._on_side(lambda: (ops.colsum(dML, self.gbmv),
+            self._on_side(lambda: (ops.colsum(dML, self.gbmv, accumulate=True),
                                    ops.gemm(dML16, 1, q16, 1, 2 * Z, self.Hv, B, C32=self.gWmv)))
             ops.gemm(dML16, 0, self.Wmv16, 1, B, self.Hv, 2 * Z, C32=dq)
         else:
-            self._on_side(lambda: (ops.colsum(dML, self.gbmv),
+            self._on_side(lambda: (ops.colsum(dML, self.gbmv, accumulate=True),
                                    ops.gemm(dML, 1, q32, 1, 2 * Z, self.Hv, B, C32=self.gWmv, use_tc=False)))
             ops.gemm(dML, 0, self.Wmv32, 1, B, self.Hv, 2 * Z, C32=dq, use_tc=False)
         d = dq

@@ -83,11 +83,7 @@ def csr_parts(x: torch.Tensor):
 
 
 def _scratch(H: int, device):
-    key = (H, str(device))
-    s = BN_SCRATCH.get(key)
-    if s is None:
-        s = BN_SCRATCH[key] = torch.empty(2 * H, dtype=torch.float64, device=device)
-    return s
+    return ops.bn_stats_scratch(H, device)
 
 
 def dense_linear(x32, x16, W, bias, relu=False, W16=None):

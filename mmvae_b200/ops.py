@@ -191,8 +191,24 @@ def decoder_mse_fused(h16, Wout16, bout, G: int, crow, col, val, dl16, loss_sum,
 
 
 # -------------------------------------------------------------------------------- BN / act / drop
-def bn_stats(Y, eps, momentum, mean, rstd, running_mean, running_var, scratch):
+_BN_SCRATCH = {}
+
+
+def bn_stats_scratch(H: int, device) -> torch.Tensor:
+    """the zero-initialised, self-cleaning scratch ``bn_stats`` needs for width H (cached per device)"""
+    key = (int(H), str(device))
+    s = _BN_SCRATCH.get(key)
+    if s is None:
+        fn = lib().cmmvae_bn_stats_scratch_bytes
+        fn.restype = _c.c_size_t
+        s = _BN_SCRATCH[key] = torch.zeros(int(fn(int(H))) // 8, dtype=torch.float64, device=device)
+    return s
+
+
+def bn_stats(Y, eps, momentum, mean, rstd, running_mean, running_var, scratch=None):
     B, H = Y.shape
+    if scratch is None:
+        scratch = bn_stats_scratch(H, Y.device)
     _check(lib().cmmvae_bn_stats(_ptr(Y), B, H, _c.c_float(eps), _c.c_float(momentum), _ptr(mean), _ptr(rstd),
                                  _ptr(running_mean), _ptr(running_var), _ptr(scratch), _stream()), "bn_stats")
 
@@ -209,11 +225,13 @@ def bn_act_drop_fwd(Y, mean, rstd, gamma, beta, relu, p_drop, seed, mask, out32,
                                         _ptr(out16), _stream()), "bn_act_drop_fwd")
 
 
-def bn_act_drop_bwd(dOut, Y, out, mean, rstd, gamma, relu, p_drop, seed, mask, dY, dY16, dgamma, dbeta, dbias):
+def bn_act_drop_bwd(dOut, Y, out, mean, rstd, gamma, relu, p_drop, seed, mask, dY, dY16, dgamma, dbeta, dbias,
+                    accumulate=False):
     B, H = dOut.shape
     _check(lib().cmmvae_bn_act_drop_bwd(_ptr(dOut), _ptr(Y), _ptr(out), B, H, _ptr(mean), _ptr(rstd), _ptr(gamma),
                                         int(relu), _c.c_float(p_drop), _c.c_ulonglong(seed), _ptr(mask), _ptr(dY),
-                                        _ptr(dY16), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), _stream()),
+                                        _ptr(dY16), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), int(accumulate),
+                                        _stream()),
            "bn_act_drop_bwd")
 
 
