@@ -28,8 +28,9 @@ def launches(path, dst):
         tot += v
     with open(dst, "w") as f:
         f.write(f"# ncu launch list ({tag}): `ncu --metrics gpu__time_duration.sum --clock-control none` over\n"
-                f"# `python bench.py --steps 2 --warmup 5 --no-cpu-baseline` (config 2, B=1024); {len(data)} launches "
-                f"= 2 timed steps, {tot:.1f} us total device time (cold-cache, serialised: compare SHARES)\n\n")
+                f"# `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (config 2, B=1024); {len(data)} launches = "
+                f"the whole process: set-up + 12 training steps (3 warm-up, 2 timed, 2 breakdown, 3+2 end to end), "
+                f"{tot:.1f} us total device time (cold-cache, serialised: compare SHARES)\n\n")
         f.write("| share | total us | launches | kernel |\n|---|---|---|---|\n")
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| {100 * t / tot:5.1f}% | {t:9.1f} | {n} | `{k}` |\n")
