@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define CMMVAE_ABI_VERSION 1
+#define CMMVAE_ABI_VERSION 2
 #define CMMVAE_F32 0
 #define CMMVAE_BF16 1
 

@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libcmmvae_b200.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "cmmvae_b200.h")
+ABI_VERSION = 2   # must equal CMMVAE_ABI_VERSION of the header the library was built from
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -84,7 +85,7 @@ def load() -> ctypes.CDLL:
                 raise RuntimeError(f"libcmmvae_b200.so does not export {name}")
         lib.cmmvae_last_error.restype = ctypes.c_char_p
         lib.cmmvae_launch_count.restype = ctypes.c_longlong
-        if lib.cmmvae_abi_version() != 1:
+        if lib.cmmvae_abi_version() != ABI_VERSION:
             raise RuntimeError("libcmmvae_b200.so ABI version mismatch")
         _lib = lib
     return _lib

@@ -31,7 +31,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert len(names) >= 20 and "cmmvae_decoder_mse_fused" in names and "cmmvae_csr_linear_fwd" in names
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.cmmvae_abi_version() == 1
+    assert lib.cmmvae_abi_version() == 2
     lib.cmmvae_last_error.restype = ctypes.c_char_p
     assert isinstance(lib.cmmvae_last_error(), bytes)
 
