@@ -197,3 +197,23 @@ def test_reference_state_dict_loads_by_name():
         model = build_b200_model(gc, tmp)
     res = model.load_state_dict({f"module.{k}": v for k, v in gc.state("init").items()}, strict=True)
     assert not res.missing_keys and not res.unexpected_keys
+
+
+def test_bench_reference_arm_contract_on_cpu():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) needs no GPU and prints one
+    JSON line with the contract's keys; a bounded sample keeps it to seconds here."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--batch", "32",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.strip().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "cells/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["vs_baseline"] is None and d["scaling"] == "weak"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
