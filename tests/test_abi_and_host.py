@@ -217,3 +217,34 @@ def test_bench_reference_arm_contract_on_cpu():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_label_lookup_matches_per_cell_dict_walk():
+    """adversary labels (cmmvae_model.py:103-115): the factorised lookup must give exactly the ids the
+    reference's per-cell dict walk gives (int64, row index in the human csv) and raise KeyError on a value the
+    csv does not hold."""
+    import types
+    import numpy as np
+    from mmvae_b200.models.cmmvae_model import CMMVAEModel
+    from mmvae_b200.modules.base.components import Adversarial
+    saved = dict(Adversarial.labels)
+    try:
+        Adversarial.labels.clear()
+        Adversarial.labels.update({"assay": {f"assay_{i}": i for i in range(8)},
+                                   "dataset_id": {f"ds_{i}": i for i in range(272)}})
+        rng = np.random.default_rng(5)
+        meta = pd.DataFrame({"assay": [f"assay_{i}" for i in rng.integers(0, 8, 777)],
+                             "dataset_id": [f"ds_{i}" for i in rng.integers(0, 272, 777)],
+                             "unrelated": np.arange(777)})
+        me = types.SimpleNamespace(_label_ring={}, _label_slot=0)
+        got = CMMVAEModel._labels(me, meta, "cpu")
+        assert list(got) == ["assay", "dataset_id"]
+        for c, table in Adversarial.labels.items():
+            want = torch.tensor([table[v] for v in meta[c].values], dtype=torch.int64)
+            assert got[c].dtype == torch.int64 and torch.equal(got[c], want)
+        meta.loc[3, "assay"] = "never_seen"
+        with pytest.raises(KeyError):
+            CMMVAEModel._labels(me, meta, "cpu")
+    finally:
+        Adversarial.labels.clear()
+        Adversarial.labels.update(saved)
