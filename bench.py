@@ -36,11 +36,18 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-G_HUMAN, G_MOUSE = 60530, 52437
-H1, H2, HV, Z = 1024, 512, 256, 128
-# BASELINE config 4 (configV2.yaml:16-84): wider VAE, latent 256, its own gene panels, 8192 cells per step
-DIMS4 = dict(G_HUMAN=60664, G_MOUSE=52417, H1=1024, H2=768, HV=512, Z=256)
 DENSITY = 0.05
+
+
+class Dims:
+    """model dimensions of a BASELINE config: gene panels, expert hidden sizes, VAE hidden size, latent size"""
+
+    def __init__(self, config: int):
+        if config == 4:   # configV2.yaml:16-84: wider VAE, latent 256, its own gene panels, 8192 cells per step
+            self.G_HUMAN, self.G_MOUSE, self.H1, self.H2, self.HV, self.Z = 60664, 52417, 1024, 768, 512, 256
+        else:             # config.yaml:34-105 / human_only.yaml:28-102
+            self.G_HUMAN, self.G_MOUSE, self.H1, self.H2, self.HV, self.Z = 60530, 52437, 1024, 512, 256, 128
+        self.species = {"human": self.G_HUMAN} if config == 2 else {"human": self.G_HUMAN, "mouse": self.G_MOUSE}
 METRIC = "train cells/sec (fwd+bwd+ELBO)"
 
 
@@ -64,7 +71,8 @@ def build_model(config: int):
     import pandas as pd
     relu = torch.nn.ReLU
     torch.manual_seed(0)
-    species = {"human": G_HUMAN} if config == 2 else {"human": G_HUMAN, "mouse": G_MOUSE}
+    d = Dims(config)
+    species, H1, H2, HV, Z = d.species, d.H1, d.H2, d.HV, d.Z
     experts = Experts([Expert(s, FCBlockConfig([g, H1, H2], dropout_rate=0.1, use_batch_norm=True, activation_fn=relu),
                               FCBlockConfig([H2, H1, g], activation_fn=relu)) for s, g in species.items()])
     vae = CLVAE(FCBlockConfig([H2, HV], use_batch_norm=True, activation_fn=relu, return_hidden=True),
@@ -140,7 +148,8 @@ def cpu_reference_leg(config, B, steps, warmup, threads=None):
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     O.FAST_CSR = True
-    species = {"human": G_HUMAN} if config == 2 else {"human": G_HUMAN, "mouse": G_MOUSE}
+    d = Dims(config)
+    species, H1, H2, HV, Z = d.species, d.H1, d.H2, d.HV, d.Z
     spec = O.ModelSpec(
         experts={s: {"encoder": O.BlockSpec.make([g, H1, H2], bn=True), "decoder": O.BlockSpec.make([H2, H1, g])}
                  for s, g in species.items()},
@@ -206,8 +215,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.config == 4:
-        globals().update(DIMS4)
+    d = Dims(args.config)
+    G_HUMAN, G_MOUSE, H1, H2, HV, Z = d.G_HUMAN, d.G_MOUSE, d.H1, d.H2, d.HV, d.Z
     B = args.batch or {2: 1024, 3: 4096, 4: 8192}[args.config]
     workload = (f"config{args.config}: " + {2: "single-species core VAE (human expert only)",
                                             3: "two-species CMMVAE + 2 GRL adversaries",
