@@ -1,34 +1,35 @@
-"""Gradient-clipping configuration objects (reference: src/cmmvae/config.py:4-26).
+"""Gradient-clipping configuration (boundary objects of ``cmmvae.config``, reference src/cmmvae/config.py:4-26).
 
-``GradientClipConfig`` unpacks as ``(val, algorithm)`` so it can be splatted into
-``clip_gradients(optimizer, *cfg)`` exactly like the reference's object.
+Both objects are plain records.  ``GradientClipConfig`` unpacks as ``(val, algorithm)`` so that it can be
+splatted into ``clip_gradients(optimizer, *cfg)`` the way ``CMMVAEModel.training_step`` does
+(cmmvae_model.py:126-129, 203-209); the fused step reads ``val`` when ``algorithm == "norm"`` and applies the
+clip inside the Adam launch.
 """
-from typing import Optional, Union
+from dataclasses import astuple, dataclass
+from typing import Iterator, Optional, Union
+
+_ALGORITHMS = (None, "norm", "value")
 
 
+@dataclass
 class GradientClipConfig:
-    def __init__(self, val: Optional[Union[int, float]] = None, algorithm: Optional[str] = None):
-        if algorithm not in (None, "norm", "value"):
-            raise ValueError(f"unknown clip algorithm {algorithm!r}")
-        self.val, self.algorithm = val, algorithm
+    val: Optional[Union[int, float]] = None
+    algorithm: Optional[str] = None
 
-    def __iter__(self):
-        yield self.val
-        yield self.algorithm
+    def __post_init__(self):
+        if self.algorithm not in _ALGORITHMS:
+            raise ValueError(f"unknown clip algorithm {self.algorithm!r} (expected one of {_ALGORITHMS[1:]})")
 
-    def __bool__(self):
+    def __iter__(self) -> Iterator:
+        return iter(astuple(self))
+
+    def __bool__(self) -> bool:     # a config object is always "present", even with val=None
         return True
 
-    def __repr__(self):
-        return f"GradientClipConfig(val={self.val}, algorithm={self.algorithm!r})"
 
-
+@dataclass
 class AutogradConfig:
-    """Which optimizer groups get clipped (None = that group is not clipped)."""
-
-    def __init__(self, adversarial_gradient_clip: Optional[GradientClipConfig] = None,
-                 vae_gradient_clip: Optional[GradientClipConfig] = None,
-                 expert_gradient_clip: Optional[GradientClipConfig] = None):
-        self.adversarial_gradient_clip = adversarial_gradient_clip
-        self.vae_gradient_clip = vae_gradient_clip
-        self.expert_gradient_clip = expert_gradient_clip
+    """One optional clip per optimizer family; ``None`` leaves that family unclipped."""
+    adversarial_gradient_clip: Optional[GradientClipConfig] = None
+    vae_gradient_clip: Optional[GradientClipConfig] = None
+    expert_gradient_clip: Optional[GradientClipConfig] = None

@@ -1,7 +1,8 @@
-"""nn.Modules of the CMMVAE network (mirror of the reference's ``cmmvae.modules``)."""
-from mmvae_b200.modules import base
-from mmvae_b200.modules.vae import VAE
-from mmvae_b200.modules.clvae import CLVAE
-from mmvae_b200.modules.cmmvae import CMMVAE
+"""The CMMVAE network as nn.Modules -- what ``cmmvae.modules`` exports: the VAE family and the
+mixture-of-experts wrapper; building blocks live in ``.base``."""
+from . import base
+from .clvae import CLVAE
+from .cmmvae import CMMVAE
+from .vae import VAE
 
-__all__ = ["base", "CLVAE", "CMMVAE", "VAE"]
+__all__ = ["VAE", "CLVAE", "CMMVAE", "base"]

@@ -1,19 +1,8 @@
-"""Building-block nn.Modules and schedules (mirror of the reference's ``cmmvae.modules.base``)."""
-from mmvae_b200.modules.base.components import (
-    Adversarial,
-    ConcatBlockConfig,
-    ConditionalLayer,
-    ConditionalLayers,
-    Encoder,
-    Expert,
-    Experts,
-    FCBlock,
-    FCBlockConfig,
-    GradientReversalFunction,
-)
-from mmvae_b200.modules.base.annealing_fn import KLAnnealingFn, LinearKLAnnealingFn
+"""Building blocks (what ``cmmvae.modules.base`` exports): fully-connected blocks and their configs, the
+latent encoder, species experts, conditional layers, GRL adversaries, KL schedules."""
+from .annealing_fn import KLAnnealingFn, LinearKLAnnealingFn
+from .components import (FCBlock, FCBlockConfig, ConcatBlockConfig, Encoder, Expert, Experts, ConditionalLayer,
+                         ConditionalLayers, Adversarial, GradientReversalFunction)
 
-__all__ = [
-    "Adversarial", "ConditionalLayer", "ConditionalLayers", "ConcatBlockConfig", "Encoder", "Expert", "Experts",
-    "FCBlock", "FCBlockConfig", "GradientReversalFunction", "KLAnnealingFn", "LinearKLAnnealingFn",
-]
+__all__ = ["FCBlock", "FCBlockConfig", "ConcatBlockConfig", "Encoder", "Expert", "Experts", "ConditionalLayer",
+           "ConditionalLayers", "Adversarial", "GradientReversalFunction", "KLAnnealingFn", "LinearKLAnnealingFn"]

@@ -1,11 +1,17 @@
-"""He initialisation of every nn.Linear under a module (reference: src/cmmvae/modules/base/init.py:4-9):
-Kaiming-normal with fan_out / relu gain on weights, zeros on biases."""
+"""Weight initialisation applied by ``BaseModel.init_weights`` to the whole LightningModule
+(reference src/cmmvae/modules/base/init.py:4-9, base_model.py:106-109): every ``nn.Linear`` gets
+He/Kaiming-normal weights (fan_out, ReLU gain, i.e. std = sqrt(2 / out_features)) and a zero bias;
+everything else (BatchNorm affine, ...) keeps torch's defaults."""
 import torch.nn as nn
 
 
+def _he_linear(layer: nn.Module) -> None:
+    if not isinstance(layer, nn.Linear):
+        return
+    nn.init.kaiming_normal_(layer.weight, nonlinearity="relu", mode="fan_out")
+    if layer.bias is not None:
+        nn.init.zeros_(layer.bias)
+
+
 def he_init_weights(module: nn.Module) -> None:
-    linears = (m for m in module.modules() if isinstance(m, nn.Linear))
-    for lin in linears:
-        nn.init.kaiming_normal_(lin.weight, mode="fan_out", nonlinearity="relu")
-        if lin.bias is not None:
-            nn.init.zeros_(lin.bias)
+    module.apply(_he_linear)

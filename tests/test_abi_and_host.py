@@ -248,3 +248,42 @@ def test_label_lookup_matches_per_cell_dict_walk():
     finally:
         Adversarial.labels.clear()
         Adversarial.labels.update(saved)
+
+
+def test_linear_kl_schedule_reproduces_the_reference_run():
+    """the KL weights the unmodified reference fed into steps 0..3 of the `two_species_adv` golden run
+    (LinearKLAnnealingFn(0.1, 1.0, warmup 1, climax 4), one step() per training step)"""
+    from helpers import GoldenCase
+    from mmvae_b200.modules.base import KLAnnealingFn, LinearKLAnnealingFn
+    gc = GoldenCase("two_species_adv")
+    fn = LinearKLAnnealingFn(min_kl_weight=0.1, max_kl_weight=1.0, warmup_steps=1, climax_steps=4)
+    for t in range(gc.n_steps):
+        assert fn.kl_weight == pytest.approx(gc.step(t)["kl_weight"], rel=1e-12)
+        fn.step()
+    for _ in range(20):
+        fn.step()
+    assert fn.kl_weight == 1.0 and (fn.m, fn.b) == (pytest.approx(0.225), 0.1)
+    const = KLAnnealingFn(0.5)
+    const.step()
+    assert const.kl_weight == 0.5
+    const.kl_weight = 0.25          # assignable, as in the reference
+    assert const.kl_weight == 0.25
+    warm = LinearKLAnnealingFn(0.1, 1.0, warmup_steps=3, climax_steps=4)
+    warm.kl_weight = 0.7            # an assigned value survives until the warm-up is over
+    warm.step(); warm.step()
+    assert warm.kl_weight == 0.7
+    warm.step()
+    assert warm.kl_weight == pytest.approx(0.1)
+
+
+def test_clip_config_objects_behave_like_the_reference_records():
+    from mmvae_b200.config import AutogradConfig, GradientClipConfig
+    c = GradientClipConfig(val=10, algorithm="norm")
+    assert tuple(c) == (10, "norm") and (c.val, c.algorithm) == (10, "norm") and bool(c)
+    assert tuple(GradientClipConfig()) == (None, None) and bool(GradientClipConfig())
+    with pytest.raises(ValueError):
+        GradientClipConfig(1.0, "l2")
+    a = AutogradConfig(c)
+    assert a.adversarial_gradient_clip is c and a.vae_gradient_clip is None and a.expert_gradient_clip is None
+    a = AutogradConfig(expert_gradient_clip=c)
+    assert a.expert_gradient_clip is c and a.adversarial_gradient_clip is None
