@@ -94,6 +94,90 @@ def test_first_layer_gradient_by_inputs_identity_two_gloo_ranks():
     assert all(r[1] == "ok" for r in res), res
 
 
+def _worker_gene_sharded(rank, world, port, out):
+    """Executable statement of the round-2 plan ("Next"): with every rank holding all ranks'
+    cells and only ITS gene rows of the two gene-sized matrices, the forward and backward of both layers need
+    no weight or weight-gradient exchange:
+      Y       = reduce_scatter_r( X_all[:, genes_r] @ W1t[genes_r] )            (first layer, all cells)
+      recon   = sum_r || relu(h_all @ Wout[genes_r].T + b[genes_r]) - X_all[:, genes_r] ||^2
+      dWout_r = dlogits_r.T @ h_all,   dW1t_r = X_all[:, genes_r].T @ dY_all       (rank-local, already summed)
+      dh      = reduce_scatter_r( dlogits_r @ Wout[genes_r] )
+    checked against the replicated-weights computation on the concatenated batch."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        B, G, H = 12, 300, 8
+
+        def close(a, b):                                   # fp32 sums in different orders: compare at the tensor's scale
+            return (a - b).abs().max() <= 2e-5 * b.abs().max()
+
+        gen = torch.Generator().manual_seed(5)           # same weights on every rank
+        W1t, Wout, bout = torch.randn(G, H, generator=gen), torch.randn(G, H, generator=gen), torch.randn(G, generator=gen)
+        crow, col, val = O.synth_csr(B, G, 0.1, seed=60 + rank)
+        X = torch.sparse_csr_tensor(torch.from_numpy(crow), torch.from_numpy(col), torch.from_numpy(val),
+                                    size=(B, G)).to_dense()
+        Xs = [torch.empty_like(X) for _ in range(world)]
+        dist.all_gather(Xs, X)
+        X_all = torch.cat(Xs)                              # [world*B, G]
+        per = dp.shard_rows(G, world, align=4)
+        lo, hi = rank * per, min((rank + 1) * per, G)
+        mine = slice(rank * B, (rank + 1) * B)            # this rank's cells inside the global batch
+
+        # ---- reference: replicated weights, global batch
+        Y_ref = X_all @ W1t
+        h_ref = torch.tanh(Y_ref)                          # stand-in for the middle of the network
+        logits = h_ref @ Wout.t() + bout
+        xhat = torch.relu(logits)
+        recon_ref = ((xhat - X_all) ** 2).sum()
+        dlog_ref = 2 * (xhat - X_all) * (logits > 0)
+        dWout_ref, dh_ref = dlog_ref.t() @ h_ref, dlog_ref @ Wout
+        dY_ref = dh_ref * (1 - h_ref ** 2)
+        dW1t_ref = X_all.t() @ dY_ref
+
+        # ---- gene-sharded: only rows [lo, hi) of W1t / Wout / bout are touched on this rank
+        part = X_all[:, lo:hi] @ W1t[lo:hi]
+        dist.all_reduce(part)                              # gloo has no reduce_scatter: all-reduce, keep my cells
+        Y = part[mine]
+        assert close(Y, Y_ref[mine])
+        h = torch.tanh(Y)
+        hs = [torch.empty_like(h) for _ in range(world)]
+        dist.all_gather(hs, h)
+        h_all = torch.cat(hs)
+        logits_r = h_all @ Wout[lo:hi].t() + bout[lo:hi]
+        xhat_r = torch.relu(logits_r)
+        recon = ((xhat_r - X_all[:, lo:hi]) ** 2).sum()
+        dist.all_reduce(recon)
+        assert close(recon, recon_ref)
+        dlog_r = 2 * (xhat_r - X_all[:, lo:hi]) * (logits_r > 0)
+        assert close(dlog_r.t() @ h_all, dWout_ref[lo:hi])
+        dh_part = dlog_r @ Wout[lo:hi]
+        dist.all_reduce(dh_part)
+        dh = dh_part[mine]
+        assert close(dh, dh_ref[mine])
+        dY = dh * (1 - h ** 2)
+        dYs = [torch.empty_like(dY) for _ in range(world)]
+        dist.all_gather(dYs, dY)
+        assert close(X_all[:, lo:hi].t() @ torch.cat(dYs), dW1t_ref[lo:hi])
+        out.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        out.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gene_sharded_layers_identity_two_gloo_ranks():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29500 + (os.getpid() + 977) % 2000
+    procs = [ctx.Process(target=_worker_gene_sharded, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    assert all(r[1] == "ok" for r in res), res
+
+
 def test_shard_rows():
     assert dp.shard_rows(60530, 8) == 7680 and dp.shard_rows(60530, 2) == 30336 and dp.shard_rows(264, 2) == 256
     assert dp.shard_rows(128, 1) == 128 and dp.shard_rows(129, 1) == 256
