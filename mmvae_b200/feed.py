@@ -167,3 +167,66 @@ class CSRStager:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.device))
             self._consumed[t.slot] = ev
+
+
+class StagedCSRBatches:
+    """Batches of a chunked CSR dataset, staged one batch ahead.
+
+    Iterates like the reference's ``SparseCSRMatrixBatcherDataPipe`` (data/local/cellxgene_datapipe.py:125-193):
+    ``source`` yields ``(scipy.sparse.csr_matrix chunk, pandas.DataFrame)`` pairs (what ``LoadCSRMatrixAndDataFrame``
+    / ``ShuffleCSRMatrixAndDataFrame`` produce from the ``.npz`` / ``.pkl`` chunk files); every chunk is cut into
+    consecutive ``batch_size``-row batches, a trailing short batch is skipped unless ``allow_partials``, metadata
+    is ``frame.iloc[i:i+batch_size].reset_index(drop=True)``, and each item is ``(torch.sparse_csr_tensor, metadata)``.
+
+    Difference: rows are never materialised as a scipy slice -- they are written straight from the chunk's
+    ``indptr / indices / data`` into a pinned ``CSRStager`` block, shipped with one asynchronous copy while the
+    previous batch is being consumed, and the yielded tensor lives on ``device``.  The block of a batch is
+    recycled once the consumer asks for the next item, i.e. after it has enqueued its work on the current stream.
+    """
+
+    def __init__(self, source, batch_size: int, allow_partials: bool = False, device="cuda", depth: int = 3):
+        if batch_size <= 0:
+            raise ValueError("batch_size must be positive")
+        if depth < 3:
+            raise ValueError("StagedCSRBatches needs depth >= 3 (consumed, staged ahead, being filled)")
+        self.source, self.batch_size, self.allow_partials = source, int(batch_size), bool(allow_partials)
+        self.device, self.depth = device, int(depth)
+        self.stager: Optional[CSRStager] = None
+
+    def _ensure_capacity(self, nnz: int):
+        if self.stager is None or nnz > self.stager.max_nnz:
+            # a denser batch than any seen so far: new ring with head room (old blocks stay alive with the
+            # tickets that reference them until their consumers are done)
+            self.stager = CSRStager(self.batch_size, int(nnz * 1.25) + 1024, device=self.device, depth=self.depth)
+
+    def __iter__(self):
+        ahead = None                      # (stager, ticket, metadata) committed but not yet handed out
+        done = None                       # (stager, ticket) handed out on the previous iteration
+        for chunk, frame in self.source:
+            indptr, indices, data = chunk.indptr, chunk.indices, chunk.data
+            n_rows, n_genes = chunk.shape
+            for lo in range(0, n_rows, self.batch_size):
+                hi = min(lo + self.batch_size, n_rows)
+                if hi - lo != self.batch_size and not self.allow_partials:
+                    continue
+                nnz = int(indptr[hi]) - int(indptr[lo])
+                self._ensure_capacity(nnz)
+                blk = self.stager.reserve(hi - lo, nnz)
+                slice_rows(indptr, indices, data, lo, hi, out=blk)
+                ticket = self.stager.commit(blk, n_genes)
+                meta = frame.iloc[lo:hi].reset_index(drop=True) if frame is not None else None
+                if ahead is not None:
+                    if done is not None:
+                        done[0].release(done[1])
+                    st, tk, md = ahead
+                    done = (st, tk)
+                    yield st.get(tk), md
+                ahead = (self.stager, ticket, meta)
+        if ahead is not None:
+            if done is not None:
+                done[0].release(done[1])
+            st, tk, md = ahead
+            done = (st, tk)
+            yield st.get(tk), md
+        if done is not None:
+            done[0].release(done[1])

@@ -151,3 +151,57 @@ def test_training_step_through_the_stager_matches_direct_feed(tmp_path):
             assert logs[0][k] == pytest.approx(logs[1][k], rel=1e-6), k
     finally:
         L.set_precision("bf16")
+
+
+def _chunks(n_chunks, rows, G=157, seed=0):
+    import pandas as pd
+    out = []
+    for k in range(n_chunks):
+        m = sp.random(rows[k], G, density=0.08 + 0.05 * k, format="csr", dtype=np.float32,
+                      random_state=np.random.default_rng(seed + k))
+        m.sort_indices()
+        out.append((m, pd.DataFrame({"cell": [f"c{k}_{i}" for i in range(rows[k])], "chunk": k})))
+    return out
+
+
+@pytest.mark.parametrize("allow_partials", [False, True])
+def test_staged_batches_iterate_like_the_reference_batcher(allow_partials):
+    """same batches, in the same order, as SparseCSRMatrixBatcherDataPipe (cellxgene_datapipe.py:169-193):
+    consecutive row slices of each chunk, short trailing batch only with allow_partials, metadata re-indexed"""
+    from mmvae_b200.feed import StagedCSRBatches
+    bs = 16
+    chunks = _chunks(3, [50, 16, 33])        # second chunk is denser than the first: the ring must grow
+    want = []
+    for m, frame in chunks:
+        for i in range(0, m.shape[0], bs):
+            b = m[i:i + bs]
+            if b.shape[0] != bs and not allow_partials:
+                continue
+            want.append((b, frame.iloc[i:i + bs].reset_index(drop=True)))
+    assert len(want) == (8 if allow_partials else 6)
+    n = 0
+    # an item is valid until the next one is requested (its block is recycled after that): compare as we go
+    staged = iter(StagedCSRBatches(chunks, bs, allow_partials=allow_partials, device="cpu"))
+    for b, wmeta in want:
+        x, meta = next(staged)
+        n += 1
+        assert x.layout == torch.sparse_csr and tuple(x.shape) == b.shape
+        np.testing.assert_array_equal(x.crow_indices().numpy(), b.indptr)
+        np.testing.assert_array_equal(x.col_indices().numpy(), b.indices)
+        np.testing.assert_array_equal(x.values().numpy().view(np.uint32), b.data.view(np.uint32))
+        assert meta.equals(wmeta)
+    assert n == len(want) and next(staged, None) is None
+
+
+def test_staged_batches_keep_a_batch_valid_until_the_next_one_is_requested():
+    from mmvae_b200.feed import StagedCSRBatches
+    chunks = _chunks(1, [64])
+    it = iter(StagedCSRBatches(chunks, 8, device="cpu", depth=3))
+    x0, _ = next(it)
+    snap = (x0.crow_indices().clone(), x0.col_indices().clone(), x0.values().clone())
+    x1, _ = next(it)            # batch 2 has been staged by now; batch 0's block must still be intact
+    assert torch.equal(x0.crow_indices(), snap[0]) and torch.equal(x0.col_indices(), snap[1])
+    assert torch.equal(x0.values(), snap[2])
+    assert len(list(it)) == 6
+    with pytest.raises(ValueError):
+        StagedCSRBatches(chunks, 8, device="cpu", depth=2)
