@@ -234,6 +234,9 @@ class FlatGroup:
                                   norm_sq, max_norm or 0.0, grad_scale, *hyper)
             first_done = torch.cuda.Event()
             first_done.record()
+            # the clip norm lives in the step's scalar block: keep the allocator from recycling that block for a
+            # later step while the background launch may still read it
+            norm_sq.record_stream(background)
             with torch.cuda.stream(background), ops.stream_scope(background):
                 background.wait_event(first_done)
                 ops.clip_adam(self.p[lo1:hi1], self.g[lo1:hi1], self.m[lo1:hi1], self.v[lo1:hi1], self.p16[lo1:hi1],
