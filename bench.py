@@ -11,13 +11,20 @@ every rank trains its own 1024-cell batch, gradients are all-reduced (mean) over
 
 One JSON line on rank 0:
   value     whole-job cells/s with the batch already resident in HBM (CUDA-event timed, max over ranks)
-  e2e       the same metric through the public API (CMMVAEModel.training_step on a torch.sparse_csr batch
-            built from PINNED HOST arrays each step; H2D copy and the D2H read of the loss scalars inside
-            the timed region)
+  e2e       the same metric through the public API: the reference batcher's iteration over PAGEABLE scipy CSR
+            chunks (mmvae_b200.feed.StagedCSRBatches: packing on worker threads, uint16 gene ids, one pinned
+            block + one async H2D copy per batch) -> CMMVAEModel.training_step -> D2H read of the loss scalars,
+            all inside the timed region
   roofline  the dominant kernel (fused decoder GEMM + ReLU + sum-MSE epilogue): algorithmic FLOPs / its
             mean launch duration (CUDA events on the launch stream) vs MEASURED_PEAKS.json bf16 peak
-  cpu_baseline  the oracle port of the reference's CPU training step on this box's host cores
-``--impl reference`` times that CPU path alone (rank 0) and prints the same line with impl=reference.
+  parity_check  one extra step from the trained weights against one oracle step (outside the timed regions);
+            the bench prints no line if they disagree
+  torch_cuda_baseline  the UNMODIFIED reference (baseline/_ref) as stock PyTorch eager on this GPU, fp32 and
+            bf16 autocast: the on-box library path the kernels have to beat
+  cpu_baseline  the unmodified reference's CPU training step on this box's host cores (bounded sample)
+  also.config3  (N > 1) BASELINE configs[2] -- two species + GRL adversaries, 4096 cells/GPU -- at the same N
+``--impl reference`` times the unmodified reference on the host cores alone (rank 0) and prints the same line
+with impl=reference (oracle port only if baseline/_ref is absent).
 """
 from __future__ import annotations
 
@@ -58,12 +65,16 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def synth_csr(B, G, density, seed, zipf=0.0):
+    from mmvae_b200.synth import synth_csr as gen
+    return gen(B, G, density, seed, zipf)
+
+
 def synth_batches(n, B, G, density, seed):
-    from oracle.cmmvae_oracle import synth_csr
     return [synth_csr(B, G, density, seed + i) for i in range(n)]
 
 
-def build_model(config: int):
+def build_model(config: int, only=None):
     from mmvae_b200.config import AutogradConfig, GradientClipConfig
     from mmvae_b200.models import CMMVAEModel
     from mmvae_b200.modules import CLVAE, CMMVAE
@@ -72,7 +83,8 @@ def build_model(config: int):
     relu = torch.nn.ReLU
     torch.manual_seed(0)
     d = Dims(config)
-    species, H1, H2, HV, Z = d.species, d.H1, d.H2, d.HV, d.Z
+    species = {s: g for s, g in d.species.items() if only is None or s in only}
+    H1, H2, HV, Z = d.H1, d.H2, d.HV, d.Z
     experts = Experts([Expert(s, FCBlockConfig([g, H1, H2], dropout_rate=0.1, use_batch_norm=True, activation_fn=relu),
                               FCBlockConfig([H2, H1, g], activation_fn=relu)) for s, g in species.items()])
     vae = CLVAE(FCBlockConfig([H2, HV], use_batch_norm=True, activation_fn=relu, return_hidden=True),
@@ -141,20 +153,32 @@ class ClockSampler:
         return out
 
 
-def cpu_reference_leg(config, B, steps, warmup, threads=None):
-    """The reference's CPU training step (oracle port: same ATen calls -- sparse-CSR addmm, dense GEMMs,
-    batch-norm, to_dense + mse, autograd backward, clip, Adam) on this box's host cores."""
+def oracle_spec(config, species, dropout=0.0, conds=None):
+    from oracle import cmmvae_oracle as O
+    d = Dims(config)
+    H1, H2, HV, Z = d.H1, d.H2, d.HV, d.Z
+    advs = []
+    if conds:
+        advs = [O.AdversarySpec(O.BlockSpec.make([HV, 128, 64]), dict(conds)),
+                O.AdversarySpec(O.BlockSpec.make([Z, 64]), dict(conds))]
+    return O.ModelSpec(
+        experts={s: {"encoder": O.BlockSpec.make([g, H1, H2], bn=True, dropout=dropout),
+                     "decoder": O.BlockSpec.make([H2, H1, g])} for s, g in species.items()},
+        vae_encoder=O.BlockSpec.make([H2, HV], bn=True, return_hidden=True),
+        vae_decoder=O.BlockSpec.make([Z, HV, H2]), latent_dim=Z, hidden_z=bool(conds), adversarials=advs)
+
+
+def cpu_port_leg(config, B, steps, warmup, threads=None, budget_s=170.0):
+    """The reference's CPU training step restated by the oracle (same ATen calls -- sparse-CSR addmm, dense
+    GEMMs, batch-norm, to_dense + mse, autograd backward, clip, Adam) on this box's host cores.  Only used when
+    the unmodified reference (baseline/_ref) is not installed."""
     from oracle import cmmvae_oracle as O
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     O.FAST_CSR = True
     d = Dims(config)
     species, H1, H2, HV, Z = d.species, d.H1, d.H2, d.HV, d.Z
-    spec = O.ModelSpec(
-        experts={s: {"encoder": O.BlockSpec.make([g, H1, H2], bn=True), "decoder": O.BlockSpec.make([H2, H1, g])}
-                 for s, g in species.items()},
-        vae_encoder=O.BlockSpec.make([H2, HV], bn=True, return_hidden=True),
-        vae_decoder=O.BlockSpec.make([Z, HV, H2]), latent_dim=Z)
+    spec = oracle_spec(config, species)
     gen = torch.Generator().manual_seed(0)
     P = {}
 
@@ -182,7 +206,7 @@ def cpu_reference_leg(config, B, steps, warmup, threads=None):
     opt = {}
     names = list(species)
     batches = {s: synth_batches(2, B, g, DENSITY, 7000) for s, g in species.items()}
-    times = []
+    times, spent = [], 0.0
     for t in range(warmup + steps):
         s = names[t % len(names)]
         crow, col, val = batches[s][t % 2]
@@ -192,12 +216,101 @@ def cpu_reference_leg(config, B, steps, warmup, threads=None):
         dt = time.perf_counter() - t0
         if t >= warmup:
             times.append(dt)
+            spent += dt
+            if spent > budget_s:
+                break
     O.FAST_CSR = False
     sec = statistics.median(times)
-    return {"value": B / sec, "unit": "cells/s", "cores": threads, "kind": "port",
-            "sample": f"{steps} steps (median) after {warmup} warm-up of the same workload (B={B}/step), "
+    return {"value": B / sec, "unit": "cells/s", "cores": threads, "kind": "port", "steps_run": len(times),
+            "sample": f"{len(times)} steps (median) after {warmup} warm-up of the same workload (B={B}/step), "
                       f"oracle port of the reference CPU step, torch {torch.__version__} fp32, {threads} threads",
             "ms_per_step": sec * 1e3}
+
+
+def cpu_reference_leg(config, B, steps, warmup, threads=None, budget_s=170.0):
+    """The reference's own CPU training step on this box's host cores: the UNMODIFIED reference package
+    (baseline/_ref, installed by tools/install_reference.sh) driven through CMMVAEModel.training_step
+    (kind "reference"); the oracle port (kind "port") only if that install is absent."""
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    from baseline import ref_arm
+    if not ref_arm.available():
+        return cpu_port_leg(config, B, steps, warmup, threads, budget_s)
+    r = ref_arm.time_reference_steps(Dims(config), config, B, steps, warmup, device="cpu", budget_s=budget_s,
+                                     density=DENSITY)
+    return {"value": r["value"], "unit": "cells/s", "cores": threads, "kind": "reference",
+            "steps_run": r["steps_run"], "ms_per_step": r["ms_per_step"], "last_loss": r["last_loss"],
+            "sample": f"{r['steps_run']} steps (median) after {warmup} warm-up of the same workload (B={B}/step): "
+                      f"unmodified reference CMMVAEModel.training_step (baseline/_ref) on torch.sparse_csr batches, "
+                      f"torch {torch.__version__} fp32 CPU, {threads} threads"}
+
+
+def torch_cuda_baseline(config, B, dev):
+    """SURVEY.md 8d / BASELINE.md 4.4: the reference's own GPU path on this box -- the unmodified reference
+    modules as stock PyTorch eager on ``cuda`` (cuSPARSE addmm, cuBLASLt GEMMs, to_dense + mse_loss, autograd,
+    clip_grad_norm_, torch.optim.Adam), fp32 and bf16 autocast.  The number every "beats" claim stands next to."""
+    from baseline import ref_arm
+    if not ref_arm.available():
+        return {"unavailable": "baseline/_ref not installed (tools/install_reference.sh)"}
+    out = {"how": "unmodified reference CMMVAEModel.training_step, stock PyTorch eager on cuda, "
+                  f"torch {torch.__version__}, B={B}, median of 8 steps after 3 warm-up, host-synchronised per step"}
+    for name, kw in (("fp32", {}), ("bf16_autocast", {"autocast": True})):
+        for dense in (False, True):
+            try:
+                r = ref_arm.time_reference_steps(Dims(config), config, B, 8, 3, device=str(dev), density=DENSITY,
+                                                 dense_input=dense, **kw)
+                out[name] = {k: r[k] for k in ("value", "ms_per_step", "last_loss", "input")}
+                break
+            except Exception as e:  # noqa: BLE001   (e.g. sparse-CSR addmm backward unsupported on cuda)
+                out[name] = {"error": f"{type(e).__name__}: {str(e)[:160]}", "input": "dense" if dense else "sparse_csr"}
+            finally:
+                torch.cuda.empty_cache()
+    return out
+
+
+def parity_check(model, eng, config, species, conds, host, metas_src, B, rank, world, dev):
+    """One extra training step outside every timed region, from the weights the benchmark has trained, on rank 0's
+    batch 0 with injected noise and dropout masks -- against ONE oracle step on the same state and inputs (rank 0).
+    The bench refuses to print a line whose arithmetic disagrees with the oracle."""
+    from mmvae_b200 import layers as L
+    model.flush_logs()
+    eng.finish()
+    s = list(species)[0]
+    G = species[s]
+    d = Dims(config)
+    P = {k[len("module."):]: v.detach().cpu().clone() for k, v in model.state_dict().items()}   # collective when world > 1
+    crow, col, val = host[s][0]
+    gen = torch.Generator().manual_seed(99 + rank)
+    eps = torch.randn(B, d.Z, generator=gen)
+    keep = [(torch.rand(B, n, generator=gen) >= 0.1) for n in (d.H1, d.H2)]
+    L.inject_noise(eps.to(dev))
+    L.inject_dropout_masks({f"experts.{s}.encoder.fc_layers.{j}.dr": k.to(torch.uint8).to(dev)
+                            for j, k in enumerate(keep)})
+    meta = metas_src[0]
+    x = torch.sparse_csr_tensor(*(torch.from_numpy(a).to(dev) for a in (crow, col, val)), size=(B, G))
+    was = model.sync_logging
+    model.sync_logging = True
+    model.logged_metrics.clear()
+    model.training_step((x, meta.copy(), s), 0)
+    model.sync_logging = was
+    got = {k.split("/")[0]: float(v) for k, v in model.logged_metrics.items()
+           if k.split("/")[0] in ("loss", "recon_loss", "kl_loss")}
+    if rank != 0:
+        return None
+    from oracle import cmmvae_oracle as O
+    O.FAST_CSR = True
+    labels = {c: torch.tensor([int(v.split("_")[-1]) for v in meta[c]], dtype=torch.int64) for c in conds} or None
+    ref = O.train_step(oracle_spec(config, species, dropout=0.1, conds=conds), P, {}, s, crow, col, val, eps, 1.0,
+                       labels=labels, return_grads=False,
+                       dropout_masks={f"experts.{s}.encoder.fc_layers.{j}.dr": k.float() for j, k in enumerate(keep)})
+    O.FAST_CSR = False
+    want = ref["logs"]
+    err = {k: abs(got[k] - want[k]) / max(abs(want[k]), 1e-30) for k in got}
+    tol = {"loss": 1e-3, "recon_loss": 1e-3, "kl_loss": 1e-2}
+    ok = all(err[k] <= tol[k] for k in err)
+    return {"ok": ok, "what": "one fused bf16 step vs one oracle step, same trained weights / batch / eps / dropout "
+                              "masks, outside the timed region", "loss_gpu": got["loss"], "loss_oracle": want["loss"],
+            "rel_err": err, "tol": tol}
 
 
 def main():
@@ -210,6 +323,11 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-torch-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--also-config3", type=int, default=None,
+                    help="extra leg: BASELINE configs[2] (two species + GRL adversaries, 4096 cells/GPU) at the same N; "
+                         "default on when N > 1")
     ap.add_argument("--e2e-diag", action="store_true", help="extra legs that split the end-to-end time")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -233,9 +351,11 @@ def main():
         if rank != 0:
             return
         cpu_B = min(B, 1024)
-        leg = cpu_reference_leg(args.config, cpu_B, max(1, min(args.steps, 3)), max(1, min(args.warmup, 1)))
+        leg = cpu_reference_leg(args.config, cpu_B, max(1, args.steps), max(0, args.warmup))
+        config = dict(config, reference_sample=f"each step = the same workload at {cpu_B} cells/step on the host cores")
         line = {"impl": "reference", "metric": METRIC, "value": leg["value"], "unit": "cells/s",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": leg["ms_per_step"],
+                "n_gpus": args.gpus, "steps": leg["steps_run"], "warmup": args.warmup,
+                "steps_requested": args.steps, "ms_per_step": leg["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": config, "cpu_baseline": leg,
                 "e2e": {"value": leg["value"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -248,8 +368,12 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         torch.set_num_threads(max(1, (os.cpu_count() or 8) // world))   # one launch thread per rank matters
-        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")   # keep stdout clean: the only stdout line is the JSON result
+        # NCCL's communicator lines (stderr) stay visible: the driver counts ranks from them
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         torch.distributed.init_process_group("nccl", device_id=dev)
+        if rank == 0:
+            print(f"[bench] NCCL communicator up: nranks={torch.distributed.get_world_size()}", file=sys.stderr)
     from mmvae_b200 import layers as L, ops
     import pandas as pd
     L.set_precision(args.precision)
@@ -257,14 +381,14 @@ def main():
     model.cuda().train()
     model.configure_optimizers()
     eng = model.engine()
-    eng.pipeline_optimizer = True   # single GPU: output-layer clip+Adam runs underneath the next forward pass
+    eng.pipeline_optimizer = True   # output-layer clip+Adam runs underneath the next forward pass
     names = list(species)
     NB = 4
     host = {s: synth_batches(NB, B, g, DENSITY, 1000 * (rank + 1)) for s, g in species.items()}
     resident = {s: [tuple(torch.from_numpy(a).to(dev) for a in b) for b in host[s]] for s in names}
     rng = np.random.default_rng(rank)
     metas = [pd.DataFrame({c: [f"{c}_{i}" for i in rng.integers(0, n, size=B)] for c, n in conds.items()})
-             for _ in range(NB)]
+             if conds else pd.DataFrame({"cell": np.arange(B)}) for _ in range(NB)]
     labels = [{c: torch.tensor([int(v.split("_")[-1]) for v in m[c]], dtype=torch.int64, device=dev) for c in conds}
               for m in metas] if conds else [None] * NB
 
@@ -273,9 +397,14 @@ def main():
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def resident_step(t):
+    def resident_batch(t):
         s = names[t % len(names)]
-        crow, col, val = resident[s][t % NB]
+        return (s,) + resident[s][t % NB]
+
+    def resident_step(t):
+        s, crow, col, val = resident_batch(t)
+        if world > 1:      # the exchange of the NEXT batch's CSR records runs underneath this step
+            eng.prefetch(*resident_batch(t + 1))
         eng.train_step(s, crow, col, val, int(col.numel()), 1.0, labels=labels[t % NB])
 
     # ---------------- device-resident throughput ----------------
@@ -307,7 +436,8 @@ def main():
     t_dw, t_dh, t_adam = eng.timer_ms("dWout_gemm"), eng.timer_ms("dh_gemm"), eng.timer_ms("norm+clip_adam")
     t_spbw = eng.timer_ms("csr_linear_bwd_w+bn")
     t_dp = {k: eng.timer_ms(k) for k in ("csr_prep", "mid_fwd", "mid_bwd", "dp_wait_shadow_first",
-                                         "dp_wait_shadow_rest", "dp_wait_grads")}
+                                         "dp_wait_shadow_rest", "dp_wait_grads", "dp_wait_Y", "dp_wait_h",
+                                         "dp_wait_dh") if eng.timers.get(k)}
     eng.timers = None
     if world > 1:
         tt = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -317,45 +447,42 @@ def main():
     value = B * world / (ms_per_step * 1e-3)
 
     # ---------------- end to end through the public API, host buffers ----------------
-    # host side of a step: the batch's three CSR arrays (numpy, as the reference's batcher emits them) go through
-    # mmvae_b200.feed.CSRStager -- packed into one pinned block, one async H2D copy on the copy stream
-    from mmvae_b200.feed import CSRStager
-    max_nnz = max(int(b[1].size) for s in names for b in host[s])
-    stager = CSRStager(max_cells=B, max_nnz=max_nnz, device=dev, depth=NB * len(names))
-    # the (synthetic) batcher has written each rotating batch into its pinned block once; a step ships its block
-    blocks = {}
-    for s in names:
-        for i, (crow, col, val) in enumerate(host[s]):
-            blk = stager.reserve(B, int(col.size))
-            blk.crow[:], blk.col[:], blk.val[:] = crow, col, val
-            blocks[(s, i)] = blk
+    # Host side of a step, all INSIDE the timed region: the reference's batcher semantics
+    # (SparseCSRMatrixBatcherDataPipe, cellxgene_datapipe.py:169-193) over pageable scipy CSR chunks ->
+    # mmvae_b200.feed.StagedCSRBatches packs each batch (native packer on worker threads, uint16 gene ids) into a
+    # pinned block, one async H2D copy on the copy stream -> CMMVAEModel.training_step on the torch.sparse_csr
+    # batch -> D2H read of the step's scalar block (one step late, so the copy never stalls the launch queue).
+    import scipy.sparse as sp
+    from mmvae_b200.feed import StagedCSRBatches
+    workers = max(1, min(6, (os.cpu_count() or 8) // world - 1))
 
-    def stage(t):
+    def chunk_source(s):
+        chunk = sp.vstack([sp.csr_matrix((v, c, r), shape=(B, species[s])) for r, c, v in host[s]], format="csr")
+        assert chunk.indices.dtype == np.int32 and chunk.data.dtype == np.float32 and chunk.has_sorted_indices
+        frame = pd.concat(metas, ignore_index=True)
+        while True:            # an endless epoch over the (pageable) chunk
+            yield chunk, frame
+
+    feeds = {s: StagedCSRBatches(chunk_source(s), B, device=dev, workers=workers) for s in names}
+    iters = {s: iter(f) for s, f in feeds.items()}
+
+    def api_step(t):
         s = names[t % len(names)]
-        return s, stager.commit(blocks[(s, t % NB)], species[s])
-
-    def api_step(t, staged):
-        s, ticket = staged
-        x = stager.get(ticket)
-        # every step ends with a D2H copy of its scalar block (loss, KL, norms) into pinned memory; with
-        # sync_logging off the host reads it one step later, so the copy never stalls the launch queue
-        model.training_step((x, metas[t % NB], s), t)
-        stager.release(ticket)
+        x, meta = next(iters[s])
+        if world > 1:
+            pass   # (the public API prefetches the next batch's exchange itself: see CMMVAEModel.training_step)
+        model.training_step((x, meta, s), t)
         v = model.logged_metrics.get(f"loss/training/{s}")
         return float(v) if v is not None else None
 
     model.sync_logging = False
-    nxt = stage(0)
     for t in range(max(args.warmup, 3)):
-        cur, nxt = nxt, stage(t + 1)
-        api_step(t, cur)
+        api_step(t)
     barrier()
-    t0 = time.perf_counter()
     e0.record()
     loss = None
     for t in range(args.steps):
-        cur, nxt = nxt, stage(t + 1 + max(args.warmup, 3))
-        loss = api_step(t, cur)
+        loss = api_step(t + max(args.warmup, 3))
     model.flush_logs()
     e1.record()
     barrier()
@@ -365,13 +492,14 @@ def main():
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
         e2e_ms = float(tt.item())
     clocks = sampler.stop() if rank == 0 else None
+    h2d = int(feeds[names[0]].stager.bytes_staged)
+    narrow = bool(feeds[names[0]].stager.narrow)
     diag = None
     if args.e2e_diag:
-        # where does the end-to-end leg lose time?  (a) the same API calls on batches already in HBM (no H2D);
-        # (b) the H2D copies alone (no compute)
+        # where does the end-to-end leg lose time?  (a) the same API calls on batches already in HBM (no H2D, no
+        # packing); (b) packing + H2D copies alone (no compute)
         def api_resident(t):
-            s = names[t % len(names)]
-            crow, col, val = resident[s][t % NB]
+            s, crow, col, val = resident_batch(t)
             model.training_step((torch.sparse_csr_tensor(crow, col, val, size=(B, species[s])), metas[t % NB], s), t)
         for t in range(3):
             api_resident(t)
@@ -384,35 +512,44 @@ def main():
         barrier()
         a_ms = e0.elapsed_time(e1) / args.steps
         barrier()
-        e0.record()
+        t0 = time.perf_counter()
         for t in range(args.steps):
-            _, tk = stage(t)
-            stager.arrays(tk)
-            stager.release(tk)
-        e1.record()
-        barrier()
-        c_ms = e0.elapsed_time(e1) / args.steps
+            next(iters[names[t % len(names)]])
+        torch.cuda.synchronize()
+        c_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         tt = torch.tensor([a_ms, c_ms], device=dev, dtype=torch.float64)
         if world > 1:
             torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
-        diag = {"api_resident_ms_per_step": float(tt[0]), "h2d_only_ms_per_step": float(tt[1]),
-                "h2d_only_gbs_per_gpu": stager.bytes_staged / (float(tt[1]) * 1e-3) / 1e9}
+        diag = {"api_resident_ms_per_step": float(tt[0]), "pack+h2d_only_ms_per_step": float(tt[1]),
+                "pack+h2d_only_gbs_per_gpu": h2d / (float(tt[1]) * 1e-3) / 1e9, "pack_workers": workers}
+    for f in feeds.values():
+        f.close()
     nnz = int(host[names[0]][0][1].size)
-    h2d = int(stager.bytes_staged)
     d2h = int(eng.last["sc"].numel()) * 8
+
+    parity = None
+    if not args.no_parity_check:
+        parity = parity_check(model, eng, args.config, species, conds, host, metas, B, rank, world, dev)
+
+    also = None
+    want_c3 = args.also_config3 if args.also_config3 is not None else int(world > 1 and args.config == 2)
+    if want_c3:
+        also = also_config3(rank, world, dev, min(args.steps, 40), max(3, min(args.warmup, 5)))
 
     if rank != 0:
         if world > 1:
             torch.distributed.destroy_process_group()
         return
+    if parity is not None and not parity["ok"]:
+        raise SystemExit(f"bench.py: the fused step disagrees with the oracle, no line printed: {json.dumps(parity)}")
     pk, pk_kind = peaks()
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this shape (ncu --set full)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_topk_dram_bytes.json")))
-        traffic = tj.get("decoder_mse_fused_kernel") if (B == 1024 and args.config == 2) else None
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_dram_bytes.json")))
+        traffic = tj.get(f"decoder_mse_fused_kernel@B{B}") if args.config == 2 else None
     except Exception:  # noqa: BLE001
         pass
-    flops = 2.0 * B * G_HUMAN * H1
+    flops = 2.0 * B * G_HUMAN * H1      # per rank and launch, also when the layer is gene-sharded (N*B cells x G/N genes)
     ach = flops / (t_dec * 1e-3) / 1e12 if t_dec > 0 else 0.0
     peak = pk["bf16_tflops_sustained"]
     spmm_bytes = nnz * 8 + (B + 1) * 4 + G_HUMAN * H1 * 2 + B * H1 * 4 + H1 * 4
@@ -422,7 +559,9 @@ def main():
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": config,
         "e2e": {"value": B * world / (e2e_ms / args.steps * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps, "last_loss": loss},
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps, "last_loss": loss,
+                "host_side": f"StagedCSRBatches over pageable scipy CSR chunks, {workers} packing threads inside the "
+                             f"timed region, gene ids on the wire: {'uint16' if narrow else 'int32'}"},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "decoder_mse_fused_kernel (K5-K7: tcgen05 GEMM + ReLU + sum-MSE-vs-CSR epilogue)",
                      "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
@@ -436,13 +575,72 @@ def main():
                  "fma_tflops": 2.0 * nnz * H1 / (t_spmm * 1e-3) / 1e12 if t_spmm > 0 else 0.0},
         "clocks": clocks,
     }
+    if parity is not None:
+        line["parity_check"] = parity
+    if also:
+        line["also"] = also
     if diag:
         line["e2e_diag"] = diag
+    if world == 1 and not args.no_torch_baseline:
+        line["torch_cuda_baseline"] = torch_cuda_baseline(args.config, B, dev)
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_reference_leg(args.config, min(B, 1024), 2, 1)
+        line["cpu_baseline"] = cpu_reference_leg(args.config, min(B, 1024), 8, 2, budget_s=25.0)
     print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def also_config3(rank, world, dev, steps, warmup):
+    """BASELINE configs[2] at the same N: two species + two GRL adversaries, 4096 cells per GPU per step,
+    device-resident cells/s (CUDA events, max over ranks).  Returned as a sub-record of the main line."""
+    import pandas as pd
+    model, species, conds = build_model(3)
+    model.cuda().train()
+    model.configure_optimizers()
+    eng = model.engine()
+    eng.pipeline_optimizer = True
+    B, NB = 4096, 2
+    names = list(species)
+    resident = {s: [tuple(torch.from_numpy(a).to(dev) for a in synth_csr(B, g, DENSITY, 5000 * (rank + 1) + i))
+                    for i in range(NB)] for s, g in species.items()}
+    rng = np.random.default_rng(rank)
+    labels = [{c: torch.from_numpy(rng.integers(0, n, size=B)).to(dev) for c, n in conds.items()} for _ in range(NB)]
+
+    def batch(t):
+        s = names[t % len(names)]
+        return (s,) + resident[s][(t // len(names)) % NB]
+
+    def step(t):
+        s, crow, col, val = batch(t)
+        if world > 1:
+            eng.prefetch(*batch(t + 1))
+        eng.train_step(s, crow, col, val, int(col.numel()), 1.0, labels=labels[t % NB])
+
+    for t in range(warmup):
+        step(t)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(steps):
+        step(warmup + t)
+    eng.finish()
+    e1.record()
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    tt = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+    ms = float(tt.item()) / steps
+    sc = eng.scalars()
+    del model, eng
+    torch.cuda.empty_cache()
+    return {"config3": {"workload": f"BASELINE configs[2]: two-species CMMVAE + 2 GRL adversaries, {B} cells/GPU/step, "
+                                    f"dp{world}, alternating human/mouse, device-resident",
+                        "value": B * world / (ms * 1e-3), "unit": "cells/s", "ms_per_step": ms, "steps": steps,
+                        "warmup": warmup, "n_gpus": world, "last_loss": sc["loss"]}}
 
 
 if __name__ == "__main__":

@@ -187,6 +187,19 @@ int cmmvae_transpose(const void* src, void* dst, int dtype, int R, int C, int ld
 /* a[i] += alpha * b[i] */
 int cmmvae_axpy(float* a, const float* b, float alpha, long long n, void* stream);
 
+
+/* ---- host -> HBM feed of CSR batches (batch format of cellxgene_datapipe.py:169-193) ---------
+ * HOST function (all pointers are host pointers): rows [lo, hi) of a CSR chunk -- what scipy's chunk[lo:hi]
+ * yields in SparseCSRMatrixBatcherDataPipe -- written into a (pinned) staging block: crow int32 rebased to 0,
+ * col as uint16 (col_u16 != 0, needs n_genes <= 65536) or int32, val fp32 bit for bit.  indptr / indices are
+ * int32 or int64 (width in bytes).  Returns the number of non-zeros, or < 0 (bad arguments / gene id out of
+ * range).  Thread safe; releases no locks, allocates nothing. */
+long long cmmvae_host_slice_rows(const void* indptr, int indptr_width, const void* indices, int indices_width,
+                                 const float* data, long long lo, long long hi, long long n_genes,
+                                 int32_t* crow_out, void* col_out, int col_u16, float* val_out);
+/* device: dst int32[n] = src uint16[n] (gene ids shipped narrow over PCIe, widened once they are in HBM) */
+int cmmvae_widen_u16_i32(const void* src_u16, int32_t* dst, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

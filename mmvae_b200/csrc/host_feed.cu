@@ -1,0 +1,96 @@
+// Host side of the CSR batch feed + the one device kernel it needs.
+//
+// cmmvae_host_slice_rows: rows [lo, hi) of a CSR chunk (what scipy's chunk[lo:hi] yields in the reference's
+// batcher, cellxgene_datapipe.py:173-183) written straight into a pinned staging block: crow rebased to 0,
+// gene ids narrowed to uint16 when the panel has <= 65536 genes (2 bytes less per non-zero on the PCIe wire;
+// the value stays fp32, bit for bit), values copied.  Plain C loops that the host compiler vectorises; called
+// through ctypes (which drops the GIL), so several batches are packed in parallel by worker threads.
+// cmmvae_widen_u16_i32: the device widens the ids back to the int32 col array every kernel consumes.
+#include <string.h>
+
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace cmmvae {
+__global__ void widen_u16_i32_kernel(const uint16_t* __restrict__ src, int32_t* __restrict__ dst, long long n) {
+  // 8 ids per thread: one 16-byte load, two 16-byte stores
+  const long long n8 = n / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    int4 a, b;
+    a.x = v.x & 0xFFFF; a.y = v.x >> 16; a.z = v.y & 0xFFFF; a.w = v.y >> 16;
+    b.x = v.z & 0xFFFF; b.y = v.z >> 16; b.z = v.w & 0xFFFF; b.w = v.w >> 16;
+    reinterpret_cast<int4*>(dst)[2 * i] = a;
+    reinterpret_cast<int4*>(dst)[2 * i + 1] = b;
+  }
+  for (long long i = n8 * 8 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+}  // namespace cmmvae
+
+using namespace cmmvae;
+
+extern "C" int cmmvae_widen_u16_i32(const void* src_u16, int32_t* dst, long long n, void* stream) {
+  if (n <= 0) return 0;
+  CMMVAE_REQUIRE((((uintptr_t)src_u16 | (uintptr_t)dst) & 15) == 0, "widen_u16_i32: buffers must be 16-byte aligned");
+  long long want = (n / 8 + 255) / 256 + 1;
+  const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
+  widen_u16_i32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)src_u16, dst, n);
+  return check_launch("widen_u16_i32");
+}
+
+template <typename I, typename O>
+static bool narrow_ids(const I* __restrict__ src, O* __restrict__ dst, long long n, long long n_genes) {
+  // unsigned max-reduction: negative ids wrap to huge values, so one compare after the loop validates the
+  // whole range and the loop body stays branch free (the host compiler vectorises it)
+  typedef typename std::make_unsigned<I>::type U;
+  U mx = 0;
+  for (long long i = 0; i < n; ++i) {
+    const U u = (U)src[i];
+    mx = u > mx ? u : mx;
+    dst[i] = (O)u;
+  }
+  return n == 0 || (unsigned long long)mx < (unsigned long long)n_genes;
+}
+
+template <typename P, typename I>
+static long long slice_rows_impl(const P* indptr, const I* indices, const float* data, long long lo, long long hi,
+                                 int32_t* crow_out, void* col_out, int col_u16, float* val_out, long long n_genes) {
+  const long long a = (long long)indptr[lo], b = (long long)indptr[hi], n = b - a;
+  for (long long r = lo; r <= hi; ++r) crow_out[r - lo] = (int32_t)((long long)indptr[r] - a);
+  const bool ok = col_u16 ? narrow_ids(indices + a, (uint16_t*)col_out, n, n_genes)
+                          : narrow_ids(indices + a, (int32_t*)col_out, n, n_genes);
+  memcpy(val_out, data + a, sizeof(float) * (size_t)n);
+  return ok ? n : -1;
+}
+
+// all pointers are HOST pointers.  indptr/indices are int32 (width 4) or int64 (width 8), data is float32.
+// Returns the number of non-zeros written, or a negative code (out-of-range gene id / bad arguments).
+extern "C" long long cmmvae_host_slice_rows(const void* indptr, int indptr_width, const void* indices,
+                                            int indices_width, const float* data, long long lo, long long hi,
+                                            long long n_genes, int32_t* crow_out, void* col_out, int col_u16,
+                                            float* val_out) {
+  if (!indptr || !indices || !data || !crow_out || !col_out || !val_out || lo < 0 || hi < lo ||
+      (col_u16 && n_genes > 65536)) {
+    set_error("host_slice_rows: bad arguments");
+    return -2;
+  }
+  long long n;
+  if (indptr_width == 4 && indices_width == 4)
+    n = slice_rows_impl((const int32_t*)indptr, (const int32_t*)indices, data, lo, hi, crow_out, col_out, col_u16, val_out, n_genes);
+  else if (indptr_width == 8 && indices_width == 8)
+    n = slice_rows_impl((const int64_t*)indptr, (const int64_t*)indices, data, lo, hi, crow_out, col_out, col_u16, val_out, n_genes);
+  else if (indptr_width == 8 && indices_width == 4)
+    n = slice_rows_impl((const int64_t*)indptr, (const int32_t*)indices, data, lo, hi, crow_out, col_out, col_u16, val_out, n_genes);
+  else if (indptr_width == 4 && indices_width == 8)
+    n = slice_rows_impl((const int32_t*)indptr, (const int64_t*)indices, data, lo, hi, crow_out, col_out, col_u16, val_out, n_genes);
+  else {
+    set_error("host_slice_rows: index width must be 4 or 8 bytes");
+    return -2;
+  }
+  if (n < 0) set_error("host_slice_rows: gene id outside [0, %lld)", n_genes);
+  return n;
+}

@@ -139,6 +139,7 @@ class FlatGroup:
         self.m = torch.zeros(mv, device=device, dtype=torch.float32)
         self.v = torch.zeros(mv, device=device, dtype=torch.float32)
         self.step_count = 0
+        self.applied = False    # set by the fused step after its own clip+Adam launch; consumed by FlatAdam.step()
         self._vec_range: Optional[tuple] = None
         self._deferred: Optional[torch.cuda.Event] = None   # output-layer update in flight on the background stream
         self.first_by_inputs = False   # set per step by the engine when gs[0] was produced from gathered inputs
@@ -224,6 +225,7 @@ class FlatGroup:
         layer, which the next forward pass reads last) is updated on that low-priority stream, after everything
         else, so the update runs underneath the next step's forward; ``wait_shadow("rest")`` joins it."""
         self.step_count += 1
+        self.applied = True
         self._ag_pending = []
         hyper = (self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.step_count)
         if background is not None and not self.sharded and len(self.seg_bounds) >= 2:
@@ -268,6 +270,34 @@ class FlatGroup:
             torch.cuda.current_stream().wait_event(self._deferred)
             self._deferred = None
 
+    def logical(self, p: nn.Parameter, buf: torch.Tensor) -> torch.Tensor:
+        """view of ``buf`` (laid out like the value buffer) with parameter ``p``'s logical shape"""
+        t = self.phys(p, buf)
+        return t.t() if self.transposed[id(p)] else t
+
+    def full_moments(self):
+        """Adam moments laid out like the value buffer (``[n]`` each).  Single process: the live buffers.
+        ZeRO-sharded: fresh full-size copies, the sharded segments all-gathered from their owners."""
+        if not self.sharded:
+            return self.m, self.v
+        out = []
+        for src in (self.m, self.v):
+            full = torch.zeros(self.n, device=src.device, dtype=torch.float32)
+            for (lo, hi), (own_lo, own_hi, _, mv) in zip(self.seg_bounds, self.ranges):
+                torch.distributed.all_gather_into_tensor(full[lo:hi], src[mv:mv + own_hi - own_lo].contiguous())
+            _, _, _, mv = self.ranges[-1]
+            full[self.tail_lo:self.n].copy_(src[mv:mv + self.n - self.tail_lo])
+            out.append(full)
+        return out
+
+    def store_moments(self, m_full: torch.Tensor, v_full: torch.Tensor):
+        """inverse of ``full_moments`` (no-op single process: the views were written in place)"""
+        if not self.sharded:
+            return
+        for src, dst in ((m_full, self.m), (v_full, self.v)):
+            for (own_lo, own_hi, _, mv) in self.ranges:
+                dst[mv:mv + own_hi - own_lo].copy_(src[own_lo:own_hi])
+
     def sync_master(self):
         """all-gather the fp32 master copy of the sharded segments (before state_dict / fp32 evaluation)"""
         if not self.sharded:
@@ -281,7 +311,15 @@ class FlatGroup:
 class FlatAdam(torch.optim.Optimizer):
     """``torch.optim.Optimizer`` face of a ``FlatGroup`` (what ``configure_optimizers`` returns, one per
     reference optimizer: Adam(lr=5e-3, weight_decay=1e-6), cmmvae_model.py:306-319).  ``step`` runs the
-    fused clip+Adam launch; a clip value set through ``set_clip`` is applied inside that launch."""
+    fused clip+Adam launch; a clip value set through ``set_clip`` is applied inside that launch.
+
+    The fused ``training_step`` launches clip+Adam itself and then calls ``step()`` on the (Lightning-wrapped)
+    optimizers it updated: the group is marked ``applied`` and ``step`` only consumes the mark, so Lightning's
+    progress tracking (``trainer.global_step``, ``max_steps``, step-based checkpoints) advances exactly as
+    with the reference's ``optimizer.step()`` calls, without a second update.
+
+    ``state_dict`` / ``load_state_dict`` speak torch.optim.Adam's format (``step``, ``exp_avg``,
+    ``exp_avg_sq`` per parameter, in the parameter's logical shape), so checkpoints resume with their moments."""
 
     def __init__(self, group: FlatGroup):
         self.flat = group
@@ -293,15 +331,56 @@ class FlatAdam(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None):
+        if self.flat.applied:
+            self.flat.applied = False
+            return
         if self.flat.world > 1:
             raise NotImplementedError("with torch.distributed the exchange + step run inside training_step")
         ns = torch.zeros(1, dtype=torch.float64, device=self.flat.p.device)
         self.flat.grad_norm_sq(ns)
         self.flat.clip_adam(ns, self._max_norm)
+        self.flat.applied = False
         self._max_norm = None
 
     def zero_grad(self, set_to_none: bool = True):
         self.flat.g.zero_()
+
+    # ---- checkpoint format of torch.optim.Adam ----
+    def state_dict(self):
+        g = self.flat
+        m_full, v_full = g.full_moments()
+        state = {}
+        if g.step_count > 0:
+            for i, p in enumerate(g.params):
+                state[i] = {"step": torch.tensor(float(g.step_count)),
+                            "exp_avg": g.logical(p, m_full).clone(), "exp_avg_sq": g.logical(p, v_full).clone()}
+        pg = dict(self.param_groups[0])
+        pg["params"] = list(range(len(g.params)))
+        return {"state": state, "param_groups": [pg]}
+
+    def load_state_dict(self, sd):
+        g = self.flat
+        state = sd.get("state", {})
+        m_full, v_full = g.full_moments()
+        steps = set()
+        for i, p in enumerate(g.params):
+            st = state.get(i, state.get(str(i)))
+            if st is None:
+                g.logical(p, m_full).zero_()
+                g.logical(p, v_full).zero_()
+                continue
+            g.logical(p, m_full).copy_(st["exp_avg"])
+            g.logical(p, v_full).copy_(st["exp_avg_sq"])
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"FlatAdam steps a whole group together; checkpoint holds steps {sorted(steps)}")
+        g.step_count = steps.pop() if steps else 0
+        g.store_moments(m_full, v_full)
+        for k, v in (sd.get("param_groups") or [{}])[0].items():
+            if k in ("lr", "weight_decay", "betas", "eps"):
+                self.param_groups[0][k] = v
+        pg = self.param_groups[0]
+        g.lr, g.wd, g.betas, g.eps = pg["lr"], pg["weight_decay"], tuple(pg["betas"]), pg["eps"]
 
 
 @dataclass
@@ -441,6 +520,11 @@ class StepEngine:
             raise UnsupportedTopology("VAE has parameters outside encoder/decoder")
         gv = self.groups["vae"] = FlatGroup("vae", chains, dev)
         self.vaeenc_plan = _plan_block(enc.fc, gv)
+        for lp in self.vaeenc_plan:
+            # the reference hands the adversary the activation right after ``af``, BEFORE ``dr``
+            # (components.py:309-313); the fused step takes the layer output, so the two only agree without dropout
+            if lp.return_hidden and lp.relu and lp.p_drop > 0:
+                raise UnsupportedTopology("return_hidden on a VAE-encoder layer with dropout is outside the fused step")
         self.vaedec_plan = _plan_block(vae.decoder, gv)
         self.Z = enc.mean_encoder.out_features
         self.Hv = enc.mean_encoder.in_features
@@ -495,6 +579,16 @@ class StepEngine:
         if t is None:
             t = self._ws[key] = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
         return t
+
+    def ws_cap(self, name: str, n: int, dtype=torch.float32) -> torch.Tensor:
+        """1-D workspace whose length follows the batch (``nnz``-sized buffers): ONE buffer per name, grown with
+        25 % headroom when a batch needs more than any before it, handed out as a ``[:n]`` view -- real batches
+        almost never repeat an nnz, so keying by exact shape would allocate (and keep) a new buffer every step"""
+        key = (name, "cap", dtype)
+        t = self._ws.get(key)
+        if t is None or t.numel() < n:
+            t = self._ws[key] = torch.empty(max(int(n * 1.25) + 1024, 1024), dtype=dtype, device=self.device)
+        return t[:n]
 
     def _t0(self, name):
         if self.timers is None or (self.timer_filter is not None and name not in self.timer_filter):
@@ -757,6 +851,11 @@ class StepEngine:
         with ops.stream_scope(torch.cuda.current_stream()):
             return self._train_step(expert_id, crow, col, val, nnz, kl_weight, eps, labels, masks)
 
+    def prefetch(self, expert_id: str, crow, col, val):
+        """data parallel: start exchanging the NEXT batch's CSR records while the current step runs (no-op with
+        one process).  ``train_step`` on the same arrays then finds its gathered inputs ready."""
+        return None
+
     def finish(self):
         """join optimizer work still in flight on the background stream (call before reading weights outside
         the engine when ``pipeline_optimizer`` is on; ``state_dict``/evaluation do it themselves)"""
@@ -765,6 +864,11 @@ class StepEngine:
 
     def _train_step(self, expert_id, crow, col, val, nnz, kl_weight, eps, labels, masks):
         dev = self.device
+        if masks is None:
+            injected = L.draw_dropout_masks()
+            if injected is not None:    # keyed by the reference's module paths -> engine layer tags
+                masks = {L.dropout_tag(k): v for k, v in injected.items() if k.split(".")[0] != "experts"
+                         or k.split(".")[1] == expert_id}
         enc, dec = self.enc_plan[expert_id], self.dec_plan[expert_id]
         B = crow.numel() - 1
         G = enc[0].K
@@ -808,7 +912,7 @@ class StepEngine:
                 n_packed = self._dp_capacity(n_packed, B)
             tp = ops.csr_tile_ptr(crow, col, val, G_tp, nnz,
                                   self.ws("tp64", (B * ((G_tp + 63) // 64 + 1),), torch.int32),
-                                  self.ws("packed", (n_packed,), torch.int32))
+                                  self.ws_cap("packed", n_packed, torch.int32))
             if by_inputs:
                 gathered = self._dp_gather_csr(gexp, tp, B, n_packed)
         self._t1(ev)
@@ -951,8 +1055,8 @@ class StepEngine:
             csc = ("tc", tp, G, s_norm(1) if fuse_norm else None, pending, gathered)
         else:
             cptr, ridx, cval = ops.csr_transpose(crow, col, val, G, nnz, self.ws("cptr", (G + 1,), torch.int32),
-                                                 self.ws("ridx", (max(nnz, 1),), torch.int32),
-                                                 self.ws("cval", (max(nnz, 1),)),
+                                                 self.ws_cap("ridx", max(nnz, 1), torch.int32),
+                                                 self.ws_cap("cval", max(nnz, 1)),
                                                  self.ws("cursor", (G + 1,), torch.int32))
             csc = ("gather", cptr, ridx, cval, G)
         for j in reversed(range(len(enc))):

@@ -20,9 +20,18 @@ device bit-identical, int32 / fp32 exactly as scipy emitted them.
 
 A slot is reused ``depth`` puts later; ``put`` first waits (host side) for the event recorded by the
 consumer of that slot's previous occupant, so an in-flight step never sees its input overwritten.
+
+``narrow_col=True`` (gene panels of <= 65 536 genes): the pinned block holds the gene ids as uint16 -- 6 instead
+of 8 bytes per non-zero over PCIe -- and a widening kernel on the copy stream restores the int32 ``col`` array
+in HBM right behind the copy (exact: ids are < 65 536), so consumers still see int32 / fp32.
+
+``StagedCSRBatches(..., workers=k)`` packs batches on ``k`` background threads with the native packer
+(``cmmvae_host_slice_rows``: no GIL, no intermediate arrays), several batches ahead of the consumer.
 """
 from __future__ import annotations
 
+import collections
+import concurrent.futures
 from dataclasses import dataclass
 from typing import Optional
 
@@ -34,11 +43,11 @@ def _align(n: int, a: int = 16) -> int:
     return (n + a - 1) // a * a
 
 
-def block_layout(n_cells: int, nnz: int):
+def block_layout(n_cells: int, nnz: int, col_bytes: int = 4):
     """byte offsets of (crow, col, val) inside one staged block and the block's size"""
     o_crow = 0
     o_col = _align(o_crow + 4 * (n_cells + 1))
-    o_val = _align(o_col + 4 * nnz)
+    o_val = _align(o_col + col_bytes * nnz)
     return o_crow, o_col, o_val, _align(o_val + 4 * nnz)
 
 
@@ -50,7 +59,8 @@ def slice_rows(indptr: np.ndarray, indices: np.ndarray, data: np.ndarray, lo: in
     a, b = int(indptr[lo]), int(indptr[hi])
     if out is not None:
         np.subtract(indptr[lo:hi + 1], indptr[lo], out=out.crow, casting="unsafe")
-        out.col[:], out.val[:] = indices[a:b], data[a:b]
+        np.copyto(out.col, indices[a:b], casting="unsafe")     # int32, or uint16 in a narrow block
+        out.val[:] = data[a:b]
         return out.crow, out.col, out.val
     crow = (indptr[lo:hi + 1] - indptr[lo]).astype(np.int32, copy=False)
     return crow, indices[a:b].astype(np.int32, copy=False), data[a:b].astype(np.float32, copy=False)
@@ -76,17 +86,22 @@ class Block:
 
 
 class CSRStager:
-    def __init__(self, max_cells: int, max_nnz: int, device="cuda", depth: int = 3):
+    def __init__(self, max_cells: int, max_nnz: int, device="cuda", depth: int = 3, narrow_col: bool = False):
         if depth < 2:
             raise ValueError("CSRStager needs depth >= 2 (one block in flight, one being filled)")
         self.device = torch.device(device)
         self.max_cells, self.max_nnz, self.depth = int(max_cells), int(max_nnz), int(depth)
-        self.nbytes = block_layout(self.max_cells, self.max_nnz)[3]
+        self.narrow = bool(narrow_col)
+        self.col_bytes = 2 if self.narrow else 4
+        self.nbytes = block_layout(self.max_cells, self.max_nnz, self.col_bytes)[3]
         self.on_gpu = self.device.type == "cuda"
         if self.on_gpu and not torch.cuda.is_available():
             raise RuntimeError("CSRStager(device='cuda') needs a CUDA device")
         self.host = [torch.empty(self.nbytes, dtype=torch.uint8, pin_memory=self.on_gpu) for _ in range(depth)]
         self.dev = [torch.empty(self.nbytes, dtype=torch.uint8, device=self.device) for _ in range(depth)]
+        # narrow blocks: the int32 col array the kernels read, widened on the device behind each copy
+        self.col32 = [torch.empty(self.max_nnz + 8, dtype=torch.int32, device=self.device) for _ in range(depth)] \
+            if self.narrow else None
         self.stream = torch.cuda.Stream(self.device) if self.on_gpu else None
         self._consumed = [None] * depth     # event: the step that read this slot has been enqueued and finished
         self._copied = [None] * depth       # event: the H2D copy out of the pinned block has finished
@@ -104,10 +119,11 @@ class CSRStager:
         self._n += 1
         if self._copied[slot] is not None:
             self._copied[slot].synchronize()      # the pinned block is free once its copy has left
-        o_crow, o_col, o_val, _ = block_layout(n_cells, nnz)
+        o_crow, o_col, o_val, _ = block_layout(n_cells, nnz, self.col_bytes)
         h = self.host[slot].numpy()
         return Block(slot, n_cells, nnz,
-                     h[o_crow:o_crow + 4 * (n_cells + 1)].view(np.int32), h[o_col:o_col + 4 * nnz].view(np.int32),
+                     h[o_crow:o_crow + 4 * (n_cells + 1)].view(np.int32),
+                     h[o_col:o_col + self.col_bytes * nnz].view(np.uint16 if self.narrow else np.int32),
                      h[o_val:o_val + 4 * nnz].view(np.float32))
 
     def commit(self, b: "Block", n_genes: int) -> Ticket:
@@ -115,16 +131,23 @@ class CSRStager:
         (unchanged) as long as it has not been handed out by a later ``reserve``"""
         if b.n_cells >= 0 and (int(b.crow[0]) != 0 or int(b.crow[-1]) != b.nnz):
             raise ValueError("inconsistent CSR arrays (crow[0] must be 0, crow[-1] == len(col) == len(val))")
-        used = block_layout(b.n_cells, b.nnz)[3]
+        o_crow, o_col, o_val, used = block_layout(b.n_cells, b.nnz, self.col_bytes)
+        if self.narrow and int(n_genes) > 65536:
+            raise ValueError(f"narrow_col stages 16-bit gene ids; the panel has {n_genes} genes")
         self.bytes_staged = used
         slot = b.slot
         if not self.on_gpu:
             self.dev[slot][:used].copy_(self.host[slot][:used])
+            if self.narrow:
+                self.col32[slot][:b.nnz].copy_(self.dev[slot][o_col:o_col + 2 * b.nnz].view(torch.uint16).to(torch.int32))
             return Ticket(slot, b.n_cells, int(n_genes), b.nnz, None)
         with torch.cuda.stream(self.stream):
             if self._consumed[slot] is not None:
                 self.stream.wait_event(self._consumed[slot])    # do not overwrite a block a step still reads
             self.dev[slot][:used].copy_(self.host[slot][:used], non_blocking=True)
+            if self.narrow:
+                from . import ops
+                ops.widen_u16_i32(self.dev[slot][o_col:], self.col32[slot], b.nnz, stream=self.stream)
             ev = torch.cuda.Event()
             ev.record(self.stream)
         self._copied[slot] = ev
@@ -138,8 +161,11 @@ class CSRStager:
             raise ValueError("inconsistent CSR arrays (crow[0] must be 0, crow[-1] == len(col) == len(val))")
         if nnz and int(col.max()) >= 2 ** 31:
             raise ValueError("CSR indices do not fit int32")
+        if self.narrow and nnz and int(col.max()) >= 65536:
+            raise ValueError("narrow_col stages 16-bit gene ids")
         b = self.reserve(n_cells, nnz)
-        b.crow[:], b.col[:], b.val[:] = crow, col, val      # casts int64 -> int32 / f64 -> f32 on the way in
+        b.crow[:], b.val[:] = crow, val      # casts int64 -> int32 / f64 -> f32 on the way in
+        np.copyto(b.col, col, casting="unsafe")
         return self.commit(b, n_genes)
 
     # ------------------------------------------------------------------------------------------ get
@@ -148,10 +174,10 @@ class CSRStager:
         current stream waits for the copy"""
         if t.ready is not None:
             torch.cuda.current_stream(self.device).wait_event(t.ready)
-        o_crow, o_col, o_val, _ = block_layout(t.n_cells, t.nnz)
+        o_crow, o_col, o_val, _ = block_layout(t.n_cells, t.nnz, self.col_bytes)
         d = self.dev[t.slot]
         crow = d[o_crow:o_crow + 4 * (t.n_cells + 1)].view(torch.int32)
-        col = d[o_col:o_col + 4 * t.nnz].view(torch.int32)
+        col = self.col32[t.slot][:t.nnz] if self.narrow else d[o_col:o_col + 4 * t.nnz].view(torch.int32)
         val = d[o_val:o_val + 4 * t.nnz].view(torch.float32)
         return crow, col, val
 
@@ -170,7 +196,7 @@ class CSRStager:
 
 
 class StagedCSRBatches:
-    """Batches of a chunked CSR dataset, staged one batch ahead.
+    """Batches of a chunked CSR dataset, staged ahead of the consumer.
 
     Iterates like the reference's ``SparseCSRMatrixBatcherDataPipe`` (data/local/cellxgene_datapipe.py:125-193):
     ``source`` yields ``(scipy.sparse.csr_matrix chunk, pandas.DataFrame)`` pairs (what ``LoadCSRMatrixAndDataFrame``
@@ -179,54 +205,95 @@ class StagedCSRBatches:
     is ``frame.iloc[i:i+batch_size].reset_index(drop=True)``, and each item is ``(torch.sparse_csr_tensor, metadata)``.
 
     Difference: rows are never materialised as a scipy slice -- they are written straight from the chunk's
-    ``indptr / indices / data`` into a pinned ``CSRStager`` block, shipped with one asynchronous copy while the
-    previous batch is being consumed, and the yielded tensor lives on ``device``.  The block of a batch is
+    ``indptr / indices / data`` into a pinned ``CSRStager`` block, shipped with one asynchronous copy while
+    earlier batches are being consumed, and the yielded tensor lives on ``device``.  The block of a batch is
     recycled once the consumer asks for the next item, i.e. after it has enqueued its work on the current stream.
-    """
 
-    def __init__(self, source, batch_size: int, allow_partials: bool = False, device="cuda", depth: int = 3):
+    ``workers`` > 0: packing (a 25 MB gather out of pageable memory per 1024-cell batch -- longer than the
+    training step itself on one core) runs on that many background threads through the native packer,
+    ``ahead`` batches in front of the consumer; batches are still yielded in order.  ``workers`` = 0 packs on
+    the consumer's thread with numpy, one batch ahead.  ``narrow_col``: ship gene ids as uint16 (None = whenever
+    the chunk has <= 65 536 genes)."""
+
+    def __init__(self, source, batch_size: int, allow_partials: bool = False, device="cuda", depth: int = 3,
+                 workers: int = 0, ahead: Optional[int] = None, narrow_col: Optional[bool] = None):
         if batch_size <= 0:
             raise ValueError("batch_size must be positive")
+        self.workers = int(workers)
+        self.ahead = int(ahead) if ahead is not None else max(1, 2 * self.workers)
         if depth < 3:
             raise ValueError("StagedCSRBatches needs depth >= 3 (consumed, staged ahead, being filled)")
+        depth = max(int(depth), self.ahead + 2)
         self.source, self.batch_size, self.allow_partials = source, int(batch_size), bool(allow_partials)
-        self.device, self.depth = device, int(depth)
+        self.device, self.depth, self.narrow_col = device, depth, narrow_col
         self.stager: Optional[CSRStager] = None
+        self._pool = None
 
-    def _ensure_capacity(self, nnz: int):
-        if self.stager is None or nnz > self.stager.max_nnz:
+    def _ensure_capacity(self, nnz: int, n_genes: int):
+        narrow = self.narrow_col if self.narrow_col is not None else n_genes <= 65536
+        if self.stager is None or nnz > self.stager.max_nnz or narrow != self.stager.narrow:
             # a denser batch than any seen so far: new ring with head room (old blocks stay alive with the
             # tickets that reference them until their consumers are done)
-            self.stager = CSRStager(self.batch_size, int(nnz * 1.25) + 1024, device=self.device, depth=self.depth)
+            self.stager = CSRStager(self.batch_size, int(nnz * 1.25) + 1024, device=self.device, depth=self.depth,
+                                    narrow_col=narrow)
 
-    def __iter__(self):
-        ahead = None                      # (stager, ticket, metadata) committed but not yet handed out
-        done = None                       # (stager, ticket) handed out on the previous iteration
+    def _tasks(self):
         for chunk, frame in self.source:
-            indptr, indices, data = chunk.indptr, chunk.indices, chunk.data
             n_rows, n_genes = chunk.shape
             for lo in range(0, n_rows, self.batch_size):
                 hi = min(lo + self.batch_size, n_rows)
                 if hi - lo != self.batch_size and not self.allow_partials:
                     continue
-                nnz = int(indptr[hi]) - int(indptr[lo])
-                self._ensure_capacity(nnz)
-                blk = self.stager.reserve(hi - lo, nnz)
-                slice_rows(indptr, indices, data, lo, hi, out=blk)
-                ticket = self.stager.commit(blk, n_genes)
-                meta = frame.iloc[lo:hi].reset_index(drop=True) if frame is not None else None
-                if ahead is not None:
-                    if done is not None:
-                        done[0].release(done[1])
-                    st, tk, md = ahead
-                    done = (st, tk)
-                    yield st.get(tk), md
-                ahead = (self.stager, ticket, meta)
-        if ahead is not None:
+                yield chunk, frame, lo, hi, n_genes
+
+    @staticmethod
+    def _pack(stager: "CSRStager", blk: "Block", chunk, lo: int, hi: int, n_genes: int, native: bool) -> Ticket:
+        indptr, indices, data = chunk.indptr, chunk.indices, chunk.data
+        if native and data.dtype == np.float32 and indices.dtype in (np.int32, np.int64) \
+                and indptr.dtype in (np.int32, np.int64):
+            from . import ops
+            if stager.on_gpu:
+                torch.cuda.set_device(stager.device)     # worker threads start on device 0
+            ops.host_slice_rows(indptr, indices, data, lo, hi, n_genes, blk.crow, blk.col, blk.val)
+        else:
+            slice_rows(indptr, indices, data, lo, hi, out=blk)
+        return stager.commit(blk, n_genes)
+
+    def __iter__(self):
+        if self.workers > 0 and self._pool is None:
+            self._pool = concurrent.futures.ThreadPoolExecutor(self.workers, thread_name_prefix="csr-pack")
+        inflight = collections.deque()    # (stager, ticket or future, metadata), in batch order
+        done = None                       # (stager, ticket) handed out on the previous iteration
+
+        def hand_out():
+            nonlocal done
+            st, tk, md = inflight.popleft()
+            if isinstance(tk, concurrent.futures.Future):
+                tk = tk.result()
             if done is not None:
                 done[0].release(done[1])
-            st, tk, md = ahead
             done = (st, tk)
-            yield st.get(tk), md
+            return st.get(tk), md
+
+        for chunk, frame, lo, hi, n_genes in self._tasks():
+            nnz = int(chunk.indptr[hi]) - int(chunk.indptr[lo])
+            self._ensure_capacity(nnz, n_genes)
+            if len(inflight) > self.ahead - 1:     # keep at most ``ahead`` batches staged in front of the consumer
+                yield hand_out()
+            st = self.stager
+            blk = st.reserve(hi - lo, nnz)         # slots are handed out in batch order, on this thread
+            meta = frame.iloc[lo:hi].reset_index(drop=True) if frame is not None else None
+            if self._pool is not None:
+                tk = self._pool.submit(self._pack, st, blk, chunk, lo, hi, n_genes, True)
+            else:
+                tk = self._pack(st, blk, chunk, lo, hi, n_genes, False)
+            inflight.append((st, tk, meta))
+        while inflight:
+            yield hand_out()
         if done is not None:
             done[0].release(done[1])
+
+    def close(self):
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None

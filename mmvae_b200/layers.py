@@ -50,6 +50,38 @@ def draw_noise(B: int, Z: int, device) -> torch.Tensor:
     return torch.randn(B, Z, device=device, dtype=torch.float32)
 
 
+# ---- dropout masks (parity runs) -----------------------------------------------------------------
+_mask_queue = collections.deque()
+
+
+def inject_dropout_masks(masks: dict) -> None:
+    """Queue keep-masks (uint8 CUDA tensors, 1 = keep) for the next fused training step, keyed by the
+    reference's sub-module path of the dropout layer (``experts.human.encoder.fc_layers.0.dr`` ...).  CPU and
+    GPU generators cannot be bit-matched, so parity runs inject the masks the oracle used (SURVEY.md 7.5);
+    without injection the kernels draw their own counter-based Bernoulli mask."""
+    _mask_queue.append(masks)
+
+
+def draw_dropout_masks():
+    return _mask_queue.popleft() if _mask_queue else None
+
+
+def dropout_tag(path: str):
+    """engine layer tag of a reference dropout sub-module path (None if it is not part of the fused step)"""
+    parts = path.split(".")
+    try:
+        j = int(parts[parts.index("fc_layers") + 1])
+    except (ValueError, IndexError):
+        return None
+    if parts[0] == "experts":
+        return f"{'enc' if parts[2] == 'encoder' else 'dec'}{j}"
+    if parts[:2] == ["vae", "encoder"]:
+        return f"venc{j}"
+    if parts[:2] == ["vae", "decoder"]:
+        return f"vdec{j}"
+    return None
+
+
 # ---- helpers -----------------------------------------------------------------------------------
 def _require_cuda(t: torch.Tensor, what: str):
     if not t.is_cuda:

@@ -55,7 +55,7 @@ class CMMVAEModel(BaseModel):
         # and logged at the NEXT training_step (or flush_logs()), so the host never waits for the GPU.
         self.sync_logging = True
         self._pending_log = None
-        self._label_ring, self._label_slot = {}, 0
+        self._label_ring = {}    # (n conditions, B) -> [pinned blocks, events of their last copy, next slot]
 
     # ------------------------------------------------------------------------------------ engine
     @staticmethod
@@ -98,6 +98,8 @@ class CMMVAEModel(BaseModel):
                                           for i in range(1, len(self.module.adversarials) + 1)}
         optimizers = []
         self.optimizer_map = convert_to_flat_list_and_map(optim_dict, optimizers)
+        if hasattr(self, "_opt_cache"):      # stand-in LightningModule: what ``self.optimizers()`` hands out
+            self._opt_cache = optimizers
         return optimizers
 
     def _configure_optimizers_module_route(self):
@@ -129,6 +131,30 @@ class CMMVAEModel(BaseModel):
                 g.sync_master()
         return super().state_dict(*args, **kwargs)
 
+    def load_state_dict(self, state_dict, *args, **kwargs):
+        """values land in the flat fp32 buffers (the parameters are views of them); the bf16 shadows the
+        kernels read are re-derived right away, so a reload before evaluation / resume never runs stale weights"""
+        if self._engine:
+            self._engine.finish()
+        out = super().load_state_dict(state_dict, *args, **kwargs)
+        if self._engine:
+            for g in self._engine.groups.values():
+                g.refresh_shadow()
+        return out
+
+    def _mark_stepped(self, expert_id: str, n_adv: int):
+        """The fused step has already applied clip+Adam.  Call ``step()`` on the optimizers the reference steps
+        in this batch (cmmvae_model.py:130,211-212: each adversary, then vae, then the expert) so Lightning's
+        manual-optimization progress (``trainer.global_step``) advances as it does for the reference;
+        ``FlatAdam.step`` sees the group's ``applied`` mark and does not update twice."""
+        opts = self.get_optimizers()
+        stepped = [o for _, o in zip(range(n_adv), (opts.get("adversarials") or {}).values())]
+        stepped += [opts["vae"], opts["experts"][expert_id]]
+        for o in stepped:
+            o.step()
+        if hasattr(self.trainer, "set_stage"):     # the stand-in trainer counts optimizer steps like Lightning
+            self.trainer.global_step += len(stepped)
+
     # ------------------------------------------------------------------------------------- steps
     def _labels(self, metadata: pd.DataFrame, device):
         """int64 class ids per condition: row index of each value in the human csv (class-level
@@ -152,13 +178,20 @@ class CMMVAEModel(BaseModel):
             t = torch.from_numpy(block).to(dev)
         else:
             # a small ring of pinned blocks: the copy is asynchronous and a block is not refilled while in flight
-            ring = self._label_ring.setdefault((len(tables), B), [])
-            if len(ring) < 4:
-                ring.append(torch.empty((len(tables), B), dtype=torch.int64, pin_memory=True))
-            self._label_slot = (self._label_slot + 1) % 4
-            pin = ring[self._label_slot % len(ring)]
-            pin.numpy()[...] = block
-            t = pin.to(dev, non_blocking=True)
+            # (one ring per block shape; a block is refilled only after the copy that last read it has finished)
+            ring = self._label_ring.get((len(tables), B))
+            if ring is None:
+                ring = self._label_ring[(len(tables), B)] = [
+                    [torch.empty((len(tables), B), dtype=torch.int64, pin_memory=True) for _ in range(4)],
+                    [None] * 4, 0]
+            pins, copied, slot = ring
+            ring[2] = (slot + 1) % len(pins)
+            if copied[slot] is not None:
+                copied[slot].synchronize()
+            pins[slot].numpy()[...] = block
+            t = pins[slot].to(dev, non_blocking=True)
+            copied[slot] = torch.cuda.Event()
+            copied[slot].record()
         return {c: t[i] for i, c in enumerate(tables)}
 
     @staticmethod
@@ -237,6 +270,7 @@ class CMMVAEModel(BaseModel):
         labels = self._labels(metadata, x.device) if len(self.module.adversarials) else None
         eng.pipeline_optimizer = not self.sync_logging    # pipelined mode: results (logs, output-layer update) trail
         rec = eng.train_step(expert_id, crow, col, val, nnz, self.kl_annealing_fn.kl_weight, labels=labels)
+        self._mark_stepped(expert_id, rec["n_adv"])
         self.kl_annealing_fn.step()
         if self.sync_logging:
             self._log_step(eng.scalars(rec), expert_id)

@@ -318,3 +318,25 @@ def transpose(src, dst):
 
 def axpy(a, b, alpha):
     _check(lib().cmmvae_axpy(_ptr(a), _ptr(b), _c.c_float(alpha), _c.c_longlong(a.numel()), _stream()), "axpy")
+
+
+def widen_u16_i32(src_u16, dst_i32, n: int, stream=None):
+    """dst int32[n] = src uint16[n] (gene ids travel narrow over PCIe; mmvae_b200.feed)"""
+    st = _c.c_void_p(stream.cuda_stream) if stream is not None else _stream()
+    _check(lib().cmmvae_widen_u16_i32(_ptr(src_u16), _ptr(dst_i32), _c.c_longlong(n), st), "widen_u16_i32")
+    return dst_i32
+
+
+def host_slice_rows(indptr, indices, data, lo: int, hi: int, n_genes: int, crow_out, col_out, val_out) -> int:
+    """HOST packer (numpy arrays in, numpy views of a pinned block out): rows [lo, hi) of a CSR chunk; see
+    cmmvae_host_slice_rows.  Releases the GIL for the duration of the copy."""
+    import numpy as np
+    fn = lib().cmmvae_host_slice_rows
+    fn.restype = _c.c_longlong
+    p = lambda a: _c.c_void_p(a.ctypes.data)  # noqa: E731
+    n = fn(p(indptr), indptr.dtype.itemsize, p(indices), indices.dtype.itemsize, p(data), _c.c_longlong(lo),
+           _c.c_longlong(hi), _c.c_longlong(n_genes), p(crow_out), p(col_out), int(col_out.dtype == np.uint16),
+           p(val_out))
+    if n < 0:
+        raise ValueError(f"host_slice_rows failed ({n}): {lib().cmmvae_last_error().decode()}")
+    return int(n)

@@ -205,3 +205,44 @@ def test_staged_batches_keep_a_batch_valid_until_the_next_one_is_requested():
     assert len(list(it)) == 6
     with pytest.raises(ValueError):
         StagedCSRBatches(chunks, 8, device="cpu", depth=2)
+
+
+def test_native_packer_equals_scipy_slicing_narrow_and_wide():
+    """cmmvae_host_slice_rows (host C code of libcmmvae_b200.so): same rows as scipy's chunk[lo:hi], bit for bit,
+    for int32 / int64 index arrays, into int32 and uint16 column blocks; out-of-range gene ids are refused."""
+    from mmvae_b200 import ops
+    m = _ragged(5)
+    for idx_t in (np.int32, np.int64):
+        indptr, indices = m.indptr.astype(idx_t), m.indices.astype(idx_t)
+        for lo, hi in [(0, 37), (2, 5), (3, 4), (30, 37), (5, 5)]:
+            ref = m[lo:hi]
+            n = int(ref.nnz)
+            for col_t in (np.int32, np.uint16):
+                crow, col, val = np.full(hi - lo + 1, -7, np.int32), np.zeros(n, col_t), np.zeros(n, np.float32)
+                assert ops.host_slice_rows(indptr, indices, m.data, lo, hi, m.shape[1], crow, col, val) == n
+                np.testing.assert_array_equal(crow, ref.indptr)
+                np.testing.assert_array_equal(col.astype(np.int64), ref.indices)
+                np.testing.assert_array_equal(val.view(np.uint32), ref.data.view(np.uint32))
+    with pytest.raises(ValueError, match="gene id"):
+        ops.host_slice_rows(m.indptr, m.indices, m.data, 0, 37, 100, np.zeros(38, np.int32),
+                            np.zeros(m.nnz, np.int32), np.zeros(m.nnz, np.float32))
+
+
+@pytest.mark.parametrize("workers", [0, 3])
+def test_staged_batches_narrow_columns_and_worker_threads(workers):
+    """uint16 gene ids on the wire + background packing threads: same batches, same order, same bits as the
+    reference batcher's scipy slices"""
+    from mmvae_b200.feed import StagedCSRBatches
+    chunks = _chunks(3, [40, 64, 24])
+    batcher = StagedCSRBatches(chunks, 8, device="cpu", depth=3, workers=workers, narrow_col=True)
+    got = [(torch.sparse_csr_tensor(x.crow_indices().clone(), x.col_indices().clone(), x.values().clone(),
+                                    size=x.shape), meta) for x, meta in batcher]    # blocks are recycled: copy out
+    batcher.close()
+    want = [(c[lo:lo + 8], f.iloc[lo:lo + 8]) for c, f in chunks for lo in range(0, c.shape[0] - 7, 8)]
+    assert len(got) == len(want) and batcher.stager.narrow
+    for (x, meta), (ref, fref) in zip(got, want):
+        np.testing.assert_array_equal(x.crow_indices().numpy(), ref.indptr)
+        np.testing.assert_array_equal(x.col_indices().numpy(), ref.indices)
+        assert x.col_indices().dtype == torch.int32
+        np.testing.assert_array_equal(x.values().numpy().view(np.uint32), ref.data.view(np.uint32))
+        assert list(meta["cell"]) == list(fref["cell"])

@@ -25,6 +25,34 @@ def rel(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
+def clustered_csr(B, G, seed, background=0.02):
+    """CSR batch whose rows hold 9..64 entries inside some 64-gene windows (real expression panels cluster:
+    the kernels keep 8 entries per (cell, window) in registers and stream the rest) on top of a uniform
+    background; every 7th row is empty, one row is completely dense"""
+    rng = np.random.default_rng(seed)
+    NW = (G + 63) // 64
+    crow, cols, vals = [0], [], []
+    for b in range(B):
+        if b % 7 == 3:
+            c = np.zeros(0, dtype=np.int64)
+        elif b == 5:
+            c = np.arange(G)
+        else:
+            c = [rng.choice(G, size=max(1, int(background * G)), replace=False)]
+            for w in rng.choice(NW, size=3, replace=False):
+                lo, hi = w * 64, min(G, w * 64 + 64)
+                c.append(lo + rng.choice(hi - lo, size=min(hi - lo, int(rng.integers(9, 65))), replace=False))
+            c = np.unique(np.concatenate(c))
+        cols.append(c.astype(np.int32))
+        vals.append(rng.uniform(0.5, 7.0, size=c.size).astype(np.float32))
+        crow.append(crow[-1] + c.size)
+    return np.asarray(crow, dtype=np.int32), np.concatenate(cols), np.concatenate(vals)
+
+
+def make_csr(B, G, density, seed):
+    return clustered_csr(B, G, seed) if density == "clustered" else O.synth_csr(B, G, density, seed=seed)
+
+
 @pytest.mark.parametrize("B,G,H,density", [(16, 200, 64, 0.1), (33, 1000, 1024, 0.05), (8, 300, 50, 0.2)])
 @pytest.mark.parametrize("wdtype", [torch.float32, torch.bfloat16])
 def test_csr_linear_fwd(ops, B, G, H, density, wdtype):
@@ -287,10 +315,14 @@ def test_cpu_tensor_rejected(ops):
 
 
 @pytest.mark.parametrize("B,G,H,density", [(24, 264, 64, 0.1), (130, 1000, 128, 0.05), (256, 6053, 1024, 0.05),
-                                            (100, 3000, 256, 0.3)])
+                                            (100, 3000, 256, 0.3), (200, 2000, 256, "clustered"),
+                                            (1024, 60530, 1024, 0.05)],
+                         ids=["tiny", "1000", "6053", "dense30", "clustered-windows", "BASELINE-config2-shape"])
 def test_decoder_mse_fused(ops, B, G, H, density):
-    """fused tcgen05 GEMM + ReLU + sum-MSE-vs-CSR epilogue against the dense restatement"""
-    crow, col, val = O.synth_csr(B, G, density, seed=11)
+    """fused tcgen05 GEMM + ReLU + sum-MSE-vs-CSR epilogue against the dense restatement -- up to the shape
+    bench.py times (1024 cells x 60 530 genes x 1024: 946-window pointer table, 1896 tiles over 148 CTAs) and
+    with rows holding more than 8 entries per 64-gene window (the spill loop)"""
+    crow, col, val = make_csr(B, G, density, 11)
     x = O.csr_to_dense(crow, col, val, G).cuda()
     g = torch.Generator().manual_seed(6)
     h = torch.relu(torch.randn(B, H, generator=g)).bfloat16().cuda()
@@ -313,11 +345,16 @@ def test_decoder_mse_fused(ops, B, G, H, density):
 
 
 @pytest.mark.parametrize("B,G,H,density", [(24, 264, 64, 0.1), (300, 3000, 512, 0.05), (130, 1000, 1024, 0.2),
-                                            (1024, 6053, 1024, 0.05), (64, 777, 256, 0.5)])
+                                            (1024, 6053, 1024, 0.05), (64, 777, 256, 0.5),
+                                            (200, 2000, 256, "clustered"), (1024, 60530, 1024, 0.05)],
+                         ids=["tiny", "3000", "dense20", "6053", "dense50", "clustered-windows",
+                              "BASELINE-config2-shape"])
 def test_csr_linear_tc_fwd_bwd(ops, B, G, H, density):
     """tensor-pipe SpMM (tile densified in smem): forward and weight gradient against the oracle with
-    x rounded to bf16 (the staged operand precision); exact zeros for absent genes; pointer table exact."""
-    crow, col, val = O.synth_csr(B, G, density, seed=21)
+    x rounded to bf16 (the staged operand precision); exact zeros for absent genes; pointer table exact.
+    Covers the benched shape (148-way split-K over 946 gene windows) and rows with more than 8 entries per
+    64-gene window (entries beyond the register-resident 8 are streamed and must be un-scattered again)."""
+    crow, col, val = make_csr(B, G, density, 21)
     g = torch.Generator().manual_seed(2)
     Wt16 = (torch.randn(G, H, generator=g) * 0.05).bfloat16()
     b = torch.randn(H, generator=g) * 0.1
@@ -335,7 +372,11 @@ def test_csr_linear_tc_fwd_bwd(ops, B, G, H, density):
     assert np.array_equal((pk >> 16).astype(np.uint16),
                           torch.from_numpy(val).bfloat16().view(torch.int16).numpy().view(np.uint16))
     val16 = torch.from_numpy(val).bfloat16().float().numpy()
-    ref = O.csr_linear(crow, col, val16, Wt16.float().t(), b)
+    O.FAST_CSR = nnz * H > 1 << 28    # the explicit per-non-zero restatement materialises [nnz, H] floats
+    try:
+        ref = O.csr_linear(crow, col, val16, Wt16.float().t(), b)
+    finally:
+        O.FAST_CSR = False
     y = ops.csr_linear_fwd_tc(packed, tp, B, G, Wt16.cuda(), b.cuda())
     assert rel(y, ref) < 2e-5
     dY16 = torch.randn(B, H, generator=g).bfloat16()
