@@ -214,7 +214,10 @@ def test_bench_reference_arm_contract_on_cpu():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "cells/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["vs_baseline"] is None and d["scaling"] == "weak"
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    have_ref = os.path.exists(os.path.join(root, "baseline", "_ref", "cmmvae", "models", "cmmvae_model.py"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")   # the unmodified reference when installed
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["steps"] == d["cpu_baseline"]["steps_run"] == 1        # the line reports the steps it actually ran
     assert d["e2e"] == {"value": d["value"], "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
 

@@ -79,8 +79,13 @@ def test_optimizer_state_dict_round_trip_resumes_adam():
             o.load_state_dict(sd)
         _step(a, 64, 1500, 0.05, 777, 3)
         _step(b, 64, 1500, 0.05, 777, 3)
-        for (k, va), (_, vb) in zip(a.state_dict().items(), b.state_dict().items()):
-            assert torch.equal(va, vb), k
+        sa, sb = a.state_dict(), b.state_dict()
+        for k, va in sa.items():      # (atomics make summation order vary run to run: equal to rounding, not bitwise)
+            if va.dtype.is_floating_point:
+                err = float((va.double() - sb[k].double()).norm() / va.double().norm().clamp_min(1e-30))
+                assert err < 2e-6, (k, err)
+            else:
+                assert torch.equal(va, sb[k]), k
         # a resumed run WITHOUT the optimizer state restarts Adam's bias correction: it must differ
         c = _model()
         c.cuda().train()
@@ -88,7 +93,7 @@ def test_optimizer_state_dict_round_trip_resumes_adam():
         c.load_state_dict(sd_model)
         _step(c, 64, 1500, 0.05, 777, 3)
         k = "module.vae.encoder.mean_encoder.weight"
-        assert not torch.equal(c.state_dict()[k], a.state_dict()[k])
+        assert float((c.state_dict()[k] - sa[k]).abs().max()) > 1e-4      # first-step Adam moves every weight by lr
     finally:
         L.set_precision("bf16")
 
