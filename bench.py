@@ -403,9 +403,9 @@ def main():
 
     def resident_step(t):
         s, crow, col, val = resident_batch(t)
-        if world > 1:      # the exchange of the NEXT batch's CSR records runs underneath this step
-            eng.prefetch(*resident_batch(t + 1))
         eng.train_step(s, crow, col, val, int(col.numel()), 1.0, labels=labels[t % NB])
+        if world > 1:      # the exchange of the NEXT batch's CSR records runs underneath this step
+            eng.prefetch(*resident_batch(t + 1), ready=True)
 
     # ---------------- device-resident throughput ----------------
     for t in range(args.warmup):
@@ -466,13 +466,20 @@ def main():
     feeds = {s: StagedCSRBatches(chunk_source(s), B, device=dev, workers=workers) for s in names}
     iters = {s: iter(f) for s, f in feeds.items()}
 
-    def api_step(t):
+    pending = {}
+
+    def fetch(t):
         s = names[t % len(names)]
         x, meta = next(iters[s])
-        if world > 1:
-            pass   # (the public API prefetches the next batch's exchange itself: see CMMVAEModel.training_step)
-        model.training_step((x, meta, s), t)
-        v = model.logged_metrics.get(f"loss/training/{s}")
+        return x, meta, s
+
+    def api_step(t):
+        batch = pending.pop(t, None) or fetch(t)
+        model.training_step(batch, t)
+        if world > 1:      # data parallel: hand the next batch over so its CSR exchange runs under this step
+            pending[t + 1] = fetch(t + 1)
+            model.prefetch_batch(pending[t + 1])
+        v = model.logged_metrics.get(f"loss/training/{batch[2]}")
         return float(v) if v is not None else None
 
     model.sync_logging = False
@@ -612,9 +619,9 @@ def also_config3(rank, world, dev, steps, warmup):
 
     def step(t):
         s, crow, col, val = batch(t)
-        if world > 1:
-            eng.prefetch(*batch(t + 1))
         eng.train_step(s, crow, col, val, int(col.numel()), 1.0, labels=labels[t % NB])
+        if world > 1:
+            eng.prefetch(*batch(t + 1), ready=True)
 
     for t in range(warmup):
         step(t)

@@ -188,6 +188,52 @@ int cmmvae_transpose(const void* src, void* dst, int dtype, int R, int C, int ld
 int cmmvae_axpy(float* a, const float* b, float alpha, long long n, void* stream);
 
 
+/* ---- data parallel over NVLink peer memory (DDP gradient mean of cmmvae_model.py:191-213, taken on a
+ * gene-sharded first / last layer) ---------------------------------------------------------
+ * No reference counterpart (the reference relies on Lightning DDP = NCCL all-reduce of 500 MB per step).  Every
+ * rank owns symmetric buffers mapped into all peers (CUDA IPC, set up by the host side); producers store into the
+ * consumers' buffers and raise flags there, consumers spin on local flags.  `route` / `dst_slots` / `peer_flags`
+ * are HOST arrays of n device pointers (one per rank, own rank included). */
+/* same product as cmmvae_csr_linear_fwd_tc, no bias; output row r is stored at row r % route_rows of
+ * route[r / route_rows] (partial sums of a gene shard for the cells of ALL ranks, delivered to their owners) */
+int cmmvae_csr_linear_fwd_tc_routed(const void* packed, const int32_t* tile_ptr, int B, int G, int H,
+                                    const void* Wt_bf16, float* const* route, int n_route, int route_rows,
+                                    void* stream);
+/* C[M,N] (f32) = opA(A) opB(B) with the same row routing (dh partials of a gene shard -> owners of the cells) */
+int cmmvae_gemm_bf16_tc_routed(const void* A, int lda, int transA, const void* Bm, int ldb, int transB,
+                               int M, int N, int K, int ldc, float* const* route, int n_route, int route_rows,
+                               void* stream);
+/* fused decoder with one loss sum per block of `loss_rows` cells (loss_sums double[ceil(B/loss_rows)], zeroed by
+ * the call): a gene-sharded rank sees the cells of all ranks and reports each rank's share separately */
+int cmmvae_decoder_mse_fused_blocks(const void* h, int ldh, const void* Wout, int ldw, const float* bout,
+                                    int B, int G, int H, const int32_t* crow, const int32_t* col, const float* val,
+                                    const int32_t* tile_ptr, void* dlogits_bf16, int ldd, double* loss_sums,
+                                    int loss_rows, void* workspace, void* stream);
+/* copy src[nbytes] (16-byte multiple) into dst_slots[i] on every rank i, then store `step` to peer_flags[i]
+ * (system-scope release; peer_flags == NULL: no flags, for all but the last part of a multi-part push).
+ * `ticket`: zeroed device uint32 owned by the caller (last-block detection). */
+int cmmvae_peer_push(const void* src, long long nbytes, void* const* dst_slots, void* const* peer_flags,
+                     int n_peers, unsigned int step, unsigned int* ticket, void* stream);
+/* flags only: after a kernel whose epilogue already stored to the peers (the routed kernels above) */
+int cmmvae_peer_signal(void* const* peer_flags, int n_peers, unsigned int step, void* stream);
+/* block the stream until local_flags[0..n_peers) (uint32, this rank's memory) have all reached `step` */
+int cmmvae_peer_wait(const void* local_flags, int n_peers, unsigned int step, void* stream);
+/* out[i] = sum_s slabs[s * slab_stride + i] (+ bias[i % H]), i < n; f32 and/or bf16 output */
+int cmmvae_slab_sum(const float* slabs, int n_slabs, long long slab_stride, long long n, const float* bias, int H,
+                    float* out_f32, void* out_bf16, void* stream);
+/* gene shard [g0, g1) of the CSR batches of all ranks.  `gathered`: n_src slabs `slab_bytes` apart, each
+ * [crow int32 (B+1) | col int32 at col_off | val f32 at val_off].  Output: one compact CSR over B * n_src rows
+ * (source-major), columns rebased to g0: crow_out int32[B*n_src+1], col_out/val_out [cap]; info[0] = non-zeros of
+ * the shard, info[1] = 1 if they exceed cap (entries beyond cap are dropped -- the caller must treat that as an
+ * error).  cnt/start: int32[B*n_src] scratch.  Bit-exact with the rows' sorted, duplicate-free column lists. */
+int cmmvae_shard_csr(const void* gathered, long long slab_bytes, long long col_off, long long val_off,
+                     int B, int n_src, int g0, int g1, int cap, int32_t* cnt, int32_t* start,
+                     int32_t* crow_out, int32_t* col_out, float* val_out, int32_t* info, void* stream);
+/* slabs: n_src rows of `stride` doubles = [loss share of rank 0..n_src-1 | sumsq of the source's shard | ...];
+ * out_recon = sum_s slab_s[rank]; out_norm += sum_s slab_s[n_src] */
+int cmmvae_dp_scalars(const double* slabs, int n_src, int stride, int rank, double* out_recon, double* out_norm,
+                      void* stream);
+
 /* ---- host -> HBM feed of CSR batches (batch format of cellxgene_datapipe.py:169-193) ---------
  * HOST function (all pointers are host pointers): rows [lo, hi) of a CSR chunk -- what scipy's chunk[lo:hi]
  * yields in SparseCSRMatrixBatcherDataPipe -- written into a (pinned) staging block: crow int32 rebased to 0,

@@ -49,7 +49,8 @@ struct DecParams {
   int ntp;
   __nv_bfloat16* dl;
   int ldd;
-  double* loss_sum;
+  double* loss_sum;   // [1], or one slot per block of `loss_rows` cells (data parallel: one slot per source rank)
+  int loss_rows;      // 0: everything into loss_sum[0]
   int num_m, num_n;
 };
 
@@ -175,6 +176,7 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
     float eval[DE], neval[DE];
     fetch(blockIdx.x, p0, cnt, ecol, eval);
     int it = 0;
+    int slot = 0;       // loss slot the partial sum in loss_acc belongs to
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -182,6 +184,16 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
       const int m0 = m_blk * DBM, n0 = n_blk * DBN;
       const int b = m0 + row;
       const bool row_ok = b < p.B;
+      if (p.loss_rows > 0) {
+        // per-thread slot (a 128-cell tile may straddle two owners when loss_rows % 128 != 0); the flush is
+        // warp-divergence safe: plain per-thread atomics on the (rare) slot change
+        const int s_new = row_ok ? b / p.loss_rows : slot;
+        if (s_new != slot) {
+          if (loss_acc != 0.0) atomicAdd(p.loss_sum + slot, loss_acc);
+          loss_acc = 0.0;
+          slot = s_new;
+        }
+      }
       const int g0 = n0 + w * 64;            // first gene of this thread's window
       fetch(t + gridDim.x, np0, ncnt, necol, neval);
 
@@ -263,9 +275,13 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
       for (int u = 0; u < DE; ++u) { ecol[u] = necol[u]; eval[u] = neval[u]; }
     }
     if (gt == 0) tma_store_wait_all();       // smem must outlive the last bulk store
-    // one atomic per warp
-    loss_acc = warp_sum(loss_acc);
-    if (lane == 0 && loss_acc != 0.0) atomicAdd(p.loss_sum, loss_acc);
+    if (p.loss_rows > 0) {
+      if (loss_acc != 0.0) atomicAdd(p.loss_sum + slot, loss_acc);
+    } else {
+      // one atomic per warp
+      loss_acc = warp_sum(loss_acc);
+      if (lane == 0 && loss_acc != 0.0) atomicAdd(p.loss_sum, loss_acc);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -285,10 +301,9 @@ extern "C" size_t cmmvae_decoder_mse_fused_workspace_bytes(int B, int G) {
   return sizeof(int32_t) * (size_t)B * (size_t)((G + 63) / 64 + 1);
 }
 
-extern "C" int cmmvae_decoder_mse_fused(const void* h, int ldh, const void* Wout, int ldw, const float* bout, int B,
-                                        int G, int H, const int32_t* crow, const int32_t* col, const float* val,
-                                        const int32_t* tile_ptr, void* dlogits_bf16, int ldd, double* loss_sum,
-                                        void* workspace, void* stream) {
+static int decoder_mse(const void* h, int ldh, const void* Wout, int ldw, const float* bout, int B, int G, int H,
+                       const int32_t* crow, const int32_t* col, const float* val, const int32_t* tile_ptr,
+                       void* dlogits_bf16, int ldd, double* loss_sum, int loss_rows, void* workspace, void* stream) {
   CMMVAE_REQUIRE(B > 0 && G > 0 && H > 0, "decoder_mse_fused: bad shape");
   CMMVAE_REQUIRE(ldh % 8 == 0 && ldw % 8 == 0 && ldd % 8 == 0 && ldd >= G,
                  "decoder_mse_fused: ldh/ldw/ldd must be multiples of 8 and ldd >= G");
@@ -300,7 +315,7 @@ extern "C" int cmmvae_decoder_mse_fused(const void* h, int ldh, const void* Wout
   DecParams p;
   p.B = B; p.G = G; p.H = H; p.bout = bout; p.col = col; p.val = val;
   p.ntp = (G + 63) / 64 + 1;
-  p.dl = (__nv_bfloat16*)dlogits_bf16; p.ldd = ldd; p.loss_sum = loss_sum;
+  p.dl = (__nv_bfloat16*)dlogits_bf16; p.ldd = ldd; p.loss_sum = loss_sum; p.loss_rows = loss_rows;
   p.num_m = (B + DBM - 1) / DBM;
   p.num_n = (G + DBN - 1) / DBN;
   CUtensorMap tmH, tmW, tmD;
@@ -317,7 +332,7 @@ extern "C" int cmmvae_decoder_mse_fused(const void* h, int ldh, const void* Wout
     }
     configured = true;
   }
-  cudaMemsetAsync(loss_sum, 0, sizeof(double), st);
+  cudaMemsetAsync(loss_sum, 0, sizeof(double) * (loss_rows > 0 ? (size_t)((B + loss_rows - 1) / loss_rows) : 1), st);
   if (!tile_ptr) {   // build the 64-gene-window pointer table (the tensor-pipe SpMM shares it when it ran)
     int blocks = B < 148 * 16 ? B : 148 * 16;   // one CTA per row
     launch_pdl(tile_ptr64_kernel, dim3(blocks), dim3(256), 0, st, crow, col, B, p.ntp, (int32_t*)workspace);
@@ -329,4 +344,21 @@ extern "C" int cmmvae_decoder_mse_fused(const void* h, int ldh, const void* Wout
   const int grid = num_tiles < sm_budget() ? num_tiles : sm_budget();
   launch_pdl(decoder_mse_fused_kernel, dim3(grid), dim3(kDecThreads), DecSmem::kTotal, st, tmH, tmW, tmD, p);
   return check_launch("decoder_mse_fused");
+}
+
+extern "C" int cmmvae_decoder_mse_fused(const void* h, int ldh, const void* Wout, int ldw, const float* bout, int B,
+                                        int G, int H, const int32_t* crow, const int32_t* col, const float* val,
+                                        const int32_t* tile_ptr, void* dlogits_bf16, int ldd, double* loss_sum,
+                                        void* workspace, void* stream) {
+  return decoder_mse(h, ldh, Wout, ldw, bout, B, G, H, crow, col, val, tile_ptr, dlogits_bf16, ldd, loss_sum, 0,
+                     workspace, stream);
+}
+
+extern "C" int cmmvae_decoder_mse_fused_blocks(const void* h, int ldh, const void* Wout, int ldw, const float* bout,
+                                               int B, int G, int H, const int32_t* crow, const int32_t* col,
+                                               const float* val, const int32_t* tile_ptr, void* dlogits_bf16, int ldd,
+                                               double* loss_sums, int loss_rows, void* workspace, void* stream) {
+  CMMVAE_REQUIRE(loss_rows > 0, "decoder_mse_fused_blocks: loss_rows must be positive");
+  return decoder_mse(h, ldh, Wout, ldw, bout, B, G, H, crow, col, val, tile_ptr, dlogits_bf16, ldd, loss_sums,
+                     loss_rows, workspace, stream);
 }

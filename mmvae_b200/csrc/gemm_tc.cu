@@ -44,6 +44,10 @@ struct GemmParams {
   int splits;  // split-K factor (gridDim.z); > 1: partial products are atomically added into a zeroed C32
   double* sumsq;  // optional: += sum of squares of the stored C (gradient-norm fused into the dW GEMM)
   int tma_out;    // f32 output leaves through 128B-swizzled smem chunks + TMA bulk stores (full-line writes)
+  // data parallel: output row gm belongs to rank gm / route_rows and is stored straight into that rank's buffer
+  // (peer memory) at row gm % route_rows; 0 = local C32
+  float* route[16];
+  int route_rows;
 };
 
 template <int BN, bool A_MN, bool B_MN>
@@ -250,6 +254,18 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < 32; ++j)
               if (gn0 + j < p.N) v[j] += __ldg(p.bias + gn0 + j);
           }
+          if (p.route_rows > 0) {   // f32 only, no accumulate / relu / bf16 copy (checked by the host)
+            float* dst = p.route[gm / p.route_rows] + (size_t)(gm % p.route_rows) * p.ldc + gn0;
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (gn0 + j < p.N) dst[j] = v[j];
+            }
+            continue;
+          }
           const size_t o = (size_t)gm * p.ldc + gn0;
           if (full) {
             if (p.accumulate) {
@@ -399,9 +415,9 @@ static int dispatch_major(int transA, int transB, const CUtensorMap& tmA, const 
 
 using namespace cmmvae;
 
-extern "C" int cmmvae_gemm_bf16_tc(const void* A, int lda, int transA, const void* Bm, int ldb, int transB, int M,
-                                   int N, int K, const float* bias, int relu, int accumulate, float* C_f32,
-                                   void* C_bf16, int ldc, double* sumsq_out, void* stream) {
+static int gemm_bf16_tc(const void* A, int lda, int transA, const void* Bm, int ldb, int transB, int M, int N, int K,
+                        const float* bias, int relu, int accumulate, float* C_f32, void* C_bf16, int ldc,
+                        double* sumsq_out, float* const* route, int n_route, int route_rows, void* stream) {
   CMMVAE_REQUIRE(M > 0 && N > 0 && K > 0 && ldc >= N, "gemm_bf16_tc: bad shape M=%d N=%d K=%d ldc=%d", M, N, K, ldc);
   CMMVAE_REQUIRE(C_f32 || C_bf16, "gemm_bf16_tc: no output");
   CMMVAE_REQUIRE(!accumulate || C_f32, "gemm_bf16_tc: accumulate needs C_f32");
@@ -412,7 +428,7 @@ extern "C" int cmmvae_gemm_bf16_tc(const void* A, int lda, int transA, const voi
   // long-K, few-tile products (dh = dlogits Wout: K = genes) are split along K to fill the 148 SMs
   int splits = 1;
   const int sms = sm_budget();
-  if (!relu && !C_bf16 && !accumulate && C_f32 && total_kb >= 64 && tiles256 * 2 <= sms && N > 128) {
+  if (!relu && !C_bf16 && !accumulate && C_f32 && total_kb >= 64 && tiles256 * 2 <= sms && N > 128 && !route) {
     splits = (int)(sms / tiles256);
     if (splits > total_kb / 16) splits = total_kb / 16;
     if (splits < 1) splits = 1;
@@ -433,6 +449,18 @@ extern "C" int cmmvae_gemm_bf16_tc(const void* A, int lda, int transA, const voi
   p.vec_ok = (ldc % 8 == 0) && (!C_f32 || ((uintptr_t)C_f32 & 15) == 0) && (!C_bf16 || ((uintptr_t)C_bf16 & 15) == 0);
   p.splits = splits;
   p.sumsq = sumsq_out;
+  p.route_rows = 0;
+  for (int i = 0; i < 16; ++i) p.route[i] = nullptr;
+  if (route) {
+    CMMVAE_REQUIRE(n_route >= 1 && n_route <= 16 && route_rows > 0 && (long long)n_route * route_rows >= M,
+                   "gemm_bf16_tc_routed: %d routes of %d rows do not cover %d rows", n_route, route_rows, M);
+    CMMVAE_REQUIRE(!relu && !C_bf16 && !accumulate && !sumsq_out, "gemm_bf16_tc_routed: plain f32 output only");
+    for (int i = 0; i < n_route; ++i) {
+      CMMVAE_REQUIRE(route[i] && ((uintptr_t)route[i] & 15) == 0, "gemm_bf16_tc_routed: bad route %d", i);
+      p.route[i] = route[i];
+    }
+    p.route_rows = route_rows;
+  }
   CMMVAE_REQUIRE(!sumsq_out || splits == 1, "gemm_bf16_tc: sumsq_out is not available on the split-K path");
   cudaStream_t st = (cudaStream_t)stream;
   if (splits > 1) {
@@ -445,9 +473,24 @@ extern "C" int cmmvae_gemm_bf16_tc(const void* A, int lda, int transA, const voi
   // big f32-only outputs (weight gradients) leave through TMA bulk stores
   CUtensorMap tmC = tmA;
   p.tma_out = (C_f32 && !C_bf16 && !accumulate && splits == 1 && ldc % 4 == 0 && ((uintptr_t)C_f32 & 15) == 0 &&
-               (long long)M * N >= (1 << 20)) ? 1 : 0;
+               (long long)M * N >= (1 << 20) && !route) ? 1 : 0;
   if (p.tma_out)
     if (int rc2 = make_tmap_f32(&tmC, C_f32, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, BM)) return rc2;
   if (BN == 256) return dispatch_major<256>(transA, transB, tmA, tmB, tmC, p, st);
   return dispatch_major<128>(transA, transB, tmA, tmB, tmC, p, st);
+}
+
+extern "C" int cmmvae_gemm_bf16_tc(const void* A, int lda, int transA, const void* Bm, int ldb, int transB, int M,
+                                   int N, int K, const float* bias, int relu, int accumulate, float* C_f32,
+                                   void* C_bf16, int ldc, double* sumsq_out, void* stream) {
+  return gemm_bf16_tc(A, lda, transA, Bm, ldb, transB, M, N, K, bias, relu, accumulate, C_f32, C_bf16, ldc, sumsq_out,
+                      nullptr, 0, 0, stream);
+}
+
+extern "C" int cmmvae_gemm_bf16_tc_routed(const void* A, int lda, int transA, const void* Bm, int ldb, int transB,
+                                          int M, int N, int K, int ldc, float* const* route, int n_route,
+                                          int route_rows, void* stream) {
+  CMMVAE_REQUIRE(route, "gemm_bf16_tc_routed: no routes");
+  return gemm_bf16_tc(A, lda, transA, Bm, ldb, transB, M, N, K, nullptr, 0, 0, route[0], nullptr, ldc, nullptr, route,
+                      n_route, route_rows, stream);
 }

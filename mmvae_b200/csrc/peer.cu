@@ -1,0 +1,290 @@
+// Data-parallel exchange over NVLink / NVSwitch PEER MEMORY (no NCCL on the data path).
+//
+// Every rank owns a set of symmetric buffers (same layout on every GPU, mapped into all peers through CUDA IPC);
+// an exchange is "the producer STORES its piece straight into every consumer's buffer, then raises a flag there".
+// Consumers spin on their local flags (system-scope acquire) and read local memory.  The big pieces -- partial
+// sums of the gene-sharded first layer and of dh -- are stored by the EPILOGUE of the kernel that computes them
+// (spmm_tc.cu / gemm_tc.cu take a PeerRoute), so transfer and math overlap tile by tile and no communication
+// kernel ever occupies SMs.  The reduction over ranks happens in the consumer (slab_sum: 8 slabs of 4 MB are a
+// few microseconds of HBM traffic).
+//
+//   cmmvae_peer_push    src -> slot of every peer (16-byte vector stores), then flags        (all-gather piece)
+//   cmmvae_peer_signal  flags only (after a kernel whose epilogue already stored to the peers)
+//   cmmvae_peer_wait    spin until the local flags of a channel reach `step`
+//   cmmvae_slab_sum     out = sum over slabs (+ bias), f32 (+ bf16 copy)                   (the reduce of reduce-scatter)
+//   cmmvae_shard_csr_*  cut the gene shard [g0, g1) out of the gathered CSR slabs of all ranks into one compact CSR
+//                       (rows = all cells of the job, columns rebased to the shard) -- bit-exact index handling
+#include "common.cuh"
+
+namespace cmmvae {
+
+constexpr int kMaxPeers = 16;
+struct PeerPtrs {
+  void* p[kMaxPeers];
+};
+
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* addr, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+  return v;
+}
+
+// grid (chunks, peers): block (c, p) copies 16-byte words c, c+chunks, ... of src into peer p's slot; the last
+// block to finish (device-scope ticket) raises this rank's flag on every peer
+__global__ void __launch_bounds__(256) peer_push_kernel(const uint4* __restrict__ src, long long n16, PeerPtrs dst,
+                                                        PeerPtrs flags, int n_peers, uint32_t step,
+                                                        unsigned int* __restrict__ ticket) {
+  pdl_sync();
+  uint4* out = reinterpret_cast<uint4*>(dst.p[blockIdx.y]);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __ldg(src + i);
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int last;
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+  __syncthreads();
+  if (last) {
+    if (threadIdx.x == 0) *ticket = 0u;
+    __threadfence_system();
+    if (threadIdx.x < n_peers && flags.p[threadIdx.x])
+      st_release_sys_u32(reinterpret_cast<uint32_t*>(flags.p[threadIdx.x]), step);
+  }
+}
+
+__global__ void peer_signal_kernel(PeerPtrs flags, int n_peers, uint32_t step) {
+  pdl_sync();   // returns once the producer grid has completed and its (peer) stores are visible
+  __threadfence_system();
+  if (threadIdx.x < n_peers) st_release_sys_u32(reinterpret_cast<uint32_t*>(flags.p[threadIdx.x]), step);
+}
+
+__global__ void peer_wait_kernel(const uint32_t* __restrict__ local_flags, int n_peers, uint32_t step) {
+  pdl_sync();
+  if (threadIdx.x < n_peers) {
+    // flags only grow; (int) difference keeps the comparison valid across a 2^32 wrap
+    while ((int)(ld_acquire_sys_u32(local_flags + threadIdx.x) - step) < 0) __nanosleep(100);
+  }
+  __syncthreads();
+  __threadfence_system();
+}
+
+// out[i] = sum_s slabs[s * stride + i] (+ bias[i % H]);  n % 4 == 0, H % 4 == 0
+__global__ void __launch_bounds__(256) slab_sum_kernel(const float4* __restrict__ slabs, int n_slabs,
+                                                       long long stride4, long long n4,
+                                                       const float* __restrict__ bias, int H,
+                                                       float4* __restrict__ out32, uint2* __restrict__ out16) {
+  pdl_sync();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = slabs[i];
+    for (int s = 1; s < n_slabs; ++s) {
+      const float4 b = slabs[(long long)s * stride4 + i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (bias) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + (i * 4) % H));
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (out32) out32[i] = a;
+    if (out16) out16[i] = make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));
+  }
+}
+
+// ---- gene shard of the gathered CSR ------------------------------------------------------------------------------
+// slab s (one per source rank) = [crow int32 (B+1) | pad to 16 B | col int32 cap | val f32 cap], `slab_bytes` apart.
+struct GatheredCsr {
+  const uint8_t* base;
+  long long slab_bytes, col_off, val_off;
+  int B, n_src;
+};
+__device__ __forceinline__ const int32_t* g_crow(const GatheredCsr& g, int s) {
+  return reinterpret_cast<const int32_t*>(g.base + (long long)s * g.slab_bytes);
+}
+__device__ __forceinline__ const int32_t* g_col(const GatheredCsr& g, int s) {
+  return reinterpret_cast<const int32_t*>(g.base + (long long)s * g.slab_bytes + g.col_off);
+}
+__device__ __forceinline__ const float* g_val(const GatheredCsr& g, int s) {
+  return reinterpret_cast<const float*>(g.base + (long long)s * g.slab_bytes + g.val_off);
+}
+
+// one thread per gathered row: [lo, hi) = entries of the row with g0 <= col < g1 (rows are sorted: two lower bounds)
+__global__ void __launch_bounds__(256) shard_csr_count_kernel(GatheredCsr g, int g0, int g1,
+                                                              int32_t* __restrict__ cnt, int32_t* __restrict__ start) {
+  pdl_sync();
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= g.B * g.n_src) return;
+  const int s = row / g.B, b = row % g.B;
+  const int32_t* crow = g_crow(g, s);
+  const int32_t* col = g_col(g, s);
+  const int r0 = crow[b], r1 = crow[b + 1];
+  int lo = r0, hi = r1;
+  while (lo < hi) { const int m = (lo + hi) >> 1; if (__ldg(col + m) < g0) lo = m + 1; else hi = m; }
+  const int a = lo;
+  hi = r1;
+  while (lo < hi) { const int m = (lo + hi) >> 1; if (__ldg(col + m) < g1) lo = m + 1; else hi = m; }
+  cnt[row] = lo - a;
+  start[row] = a;
+}
+
+// exclusive scan of cnt[0..n) -> crow_out[0..n], single CTA of 1024 threads (n <= a few 100 K rows);
+// overflow[0] = 1 if the total exceeds `cap` (the copy kernel then writes nothing beyond cap)
+__global__ void __launch_bounds__(1024) shard_csr_scan_kernel(const int32_t* __restrict__ cnt, int n, int cap,
+                                                              int32_t* __restrict__ crow_out,
+                                                              int32_t* __restrict__ info) {
+  pdl_sync();
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < n ? cnt[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) warp_tot[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int t = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+      warp_tot[lane] = t;
+    }
+    __syncthreads();
+    const int excl = carry + (w ? warp_tot[w - 1] : 0) + x - v;
+    if (i < n) crow_out[i] = min(excl, cap);   // on overflow the tail rows come out empty (flagged), never out of bounds
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    crow_out[n] = min(carry, cap);
+    info[0] = carry;                 // non-zeros of the shard
+    info[1] = carry > cap ? 1 : 0;   // overflow
+  }
+}
+
+// one warp per gathered row: copy its shard entries to the compact CSR, columns rebased to the shard
+__global__ void __launch_bounds__(256) shard_csr_copy_kernel(GatheredCsr g, int g0, const int32_t* __restrict__ cnt,
+                                                             const int32_t* __restrict__ start,
+                                                             const int32_t* __restrict__ crow_out, int cap,
+                                                             int32_t* __restrict__ col_out,
+                                                             float* __restrict__ val_out) {
+  pdl_sync();
+  const int lane = threadIdx.x & 31;
+  const int n_rows = g.B * g.n_src;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += (gridDim.x * blockDim.x) >> 5) {
+    const int s = row / g.B;
+    const int32_t* col = g_col(g, s);
+    const float* val = g_val(g, s);
+    const int n = cnt[row], a = start[row], o = crow_out[row];
+    for (int k = lane; k < n; k += 32)
+      if (o + k < cap) {
+        col_out[o + k] = __ldg(col + a + k) - g0;
+        val_out[o + k] = __ldg(val + a + k);
+      }
+  }
+}
+
+// recon of THIS rank's cells and the squared gradient norm of a gene-sharded group, from the scalar slabs all
+// ranks pushed: slab s = [loss_part_s[0..N) | shard_sumsq_s]  (doubles).  out_recon = sum_s slab_s[rank];
+// out_norm += sum_s shard_sumsq_s
+__global__ void dp_scalars_kernel(const double* __restrict__ slabs, int n_src, int stride, int rank,
+                                  double* __restrict__ out_recon, double* __restrict__ out_norm) {
+  pdl_sync();
+  if (threadIdx.x == 0) {
+    double r = 0.0, q = 0.0;
+    for (int s = 0; s < n_src; ++s) {
+      r += slabs[s * stride + rank];
+      q += slabs[s * stride + n_src];
+    }
+    *out_recon = r;
+    *out_norm += q;
+  }
+}
+
+}  // namespace cmmvae
+
+using namespace cmmvae;
+
+static int fill_ptrs(PeerPtrs& out, void* const* ptrs, int n, const char* what) {
+  CMMVAE_REQUIRE(n >= 1 && n <= kMaxPeers && ptrs, "%s: 1..%d peers", what, kMaxPeers);
+  for (int i = 0; i < kMaxPeers; ++i) out.p[i] = i < n ? ptrs[i] : nullptr;
+  return 0;
+}
+
+extern "C" int cmmvae_peer_push(const void* src, long long nbytes, void* const* dst_slots, void* const* peer_flags,
+                                int n_peers, unsigned int step, unsigned int* ticket, void* stream) {
+  CMMVAE_REQUIRE(nbytes >= 0 && nbytes % 16 == 0 && ((uintptr_t)src & 15) == 0 && ticket,
+                 "peer_push: 16-byte aligned source and size");
+  PeerPtrs d, f;
+  if (int rc = fill_ptrs(d, dst_slots, n_peers, "peer_push")) return rc;
+  if (peer_flags) {
+    if (int rc = fill_ptrs(f, peer_flags, n_peers, "peer_push")) return rc;
+  } else {
+    for (int i = 0; i < kMaxPeers; ++i) f.p[i] = nullptr;   // a piece of a multi-part push: flags come with the last part
+  }
+  for (int i = 0; i < n_peers; ++i) CMMVAE_REQUIRE(((uintptr_t)d.p[i] & 15) == 0, "peer_push: unaligned slot");
+  const long long n16 = nbytes / 16;
+  long long want = (n16 + 255) / 256;
+  const int chunks = (int)(want < 1 ? 1 : (want > 32 ? 32 : want));   // a few CTAs per peer saturate the links
+  launch_pdl(peer_push_kernel, dim3(chunks, n_peers), dim3(256), 0, (cudaStream_t)stream, (const uint4*)src, n16, d, f,
+             n_peers, (uint32_t)step, ticket);
+  return check_launch("peer_push");
+}
+
+extern "C" int cmmvae_peer_signal(void* const* peer_flags, int n_peers, unsigned int step, void* stream) {
+  PeerPtrs f;
+  if (int rc = fill_ptrs(f, peer_flags, n_peers, "peer_signal")) return rc;
+  launch_pdl(peer_signal_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, f, n_peers, (uint32_t)step);
+  return check_launch("peer_signal");
+}
+
+extern "C" int cmmvae_peer_wait(const void* local_flags, int n_peers, unsigned int step, void* stream) {
+  CMMVAE_REQUIRE(local_flags && n_peers >= 1 && n_peers <= kMaxPeers, "peer_wait: bad arguments");
+  launch_pdl(peer_wait_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, (const uint32_t*)local_flags, n_peers,
+             (uint32_t)step);
+  return check_launch("peer_wait");
+}
+
+extern "C" int cmmvae_slab_sum(const float* slabs, int n_slabs, long long slab_stride, long long n, const float* bias,
+                               int H, float* out_f32, void* out_bf16, void* stream) {
+  CMMVAE_REQUIRE(n_slabs >= 1 && n > 0 && n % 4 == 0 && slab_stride % 4 == 0 && (!bias || H % 4 == 0),
+                 "slab_sum: sizes must be multiples of 4");
+  CMMVAE_REQUIRE((((uintptr_t)slabs | (uintptr_t)out_f32) & 15) == 0 && ((uintptr_t)out_bf16 & 7) == 0,
+                 "slab_sum: alignment");
+  const long long n4 = n / 4;
+  long long want = (n4 + 255) / 256;
+  const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
+  launch_pdl(slab_sum_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, (const float4*)slabs, n_slabs,
+             slab_stride / 4, n4, bias, H, (float4*)out_f32, (uint2*)out_bf16);
+  return check_launch("slab_sum");
+}
+
+extern "C" int cmmvae_shard_csr(const void* gathered, long long slab_bytes, long long col_off, long long val_off,
+                                int B, int n_src, int g0, int g1, int cap, int32_t* cnt, int32_t* start,
+                                int32_t* crow_out, int32_t* col_out, float* val_out, int32_t* info, void* stream) {
+  CMMVAE_REQUIRE(gathered && B > 0 && n_src >= 1 && g0 >= 0 && g1 > g0 && cap > 0, "shard_csr: bad arguments");
+  GatheredCsr g{(const uint8_t*)gathered, slab_bytes, col_off, val_off, B, n_src};
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rows = B * n_src;
+  launch_pdl(shard_csr_count_kernel, dim3((rows + 255) / 256), dim3(256), 0, st, g, g0, g1, cnt, start);
+  if (int rc = check_launch("shard_csr_count")) return rc;
+  launch_pdl(shard_csr_scan_kernel, dim3(1), dim3(1024), 0, st, (const int32_t*)cnt, rows, cap, crow_out, info);
+  if (int rc = check_launch("shard_csr_scan")) return rc;
+  long long want = ((long long)rows * 32 + 255) / 256;
+  const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
+  launch_pdl(shard_csr_copy_kernel, dim3(blocks), dim3(256), 0, st, g, g0, (const int32_t*)cnt, (const int32_t*)start,
+             (const int32_t*)crow_out, cap, col_out, val_out);
+  return check_launch("shard_csr_copy");
+}
+
+extern "C" int cmmvae_dp_scalars(const double* slabs, int n_src, int stride, int rank, double* out_recon,
+                                 double* out_norm, void* stream) {
+  CMMVAE_REQUIRE(slabs && n_src >= 1 && stride > n_src && rank >= 0 && rank < n_src, "dp_scalars: bad arguments");
+  launch_pdl(dp_scalars_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, slabs, n_src, stride, rank, out_recon,
+             out_norm);
+  return check_launch("dp_scalars");
+}

@@ -48,6 +48,11 @@ struct SpParams {
   double* sumsq;       // backward only, optional: += sum of squares of dWt (fused gradient norm)
   int win0, row0;      // backward only: window index of tp's first row / gene index of out's first row (shard views)
   int m_begin, m_end;  // backward only: gene range [m_begin, m_end) computed by this launch (m_begin % 128 == 0)
+  // forward only, data parallel: output row gm belongs to rank gm / route_rows and is stored straight into that
+  // rank's buffer (peer memory over NVLink) at row gm % route_rows -- the "scatter" of a reduce-scatter done by
+  // the epilogue while the next tile is being multiplied.  route_rows == 0: plain local output `out`.
+  float* route[16];
+  int route_rows;
 };
 
 // tp[w][b] = first position p in row b with col[p] >= 64*w, w = 0..NW (NW = ceil(G/64)); window-major so
@@ -377,7 +382,9 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          float* orow = p.out + (size_t)gm * p.H + gn0;
+          float* orow = (!BWD && p.route_rows > 0)
+                            ? p.route[gm / p.route_rows] + (size_t)(gm % p.route_rows) * p.H + gn0
+                            : p.out + (size_t)gm * p.H + gn0;
           const bool full = gn0 + 32 <= p.H;
           if (!BWD && p.bias && z == 0) {
 #pragma unroll
@@ -474,20 +481,32 @@ extern "C" int cmmvae_csr_tile_ptr(const int32_t* crow, const int32_t* col, cons
   return check_launch("csr_pack");
 }
 
-extern "C" int cmmvae_csr_linear_fwd_tc(const void* packed, const int32_t* tile_ptr, int B, int G, int H,
-                                        const void* Wt_bf16, const float* bias, float* Y, void* stream) {
+static int spmm_fwd(const void* packed, const int32_t* tile_ptr, int B, int G, int H, const void* Wt_bf16,
+                    const float* bias, float* Y, float* const* route, int n_route, int route_rows, void* stream) {
   CMMVAE_REQUIRE(B > 0 && G > 0 && H > 0 && H % 8 == 0, "csr_linear_fwd_tc: bad shape (H must be a multiple of 8)");
   CMMVAE_REQUIRE(((uintptr_t)Wt_bf16 & 15) == 0 && ((uintptr_t)Y & 15) == 0, "csr_linear_fwd_tc: alignment");
   cudaStream_t st = (cudaStream_t)stream;
   SpParams p;
   p.B = B; p.G = G; p.H = H; p.packed = (const uint32_t*)packed; p.tp = tile_ptr; p.ntp = (G + 63) / 64 + 1;
   p.bias = bias; p.out = Y; p.sumsq = nullptr; p.m_begin = 0; p.m_end = B; p.win0 = 0; p.row0 = 0;
+  p.route_rows = 0;
+  for (int i = 0; i < 16; ++i) p.route[i] = nullptr;
+  if (route) {
+    CMMVAE_REQUIRE(n_route >= 1 && n_route <= 16 && route_rows > 0 && (long long)n_route * route_rows >= B,
+                   "csr_linear_fwd_tc_routed: %d routes of %d rows do not cover %d rows", n_route, route_rows, B);
+    for (int i = 0; i < n_route; ++i) {
+      CMMVAE_REQUIRE(route[i] && ((uintptr_t)route[i] & 15) == 0, "csr_linear_fwd_tc_routed: bad route %d", i);
+      p.route[i] = route[i];
+    }
+    p.route_rows = route_rows;
+  }
   const int tiles = ((B + SBM - 1) / SBM) * ((H + SBN - 1) / SBN);
   const int total_kb = (G + SBK - 1) / SBK;
   const int sms = sm_budget();
   int splits = tiles >= sms ? 1 : sms / tiles;
   if (splits > total_kb / 8) splits = total_kb / 8;
   if (splits < 1) splits = 1;
+  if (route) splits = 1;   // every partial tile goes to its owner exactly once (summed there over the source ranks)
   p.splits = splits;
   CUtensorMap tm;
   if (int rc = make_tmap_bf16(&tm, Wt_bf16, (uint64_t)H, (uint64_t)G, (uint64_t)H, 64, SBK)) return rc;
@@ -495,6 +514,18 @@ extern "C" int cmmvae_csr_linear_fwd_tc(const void* packed, const int32_t* tile_
   const int units = tiles * splits;
   dim3 grid(units < sms ? units : sms);
   return launch_spmm_tc<false>(tm, tm, p, grid, st);
+}
+
+extern "C" int cmmvae_csr_linear_fwd_tc(const void* packed, const int32_t* tile_ptr, int B, int G, int H,
+                                        const void* Wt_bf16, const float* bias, float* Y, void* stream) {
+  return spmm_fwd(packed, tile_ptr, B, G, H, Wt_bf16, bias, Y, nullptr, 0, 0, stream);
+}
+
+extern "C" int cmmvae_csr_linear_fwd_tc_routed(const void* packed, const int32_t* tile_ptr, int B, int G, int H,
+                                               const void* Wt_bf16, float* const* route, int n_route,
+                                               int route_rows, void* stream) {
+  CMMVAE_REQUIRE(route, "csr_linear_fwd_tc_routed: no routes");
+  return spmm_fwd(packed, tile_ptr, B, G, H, Wt_bf16, nullptr, route[0], route, n_route, route_rows, stream);
 }
 
 static int spmm_bwd_w(const void* packed, const int32_t* tile_ptr, int B, int G, int H, const void* dY_bf16,
@@ -507,6 +538,8 @@ static int spmm_bwd_w(const void* packed, const int32_t* tile_ptr, int B, int G,
   CMMVAE_REQUIRE(g_begin >= 0 && g_begin < g_end && g_begin % SBM == 0 && (g_end == G || g_end % SBM == 0),
                  "csr_linear_bwd_w_tc: gene range [%d,%d) must be 128-aligned", g_begin, g_end);
   p.bias = nullptr; p.out = dWt; p.splits = 1; p.sumsq = sumsq_out; p.m_begin = g_begin; p.m_end = g_end;
+  p.route_rows = 0;
+  for (int i = 0; i < 16; ++i) p.route[i] = nullptr;
   p.win0 = shard_view ? g_begin / 64 : 0;
   p.row0 = shard_view ? g_begin : 0;
   CUtensorMap tm;

@@ -57,3 +57,13 @@ def shard_rows(rows: int, world: int, align: int = 128) -> int:
     world * n rows.  The last ranks may own only padding."""
     per = (rows + world - 1) // world
     return (per + align - 1) // align * align
+
+
+def host_allreduce_max(values: Sequence[int]) -> List[int]:
+    """element-wise MAX of a few host integers over the ranks (set-up time only)"""
+    if world_size() == 1:
+        return [int(v) for v in values]
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor(list(values), dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [int(v) for v in t.tolist()]

@@ -10,7 +10,8 @@ exact semantics in SURVEY.md Appendix A) as an explicit sequence of C-ABI kernel
             backward, CSC gather for the sparse weight gradient (K1b)
   optimiser one sum-of-squares + one clip+Adam launch per optimizer group over flat buffers (K13-K15),
             clip coefficient read on the device; bf16 shadows refreshed by the same launch
-  DP        one gradient all-reduce per group over NCCL when torch.distributed is initialised
+  DP        gene-sharded first / last layer over NVLink peer memory (no NCCL on the data path): see
+            ``_train_step`` (data-parallel route) and csrc/peer.cu
 
 Parameters of each optimizer group live in one flat fp32 buffer (``FlatGroup``); the nn.Parameters of
 the modules are views into it, so ``state_dict()`` keeps the reference's names and shapes.  The first
@@ -39,111 +40,87 @@ def _ceil(a: int, b: int) -> int:
 class FlatGroup:
     """One optimizer group (``experts/<id>``, ``vae`` or ``adversarials/<i>``) as flat buffers.
 
-    Layout: ``[segment 0 | segment 1 | ... | tail]``.  With one process the distinction is moot (one range).
-    With ``world`` > 1 ranks each *segment* (the big weight matrices) is ZeRO-1 sharded: gradients are
-    reduce-scattered, every rank runs clip+Adam on its 1/world shard only (Adam state exists only for the
-    shard) and the refreshed bf16 shadow is all-gathered; the fp32 master copy of a segment is current
-    only inside the owner's shard until ``sync_master()``.  The *tail* (biases, BatchNorm affine, small
-    matrices) is replicated: all-reduced gradients, identical Adam on every rank."""
+    Layout: ``[row-sharded parameters ... | tail]``.  With one process the distinction is moot.  With ``world``
+    ranks the *row-sharded* parameters -- the two gene-sized matrices of an expert (first-layer weight, stored
+    ``[genes, hidden]``, and output-layer weight ``[genes, hidden]``) and the output bias ``[genes]`` -- are
+    owned by GENE RANGE: rank r holds the current value, the gradient and the Adam state of rows
+    ``[r * per, (r + 1) * per)`` only (``per`` = rows per rank, 128-aligned, the matrix padded to ``world * per``
+    rows).  Nothing of them is ever exchanged: the step computes each rank's rows of the SUMMED gradient locally
+    (engine, data-parallel route).  The full-size fp32 buffer is kept so that ``state_dict()`` has its usual shapes;
+    rows of other ranks are refreshed by ``sync_master()`` only.  The *tail* (biases, BatchNorm affine, small
+    matrices) is replicated: gradients are summed over ranks, identical Adam on every rank."""
 
     ALIGN = 64
 
     def __init__(self, name: str, chains: List[List[tuple]], device, lr=5e-3, weight_decay=1e-6,
-                 betas=(0.9, 0.999), eps=1e-8, segments: Optional[List[List[List[tuple]]]] = None,
-                 split_first: int = 1, row_shard_first: bool = False):
-        """``chains`` (tail) / ``segments[i]`` (sharded when world > 1): lists of chains; a chain is a list
-        of ``(param, transposed)`` stored back to back (e.g. mean/var head weights = one matrix)."""
+                 betas=(0.9, 0.999), eps=1e-8, sharded: Optional[List[tuple]] = None, world: int = 1, rank: int = 0,
+                 background_last: bool = True):
+        """``chains`` (tail): lists of ``(param, transposed)`` stored back to back (e.g. mean/var head weights =
+        one matrix).  ``sharded``: ``(param, transposed)`` whose physical rows are gene rows."""
         self.name, self.lr, self.wd, self.betas, self.eps = name, lr, weight_decay, betas, eps
-        self.world, self.rank = dp.world_size(), dp.rank()
+        self.world, self.rank = int(world), int(rank)
         self.params: List[nn.Parameter] = []
         self.offset: Dict[int, int] = {}
         self.transposed: Dict[int, bool] = {}
-        segments = segments or []
-        seg_align = self.world * 256
+        self.rows_pad: Dict[int, int] = {}      # id(param) -> padded rows of a row-sharded parameter
+        sharded = sharded or []
+        self.sharded = self.world > 1 and len(sharded) > 0
+        self.per = 0
         total = 0
-        self.seg_bounds: List[tuple] = []
-
-        def place(chain_list):
-            nonlocal total
-            for chain in chain_list:
-                total = _ceil(total, self.ALIGN)
-                for p, tr in chain:
-                    self.params.append(p)
-                    self.offset[id(p)] = total
-                    self.transposed[id(p)] = tr
-                    total += p.numel()
-
-        self.first_rows: List[tuple] = []      # row ranges of the first parameter covered by segments 0..k-1
-        # row_shard_first (world > 1): segment 0 holds ONE row-major matrix and is padded to world * Rs rows
-        # (Rs a multiple of 128) so that rank r's ZeRO shard is exactly rows [r*Rs, (r+1)*Rs): the rank can then
-        # COMPUTE its shard of the summed gradient from all-gathered inputs instead of reduce-scattering it
-        self.row_shard: Optional[tuple] = None   # (rows per rank, width, padded rows)
-        for si, seg in enumerate(segments):
-            total = _ceil(total, seg_align)
-            lo = total
-            place(seg)
-            if si == 0 and row_shard_first and self.world > 1:
-                assert len(seg) == 1 and len(seg[0]) == 1, "row-sharded segment = one matrix"
-                p0, tr0 = seg[0][0]
-                rows, width = (p0.shape[1], p0.shape[0]) if tr0 else (p0.shape[0], p0.shape[1])
+        self.shard_blocks: List[tuple] = []     # (flat lo of the padded block, rows_pad, width)
+        for p, tr in sharded:
+            rows, width = self._rows_width(p, tr)
+            total = _ceil(total, 256)
+            self.params.append(p)
+            self.offset[id(p)] = total
+            self.transposed[id(p)] = tr
+            if self.world > 1:
                 per = dp.shard_rows(rows, self.world)
-                assert (per * width) % 256 == 0
-                total = lo + self.world * per * width
-                self.row_shard = (per, width, self.world * per)
-                self.seg_bounds.append((lo, total))
-                self.first_rows = [(0, 0)]
-                continue
-            total = _ceil(total, seg_align)
-            if si == 0 and split_first > 1 and self.world > 1:
-                # cut segment 0 inside its first (big, row-major) parameter at 128-row boundaries so that
-                # finished row ranges of its gradient can be exchanged while the rest is still computed
-                p0, tr0 = seg[0][0]
-                rows, width = (p0.shape[1], p0.shape[0]) if tr0 else (p0.shape[0], p0.shape[1])
-                per = _ceil((rows + split_first - 1) // split_first, 128)
-                cuts = [r for r in range(per, rows, per)]
-                if all((r * width) % seg_align == 0 for r in cuts) and self.offset[id(p0)] == lo:
-                    edges = [0] + cuts + [rows]
-                    starts = [lo + r * width for r in edges[:-1]]
-                    ends = starts[1:] + [total]
-                    self.seg_bounds += list(zip(starts, ends))
-                    self.first_rows = list(zip(edges[:-1], edges[1:]))
-                    continue
-            self.seg_bounds.append((lo, total))
-            if si == 0:
-                self.first_rows = [(0, 0)]
-        self.n_first = max(len(self.first_rows), 1)   # segments 0..n_first-1 = pieces of the original segment 0
+                assert self.per in (0, per), "row-sharded parameters of a group share the gene axis"
+                self.per = per
+                rows_p = self.world * per
+            else:
+                rows_p = rows
+            self.rows_pad[id(p)] = rows_p
+            self.shard_blocks.append((total, rows_p, width))
+            total += rows_p * width
+        total = _ceil(total, 256)
         self.tail_lo = total
-        place(chains)
+        for chain in chains:
+            total = _ceil(total, self.ALIGN)
+            for p, tr in chain:
+                self.params.append(p)
+                self.offset[id(p)] = total
+                self.transposed[id(p)] = tr
+                total += p.numel()
         self.n = _ceil(max(total, 4), 4)
-        self.sharded = self.world > 1 and len(self.seg_bounds) > 0
-        # ranges the optimizer walks: (flat lo, flat hi, grad buffer, offset into m/v)
         self.p = torch.zeros(self.n, device=device, dtype=torch.float32)
         self.g = torch.zeros(self.n, device=device, dtype=torch.float32)
         self.p16 = torch.zeros(self.n, device=device, dtype=torch.bfloat16)
-        self.gs: List[torch.Tensor] = []       # reduce-scatter outputs (one per segment)
+        # ranges the optimizer walks on this rank: (flat lo, flat hi, offset into m/v)
         self.ranges: List[tuple] = []
         mv = 0
         if self.sharded:
-            for lo, hi in self.seg_bounds:
-                ns = (hi - lo) // self.world
-                gs = torch.zeros(ns, device=device, dtype=torch.float32)
-                self.gs.append(gs)
-                own = lo + self.rank * ns
-                self.ranges.append((own, own + ns, gs, mv))
-                mv += ns
-            self.ranges.append((self.tail_lo, self.n, self.g[self.tail_lo:self.n], mv))
+            for lo, rows_p, width in self.shard_blocks:
+                own = lo + self.rank * self.per * width
+                n_own = self.per * width
+                self.ranges.append((own, own + n_own, mv))
+                mv += _ceil(n_own, 4)
+            self.ranges.append((self.tail_lo, self.n, mv))
             mv += self.n - self.tail_lo
         else:
-            self.ranges.append((0, self.n, self.g, 0))
+            self.ranges.append((0, self.n, 0))
             mv = self.n
         self.m = torch.zeros(mv, device=device, dtype=torch.float32)
         self.v = torch.zeros(mv, device=device, dtype=torch.float32)
+        # single process: the LAST row-sharded block (the output layer, which the next forward reads last) may be
+        # updated on a background stream underneath the next step; data parallel: same, for this rank's rows
+        self.bg_range = (len(self.shard_blocks) - 2) if (background_last and len(self.shard_blocks) >= 2) else None
         self.step_count = 0
         self.applied = False    # set by the fused step after its own clip+Adam launch; consumed by FlatAdam.step()
+        self.master_dirty = False
         self._vec_range: Optional[tuple] = None
         self._deferred: Optional[torch.cuda.Event] = None   # output-layer update in flight on the background stream
-        self.first_by_inputs = False   # set per step by the engine when gs[0] was produced from gathered inputs
-        self._ag_pending: List = []
         for p in self.params:
             phys = self.phys(p)
             src = p.data.to(device)
@@ -154,15 +131,22 @@ class FlatGroup:
             L.SHADOWS[id(p)] = self.phys(p, self.p16)
         self.refresh_shadow()
 
+    @staticmethod
+    def _rows_width(p, tr):
+        if p.dim() == 1:
+            return p.shape[0], 1
+        return (p.shape[1], p.shape[0]) if tr else (p.shape[0], p.shape[1])
+
     def zero_vector_grads(self):
         """one fill per step over the gradients of the 1-D parameters (biases, BatchNorm affine): the kernels
         that produce them accumulate, instead of each issuing its own memsets in the middle of the backward
         pass.  Matrix gradients are overwritten by their GEMMs and need no zeroing."""
         if self._vec_range is None:
-            vec = [(self.offset[id(p)], self.offset[id(p)] + p.numel()) for p in self.params if p.dim() == 1]
+            vec = [(self.offset[id(p)], self.offset[id(p)] + self.rows_pad.get(id(p), p.numel()))
+                   for p in self.params if p.dim() == 1]
             if not vec:
                 self._vec_range = (0, 0)
-            elif self.seg_bounds:       # tail = vectors first, then (data parallel) the small matrices
+            elif self.shard_blocks:     # vectors are contiguous: [sharded bias | tail vectors first]
                 self._vec_range = (min(a for a, _ in vec), max(b for _, b in vec))
             else:                       # small group with interleaved layout: clear everything
                 self._vec_range = (0, self.n)
@@ -179,30 +163,38 @@ class FlatGroup:
             shape = shape[::-1]
         return buf[o:o + p.numel()].view(shape)
 
+    def phys_padded(self, p: nn.Parameter, buf: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """row-sharded parameter incl. its padding rows: ``[rows_pad, width]`` (``[rows_pad]`` for a vector)"""
+        buf = self.p if buf is None else buf
+        o = self.offset[id(p)]
+        rows_p = self.rows_pad[id(p)]
+        rows, width = self._rows_width(p, self.transposed[id(p)])
+        t = buf[o:o + rows_p * width]
+        return t if p.dim() == 1 else t.view(rows_p, width)
+
+    def own_rows(self, p: nn.Parameter, buf: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """this rank's rows ``[rank * per, (rank + 1) * per)`` of a row-sharded parameter"""
+        t = self.phys_padded(p, buf)
+        if not self.sharded:
+            return t
+        return t[self.rank * self.per:(self.rank + 1) * self.per]
+
     def refresh_shadow(self):
         ops.cast_bf16(self.p, self.p16)
 
-    # ---- gradient exchange (world > 1) ----
-    def exchange_segment_async(self, i: int):
-        """reduce-scatter (SUM) of segment i's gradient into this rank's shard buffer"""
-        if not self.sharded:
-            return None
-        if i == 0 and self.first_by_inputs:
-            return None    # the shard of the summed gradient was computed in place (StepEngine._first_layer_grad_shard)
-        lo, hi = self.seg_bounds[i]
-        return torch.distributed.reduce_scatter_tensor(self.gs[i], self.g[lo:hi], async_op=True)
-
-    def exchange_rest_async(self):
-        """all-reduce (SUM) of everything that is not sharded"""
-        if self.world == 1:
-            return None
-        lo = self.tail_lo if self.sharded else 0
-        return dp.allreduce_sum_(self.g[lo:self.n], async_op=True)
-
-    def grad_norm_sq(self, out: torch.Tensor, skip: Optional[List[nn.Parameter]] = None):
-        """out (double[1], pre-zeroed) += || sum_r g_r ||^2 over the whole group (padding is zero).
-        ``skip``: parameters whose contribution a producer kernel already added to ``out`` (single process)."""
-        if skip and not self.sharded and self.world == 1:
+    def grad_norm_sq(self, out: torch.Tensor, skip: Optional[List[nn.Parameter]] = None, shard_out=None):
+        """out (double[1], pre-zeroed) += || sum_r g_r ||^2 over the replicated part (single process: the whole
+        group; padding is zero).  ``skip``: row-sharded parameters whose contribution a producer kernel already
+        added.  Data parallel: the sum of squares of THIS rank's rows goes to ``shard_out`` (the engine adds the
+        other ranks' shares after the scalar exchange)."""
+        skip_ids = {id(p) for p in (skip or [])}
+        if self.sharded:
+            for (lo, hi, _), p in zip(self.ranges, [q for q in self.params if id(q) in self.rows_pad]):
+                if id(p) not in skip_ids:
+                    ops.sumsq(self.g[lo:hi], shard_out)
+            ops.sumsq(self.g[self.tail_lo:self.n], out)
+            return
+        if skip_ids:
             cuts = sorted((self.offset[id(p)], self.offset[id(p)] + p.numel()) for p in skip)
             lo = 0
             for a, b in cuts + [(self.n, self.n)]:
@@ -211,29 +203,35 @@ class FlatGroup:
                     ops.sumsq(self.g[lo4:a4], out)
                 lo = b
             return
-        if self.sharded:
-            for gs in self.gs:
-                ops.sumsq(gs, out)
-            torch.distributed.all_reduce(out)
-            ops.sumsq(self.g[self.tail_lo:self.n], out)
-        else:
-            ops.sumsq(self.g, out)
+        ops.sumsq(self.g, out)
 
     def clip_adam(self, norm_sq: torch.Tensor, max_norm: Optional[float], grad_scale: float = 1.0,
                   background: Optional[torch.cuda.Stream] = None):
-        """fused clip + Adam over the group.  ``background`` (single process only): the LAST segment (the output
-        layer, which the next forward pass reads last) is updated on that low-priority stream, after everything
-        else, so the update runs underneath the next step's forward; ``wait_shadow("rest")`` joins it."""
+        """fused clip + Adam over the ranges this rank owns.  ``background``: the output layer's range (which the
+        next forward pass reads last) is updated on that low-priority stream, after everything else, so the update
+        runs underneath the next step's forward; ``join_background()`` joins it."""
         self.step_count += 1
         self.applied = True
-        self._ag_pending = []
+        self.master_dirty = True     # rows owned by other ranks are now stale in this rank's fp32 buffer
         hyper = (self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.step_count)
-        if background is not None and not self.sharded and len(self.seg_bounds) >= 2:
-            lo1, hi1 = self.seg_bounds[-1]
-            for lo, hi in ((0, lo1), (hi1, self.n)):
-                if hi > lo:
-                    ops.clip_adam(self.p[lo:hi], self.g[lo:hi], self.m[lo:hi], self.v[lo:hi], self.p16[lo:hi],
-                                  norm_sq, max_norm or 0.0, grad_scale, *hyper)
+        if self.sharded:
+            todo = list(self.ranges)
+            bg = todo.pop(len(self.shard_blocks) - 2) if (background is not None and self.bg_range is not None) else None
+        elif background is not None and self.bg_range is not None:
+            lo1, rows_p, width = self.shard_blocks[self.bg_range]
+            hi1 = _ceil(lo1 + rows_p * width, 4)
+            todo = [(0, lo1, 0), (hi1, self.n, hi1)]
+            bg = (lo1, hi1, lo1)
+        else:
+            todo, bg = list(self.ranges), None
+        for lo, hi, mv in todo:
+            n = hi - lo
+            if n > 0:
+                ops.clip_adam(self.p[lo:hi], self.g[lo:hi], self.m[mv:mv + n], self.v[mv:mv + n], self.p16[lo:hi],
+                              norm_sq, max_norm or 0.0, grad_scale, *hyper)
+        if bg is not None:
+            lo, hi, mv = bg
+            n = hi - lo
             first_done = torch.cuda.Event()
             first_done.record()
             # the clip norm lives in the step's scalar block: keep the allocator from recycling that block for a
@@ -241,32 +239,14 @@ class FlatGroup:
             norm_sq.record_stream(background)
             with torch.cuda.stream(background), ops.stream_scope(background):
                 background.wait_event(first_done)
-                ops.clip_adam(self.p[lo1:hi1], self.g[lo1:hi1], self.m[lo1:hi1], self.v[lo1:hi1], self.p16[lo1:hi1],
+                ops.clip_adam(self.p[lo:hi], self.g[lo:hi], self.m[mv:mv + n], self.v[mv:mv + n], self.p16[lo:hi],
                               norm_sq, max_norm or 0.0, grad_scale, *hyper, background=True)
                 self._deferred = torch.cuda.Event()
                 self._deferred.record(background)
-            return
-        for i, (lo, hi, g, mv) in enumerate(self.ranges):
-            n = hi - lo
-            ops.clip_adam(self.p[lo:hi], g, self.m[mv:mv + n], self.v[mv:mv + n], self.p16[lo:hi], norm_sq,
-                          max_norm or 0.0, grad_scale, *hyper)
-            if self.sharded and i < len(self.seg_bounds):
-                # publish the refreshed bf16 shard right away (segment 0 = first-layer weight is needed first by
-                # the next forward); consumers wait just before they read it
-                slo, shi = self.seg_bounds[i]
-                self._ag_pending.append(torch.distributed.all_gather_into_tensor(
-                    self.p16[slo:shi], self.p16[lo:hi], async_op=True))
 
-    def wait_shadow(self, which: Optional[str] = None):
-        """make the current stream wait for the all-gather of bf16 shadows: "first" = the pieces of the original
-        segment 0 (first-layer weight), "rest" = the other segments, None = all; "rest"/None also join an
-        output-layer update still running on the background stream"""
-        for j, w in enumerate(self._ag_pending):
-            hit = which is None or (which == "first") == (j < self.n_first)
-            if w is not None and hit:
-                w.wait()
-                self._ag_pending[j] = None
-        if which != "first" and self._deferred is not None:
+    def join_background(self):
+        """make the current stream wait for an output-layer update still running on the background stream"""
+        if self._deferred is not None:
             torch.cuda.current_stream().wait_event(self._deferred)
             self._deferred = None
 
@@ -275,17 +255,26 @@ class FlatGroup:
         t = self.phys(p, buf)
         return t.t() if self.transposed[id(p)] else t
 
+    def _gather_rows(self, own: torch.Tensor, full: torch.Tensor):
+        """full[world * n] <- all ranks' own[n] (rare: state_dict / checkpoint time; torch.distributed plumbing)"""
+        if torch.distributed.get_backend() == "nccl":
+            torch.distributed.all_gather_into_tensor(full, own.contiguous())
+        else:
+            parts = [torch.empty(own.numel(), dtype=own.dtype) for _ in range(self.world)]
+            torch.distributed.all_gather(parts, own.detach().cpu().contiguous())
+            full.copy_(torch.cat(parts))
+
     def full_moments(self):
         """Adam moments laid out like the value buffer (``[n]`` each).  Single process: the live buffers.
-        ZeRO-sharded: fresh full-size copies, the sharded segments all-gathered from their owners."""
+        Gene-sharded: fresh full-size copies, the row-sharded blocks all-gathered from their owners."""
         if not self.sharded:
             return self.m, self.v
         out = []
         for src in (self.m, self.v):
             full = torch.zeros(self.n, device=src.device, dtype=torch.float32)
-            for (lo, hi), (own_lo, own_hi, _, mv) in zip(self.seg_bounds, self.ranges):
-                torch.distributed.all_gather_into_tensor(full[lo:hi], src[mv:mv + own_hi - own_lo].contiguous())
-            _, _, _, mv = self.ranges[-1]
+            for (lo, rows_p, width), (own_lo, own_hi, mv) in zip(self.shard_blocks, self.ranges):
+                self._gather_rows(src[mv:mv + own_hi - own_lo], full[lo:lo + rows_p * width])
+            _, _, mv = self.ranges[-1]
             full[self.tail_lo:self.n].copy_(src[mv:mv + self.n - self.tail_lo])
             out.append(full)
         return out
@@ -295,17 +284,20 @@ class FlatGroup:
         if not self.sharded:
             return
         for src, dst in ((m_full, self.m), (v_full, self.v)):
-            for (own_lo, own_hi, _, mv) in self.ranges:
+            for (own_lo, own_hi, mv) in self.ranges:
                 dst[mv:mv + own_hi - own_lo].copy_(src[own_lo:own_hi])
 
     def sync_master(self):
-        """all-gather the fp32 master copy of the sharded segments (before state_dict / fp32 evaluation)"""
-        if not self.sharded:
-            self.wait_shadow()
+        """refresh the rows of the row-sharded fp32 parameters that other ranks own (before state_dict / fp32
+        evaluation); also joins a background update"""
+        self.join_background()
+        if not self.sharded or not self.master_dirty:
             return
-        self.wait_shadow()
-        for (lo, hi), (own_lo, own_hi, _, _) in zip(self.seg_bounds, self.ranges):
-            torch.distributed.all_gather_into_tensor(self.p[lo:hi], self.p[own_lo:own_hi])
+        self.master_dirty = False
+        for (lo, rows_p, width), (own_lo, own_hi, _) in zip(self.shard_blocks, self.ranges):
+            own = self.p[own_lo:own_hi].clone()
+            self._gather_rows(own, self.p[lo:lo + rows_p * width])
+        self.refresh_shadow()
 
 
 class FlatAdam(torch.optim.Optimizer):
@@ -464,10 +456,19 @@ class StepEngine:
         if self.device.type != "cuda":
             raise RuntimeError("StepEngine needs a CUDA device (no CPU fallback)")
         self.precision = precision or L.get_precision()
-        # world > 1: the first-layer weight gradient shard is computed from all-gathered inputs (packed CSR, window
-        # pointers, dY) instead of reduce-scattering 4*G*H1 bytes of output; CMMVAE_DP_BY_INPUTS=0 -> reduce-scatter
-        self.dp_by_inputs = os.environ.get("CMMVAE_DP_BY_INPUTS", "1") != "0" and self.precision == "bf16"
-        self._dp_cap = None
+        # data parallel (one process per GPU): peer-memory exchange, gene-sharded first / last layer.
+        # CMMVAE_FORCE_DP=1 runs that route with a single process (its own "peer"): the single-GPU test of the route
+        self.comm = None
+        self.world, self.rank = 1, 0
+        if dp.world_size() > 1 or os.environ.get("CMMVAE_FORCE_DP") == "1":
+            if self.precision != "bf16":
+                raise RuntimeError("the data-parallel route runs the bf16 policy only (tensor-pipe SpMM, fused decoder)")
+            from .peer import PeerComm
+            self.comm = PeerComm(self.device)
+            self.world, self.rank = self.comm.world, self.comm.rank
+        self._dp = None          # symmetric buffers, allocated on the first step (needs B and nnz)
+        self._dp_step = 0
+        self._csr_pushed = {}    # (pointers, nnz) of a prefetched batch -> step it was pushed for
         # single process: run the step on a high-priority stream and the output layer's clip+Adam on a
         # low-priority one, underneath the next step's forward pass (37 % of a B=1024 step is optimizer HBM
         # traffic, half of it the output layer whose new value is only needed by the decoder kernel).  Weights
@@ -475,7 +476,6 @@ class StepEngine:
         # pipelined mode, sync_logging=False)
         self.pipeline_optimizer = False
         self._hp = self._bg = None
-        self.dp_chunks = int(os.environ.get("CMMVAE_DP_CHUNKS", "2"))     # world > 1: pieces the first-layer weight gradient is exchanged in (overlap)
         self.adv_weight = adv_weight
         self.clip = clip or {"vae": 10.0, "expert": 10.0, "adversarial": 10.0}
         vae = module.vae
@@ -491,19 +491,18 @@ class StepEngine:
         self.enc_plan: Dict[str, List[LayerPlan]] = {}
         self.dec_plan: Dict[str, List[LayerPlan]] = {}
         for eid, expert in module.experts.items():
-            # big matrices: segment 0 = everything but the output layer, segment 1 = the output layer (its
-            # gradient is final first, so its exchange overlaps the rest of the backward pass); vectors: tail
-            mats = _block_chains(expert.encoder, sparse_first=True, kind="matrix") + \
-                _block_chains(expert.decoder, kind="matrix")
-            vecs = _block_chains(expert.encoder, kind="vector") + _block_chains(expert.decoder, kind="vector")
-            if dp.world_size() > 1 and self.dp_by_inputs:
-                # first-layer weight alone in segment 0 with row-aligned shards (its gradient shard is computed
-                # from all-gathered inputs); the two small matrices join the replicated tail
-                g = FlatGroup(f"experts/{eid}", vecs + mats[1:-1], dev, segments=[mats[:1], mats[-1:]],
-                              row_shard_first=True)
-            else:
-                g = FlatGroup(f"experts/{eid}", vecs, dev, segments=[mats[:-1], mats[-1:]],
-                              split_first=self.dp_chunks)
+            # row-sharded by genes when data parallel: first-layer weight (stored [genes, hidden]), output-layer
+            # weight [genes, hidden] and output bias [genes]; replicated tail: vectors first, then the small matrices
+            w1 = expert.encoder.fc_layers[0].lin.weight
+            last_lin = expert.decoder.fc_layers[len(expert.decoder.fc_layers) - 1].lin
+            big = {id(w1), id(last_lin.weight), id(last_lin.bias)}
+            mats = [c for c in _block_chains(expert.encoder, kind="matrix") + _block_chains(expert.decoder, kind="matrix")
+                    if id(c[0][0]) not in big]
+            vecs = [c for c in _block_chains(expert.encoder, kind="vector") + _block_chains(expert.decoder, kind="vector")
+                    if id(c[0][0]) not in big]
+            g = FlatGroup(f"experts/{eid}", vecs + mats, dev,
+                          sharded=[(w1, True), (last_lin.weight, False), (last_lin.bias, False)],
+                          world=self.world, rank=self.rank)
             self.groups[f"experts/{eid}"] = g
             self.enc_plan[eid] = _plan_block(expert.encoder, g, sparse_first=True)
             self.dec_plan[eid] = _plan_block(expert.decoder, g)
@@ -566,10 +565,8 @@ class StepEngine:
         self.timers: Optional[Dict[str, list]] = None   # name -> [(start_event, end_event)] when profiling
         self.timer_filter = None   # optional set of section names to time (an event record ends a PDL chain)
         self._seed = 0x5EED
-        self.nccl_sms = int(os.environ.get("CMMVAE_NCCL_SMS", "32"))                  # SMs left to communication kernels when world > 1
         self.spmm_tc = True                 # bf16 policy: expert-encoder SpMM on the tensor pipe ...
         self.spmm_tc_min_density = 0.015    # ... when the batch is at least this dense (else gather kernel)
-        self.world = 1
         self.last = None
 
     # ------------------------------------------------------------------------------------ utilities
@@ -640,11 +637,14 @@ class StepEngine:
         ops.gemm(x32, 0, lp.W32, 0, B, lp.N, lp.K, bias=lp.b, relu=fuse_relu, C32=y32, use_tc=False)
         return y32, None
 
-    def _layer_fwd(self, tag, lp: LayerPlan, x32, x16, B, csr=None, training=True, masks=None):
-        """full layer; returns (out32, out16, cache)"""
+    def _layer_fwd(self, tag, lp: LayerPlan, x32, x16, B, csr=None, training=True, masks=None, Y_pre=None):
+        """full layer; returns (out32, out16, cache).  ``Y_pre``: the layer's linear part was computed elsewhere
+        (data-parallel first layer: partial sums from all ranks)"""
         want16 = self.precision == "bf16"
         plain = lp.bn is None and lp.p_drop == 0.0
-        if lp.sparse:
+        if Y_pre is not None:
+            Y, y16, fused_relu = Y_pre, None, False
+        elif lp.sparse:
             crow, col, val, G, tp = csr
             Wt = lp.W16 if self.precision == "bf16" else lp.W32
             ev = self._t0("csr_linear_fwd")
@@ -699,16 +699,11 @@ class StepEngine:
             dY16 = ops.cast_bf16(dY, self.ws(tag + ".dY16", (B, lp.N), torch.bfloat16)) if want16 else None
             ops.colsum(dY, lp.gb, accumulate=True)
         if lp.sparse:
-            if csc[0] == "tc":
-                _, tp, G, ssq, pending, gathered = csc
-                if gathered is not None:
-                    self._first_layer_grad_shard(lp.group, gathered, dY16, B)
-                    return None
-                pieces = lp.group.first_rows if (lp.group.sharded and lp.group.n_first > 1) else [(0, G)]
-                for i, (g0, g1) in enumerate(pieces):
-                    ops.csr_linear_bwd_w_tc(tp[1], tp[0], B, G, dY16, lp.gW, sumsq_out=ssq, g_begin=g0, g_end=g1)
-                    if i + 1 < len(pieces):   # this row range is final: exchange it while the next one is computed
-                        pending.append(lp.group.exchange_segment_async(i))
+            if csc[0] == "dp":
+                self._dp_first_layer_grad(csc[1], lp, dY16, B)
+            elif csc[0] == "tc":
+                _, tp, G, ssq = csc
+                ops.csr_linear_bwd_w_tc(tp[1], tp[0], B, G, dY16, lp.gW, sumsq_out=ssq)
             else:
                 _, cptr, ridx, cval, G = csc
                 ops.csr_linear_bwd_w(cptr, ridx, cval, B, G, dY, lp.gW)
@@ -783,61 +778,276 @@ class StepEngine:
         self._join_side()
         return d
 
-    # ------------------------------------------------------------- data parallel: first layer by inputs
-    def _dp_capacity(self, n_packed: int, B: int) -> int:
-        """records per rank in the all-gathered packed CSR (identical on every rank; agreed once, with headroom)"""
-        if self._dp_cap is None:
-            t = torch.tensor([n_packed, B, -B], dtype=torch.int64, device=self.device)
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-            mx, bmax, bmin = (int(v) for v in t.tolist())
-            if bmax != -bmin:
-                raise RuntimeError("data-parallel step needs the same number of cells on every rank")
-            self._dp_cap = _ceil(int(mx * 1.15) + 1024, 1024)
-        if n_packed > self._dp_cap:
-            raise RuntimeError(f"batch with {n_packed} non-zero records exceeds the data-parallel CSR capacity "
-                               f"{self._dp_cap} agreed on the first step; set engine._dp_cap (same value on every "
-                               "rank) before training on batches of very different density")
-        return self._dp_cap
+    # ------------------------------------------------------ data parallel over peer memory (gene shards)
+    # Cells shard across ranks; the two gene-sized layers shard by GENES.  Rank r owns rows
+    # [r * per, (r + 1) * per) of W1 (stored [genes, hidden]), Wout and bout -- values, gradients, Adam state -- and
+    # multiplies them against the cells of ALL ranks:
+    #   forward   Y_part[N*B, H1] = X_all[:, genes_r] W1[genes_r]   epilogue stores each cell block into its owner's
+    #             buffer (peer memory), the owner sums the N slabs                               ("reduce-scatter")
+    #             h of all ranks is pushed to every rank ("all-gather", 2 MB per rank), the fused decoder runs on
+    #             h_all x Wout[genes_r] against X_all[:, genes_r]: dlogits, dWout[genes_r], dbout[genes_r] stay local
+    #   backward  dh_part[N*B, Hd] = dlogits Wout[genes_r]          routed to the owners like Y_part
+    #             dW1[genes_r] = X_all[:, genes_r]^T dY_all          (dY pushed like h)
+    # What crosses NVLink per step and rank: the CSR records of the batch (prefetched one step ahead), two
+    # [N*B, hidden] f32 partial-sum slabs, two [B, hidden] bf16 all-gathers and ~6 MB of small gradients -- instead
+    # of 500 MB of gradient all-reduce.  No gradient, weight or optimizer state of the 125 M gene-sized parameters is
+    # ever exchanged; the sums over ranks that DDP takes on gradients are taken on the layer's inputs.
+    def _dp_setup(self, B: int, nnz: int, H1: int, Hd: int):
+        """collective, first step: agree on capacities and allocate the symmetric buffers"""
+        comm, N = self.comm, self.world
+        mx, bmax, bmin = dp.host_allreduce_max([nnz, B, -B])
+        if bmax != -bmin:
+            raise RuntimeError("data-parallel step needs the same number of cells on every rank")
+        cap = _ceil(int(mx * float(os.environ.get("CMMVAE_DP_CSR_HEADROOM", "1.5"))) + 4096, 1024)
+        d = dict(B=B, cap=cap, H1=H1, Hd=Hd)
+        d["col_off"] = _ceil(4 * (B + 1), 256)
+        d["val_off"] = d["col_off"] + 4 * cap
+        d["slab"] = d["val_off"] + 4 * cap
+        d["csr"] = [comm.alloc(f"csr{i}", N * d["slab"]) for i in range(2)]
+        d["stage"] = [torch.zeros(d["slab"], dtype=torch.uint8, device=self.device) for _ in range(2)]
+        d["Yin"] = comm.alloc("Yin", N * B * H1 * 4)
+        d["hall"] = comm.alloc("hall", N * B * Hd * 2)
+        d["dhin"] = comm.alloc("dhin", N * B * Hd * 4)
+        d["dYall"] = comm.alloc("dYall", N * B * H1 * 2)
+        d["SC"] = 32
+        d["scal"] = comm.alloc("scal", N * d["SC"] * 8)
+        d["tails"] = {}
+        # shard CSR capacity: a gene shard of all ranks' cells holds about one rank's worth of non-zeros
+        d["cap_s"] = _ceil(int(cap * float(os.environ.get("CMMVAE_DP_SHARD_HEADROOM", "1.0"))), 1024)
+        d["stream"] = torch.cuda.Stream(self.device)
+        d["ticket_pf"] = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._dp = d
+        return d
 
-    def _dp_gather_csr(self, gexp: FlatGroup, tp, B: int, cap: int):
-        """start the exchange that lets every rank compute ITS gene shard of the summed first-layer weight
-        gradient: all-gather of the packed CSR records (4 B per non-zero) and all-to-all of the window pointers
-        (rank r receives, from every rank, the pointer rows of r's windows, rebased into the gathered array).
-        Runs on the NCCL stream under the forward pass; consumed by ``_first_layer_grad_shard``."""
-        per, width, _ = gexp.row_shard
-        world, rank, WS = self.world, dp.rank(), gexp.row_shard[0] // 64
-        table, packed = tp
-        packed_all = self.ws("dp.packed_all", (world * cap,), torch.int32)
-        w_pk = torch.distributed.all_gather_into_tensor(packed_all, packed[:cap], async_op=True)
-        tp2d = table.view(-1, B)                                # [world * WS + 1, B]
-        send = self.ws("dp.tp_send", (world, WS + 1, B), torch.int32)
-        send[:, :WS].copy_(tp2d[:world * WS].view(world, WS, B))
-        send[:, WS].copy_(tp2d[WS::WS][:world])                 # closing row of every shard
-        send += rank * cap
-        recv = self.ws("dp.tp_recv", (world, WS + 1, B), torch.int32)
-        w_tp = torch.distributed.all_to_all_single(recv.view(-1), send.view(-1), async_op=True)
-        return dict(packed_all=packed_all, recv=recv, waits=[w_pk, w_tp], WS=WS)
+    def set_dp_capacity(self, max_nnz_per_rank: int):
+        """(before the first step, same value on every rank) non-zeros per rank the exchange buffers are sized for;
+        default: 1.5 x the densest first batch"""
+        os.environ["CMMVAE_DP_CSR_HEADROOM"] = "1.0"
+        self._dp_force_nnz = int(max_nnz_per_rank)
 
-    def _first_layer_grad_shard(self, gexp: FlatGroup, gathered, dY16, B: int):
-        """dW1^T[shard] = X_all^T[shard] . dY_all  -- the shard of the SUM over ranks, written straight into the
-        ZeRO gradient shard (no 4*G*H1-byte reduce-scatter; only dY, 2*B*H1 bytes per rank, is exchanged here)"""
-        per, width, rows_pad = gexp.row_shard
-        world, rank, WS = self.world, dp.rank(), gathered["WS"]
-        for w in gathered["waits"]:
-            w.wait()
-        tp_shard = self.ws("dp.tp_shard", (WS + 1, world * B), torch.int32)
-        tp_shard.view(WS + 1, world, B).copy_(gathered["recv"].permute(1, 0, 2))
-        dY_all = self.ws("dp.dY_all", (world * B, width), torch.bfloat16)
-        torch.distributed.all_gather_into_tensor(dY_all, dY16)
-        ops.csr_linear_bwd_w_tc_shard(gathered["packed_all"], tp_shard, world * B, rows_pad, dY_all,
-                                      gexp.gs[0].view(per, width), rank * per, (rank + 1) * per)
+    def _dp_tail(self, group: FlatGroup, n: int):
+        d = self._dp
+        buf = d["tails"].get(group.name)
+        if buf is None:
+            buf = d["tails"][group.name] = self.comm.alloc(f"tail/{group.name}", self.world * _ceil(n, 4) * 4)
+        return buf
+
+    def _dp_push_csr(self, crow, col, val, nnz: int, step: int, ticket=None):
+        """this rank's batch -> slab `rank` of every rank's gathered-CSR buffer (parity of the consuming step)"""
+        d, N, r = self._dp, self.world, self.rank
+        if nnz > d["cap"]:
+            raise RuntimeError(f"batch with {nnz} non-zeros exceeds the data-parallel exchange capacity {d['cap']} "
+                               "agreed on the first step; call engine.set_dp_capacity(n) (same n on every rank) "
+                               "before training on batches of very different density")
+        par = step & 1
+        B = d["B"]
+        st = d["stage"][par]
+        st[:4 * (B + 1)].view(torch.int32).copy_(crow)
+        st[d["col_off"]:d["col_off"] + 4 * nnz].view(torch.int32).copy_(col)
+        st[d["val_off"]:d["val_off"] + 4 * nnz].view(torch.float32).copy_(val)
+        buf = d["csr"][par]
+        n1 = d["col_off"] + _ceil(4 * nnz, 16)
+        n2 = _ceil(4 * nnz, 16)
+        base = [p + r * d["slab"] for p in buf.ptr]
+        ticket = self.comm.ticket if ticket is None else ticket     # (one last-block counter per stream)
+        ops.peer_push(st, n1, base, None, step, ticket)
+        ops.peer_push(st[d["val_off"]:], n2, [b + d["val_off"] for b in base],
+                      self.comm.flag_ptrs(f"csr{par}"), step, ticket)
+
+    def prefetch(self, expert_id: str, crow, col, val, ready=None):
+        """data parallel: call right AFTER ``train_step`` with the NEXT batch -- its CSR records are exchanged
+        underneath the step that was just enqueued, and the next ``train_step`` on the same arrays finds its gathered
+        inputs ready (no-op with one process).  ``ready``: a CUDA event after which the arrays are complete (the
+        stager's copy event), ``True`` if they already are, ``None`` = whatever is enqueued on the current stream
+        (always correct, but the current stream waits for the running step, so nothing overlaps)."""
+        if self.comm is None or self._dp is None:
+            return None       # buffers exist after the first step
+        nnz = int(col.numel())
+        key = (crow.data_ptr(), col.data_ptr(), val.data_ptr(), nnz)
+        if self._csr_pushed:
+            return None       # one batch ahead (two buffers)
+        step = self._dp_step + 1
+        st = self._dp["stream"]
+        if ready is None:
+            ready = torch.cuda.Event()
+            ready.record()
+        with torch.cuda.stream(st), ops.stream_scope(st):
+            if ready is not True:
+                st.wait_event(ready)               # the batch arrays are complete
+            if self._dp.get("safe") is not None:   # every rank is past the step that last read this buffer parity
+                st.wait_event(self._dp["safe"])
+            self._dp_push_csr(crow, col, val, nnz, step, self._dp["ticket_pf"])
+        self._csr_pushed[key] = step
+        return None
+
+    def _dp_prepare(self, gexp: FlatGroup, enc0: LayerPlan, crow, col, val, nnz: int, B: int, G: int, Hd: int):
+        """start of a data-parallel step: gathered CSR of all ranks -> this rank's gene shard as one compact CSR
+        (+ window pointer table and packed records for the tensor-pipe kernels)"""
+        N, r = self.world, self.rank
+        if self._dp is None:
+            self._dp_setup(B, getattr(self, "_dp_force_nnz", nnz), enc0.N, Hd)
+        d = self._dp
+        if B != d["B"]:
+            raise RuntimeError(f"data-parallel step was set up for {d['B']} cells per rank, got {B}")
+        self._dp_step += 1
+        step = self._dp_step
+        par = step & 1
+        key = (crow.data_ptr(), col.data_ptr(), val.data_ptr(), nnz)
+        if self._csr_pushed.pop(key, None) != step:
+            if self._csr_pushed:
+                raise RuntimeError("prefetch() was called for a different batch than the one being stepped")
+            self._dp_push_csr(crow, col, val, nnz, step)
+        per = gexp.per if gexp.sharded else _ceil(G, 128)
+        g0 = r * per
+        g1 = min(G, g0 + per)
+        NB = N * B
+        ops.peer_wait(self.comm.local_flags(f"csr{par}"), N, step)
+        cap_s = d["cap_s"]
+        crow_s = self.ws("dp.crow_s", (NB + 1,), torch.int32)
+        col_s = self.ws("dp.col_s", (cap_s + 8,), torch.int32, zero=True)
+        val_s = self.ws("dp.val_s", (cap_s + 8,), zero=True)
+        info = self.ws("dp.info", (2,), torch.int32)
+        if g1 > g0:
+            ops.shard_csr(d["csr"][par].local, d["slab"], d["col_off"], d["val_off"], B, N, g0, g1, cap_s,
+                          self.ws("dp.cnt", (NB,), torch.int32), self.ws("dp.start", (NB,), torch.int32),
+                          crow_s, col_s, val_s, info)
+        else:      # a trailing rank that owns only padding rows
+            crow_s.zero_()
+            info.zero_()
+        tp = ops.csr_tile_ptr(crow_s, col_s, val_s, per, cap_s - 8,
+                              self.ws("dp.tp64", (NB * ((per + 63) // 64 + 1),), torch.int32),
+                              self.ws("dp.packed", (cap_s + 8,), torch.int32))
+        return dict(step=step, per=per, g0=g0, g1=g1, NB=NB, crow=crow_s, col=col_s, val=val_s, tp=tp, info=info,
+                    shard_ssq=self.ws("dp.shard_ssq", (1,), torch.float64), loss_part=self.ws("dp.loss_part", (N,), torch.float64))
+
+    def _dp_first_layer_fwd(self, dpm, gexp: FlatGroup, lp: LayerPlan, B: int):
+        """Y[B, H1] of this rank's cells = sum over gene shards (all ranks) + bias"""
+        d, N, r, step = self._dp, self.world, self.rank, dpm["step"]
+        H1 = lp.N
+        W16 = gexp.own_rows(lp.lin.weight, gexp.p16)
+        if W16.shape[0] != dpm["per"]:       # single-process test route: pad the view up to the 128-aligned shard
+            W16 = self._dp_padded("dp.W1pad", W16, dpm["per"])
+        ev = self._t0("csr_linear_fwd")
+        ops.csr_linear_fwd_tc_routed(dpm["tp"][1], dpm["tp"][0], dpm["NB"], dpm["per"], W16,
+                                     [p + r * B * H1 * 4 for p in d["Yin"].ptr], B)
+        self._t1(ev)
+        ops.peer_signal(self.comm.flag_ptrs("Y"), step)
+        ev = self._t0("dp_wait_Y")
+        ops.peer_wait(self.comm.local_flags("Y"), N, step)
+        self._t1(ev)
+        # every rank has cut its shard out of this step's gathered CSR (Y partials come after that): the buffer of
+        # the other parity may be refilled for the next step from here on
+        d["safe"] = torch.cuda.Event()
+        d["safe"].record()
+        Y = self.ws("enc0.y32", (B, H1))
+        ops.slab_sum(d["Yin"].local.view(torch.float32), N, B * H1, B * H1, out32=Y, bias=lp.b, H=H1)
+        return Y
+
+    def _dp_padded(self, name, t, rows):
+        out = self.ws(name, (rows,) + tuple(t.shape[1:]), t.dtype, zero=True)
+        out[:t.shape[0]].copy_(t)
+        return out
+
+    def _dp_decoder(self, dpm, gexp: FlatGroup, out: LayerPlan, h16, B: int):
+        """all-gather h, fused decoder + loss on (all cells) x (this rank's genes), dWout / dbout rows, and the dh
+        partial sums routed to the cells' owners.  Returns dh[B, Hd] of this rank's cells."""
+        d, N, r, step = self._dp, self.world, self.rank, dpm["step"]
+        Hd, per, NB = out.K, dpm["per"], dpm["NB"]
+        ops.peer_push(h16, B * Hd * 2, [p + r * B * Hd * 2 for p in d["hall"].ptr], self.comm.flag_ptrs("h"), step,
+                      self.comm.ticket)
+        ev = self._t0("dp_wait_h")
+        ops.peer_wait(self.comm.local_flags("h"), N, step)
+        self._t1(ev)
+        h_all = d["hall"].local.view(torch.bfloat16).view(NB, Hd)
+        W16 = gexp.own_rows(out.lin.weight, gexp.p16)
+        bout = gexp.own_rows(out.lin.bias)
+        gW = gexp.own_rows(out.lin.weight, gexp.g)
+        gb = gexp.own_rows(out.lin.bias, gexp.g)
+        if W16.shape[0] != per:
+            W16, bout = self._dp_padded("dp.Woutpad", W16, per), self._dp_padded("dp.boutpad", bout, per)
+            gW_out, gb_out = self.ws("dp.gWoutpad", (per, Hd)), self.ws("dp.gboutpad", (per,), zero=True)
+            gb_out.zero_()
+        else:
+            gW_out, gb_out = gW, gb
+        ldd = _ceil(per, 64)
+        dl = self.ws("dp.dlogits16", (NB, ldd), torch.bfloat16, zero=True)
+        ev = self._t0("decoder_mse_fused")
+        ops.decoder_mse_fused_blocks(h_all, W16, bout, per, dpm["crow"], dpm["col"], dpm["val"], dl, dpm["loss_part"],
+                                     B, dpm["tp"][0])
+        self._t1(ev)
+        dpm["shard_ssq"].zero_()
+        ev = self._t0("dWout_gemm")
+        ops.gemm(dl, 1, h_all, 1, per, Hd, NB, C32=gW_out, sumsq_out=dpm["shard_ssq"])
+        self._t1(ev)
+        ops.colsum(dl, gb_out, M=NB, N=per, accumulate=True)
+        if gW_out is not gW:
+            gW.copy_(gW_out[:gW.shape[0]])
+            gb.copy_(gb_out[:gb.shape[0]])
+        ops.sumsq(gb_out, dpm["shard_ssq"])
+        ev = self._t0("dh_gemm")
+        ops.gemm_routed(dl, 0, W16, 1, NB, Hd, per, Hd, [p + r * B * Hd * 4 for p in d["dhin"].ptr], B)
+        self._t1(ev)
+        ops.peer_signal(self.comm.flag_ptrs("dh"), step)
+        ev = self._t0("dp_wait_dh")
+        ops.peer_wait(self.comm.local_flags("dh"), N, step)
+        self._t1(ev)
+        dh = self.ws("dh", (B, Hd))
+        ops.slab_sum(d["dhin"].local.view(torch.float32), N, B * Hd, B * Hd, out32=dh)
+        return dh, dl
+
+    def _dp_first_layer_grad(self, dpm, lp: LayerPlan, dY16, B: int):
+        """dW1[genes_r] = X_all[:, genes_r]^T dY_all: this rank's rows of the gradient SUMMED over ranks"""
+        d, N, r, step = self._dp, self.world, self.rank, dpm["step"]
+        gexp, H1, per = lp.group, lp.N, dpm["per"]
+        ops.peer_push(dY16, B * H1 * 2, [p + r * B * H1 * 2 for p in d["dYall"].ptr], self.comm.flag_ptrs("dY"), step,
+                      self.comm.ticket)
+        # everything but dW1 is final now: the small (replicated) gradients travel while dW1 is computed
+        gvae = self.groups["vae"]
+        self._dp_allreduce_start(dpm, gexp, gexp.tail_lo, gexp.n)
+        self._dp_allreduce_start(dpm, gvae, 0, gvae.n)
+        ops.peer_wait(self.comm.local_flags("dY"), N, step)
+        dY_all = d["dYall"].local.view(torch.bfloat16).view(dpm["NB"], H1)
+        gW = gexp.own_rows(lp.lin.weight, gexp.g)
+        if gW.shape[0] != per:
+            tmp = self.ws("dp.gW1pad", (per, H1))
+            ops.csr_linear_bwd_w_tc(dpm["tp"][1], dpm["tp"][0], dpm["NB"], per, dY_all, tmp, sumsq_out=dpm["shard_ssq"])
+            gW.copy_(tmp[:gW.shape[0]])
+        else:
+            ops.csr_linear_bwd_w_tc(dpm["tp"][1], dpm["tp"][0], dpm["NB"], per, dY_all, gW, sumsq_out=dpm["shard_ssq"])
+
+    def _dp_allreduce_start(self, dpm, group: FlatGroup, lo: int, hi: int):
+        """push g[lo:hi] of a replicated group into slab `rank` of every rank"""
+        n = _ceil(hi - lo, 4)
+        buf = self._dp_tail(group, n)
+        ops.peer_push(group.g[lo:lo + n], n * 4, [p + self.rank * n * 4 for p in buf.ptr],
+                      self.comm.flag_ptrs(f"tail/{group.name}"), dpm["step"], self.comm.ticket)
+
+    def _dp_allreduce_finish(self, dpm, group: FlatGroup, lo: int, hi: int):
+        """g[lo:hi] <- sum over ranks"""
+        n = _ceil(hi - lo, 4)
+        buf = self._dp_tail(group, n)
+        ops.peer_wait(self.comm.local_flags(f"tail/{group.name}"), self.world, dpm["step"])
+        ops.slab_sum(buf.local.view(torch.float32), self.world, n, n, out32=group.g[lo:lo + n])
+
+    def _dp_finish_scalars(self, dpm, sc, s_norm_expert):
+        """exchange the per-rank scalars: loss share of every rank's cells and the sum of squares of this rank's
+        gradient rows; afterwards sc[0] = recon of THIS rank's cells, s_norm_expert += all shards"""
+        d, N, r, step = self._dp, self.world, self.rank, dpm["step"]
+        SC = d["SC"]
+        mine = self.ws("dp.scal_mine", (SC,), torch.float64, zero=True)
+        mine[:N].copy_(dpm["loss_part"])
+        mine[N:N + 1].copy_(dpm["shard_ssq"])
+        ops.peer_push(mine, SC * 8, [p + r * SC * 8 for p in d["scal"].ptr], self.comm.flag_ptrs("scal"), step,
+                      self.comm.ticket)
+        ops.peer_wait(self.comm.local_flags("scal"), N, step)
+        ops.dp_scalars(d["scal"].local.view(torch.float64), N, SC, r, sc[0:1], s_norm_expert)
 
     # ----------------------------------------------------------------------------------------- step
     def train_step(self, expert_id: str, crow, col, val, nnz: int, kl_weight: float, eps=None,
                    labels: Optional[Dict[str, torch.Tensor]] = None, masks=None):
         """One optimisation step on a CSR batch already resident on the device (no host sync).
         Returns the step record (device scalar block etc.) for ``scalars()``."""
-        if self.pipeline_optimizer and dp.world_size() == 1:
+        if self.pipeline_optimizer:
             if self._hp is None:
                 lo_pri, hi_pri = torch.cuda.Stream.priority_range()
                 self._hp = torch.cuda.Stream(self.device, priority=hi_pri)
@@ -851,16 +1061,11 @@ class StepEngine:
         with ops.stream_scope(torch.cuda.current_stream()):
             return self._train_step(expert_id, crow, col, val, nnz, kl_weight, eps, labels, masks)
 
-    def prefetch(self, expert_id: str, crow, col, val):
-        """data parallel: start exchanging the NEXT batch's CSR records while the current step runs (no-op with
-        one process).  ``train_step`` on the same arrays then finds its gathered inputs ready."""
-        return None
-
     def finish(self):
         """join optimizer work still in flight on the background stream (call before reading weights outside
         the engine when ``pipeline_optimizer`` is on; ``state_dict``/evaluation do it themselves)"""
         for g in self.groups.values():
-            g.wait_shadow()
+            g.join_background()
 
     def _train_step(self, expert_id, crow, col, val, nnz, kl_weight, eps, labels, masks):
         dev = self.device
@@ -873,19 +1078,13 @@ class StepEngine:
         B = crow.numel() - 1
         G = enc[0].K
         Z = self.Z
-        self.world = dp.world_size()
-        # NCCL's all-gather (start of the forward) and reduce-scatter (backward after dWout) kernels hold some
-        # SMs while they run: during those windows the persistent kernels plan for the remaining SMs so that
-        # no planned CTA has to wait for a free SM; elsewhere they use all 148
-        comm_budget = (lambda on: ops.set_sm_budget(148 - self.nccl_sms if on else 148)) if self.world > 1 \
-            else (lambda on: None)
-        comm_budget(True)
-        gscale = 1.0 / self.world
+        out = dec[-1]
+        gscale = 1.0 / self.world      # DDP semantics: the MEAN of the per-rank gradients is applied
         bf = self.precision == "bf16"
         n_adv = min(len(self.adv), self.n_hidden)   # zip(hidden, adversarials) truncates (cmmvae_model.py:67-70)
-        # scalar slots (double): 0 recon | 1..3 kl,sum mu,sum var | then norms | then CE sums
+        # scalar slots (double): 0 recon | 1..3 kl,sum mu,sum var | then norms | then CE sums | 2 data-parallel info
         n_ce = sum(len(a.conditions) for a in self.adv[:n_adv])
-        sc = torch.zeros(4 + 2 + 2 * n_adv + 2 * n_ce, dtype=torch.float64, device=dev)
+        sc = torch.zeros(4 + 2 + 2 * n_adv + 2 * n_ce + 2, dtype=torch.float64, device=dev)
         s_norm = lambda k: sc[4 + k:5 + k]  # noqa: E731   0 vae, 1 expert, 2.. disc_i, then gen_i
         ce_base = 4 + 2 + 2 * n_adv
 
@@ -897,34 +1096,29 @@ class StepEngine:
         x32 = x16 = None
         # tensor-pipe SpMM (tile densified in smem) above the density where it beats the gather kernel
         tc_ok = bf and self.spmm_tc and enc[0].N % 8 == 0 and G <= 65536
-        # data parallel: every rank must take the same route (it decides which collectives run), so the
-        # density test is dropped there
-        by_inputs = tc_ok and self.world > 1 and gexp.row_shard is not None
-        use_tc_spmm = tc_ok and (by_inputs or nnz >= self.spmm_tc_min_density * B * G)
-        gexp.first_by_inputs = by_inputs
-        G_tp = gexp.row_shard[2] if by_inputs else G     # window table padded to world * rows-per-rank genes
+        dpm = None
         tp = None
-        gathered = None
         ev = self._t0("csr_prep")
-        if use_tc_spmm:
-            n_packed = (nnz + 3) // 4 * 4 + 4
-            if by_inputs:
-                n_packed = self._dp_capacity(n_packed, B)
-            tp = ops.csr_tile_ptr(crow, col, val, G_tp, nnz,
-                                  self.ws("tp64", (B * ((G_tp + 63) // 64 + 1),), torch.int32),
-                                  self.ws_cap("packed", n_packed, torch.int32))
-            if by_inputs:
-                gathered = self._dp_gather_csr(gexp, tp, B, n_packed)
-        self._t1(ev)
-        # index preparation needs no weights: it runs while the previous step's shadow all-gather finishes
-        ev = self._t0("dp_wait_shadow_first")
-        gexp.wait_shadow("first")   # bf16 shards published by the previous step's optimizer (world > 1)
+        if self.comm is not None:
+            # data parallel: every rank takes the same route (tensor pipe, gene shards), whatever its batch density
+            if not (tc_ok and self._tc(out.K)):
+                raise RuntimeError("the data-parallel route needs the bf16 tensor-pipe kernels (hidden sizes % 8 == 0)")
+            dpm = self._dp_prepare(gexp, enc[0], crow, col, val, nnz, B, G, out.K)
+            use_tc_spmm = True
+        else:
+            use_tc_spmm = tc_ok and nnz >= self.spmm_tc_min_density * B * G
+            if use_tc_spmm:
+                n_packed = (nnz + 3) // 4 * 4 + 4
+                tp = ops.csr_tile_ptr(crow, col, val, G, nnz,
+                                      self.ws("tp64", (B * ((G + 63) // 64 + 1),), torch.int32),
+                                      self.ws_cap("packed", n_packed, torch.int32))
         self._t1(ev)
         ev_mid = None
         for j, lp in enumerate(enc):
+            Y_pre = self._dp_first_layer_fwd(dpm, gexp, lp, B) if (dpm is not None and j == 0) else None
             x32, x16, caches[("enc", j)] = self._layer_fwd(f"enc{j}", lp, x32, x16, B,
                                                             csr=(crow, col, val, G, tp) if j == 0 else None,
-                                                            masks=masks)
+                                                            masks=masks, Y_pre=Y_pre)
             if j == 0:
                 ev_mid = self._t0("mid_fwd")     # everything between the two gene-sized layers
         hidden = []
@@ -951,14 +1145,16 @@ class StepEngine:
         for j, lp in enumerate(dec[:-1]):
             x32, x16, caches[("dec", j)] = self._layer_fwd(f"dec{j}", lp, x32, x16, B, masks=masks)
         h32, h16 = x32, x16
-        out = dec[-1]
         self._t1(ev_mid)
-        ev = self._t0("dp_wait_shadow_rest")
-        gexp.wait_shadow("rest")
-        self._t1(ev)
-        comm_budget(False)      # all-gathers are done: decoder + dWout run on every SM
+        gexp.join_background()      # the output layer's update of the previous step (background stream)
         fused = self._tc(out.K) and bf
-        if fused:
+        H1 = out.K
+        # single process: the two big weight-gradient kernels add their own sum of squares to the clip norm
+        fuse_norm = dpm is None and fused and use_tc_spmm
+        if dpm is not None:
+            # decoder + loss + dWout rows + dh partial sums on (all cells) x (this rank's genes)
+            dh, dl = self._dp_decoder(dpm, gexp, out, h16, B)
+        elif fused:
             ldd = _ceil(G, 64)
             dl = self.ws("dlogits16", (B, ldd), torch.bfloat16, zero=True)
             wsb = self.ws("tileptr", (ops.decoder_mse_fused_workspace_bytes(B, G),), torch.uint8)
@@ -985,9 +1181,9 @@ class StepEngine:
                 slot += len(ap.conditions)
                 dla = self._adv_loss(f"adv{i}", ap, logits_a, labels, 1.0, B, slots)
                 self._adv_bwd(f"adv{i}", ap, code, ac, dla, B, need_dx=False)
-                w = ap.group.exchange_rest_async()
-                if w is not None:
-                    w.wait()
+                if dpm is not None:      # sum of the discriminator gradients over ranks (replicated group)
+                    self._dp_allreduce_start(dpm, ap.group, 0, ap.group.n)
+                    self._dp_allreduce_finish(dpm, ap.group, 0, ap.group.n)
                 ap.group.grad_norm_sq(s_norm(2 + i))
                 ap.group.clip_adam(s_norm(2 + i), self.clip.get("adversarial"), gscale)
             for i in range(n_adv):
@@ -1001,27 +1197,22 @@ class StepEngine:
                 ap.group.grad_norm_sq(s_norm(2 + n_adv + i))   # "generator_i" norm: logged, never applied
 
         # ---------------- backward ----------------
-        # single process: the two big weight-gradient kernels add their own sum of squares to the clip norm
-        fuse_norm = self.world == 1 and fused and use_tc_spmm
-        H1 = out.K
-        dh = self.ws("dh", (B, H1))
-        if fused:
+        if dpm is not None:
+            pass                                                           # dWout / dbout / dh came with the decoder
+        elif fused:
+            dh = self.ws("dh", (B, H1))
             ev = self._t0("dWout_gemm")
             ops.gemm(dl, 1, h16, 1, G, H1, B, C32=out.gW,                 # dWout = dlogits^T h (+ its ||.||^2)
                      sumsq_out=s_norm(1) if fuse_norm else None)
             self._t1(ev)
             ops.colsum(dl, out.gb, M=B, N=G, accumulate=True)
-            # the output layer's gradient (half of the expert group) is final: start exchanging it now so
-            # the transfer overlaps the rest of the backward pass
-            pending = [gexp.exchange_segment_async(gexp.n_first)]
-            comm_budget(True)
             ev = self._t0("dh_gemm")
             ops.gemm(dl, 0, out.W16, 1, B, H1, G, C32=dh)                 # dh = dlogits Wout
             self._t1(ev)
         else:
+            dh = self.ws("dh", (B, H1))
             ops.gemm(dl, 1, h32, 1, G, H1, B, C32=out.gW, use_tc=False)
             ops.colsum(dl, out.gb, accumulate=True)
-            pending = [gexp.exchange_segment_async(gexp.n_first)]
             ops.gemm(dl, 0, out.W32, 1, B, H1, G, C32=dh, use_tc=False)
         d = dh
         ev_mid = self._t0("mid_bwd")
@@ -1051,8 +1242,10 @@ class StepEngine:
                 if hidden[i][0] == "venc" and hidden[i][1] == j:
                     ops.axpy(d, d_hidden[i], -1.0)
             d = self._layer_bwd(f"venc{j}", self.vaeenc_plan[j], caches[("venc", j)], d, B)
-        if use_tc_spmm:
-            csc = ("tc", tp, G, s_norm(1) if fuse_norm else None, pending, gathered)
+        if dpm is not None:
+            csc = ("dp", dpm)
+        elif use_tc_spmm:
+            csc = ("tc", tp, G, s_norm(1) if fuse_norm else None)
         else:
             cptr, ridx, cval = ops.csr_transpose(crow, col, val, G, nnz, self.ws("cptr", (G + 1,), torch.int32),
                                                  self.ws_cap("ridx", max(nnz, 1), torch.int32),
@@ -1062,6 +1255,8 @@ class StepEngine:
         for j in reversed(range(len(enc))):
             if j == 0:
                 self._t1(ev_mid)
+                if dpm is not None:
+                    self._join_side()     # the small weight gradients are about to travel: they must be complete
             ev = self._t0("csr_linear_bwd_w+bn") if j == 0 else None
             d = self._layer_bwd(f"enc{j}", enc[j], caches[("enc", j)], d, B, need_dx=(j > 0),
                                 csc=csc if j == 0 else None)
@@ -1069,28 +1264,26 @@ class StepEngine:
 
         # ---------------- grad norms, clip, Adam ----------------
         self._join_side()
-        pending.append(gexp.exchange_segment_async(gexp.n_first - 1))   # last piece of W1 + the small matrices
-        if not (use_tc_spmm and gexp.n_first > 1):
-            for i in range(gexp.n_first - 1):
-                pending.append(gexp.exchange_segment_async(i))
-        pending.append(gexp.exchange_rest_async())
-        pending.append(gvae.exchange_rest_async())
-        ev = self._t0("dp_wait_grads")
-        for w in pending:
-            if w is not None:
-                w.wait()
-        self._t1(ev)
-        comm_budget(False)
         ev = self._t0("norm+clip_adam")
-        gvae.grad_norm_sq(s_norm(0))
-        gexp.grad_norm_sq(s_norm(1), skip=[enc[0].lin.weight, out.lin.weight] if fuse_norm else None)
+        if dpm is not None:
+            ev2 = self._t0("dp_wait_grads")
+            self._dp_allreduce_finish(dpm, gexp, gexp.tail_lo, gexp.n)
+            self._dp_allreduce_finish(dpm, gvae, 0, gvae.n)
+            self._t1(ev2)
+            gvae.grad_norm_sq(s_norm(0))
+            ops.sumsq(gexp.g[gexp.tail_lo:gexp.n], s_norm(1))          # replicated part (summed over ranks)
+            self._dp_finish_scalars(dpm, sc, s_norm(1))                 # + every rank's rows; recon of MY cells
+            sc[-2:].copy_(dpm["info"])
+        else:
+            gvae.grad_norm_sq(s_norm(0))
+            gexp.grad_norm_sq(s_norm(1), skip=[enc[0].lin.weight, out.lin.weight] if fuse_norm else None)
+        bg = self._bg if self.pipeline_optimizer else None
         gvae.clip_adam(s_norm(0), self.clip.get("vae"), gscale)
-        gexp.clip_adam(s_norm(1), self.clip.get("expert"), gscale,
-                       background=self._bg if (self.pipeline_optimizer and self.world == 1) else None)
+        gexp.clip_adam(s_norm(1), self.clip.get("expert"), gscale, background=bg)
         self._t1(ev)
 
         self.last = dict(sc=sc, B=B, Z=Z, kl_weight=float(kl_weight), expert_id=expert_id, n_adv=n_adv,
-                         gscale=gscale, ce_base=ce_base, z=z32, dl=dl)
+                         gscale=gscale, ce_base=ce_base, z=z32, dl=dl, dp=dpm is not None)
         return self.last
 
     # ---------------------------------------------------------------------------------------- logs
@@ -1113,6 +1306,9 @@ class StepEngine:
         else:
             sc = rec["sc"].cpu().tolist()
         B, Z, n_adv = rec["B"], rec["Z"], rec["n_adv"]
+        if rec.get("dp") and sc[-1] != 0:
+            raise RuntimeError(f"data parallel: this rank's gene shard holds {int(sc[-2])} non-zeros, more than the "
+                               "shard capacity (set CMMVAE_DP_SHARD_HEADROOM > 1 for gene panels with skewed shards)")
         out = {"recon_loss": sc[0], "kl_loss": sc[1] / B, "kl_weight": rec["kl_weight"],
                "Mean": sc[2] / (B * Z), "Variance": sc[3] / (B * Z)}
         total = out["recon_loss"] + rec["kl_weight"] * out["kl_loss"]
@@ -1143,10 +1339,7 @@ class StepEngine:
         enc, dec = self.enc_plan[expert_id], self.dec_plan[expert_id]
         B, G, Z = crow.numel() - 1, enc[0].K, self.Z
         bf = self.precision == "bf16"
-        if bf:
-            self.groups[f"experts/{expert_id}"].wait_shadow(None)
-        else:
-            self.groups[f"experts/{expert_id}"].sync_master()
+        self.groups[f"experts/{expert_id}"].sync_master()   # joins a background update; data parallel: gathers the rows
         sc = torch.zeros(4, dtype=torch.float64, device=self.device)
         x32 = x16 = None
         for j, lp in enumerate(enc):

@@ -184,7 +184,9 @@ class CSRStager:
     def get(self, t: Ticket) -> torch.Tensor:
         """the staged batch as the ``torch.sparse_csr_tensor`` the reference's ``training_step`` receives"""
         crow, col, val = self.arrays(t)
-        return torch.sparse_csr_tensor(crow, col, val, size=(t.n_cells, t.n_genes))
+        x = torch.sparse_csr_tensor(crow, col, val, size=(t.n_cells, t.n_genes))
+        x._cmmvae_ready = t.ready if t.ready is not None else True     # for CMMVAEModel.prefetch_batch (data parallel)
+        return x
 
     def release(self, t: Ticket):
         """call after the step that consumes ``t`` has been enqueued: its slot may be refilled once that

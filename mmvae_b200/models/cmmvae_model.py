@@ -279,6 +279,18 @@ class CMMVAEModel(BaseModel):
             if prev is not None:
                 self._log_step(eng.scalars(prev[1], host=prev[0]), prev[2])
 
+    def prefetch_batch(self, batch) -> None:
+        """Data parallel only (no-op otherwise): call right after ``training_step`` with the NEXT batch, so that
+        the exchange of its CSR records between the ranks runs underneath the step that was just enqueued.
+        Without it the exchange happens at the start of the next ``training_step`` (same results, ~0.1 ms later)."""
+        eng = self._engine
+        if eng and eng.comm is not None:
+            x, _, expert_id = batch
+            crow, col, val, _ = self._csr(x)
+            # batches from mmvae_b200.feed carry the event of their H2D copy: the exchange then waits for the copy
+            # only, not for the step that is running
+            eng.prefetch(expert_id, crow, col, val, ready=getattr(x, "_cmmvae_ready", None))
+
     def flush_logs(self):
         """log the scalars of the last step when ``sync_logging`` is off"""
         if self._pending_log is not None:

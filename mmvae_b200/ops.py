@@ -340,3 +340,68 @@ def host_slice_rows(indptr, indices, data, lo: int, hi: int, n_genes: int, crow_
     if n < 0:
         raise ValueError(f"host_slice_rows failed ({n}): {lib().cmmvae_last_error().decode()}")
     return int(n)
+
+
+# ------------------------------------------------------------------- data parallel over peer memory
+def _ptr_array(ptrs):
+    arr = (_c.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+    return arr
+
+
+def csr_linear_fwd_tc_routed(packed, tile_ptr, B: int, G: int, Wt16, route_ptrs, route_rows: int):
+    """partial first-layer product of a gene shard for the cells of all ranks; row r goes to route[r // route_rows]"""
+    H = Wt16.shape[1]
+    assert Wt16.dtype == torch.bfloat16 and Wt16.is_contiguous() and Wt16.shape[0] == G
+    _check(lib().cmmvae_csr_linear_fwd_tc_routed(_ptr(packed), _ptr(tile_ptr), B, G, H, _ptr(Wt16),
+                                                 _ptr_array(route_ptrs), len(route_ptrs), int(route_rows), _stream()),
+           "csr_linear_fwd_tc_routed")
+
+
+def gemm_routed(A, transA, Bm, transB, M, N, K, ldc, route_ptrs, route_rows: int):
+    assert A.dtype == torch.bfloat16 and Bm.dtype == torch.bfloat16
+    _check(lib().cmmvae_gemm_bf16_tc_routed(_ptr(A), _ld(A), int(transA), _ptr(Bm), _ld(Bm), int(transB), M, N, K,
+                                            int(ldc), _ptr_array(route_ptrs), len(route_ptrs), int(route_rows),
+                                            _stream()), "gemm_bf16_tc_routed")
+
+
+def decoder_mse_fused_blocks(h16, Wout16, bout, G: int, crow, col, val, dl16, loss_sums, loss_rows: int, tile_ptr):
+    B, H = h16.shape
+    assert loss_sums.dtype == torch.float64 and loss_sums.numel() >= (B + loss_rows - 1) // loss_rows
+    _check(lib().cmmvae_decoder_mse_fused_blocks(_ptr(h16), h16.stride(0), _ptr(Wout16), Wout16.stride(0), _ptr(bout),
+                                                 B, G, H, _ptr(crow), _ptr(col), _ptr(val), _ptr(tile_ptr), _ptr(dl16),
+                                                 dl16.stride(0), _ptr(loss_sums), int(loss_rows), _ptr(None),
+                                                 _stream()), "decoder_mse_fused_blocks")
+
+
+def peer_push(src, nbytes: int, dst_ptrs, flag_ptrs, step: int, ticket):
+    """src -> dst_ptrs[i] on every rank, then (flag_ptrs not None) raise the flags to ``step``"""
+    _check(lib().cmmvae_peer_push(_ptr(src), _c.c_longlong(nbytes), _ptr_array(dst_ptrs),
+                                  _ptr_array(flag_ptrs) if flag_ptrs is not None else None,
+                                  len(dst_ptrs), _c.c_uint(step & 0xFFFFFFFF), _ptr(ticket), _stream()), "peer_push")
+
+
+def peer_signal(flag_ptrs, step: int):
+    _check(lib().cmmvae_peer_signal(_ptr_array(flag_ptrs), len(flag_ptrs), _c.c_uint(step & 0xFFFFFFFF), _stream()),
+           "peer_signal")
+
+
+def peer_wait(local_flags, n_peers: int, step: int):
+    _check(lib().cmmvae_peer_wait(_ptr(local_flags), int(n_peers), _c.c_uint(step & 0xFFFFFFFF), _stream()),
+           "peer_wait")
+
+
+def slab_sum(slabs, n_slabs: int, slab_stride: int, n: int, out32=None, out16=None, bias=None, H: int = 0):
+    _check(lib().cmmvae_slab_sum(_ptr(slabs), int(n_slabs), _c.c_longlong(slab_stride), _c.c_longlong(n), _ptr(bias),
+                                 int(H), _ptr(out32), _ptr(out16), _stream()), "slab_sum")
+
+
+def shard_csr(gathered, slab_bytes: int, col_off: int, val_off: int, B: int, n_src: int, g0: int, g1: int, cap: int,
+              cnt, start, crow_out, col_out, val_out, info):
+    _check(lib().cmmvae_shard_csr(_ptr(gathered), _c.c_longlong(slab_bytes), _c.c_longlong(col_off),
+                                  _c.c_longlong(val_off), B, n_src, g0, g1, cap, _ptr(cnt), _ptr(start), _ptr(crow_out),
+                                  _ptr(col_out), _ptr(val_out), _ptr(info), _stream()), "shard_csr")
+
+
+def dp_scalars(slabs, n_src: int, stride: int, rank: int, out_recon, out_norm):
+    _check(lib().cmmvae_dp_scalars(_ptr(slabs), n_src, stride, rank, _ptr(out_recon), _ptr(out_norm), _stream()),
+           "dp_scalars")
