@@ -126,6 +126,12 @@ int cmmvae_gemm_f32(const float* A, int lda, int transA, const float* Bm, int ld
 int cmmvae_gemm_bf16_tc(const void* A, int lda, int transA, const void* Bm, int ldb, int transB,
                         int M, int N, int K, const float* bias, int relu, int accumulate,
                         float* C_f32, void* C_bf16, int ldc, double* sumsq_out, void* stream);
+/* same pipeline with f32 operands read as TF32 (tcgen05 kind::tf32, 10-bit mantissa): used for the small GEMMs
+ * between the two gene-sized layers, where operand rounding -- not throughput -- decides gradient parity.
+ * lda/ldb multiples of 4 elements. */
+int cmmvae_gemm_tf32_tc(const float* A, int lda, int transA, const float* Bm, int ldb, int transB,
+                        int M, int N, int K, const float* bias, int relu, int accumulate,
+                        float* C_f32, void* C_bf16, int ldc, double* sumsq_out, void* stream);
 /* column sums: out[N] (=|+=) sum_m X[m,n]  (bias gradients) */
 int cmmvae_colsum(const void* X, int x_dtype, int M, int N, int ldx, float* out, int accumulate, void* stream);
 

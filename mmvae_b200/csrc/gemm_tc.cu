@@ -50,7 +50,10 @@ struct GemmParams {
   int route_rows;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+// TF32 = false: bf16 operands (64 per 128-byte k-block row, UMMA K = 16).  TF32 = true: fp32 operands read as
+// TF32 (32 per k-block row, UMMA K = 8) -- the byte geometry of tiles, swizzle and descriptors is identical, so
+// the same pipeline serves both; the small GEMMs between the two gene-sized layers use it for operand precision.
+template <int BN, bool A_MN, bool B_MN, bool TF32>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
@@ -68,7 +71,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // two TMEM accumulators let the epilogue of unit i overlap the main loop of unit i+1
   const int tiles_n = (p.N + BN - 1) / BN, tiles_m = (p.M + BM - 1) / BM;
   const int num_units = tiles_n * tiles_m * p.splits;
-  const int total_kb = (p.K + BK - 1) / BK;
+  constexpr int BKE = TF32 ? 32 : 64;   // elements per k-block row (128 bytes)
+  constexpr int KI = TF32 ? 8 : 16;     // K of one UMMA
+  constexpr int MNB = BKE;              // elements of one 128-byte MN-major group
+  const int total_kb = (p.K + BKE - 1) / BKE;
   const int kb_per = (total_kb + p.splits - 1) / p.splits;
   auto unit_coords = [&](int u, int& m0, int& n0, int& z, int& kb0, int& num_kb) {
     n0 = (u % tiles_n) * BN;
@@ -114,18 +120,18 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint8_t* sA = smem + stage * S::kStageBytes;
           uint8_t* sB = sA + S::kABytes;
           mbar_expect_tx(&full_bar[stage], S::kStageBytes);
-          const int k0 = (kb0 + kb) * BK;
+          const int k0 = (kb0 + kb) * BKE;
           if (!A_MN) {
             tma_load_2d(sA, &tmA, &full_bar[stage], k0, m0);
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[stage], m0 + 64 * j, k0);
+            for (int j = 0; j < BM / MNB; ++j) tma_load_2d(sA + j * (BKE * 128), &tmA, &full_bar[stage], m0 + MNB * j, k0);
           }
           if (!B_MN) {
             tma_load_2d(sB, &tmB, &full_bar[stage], k0, n0);
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[stage], n0 + 64 * j, k0);
+            for (int j = 0; j < BN / MNB; ++j) tma_load_2d(sB + j * (BKE * 128), &tmB, &full_bar[stage], n0 + MNB * j, k0);
           }
           if (++stage == S::kStages) { stage = 0; phase ^= 1; }
         }
@@ -134,7 +140,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == kMmaWarp) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc = TF32 ? make_idesc_tf32(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0)
+                                      : make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -152,14 +159,18 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t sA = smem_u32(smem + stage * S::kStageBytes);
           const uint32_t sB = sA + S::kABytes;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // K-major: 8-row groups 1024 B apart, +32 B per 16-element K step inside the swizzle span.
-            // MN-major: 64-element MN groups BK*128 B apart (LBO), 8 K-rows = 1024 B (SBO), +2048 B per K step.
-            const uint64_t da = A_MN ? make_desc_sw128(sA + k * 2048, BK * 128, 1024)
+          for (int k = 0; k < BKE / KI; ++k) {
+            // K-major: 8-row groups 1024 B apart, +32 B per K step (16 bf16 / 8 tf32) inside the swizzle span.
+            // MN-major: 128-byte MN groups BKE*128 B apart (LBO), 8 K-rows = 1024 B (SBO), +KI*128 B per K step.
+            // (MN-major TF32: 4-row swizzle atoms of 512 B, see make_desc_sw128_base32)
+            const uint64_t da = A_MN ? (TF32 ? make_desc_sw128_base32(sA + k * (KI * 128), BKE * 128, 512)
+                                             : make_desc_sw128(sA + k * (KI * 128), BKE * 128, 1024))
                                      : make_desc_sw128(sA + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_desc_sw128(sB + k * 2048, BK * 128, 1024)
+            const uint64_t db = B_MN ? (TF32 ? make_desc_sw128_base32(sB + k * (KI * 128), BKE * 128, 512)
+                                             : make_desc_sw128(sB + k * (KI * 128), BKE * 128, 1024))
                                      : make_desc_sw128(sB + k * 32, 16, 1024);
-            umma_bf16(tmem_d, da, db, idesc, (kb | k) ? 1u : 0u);
+            if (TF32) umma_tf32(tmem_d, da, db, idesc, (kb | k) ? 1u : 0u);
+            else umma_bf16(tmem_d, da, db, idesc, (kb | k) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == S::kStages) { stage = 0; phase ^= 1; }
@@ -348,7 +359,8 @@ static EncodeTiledFn get_encode() {
 }
 
 static int make_tmap(CUtensorMap* m, CUtensorMapDataType dt, int esize, const void* base, uint64_t inner,
-                    uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer);
+                    uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer,
+                    CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B);
 
 // 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of pitch `ld` elements
 int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
@@ -359,9 +371,22 @@ int make_tmap_f32(CUtensorMap* m, const void* base, uint64_t inner, uint64_t out
                   uint32_t box_outer) {
   return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, inner, outer, ld, box_inner, box_outer);
 }
+// f32 in global memory -> TF32 operand tiles.  Data type TFLOAT32: the TMA unit ROUNDS to TF32 on the way into shared
+// memory (with plain FLOAT32 the tensor core truncates the low 13 mantissa bits, a systematic -2^-12 bias per
+// operand that shrinks every layer's output and shows up as a 6e-4 shift of the loss).
+static int make_tmap_tf32(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
+                          uint32_t box_inner, uint32_t box_outer) {
+  return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, base, inner, outer, ld, box_inner, box_outer);
+}
+// ... for an MN-major TF32 operand: 128-byte swizzle with 32-byte atoms
+static int make_tmap_tf32_mn(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
+                             uint32_t box_inner, uint32_t box_outer) {
+  return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, base, inner, outer, ld, box_inner, box_outer,
+                   CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+}
 
 static int make_tmap(CUtensorMap* m, CUtensorMapDataType dt, int esize, const void* base, uint64_t inner,
-                    uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
+                    uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swz) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -372,7 +397,7 @@ static int make_tmap(CUtensorMap* m, CUtensorMapDataType dt, int esize, const vo
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): base=%p inner=%llu outer=%llu ld=%llu box=%ux%u", (int)r, base,
@@ -382,11 +407,11 @@ static int make_tmap(CUtensorMap* m, CUtensorMapDataType dt, int esize, const vo
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool TF32>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
                        cudaStream_t st) {
   using S = GemmSmem<BN>;
-  auto kern = gemm_bf16_tc_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_bf16_tc_kernel<BN, A_MN, B_MN, TF32>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
@@ -402,13 +427,13 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return check_launch("gemm_bf16_tc");
 }
 
-template <int BN>
+template <int BN, bool TF32 = false>
 static int dispatch_major(int transA, int transB, const CUtensorMap& tmA, const CUtensorMap& tmB,
                           const CUtensorMap& tmC, const GemmParams& p, cudaStream_t st) {
-  if (!transA && !transB) return launch_gemm<BN, false, false>(tmA, tmB, tmC, p, st);
-  if (!transA && transB) return launch_gemm<BN, false, true>(tmA, tmB, tmC, p, st);
-  if (transA && !transB) return launch_gemm<BN, true, false>(tmA, tmB, tmC, p, st);
-  return launch_gemm<BN, true, true>(tmA, tmB, tmC, p, st);
+  if (!transA && !transB) return launch_gemm<BN, false, false, TF32>(tmA, tmB, tmC, p, st);
+  if (!transA && transB) return launch_gemm<BN, false, true, TF32>(tmA, tmB, tmC, p, st);
+  if (transA && !transB) return launch_gemm<BN, true, false, TF32>(tmA, tmB, tmC, p, st);
+  return launch_gemm<BN, true, true, TF32>(tmA, tmB, tmC, p, st);
 }
 
 }  // namespace cmmvae
@@ -417,14 +442,17 @@ using namespace cmmvae;
 
 static int gemm_bf16_tc(const void* A, int lda, int transA, const void* Bm, int ldb, int transB, int M, int N, int K,
                         const float* bias, int relu, int accumulate, float* C_f32, void* C_bf16, int ldc,
-                        double* sumsq_out, float* const* route, int n_route, int route_rows, void* stream) {
+                        double* sumsq_out, float* const* route, int n_route, int route_rows, void* stream,
+                        bool tf32 = false) {
   CMMVAE_REQUIRE(M > 0 && N > 0 && K > 0 && ldc >= N, "gemm_bf16_tc: bad shape M=%d N=%d K=%d ldc=%d", M, N, K, ldc);
   CMMVAE_REQUIRE(C_f32 || C_bf16, "gemm_bf16_tc: no output");
   CMMVAE_REQUIRE(!accumulate || C_f32, "gemm_bf16_tc: accumulate needs C_f32");
   CMMVAE_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)Bm & 15) == 0, "gemm_bf16_tc: operands must be 16-byte aligned");
-  CMMVAE_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm_bf16_tc: lda/ldb must be multiples of 8 (got %d, %d)", lda, ldb);
+  const int ea = tf32 ? 4 : 8;   // elements per 16 bytes
+  CMMVAE_REQUIRE(lda % ea == 0 && ldb % ea == 0, "gemm_tc: lda/ldb must be multiples of %d (got %d, %d)", ea, lda, ldb);
   const long long tiles256 = (long long)((M + 127) / 128) * ((N + 255) / 256);
-  const int total_kb = (K + BK - 1) / BK;
+  const int BKE = tf32 ? 32 : 64;
+  const int total_kb = (K + BKE - 1) / BKE;
   // long-K, few-tile products (dh = dlogits Wout: K = genes) are split along K to fill the 148 SMs
   int splits = 1;
   const int sms = sm_budget();
@@ -436,12 +464,14 @@ static int gemm_bf16_tc(const void* A, int lda, int transA, const void* Bm, int 
   const int BN = (N > 128 && (tiles256 >= sms || splits > 1)) ? 256 : 128;
   CUtensorMap tmA, tmB;
   int rc;
-  // K-major: inner = K, rows = M (or N).  MN-major: inner = M (or N), rows = K, box 64 x 64.
-  if (!transA) rc = make_tmap_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM);
-  else rc = make_tmap_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
+  // K-major: inner = K, rows = M (or N).  MN-major: inner = M (or N), rows = K, box (128 bytes) x (one k-block).
+  auto tmap = tf32 ? make_tmap_tf32 : make_tmap_bf16;
+  auto tmap_mn = tf32 ? make_tmap_tf32_mn : make_tmap_bf16;
+  if (!transA) rc = tmap(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BKE, BM);
+  else rc = tmap_mn(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BKE, BKE);
   if (rc) return rc;
-  if (!transB) rc = make_tmap_bf16(&tmB, Bm, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN);
-  else rc = make_tmap_bf16(&tmB, Bm, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
+  if (!transB) rc = tmap(&tmB, Bm, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BKE, BN);
+  else rc = tmap_mn(&tmB, Bm, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BKE, BKE);
   if (rc) return rc;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.relu = relu; p.accumulate = accumulate;
@@ -476,8 +506,19 @@ static int gemm_bf16_tc(const void* A, int lda, int transA, const void* Bm, int 
                (long long)M * N >= (1 << 20) && !route) ? 1 : 0;
   if (p.tma_out)
     if (int rc2 = make_tmap_f32(&tmC, C_f32, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32, BM)) return rc2;
+  if (tf32) {
+    if (BN == 256) return dispatch_major<256, true>(transA, transB, tmA, tmB, tmC, p, st);
+    return dispatch_major<128, true>(transA, transB, tmA, tmB, tmC, p, st);
+  }
   if (BN == 256) return dispatch_major<256>(transA, transB, tmA, tmB, tmC, p, st);
   return dispatch_major<128>(transA, transB, tmA, tmB, tmC, p, st);
+}
+
+extern "C" int cmmvae_gemm_tf32_tc(const float* A, int lda, int transA, const float* Bm, int ldb, int transB, int M,
+                                   int N, int K, const float* bias, int relu, int accumulate, float* C_f32,
+                                   void* C_bf16, int ldc, double* sumsq_out, void* stream) {
+  return gemm_bf16_tc(A, lda, transA, Bm, ldb, transB, M, N, K, bias, relu, accumulate, C_f32, C_bf16, ldc, sumsq_out,
+                      nullptr, 0, 0, stream, true);
 }
 
 extern "C" int cmmvae_gemm_bf16_tc(const void* A, int lda, int transA, const void* Bm, int ldb, int transB, int M,

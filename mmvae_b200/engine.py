@@ -565,6 +565,7 @@ class StepEngine:
         self.timers: Optional[Dict[str, list]] = None   # name -> [(start_event, end_event)] when profiling
         self.timer_filter = None   # optional set of section names to time (an event record ends a PDL chain)
         self._seed = 0x5EED
+        self.mid_tf32 = os.environ.get("CMMVAE_MID_TF32", "1") != "0"
         self.spmm_tc = True                 # bf16 policy: expert-encoder SpMM on the tensor pipe ...
         self.spmm_tc_min_density = 0.015    # ... when the batch is at least this dense (else gather kernel)
         self.last = None
@@ -622,6 +623,12 @@ class StepEngine:
     def _tc(self, *dims) -> bool:
         return self.precision == "bf16" and all(d % 8 == 0 for d in dims)
 
+    def _tf(self, *dims) -> bool:
+        """small GEMMs of the middle chain: TF32 operands (fp32 activations / master weights) instead of bf16.
+        2 % of the step's FLOPs, but their operand rounding is what flips ReLU masks upstream of every encoder
+        gradient (tools/diag_precision.py); TF32 rounds 8x finer at no measurable cost."""
+        return self.precision == "bf16" and self.mid_tf32 and all(d % 4 == 0 for d in dims)
+
     def _next_seed(self) -> int:
         self._seed = (self._seed * 6364136223846793005 + 1442695040888963407) & ((1 << 63) - 1)
         return self._seed
@@ -630,6 +637,10 @@ class StepEngine:
     def _linear(self, tag, lp: LayerPlan, x32, x16, B, fuse_relu):
         """Y = x W^T + b (optionally ReLU fused in the GEMM epilogue) -> (y32, y16|None)"""
         y32 = self.ws(tag + ".y32", (B, lp.N))
+        if self._tf(lp.K, lp.N):
+            y16 = self.ws(tag + ".y16", (B, lp.N), torch.bfloat16) if (fuse_relu and lp.N % 8 == 0) else None
+            ops.gemm(x32, 0, lp.W32, 0, B, lp.N, lp.K, bias=lp.b, relu=fuse_relu, C32=y32, C16=y16, tf32=True)
+            return y32, y16
         if self._tc(lp.K, lp.N):
             y16 = self.ws(tag + ".y16", (B, lp.N), torch.bfloat16) if fuse_relu else None
             ops.gemm(x16, 0, lp.W16, 0, B, lp.N, lp.K, bias=lp.b, relu=fuse_relu, C32=y32, C16=y16)
@@ -709,7 +720,12 @@ class StepEngine:
                 ops.csr_linear_bwd_w(cptr, ridx, cval, B, G, dY, lp.gW)
             return None
         dX = self.ws(tag + ".dX", (B, lp.K)) if need_dx else None
-        if self._tc(lp.K, lp.N):
+        if self._tf(lp.K, lp.N):
+            x32 = cache["x32"]
+            self._on_side(lambda: ops.gemm(dY, 1, x32, 1, lp.N, lp.K, B, C32=lp.gW, tf32=True))
+            if need_dx:
+                ops.gemm(dY, 0, lp.W32, 1, B, lp.K, lp.N, C32=dX, tf32=True)
+        elif self._tc(lp.K, lp.N):
             x16 = cache["x16"]
             self._on_side(lambda: ops.gemm(dY16, 1, x16, 1, lp.N, lp.K, B, C32=lp.gW))
             if need_dx:
@@ -739,7 +755,9 @@ class StepEngine:
                 caches.append(c)
             sumC, K = ap.Wh32.shape
             logits = self.ws(tag + ".logits", (B, sumC))
-            if tc:
+            if tc and self.mid_tf32:
+                ops.gemm(x, 0, ap.Wh32, 0, B, sumC, K, bias=ap.bh, C32=logits, tf32=True)
+            elif tc:
                 ops.gemm(x16, 0, ap.Wh16, 0, B, sumC, K, bias=ap.bh, C32=logits)
             else:
                 ops.gemm(x, 0, ap.Wh32, 0, B, sumC, K, bias=ap.bh, C32=logits, use_tc=False)
@@ -764,7 +782,10 @@ class StepEngine:
             ap.group.zero_vector_grads()
             ops.colsum(dl, ap.gbh, accumulate=True)
             d = self.ws(tag + ".dcode", (B, K))
-            if tc:
+            if tc and self.mid_tf32:
+                self._on_side(lambda: ops.gemm(dl, 1, code32, 1, sumC, K, B, C32=ap.gWh, tf32=True))
+                ops.gemm(dl, 0, ap.Wh32, 1, B, K, sumC, C32=d, tf32=True)
+            elif tc:
                 dl16 = ops.cast_bf16(dl, self.ws(tag + ".dl16", tuple(dl.shape), torch.bfloat16))
                 self._on_side(lambda: ops.gemm(dl16, 1, code16, 1, sumC, K, B, C32=ap.gWh))
                 ops.gemm(dl16, 0, ap.Wh16, 1, B, K, sumC, C32=d)
@@ -1128,7 +1149,9 @@ class StepEngine:
                 hidden.append(("venc", j, x32, x16))
         q32, q16 = x32, x16
         ML = self.ws("ML", (B, 2 * Z))
-        if self._tc(self.Hv, 2 * Z):
+        if self._tf(self.Hv, 2 * Z):
+            ops.gemm(q32, 0, self.Wmv32, 0, B, 2 * Z, self.Hv, bias=self.bmv, C32=ML, tf32=True)
+        elif self._tc(self.Hv, 2 * Z):
             ops.gemm(q16, 0, self.Wmv16, 0, B, 2 * Z, self.Hv, bias=self.bmv, C32=ML)
         else:
             ops.gemm(q32, 0, self.Wmv32, 0, B, 2 * Z, self.Hv, bias=self.bmv, C32=ML, use_tc=False)
@@ -1228,7 +1251,11 @@ class StepEngine:
         dML16 = self.ws("dML16", (B, 2 * Z), torch.bfloat16) if bf else None
         ops.reparam_kl_bwd(ML, eps, dz, Z, self.var_eps, float(kl_weight) / B, dML, dML16)
         dq = self.ws("dq", (B, self.Hv))
-        if self._tc(self.Hv, 2 * Z):
+        if self._tf(self.Hv, 2 * Z):
+            self._on_side(lambda: (ops.colsum(dML, self.gbmv, accumulate=True),
+                                   ops.gemm(dML, 1, q32, 1, 2 * Z, self.Hv, B, C32=self.gWmv, tf32=True)))
+            ops.gemm(dML, 0, self.Wmv32, 1, B, self.Hv, 2 * Z, C32=dq, tf32=True)
+        elif self._tc(self.Hv, 2 * Z):
             self._on_side(lambda: (ops.colsum(dML, self.gbmv, accumulate=True),
                                    ops.gemm(dML16, 1, q16, 1, 2 * Z, self.Hv, B, C32=self.gWmv)))
             ops.gemm(dML16, 0, self.Wmv16, 1, B, self.Hv, 2 * Z, C32=dq)

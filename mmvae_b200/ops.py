@@ -242,12 +242,19 @@ def _ld(t):
 
 
 def gemm(A, transA, Bm, transB, M, N, K, bias=None, relu=False, accumulate=False, C32=None, C16=None,
-         use_tc: Optional[bool] = None, sumsq_out=None):
-    """C[M,N] = act(opA(A) opB(B) + bias) (+C).  A: [M,K] or (transA) [K,M]; B: [N,K] or (transB) [K,N]."""
+         use_tc: Optional[bool] = None, sumsq_out=None, tf32: bool = False):
+    """C[M,N] = act(opA(A) opB(B) + bias) (+C).  A: [M,K] or (transA) [K,M]; B: [N,K] or (transB) [K,N].
+    bf16 operands -> tcgen05 kind::f16; f32 operands with ``tf32`` -> tcgen05 kind::tf32; f32 otherwise -> CUDA cores."""
     C = C32 if C32 is not None else C16
     ldc = _ld(C)
     if C32 is not None and C16 is not None:
         assert _ld(C32) == _ld(C16)
+    if tf32:
+        assert A.dtype == torch.float32 and Bm.dtype == torch.float32
+        _check(lib().cmmvae_gemm_tf32_tc(_ptr(A), _ld(A), int(transA), _ptr(Bm), _ld(Bm), int(transB), M, N, K,
+                                         _ptr(bias), int(relu), int(accumulate), _ptr(C32), _ptr(C16), ldc,
+                                         _ptr(sumsq_out), _stream()), "gemm_tf32_tc")
+        return C
     tc = (A.dtype == torch.bfloat16) if use_tc is None else use_tc
     if tc:
         assert A.dtype == torch.bfloat16 and Bm.dtype == torch.bfloat16

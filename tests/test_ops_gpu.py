@@ -208,6 +208,46 @@ def test_gemm_bf16_tc(ops, M, N, K, tA, tB):
     assert rel(C16.float(), ref2) < 1e-2
 
 
+def _pad4(t):
+    R, C = t.shape
+    ld = (C + 3) // 4 * 4
+    buf = torch.zeros(R, ld, dtype=t.dtype, device=t.device)
+    buf[:, :C] = t
+    return buf[:, :C]
+
+
+def _tf32(t):
+    """operand as the tensor core reads it: fp32 ROUNDED to TF32's 10-bit mantissa (the TMA unit rounds on the way
+    into shared memory, tensor-map data type TFLOAT32; ties may differ from this half-away emulation)"""
+    return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.parametrize("M,N,K", [(24, 64, 32), (130, 72, 100), (1024, 512, 1024), (1024, 256, 512), (300, 1024, 36),
+                                   (512, 280, 64), (256, 128, 4096)])
+@pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_gemm_tf32_tc(ops, M, N, K, tA, tB):
+    """tcgen05 kind::tf32 on fp32 operands (K-major and MN-major, edge tiles): exact against the product of the
+    TF32-truncated operands; within TF32 rounding (2^-11) of the fp32 product -- 8x finer than bf16 operands"""
+    g = torch.Generator().manual_seed(M * 5 + N + K)
+    A = torch.randn(M, K, generator=g).cuda()
+    Bm = torch.randn(N, K, generator=g).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    ref_t = _tf32(A).double() @ _tf32(Bm).double().t() + bias.double()
+    ref = A.double() @ Bm.double().t() + bias.double()
+    Ad = _pad4(A.t().contiguous() if tA else A)
+    Bd = _pad4(Bm.t().contiguous() if tB else Bm)
+    C = _pad8(torch.empty(M, N).cuda())
+    ops.gemm(Ad, tA, Bd, tB, M, N, K, bias=bias, C32=C, tf32=True)
+    assert rel(C, ref_t) < 5e-5, (tA, tB, rel(C, ref_t), rel(C, ref))
+    assert rel(C, ref) < 5e-4        # rounding, not truncation: no systematic shrink of the product
+    assert abs(float((C.double() - ref).sum() / ref.abs().sum())) < 2e-5
+    C2 = _pad8(torch.ones(M, N).cuda())
+    C16 = torch.zeros(M, C2.stride(0), dtype=torch.bfloat16).cuda()[:, :N]
+    ops.gemm(Ad, tA, Bd, tB, M, N, K, bias=bias, relu=True, accumulate=True, C32=C2, C16=C16, tf32=True)
+    assert rel(C2, torch.relu(ref + 1.0)) < 1e-3
+    assert rel(C16.float(), torch.relu(ref + 1.0)) < 1e-2
+
+
 def test_reparam_kl(ops):
     B, Z = 48, 32
     g = torch.Generator().manual_seed(2)

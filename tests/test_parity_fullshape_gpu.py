@@ -7,13 +7,15 @@
   curve     100 optimisation steps, lr 5e-3, dropout 0.1: the bf16 ELBO curve stays within 1 % of the oracle's
 
 Stated tolerances (bf16 operands, fp32 accumulation, fp32 everything else): loss / recon 5e-4, KL 5e-3,
-adversary CE 1e-2, gradient norms 3e-2, per-tensor gradients <= 1.1e-1 rel-L2.
+adversary CE 1e-2, gradient norms 3e-2, per-tensor gradients <= 8e-2 rel-L2.
 
-Why gradients sit at 1e-1 while the loss agrees to 1e-5: a bf16 operand carries 2^-9 relative rounding, so
-pre-activations differ by ~0.3 % and ~0.3 % of the ReLU masks of a layer flip; a flipped element contributes its
-whole gradient as error, i.e. sqrt(0.003) ~ 5 % rel-L2 per ReLU layer on everything upstream of it (measured
-with tools/diag_precision.py: decoder-side tensors 0.2-1.2 %, encoder-side 9-10 %; torch's own bf16 autocast
-gives 9e-2 on W1.grad).  It is a property of bf16 operands, not of these kernels.
+Why gradients sit at several 1e-2 while the loss agrees to 1e-5: a bf16 operand carries 2^-9 relative rounding,
+so pre-activations differ by ~0.3 % and ~0.3 % of the ReLU masks of a layer flip; a flipped element contributes
+its whole gradient as error, i.e. sqrt(0.003) ~ 5 % rel-L2 per ReLU layer on everything upstream of it.  Measured
+(tools/diag_precision.py, config 2): with every GEMM on bf16 operands the encoder-side tensors sit at 9-10 %
+(torch's own bf16 autocast: 9e-2 on W1.grad); the small GEMMs between the two gene-sized layers
+therefore run on TF32 operands (tcgen05 kind::tf32, rounded by the TMA unit), which brings them to 3-6 %; what
+remains comes from the bf16 operands of the two gene-sized layers themselves.
 """
 import os
 
@@ -39,7 +41,7 @@ def _sparse_addmm_in_the_oracle():
     O.FAST_CSR = False
 
 
-TOL = dict(loss=5e-4, kl=5e-3, adv=1e-2, norm=3e-2, grad=1.1e-1)
+TOL = dict(loss=5e-4, kl=5e-3, adv=1e-2, norm=3e-2, grad=8e-2)
 
 
 def bias_feeds_batchnorm(name, state):
