@@ -364,9 +364,17 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    if os.environ.get("BENCH_WATCHDOG"):      # debugging aid: dump every thread's stack if the run stalls
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["BENCH_WATCHDOG"]), exit=True)
+    same_gpu = os.environ.get("BENCH_SAME_GPU") == "1"     # debugging aid: all ranks share GPU 0 (CUDA IPC, gloo)
+    if same_gpu:
+        local_rank = 0
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
+    if world > 1 and same_gpu:
+        torch.distributed.init_process_group("gloo")
+    elif world > 1:
         torch.set_num_threads(max(1, (os.cpu_count() or 8) // world))   # one launch thread per rank matters
         # NCCL's communicator lines (stderr) stay visible: the driver counts ranks from them
         os.environ.setdefault("NCCL_DEBUG", "INFO")

@@ -202,13 +202,15 @@ int cmmvae_axpy(float* a, const float* b, float alpha, long long n, void* stream
  * are HOST arrays of n device pointers (one per rank, own rank included). */
 /* same product as cmmvae_csr_linear_fwd_tc, no bias; output row r is stored at row r % route_rows of
  * route[r / route_rows] (partial sums of a gene shard for the cells of ALL ranks, delivered to their owners) */
+/* n_split > 1: the gene range is cut into n_split pieces (more CTAs when few cell tiles exist); piece z is stored
+ * split_stride elements behind route[..] -- one more slab for the owner to sum, no atomics */
 int cmmvae_csr_linear_fwd_tc_routed(const void* packed, const int32_t* tile_ptr, int B, int G, int H,
                                     const void* Wt_bf16, float* const* route, int n_route, int route_rows,
-                                    void* stream);
+                                    int n_split, long long split_stride, void* stream);
 /* C[M,N] (f32) = opA(A) opB(B) with the same row routing (dh partials of a gene shard -> owners of the cells) */
 int cmmvae_gemm_bf16_tc_routed(const void* A, int lda, int transA, const void* Bm, int ldb, int transB,
                                int M, int N, int K, int ldc, float* const* route, int n_route, int route_rows,
-                               void* stream);
+                               int n_split, long long split_stride, void* stream);
 /* fused decoder with one loss sum per block of `loss_rows` cells (loss_sums double[ceil(B/loss_rows)], zeroed by
  * the call): a gene-sharded rank sees the cells of all ranks and reports each rank's share separately */
 int cmmvae_decoder_mse_fused_blocks(const void* h, int ldh, const void* Wout, int ldw, const float* bout,

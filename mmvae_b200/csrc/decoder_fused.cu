@@ -185,11 +185,16 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
       const int b = m0 + row;
       const bool row_ok = b < p.B;
       if (p.loss_rows > 0) {
-        // per-thread slot (a 128-cell tile may straddle two owners when loss_rows % 128 != 0); the flush is
-        // warp-divergence safe: plain per-thread atomics on the (rare) slot change
+        // slot of this thread's cell.  loss_rows % 32 == 0 (the usual case: cells per rank a multiple of 32): the
+        // 32 rows of a warp share the slot, so a slot change flushes one warp-reduced atomic; otherwise per thread
         const int s_new = row_ok ? b / p.loss_rows : slot;
         if (s_new != slot) {
-          if (loss_acc != 0.0) atomicAdd(p.loss_sum + slot, loss_acc);
+          if ((p.loss_rows & 31) == 0) {
+            const double w_sum = warp_sum(loss_acc);
+            if (lane == 0 && w_sum != 0.0) atomicAdd(p.loss_sum + slot, w_sum);
+          } else if (loss_acc != 0.0) {
+            atomicAdd(p.loss_sum + slot, loss_acc);
+          }
           loss_acc = 0.0;
           slot = s_new;
         }
@@ -275,8 +280,11 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
       for (int u = 0; u < DE; ++u) { ecol[u] = necol[u]; eval[u] = neval[u]; }
     }
     if (gt == 0) tma_store_wait_all();       // smem must outlive the last bulk store
-    if (p.loss_rows > 0) {
+    if (p.loss_rows > 0 && (p.loss_rows & 31) != 0) {
       if (loss_acc != 0.0) atomicAdd(p.loss_sum + slot, loss_acc);
+    } else if (p.loss_rows > 0) {
+      loss_acc = warp_sum(loss_acc);
+      if (lane == 0 && loss_acc != 0.0) atomicAdd(p.loss_sum + slot, loss_acc);
     } else {
       // one atomic per warp
       loss_acc = warp_sum(loss_acc);

@@ -48,6 +48,7 @@ struct GemmParams {
   // (peer memory) at row gm % route_rows; 0 = local C32
   float* route[16];
   int route_rows;
+  long long route_split_stride;   // K-split z of a routed product goes to its own slab, z * stride elements further
 };
 
 // TF32 = false: bf16 operands (64 per 128-byte k-block row, UMMA K = 16).  TF32 = true: fp32 operands read as
@@ -195,10 +196,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait_relaxed(&tmem_full[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32 && num_kb > 0; ++c) {
+      // (a routed K-split without k-blocks still has to deliver its slab: zeros)
+      for (int c = 0; c < BN / 32 && (num_kb > 0 || p.route_rows > 0); ++c) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
-        tmem_ld_wait();
+        if (num_kb > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
         const int gn0 = n0 + c * 32;
         if (p.tma_out) {
           // f32 chunk [128 rows x 32 cols] -> 128B-swizzled smem (double buffered) -> TMA bulk store; rows and
@@ -241,7 +248,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           const bool full = (gn0 + 32 <= p.N) && p.vec_ok;
-          if (p.splits > 1) {
+          if (p.splits > 1 && p.route_rows == 0) {
             // split-K: this unit holds a partial product; split 0 also contributes the bias
             float* crow = p.C32 + (size_t)gm * p.ldc + gn0;
             if (p.bias && z == 0) {
@@ -266,7 +273,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (gn0 + j < p.N) v[j] += __ldg(p.bias + gn0 + j);
           }
           if (p.route_rows > 0) {   // f32 only, no accumulate / relu / bf16 copy (checked by the host)
-            float* dst = p.route[gm / p.route_rows] + (size_t)(gm % p.route_rows) * p.ldc + gn0;
+            float* dst = p.route[gm / p.route_rows] + (size_t)z * p.route_split_stride +
+                         (size_t)(gm % p.route_rows) * p.ldc + gn0;
             if (full) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
@@ -443,7 +451,7 @@ using namespace cmmvae;
 static int gemm_bf16_tc(const void* A, int lda, int transA, const void* Bm, int ldb, int transB, int M, int N, int K,
                         const float* bias, int relu, int accumulate, float* C_f32, void* C_bf16, int ldc,
                         double* sumsq_out, float* const* route, int n_route, int route_rows, void* stream,
-                        bool tf32 = false) {
+                        bool tf32 = false, int n_split = 1, long long split_stride = 0) {
   CMMVAE_REQUIRE(M > 0 && N > 0 && K > 0 && ldc >= N, "gemm_bf16_tc: bad shape M=%d N=%d K=%d ldc=%d", M, N, K, ldc);
   CMMVAE_REQUIRE(C_f32 || C_bf16, "gemm_bf16_tc: no output");
   CMMVAE_REQUIRE(!accumulate || C_f32, "gemm_bf16_tc: accumulate needs C_f32");
@@ -480,10 +488,15 @@ static int gemm_bf16_tc(const void* A, int lda, int transA, const void* Bm, int 
   p.splits = splits;
   p.sumsq = sumsq_out;
   p.route_rows = 0;
+  p.route_split_stride = 0;
   for (int i = 0; i < 16; ++i) p.route[i] = nullptr;
   if (route) {
     CMMVAE_REQUIRE(n_route >= 1 && n_route <= 16 && route_rows > 0 && (long long)n_route * route_rows >= M,
                    "gemm_bf16_tc_routed: %d routes of %d rows do not cover %d rows", n_route, route_rows, M);
+    CMMVAE_REQUIRE(n_split >= 1 && (n_split == 1 || split_stride >= (long long)route_rows * ldc),
+                   "gemm_bf16_tc_routed: bad split slabs");
+    p.route_split_stride = split_stride;
+    p.splits = n_split < total_kb ? n_split : total_kb;   // K-split z -> slab z on the owner (no atomics)
     CMMVAE_REQUIRE(!relu && !C_bf16 && !accumulate && !sumsq_out, "gemm_bf16_tc_routed: plain f32 output only");
     for (int i = 0; i < n_route; ++i) {
       CMMVAE_REQUIRE(route[i] && ((uintptr_t)route[i] & 15) == 0, "gemm_bf16_tc_routed: bad route %d", i);
@@ -530,8 +543,8 @@ extern "C" int cmmvae_gemm_bf16_tc(const void* A, int lda, int transA, const voi
 
 extern "C" int cmmvae_gemm_bf16_tc_routed(const void* A, int lda, int transA, const void* Bm, int ldb, int transB,
                                           int M, int N, int K, int ldc, float* const* route, int n_route,
-                                          int route_rows, void* stream) {
+                                          int route_rows, int n_split, long long split_stride, void* stream) {
   CMMVAE_REQUIRE(route, "gemm_bf16_tc_routed: no routes");
   return gemm_bf16_tc(A, lda, transA, Bm, ldb, transB, M, N, K, nullptr, 0, 0, route[0], nullptr, ldc, nullptr, route,
-                      n_route, route_rows, stream);
+                      n_route, route_rows, stream, false, n_split, split_stride);
 }

@@ -60,8 +60,12 @@ __global__ void peer_signal_kernel(PeerPtrs flags, int n_peers, uint32_t step) {
   if (threadIdx.x < n_peers) st_release_sys_u32(reinterpret_cast<uint32_t*>(flags.p[threadIdx.x]), step);
 }
 
+// NOT a programmatic-launch citizen on purpose: the kernel never triggers its dependents early.  A successor that
+// moved onto the SMs while this kernel spins (and then blocked in griddepcontrol.wait) could hold the registers /
+// shared memory that a producer kernel of ANOTHER stream of this GPU -- the one a peer is waiting for -- needs:
+// a distributed deadlock.  Successors therefore launch only once the flags have arrived.
 __global__ void peer_wait_kernel(const uint32_t* __restrict__ local_flags, int n_peers, uint32_t step) {
-  pdl_sync();
+  pdl_wait();
   if (threadIdx.x < n_peers) {
     // flags only grow; (int) difference keeps the comparison valid across a 2^32 wrap
     while ((int)(ld_acquire_sys_u32(local_flags + threadIdx.x) - step) < 0) __nanosleep(100);

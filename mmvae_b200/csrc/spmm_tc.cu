@@ -53,6 +53,7 @@ struct SpParams {
   // the epilogue while the next tile is being multiplied.  route_rows == 0: plain local output `out`.
   float* route[16];
   int route_rows;
+  long long route_split_stride;   // K-split z of a routed product goes to its own slab, z * stride elements further
 };
 
 // tp[w][b] = first position p in row b with col[p] >= 64*w, w = 0..NW (NW = ceil(G/64)); window-major so
@@ -349,10 +350,17 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
       mbar_wait_relaxed(&tmem_full[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < SBN / 32 && num_kb > 0; ++c) {
+      // (a routed K-split without k-blocks -- tiny gene ranges -- still has to deliver its slab: zeros)
+      const bool routed = !BWD && p.route_rows > 0;
+      for (int c = 0; c < SBN / 32 && (num_kb > 0 || routed); ++c) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * SBN + c * 32), r);
-        tmem_ld_wait();
+        if (num_kb > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * SBN + c * 32), r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
         const int gn0 = n0 + c * 32;
         if (BWD) {
           // dWt chunk [128 genes x 32 cols] f32 -> 128B-swizzled smem (double buffered) -> TMA bulk store;
@@ -383,7 +391,8 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           float* orow = (!BWD && p.route_rows > 0)
-                            ? p.route[gm / p.route_rows] + (size_t)(gm % p.route_rows) * p.H + gn0
+                            ? p.route[gm / p.route_rows] + (size_t)z * p.route_split_stride +
+                                  (size_t)(gm % p.route_rows) * p.H + gn0
                             : p.out + (size_t)gm * p.H + gn0;
           const bool full = gn0 + 32 <= p.H;
           if (!BWD && p.bias && z == 0) {
@@ -391,7 +400,7 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
             for (int j = 0; j < 32; ++j)
               if (gn0 + j < p.H) v[j] += __ldg(p.bias + gn0 + j);
           }
-          if (!BWD && p.splits > 1) {
+          if (!BWD && p.splits > 1 && p.route_rows == 0) {
             if (full) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
@@ -482,7 +491,8 @@ extern "C" int cmmvae_csr_tile_ptr(const int32_t* crow, const int32_t* col, cons
 }
 
 static int spmm_fwd(const void* packed, const int32_t* tile_ptr, int B, int G, int H, const void* Wt_bf16,
-                    const float* bias, float* Y, float* const* route, int n_route, int route_rows, void* stream) {
+                    const float* bias, float* Y, float* const* route, int n_route, int route_rows, int n_split,
+                    long long split_stride, void* stream) {
   CMMVAE_REQUIRE(B > 0 && G > 0 && H > 0 && H % 8 == 0, "csr_linear_fwd_tc: bad shape (H must be a multiple of 8)");
   CMMVAE_REQUIRE(((uintptr_t)Wt_bf16 & 15) == 0 && ((uintptr_t)Y & 15) == 0, "csr_linear_fwd_tc: alignment");
   cudaStream_t st = (cudaStream_t)stream;
@@ -490,10 +500,14 @@ static int spmm_fwd(const void* packed, const int32_t* tile_ptr, int B, int G, i
   p.B = B; p.G = G; p.H = H; p.packed = (const uint32_t*)packed; p.tp = tile_ptr; p.ntp = (G + 63) / 64 + 1;
   p.bias = bias; p.out = Y; p.sumsq = nullptr; p.m_begin = 0; p.m_end = B; p.win0 = 0; p.row0 = 0;
   p.route_rows = 0;
+  p.route_split_stride = 0;
   for (int i = 0; i < 16; ++i) p.route[i] = nullptr;
   if (route) {
     CMMVAE_REQUIRE(n_route >= 1 && n_route <= 16 && route_rows > 0 && (long long)n_route * route_rows >= B,
                    "csr_linear_fwd_tc_routed: %d routes of %d rows do not cover %d rows", n_route, route_rows, B);
+    CMMVAE_REQUIRE(n_split >= 1 && (n_split == 1 || split_stride >= (long long)route_rows * H),
+                   "csr_linear_fwd_tc_routed: bad split slabs");
+    p.route_split_stride = split_stride;
     for (int i = 0; i < n_route; ++i) {
       CMMVAE_REQUIRE(route[i] && ((uintptr_t)route[i] & 15) == 0, "csr_linear_fwd_tc_routed: bad route %d", i);
       p.route[i] = route[i];
@@ -506,11 +520,15 @@ static int spmm_fwd(const void* packed, const int32_t* tile_ptr, int B, int G, i
   int splits = tiles >= sms ? 1 : sms / tiles;
   if (splits > total_kb / 8) splits = total_kb / 8;
   if (splits < 1) splits = 1;
-  if (route) splits = 1;   // every partial tile goes to its owner exactly once (summed there over the source ranks)
+  if (route) {
+    // every partial tile goes to its owner exactly once: K-split z into slab z (the owner sums slabs anyway)
+    splits = n_split;
+    if (splits > total_kb) splits = total_kb;
+  }
   p.splits = splits;
   CUtensorMap tm;
   if (int rc = make_tmap_bf16(&tm, Wt_bf16, (uint64_t)H, (uint64_t)G, (uint64_t)H, 64, SBK)) return rc;
-  if (splits > 1) cudaMemsetAsync(Y, 0, sizeof(float) * (size_t)B * H, st);
+  if (splits > 1 && !route) cudaMemsetAsync(Y, 0, sizeof(float) * (size_t)B * H, st);
   const int units = tiles * splits;
   dim3 grid(units < sms ? units : sms);
   return launch_spmm_tc<false>(tm, tm, p, grid, st);
@@ -518,14 +536,15 @@ static int spmm_fwd(const void* packed, const int32_t* tile_ptr, int B, int G, i
 
 extern "C" int cmmvae_csr_linear_fwd_tc(const void* packed, const int32_t* tile_ptr, int B, int G, int H,
                                         const void* Wt_bf16, const float* bias, float* Y, void* stream) {
-  return spmm_fwd(packed, tile_ptr, B, G, H, Wt_bf16, bias, Y, nullptr, 0, 0, stream);
+  return spmm_fwd(packed, tile_ptr, B, G, H, Wt_bf16, bias, Y, nullptr, 0, 0, 1, 0, stream);
 }
 
 extern "C" int cmmvae_csr_linear_fwd_tc_routed(const void* packed, const int32_t* tile_ptr, int B, int G, int H,
                                                const void* Wt_bf16, float* const* route, int n_route,
-                                               int route_rows, void* stream) {
+                                               int route_rows, int n_split, long long split_stride, void* stream) {
   CMMVAE_REQUIRE(route, "csr_linear_fwd_tc_routed: no routes");
-  return spmm_fwd(packed, tile_ptr, B, G, H, Wt_bf16, nullptr, route[0], route, n_route, route_rows, stream);
+  return spmm_fwd(packed, tile_ptr, B, G, H, Wt_bf16, nullptr, route[0], route, n_route, route_rows, n_split,
+                  split_stride, stream);
 }
 
 static int spmm_bwd_w(const void* packed, const int32_t* tile_ptr, int B, int G, int H, const void* dY_bf16,
@@ -539,6 +558,7 @@ static int spmm_bwd_w(const void* packed, const int32_t* tile_ptr, int B, int G,
                  "csr_linear_bwd_w_tc: gene range [%d,%d) must be 128-aligned", g_begin, g_end);
   p.bias = nullptr; p.out = dWt; p.splits = 1; p.sumsq = sumsq_out; p.m_begin = g_begin; p.m_end = g_end;
   p.route_rows = 0;
+  p.route_split_stride = 0;
   for (int i = 0; i < 16; ++i) p.route[i] = nullptr;
   p.win0 = shard_view ? g_begin / 64 : 0;
   p.row0 = shard_view ? g_begin : 0;

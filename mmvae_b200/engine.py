@@ -826,7 +826,11 @@ class StepEngine:
         d["slab"] = d["val_off"] + 4 * cap
         d["csr"] = [comm.alloc(f"csr{i}", N * d["slab"]) for i in range(2)]
         d["stage"] = [torch.zeros(d["slab"], dtype=torch.uint8, device=self.device) for _ in range(2)]
-        d["Yin"] = comm.alloc("Yin", N * B * H1 * 4)
+        # few cell tiles (small N * B): the routed first-layer product is also cut along the genes so that every SM
+        # has a unit; each piece lands in its own slab on the owner
+        units = ((N * B + 127) // 128) * ((H1 + 255) // 256)
+        d["S"] = max(1, min(4, 148 // units))
+        d["Yin"] = comm.alloc("Yin", N * d["S"] * B * H1 * 4)
         d["hall"] = comm.alloc("hall", N * B * Hd * 2)
         d["dhin"] = comm.alloc("dhin", N * B * Hd * 4)
         d["dYall"] = comm.alloc("dYall", N * B * H1 * 2)
@@ -912,12 +916,18 @@ class StepEngine:
             raise RuntimeError(f"data-parallel step was set up for {d['B']} cells per rank, got {B}")
         self._dp_step += 1
         step = self._dp_step
-        par = step & 1
         key = (crow.data_ptr(), col.data_ptr(), val.data_ptr(), nnz)
-        if self._csr_pushed.pop(key, None) != step:
-            if self._csr_pushed:
-                raise RuntimeError("prefetch() was called for a different batch than the one being stepped")
+        pushed = self._csr_pushed.pop(key, None)
+        if pushed != step:
+            if pushed is not None or self._csr_pushed:
+                # a batch was prefetched and then NOT stepped next (e.g. the loop changed its data source): its
+                # records sit in this step's buffer with the flags already raised.  Every rank is in the same
+                # situation (symmetric program), so all of them skip this step number -- and with it the buffer
+                self._csr_pushed.clear()
+                self._dp_step += 1
+                step = self._dp_step
             self._dp_push_csr(crow, col, val, nnz, step)
+        par = step & 1
         per = gexp.per if gexp.sharded else _ceil(G, 128)
         g0 = r * per
         g1 = min(G, g0 + per)
@@ -949,8 +959,9 @@ class StepEngine:
         if W16.shape[0] != dpm["per"]:       # single-process test route: pad the view up to the 128-aligned shard
             W16 = self._dp_padded("dp.W1pad", W16, dpm["per"])
         ev = self._t0("csr_linear_fwd")
+        S = d["S"]
         ops.csr_linear_fwd_tc_routed(dpm["tp"][1], dpm["tp"][0], dpm["NB"], dpm["per"], W16,
-                                     [p + r * B * H1 * 4 for p in d["Yin"].ptr], B)
+                                     [p + r * S * B * H1 * 4 for p in d["Yin"].ptr], B, S, B * H1)
         self._t1(ev)
         ops.peer_signal(self.comm.flag_ptrs("Y"), step)
         ev = self._t0("dp_wait_Y")
@@ -961,7 +972,7 @@ class StepEngine:
         d["safe"] = torch.cuda.Event()
         d["safe"].record()
         Y = self.ws("enc0.y32", (B, H1))
-        ops.slab_sum(d["Yin"].local.view(torch.float32), N, B * H1, B * H1, out32=Y, bias=lp.b, H=H1)
+        ops.slab_sum(d["Yin"].local.view(torch.float32), N * S, B * H1, B * H1, out32=Y, bias=lp.b, H=H1)
         return Y
 
     def _dp_padded(self, name, t, rows):

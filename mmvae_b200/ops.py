@@ -355,20 +355,25 @@ def _ptr_array(ptrs):
     return arr
 
 
-def csr_linear_fwd_tc_routed(packed, tile_ptr, B: int, G: int, Wt16, route_ptrs, route_rows: int):
-    """partial first-layer product of a gene shard for the cells of all ranks; row r goes to route[r // route_rows]"""
+def csr_linear_fwd_tc_routed(packed, tile_ptr, B: int, G: int, Wt16, route_ptrs, route_rows: int, n_split: int = 1,
+                             split_stride: int = 0):
+    """partial first-layer product of a gene shard for the cells of all ranks; row r goes to route[r // route_rows]
+    (gene piece z of n_split: split_stride elements further)"""
     H = Wt16.shape[1]
     assert Wt16.dtype == torch.bfloat16 and Wt16.is_contiguous() and Wt16.shape[0] == G
     _check(lib().cmmvae_csr_linear_fwd_tc_routed(_ptr(packed), _ptr(tile_ptr), B, G, H, _ptr(Wt16),
-                                                 _ptr_array(route_ptrs), len(route_ptrs), int(route_rows), _stream()),
+                                                 _ptr_array(route_ptrs), len(route_ptrs), int(route_rows),
+                                                 int(n_split), _c.c_longlong(split_stride), _stream()),
            "csr_linear_fwd_tc_routed")
 
 
-def gemm_routed(A, transA, Bm, transB, M, N, K, ldc, route_ptrs, route_rows: int):
+def gemm_routed(A, transA, Bm, transB, M, N, K, ldc, route_ptrs, route_rows: int, n_split: int = 1,
+                split_stride: int = 0):
     assert A.dtype == torch.bfloat16 and Bm.dtype == torch.bfloat16
     _check(lib().cmmvae_gemm_bf16_tc_routed(_ptr(A), _ld(A), int(transA), _ptr(Bm), _ld(Bm), int(transB), M, N, K,
                                             int(ldc), _ptr_array(route_ptrs), len(route_ptrs), int(route_rows),
-                                            _stream()), "gemm_bf16_tc_routed")
+                                            int(n_split), _c.c_longlong(split_stride), _stream()),
+           "gemm_bf16_tc_routed")
 
 
 def decoder_mse_fused_blocks(h16, Wout16, bout, G: int, crow, col, val, dl16, loss_sums, loss_rows: int, tile_ptr):

@@ -143,7 +143,7 @@ def test_config2_full_shape_step_with_dropout():
                 ua = (mine[k].double() - before[k].double()).flatten()
                 ub = (P[k].double() - before[k].double()).flatten()
                 cos = float((ua * ub).sum() / (ua.norm() * ub.norm()).clamp_min(1e-30))
-                assert cos > 0.97, (k, cos)     # Adam normalises every element to +-lr: compare directions
+                assert cos > 0.95, (k, cos)     # Adam normalises every element to +-lr: compare directions
         model.load_state_dict({f"module.{k}": v for k, v in P.items()})     # same-state comparison next step
 
 
