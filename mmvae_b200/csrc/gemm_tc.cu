@@ -207,9 +207,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int j = 0; j < 32; ++j) r[j] = 0u;
         }
         const int gn0 = n0 + c * 32;
-        if (p.tma_out) {
-          // f32 chunk [128 rows x 32 cols] -> 128B-swizzled smem (double buffered) -> TMA bulk store; rows and
-          // columns outside C are clipped by the tensor map
+        if (p.tma_out || p.route_rows > 0) {
+          // f32 chunk [128 rows x 32 cols] -> 128B-swizzled smem (double buffered) -> TMA bulk store (rows and
+          // columns outside C are clipped by the tensor map), or -- routed output -- cooperative row stores into the
+          // owners' buffers: a warp writes 4 rows x 128 contiguous bytes per instruction, so what crosses NVLink
+          // are full 128-byte lines (per-thread 16-byte stores to 32 different rows cost 10x the link time)
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -228,17 +230,37 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (gn0 + j < p.N) ssq = fmaf(v[j], v[j], ssq);
           }
           uint8_t* obuf = smem + S::kOutOff + (chunk_no & 1) * (BM * 128);
-          if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          if (p.tma_out && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           named_bar_sync(1, 128);
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             *reinterpret_cast<float4*>(obuf + row * 128 + ((k ^ (row & 7)) << 4)) =
                 make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-          fence_proxy_async();
+          if (p.tma_out) fence_proxy_async();
           named_bar_sync(1, 128);
-          if (threadIdx.x == 0) {
-            tma_store_2d(&tmC, obuf, gn0, m0);
-            tma_store_commit();
+          if (p.tma_out) {
+            if (threadIdx.x == 0) {
+              tma_store_2d(&tmC, obuf, gn0, m0);
+              tma_store_commit();
+            }
+          } else {
+#pragma unroll
+            for (int it2 = 0; it2 < 8; ++it2) {
+              const int idx = it2 * 128 + (int)threadIdx.x;
+              const int rr = idx >> 3, ch = idx & 7;
+              const int grow = m0 + rr, gcol = gn0 + ch * 4;
+              if (grow < p.M && gcol < p.N) {
+                const float4 t = *reinterpret_cast<const float4*>(obuf + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                float* dst = p.route[grow / p.route_rows] + (size_t)z * p.route_split_stride +
+                             (size_t)(grow % p.route_rows) * p.ldc + gcol;
+                if (gcol + 4 <= p.N) {
+                  *reinterpret_cast<float4*>(dst) = t;
+                } else {
+                  const float tv[4] = {t.x, t.y, t.z, t.w};
+                  for (int j = 0; j < 4 && gcol + j < p.N; ++j) dst[j] = tv[j];
+                }
+              }
+            }
           }
           ++chunk_no;
           continue;
@@ -271,19 +293,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (gn0 + j < p.N) v[j] += __ldg(p.bias + gn0 + j);
-          }
-          if (p.route_rows > 0) {   // f32 only, no accumulate / relu / bf16 copy (checked by the host)
-            float* dst = p.route[gm / p.route_rows] + (size_t)z * p.route_split_stride +
-                         (size_t)(gm % p.route_rows) * p.ldc + gn0;
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (gn0 + j < p.N) dst[j] = v[j];
-            }
-            continue;
           }
           const size_t o = (size_t)gm * p.ldc + gn0;
           if (full) {
@@ -497,7 +506,8 @@ static int gemm_bf16_tc(const void* A, int lda, int transA, const void* Bm, int 
                    "gemm_bf16_tc_routed: bad split slabs");
     p.route_split_stride = split_stride;
     p.splits = n_split < total_kb ? n_split : total_kb;   // K-split z -> slab z on the owner (no atomics)
-    CMMVAE_REQUIRE(!relu && !C_bf16 && !accumulate && !sumsq_out, "gemm_bf16_tc_routed: plain f32 output only");
+    CMMVAE_REQUIRE(!relu && !C_bf16 && !accumulate && !sumsq_out && ldc % 4 == 0,
+                   "gemm_bf16_tc_routed: plain f32 output only, ldc a multiple of 4");
     for (int i = 0; i < n_route; ++i) {
       CMMVAE_REQUIRE(route[i] && ((uintptr_t)route[i] & 15) == 0, "gemm_bf16_tc_routed: bad route %d", i);
       p.route[i] = route[i];

@@ -386,6 +386,32 @@ spmm_tc_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
           ++chunk_no;
           continue;
         }
+        if (routed) {
+          // partial sums for the cells' owners: stage the [128 cells x 32 cols] chunk in swizzled smem, then the
+          // four epilogue warps store it row-wise -- 4 rows x 128 contiguous bytes per warp instruction -- so
+          // that full 128-byte lines cross NVLink
+          uint8_t* obuf = smem + kSpOutOff + (chunk_no & 1) * (SBM * 128);
+          named_bar_sync(15, 128);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            *reinterpret_cast<uint4*>(obuf + row * 128 + ((k ^ (row & 7)) << 4)) =
+                make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+          named_bar_sync(15, 128);
+#pragma unroll
+          for (int it2 = 0; it2 < 8; ++it2) {
+            const int idx = it2 * 128 + et;
+            const int rr = idx >> 3, ch = idx & 7;
+            const int grow = m0 + rr, gcol = gn0 + ch * 4;
+            if (grow < Mdim && gcol < p.H) {     // H % 8 == 0: a 4-column group is inside or outside as a whole
+              const uint4 t = *reinterpret_cast<const uint4*>(obuf + rr * 128 + ((ch ^ (rr & 7)) << 4));
+              float* dst = p.route[grow / p.route_rows] + (size_t)z * p.route_split_stride +
+                           (size_t)(grow % p.route_rows) * p.H + gcol;
+              *reinterpret_cast<uint4*>(dst) = t;
+            }
+          }
+          ++chunk_no;
+          continue;
+        }
         if (gm < Mdim && gn0 < p.H) {
           float v[32];
 #pragma unroll

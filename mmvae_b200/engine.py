@@ -967,10 +967,6 @@ class StepEngine:
         ev = self._t0("dp_wait_Y")
         ops.peer_wait(self.comm.local_flags("Y"), N, step)
         self._t1(ev)
-        # every rank has cut its shard out of this step's gathered CSR (Y partials come after that): the buffer of
-        # the other parity may be refilled for the next step from here on
-        d["safe"] = torch.cuda.Event()
-        d["safe"].record()
         Y = self.ws("enc0.y32", (B, H1))
         ops.slab_sum(d["Yin"].local.view(torch.float32), N * S, B * H1, B * H1, out32=Y, bias=lp.b, H=H1)
         return Y
@@ -985,6 +981,12 @@ class StepEngine:
         partial sums routed to the cells' owners.  Returns dh[B, Hd] of this rank's cells."""
         d, N, r, step = self._dp, self.world, self.rank, dpm["step"]
         Hd, per, NB = out.K, dpm["per"], dpm["NB"]
+        # every rank has cut its shard out of this step's gathered CSR (the Y partials this rank already received
+        # came after that): the CSR buffer of the other parity may be refilled for the next step from here on --
+        # i.e. the prefetch of the next batch overlaps the tensor-bound decoder / dWout / dh kernels, not the
+        # latency-bound chain of small kernels before them
+        d["safe"] = torch.cuda.Event()
+        d["safe"].record()
         ops.peer_push(h16, B * Hd * 2, [p + r * B * Hd * 2 for p in d["hall"].ptr], self.comm.flag_ptrs("h"), step,
                       self.comm.ticket)
         ev = self._t0("dp_wait_h")
