@@ -229,14 +229,24 @@ int cmmvae_peer_wait(const void* local_flags, int n_peers, unsigned int step, vo
 /* out[i] = sum_s slabs[s * slab_stride + i] (+ bias[i % H]), i < n; f32 and/or bf16 output */
 int cmmvae_slab_sum(const float* slabs, int n_slabs, long long slab_stride, long long n, const float* bias, int H,
                     float* out_f32, void* out_bf16, void* stream);
-/* gene shard [g0, g1) of the CSR batches of all ranks.  `gathered`: n_src slabs `slab_bytes` apart, each
- * [crow int32 (B+1) | col int32 at col_off | val f32 at val_off].  Output: one compact CSR over B * n_src rows
- * (source-major), columns rebased to g0: crow_out int32[B*n_src+1], col_out/val_out [cap]; info[0] = non-zeros of
- * the shard, info[1] = 1 if they exceed cap (entries beyond cap are dropped -- the caller must treat that as an
- * error).  cnt/start: int32[B*n_src] scratch.  Bit-exact with the rows' sorted, duplicate-free column lists. */
-int cmmvae_shard_csr(const void* gathered, long long slab_bytes, long long col_off, long long val_off,
-                     int B, int n_src, int g0, int g1, int cap, int32_t* cnt, int32_t* start,
-                     int32_t* crow_out, int32_t* col_out, float* val_out, int32_t* info, void* stream);
+/* All-to-all of this rank's batch by gene shard: rows are cut at the shard boundaries q * per (rows are sorted, so
+ * piece q is a contiguous range) and piece q is stored into rank q's buffer: dst_crow[q] int32[B+1] (offsets of
+ * the pieces, starting at 0), dst_col[q] / dst_val[q] [cap] with columns REBASED to the shard (col - q * per).
+ * info[0] = largest piece, info[1] = 1 if a piece exceeds cap (its tail rows then arrive empty -- the caller must
+ * treat that as an error).  cnt/start/offs: int32[B * n_dst] scratch.  dst_* are HOST arrays of n_dst device
+ * (peer) pointers.  Bit-exact with the rows' sorted, duplicate-free column lists. */
+int cmmvae_csr_scatter_shards(const int32_t* crow, const int32_t* col, const float* val, int B, int n_dst, int per,
+                              int cap, void* const* dst_crow, void* const* dst_col, void* const* dst_val,
+                              int32_t* cnt, int32_t* start, int32_t* offs, int32_t* info, void* stream);
+/* n_src received slabs, `slab_bytes` apart, each starting with its crow int32[B+1]: row_begin / row_end
+ * [B * n_src] = positions of every row in ONE int32/f32 array spanning all slabs (position = slab * slab_bytes/4
+ * + offset inside the slab's col / val section) */
+int cmmvae_slab_rows(const void* slabs, long long slab_bytes, int B, int n_src, int32_t* row_begin,
+                     int32_t* row_end, void* stream);
+/* cmmvae_csr_tile_ptr for rows given as (begin, end) position arrays instead of one crow array; n_records =
+ * positions covered by col / val (records of all positions are packed, gaps included) */
+int cmmvae_csr_tile_ptr_rows(const int32_t* row_begin, const int32_t* row_end, const int32_t* col, const float* val,
+                             int B, int G, long long n_records, int32_t* tile_ptr, void* packed, void* stream);
 /* slabs: n_src rows of `stride` doubles = [loss share of rank 0..n_src-1 | sumsq of the source's shard | ...];
  * out_recon = sum_s slab_s[rank]; out_norm += sum_s slab_s[n_src] */
 int cmmvae_dp_scalars(const double* slabs, int n_src, int stride, int rank, double* out_recon, double* out_norm,

@@ -298,8 +298,8 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
 
 int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
                    uint32_t box_outer);
-__global__ void tile_ptr64_kernel(const int32_t* __restrict__ crow, const int32_t* __restrict__ col, int B, int ntp,
-                                  int32_t* __restrict__ tp);
+__global__ void tile_ptr64_kernel(const int32_t* __restrict__ rbeg, const int32_t* __restrict__ rend,
+                                  const int32_t* __restrict__ col, int B, int ntp, int32_t* __restrict__ tp);
 
 }  // namespace cmmvae
 
@@ -343,7 +343,7 @@ static int decoder_mse(const void* h, int ldh, const void* Wout, int ldw, const 
   cudaMemsetAsync(loss_sum, 0, sizeof(double) * (loss_rows > 0 ? (size_t)((B + loss_rows - 1) / loss_rows) : 1), st);
   if (!tile_ptr) {   // build the 64-gene-window pointer table (the tensor-pipe SpMM shares it when it ran)
     int blocks = B < 148 * 16 ? B : 148 * 16;   // one CTA per row
-    launch_pdl(tile_ptr64_kernel, dim3(blocks), dim3(256), 0, st, crow, col, B, p.ntp, (int32_t*)workspace);
+    launch_pdl(tile_ptr64_kernel, dim3(blocks), dim3(256), 0, st, crow, crow + 1, col, B, p.ntp, (int32_t*)workspace);
     if (int rc = check_launch("tile_ptr64")) return rc;
     tile_ptr = (const int32_t*)workspace;
   }

@@ -12,8 +12,9 @@
 //   cmmvae_peer_signal  flags only (after a kernel whose epilogue already stored to the peers)
 //   cmmvae_peer_wait    spin until the local flags of a channel reach `step`
 //   cmmvae_slab_sum     out = sum over slabs (+ bias), f32 (+ bf16 copy)                   (the reduce of reduce-scatter)
-//   cmmvae_shard_csr_*  cut the gene shard [g0, g1) out of the gathered CSR slabs of all ranks into one compact CSR
-//                       (rows = all cells of the job, columns rebased to the shard) -- bit-exact index handling
+//   cmmvae_csr_scatter_shards  all-to-all of the batch: piece q (gene shard q) of every row goes straight into rank
+//                       q's buffer, columns rebased to the shard -- bit-exact index handling
+//   cmmvae_slab_rows    row ranges over the received slabs, in place
 #include "common.cuh"
 
 namespace cmmvae {
@@ -95,56 +96,45 @@ __global__ void __launch_bounds__(256) slab_sum_kernel(const float4* __restrict_
   }
 }
 
-// ---- gene shard of the gathered CSR ------------------------------------------------------------------------------
-// slab s (one per source rank) = [crow int32 (B+1) | pad to 16 B | col int32 cap | val f32 cap], `slab_bytes` apart.
-struct GatheredCsr {
-  const uint8_t* base;
-  long long slab_bytes, col_off, val_off;
-  int B, n_src;
-};
-__device__ __forceinline__ const int32_t* g_crow(const GatheredCsr& g, int s) {
-  return reinterpret_cast<const int32_t*>(g.base + (long long)s * g.slab_bytes);
-}
-__device__ __forceinline__ const int32_t* g_col(const GatheredCsr& g, int s) {
-  return reinterpret_cast<const int32_t*>(g.base + (long long)s * g.slab_bytes + g.col_off);
-}
-__device__ __forceinline__ const float* g_val(const GatheredCsr& g, int s) {
-  return reinterpret_cast<const float*>(g.base + (long long)s * g.slab_bytes + g.val_off);
-}
-
-// one thread per gathered row: [lo, hi) = entries of the row with g0 <= col < g1 (rows are sorted: two lower bounds)
-__global__ void __launch_bounds__(256) shard_csr_count_kernel(GatheredCsr g, int g0, int g1,
-                                                              int32_t* __restrict__ cnt, int32_t* __restrict__ start) {
+// ---- all-to-all of the batch by gene shard ---------------------------------------------------------------------------
+// Instead of gathering every rank's whole batch everywhere (N x the batch per rank), each rank cuts ITS rows into the
+// N gene shards and stores piece q straight into rank q's buffer (slab = source rank): crow (B+1), then the entries
+// with columns rebased to the shard.  Rows are sorted, so piece q of a row is the contiguous range between two lower
+// bounds.  The receiver moves nothing: it only derives row ranges / window pointers over the slabs in place.
+//   count: thread per (dest, row)      scan: one CTA per dest (crow written to the peer + a local copy of the offsets)
+//   copy:  warp per (dest, row), 128 contiguous bytes per store instruction into peer memory
+__global__ void __launch_bounds__(256) scatter_count_kernel(const int32_t* __restrict__ crow,
+                                                            const int32_t* __restrict__ col, int B, int n_dst, int per,
+                                                            int32_t* __restrict__ cnt, int32_t* __restrict__ start) {
   pdl_sync();
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= g.B * g.n_src) return;
-  const int s = row / g.B, b = row % g.B;
-  const int32_t* crow = g_crow(g, s);
-  const int32_t* col = g_col(g, s);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * n_dst) return;
+  const int q = i / B, b = i % B;
   const int r0 = crow[b], r1 = crow[b + 1];
+  const int g0 = q * per, g1 = g0 + per;
   int lo = r0, hi = r1;
   while (lo < hi) { const int m = (lo + hi) >> 1; if (__ldg(col + m) < g0) lo = m + 1; else hi = m; }
   const int a = lo;
   hi = r1;
   while (lo < hi) { const int m = (lo + hi) >> 1; if (__ldg(col + m) < g1) lo = m + 1; else hi = m; }
-  cnt[row] = lo - a;
-  start[row] = a;
+  cnt[i] = lo - a;
+  start[i] = a;
 }
 
-// exclusive scan of cnt[0..n) -> crow_out[0..n], single CTA of 1024 threads (n <= a few 100 K rows);
-// overflow[0] = 1 if the total exceeds `cap` (the copy kernel then writes nothing beyond cap)
-__global__ void __launch_bounds__(1024) shard_csr_scan_kernel(const int32_t* __restrict__ cnt, int n, int cap,
-                                                              int32_t* __restrict__ crow_out,
-                                                              int32_t* __restrict__ info) {
+__global__ void __launch_bounds__(1024) scatter_scan_kernel(const int32_t* __restrict__ cnt, int B, int cap,
+                                                            PeerPtrs dst_crow, int32_t* __restrict__ offs,
+                                                            int32_t* __restrict__ info) {
   pdl_sync();
   __shared__ int warp_tot[32];
   __shared__ int carry;
+  const int q = blockIdx.x;
+  int32_t* crow_out = reinterpret_cast<int32_t*>(dst_crow.p[q]);
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int base = 0; base < n; base += 1024) {
+  for (int base = 0; base < B; base += 1024) {
     const int i = base + threadIdx.x;
-    const int v = i < n ? cnt[i] : 0;
+    const int v = i < B ? cnt[q * B + i] : 0;
     int x = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
@@ -158,38 +148,58 @@ __global__ void __launch_bounds__(1024) shard_csr_scan_kernel(const int32_t* __r
     }
     __syncthreads();
     const int excl = carry + (w ? warp_tot[w - 1] : 0) + x - v;
-    if (i < n) crow_out[i] = min(excl, cap);   // on overflow the tail rows come out empty (flagged), never out of bounds
+    if (i < B) {
+      const int c = min(excl, cap);   // on overflow the tail rows come out empty (flagged), never out of bounds
+      crow_out[i] = c;
+      offs[q * B + i] = c;
+    }
     __syncthreads();
     if (threadIdx.x == 1023) carry = excl + v;
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    crow_out[n] = min(carry, cap);
-    info[0] = carry;                 // non-zeros of the shard
-    info[1] = carry > cap ? 1 : 0;   // overflow
+    crow_out[B] = min(carry, cap);
+    atomicMax(&info[0], carry);              // densest piece
+    if (carry > cap) atomicExch(&info[1], 1);   // overflow
   }
 }
 
-// one warp per gathered row: copy its shard entries to the compact CSR, columns rebased to the shard
-__global__ void __launch_bounds__(256) shard_csr_copy_kernel(GatheredCsr g, int g0, const int32_t* __restrict__ cnt,
-                                                             const int32_t* __restrict__ start,
-                                                             const int32_t* __restrict__ crow_out, int cap,
-                                                             int32_t* __restrict__ col_out,
-                                                             float* __restrict__ val_out) {
+__global__ void __launch_bounds__(256) scatter_copy_kernel(const int32_t* __restrict__ col, const float* __restrict__ val,
+                                                           int B, int n_dst, int per, int cap,
+                                                           const int32_t* __restrict__ cnt,
+                                                           const int32_t* __restrict__ start,
+                                                           const int32_t* __restrict__ offs, PeerPtrs dst_col,
+                                                           PeerPtrs dst_val) {
   pdl_sync();
   const int lane = threadIdx.x & 31;
-  const int n_rows = g.B * g.n_src;
-  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += (gridDim.x * blockDim.x) >> 5) {
-    const int s = row / g.B;
-    const int32_t* col = g_col(g, s);
-    const float* val = g_val(g, s);
-    const int n = cnt[row], a = start[row], o = crow_out[row];
+  const int n_rows = B * n_dst;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_rows; i += (gridDim.x * blockDim.x) >> 5) {
+    const int q = i / B;
+    int32_t* oc = reinterpret_cast<int32_t*>(dst_col.p[q]);
+    float* ov = reinterpret_cast<float*>(dst_val.p[q]);
+    const int n = cnt[i], a = start[i], o = offs[i], g0 = q * per;
     for (int k = lane; k < n; k += 32)
       if (o + k < cap) {
-        col_out[o + k] = __ldg(col + a + k) - g0;
-        val_out[o + k] = __ldg(val + a + k);
+        oc[o + k] = __ldg(col + a + k) - g0;
+        ov[o + k] = __ldg(val + a + k);
       }
   }
+  __threadfence_system();
+}
+
+// row ranges of the N received slabs as positions in ONE array that spans all slabs (gaps between slabs are never
+// addressed): begin/end[s * B + b] = s * slab_elems + crow_s[b], crow_s[b + 1]
+__global__ void __launch_bounds__(256) slab_rows_kernel(const uint8_t* __restrict__ base, long long slab_bytes, int B,
+                                                        int n_src, int32_t* __restrict__ rbeg,
+                                                        int32_t* __restrict__ rend) {
+  pdl_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * n_src) return;
+  const int s = i / B, b = i % B;
+  const int32_t* crow = reinterpret_cast<const int32_t*>(base + (long long)s * slab_bytes);
+  const int off = (int)((long long)s * (slab_bytes / 4));
+  rbeg[i] = off + crow[b];
+  rend[i] = off + crow[b + 1];
 }
 
 // recon of THIS rank's cells and the squared gradient norm of a gene-sharded group, from the scalar slabs all
@@ -267,28 +277,43 @@ extern "C" int cmmvae_slab_sum(const float* slabs, int n_slabs, long long slab_s
   return check_launch("slab_sum");
 }
 
-extern "C" int cmmvae_shard_csr(const void* gathered, long long slab_bytes, long long col_off, long long val_off,
-                                int B, int n_src, int g0, int g1, int cap, int32_t* cnt, int32_t* start,
-                                int32_t* crow_out, int32_t* col_out, float* val_out, int32_t* info, void* stream) {
-  CMMVAE_REQUIRE(gathered && B > 0 && n_src >= 1 && g0 >= 0 && g1 > g0 && cap > 0, "shard_csr: bad arguments");
-  GatheredCsr g{(const uint8_t*)gathered, slab_bytes, col_off, val_off, B, n_src};
-  cudaStream_t st = (cudaStream_t)stream;
-  const int rows = B * n_src;
-  launch_pdl(shard_csr_count_kernel, dim3((rows + 255) / 256), dim3(256), 0, st, g, g0, g1, cnt, start);
-  if (int rc = check_launch("shard_csr_count")) return rc;
-  launch_pdl(shard_csr_scan_kernel, dim3(1), dim3(1024), 0, st, (const int32_t*)cnt, rows, cap, crow_out, info);
-  if (int rc = check_launch("shard_csr_scan")) return rc;
-  long long want = ((long long)rows * 32 + 255) / 256;
-  const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
-  launch_pdl(shard_csr_copy_kernel, dim3(blocks), dim3(256), 0, st, g, g0, (const int32_t*)cnt, (const int32_t*)start,
-             (const int32_t*)crow_out, cap, col_out, val_out);
-  return check_launch("shard_csr_copy");
-}
-
 extern "C" int cmmvae_dp_scalars(const double* slabs, int n_src, int stride, int rank, double* out_recon,
                                  double* out_norm, void* stream) {
   CMMVAE_REQUIRE(slabs && n_src >= 1 && stride > n_src && rank >= 0 && rank < n_src, "dp_scalars: bad arguments");
   launch_pdl(dp_scalars_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, slabs, n_src, stride, rank, out_recon,
              out_norm);
   return check_launch("dp_scalars");
+}
+
+extern "C" int cmmvae_csr_scatter_shards(const int32_t* crow, const int32_t* col, const float* val, int B, int n_dst,
+                                         int per, int cap, void* const* dst_crow, void* const* dst_col,
+                                         void* const* dst_val, int32_t* cnt, int32_t* start, int32_t* offs,
+                                         int32_t* info, void* stream) {
+  CMMVAE_REQUIRE(crow && col && val && B > 0 && per > 0 && cap > 0 && cnt && start && offs && info,
+                 "csr_scatter_shards: bad arguments");
+  PeerPtrs pc, pl, pv;
+  if (int rc = fill_ptrs(pc, dst_crow, n_dst, "csr_scatter_shards")) return rc;
+  if (int rc = fill_ptrs(pl, dst_col, n_dst, "csr_scatter_shards")) return rc;
+  if (int rc = fill_ptrs(pv, dst_val, n_dst, "csr_scatter_shards")) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rows = B * n_dst;
+  cudaMemsetAsync(info, 0, 2 * sizeof(int32_t), st);
+  launch_pdl(scatter_count_kernel, dim3((rows + 255) / 256), dim3(256), 0, st, crow, col, B, n_dst, per, cnt, start);
+  if (int rc = check_launch("scatter_count")) return rc;
+  launch_pdl(scatter_scan_kernel, dim3(n_dst), dim3(1024), 0, st, (const int32_t*)cnt, B, cap, pc, offs, info);
+  if (int rc = check_launch("scatter_scan")) return rc;
+  long long want = ((long long)rows * 32 + 255) / 256;
+  const int blocks = (int)(want < 148 * 4 ? want : 148 * 4);
+  launch_pdl(scatter_copy_kernel, dim3(blocks), dim3(256), 0, st, col, val, B, n_dst, per, cap, (const int32_t*)cnt,
+             (const int32_t*)start, (const int32_t*)offs, pl, pv);
+  return check_launch("scatter_copy");
+}
+
+extern "C" int cmmvae_slab_rows(const void* slabs, long long slab_bytes, int B, int n_src, int32_t* row_begin,
+                                int32_t* row_end, void* stream) {
+  CMMVAE_REQUIRE(slabs && slab_bytes % 4 == 0 && B > 0 && n_src >= 1, "slab_rows: bad arguments");
+  const int rows = B * n_src;
+  launch_pdl(slab_rows_kernel, dim3((rows + 255) / 256), dim3(256), 0, (cudaStream_t)stream, (const uint8_t*)slabs,
+             slab_bytes, B, n_src, row_begin, row_end);
+  return check_launch("slab_rows");
 }

@@ -61,12 +61,14 @@ struct SpParams {
 // One thread per non-zero: entry i of row b opens every window in (window(i-1), window(i)] (all windows up
 // to window(i) when it is the row's first entry); the row's last entry also closes the windows after it.
 // Every table cell is written exactly once; rows without entries are filled by tile_ptr64_empty_rows.
-__global__ void __launch_bounds__(256) tile_ptr64_kernel(const int32_t* __restrict__ crow,
+// (rbeg / rend: first / one-past-last position of every row; plain CSR passes crow and crow + 1)
+__global__ void __launch_bounds__(256) tile_ptr64_kernel(const int32_t* __restrict__ rbeg,
+                                                         const int32_t* __restrict__ rend,
                                                          const int32_t* __restrict__ col, int B, int ntp,
                                                          int32_t* __restrict__ tp) {
   pdl_sync();
   for (int b = blockIdx.x; b < B; b += gridDim.x) {      // one CTA per row
-    const int s = crow[b], e = crow[b + 1];
+    const int s = rbeg[b], e = rend[b];
     if (s == e) {
       for (int w = threadIdx.x; w < ntp; w += blockDim.x) tp[(size_t)w * B + b] = s;
       continue;
@@ -498,15 +500,29 @@ extern "C" size_t cmmvae_csr_tile_ptr_bytes(int B, int G) {
 }
 extern "C" size_t cmmvae_csr_packed_bytes(long long nnz) { return sizeof(uint32_t) * (size_t)((nnz + 3) / 4 * 4 + 4); }
 
+static int csr_tile_ptr_rows(const int32_t* rbeg, const int32_t* rend, const int32_t* col, const float* val, int B,
+                             int G, long long nnz, int32_t* tile_ptr, void* packed, void* stream);
+
 extern "C" int cmmvae_csr_tile_ptr(const int32_t* crow, const int32_t* col, const float* val, int B, int G,
                                    long long nnz, int32_t* tile_ptr, void* packed, void* stream) {
+  return csr_tile_ptr_rows(crow, crow + 1, col, val, B, G, nnz, tile_ptr, packed, stream);
+}
+
+extern "C" int cmmvae_csr_tile_ptr_rows(const int32_t* row_begin, const int32_t* row_end, const int32_t* col,
+                                        const float* val, int B, int G, long long n_records, int32_t* tile_ptr,
+                                        void* packed, void* stream) {
+  return csr_tile_ptr_rows(row_begin, row_end, col, val, B, G, n_records, tile_ptr, packed, stream);
+}
+
+static int csr_tile_ptr_rows(const int32_t* crow, const int32_t* crow_end, const int32_t* col, const float* val, int B,
+                             int G, long long nnz, int32_t* tile_ptr, void* packed, void* stream) {
   CMMVAE_REQUIRE(B > 0 && G > 0 && tile_ptr && packed, "csr_tile_ptr: bad arguments");
   CMMVAE_REQUIRE(G <= 65536, "csr_tile_ptr: packed records hold 16-bit gene ids (G=%d)", G);
   CMMVAE_REQUIRE(((uintptr_t)packed & 15) == 0, "csr_tile_ptr: packed must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const int ntp = (G + 63) / 64 + 1;
   int blocks = B < 148 * 16 ? B : 148 * 16;   // one CTA per row
-  launch_pdl(tile_ptr64_kernel, dim3(blocks), dim3(256), 0, st, crow, col, B, ntp, tile_ptr);
+  launch_pdl(tile_ptr64_kernel, dim3(blocks), dim3(256), 0, st, crow, crow_end, col, B, ntp, tile_ptr);
   if (int rc = check_launch("csr_tile_ptr")) return rc;
   long long want;
   const long long padded = (nnz + 3) / 4 * 4 + 4;

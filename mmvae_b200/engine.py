@@ -819,13 +819,17 @@ class StepEngine:
         mx, bmax, bmin = dp.host_allreduce_max([nnz, B, -B])
         if bmax != -bmin:
             raise RuntimeError("data-parallel step needs the same number of cells on every rank")
-        cap = _ceil(int(mx * float(os.environ.get("CMMVAE_DP_CSR_HEADROOM", "1.5"))) + 4096, 1024)
+        # every rank receives, from every rank, the piece of the batch that falls into its gene shard: about
+        # nnz / N entries per piece (uniform panels); headroom for skew, checked on the device every step
+        head = float(os.environ.get("CMMVAE_DP_CSR_HEADROOM", "1.5"))
+        cap = _ceil(int(mx / N * head) + 4096, 1024)
         d = dict(B=B, cap=cap, H1=H1, Hd=Hd)
         d["col_off"] = _ceil(4 * (B + 1), 256)
         d["val_off"] = d["col_off"] + 4 * cap
         d["slab"] = d["val_off"] + 4 * cap
         d["csr"] = [comm.alloc(f"csr{i}", N * d["slab"]) for i in range(2)]
-        d["stage"] = [torch.zeros(d["slab"], dtype=torch.uint8, device=self.device) for _ in range(2)]
+        d["scratch"] = [tuple(torch.zeros(N * B, dtype=torch.int32, device=self.device) for _ in range(3)) +
+                        (torch.zeros(2, dtype=torch.int32, device=self.device),) for _ in range(2)]
         # few cell tiles (small N * B): the routed first-layer product is also cut along the genes so that every SM
         # has a unit; each piece lands in its own slab on the owner
         units = ((N * B + 127) // 128) * ((H1 + 255) // 256)
@@ -837,16 +841,14 @@ class StepEngine:
         d["SC"] = 32
         d["scal"] = comm.alloc("scal", N * d["SC"] * 8)
         d["tails"] = {}
-        # shard CSR capacity: a gene shard of all ranks' cells holds about one rank's worth of non-zeros
-        d["cap_s"] = _ceil(int(cap * float(os.environ.get("CMMVAE_DP_SHARD_HEADROOM", "1.0"))), 1024)
         d["stream"] = torch.cuda.Stream(self.device)
         d["ticket_pf"] = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._dp = d
         return d
 
     def set_dp_capacity(self, max_nnz_per_rank: int):
-        """(before the first step, same value on every rank) non-zeros per rank the exchange buffers are sized for;
-        default: 1.5 x the densest first batch"""
+        """(before the first step, same value on every rank) densest batch, in non-zeros per rank, the exchange buffers
+        are sized for (each of the N pieces of a batch gets 1/N of it); default: 1.5 x the densest first batch"""
         os.environ["CMMVAE_DP_CSR_HEADROOM"] = "1.0"
         self._dp_force_nnz = int(max_nnz_per_rank)
 
@@ -857,27 +859,17 @@ class StepEngine:
             buf = d["tails"][group.name] = self.comm.alloc(f"tail/{group.name}", self.world * _ceil(n, 4) * 4)
         return buf
 
-    def _dp_push_csr(self, crow, col, val, nnz: int, step: int, ticket=None):
-        """this rank's batch -> slab `rank` of every rank's gathered-CSR buffer (parity of the consuming step)"""
+    def _dp_push_csr(self, crow, col, val, nnz: int, step: int, per: int):
+        """all-to-all of this rank's batch by gene shard: piece q of every row is stored straight into slab `rank`
+        of rank q's buffer (parity of the consuming step), columns rebased to the shard; then the flags"""
         d, N, r = self._dp, self.world, self.rank
-        if nnz > d["cap"]:
-            raise RuntimeError(f"batch with {nnz} non-zeros exceeds the data-parallel exchange capacity {d['cap']} "
-                               "agreed on the first step; call engine.set_dp_capacity(n) (same n on every rank) "
-                               "before training on batches of very different density")
         par = step & 1
-        B = d["B"]
-        st = d["stage"][par]
-        st[:4 * (B + 1)].view(torch.int32).copy_(crow)
-        st[d["col_off"]:d["col_off"] + 4 * nnz].view(torch.int32).copy_(col)
-        st[d["val_off"]:d["val_off"] + 4 * nnz].view(torch.float32).copy_(val)
         buf = d["csr"][par]
-        n1 = d["col_off"] + _ceil(4 * nnz, 16)
-        n2 = _ceil(4 * nnz, 16)
+        cnt, start, offs, info = d["scratch"][par]
         base = [p + r * d["slab"] for p in buf.ptr]
-        ticket = self.comm.ticket if ticket is None else ticket     # (one last-block counter per stream)
-        ops.peer_push(st, n1, base, None, step, ticket)
-        ops.peer_push(st[d["val_off"]:], n2, [b + d["val_off"] for b in base],
-                      self.comm.flag_ptrs(f"csr{par}"), step, ticket)
+        ops.csr_scatter_shards(crow, col, val, d["B"], N, per, d["cap"], base, [b + d["col_off"] for b in base],
+                               [b + d["val_off"] for b in base], cnt, start, offs, info)
+        ops.peer_signal(self.comm.flag_ptrs(f"csr{par}"), step)
 
     def prefetch(self, expert_id: str, crow, col, val, ready=None):
         """data parallel: call right AFTER ``train_step`` with the NEXT batch -- its CSR records are exchanged
@@ -901,19 +893,23 @@ class StepEngine:
                 st.wait_event(ready)               # the batch arrays are complete
             if self._dp.get("safe") is not None:   # every rank is past the step that last read this buffer parity
                 st.wait_event(self._dp["safe"])
-            self._dp_push_csr(crow, col, val, nnz, step, self._dp["ticket_pf"])
+            g = self.groups[f"experts/{expert_id}"]
+            per = g.per if g.sharded else _ceil(self.enc_plan[expert_id][0].K, 128)
+            self._dp_push_csr(crow, col, val, nnz, step, per)
         self._csr_pushed[key] = step
         return None
 
     def _dp_prepare(self, gexp: FlatGroup, enc0: LayerPlan, crow, col, val, nnz: int, B: int, G: int, Hd: int):
-        """start of a data-parallel step: gathered CSR of all ranks -> this rank's gene shard as one compact CSR
-        (+ window pointer table and packed records for the tensor-pipe kernels)"""
+        """start of a data-parallel step: the pieces of every rank's batch that fall into this rank's gene shard
+        (all-to-all, normally prefetched) -> row ranges, window pointer table and packed records over the received
+        slabs, in place"""
         N, r = self.world, self.rank
         if self._dp is None:
             self._dp_setup(B, getattr(self, "_dp_force_nnz", nnz), enc0.N, Hd)
         d = self._dp
         if B != d["B"]:
             raise RuntimeError(f"data-parallel step was set up for {d['B']} cells per rank, got {B}")
+        per = d["per"] = gexp.per if gexp.sharded else _ceil(G, 128)
         self._dp_step += 1
         step = self._dp_step
         key = (crow.data_ptr(), col.data_ptr(), val.data_ptr(), nnz)
@@ -926,28 +922,23 @@ class StepEngine:
                 self._csr_pushed.clear()
                 self._dp_step += 1
                 step = self._dp_step
-            self._dp_push_csr(crow, col, val, nnz, step)
+            self._dp_push_csr(crow, col, val, nnz, step, per)
         par = step & 1
-        per = gexp.per if gexp.sharded else _ceil(G, 128)
-        g0 = r * per
-        g1 = min(G, g0 + per)
         NB = N * B
         ops.peer_wait(self.comm.local_flags(f"csr{par}"), N, step)
-        cap_s = d["cap_s"]
-        crow_s = self.ws("dp.crow_s", (NB + 1,), torch.int32)
-        col_s = self.ws("dp.col_s", (cap_s + 8,), torch.int32, zero=True)
-        val_s = self.ws("dp.val_s", (cap_s + 8,), zero=True)
-        info = self.ws("dp.info", (2,), torch.int32)
-        if g1 > g0:
-            ops.shard_csr(d["csr"][par].local, d["slab"], d["col_off"], d["val_off"], B, N, g0, g1, cap_s,
-                          self.ws("dp.cnt", (NB,), torch.int32), self.ws("dp.start", (NB,), torch.int32),
-                          crow_s, col_s, val_s, info)
-        else:      # a trailing rank that owns only padding rows
-            crow_s.zero_()
-            info.zero_()
-        tp = ops.csr_tile_ptr(crow_s, col_s, val_s, per, cap_s - 8,
-                              self.ws("dp.tp64", (NB * ((per + 63) // 64 + 1),), torch.int32),
-                              self.ws("dp.packed", (cap_s + 8,), torch.int32))
+        # the N received slabs are used in place: row ranges over one array spanning all slabs, window pointers
+        # and packed records on top of it -- nothing is copied
+        buf = d["csr"][par].local
+        rbeg, rend = self.ws("dp.rbeg", (NB,), torch.int32), self.ws("dp.rend", (NB,), torch.int32)
+        ops.slab_rows(buf, d["slab"], B, N, rbeg, rend)
+        n_rec = (N * d["slab"] - d["val_off"]) // 4
+        col_s = buf[d["col_off"]:d["col_off"] + 4 * n_rec].view(torch.int32)
+        val_s = buf[d["val_off"]:d["val_off"] + 4 * n_rec].view(torch.float32)
+        tp = ops.csr_tile_ptr_rows(rbeg, rend, col_s, val_s, NB, per, n_rec - 8,
+                                   self.ws("dp.tp64", (NB * ((per + 63) // 64 + 1),), torch.int32),
+                                   self.ws("dp.packed", (n_rec + 8,), torch.int32))
+        info = d["scratch"][par][3]
+        g0, g1, crow_s = r * per, min(G, (r + 1) * per), None
         return dict(step=step, per=per, g0=g0, g1=g1, NB=NB, crow=crow_s, col=col_s, val=val_s, tp=tp, info=info,
                     shard_ssq=self.ws("dp.shard_ssq", (1,), torch.float64), loss_part=self.ws("dp.loss_part", (N,), torch.float64))
 
@@ -1347,8 +1338,9 @@ class StepEngine:
             sc = rec["sc"].cpu().tolist()
         B, Z, n_adv = rec["B"], rec["Z"], rec["n_adv"]
         if rec.get("dp") and sc[-1] != 0:
-            raise RuntimeError(f"data parallel: this rank's gene shard holds {int(sc[-2])} non-zeros, more than the "
-                               "shard capacity (set CMMVAE_DP_SHARD_HEADROOM > 1 for gene panels with skewed shards)")
+            raise RuntimeError(f"data parallel: a gene shard of this rank's batch holds {int(sc[-2])} non-zeros, more "
+                               "than the exchange capacity agreed on the first step (CMMVAE_DP_CSR_HEADROOM, default "
+                               "1.5 x nnz / world; raise it for gene panels whose shards are unevenly populated)")
         out = {"recon_loss": sc[0], "kl_loss": sc[1] / B, "kl_weight": rec["kl_weight"],
                "Mean": sc[2] / (B * Z), "Variance": sc[3] / (B * Z)}
         total = out["recon_loss"] + rec["kl_weight"] * out["kl_loss"]

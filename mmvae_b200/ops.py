@@ -407,11 +407,25 @@ def slab_sum(slabs, n_slabs: int, slab_stride: int, n: int, out32=None, out16=No
                                  int(H), _ptr(out32), _ptr(out16), _stream()), "slab_sum")
 
 
-def shard_csr(gathered, slab_bytes: int, col_off: int, val_off: int, B: int, n_src: int, g0: int, g1: int, cap: int,
-              cnt, start, crow_out, col_out, val_out, info):
-    _check(lib().cmmvae_shard_csr(_ptr(gathered), _c.c_longlong(slab_bytes), _c.c_longlong(col_off),
-                                  _c.c_longlong(val_off), B, n_src, g0, g1, cap, _ptr(cnt), _ptr(start), _ptr(crow_out),
-                                  _ptr(col_out), _ptr(val_out), _ptr(info), _stream()), "shard_csr")
+def csr_scatter_shards(crow, col, val, B: int, n_dst: int, per: int, cap: int, dst_crow, dst_col, dst_val, cnt, start,
+                       offs, info):
+    """all-to-all of the batch by gene shard: piece q of every row -> rank q's slab (peer pointers)"""
+    _check(lib().cmmvae_csr_scatter_shards(_ptr(crow), _ptr(col), _ptr(val), B, n_dst, per, cap, _ptr_array(dst_crow),
+                                           _ptr_array(dst_col), _ptr_array(dst_val), _ptr(cnt), _ptr(start),
+                                           _ptr(offs), _ptr(info), _stream()), "csr_scatter_shards")
+
+
+def slab_rows(slabs, slab_bytes: int, B: int, n_src: int, row_begin, row_end):
+    _check(lib().cmmvae_slab_rows(_ptr(slabs), _c.c_longlong(slab_bytes), B, n_src, _ptr(row_begin), _ptr(row_end),
+                                  _stream()), "slab_rows")
+
+
+def csr_tile_ptr_rows(row_begin, row_end, col, val, B: int, G: int, n_records: int, tp, packed):
+    assert tp.numel() >= B * ((G + 63) // 64 + 1) and packed.numel() >= (n_records + 3) // 4 * 4 + 4
+    _check(lib().cmmvae_csr_tile_ptr_rows(_ptr(row_begin), _ptr(row_end), _ptr(col), _ptr(val), B, G,
+                                          _c.c_longlong(n_records), _ptr(tp), _ptr(packed), _stream()),
+           "csr_tile_ptr_rows")
+    return tp, packed
 
 
 def dp_scalars(slabs, n_src: int, stride: int, rank: int, out_recon, out_norm):
