@@ -390,6 +390,7 @@ def main():
     model.configure_optimizers()
     eng = model.engine()
     eng.pipeline_optimizer = True   # output-layer clip+Adam runs underneath the next forward pass
+    eng.use_graph = os.environ.get("BENCH_GRAPH", "1") != "0"   # single process: steps replayed from CUDA graphs
     names = list(species)
     NB = 4
     host = {s: synth_batches(NB, B, g, DENSITY, 1000 * (rank + 1)) for s, g in species.items()}
@@ -411,7 +412,7 @@ def main():
 
     def resident_step(t):
         s, crow, col, val = resident_batch(t)
-        eng.train_step(s, crow, col, val, int(col.numel()), 1.0, labels=labels[t % NB])
+        eng.train_step(s, crow, col, val, int(col.numel()), 1.0, labels=labels[t % NB], nnz_cap=int(col.numel()))
         if world > 1:      # the exchange of the NEXT batch's CSR records runs underneath this step
             eng.prefetch(*resident_batch(t + 1), ready=True)
 
@@ -425,7 +426,14 @@ def main():
     # inside the timed region only the two kernels the roofline lines are computed from carry CUDA events (an
     # event record between two kernels ends a programmatic-dependent-launch chain); the other sections are
     # timed in a short separate pass afterwards
-    eng.timers, eng.timer_filter = {}, {"decoder_mse_fused", "csr_linear_fwd"}
+    graph_mode = eng.use_graph and world == 1
+    if graph_mode:     # the two roofline kernels are timed by event nodes INSIDE the replayed graphs
+        eng.graph_timers = {"decoder_mse_fused", "csr_linear_fwd"}
+        for t in range(2 * NB * len(names)):          # visit every rotating batch twice: eager warm-up, then capture
+            resident_step(args.warmup + t)
+        barrier()
+    else:
+        eng.timers, eng.timer_filter = {}, {"decoder_mse_fused", "csr_linear_fwd"}
     l0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -436,11 +444,18 @@ def main():
     barrier()
     launches = ops.launch_count() - l0
     ms = e0.elapsed_time(e1)
-    t_dec, t_spmm = eng.timer_ms("decoder_mse_fused"), eng.timer_ms("csr_linear_fwd")
+    if graph_mode:
+        t_dec, t_spmm = eng.graph_timer_ms("decoder_mse_fused"), eng.graph_timer_ms("csr_linear_fwd")
+        launches = None     # replayed launches do not pass through the C ABI: counted from the eager pass below
+    else:
+        t_dec, t_spmm = eng.timer_ms("decoder_mse_fused"), eng.timer_ms("csr_linear_fwd")
     eng.timers, eng.timer_filter = {}, None
+    l1 = ops.launch_count()
     for t in range(min(args.steps, 20)):
         resident_step(args.warmup + args.steps + t)
     barrier()
+    if launches is None:   # kernels per step (eager pass, same launch sequence the graphs replay) x timed steps
+        launches = (ops.launch_count() - l1) // min(args.steps, 20) * args.steps
     t_dw, t_dh, t_adam = eng.timer_ms("dWout_gemm"), eng.timer_ms("dh_gemm"), eng.timer_ms("norm+clip_adam")
     t_spbw = eng.timer_ms("csr_linear_bwd_w+bn")
     t_dp = {k: eng.timer_ms(k) for k in ("csr_prep", "mid_fwd", "mid_bwd", "dp_wait_shadow_first",
@@ -578,6 +593,8 @@ def main():
                 "host_side": f"StagedCSRBatches over pageable scipy CSR chunks, {workers} packing threads inside the "
                              f"timed region, gene ids on the wire: {'uint16' if narrow else 'int32'}"},
         "gpu_launches": int(launches),
+        "launch_mode": ("2 CUDA graphs per step, captured from this library's own launch sequence; gpu_launches = "
+                        "kernels inside the replayed graphs") if graph_mode else "stream launches through the C ABI",
         "roofline": {"kernel": "decoder_mse_fused_kernel (K5-K7: tcgen05 GEMM + ReLU + sum-MSE-vs-CSR epilogue)",
                      "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                      "traffic": traffic, "peak_source": f"{pk_kind} bf16_tflops_sustained (kernel timed inside a step)",

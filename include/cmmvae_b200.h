@@ -194,6 +194,27 @@ int cmmvae_transpose(const void* src, void* dst, int dtype, int R, int C, int ld
 int cmmvae_axpy(float* a, const float* b, float alpha, long long n, void* stream);
 
 
+/* ---- launches that can be REPLAYED from a captured CUDA graph ---------------------------------------------------
+ * The per-step scalars a replayed launch cannot carry by value live in device memory instead: the batch's nnz is
+ * read from crow[B]; the dropout seed is *seed_base + seed; the KL weight is *kl_weight (kl_scale then = 1/B); Adam's
+ * bias corrections are bc[0] = 1 - beta1^t, bc[1] = 1 - beta2^t.  Otherwise identical to the functions above. */
+int cmmvae_csr_tile_ptr_dyn(const int32_t* crow, const int32_t* col, const float* val, int B, int G, long long cap,
+                            int32_t* tile_ptr, void* packed, void* stream);
+int cmmvae_bn_act_drop_fwd_dyn(const float* Y, int B, int H, const float* mean, const float* rstd,
+                               const float* gamma, const float* beta, int relu, float p_drop,
+                               unsigned long long seed, const unsigned long long* seed_base, const uint8_t* mask,
+                               float* out_f32, void* out_bf16, void* stream);
+int cmmvae_bn_act_drop_bwd_dyn(const float* dOut, const float* Y, const float* out, int B, int H,
+                               const float* mean, const float* rstd, const float* gamma,
+                               int relu, float p_drop, unsigned long long seed, const unsigned long long* seed_base,
+                               const uint8_t* mask, float* dY, void* dY_bf16, float* dgamma, float* dbeta,
+                               float* dbias, int accumulate, void* stream);
+int cmmvae_reparam_kl_bwd_dyn(const float* ML, const float* eps, const float* dz, int B, int Z, float var_eps,
+                              float kl_scale, const float* kl_weight, float* dML, void* dML_bf16, void* stream);
+int cmmvae_clip_adam_dyn(float* p, const float* g, float* m, float* v, void* p_bf16, long long n,
+                         const double* norm_sq, float max_norm, float grad_scale, float lr, float beta1, float beta2,
+                         float eps, float wd, const float* bc, int background, void* stream);
+
 /* ---- data parallel over NVLink peer memory (DDP gradient mean of cmmvae_model.py:191-213, taken on a
  * gene-sharded first / last layer) ---------------------------------------------------------
  * No reference counterpart (the reference relies on Lightning DDP = NCCL all-reduce of 500 MB per step).  Every

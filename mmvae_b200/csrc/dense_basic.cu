@@ -77,10 +77,12 @@ __global__ void __launch_bounds__(256) bn_act_drop_fwd_kernel(const float* __res
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, int relu,
                                                               float p_drop, unsigned long long seed,
+                                                              const unsigned long long* __restrict__ seed_base,
                                                               const uint8_t* __restrict__ mask,
                                                               float* __restrict__ o32,
                                                               __nv_bfloat16* __restrict__ o16) {
   pdl_sync();
+  if (seed_base) seed += *seed_base;   // per-step seed kept in device memory (a captured graph replays the launch)
   const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -114,9 +116,12 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
                                                             const float* __restrict__ out, int B, int H,
                                                             const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, int relu, float p_drop,
-                                                            unsigned long long seed, const uint8_t* __restrict__ mask,
+                                                            unsigned long long seed,
+                                                            const unsigned long long* __restrict__ seed_base,
+                                                            const uint8_t* __restrict__ mask,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
   pdl_sync();
+  if (seed_base) seed += *seed_base;
   __shared__ float s1[8][33], s2[8][33];
   const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
   const int h = blockIdx.x * 32 + threadIdx.x;
@@ -152,12 +157,15 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            const float* __restrict__ mean,
                                                            const float* __restrict__ rstd,
                                                            const float* __restrict__ gamma, int relu, float p_drop,
-                                                           unsigned long long seed, const uint8_t* __restrict__ mask,
+                                                           unsigned long long seed,
+                                                           const unsigned long long* __restrict__ seed_base,
+                                                           const uint8_t* __restrict__ mask,
                                                            const float* __restrict__ dgamma,
                                                            const float* __restrict__ dbeta, float* __restrict__ dY,
                                                            __nv_bfloat16* __restrict__ dY16,
                                                            float* __restrict__ dbias) {
   pdl_sync();
+  if (seed_base) seed += *seed_base;
   __shared__ float s1[8][33];
   const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
   const int h = blockIdx.x * 32 + threadIdx.x;
@@ -284,9 +292,12 @@ __global__ void __launch_bounds__(256) reparam_kl_fwd_kernel(const float* __rest
 __global__ void __launch_bounds__(256) reparam_kl_bwd_kernel(const float* __restrict__ ML,
                                                              const float* __restrict__ eps,
                                                              const float* __restrict__ dz, int B, int Z,
-                                                             float var_eps, float kl_scale, float* __restrict__ dML,
+                                                             float var_eps, float kl_scale,
+                                                             const float* __restrict__ kl_weight_dev,
+                                                             float* __restrict__ dML,
                                                              __nv_bfloat16* __restrict__ dML16) {
   pdl_sync();
+  if (kl_weight_dev) kl_scale *= *kl_weight_dev;   // kl_scale then carries only 1/B
   const long long n = (long long)B * Z;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -442,8 +453,10 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(float* __restrict__ p, c
                                                         __nv_bfloat16* __restrict__ p16, long long n,
                                                         const double* __restrict__ norm_sq, float max_norm,
                                                         float grad_scale, float lr, float b1, float b2, float eps,
-                                                        float wd, float bc1, float bc2) {
+                                                        float wd, float bc1, float bc2,
+                                                        const float* __restrict__ bc_dev) {
   pdl_sync();
+  if (bc_dev) { bc1 = bc_dev[0]; bc2 = bc_dev[1]; }   // bias corrections of THIS step, kept in device memory
   float coef = 1.f;
   if (max_norm > 0.f && norm_sq) {
     const float total = (float)sqrt(*norm_sq) * fabsf(grad_scale);
@@ -498,8 +511,10 @@ __global__ void __launch_bounds__(128) clip_adam_bg_kernel(float* __restrict__ p
                                                            __nv_bfloat16* __restrict__ p16, long long n,
                                                            const double* __restrict__ norm_sq, float max_norm,
                                                            float grad_scale, float lr, float b1, float b2,
-                                                           float eps, float wd, float bc1, float bc2) {
+                                                           float eps, float wd, float bc1, float bc2,
+                                                           const float* __restrict__ bc_dev) {
   pdl_sync();
+  if (bc_dev) { bc1 = bc_dev[0]; bc2 = bc_dev[1]; }
   float coef = 1.f;
   if (max_norm > 0.f && norm_sq) {
     const float total = (float)sqrt(*norm_sq) * fabsf(grad_scale);
@@ -603,23 +618,47 @@ extern "C" int cmmvae_rstd_from_var(const float* var, int H, float eps, float* r
   return check_launch("rstd_from_var");
 }
 
+extern "C" int cmmvae_bn_act_drop_fwd_dyn(const float* Y, int B, int H, const float* mean, const float* rstd,
+                                          const float* gamma, const float* beta, int relu, float p_drop,
+                                          unsigned long long seed, const unsigned long long* seed_base,
+                                          const uint8_t* mask, float* out_f32, void* out_bf16, void* stream);
 extern "C" int cmmvae_bn_act_drop_fwd(const float* Y, int B, int H, const float* mean, const float* rstd,
                                       const float* gamma, const float* beta, int relu, float p_drop,
                                       unsigned long long seed, const uint8_t* mask, float* out_f32,
                                       void* out_bf16, void* stream) {
+  return cmmvae_bn_act_drop_fwd_dyn(Y, B, H, mean, rstd, gamma, beta, relu, p_drop, seed, nullptr, mask, out_f32,
+                                    out_bf16, stream);
+}
+extern "C" int cmmvae_bn_act_drop_fwd_dyn(const float* Y, int B, int H, const float* mean, const float* rstd,
+                                          const float* gamma, const float* beta, int relu, float p_drop,
+                                          unsigned long long seed, const unsigned long long* seed_base,
+                                          const uint8_t* mask, float* out_f32, void* out_bf16, void* stream) {
   CMMVAE_REQUIRE(B > 0 && H > 0, "bn_act_drop_fwd: bad shape");
   CMMVAE_REQUIRE(!gamma || (mean && rstd && beta), "bn_act_drop_fwd: gamma without mean/rstd/beta");
   CMMVAE_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "bn_act_drop_fwd: p_drop out of range");
   const long long n = (long long)B * H;
-  launch_pdl(bn_act_drop_fwd_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, Y, n, H, mean, rstd, gamma, beta, relu, p_drop, seed, mask, out_f32, (__nv_bfloat16*)out_bf16);
+  launch_pdl(bn_act_drop_fwd_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, Y, n, H, mean, rstd, gamma, beta, relu, p_drop, seed, seed_base, mask, out_f32, (__nv_bfloat16*)out_bf16);
   return check_launch("bn_act_drop_fwd");
 }
 
+extern "C" int cmmvae_bn_act_drop_bwd_dyn(const float* dOut, const float* Y, const float* out, int B, int H,
+                                          const float* mean, const float* rstd, const float* gamma, int relu,
+                                          float p_drop, unsigned long long seed, const unsigned long long* seed_base,
+                                          const uint8_t* mask, float* dY, void* dY_bf16, float* dgamma, float* dbeta,
+                                          float* dbias, int accumulate, void* stream);
 extern "C" int cmmvae_bn_act_drop_bwd(const float* dOut, const float* Y, const float* out, int B, int H,
                                       const float* mean, const float* rstd, const float* gamma, int relu,
                                       float p_drop, unsigned long long seed, const uint8_t* mask, float* dY,
                                       void* dY_bf16, float* dgamma, float* dbeta, float* dbias, int accumulate,
                                       void* stream) {
+  return cmmvae_bn_act_drop_bwd_dyn(dOut, Y, out, B, H, mean, rstd, gamma, relu, p_drop, seed, nullptr, mask, dY,
+                                    dY_bf16, dgamma, dbeta, dbias, accumulate, stream);
+}
+extern "C" int cmmvae_bn_act_drop_bwd_dyn(const float* dOut, const float* Y, const float* out, int B, int H,
+                                          const float* mean, const float* rstd, const float* gamma, int relu,
+                                          float p_drop, unsigned long long seed, const unsigned long long* seed_base,
+                                          const uint8_t* mask, float* dY, void* dY_bf16, float* dgamma, float* dbeta,
+                                          float* dbias, int accumulate, void* stream) {
   CMMVAE_REQUIRE(B > 0 && H > 0, "bn_act_drop_bwd: bad shape");
   CMMVAE_REQUIRE(!gamma || (mean && rstd && dgamma && dbeta && Y), "bn_act_drop_bwd: BN needs stats and outputs");
   CMMVAE_REQUIRE(!relu || out, "bn_act_drop_bwd: relu needs the forward output");
@@ -633,11 +672,11 @@ extern "C" int cmmvae_bn_act_drop_bwd(const float* dOut, const float* Y, const f
     if (dbias) cudaMemsetAsync(dbias, 0, sizeof(float) * H, st);
   }
   if (gamma) {
-    launch_pdl(bn_bwd_reduce_kernel, dim3(grid), dim3(block), 0, st, dOut, Y, out, B, H, mean, rstd, relu, p_drop, seed, mask,
+    launch_pdl(bn_bwd_reduce_kernel, dim3(grid), dim3(block), 0, st, dOut, Y, out, B, H, mean, rstd, relu, p_drop, seed, seed_base, mask,
                                                  dgamma, dbeta);
     if (int rc = check_launch("bn_bwd_reduce")) return rc;
   }
-  launch_pdl(bn_bwd_apply_kernel, dim3(grid), dim3(block), 0, st, dOut, Y, out, B, H, mean, rstd, gamma, relu, p_drop, seed, mask,
+  launch_pdl(bn_bwd_apply_kernel, dim3(grid), dim3(block), 0, st, dOut, Y, out, B, H, mean, rstd, gamma, relu, p_drop, seed, seed_base, mask,
                                               dgamma, dbeta, dY, (__nv_bfloat16*)dY_bf16, dbias);
   return check_launch("bn_bwd_apply");
 }
@@ -671,13 +710,18 @@ extern "C" int cmmvae_reparam_kl_fwd(const float* ML, const float* eps, int B, i
   return check_launch("reparam_kl_fwd");
 }
 
-extern "C" int cmmvae_reparam_kl_bwd(const float* ML, const float* eps, const float* dz, int B, int Z,
-                                     float var_eps, float kl_scale, float* dML, void* dML_bf16, void* stream) {
+extern "C" int cmmvae_reparam_kl_bwd_dyn(const float* ML, const float* eps, const float* dz, int B, int Z,
+                                         float var_eps, float kl_scale, const float* kl_weight_dev, float* dML,
+                                         void* dML_bf16, void* stream) {
   CMMVAE_REQUIRE(B > 0 && Z > 0, "reparam_kl_bwd: bad shape");
   const long long n = (long long)B * Z;
-  launch_pdl(reparam_kl_bwd_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, ML, eps, dz, B, Z, var_eps, kl_scale, dML,
-                                                                         (__nv_bfloat16*)dML_bf16);
+  launch_pdl(reparam_kl_bwd_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, ML, eps, dz, B, Z, var_eps, kl_scale,
+             kl_weight_dev, dML, (__nv_bfloat16*)dML_bf16);
   return check_launch("reparam_kl_bwd");
+}
+extern "C" int cmmvae_reparam_kl_bwd(const float* ML, const float* eps, const float* dz, int B, int Z,
+                                     float var_eps, float kl_scale, float* dML, void* dML_bf16, void* stream) {
+  return cmmvae_reparam_kl_bwd_dyn(ML, eps, dz, B, Z, var_eps, kl_scale, nullptr, dML, dML_bf16, stream);
 }
 
 extern "C" int cmmvae_softmax_ce_sum(const float* logits, int ldl, int B, int C, const long long* labels,
@@ -709,9 +753,9 @@ extern "C" int cmmvae_sumsq(const float* g, long long n, double* norm_sq, void* 
   return check_launch("sumsq");
 }
 
-extern "C" int cmmvae_clip_adam(float* p, const float* g, float* m, float* v, void* p_bf16, long long n,
-                                const double* norm_sq, float max_norm, float grad_scale, float lr, float beta1,
-                                float beta2, float eps, float wd, float bc1, float bc2, void* stream) {
+static int clip_adam_fg(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, const double* norm_sq,
+                        float max_norm, float grad_scale, float lr, float beta1, float beta2, float eps, float wd,
+                        float bc1, float bc2, const float* bc_dev, void* stream) {
   CMMVAE_REQUIRE(n >= 0, "clip_adam: bad n");
   CMMVAE_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0,
                  "clip_adam: buffers must be 16-byte aligned");
@@ -730,13 +774,19 @@ extern "C" int cmmvae_clip_adam(float* p, const float* g, float* m, float* v, vo
   int blocks = (int)(want < cap ? want : cap);
   launch_pdl(clip_adam_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, (__nv_bfloat16*)p_bf16, n, norm_sq,
                                                              max_norm, grad_scale, lr, beta1, beta2, eps, wd, bc1,
-                                                             bc2);
+                                                             bc2, bc_dev);
   return check_launch("clip_adam");
 }
+extern "C" int cmmvae_clip_adam(float* p, const float* g, float* m, float* v, void* p_bf16, long long n,
+                                const double* norm_sq, float max_norm, float grad_scale, float lr, float beta1,
+                                float beta2, float eps, float wd, float bc1, float bc2, void* stream) {
+  return clip_adam_fg(p, g, m, v, p_bf16, n, norm_sq, max_norm, grad_scale, lr, beta1, beta2, eps, wd, bc1, bc2, nullptr,
+                      stream);
+}
 
-extern "C" int cmmvae_clip_adam_bg(float* p, const float* g, float* m, float* v, void* p_bf16, long long n,
-                                   const double* norm_sq, float max_norm, float grad_scale, float lr, float beta1,
-                                   float beta2, float eps, float wd, float bc1, float bc2, void* stream) {
+static int clip_adam_bg(float* p, const float* g, float* m, float* v, void* p_bf16, long long n, const double* norm_sq,
+                        float max_norm, float grad_scale, float lr, float beta1, float beta2, float eps, float wd,
+                        float bc1, float bc2, const float* bc_dev, void* stream) {
   CMMVAE_REQUIRE(n >= 0 && n / 1024 < 2147483647LL, "clip_adam_bg: bad n");
   CMMVAE_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0,
                  "clip_adam_bg: buffers must be 16-byte aligned");
@@ -744,8 +794,27 @@ extern "C" int cmmvae_clip_adam_bg(float* p, const float* g, float* m, float* v,
   if (n == 0) return 0;
   const long long blocks = (n / 4 + 255) / 256 + 1;
   launch_pdl(clip_adam_bg_kernel, dim3((unsigned)blocks), dim3(128), 0, (cudaStream_t)stream, p, g, m, v,
-             (__nv_bfloat16*)p_bf16, n, norm_sq, max_norm, grad_scale, lr, beta1, beta2, eps, wd, bc1, bc2);
+             (__nv_bfloat16*)p_bf16, n, norm_sq, max_norm, grad_scale, lr, beta1, beta2, eps, wd, bc1, bc2, bc_dev);
   return check_launch("clip_adam_bg");
+}
+extern "C" int cmmvae_clip_adam_bg(float* p, const float* g, float* m, float* v, void* p_bf16, long long n,
+                                   const double* norm_sq, float max_norm, float grad_scale, float lr, float beta1,
+                                   float beta2, float eps, float wd, float bc1, float bc2, void* stream) {
+  return clip_adam_bg(p, g, m, v, p_bf16, n, norm_sq, max_norm, grad_scale, lr, beta1, beta2, eps, wd, bc1, bc2, nullptr,
+                      stream);
+}
+// bias corrections read from device memory (bc_dev[0] = 1 - beta1^t, bc_dev[1] = 1 - beta2^t): the launch can be
+// replayed from a captured CUDA graph while the step count advances
+extern "C" int cmmvae_clip_adam_dyn(float* p, const float* g, float* m, float* v, void* p_bf16, long long n,
+                                    const double* norm_sq, float max_norm, float grad_scale, float lr, float beta1,
+                                    float beta2, float eps, float wd, const float* bc_dev, int background,
+                                    void* stream) {
+  CMMVAE_REQUIRE(bc_dev, "clip_adam_dyn: bc_dev missing");
+  if (background)
+    return clip_adam_bg(p, g, m, v, p_bf16, n, norm_sq, max_norm, grad_scale, lr, beta1, beta2, eps, wd, 1.f, 1.f, bc_dev,
+                        stream);
+  return clip_adam_fg(p, g, m, v, p_bf16, n, norm_sq, max_norm, grad_scale, lr, beta1, beta2, eps, wd, 1.f, 1.f, bc_dev,
+                      stream);
 }
 
 extern "C" int cmmvae_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {

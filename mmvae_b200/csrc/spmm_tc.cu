@@ -85,8 +85,10 @@ __global__ void __launch_bounds__(256) tile_ptr64_kernel(const int32_t* __restri
 
 // packed[i] = col[i] | bf16(val[i]) << 16   (G <= 65536); one 4-byte record per non-zero
 __global__ void csr_pack_kernel(const int32_t* __restrict__ col, const float* __restrict__ val, long long nnz,
-                                long long padded, uint32_t* __restrict__ packed) {
+                                long long padded, uint32_t* __restrict__ packed,
+                                const int32_t* __restrict__ nnz_dev) {
   pdl_sync();
+  if (nnz_dev) nnz = min((long long)*nnz_dev, nnz);   // real count from crow[B] (graph replay); `nnz` = capacity
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < padded;
        i += (long long)gridDim.x * blockDim.x) {
     uint32_t r = 0;
@@ -501,7 +503,15 @@ extern "C" size_t cmmvae_csr_tile_ptr_bytes(int B, int G) {
 extern "C" size_t cmmvae_csr_packed_bytes(long long nnz) { return sizeof(uint32_t) * (size_t)((nnz + 3) / 4 * 4 + 4); }
 
 static int csr_tile_ptr_rows(const int32_t* rbeg, const int32_t* rend, const int32_t* col, const float* val, int B,
-                             int G, long long nnz, int32_t* tile_ptr, void* packed, void* stream);
+                             int G, long long nnz, int32_t* tile_ptr, void* packed, void* stream,
+                             const int32_t* nnz_dev = nullptr);
+
+// nnz is read on the device from crow[B]; `cap` records are written (zeros beyond nnz): the call can be replayed from
+// a captured CUDA graph for batches of different density staged at the same addresses
+extern "C" int cmmvae_csr_tile_ptr_dyn(const int32_t* crow, const int32_t* col, const float* val, int B, int G,
+                                       long long cap, int32_t* tile_ptr, void* packed, void* stream) {
+  return csr_tile_ptr_rows(crow, crow + 1, col, val, B, G, cap, tile_ptr, packed, stream, crow + B);
+}
 
 extern "C" int cmmvae_csr_tile_ptr(const int32_t* crow, const int32_t* col, const float* val, int B, int G,
                                    long long nnz, int32_t* tile_ptr, void* packed, void* stream) {
@@ -515,7 +525,8 @@ extern "C" int cmmvae_csr_tile_ptr_rows(const int32_t* row_begin, const int32_t*
 }
 
 static int csr_tile_ptr_rows(const int32_t* crow, const int32_t* crow_end, const int32_t* col, const float* val, int B,
-                             int G, long long nnz, int32_t* tile_ptr, void* packed, void* stream) {
+                             int G, long long nnz, int32_t* tile_ptr, void* packed, void* stream,
+                             const int32_t* nnz_dev) {
   CMMVAE_REQUIRE(B > 0 && G > 0 && tile_ptr && packed, "csr_tile_ptr: bad arguments");
   CMMVAE_REQUIRE(G <= 65536, "csr_tile_ptr: packed records hold 16-bit gene ids (G=%d)", G);
   CMMVAE_REQUIRE(((uintptr_t)packed & 15) == 0, "csr_tile_ptr: packed must be 16-byte aligned");
@@ -528,7 +539,7 @@ static int csr_tile_ptr_rows(const int32_t* crow, const int32_t* crow_end, const
   const long long padded = (nnz + 3) / 4 * 4 + 4;
   want = (padded + 255) / 256;
   blocks = (int)(want < 148 * 16 ? want : 148 * 16);
-  launch_pdl(csr_pack_kernel, dim3(blocks), dim3(256), 0, st, col, val, nnz, padded, (uint32_t*)packed);
+  launch_pdl(csr_pack_kernel, dim3(blocks), dim3(256), 0, st, col, val, nnz, padded, (uint32_t*)packed, nnz_dev);
   return check_launch("csr_pack");
 }
 

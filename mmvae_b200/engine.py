@@ -118,6 +118,7 @@ class FlatGroup:
         self.bg_range = (len(self.shard_blocks) - 2) if (background_last and len(self.shard_blocks) >= 2) else None
         self.step_count = 0
         self.applied = False    # set by the fused step after its own clip+Adam launch; consumed by FlatAdam.step()
+        self.bc_dev: Optional[torch.Tensor] = None   # device float[2] with this step's Adam bias corrections (graph mode)
         self.master_dirty = False
         self._vec_range: Optional[tuple] = None
         self._deferred: Optional[torch.cuda.Event] = None   # output-layer update in flight on the background stream
@@ -205,15 +206,25 @@ class FlatGroup:
             return
         ops.sumsq(self.g, out)
 
+    def advance(self):
+        """host-side bookkeeping of one optimizer step (what ``clip_adam`` does besides launching)"""
+        self.step_count += 1
+        self.applied = True
+        self.master_dirty = True
+
+    def bias_corrections(self):
+        t = self.step_count
+        return 1.0 - self.betas[0] ** t, 1.0 - self.betas[1] ** t
+
     def clip_adam(self, norm_sq: torch.Tensor, max_norm: Optional[float], grad_scale: float = 1.0,
-                  background: Optional[torch.cuda.Stream] = None):
+                  background: Optional[torch.cuda.Stream] = None, defer_background: bool = False, advance: bool = True):
         """fused clip + Adam over the ranges this rank owns.  ``background``: the output layer's range (which the
         next forward pass reads last) is updated on that low-priority stream, after everything else, so the update
         runs underneath the next step's forward; ``join_background()`` joins it."""
-        self.step_count += 1
-        self.applied = True
-        self.master_dirty = True     # rows owned by other ranks are now stale in this rank's fp32 buffer
+        if advance:
+            self.advance()               # (rows owned by other ranks are now stale in this rank's fp32 buffer)
         hyper = (self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.step_count)
+        bc = self.bc_dev
         if self.sharded:
             todo = list(self.ranges)
             bg = todo.pop(len(self.shard_blocks) - 2) if (background is not None and self.bg_range is not None) else None
@@ -228,10 +239,13 @@ class FlatGroup:
             n = hi - lo
             if n > 0:
                 ops.clip_adam(self.p[lo:hi], self.g[lo:hi], self.m[mv:mv + n], self.v[mv:mv + n], self.p16[lo:hi],
-                              norm_sq, max_norm or 0.0, grad_scale, *hyper)
-        if bg is not None:
-            lo, hi, mv = bg
-            n = hi - lo
+                              norm_sq, max_norm or 0.0, grad_scale, *hyper, bc_dev=bc)
+        if bg is None:
+            return None
+        lo, hi, mv = bg
+        n = hi - lo
+
+        def launch_background():
             first_done = torch.cuda.Event()
             first_done.record()
             # the clip norm lives in the step's scalar block: keep the allocator from recycling that block for a
@@ -240,9 +254,14 @@ class FlatGroup:
             with torch.cuda.stream(background), ops.stream_scope(background):
                 background.wait_event(first_done)
                 ops.clip_adam(self.p[lo:hi], self.g[lo:hi], self.m[mv:mv + n], self.v[mv:mv + n], self.p16[lo:hi],
-                              norm_sq, max_norm or 0.0, grad_scale, *hyper, background=True)
+                              norm_sq, max_norm or 0.0, grad_scale, *hyper, background=True, bc_dev=bc)
                 self._deferred = torch.cuda.Event()
                 self._deferred.record(background)
+
+        if defer_background:      # graph capture: the caller launches it after the capture has ended
+            return launch_background
+        launch_background()
+        return None
 
     def join_background(self):
         """make the current stream wait for an output-layer update still running on the background stream"""
@@ -476,6 +495,15 @@ class StepEngine:
         # pipelined mode, sync_logging=False)
         self.pipeline_optimizer = False
         self._hp = self._bg = None
+        # CUDA-graph mode (single process, pipelined mode): a step is ~70 launches of this library, most of them a
+        # few microseconds of GPU work -- replaying them from two captured graphs removes the launch-bound gaps
+        # between the small kernels and nearly all host work.  Per-step scalars (dropout seed, KL weight, Adam bias
+        # corrections, the batch's nnz) are read from device memory by the replayed launches (``_dyn`` block).
+        self.use_graph = False
+        self.graph_timers: Optional[set] = None    # section names timed INSIDE the captured graphs (bench roofline)
+        self._graphs: Dict[tuple, dict] = {}
+        self._dyn = None
+        self._gmode = None
         self.adv_weight = adv_weight
         self.clip = clip or {"vae": 10.0, "expert": 10.0, "adversarial": 10.0}
         vae = module.vae
@@ -589,6 +617,17 @@ class StepEngine:
         return t[:n]
 
     def _t0(self, name):
+        gm = self._gmode
+        if gm is not None and gm.get("graphs") is not None:
+            # capturing: timing events become event-record nodes of the graph (external events); after a replay they
+            # hold that replay's timestamps
+            if self.graph_timers and name in self.graph_timers:
+                ev = (torch.cuda.Event(enable_timing=True, external=True),
+                      torch.cuda.Event(enable_timing=True, external=True))
+                ev[0].record()
+                gm["events"].setdefault(name, []).append(ev)
+                return ev
+            return None
         if self.timers is None or (self.timer_filter is not None and name not in self.timer_filter):
             return None
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -604,6 +643,13 @@ class StepEngine:
     def timer_ms(self, name) -> float:
         """mean duration (ms) of the events recorded under ``name`` (call after a synchronize)"""
         evs = (self.timers or {}).get(name, [])
+        return sum(a.elapsed_time(b) for a, b in evs) / max(len(evs), 1)
+
+    def graph_timer_ms(self, name) -> float:
+        """graph mode: mean duration (ms) of section ``name`` over the LAST replay of every captured step graph
+        (call after a synchronize; ``graph_timers`` must have held the name when the graphs were captured)"""
+        evs = [ev for e in self._graphs.values() if "gA" in e and e.get("replays", 0) > 0
+               for ev in e["events"].get(name, [])]
         return sum(a.elapsed_time(b) for a, b in evs) / max(len(evs), 1)
 
     def _on_side(self, fn):
@@ -669,7 +715,7 @@ class StepEngine:
         else:
             fused_relu = plain and lp.relu
             Y, y16 = self._linear(tag, lp, x32, x16, B, fused_relu)
-        cache = dict(x32=x32, x16=x16, Y=Y, mean=None, rstd=None, seed=0, mask=None, p=0.0)
+        cache = dict(x32=x32, x16=x16, Y=Y, mean=None, rstd=None, seed=0, mask=None, p=0.0, seed_base=None)
         if plain and (fused_relu or not lp.relu):
             out32, out16 = Y, y16
             if want16 and out16 is None:
@@ -686,12 +732,18 @@ class StepEngine:
                     ops.rstd_from_var(lp.bn.running_var, lp.bn.eps, rstd)
             p = lp.p_drop if training else 0.0
             mask = masks.get(tag) if (masks and p > 0) else None
-            seed = self._next_seed() if (p > 0 and mask is None) else 0
+            sb = None
+            if p > 0 and mask is None and self._dyn is not None:
+                # graph mode: per-step seed in device memory + a per-layer salt (the launch itself is replayed)
+                seed, sb = (hash(tag) & 0xFFFFFFF) * 0x9E3779B1, self._dyn["seed"]
+            else:
+                seed = self._next_seed() if (p > 0 and mask is None) else 0
             out32 = self.ws(tag + ".o32", (B, lp.N))
             out16 = self.ws(tag + ".o16", (B, lp.N), torch.bfloat16) if want16 else None
             ops.bn_act_drop_fwd(Y, mean, rstd, lp.gamma if lp.bn is not None else None,
-                                lp.beta if lp.bn is not None else None, lp.relu, p, seed, mask, out32, out16)
-            cache.update(mean=mean, rstd=rstd, seed=seed, mask=mask, p=p)
+                                lp.beta if lp.bn is not None else None, lp.relu, p, seed, mask, out32, out16,
+                                seed_base=sb)
+            cache.update(mean=mean, rstd=rstd, seed=seed, mask=mask, p=p, seed_base=sb)
         cache.update(out32=out32, out16=out16)
         return out32, out16, cache
 
@@ -704,7 +756,8 @@ class StepEngine:
             dY16 = self.ws(tag + ".dY16", (B, lp.N), torch.bfloat16) if want16 else None
             ops.bn_act_drop_bwd(dOut32, cache["Y"], cache["out32"], cache["mean"], cache["rstd"],
                                 lp.gamma if lp.bn is not None else None, lp.relu, cache["p"], cache["seed"],
-                                cache["mask"], dY, dY16, lp.ggamma, lp.gbeta, lp.gb, accumulate=True)
+                                cache["mask"], dY, dY16, lp.ggamma, lp.gbeta, lp.gb, accumulate=True,
+                                seed_base=cache["seed_base"])
         else:
             dY = dOut32
             dY16 = ops.cast_bf16(dY, self.ws(tag + ".dY16", (B, lp.N), torch.bfloat16)) if want16 else None
@@ -1069,9 +1122,11 @@ class StepEngine:
 
     # ----------------------------------------------------------------------------------------- step
     def train_step(self, expert_id: str, crow, col, val, nnz: int, kl_weight: float, eps=None,
-                   labels: Optional[Dict[str, torch.Tensor]] = None, masks=None):
+                   labels: Optional[Dict[str, torch.Tensor]] = None, masks=None, nnz_cap: Optional[int] = None):
         """One optimisation step on a CSR batch already resident on the device (no host sync).
-        Returns the step record (device scalar block etc.) for ``scalars()``."""
+        Returns the step record (device scalar block etc.) for ``scalars()``.  ``nnz_cap``: elements that may be
+        read behind ``col`` / ``val`` (capacity of the staging block); with it, ``use_graph`` replays the step from
+        captured CUDA graphs keyed by the batch's addresses."""
         if self.pipeline_optimizer:
             if self._hp is None:
                 lo_pri, hi_pri = torch.cuda.Stream.priority_range()
@@ -1080,11 +1135,96 @@ class StepEngine:
             cur = torch.cuda.current_stream()
             self._hp.wait_stream(cur)
             with torch.cuda.stream(self._hp), ops.stream_scope(self._hp):
-                rec = self._train_step(expert_id, crow, col, val, nnz, kl_weight, eps, labels, masks)
+                graphable = (self.use_graph and self.comm is None and nnz_cap is not None and eps is None
+                             and masks is None and self.timers is None and self.precision == "bf16"
+                             and not L._noise_queue and not L._mask_queue)
+                if graphable:
+                    rec = self._graph_step(expert_id, crow, col, val, nnz, kl_weight, labels, int(nnz_cap))
+                else:
+                    rec = self._train_step(expert_id, crow, col, val, nnz, kl_weight, eps, labels, masks)
             cur.wait_stream(self._hp)
             return rec
         with ops.stream_scope(torch.cuda.current_stream()):
             return self._train_step(expert_id, crow, col, val, nnz, kl_weight, eps, labels, masks)
+
+    # ------------------------------------------------------------------------------------ graph mode
+    def _ensure_dyn(self):
+        if self._dyn is None:
+            names = list(self.groups)
+            nbytes = _ceil(16 + 8 * len(names), 16)
+            dev = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+            self._dyn = dict(dev=dev, seed=dev[0:8].view(torch.int64), klw=dev[8:12].view(torch.float32),
+                             host=[torch.zeros(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(8)],
+                             copied=[None] * 8, slot=0, index={n: i for i, n in enumerate(names)}, labels={})
+            for n, i in self._dyn["index"].items():
+                self.groups[n].bc_dev = dev[16 + 8 * i:24 + 8 * i].view(torch.float32)
+        return self._dyn
+
+    def _write_dyn(self, kl_weight: float):
+        """this step's scalars -> pinned block -> device block (one small async copy, stream-ordered before the step)"""
+        d = self._dyn
+        k = d["slot"]
+        d["slot"] = (k + 1) % len(d["host"])
+        if d["copied"][k] is not None:
+            d["copied"][k].synchronize()
+        h = d["host"][k]
+        h[0:8].view(torch.int64)[0] = self._next_seed()
+        f = h[8:].view(torch.float32)
+        f[0] = float(kl_weight)
+        for n, i in d["index"].items():
+            bc1, bc2 = self.groups[n].bias_corrections()
+            f[2 + 2 * i], f[3 + 2 * i] = bc1, bc2
+        d["dev"].copy_(h, non_blocking=True)
+        d["copied"][k] = torch.cuda.Event()
+        d["copied"][k].record()
+
+    def _graph_step(self, expert_id, crow, col, val, nnz, kl_weight, labels, nnz_cap):
+        d = self._ensure_dyn()
+        n_adv = min(len(self.adv), self.n_hidden)
+        if n_adv and labels is not None:      # labels at fixed addresses (the captured launches read them there)
+            for c, t in labels.items():
+                st = d["labels"].get((c, t.numel()))
+                if st is None:
+                    st = d["labels"][(c, t.numel())] = torch.empty_like(t)
+                st.copy_(t, non_blocking=True)
+            labels = {c: d["labels"][(c, t.numel())] for c, t in labels.items()}
+        stepped = [self.groups["vae"], self.groups[f"experts/{expert_id}"]] + [a.group for a in self.adv[:n_adv]]
+        for g in stepped:
+            g.advance()
+        self._write_dyn(kl_weight)
+        key = (expert_id, crow.data_ptr(), col.data_ptr(), val.data_ptr(), crow.numel(), nnz_cap)
+        e = self._graphs.get(key)
+        if e is None:
+            # first visit: eager, with the device-side scalars (allocates every workspace the capture will need)
+            self._gmode = dict(cap=nnz_cap, graphs=None)
+            try:
+                rec = self._train_step(expert_id, crow, col, val, nnz, kl_weight, None, labels, None)
+            finally:
+                self._gmode = None
+            self._graphs[key] = dict()
+            return rec
+        if "gA" not in e:
+            gA, gB = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            self._gmode = dict(cap=nnz_cap, graphs=(gA, gB), events={})
+            gexp = self.groups[f"experts/{expert_id}"]
+            gexp.join_background()
+            try:
+                gA.capture_begin(capture_error_mode="thread_local")   # (packing threads keep issuing copies)
+                rec = self._train_step(expert_id, crow, col, val, nnz, kl_weight, None, labels, None)
+                gB.capture_end()
+                events = self._gmode["events"]
+            finally:
+                self._gmode = None
+            e.update(gA=gA, gB=gB, rec=rec, bg=rec.pop("launch_bg", None), gexp=gexp, events=events, replays=0)
+        e["replays"] += 1
+        e["gA"].replay()
+        e["gexp"].join_background()     # the output layer's update of the previous step (background stream)
+        e["gB"].replay()
+        if e["bg"] is not None:
+            e["bg"]()
+        # (the record's tensors are the graph's static outputs; per-step host values go into a fresh copy)
+        self.last = dict(e["rec"], kl_weight=float(kl_weight))
+        return self.last
 
     def finish(self):
         """join optimizer work still in flight on the background stream (call before reading weights outside
@@ -1130,6 +1270,15 @@ class StepEngine:
                 raise RuntimeError("the data-parallel route needs the bf16 tensor-pipe kernels (hidden sizes % 8 == 0)")
             dpm = self._dp_prepare(gexp, enc[0], crow, col, val, nnz, B, G, out.K)
             use_tc_spmm = True
+        elif self._gmode is not None:
+            # graph mode: always the tensor-pipe route; nnz is read on the device, `cap` records are packed
+            if not tc_ok:
+                raise RuntimeError("graph mode needs the bf16 tensor-pipe SpMM (hidden size % 8 == 0, G <= 65536)")
+            use_tc_spmm = True
+            cap = self._gmode["cap"]
+            tp = ops.csr_tile_ptr_dyn(crow, col, val, G, cap,
+                                      self.ws("tp64", (B * ((G + 63) // 64 + 1),), torch.int32),
+                                      self.ws_cap("packed", (cap + 3) // 4 * 4 + 4, torch.int32))
         else:
             use_tc_spmm = tc_ok and nnz >= self.spmm_tc_min_density * B * G
             if use_tc_spmm:
@@ -1173,7 +1322,13 @@ class StepEngine:
             x32, x16, caches[("dec", j)] = self._layer_fwd(f"dec{j}", lp, x32, x16, B, masks=masks)
         h32, h16 = x32, x16
         self._t1(ev_mid)
+        capturing = self._gmode is not None and self._gmode["graphs"] is not None
+        if capturing:       # first graph ends here: the join with the background stream happens between the two
+            self._gmode["graphs"][0].capture_end()
         gexp.join_background()      # the output layer's update of the previous step (background stream)
+        if capturing:
+            self._gmode["graphs"][1].capture_begin(pool=self._gmode["graphs"][0].pool(),
+                                                   capture_error_mode="thread_local")
         fused = self._tc(out.K) and bf
         H1 = out.K
         # single process: the two big weight-gradient kernels add their own sum of squares to the clip norm
@@ -1212,7 +1367,7 @@ class StepEngine:
                     self._dp_allreduce_start(dpm, ap.group, 0, ap.group.n)
                     self._dp_allreduce_finish(dpm, ap.group, 0, ap.group.n)
                 ap.group.grad_norm_sq(s_norm(2 + i))
-                ap.group.clip_adam(s_norm(2 + i), self.clip.get("adversarial"), gscale)
+                ap.group.clip_adam(s_norm(2 + i), self.clip.get("adversarial"), gscale, advance=self._gmode is None)
             for i in range(n_adv):
                 ap = self.adv[i]
                 hid, hid16 = hidden[i][2], hidden[i][3]
@@ -1253,7 +1408,10 @@ class StepEngine:
                 ops.axpy(dz, d_hidden[i], -1.0)                            # GRL: -alpha * grad, alpha = 1
         dML = self.ws("dML", (B, 2 * Z))
         dML16 = self.ws("dML16", (B, 2 * Z), torch.bfloat16) if bf else None
-        ops.reparam_kl_bwd(ML, eps, dz, Z, self.var_eps, float(kl_weight) / B, dML, dML16)
+        if self._dyn is not None:     # graph mode: the KL weight of this step lives in device memory
+            ops.reparam_kl_bwd(ML, eps, dz, Z, self.var_eps, 1.0 / B, dML, dML16, kl_weight_dev=self._dyn["klw"])
+        else:
+            ops.reparam_kl_bwd(ML, eps, dz, Z, self.var_eps, float(kl_weight) / B, dML, dML16)
         dq = self.ws("dq", (B, self.Hv))
         if self._tf(self.Hv, 2 * Z):
             self._on_side(lambda: (ops.colsum(dML, self.gbmv, accumulate=True),
@@ -1309,12 +1467,15 @@ class StepEngine:
             gvae.grad_norm_sq(s_norm(0))
             gexp.grad_norm_sq(s_norm(1), skip=[enc[0].lin.weight, out.lin.weight] if fuse_norm else None)
         bg = self._bg if self.pipeline_optimizer else None
-        gvae.clip_adam(s_norm(0), self.clip.get("vae"), gscale)
-        gexp.clip_adam(s_norm(1), self.clip.get("expert"), gscale, background=bg)
+        gvae.clip_adam(s_norm(0), self.clip.get("vae"), gscale, advance=self._gmode is None)
+        launch_bg = gexp.clip_adam(s_norm(1), self.clip.get("expert"), gscale, background=bg,
+                                   defer_background=capturing, advance=self._gmode is None)
         self._t1(ev)
 
         self.last = dict(sc=sc, B=B, Z=Z, kl_weight=float(kl_weight), expert_id=expert_id, n_adv=n_adv,
                          gscale=gscale, ce_base=ce_base, z=z32, dl=dl, dp=dpm is not None)
+        if launch_bg is not None:
+            self.last["launch_bg"] = launch_bg
         return self.last
 
     # ---------------------------------------------------------------------------------------- logs

@@ -119,7 +119,9 @@ class CSRStager:
         self._n += 1
         if self._copied[slot] is not None:
             self._copied[slot].synchronize()      # the pinned block is free once its copy has left
-        o_crow, o_col, o_val, _ = block_layout(n_cells, nnz, self.col_bytes)
+        # sections sit at offsets fixed by the ring's CAPACITY, so a slot hands out the same device addresses for
+        # every batch (the fused step replays CUDA graphs keyed by them)
+        o_crow, o_col, o_val, _ = block_layout(self.max_cells, self.max_nnz, self.col_bytes)
         h = self.host[slot].numpy()
         return Block(slot, n_cells, nnz,
                      h[o_crow:o_crow + 4 * (n_cells + 1)].view(np.int32),
@@ -131,20 +133,25 @@ class CSRStager:
         (unchanged) as long as it has not been handed out by a later ``reserve``"""
         if b.n_cells >= 0 and (int(b.crow[0]) != 0 or int(b.crow[-1]) != b.nnz):
             raise ValueError("inconsistent CSR arrays (crow[0] must be 0, crow[-1] == len(col) == len(val))")
-        o_crow, o_col, o_val, used = block_layout(b.n_cells, b.nnz, self.col_bytes)
+        o_crow, o_col, o_val, _ = block_layout(self.max_cells, self.max_nnz, self.col_bytes)
         if self.narrow and int(n_genes) > 65536:
             raise ValueError(f"narrow_col stages 16-bit gene ids; the panel has {n_genes} genes")
-        self.bytes_staged = used
+        # two copies per batch: [crow | col] (contiguous prefix) and val; only the bytes the batch uses travel
+        n1 = _align(o_col + self.col_bytes * b.nnz)
+        n2 = _align(4 * b.nnz)
+        self.bytes_staged = n1 + n2
         slot = b.slot
         if not self.on_gpu:
-            self.dev[slot][:used].copy_(self.host[slot][:used])
+            self.dev[slot][:n1].copy_(self.host[slot][:n1])
+            self.dev[slot][o_val:o_val + n2].copy_(self.host[slot][o_val:o_val + n2])
             if self.narrow:
                 self.col32[slot][:b.nnz].copy_(self.dev[slot][o_col:o_col + 2 * b.nnz].view(torch.uint16).to(torch.int32))
             return Ticket(slot, b.n_cells, int(n_genes), b.nnz, None)
         with torch.cuda.stream(self.stream):
             if self._consumed[slot] is not None:
                 self.stream.wait_event(self._consumed[slot])    # do not overwrite a block a step still reads
-            self.dev[slot][:used].copy_(self.host[slot][:used], non_blocking=True)
+            self.dev[slot][:n1].copy_(self.host[slot][:n1], non_blocking=True)
+            self.dev[slot][o_val:o_val + n2].copy_(self.host[slot][o_val:o_val + n2], non_blocking=True)
             if self.narrow:
                 from . import ops
                 ops.widen_u16_i32(self.dev[slot][o_col:], self.col32[slot], b.nnz, stream=self.stream)
@@ -174,7 +181,7 @@ class CSRStager:
         current stream waits for the copy"""
         if t.ready is not None:
             torch.cuda.current_stream(self.device).wait_event(t.ready)
-        o_crow, o_col, o_val, _ = block_layout(t.n_cells, t.nnz, self.col_bytes)
+        o_crow, o_col, o_val, _ = block_layout(self.max_cells, self.max_nnz, self.col_bytes)
         d = self.dev[t.slot]
         crow = d[o_crow:o_crow + 4 * (t.n_cells + 1)].view(torch.int32)
         col = self.col32[t.slot][:t.nnz] if self.narrow else d[o_col:o_col + 4 * t.nnz].view(torch.int32)
@@ -186,6 +193,7 @@ class CSRStager:
         crow, col, val = self.arrays(t)
         x = torch.sparse_csr_tensor(crow, col, val, size=(t.n_cells, t.n_genes))
         x._cmmvae_ready = t.ready if t.ready is not None else True     # for CMMVAEModel.prefetch_batch (data parallel)
+        x._cmmvae_cap = self.max_nnz       # elements behind col / val that may be addressed (graph replay)
         return x
 
     def release(self, t: Ticket):

@@ -54,6 +54,9 @@ class CMMVAEModel(BaseModel):
         # step, the reference's timing).  False: the scalars are copied to pinned host memory asynchronously
         # and logged at the NEXT training_step (or flush_logs()), so the host never waits for the GPU.
         self.sync_logging = True
+        # pipelined mode + batches from mmvae_b200.feed (fixed addresses per ring slot): the step is replayed from
+        # captured CUDA graphs
+        self.use_cuda_graphs = True
         self._pending_log = None
         self._label_ring = {}    # (n conditions, B) -> [pinned blocks, events of their last copy, next slot]
 
@@ -269,7 +272,9 @@ class CMMVAEModel(BaseModel):
         crow, col, val, nnz = self._csr(x)
         labels = self._labels(metadata, x.device) if len(self.module.adversarials) else None
         eng.pipeline_optimizer = not self.sync_logging    # pipelined mode: results (logs, output-layer update) trail
-        rec = eng.train_step(expert_id, crow, col, val, nnz, self.kl_annealing_fn.kl_weight, labels=labels)
+        eng.use_graph = eng.pipeline_optimizer and self.use_cuda_graphs
+        rec = eng.train_step(expert_id, crow, col, val, nnz, self.kl_annealing_fn.kl_weight, labels=labels,
+                             nnz_cap=getattr(x, "_cmmvae_cap", None))
         self._mark_stepped(expert_id, rec["n_adv"])
         self.kl_annealing_fn.step()
         if self.sync_logging:

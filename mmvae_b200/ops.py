@@ -134,6 +134,15 @@ def csr_tile_ptr(crow, col, val, G: int, nnz: int, tp=None, packed=None):
     return tp, packed
 
 
+def csr_tile_ptr_dyn(crow, col, val, G: int, cap: int, tp, packed):
+    """csr_tile_ptr whose non-zero count is read on the device (crow[B]); ``cap`` records are written"""
+    B = crow.numel() - 1
+    assert tp.numel() >= B * ((G + 63) // 64 + 1) and packed.numel() >= (cap + 3) // 4 * 4 + 4
+    _check(lib().cmmvae_csr_tile_ptr_dyn(_ptr(crow), _ptr(col), _ptr(val), B, G, _c.c_longlong(cap), _ptr(tp),
+                                         _ptr(packed), _stream()), "csr_tile_ptr_dyn")
+    return tp, packed
+
+
 def csr_linear_fwd_tc(packed, tile_ptr, B: int, G: int, Wt16, bias, out=None):
     H = Wt16.shape[1]
     assert Wt16.dtype == torch.bfloat16 and Wt16.is_contiguous() and Wt16.shape[0] == G
@@ -218,20 +227,21 @@ def rstd_from_var(var, eps, rstd):
            "rstd_from_var")
 
 
-def bn_act_drop_fwd(Y, mean, rstd, gamma, beta, relu, p_drop, seed, mask, out32, out16):
+def bn_act_drop_fwd(Y, mean, rstd, gamma, beta, relu, p_drop, seed, mask, out32, out16, seed_base=None):
+    """``seed_base`` (device uint64[1], optional): effective seed = *seed_base + seed (graph replay)"""
     B, H = Y.shape
-    _check(lib().cmmvae_bn_act_drop_fwd(_ptr(Y), B, H, _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta), int(relu),
-                                        _c.c_float(p_drop), _c.c_ulonglong(seed), _ptr(mask), _ptr(out32),
-                                        _ptr(out16), _stream()), "bn_act_drop_fwd")
+    _check(lib().cmmvae_bn_act_drop_fwd_dyn(_ptr(Y), B, H, _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(beta), int(relu),
+                                            _c.c_float(p_drop), _c.c_ulonglong(seed), _ptr(seed_base), _ptr(mask),
+                                            _ptr(out32), _ptr(out16), _stream()), "bn_act_drop_fwd")
 
 
 def bn_act_drop_bwd(dOut, Y, out, mean, rstd, gamma, relu, p_drop, seed, mask, dY, dY16, dgamma, dbeta, dbias,
-                    accumulate=False):
+                    accumulate=False, seed_base=None):
     B, H = dOut.shape
-    _check(lib().cmmvae_bn_act_drop_bwd(_ptr(dOut), _ptr(Y), _ptr(out), B, H, _ptr(mean), _ptr(rstd), _ptr(gamma),
-                                        int(relu), _c.c_float(p_drop), _c.c_ulonglong(seed), _ptr(mask), _ptr(dY),
-                                        _ptr(dY16), _ptr(dgamma), _ptr(dbeta), _ptr(dbias), int(accumulate),
-                                        _stream()),
+    _check(lib().cmmvae_bn_act_drop_bwd_dyn(_ptr(dOut), _ptr(Y), _ptr(out), B, H, _ptr(mean), _ptr(rstd), _ptr(gamma),
+                                            int(relu), _c.c_float(p_drop), _c.c_ulonglong(seed), _ptr(seed_base),
+                                            _ptr(mask), _ptr(dY), _ptr(dY16), _ptr(dgamma), _ptr(dbeta), _ptr(dbias),
+                                            int(accumulate), _stream()),
            "bn_act_drop_bwd")
 
 
@@ -282,10 +292,12 @@ def reparam_kl_fwd(ML, eps, Z, var_eps, z32, z16, sums):
                                        _ptr(sums), _stream()), "reparam_kl_fwd")
 
 
-def reparam_kl_bwd(ML, eps, dz, Z, var_eps, kl_scale, dML, dML16):
+def reparam_kl_bwd(ML, eps, dz, Z, var_eps, kl_scale, dML, dML16, kl_weight_dev=None):
+    """``kl_weight_dev`` (device float[1], optional): effective scale = kl_scale * *kl_weight_dev (graph replay)"""
     B = ML.shape[0]
-    _check(lib().cmmvae_reparam_kl_bwd(_ptr(ML), _ptr(eps), _ptr(dz), B, Z, _c.c_float(var_eps),
-                                       _c.c_float(kl_scale), _ptr(dML), _ptr(dML16), _stream()), "reparam_kl_bwd")
+    _check(lib().cmmvae_reparam_kl_bwd_dyn(_ptr(ML), _ptr(eps), _ptr(dz), B, Z, _c.c_float(var_eps),
+                                           _c.c_float(kl_scale), _ptr(kl_weight_dev), _ptr(dML), _ptr(dML16),
+                                           _stream()), "reparam_kl_bwd")
 
 
 def softmax_ce_sum(logits, C, labels, scale, dlogits, loss_sum):
@@ -301,7 +313,16 @@ def sumsq(g, norm_sq):
     _check(lib().cmmvae_sumsq(_ptr(g), _c.c_longlong(g.numel()), _ptr(norm_sq), _stream()), "sumsq")
 
 
-def clip_adam(p, g, m, v, p16, norm_sq, max_norm, grad_scale, lr, beta1, beta2, eps, wd, step, background=False):
+def clip_adam(p, g, m, v, p16, norm_sq, max_norm, grad_scale, lr, beta1, beta2, eps, wd, step, background=False,
+              bc_dev=None):
+    """``bc_dev`` (device float[2], optional): the two bias corrections live in device memory (graph replay)"""
+    if bc_dev is not None:
+        _check(lib().cmmvae_clip_adam_dyn(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p16), _c.c_longlong(p.numel()),
+                                          _ptr(norm_sq), _c.c_float(max_norm if max_norm else 0.0),
+                                          _c.c_float(grad_scale), _c.c_float(lr), _c.c_float(beta1), _c.c_float(beta2),
+                                          _c.c_float(eps), _c.c_float(wd), _ptr(bc_dev), int(background), _stream()),
+               "clip_adam_dyn")
+        return
     bc1 = 1.0 - beta1 ** step
     bc2 = 1.0 - beta2 ** step
     fn = lib().cmmvae_clip_adam_bg if background else lib().cmmvae_clip_adam
