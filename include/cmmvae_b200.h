@@ -32,6 +32,11 @@ long long cmmvae_launch_count(void);
 /* SMs the persistent tensor kernels plan their grids / split-K factors for (default 148).  Lower it while
  * communication kernels (NCCL) share the GPU so that all planned CTAs are co-resident. */
 int cmmvae_set_sm_budget(int sms);
+/* programmatic dependent launch between consecutive kernels of a stream (default on; CMMVAE_PDL=0 disables it for
+ * the process).  The host turns it off while it CAPTURES a CUDA graph: measured on B200, graph nodes with
+ * programmatic edges replay slower (1.65 ms per step) than plain nodes (1.55 ms), while stream launches gain from
+ * it (1.58 -> 1.50 ms). */
+int cmmvae_set_pdl(int on);
 
 /* ---- K1: expert-encoder first layer on a CSR batch ---------------------------------------
  * replaces nn.Linear applied to torch.sparse_csr input: components.py:276,306 (FCBlock layer 0

@@ -10,12 +10,13 @@ static thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 static std::atomic<int> g_sm_budget{kNumSMs};
 int sm_budget() { return g_sm_budget.load(std::memory_order_relaxed); }
+static std::atomic<int> g_pdl{1};
 bool pdl_enabled() {
   static const bool on = [] {
     const char* e = getenv("CMMVAE_PDL");
     return !(e && strcmp(e, "0") == 0);
   }();
-  return on;
+  return on && g_pdl.load(std::memory_order_relaxed) != 0;
 }
 
 void set_error(const char* fmt, ...) {
@@ -35,5 +36,10 @@ extern "C" int cmmvae_set_sm_budget(int sms) {
     return -1;
   }
   cmmvae::g_sm_budget.store(sms);
+  return 0;
+}
+
+extern "C" int cmmvae_set_pdl(int on) {
+  cmmvae::g_pdl.store(on ? 1 : 0);
   return 0;
 }

@@ -1124,9 +1124,9 @@ class StepEngine:
     def train_step(self, expert_id: str, crow, col, val, nnz: int, kl_weight: float, eps=None,
                    labels: Optional[Dict[str, torch.Tensor]] = None, masks=None, nnz_cap: Optional[int] = None):
         """One optimisation step on a CSR batch already resident on the device (no host sync).
-        Returns the step record (device scalar block etc.) for ``scalars()``.  ``nnz_cap``: elements that may be
-        read behind ``col`` / ``val`` (capacity of the staging block); with it, ``use_graph`` replays the step from
-        captured CUDA graphs keyed by the batch's addresses."""
+        Returns the step record (device scalar block etc.) for ``scalars()``.  With ``use_graph`` (pipelined mode,
+        single process) the step is replayed from captured CUDA graphs; ``nnz_cap`` (optional) = the densest batch
+        to size the graph's input buffers for."""
         if self.pipeline_optimizer:
             if self._hp is None:
                 lo_pri, hi_pri = torch.cuda.Stream.priority_range()
@@ -1135,11 +1135,11 @@ class StepEngine:
             cur = torch.cuda.current_stream()
             self._hp.wait_stream(cur)
             with torch.cuda.stream(self._hp), ops.stream_scope(self._hp):
-                graphable = (self.use_graph and self.comm is None and nnz_cap is not None and eps is None
+                graphable = (self.use_graph and self.comm is None and eps is None
                              and masks is None and self.timers is None and self.precision == "bf16"
                              and not L._noise_queue and not L._mask_queue)
                 if graphable:
-                    rec = self._graph_step(expert_id, crow, col, val, nnz, kl_weight, labels, int(nnz_cap))
+                    rec = self._graph_step(expert_id, crow, col, val, nnz, kl_weight, labels, nnz_cap)
                 else:
                     rec = self._train_step(expert_id, crow, col, val, nnz, kl_weight, eps, labels, masks)
             cur.wait_stream(self._hp)
@@ -1155,7 +1155,8 @@ class StepEngine:
             dev = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
             self._dyn = dict(dev=dev, seed=dev[0:8].view(torch.int64), klw=dev[8:12].view(torch.float32),
                              host=[torch.zeros(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(8)],
-                             copied=[None] * 8, slot=0, index={n: i for i, n in enumerate(names)}, labels={})
+                             copied=[None] * 8, slot=0, index={n: i for i, n in enumerate(names)}, labels={},
+                             inputs={})
             for n, i in self._dyn["index"].items():
                 self.groups[n].bc_dev = dev[16 + 8 * i:24 + 8 * i].view(torch.float32)
         return self._dyn
@@ -1192,7 +1193,22 @@ class StepEngine:
         for g in stepped:
             g.advance()
         self._write_dyn(kl_weight)
-        key = (expert_id, crow.data_ptr(), col.data_ptr(), val.data_ptr(), crow.numel(), nnz_cap)
+        # the batch is copied to fixed addresses first (25 MB device-to-device, a few microseconds): ONE graph pair per
+        # (expert, cell count) serves every batch, wherever it was staged
+        Bp1 = crow.numel()
+        gin = d["inputs"].get((expert_id, Bp1))
+        if gin is None or gin["cap"] < nnz:
+            cap = max(int(nnz * 1.25) + 1024, int(nnz_cap or 0))
+            gin = d["inputs"][(expert_id, Bp1)] = dict(
+                cap=cap, crow=torch.empty(Bp1, dtype=torch.int32, device=self.device),
+                col=torch.empty(cap, dtype=torch.int32, device=self.device),
+                val=torch.empty(cap, dtype=torch.float32, device=self.device))
+            self._graphs.pop((expert_id, Bp1), None)       # captured against the old addresses
+        gin["crow"].copy_(crow, non_blocking=True)
+        gin["col"][:nnz].copy_(col, non_blocking=True)
+        gin["val"][:nnz].copy_(val, non_blocking=True)
+        crow, col, val, nnz_cap = gin["crow"], gin["col"][:nnz], gin["val"][:nnz], gin["cap"]
+        key = (expert_id, Bp1)
         e = self._graphs.get(key)
         if e is None:
             # first visit: eager, with the device-side scalars (allocates every workspace the capture will need)
@@ -1208,6 +1224,7 @@ class StepEngine:
             self._gmode = dict(cap=nnz_cap, graphs=(gA, gB), events={})
             gexp = self.groups[f"experts/{expert_id}"]
             gexp.join_background()
+            ops.set_pdl(False)    # plain graph nodes replay faster than nodes with programmatic edges (measured)
             try:
                 gA.capture_begin(capture_error_mode="thread_local")   # (packing threads keep issuing copies)
                 rec = self._train_step(expert_id, crow, col, val, nnz, kl_weight, None, labels, None)
@@ -1215,6 +1232,7 @@ class StepEngine:
                 events = self._gmode["events"]
             finally:
                 self._gmode = None
+                ops.set_pdl(True)
             e.update(gA=gA, gB=gB, rec=rec, bg=rec.pop("launch_bg", None), gexp=gexp, events=events, replays=0)
         e["replays"] += 1
         e["gA"].replay()

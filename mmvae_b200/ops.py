@@ -73,6 +73,10 @@ def launch_count() -> int:
     return int(lib().cmmvae_launch_count())
 
 
+def set_pdl(on: bool) -> None:
+    _check(lib().cmmvae_set_pdl(int(bool(on))), "set_pdl")
+
+
 def set_sm_budget(sms: int) -> None:
     _check(lib().cmmvae_set_sm_budget(int(sms)), "set_sm_budget")
 
