@@ -78,7 +78,7 @@ def test_graph_replay_trains_like_stream_launches(with_adv, tmp_path):
         assert a.keys() == b.keys()
         for k in a:
             # dropout is off here, so the two runs differ only by atomics' summation order
-            tol = 2e-2 if k.startswith("grad_norms") else 2e-3     # (gradients react to last-bit differences upstream)
+            tol = 2e-2 if k.startswith("grad_norms") else 5e-3     # (gradients react to last-bit differences upstream)
             atol = 2e-3 if k.startswith("Mean") else 1e-6          # mean of mu: a difference of O(1) terms near zero
             assert b[k] == pytest.approx(a[k], rel=tol, abs=atol), (t, k, a[k], b[k])
     for k, v in sa.items():

@@ -16,6 +16,13 @@ printf '\n[options.packages.find]\nwhere = src\n' >> "$TMP/setup.cfg"
 rm -rf "$ROOT/baseline/_ref"
 python -m pip install --no-index --no-build-isolation --find-links /opt/wheelhouse --no-deps \
     --target "$ROOT/baseline/_ref" "$TMP" >/dev/null
+# the reference's own unit tests travel with the install (git-ignored like the rest of baseline/_ref):
+# tests/test_reference_unit_tests_gpu.py runs them, unmodified, against this repo's modules on the GPU
+mkdir -p "$ROOT/baseline/_ref/reference_tests"
+cp "$SRC/tests/test_components.py" "$SRC/tests/test_tag_log_dict.py" "$ROOT/baseline/_ref/reference_tests/"
+# (two of those tests read a label list relative to the reference's repository root)
+mkdir -p "$ROOT/baseline/_ref/reference_tests/src/cmmvae/data/conditional_layers"
+cp "$SRC/src/cmmvae/data/conditional_layers/unique_assays.csv" "$ROOT/baseline/_ref/reference_tests/src/cmmvae/data/conditional_layers/"
 rm -rf "$TMP"
 python - <<PY
 import sys; sys.path.insert(0, "$ROOT/baseline/_ref")
