@@ -16,6 +16,9 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from . import torch_ops  # noqa: F401  (registers torch.ops.cmmvae.*)
+
+C = torch.ops.cmmvae     # the module route goes through the custom-op layer (see torch_ops.py)
 
 _PRECISION = "bf16"
 BN_SCRATCH = {}
@@ -98,7 +101,7 @@ def bf16_of(t: torch.Tensor) -> torch.Tensor:
     """fresh bf16 copy of an fp32 tensor (cast kernel)"""
     src = t.detach().contiguous()
     dst = torch.empty(src.shape, dtype=torch.bfloat16, device=t.device)
-    ops.cast_bf16(src, dst)
+    C.cast_bf16(src, dst)
     return dst
 
 
@@ -128,12 +131,12 @@ def dense_linear(x32, x16, W, bias, relu=False, W16=None):
         if x16 is None:
             x16 = bf16_of(x32)
         y16 = torch.empty(B, N, device=dev, dtype=torch.bfloat16)
-        ops.gemm(x16, 0, W16 if W16 is not None else bf16_of(W), 0, B, N, K, bias=bias, relu=relu, C32=y32, C16=y16)
+        C.gemm(x16, False, W16 if W16 is not None else bf16_of(W), False, B, N, K, bias, relu, y32, y16, False)
         return y32, y16
     if x32 is None:
         x32 = x16.float()
     Wc = W if W.stride(1) == 1 else W.contiguous()
-    ops.gemm(x32.contiguous(), 0, Wc, 0, B, N, K, bias=bias, relu=relu, C32=y32, use_tc=False)
+    C.gemm(x32.contiguous(), False, Wc, False, B, N, K, bias, relu, y32, None, False)
     return y32, None
 
 
@@ -144,18 +147,18 @@ def dense_linear_bwd(dY32, x32, W, need_dx=True, W16=None):
     dev = W.device
     dW = torch.empty(N, K, device=dev, dtype=torch.float32)
     db = torch.empty(N, device=dev, dtype=torch.float32)
-    ops.colsum(dY32, db)
+    C.colsum(dY32, db)
     dX = torch.empty(B, K, device=dev, dtype=torch.float32) if need_dx else None
     if tc_ok(K, N) and W.is_contiguous():
         dY16, x16 = bf16_of(dY32), bf16_of(x32)
-        ops.gemm(dY16, 1, x16, 1, N, K, B, C32=dW)
+        C.gemm(dY16, True, x16, True, N, K, B, None, False, dW, None, False)
         if need_dx:
-            ops.gemm(dY16, 0, W16 if W16 is not None else bf16_of(W), 1, B, K, N, C32=dX)
+            C.gemm(dY16, False, W16 if W16 is not None else bf16_of(W), True, B, K, N, None, False, dX, None, False)
     else:
         Wc = W if W.stride(1) == 1 else W.contiguous()
-        ops.gemm(dY32, 1, x32.contiguous(), 1, N, K, B, C32=dW, use_tc=False)
+        C.gemm(dY32, True, x32.contiguous(), True, N, K, B, None, False, dW, None, False)
         if need_dx:
-            ops.gemm(dY32, 0, Wc, 1, B, K, N, C32=dX, use_tc=False)
+            C.gemm(dY32, False, Wc, True, B, K, N, None, False, dX, None, False)
     return dX, dW, db
 
 
@@ -181,7 +184,7 @@ class _LayerFn(torch.autograd.Function):
                     Wt = Wt.contiguous()
                 if _PRECISION == "bf16":
                     Wt = bf16_of(Wt)
-            Y = ops.csr_linear_fwd(crow, col, val, spec.G, Wt, b)
+            Y = C.csr_linear_fwd(crow, col, val, spec.G, Wt, b)
         else:
             Y, _ = dense_linear(x, None, W, b, relu=False, W16=spec.W16)
         B, H = Y.shape
@@ -190,16 +193,16 @@ class _LayerFn(torch.autograd.Function):
             mean = torch.empty(H, device=dev)
             rstd = torch.empty(H, device=dev)
             if spec.training:
-                ops.bn_stats(Y, spec.eps, spec.momentum, mean, rstd, rm, rv, _scratch(H, dev))
+                C.bn_stats(Y, spec.eps, spec.momentum, mean, rstd, rm, rv)
             else:
                 mean = rm
-                ops.rstd_from_var(rv, spec.eps, rstd)
+                C.rstd_from_var(rv, spec.eps, rstd)
         p = spec.p if spec.training else 0.0
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if p > 0 else 0
         if spec.has_bn or spec.relu or p > 0:
             out = torch.empty_like(Y)
-            ops.bn_act_drop_fwd(Y, mean, rstd, gamma if spec.has_bn else None, beta if spec.has_bn else None,
-                                spec.relu, p, seed, None, out, None)
+            C.bn_act_drop_fwd(Y, mean, rstd, gamma if spec.has_bn else None, beta if spec.has_bn else None,
+                              bool(spec.relu), p, seed, out)
         else:
             out = Y
         ctx.spec, ctx.seed, ctx.p = spec, seed, p
@@ -220,17 +223,15 @@ class _LayerFn(torch.autograd.Function):
             dY = torch.empty_like(dOut)
             if spec.has_bn:
                 dgamma, dbeta = torch.empty(H, device=dev), torch.empty(H, device=dev)
-            ops.bn_act_drop_bwd(dOut, Y, out, mean, rstd, gamma if spec.has_bn else None, spec.relu, ctx.p,
-                                ctx.seed, None, dY, None, dgamma, dbeta, None)
+            C.bn_act_drop_bwd(dOut, Y, out, mean, rstd, gamma if spec.has_bn else None, bool(spec.relu), ctx.p,
+                              ctx.seed, dY, dgamma, dbeta)
         else:
             dY = dOut
         if spec.csr is not None:
             crow, col, val, nnz = spec.csr
-            cptr, ridx, cval = ops.csr_transpose(crow, col, val, spec.G, nnz)
-            dWt = torch.empty(spec.G, H, device=dev)
-            ops.csr_linear_bwd_w(cptr, ridx, cval, B, spec.G, dY, dWt)
+            dWt = C.csr_linear_bwd_w(crow, col, val, spec.G, dY)
             db = torch.empty(H, device=dev)
-            ops.colsum(dY, db)
+            C.colsum(dY, db)
             return None, dWt.t(), db, dgamma, dbeta, None, None, None
         dX, dW, db = dense_linear_bwd(dY, x, W, need_dx=ctx.needs_input_grad[0], W16=spec.W16)
         return dX, dW, db, dgamma, dbeta, None, None, None
@@ -290,9 +291,7 @@ class _LatentFn(torch.autograd.Function):
     def forward(ctx, ML, eps, var_eps):
         B, Z2 = ML.shape
         Z = Z2 // 2
-        z = torch.empty(B, Z, device=ML.device)
-        sums = torch.empty(3, dtype=torch.float64, device=ML.device)
-        ops.reparam_kl_fwd(ML, eps, Z, var_eps, z, None, sums)
+        z, _ = C.reparam_kl_fwd(ML, eps, float(var_eps))
         mu = ML[:, :Z]
         var = torch.exp(ML[:, Z:]) + var_eps
         ctx.save_for_backward(ML, eps)
@@ -304,8 +303,7 @@ class _LatentFn(torch.autograd.Function):
         ML, eps = ctx.saved_tensors
         B, Z2 = ML.shape
         Z = Z2 // 2
-        dML = torch.empty_like(ML)
-        ops.reparam_kl_bwd(ML, eps, dz.contiguous() if dz is not None else None, Z, ctx.var_eps, 0.0, dML, None)
+        dML = C.reparam_kl_bwd(ML, eps, dz.contiguous() if dz is not None else None, float(ctx.var_eps), 0.0)
         if dmu is not None:
             dML[:, :Z] += dmu
         if dvar is not None:

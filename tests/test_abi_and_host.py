@@ -290,3 +290,13 @@ def test_clip_config_objects_behave_like_the_reference_records():
     assert a.adversarial_gradient_clip is c and a.vae_gradient_clip is None and a.expert_gradient_clip is None
     a = AutogradConfig(expert_gradient_clip=c)
     assert a.expert_gradient_clip is c and a.adversarial_gradient_clip is None
+
+
+def test_custom_op_layer_is_registered():
+    """the C-ABI entry points are reachable as torch.ops.cmmvae.* (CUDA kernels only: a CPU tensor is
+    refused by the dispatcher, there is nothing to fall back to)"""
+    import mmvae_b200.torch_ops as T
+    for name in T.OPS:
+        assert hasattr(torch.ops.cmmvae, name), name
+    with pytest.raises(NotImplementedError, match="CPU"):
+        torch.ops.cmmvae.cast_bf16(torch.randn(4), torch.empty(4, dtype=torch.bfloat16))

@@ -464,3 +464,24 @@ def test_csr_linear_bwd_w_tc_shard_equals_sum_of_full_gradients(ops):
         assert torch.isfinite(out).all()
         assert (out - ref).abs().max().item() <= 1e-5 * ref.abs().max().item() + 1e-6
         assert torch.equal(out[max(0, G - r * per):], torch.zeros_like(out[max(0, G - r * per):]))   # padding rows
+
+
+def test_torch_custom_ops_reach_the_kernels(ops):
+    """torch.ops.cmmvae.* (mmvae_b200/torch_ops.py) call the same C entry points as the ctypes wrappers"""
+    import mmvae_b200.torch_ops  # noqa: F401
+    crow, col, val = O.synth_csr(64, 500, 0.1, seed=9)
+    g = torch.Generator().manual_seed(1)
+    Wt = (torch.randn(500, 96, generator=g) * 0.05).cuda()
+    b = torch.randn(96, generator=g).cuda()
+    y = torch.ops.cmmvae.csr_linear_fwd(dev(crow), dev(col), dev(val), 500, Wt, b)
+    assert torch.equal(y, ops.csr_linear_fwd(dev(crow), dev(col), dev(val), 500, Wt, b))
+    dY = torch.randn(64, 96, generator=g).cuda()
+    dWt = torch.ops.cmmvae.csr_linear_bwd_w(dev(crow), dev(col), dev(val), 500, dY)
+    assert rel(dWt, O.csr_to_dense(crow, col, val, 500).t() @ dY.cpu()) < 1e-5
+    A, Bm = torch.randn(130, 64, generator=g).cuda(), torch.randn(72, 64, generator=g).cuda()
+    Cc = torch.empty(130, 72).cuda()
+    torch.ops.cmmvae.gemm(A, False, Bm, False, 130, 72, 64, None, False, Cc, None, True)
+    assert rel(Cc, A.double() @ Bm.double().t()) < 1e-3
+    ML, eps = torch.randn(32, 16, generator=g).cuda(), torch.randn(32, 8, generator=g).cuda()
+    z, sums = torch.ops.cmmvae.reparam_kl_fwd(ML, eps, 1e-4)
+    assert rel(z, ML[:, :8] + eps * torch.sqrt(torch.exp(ML[:, 8:]) + 1e-4)) < 1e-6 and sums.shape == (3,)
