@@ -1135,11 +1135,10 @@ class StepEngine:
             cur = torch.cuda.current_stream()
             self._hp.wait_stream(cur)
             with torch.cuda.stream(self._hp), ops.stream_scope(self._hp):
-                graphable = (self.use_graph and self.comm is None and eps is None
-                             and masks is None and self.timers is None and self.precision == "bf16"
-                             and not L._noise_queue and not L._mask_queue)
+                graphable = (self.use_graph and self.comm is None and masks is None and self.timers is None
+                             and self.precision == "bf16" and not L._mask_queue)
                 if graphable:
-                    rec = self._graph_step(expert_id, crow, col, val, nnz, kl_weight, labels, nnz_cap)
+                    rec = self._graph_step(expert_id, crow, col, val, nnz, kl_weight, eps, labels, nnz_cap)
                 else:
                     rec = self._train_step(expert_id, crow, col, val, nnz, kl_weight, eps, labels, masks)
             cur.wait_stream(self._hp)
@@ -1179,8 +1178,19 @@ class StepEngine:
         d["copied"][k] = torch.cuda.Event()
         d["copied"][k].record()
 
-    def _graph_step(self, expert_id, crow, col, val, nnz, kl_weight, labels, nnz_cap):
+    def _graph_step(self, expert_id, crow, col, val, nnz, kl_weight, eps, labels, nnz_cap):
         d = self._ensure_dyn()
+        # reparameterisation noise at a fixed address, drawn (or injected) OUTSIDE the graph: torch's generator then
+        # advances exactly as in a stream-launched step
+        Bn, Z = crow.numel() - 1, self.Z
+        eps_static = d["inputs"].get(("eps", Bn, Z))
+        if eps_static is None:
+            eps_static = d["inputs"][("eps", Bn, Z)] = torch.empty(Bn, Z, device=self.device)
+        if eps is not None or L._noise_queue:
+            eps_static.copy_(eps if eps is not None else L.draw_noise(Bn, Z, self.device), non_blocking=True)
+        else:
+            eps_static.normal_()
+        eps = eps_static
         n_adv = min(len(self.adv), self.n_hidden)
         if n_adv and labels is not None:      # labels at fixed addresses (the captured launches read them there)
             for c, t in labels.items():
@@ -1214,7 +1224,7 @@ class StepEngine:
             # first visit: eager, with the device-side scalars (allocates every workspace the capture will need)
             self._gmode = dict(cap=nnz_cap, graphs=None)
             try:
-                rec = self._train_step(expert_id, crow, col, val, nnz, kl_weight, None, labels, None)
+                rec = self._train_step(expert_id, crow, col, val, nnz, kl_weight, eps, labels, None)
             finally:
                 self._gmode = None
             self._graphs[key] = dict()
@@ -1227,7 +1237,7 @@ class StepEngine:
             ops.set_pdl(False)    # plain graph nodes replay faster than nodes with programmatic edges (measured)
             try:
                 gA.capture_begin(capture_error_mode="thread_local")   # (packing threads keep issuing copies)
-                rec = self._train_step(expert_id, crow, col, val, nnz, kl_weight, None, labels, None)
+                rec = self._train_step(expert_id, crow, col, val, nnz, kl_weight, eps, labels, None)
                 gB.capture_end()
                 events = self._gmode["events"]
             finally:

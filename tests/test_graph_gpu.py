@@ -51,18 +51,21 @@ def test_graph_replay_trains_like_stream_launches(with_adv, tmp_path):
     metas = [pd.DataFrame({"assay": [f"assay_{i}" for i in rng.integers(0, 5, B)],
                            "dataset_id": [f"dataset_id_{i}" for i in rng.integers(0, 11, B)]}) for _ in batches]
     runs = []
-    for use_graph in (False, True):
+    for use_graph in (False, False, True):       # two stream-launched runs measure the run-to-run noise floor
         model = _model(G, with_adv, str(tmp_path / str(use_graph)))
         model.cuda().train()
         model.configure_optimizers()
         model.sync_logging = False
         model.use_cuda_graphs = use_graph
-        torch.manual_seed(1234)          # reparameterisation noise: same generator stream on both sides
+        for g in model.engine().groups.values():
+            g.lr = 2e-4        # the reference's hard-coded 5e-3 makes 12 free-running steps chaotic (run-to-run noise of
+                               # several per cent, occasionally far more); the comparison needs trajectories that stay close
         stager = CSRStager(max_cells=B, max_nnz=int(0.09 * B * G), device="cuda", depth=2, narrow_col=True)
         logs = []
         for t in range(steps):
             crow, col, val = batches[t % len(batches)]
             tk = stager.put(crow, col, val, G)
+            L.inject_noise(torch.randn(B, 32, generator=torch.Generator().manual_seed(900 + t)).cuda())
             model.logged_metrics.clear()
             model.training_step((stager.get(tk), metas[t % len(batches)].copy(), "human"), t)
             stager.release(tk)
@@ -73,17 +76,27 @@ def test_graph_replay_trains_like_stream_launches(with_adv, tmp_path):
         n_graphs = sum(1 for e in eng._graphs.values() if "gA" in e)
         assert n_graphs == (1 if use_graph else 0)          # one graph pair serves every batch of the expert
         runs.append((logs, {k: v.detach().cpu() for k, v in model.state_dict().items()}))
-    (la, sa), (lb, sb) = runs
-    for t, (a, b) in enumerate(zip(la, lb)):
-        assert a.keys() == b.keys()
-        for k in a:
-            # dropout is off here, so the two runs differ only by atomics' summation order
-            tol = 2e-2 if k.startswith("grad_norms") else 5e-3     # (gradients react to last-bit differences upstream)
-            atol = 2e-3 if k.startswith("Mean") else 1e-6          # mean of mu: a difference of O(1) terms near zero
-            assert b[k] == pytest.approx(a[k], rel=tol, abs=atol), (t, k, a[k], b[k])
+    def deviation(x, y):
+        worst = {}
+        for t, (a, b) in enumerate(zip(x, y)):
+            assert a.keys() == b.keys()
+            for k in a:
+                kind = "grad" if k.startswith("grad_norms") else ("mean" if k.startswith("Mean") else "other")
+                dev = abs(a[k] - b[k]) / max(abs(a[k]), 1e-2 if kind == "mean" else 1e-12)
+                if dev > worst.get(kind, (0.0,))[0]:
+                    worst[kind] = (dev, t, k, a[k], b[k])
+        return worst
+
+    (la, sa), (lb, sb), (lg, sg) = runs
+    # free-running trajectories (lr 5e-3, no re-synchronisation): two stream-launched runs already differ -- atomics'
+    # summation order, amplified step by step -- so the replayed run is held to that noise floor, not to zero
+    floor, got = deviation(la, lb), deviation(la, lg)
+    for kind, dev in got.items():
+        assert dev[0] <= max(4 * floor.get(kind, (0.0,))[0], 1e-2), (kind, dev, floor)
     for k, v in sa.items():
         if v.dtype.is_floating_point and not k.endswith("lin.bias"):
-            err = float((sb[k].double() - v.double()).norm() / v.double().norm().clamp_min(1e-30))
-            assert err < 5e-2, (k, err)
+            ref = float((sb[k].double() - v.double()).norm() / v.double().norm().clamp_min(1e-30))
+            err = float((sg[k].double() - v.double()).norm() / v.double().norm().clamp_min(1e-30))
+            assert err <= max(4 * ref, 1e-3), (k, err, ref)
         elif not v.dtype.is_floating_point:
-            assert torch.equal(sb[k], v), k
+            assert torch.equal(sg[k], v), k
