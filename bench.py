@@ -101,8 +101,13 @@ def build_model(config: int, only=None):
         advs = [Adversarial(FCBlockConfig([HV, 128, 64], activation_fn=relu), FCBlockConfig([64]), list(conds), tmp),
                 Adversarial(FCBlockConfig([Z, 64], activation_fn=relu), FCBlockConfig([64]), list(conds), tmp)]
     clip = lambda: GradientClipConfig(val=10, algorithm="norm")  # noqa: E731
+    extra = {}
+    if config == 4:      # BASELINE configs[3]: "+ output discriminator" (one per species, trained inside the step)
+        from mmvae_b200.modules import create_discriminators
+        extra["output_discriminators"] = create_discriminators(species)
     model = CMMVAEModel(CMMVAE(vae, experts, advs), adv_weight=1.0,
-                        autograd_config=AutogradConfig(clip(), clip(), clip()), kl_annealing_fn=KLAnnealingFn(1.0))
+                        autograd_config=AutogradConfig(clip(), clip(), clip()), kl_annealing_fn=KLAnnealingFn(1.0),
+                        **extra)
     return model, species, conds
 
 
@@ -339,7 +344,8 @@ def main():
     workload = (f"config{args.config}: " + {2: "single-species core VAE (human expert only)",
                                             3: "two-species CMMVAE + 2 GRL adversaries",
                                             4: f"two-species CMMVAE, latent {Z} ({H1}-{H2}|{H2}-{HV}-Z{Z}), "
-                                               "no output discriminator"}[args.config] +
+                                               "+ per-species output discriminator G-128-64-1 on the "
+                                               "reconstruction"}[args.config] +
                 f", {B} cells/GPU/step, G={G_HUMAN}" + (f"/{G_MOUSE}" if args.config != 2 else "") +
                 f", CSR {DENSITY:.0%} nnz, {args.precision}")
     config = {"workload": workload, "batch_per_gpu": B, "global_batch": B * world, "genes": G_HUMAN,

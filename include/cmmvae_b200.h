@@ -199,6 +199,21 @@ int cmmvae_transpose(const void* src, void* dst, int dtype, int R, int C, int ld
 int cmmvae_axpy(float* a, const float* b, float alpha, long long n, void* stream);
 
 
+/* ---- output discriminator on the reconstruction (BASELINE config 4; MLP of runners/meta_discriminators.py:33-49:
+ * Linear(G,128) Sigmoid Linear(128,64) Sigmoid Linear(64,1) Sigmoid, binary_cross_entropy(mean), 112-148) ------
+ * xhat is never in HBM; it follows from the decoder's dlogits (bf16) and the CSR batch:
+ *   xhat = dlogits/2 + x where dlogits != 0, else 0   =>   xhat W^T = 1/2 dlogits W^T + Xm W^T,
+ * Xm = the batch restricted to entries with non-zero dlogits.  val_masked[i] = dlogits[row(i), col[i]] != 0 ?
+ * val[i] : 0; the two products then run on the GEMM / SpMM entry points above. */
+int cmmvae_mask_vals_by_dl(const int32_t* crow, const int32_t* col, const float* val, int B,
+                           const void* dlogits_bf16, int ldd, float* val_masked, void* stream);
+int cmmvae_sigmoid_fwd(const float* x, long long n, float* out_f32, void* out_bf16, void* stream);
+/* dx = dout * out * (1 - out) */
+int cmmvae_sigmoid_bwd(const float* dout, const float* out, long long n, float* dx, void* dx_bf16, void* stream);
+/* p = sigmoid(a[B]); loss (double[1], zeroed by the call) = mean BCE(p, label) with torch's log clamp at -100;
+ * da = (p - label) / B (gradient of the mean BCE through the sigmoid); p_out optional */
+int cmmvae_bce_sigmoid(const float* a, int B, float label, float* p_out, float* da, double* loss, void* stream);
+
 /* ---- launches that can be REPLAYED from a captured CUDA graph ---------------------------------------------------
  * The per-step scalars a replayed launch cannot carry by value live in device memory instead: the batch's nnz is
  * read from crow[B]; the dropout seed is *seed_base + seed; the KL weight is *kl_weight (kl_scale then = 1/B); Adam's

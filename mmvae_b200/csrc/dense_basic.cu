@@ -590,6 +590,74 @@ __global__ void axpy_kernel(float* __restrict__ a, const float* __restrict__ b, 
     a[i] = fmaf(alpha, b[i], a[i]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// output discriminator (BASELINE config 4; reference MLP: runners/meta_discriminators.py:33-49,112-148)
+// ---------------------------------------------------------------------------------------------
+// The discriminator reads the reconstruction xhat = relu(logits), which the fused decoder never writes.  What it
+// does write is dlogits = 2 (xhat - x) 1[logits > 0] (bf16), and that determines xhat:
+//     xhat = dlogits / 2 + x   where dlogits != 0,     xhat = 0   where dlogits == 0
+// (dlogits == 0 with xhat > 0 would need xhat == x exactly).  So  xhat W^T = 1/2 dlogits W^T + Xm W^T  with
+// Xm = the CSR batch restricted to entries whose dlogits is non-zero: a dense GEMM over the tensor that is
+// already in HBM plus a sparse product -- xhat itself is never materialised.  This kernel builds Xm's values.
+__global__ void __launch_bounds__(256) mask_vals_by_dl_kernel(const int32_t* __restrict__ crow,
+                                                              const int32_t* __restrict__ col,
+                                                              const float* __restrict__ val, int B,
+                                                              const __nv_bfloat16* __restrict__ dl, int ldd,
+                                                              float* __restrict__ val_m) {
+  pdl_sync();
+  const int lane = threadIdx.x & 31;
+  for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += (gridDim.x * blockDim.x) >> 5) {
+    const int s = crow[b], e = crow[b + 1];
+    const __nv_bfloat16* row = dl + (size_t)b * ldd;
+    for (int i = s + lane; i < e; i += 32) {
+      const uint16_t bits = *reinterpret_cast<const uint16_t*>(row + __ldg(col + i));
+      val_m[i] = (bits & 0x7FFF) ? __ldg(val + i) : 0.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) sigmoid_fwd_kernel(const float* __restrict__ x, long long n,
+                                                          float* __restrict__ o32, __nv_bfloat16* __restrict__ o16) {
+  pdl_sync();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = 1.f / (1.f + expf(-x[i]));
+    if (o32) o32[i] = v;
+    if (o16) o16[i] = __float2bfloat16(v);
+  }
+}
+
+// dx = dout * out * (1 - out)
+__global__ void __launch_bounds__(256) sigmoid_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                                          long long n, float* __restrict__ dx,
+                                                          __nv_bfloat16* __restrict__ dx16) {
+  pdl_sync();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float o = out[i];
+    const float d = dout[i] * o * (1.f - o);
+    if (dx) dx[i] = d;
+    if (dx16) dx16[i] = __float2bfloat16(d);
+  }
+}
+
+// p = sigmoid(a); loss += mean_b BCE(p, y) with torch's log clamp at -100; da = dBCE/da = (p - y) / B
+// (binary_cross_entropy(reduction='mean') after nn.Sigmoid, meta_discriminators.py:47-49,131-134)
+__global__ void __launch_bounds__(256) bce_sigmoid_kernel(const float* __restrict__ a, int B, float y,
+                                                          float* __restrict__ p_out, float* __restrict__ da,
+                                                          double* __restrict__ loss) {
+  pdl_sync();
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
+    const float p = 1.f / (1.f + expf(-a[i]));
+    const float lp = fmaxf(logf(p), -100.f), lq = fmaxf(logf(1.f - p), -100.f);
+    acc -= (double)(y * lp + (1.f - y) * lq);
+    if (p_out) p_out[i] = p;
+    if (da) da[i] = (p - y) / (float)B;
+  }
+  const double t = block_sum<double>(acc, red);
+  if (threadIdx.x == 0) atomicAdd(loss, t / (double)B);
+}
+
 static inline int ew_blocks(long long n) {
   long long b = (n + 255) / 256;
   return (int)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
@@ -839,4 +907,37 @@ extern "C" int cmmvae_axpy(float* a, const float* b, float alpha, long long n, v
   if (n <= 0) return 0;
   launch_pdl(axpy_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, a, b, alpha, n);
   return check_launch("axpy");
+}
+
+extern "C" int cmmvae_mask_vals_by_dl(const int32_t* crow, const int32_t* col, const float* val, int B,
+                                      const void* dlogits_bf16, int ldd, float* val_masked, void* stream) {
+  CMMVAE_REQUIRE(crow && col && val && dlogits_bf16 && val_masked && B > 0, "mask_vals_by_dl: bad arguments");
+  long long want = ((long long)B * 32 + 255) / 256;
+  const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
+  launch_pdl(mask_vals_by_dl_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, crow, col, val, B,
+             (const __nv_bfloat16*)dlogits_bf16, ldd, val_masked);
+  return check_launch("mask_vals_by_dl");
+}
+
+extern "C" int cmmvae_sigmoid_fwd(const float* x, long long n, float* out_f32, void* out_bf16, void* stream) {
+  if (n <= 0) return 0;
+  launch_pdl(sigmoid_fwd_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, x, n, out_f32,
+             (__nv_bfloat16*)out_bf16);
+  return check_launch("sigmoid_fwd");
+}
+
+extern "C" int cmmvae_sigmoid_bwd(const float* dout, const float* out, long long n, float* dx, void* dx_bf16,
+                                  void* stream) {
+  if (n <= 0) return 0;
+  launch_pdl(sigmoid_bwd_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, dout, out, n, dx,
+             (__nv_bfloat16*)dx_bf16);
+  return check_launch("sigmoid_bwd");
+}
+
+extern "C" int cmmvae_bce_sigmoid(const float* a, int B, float label, float* p_out, float* da, double* loss,
+                                  void* stream) {
+  CMMVAE_REQUIRE(a && B > 0 && loss, "bce_sigmoid: bad arguments");
+  cudaMemsetAsync(loss, 0, sizeof(double), (cudaStream_t)stream);
+  launch_pdl(bce_sigmoid_kernel, dim3(ew_blocks(B)), dim3(256), 0, (cudaStream_t)stream, a, B, label, p_out, da, loss);
+  return check_launch("bce_sigmoid");
 }

@@ -473,8 +473,10 @@ static int gemm_bf16_tc(const void* A, int lda, int transA, const void* Bm, int 
   // long-K, few-tile products (dh = dlogits Wout: K = genes) are split along K to fill the 148 SMs
   int splits = 1;
   const int sms = sm_budget();
-  if (!relu && !C_bf16 && !accumulate && C_f32 && total_kb >= 64 && tiles256 * 2 <= sms && N > 128 && !route) {
-    splits = (int)(sms / tiles256);
+  // (narrow outputs, N <= 128 -- the output discriminator's first layer -- walk 128-wide tiles and split as well)
+  const long long tiles_sel = N > 128 ? tiles256 : (long long)((M + 127) / 128);
+  if (!relu && !C_bf16 && !accumulate && C_f32 && total_kb >= 64 && tiles_sel * 2 <= sms && !route) {
+    splits = (int)(sms / tiles_sel);
     if (splits > total_kb / 16) splits = total_kb / 16;
     if (splits < 1) splits = 1;
   }

@@ -469,7 +469,8 @@ class AdvPlan:
 
 class StepEngine:
     def __init__(self, module, adv_weight: float = 1.0, clip: Optional[Dict[str, Optional[float]]] = None,
-                 precision: Optional[str] = None, device=None):
+                 precision: Optional[str] = None, device=None, output_discriminators=None,
+                 output_discriminator_lr: float = 1e-3):
         self.module = module
         self.device = torch.device(device or "cuda")
         if self.device.type != "cuda":
@@ -585,6 +586,24 @@ class StepEngine:
             o = g.offset[id(heads[0].fc_layers[0].lin.bias)]
             ap.bh, ap.gbh = g.p[o:o + sumC], g.g[o:o + sumC]
             self.adv.append(ap)
+        # ---- output discriminators on the reconstruction (BASELINE config 4) ----
+        self.odisc: Dict[str, dict] = {}
+        for sid, disc in (output_discriminators or {}).items():
+            if self.comm is not None:
+                raise UnsupportedTopology("output discriminators are not part of the data-parallel route yet")
+            l1, l2, l3 = disc.linears
+            disc.to(dev)
+            # first-layer weight stored [genes, hidden] (like the expert encoder's): the operand layout of both the
+            # dense and the sparse half of xhat W^T; torch.optim.Adam defaults (no weight decay) at lr 1e-3
+            g = self.groups[f"output_discriminators/{sid}"] = FlatGroup(
+                f"output_discriminators/{sid}", [[(l1.bias, False)], [(l2.bias, False)], [(l3.bias, False)],
+                                                 [(l2.weight, False)], [(l3.weight, False)]], dev,
+                lr=output_discriminator_lr, weight_decay=0.0, sharded=[(l1.weight, True)], background_last=False)
+            ph = lambda p, buf=None, g=g: g.phys(p, buf)   # noqa: E731
+            self.odisc[sid] = dict(group=g, G=l1.in_features, H1=l1.out_features, H2=l2.out_features,
+                                   W1t16=ph(l1.weight, g.p16), gW1t=ph(l1.weight, g.g), b1=ph(l1.bias), gb1=ph(l1.bias, g.g),
+                                   W2=ph(l2.weight), gW2=ph(l2.weight, g.g), b2=ph(l2.bias), gb2=ph(l2.bias, g.g),
+                                   W3=ph(l3.weight), gW3=ph(l3.weight, g.g), b3=ph(l3.bias), gb3=ph(l3.bias, g.g))
         self._ws: Dict[tuple, torch.Tensor] = {}
         # small weight-gradient GEMMs are off the critical path (only the optimizer needs them): they run on a
         # side stream, concurrently with the dX chain of the main stream
@@ -851,6 +870,58 @@ class StepEngine:
             self.precision = saved_precision
         self._join_side()
         return d
+
+    # --------------------------------------------------------------------------- output discriminator
+    def _output_disc_step(self, od, expert_id, crow, col, val, nnz, tp, dl, B, G, loss_slot, norm_slot):
+        """One optimisation step of the species' output discriminator on this step's (detached) reconstruction:
+        Linear(G,128) Sigmoid Linear(128,64) Sigmoid Linear(64,1) Sigmoid, BCE(mean) against the species label,
+        Adam(lr 1e-3) (meta_discriminators.py:33-49,112-148).  xhat is not in HBM: xhat W1^T = 1/2 dlogits W1^T +
+        Xm W1^T (Xm: entries of the batch with non-zero dlogits), and likewise dW1 = xhat^T da1."""
+        from mmvae_b200.modules.output_discriminator import SPECIES_LABEL
+        g, H1, H2 = od["group"], od["H1"], od["H2"]
+        y = SPECIES_LABEL.get(expert_id, 0.0)
+        cap = self._gmode["cap"] if self._gmode is not None else nnz
+        val_m = ops.mask_vals_by_dl(crow, col, val, dl, self.ws_cap("od.valm", max(cap, 1)))
+        tp_buf = self.ws("od.tp64", (B * ((G + 63) // 64 + 1),), torch.int32)
+        pk_buf = self.ws_cap("od.packed", (cap + 3) // 4 * 4 + 4, torch.int32)
+        if self._gmode is not None:
+            tpm = ops.csr_tile_ptr_dyn(crow, col, val_m, G, cap, tp_buf, pk_buf)
+        else:
+            tpm = ops.csr_tile_ptr(crow, col, val_m, G, nnz, tp_buf, pk_buf)
+        # ---- forward
+        a1pre = ops.csr_linear_fwd_tc(tpm[1], tpm[0], B, G, od["W1t16"], od["b1"], out=self.ws("od.a1pre", (B, H1)))
+        half = self.ws("od.half", (B, H1))
+        ops.gemm(dl, 0, od["W1t16"], 1, B, H1, G, C32=half)             # dlogits W1^T   (K = genes)
+        ops.axpy(a1pre, half, 0.5)
+        a1 = self.ws("od.a1", (B, H1))
+        ops.sigmoid_fwd(a1pre, a1)
+        a2pre, a2 = self.ws("od.a2pre", (B, H2)), self.ws("od.a2", (B, H2))
+        ops.gemm(a1, 0, od["W2"], 0, B, H2, H1, bias=od["b2"], C32=a2pre, tf32=True)
+        ops.sigmoid_fwd(a2pre, a2)
+        a3 = self.ws("od.a3", (B, 1))
+        ops.gemm(a2, 0, od["W3"], 0, B, 1, H2, bias=od["b3"], C32=a3, use_tc=False)
+        da3 = self.ws("od.da3", (B, 1))
+        ops.bce_sigmoid(a3, y, None, da3, loss_slot)
+        # ---- backward
+        ops.colsum(da3, od["gb3"])
+        ops.gemm(da3, 1, a2, 1, 1, H2, B, C32=od["gW3"], use_tc=False)
+        da2 = self.ws("od.da2", (B, H2))
+        ops.gemm(da3, 0, od["W3"], 1, B, H2, 1, C32=da2, use_tc=False)
+        da2pre = self.ws("od.da2pre", (B, H2))
+        ops.sigmoid_bwd(da2, a2, da2pre)
+        ops.colsum(da2pre, od["gb2"])
+        ops.gemm(da2pre, 1, a1, 1, H2, H1, B, C32=od["gW2"], tf32=True)
+        da1 = self.ws("od.da1", (B, H1))
+        ops.gemm(da2pre, 0, od["W2"], 1, B, H1, H2, C32=da1, tf32=True)
+        da1pre, da1pre16 = self.ws("od.da1pre", (B, H1)), self.ws("od.da1pre16", (B, H1), torch.bfloat16)
+        ops.sigmoid_bwd(da1, a1, da1pre, da1pre16)
+        ops.colsum(da1pre, od["gb1"])
+        ops.csr_linear_bwd_w_tc(tpm[1], tpm[0], B, G, da1pre16, od["gW1t"])          # Xm^T da1
+        halfw = self.ws("od.halfw", (G, H1))
+        ops.gemm(dl, 1, da1pre16, 1, G, H1, B, C32=halfw)                            # dlogits^T da1
+        ops.axpy(od["gW1t"], halfw, 0.5)
+        g.grad_norm_sq(norm_slot)
+        g.clip_adam(norm_slot, None, 1.0, advance=self._gmode is None)
 
     # ------------------------------------------------------ data parallel over peer memory (gene shards)
     # Cells shard across ranks; the two gene-sized layers shard by GENES (SURVEY.md 7.8).  Rank r owns rows
@@ -1200,6 +1271,8 @@ class StepEngine:
                 st.copy_(t, non_blocking=True)
             labels = {c: d["labels"][(c, t.numel())] for c, t in labels.items()}
         stepped = [self.groups["vae"], self.groups[f"experts/{expert_id}"]] + [a.group for a in self.adv[:n_adv]]
+        if expert_id in self.odisc:
+            stepped.append(self.odisc[expert_id]["group"])
         for g in stepped:
             g.advance()
         self._write_dyn(kl_weight)
@@ -1277,7 +1350,8 @@ class StepEngine:
         n_adv = min(len(self.adv), self.n_hidden)   # zip(hidden, adversarials) truncates (cmmvae_model.py:67-70)
         # scalar slots (double): 0 recon | 1..3 kl,sum mu,sum var | then norms | then CE sums | 2 data-parallel info
         n_ce = sum(len(a.conditions) for a in self.adv[:n_adv])
-        sc = torch.zeros(4 + 2 + 2 * n_adv + 2 * n_ce + 2, dtype=torch.float64, device=dev)
+        sc = torch.zeros(4 + 2 + 2 * n_adv + 2 * n_ce + 2 + 2, dtype=torch.float64, device=dev)
+        od_slot = 4 + 2 + 2 * n_adv + 2 * n_ce      # [loss, grad norm^2] of the output discriminator; then 2 DP info
         s_norm = lambda k: sc[4 + k:5 + k]  # noqa: E731   0 vae, 1 expert, 2.. disc_i, then gen_i
         ce_base = 4 + 2 + 2 * n_adv
 
@@ -1377,6 +1451,13 @@ class StepEngine:
             ops.gemm(h32, 0, out.W32, 0, B, G, out.K, bias=out.b, C32=logits, use_tc=False)
             dl = self.ws("dlogits32", (B, G))
             ops.mse_relu_csr(logits, G, crow, col, val, False, dl, None, sc[0:1])
+
+        od = self.odisc.get(expert_id)
+        if od is not None:
+            if not (fused and use_tc_spmm):
+                raise RuntimeError("the output discriminator runs on the fused bf16 decoder route only")
+            self._output_disc_step(od, expert_id, crow, col, val, nnz, tp, dl, B, G, sc[od_slot:od_slot + 1],
+                                   sc[od_slot + 1:od_slot + 2])
 
         # ---------------- adversaries: discriminator update, then generator pass ----------------
         d_hidden = {}
@@ -1501,7 +1582,8 @@ class StepEngine:
         self._t1(ev)
 
         self.last = dict(sc=sc, B=B, Z=Z, kl_weight=float(kl_weight), expert_id=expert_id, n_adv=n_adv,
-                         gscale=gscale, ce_base=ce_base, z=z32, dl=dl, dp=dpm is not None)
+                         gscale=gscale, ce_base=ce_base, z=z32, dl=dl, dp=dpm is not None,
+                         od_slot=od_slot if od is not None else None)
         if launch_bg is not None:
             self.last["launch_bg"] = launch_bg
         return self.last
@@ -1550,6 +1632,9 @@ class StepEngine:
                 if tag == "generator":
                     total += self.adv_weight * summed
         out["loss"] = total
+        if rec.get("od_slot") is not None:     # reference writer tags: meta_disc/md_<species> (meta_discriminators.py:165-167)
+            out[f"meta_disc/md_{rec['expert_id']}"] = sc[rec["od_slot"]]
+            out[f"grad_norms/output_discriminator_{rec['expert_id']}"] = math.sqrt(sc[rec["od_slot"] + 1])
         return out
 
     # ------------------------------------------------------------------------------- eval forward

@@ -41,9 +41,15 @@ def convert_to_flat_list_and_map(d: dict, flat_list: Optional[list] = None) -> d
 
 class CMMVAEModel(BaseModel):
     def __init__(self, module: CMMVAE, adv_weight: Optional[float] = None,
-                 autograd_config: Optional[AutogradConfig] = None, *args, **kwargs):
+                 autograd_config: Optional[AutogradConfig] = None, *args, output_discriminators=None,
+                 output_discriminator_lr: float = 1e-3, **kwargs):
         super().__init__(*args, **kwargs)
         self.module = module
+        # extension (BASELINE config 4): per-species discriminators on the reconstruction, trained inside
+        # the step on the detached x-hat (mmvae_b200.modules.OutputDiscriminator); the reference only has the post-hoc
+        # runner (runners/meta_discriminators.py)
+        self.output_discriminators = torch.nn.ModuleDict(dict(output_discriminators or {}))
+        self.output_discriminator_lr = float(output_discriminator_lr)
         self.automatic_optimization = False
         self.adversarial_criterion = torch.nn.CrossEntropyLoss(reduction="sum")
         self.init_weights()
@@ -80,7 +86,9 @@ class CMMVAEModel(BaseModel):
             clip = {"vae": self._clip_val(ac.vae_gradient_clip), "expert": self._clip_val(ac.expert_gradient_clip),
                     "adversarial": self._clip_val(ac.adversarial_gradient_clip)}
             try:
-                self._engine = StepEngine(self.module, adv_weight=self.adv_weight, clip=clip)
+                self._engine = StepEngine(self.module, adv_weight=self.adv_weight, clip=clip,
+                                          output_discriminators=dict(self.output_discriminators.items()),
+                                          output_discriminator_lr=self.output_discriminator_lr)
             except UnsupportedTopology as why:
                 self._engine = False
                 self._module_route_reason = str(why)
@@ -99,6 +107,9 @@ class CMMVAEModel(BaseModel):
         if len(self.module.adversarials):
             optim_dict["adversarials"] = {i: FlatAdam(eng.groups[f"adversarials/{i}"])
                                           for i in range(1, len(self.module.adversarials) + 1)}
+        if len(self.output_discriminators):      # after the reference's entries: existing indices stay what they are
+            optim_dict["output_discriminators"] = {s: FlatAdam(eng.groups[f"output_discriminators/{s}"])
+                                                   for s in self.output_discriminators.keys()}
         optimizers = []
         self.optimizer_map = convert_to_flat_list_and_map(optim_dict, optimizers)
         if hasattr(self, "_opt_cache"):      # stand-in LightningModule: what ``self.optimizers()`` hands out
@@ -153,6 +164,8 @@ class CMMVAEModel(BaseModel):
         opts = self.get_optimizers()
         stepped = [o for _, o in zip(range(n_adv), (opts.get("adversarials") or {}).values())]
         stepped += [opts["vae"], opts["experts"][expert_id]]
+        if expert_id in self.output_discriminators:
+            stepped.append(opts["output_discriminators"][expert_id])
         for o in stepped:
             o.step()
         if hasattr(self.trainer, "set_stage"):     # the stand-in trainer counts optimizer steps like Lightning
@@ -309,7 +322,7 @@ class CMMVAEModel(BaseModel):
         stage = self.stage_name
         main = {k: s[k] for k in (RK.LOSS, RK.RECON_LOSS, RK.KL_LOSS, RK.KL_WEIGHT, "Mean", "Variance")}
         for key, v in s.items():
-            if key.startswith("grad_norms/"):
+            if key.startswith("grad_norms/") or key.startswith("meta_disc/"):
                 self.log(key, v)
             elif "/adversarial_loss/" in key:
                 tag, _, cond = key.split("/")

@@ -456,3 +456,26 @@ def csr_tile_ptr_rows(row_begin, row_end, col, val, B: int, G: int, n_records: i
 def dp_scalars(slabs, n_src: int, stride: int, rank: int, out_recon, out_norm):
     _check(lib().cmmvae_dp_scalars(_ptr(slabs), n_src, stride, rank, _ptr(out_recon), _ptr(out_norm), _stream()),
            "dp_scalars")
+
+
+# ------------------------------------------------------------------------------ output discriminator
+def mask_vals_by_dl(crow, col, val, dl16, val_m):
+    B = crow.numel() - 1
+    _check(lib().cmmvae_mask_vals_by_dl(_ptr(crow), _ptr(col), _ptr(val), B, _ptr(dl16), dl16.stride(0), _ptr(val_m),
+                                        _stream()), "mask_vals_by_dl")
+    return val_m
+
+
+def sigmoid_fwd(x, out32=None, out16=None):
+    _check(lib().cmmvae_sigmoid_fwd(_ptr(x), _c.c_longlong(x.numel()), _ptr(out32), _ptr(out16), _stream()),
+           "sigmoid_fwd")
+
+
+def sigmoid_bwd(dout, out, dx=None, dx16=None):
+    _check(lib().cmmvae_sigmoid_bwd(_ptr(dout), _ptr(out), _c.c_longlong(out.numel()), _ptr(dx), _ptr(dx16), _stream()),
+           "sigmoid_bwd")
+
+
+def bce_sigmoid(a, label: float, p_out, da, loss):
+    _check(lib().cmmvae_bce_sigmoid(_ptr(a), a.numel(), _c.c_float(label), _ptr(p_out), _ptr(da), _ptr(loss),
+                                    _stream()), "bce_sigmoid")

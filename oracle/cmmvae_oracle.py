@@ -456,6 +456,36 @@ def eval_step(spec: ModelSpec, P, expert_id, crow, col, val, eps_noise, kl_weigh
 
 
 # --------------------------------------------------------------------------------------------
+# output discriminator (BASELINE config 4) -- restated from runners/meta_discriminators.py
+# --------------------------------------------------------------------------------------------
+
+
+def output_discriminator_step(Pd: Dict[str, torch.Tensor], opt: OptState, xhat: torch.Tensor, label: float,
+                              lr: float = 1e-3):
+    """One training step of a species' output discriminator on a (detached) reconstruction:
+    nn.Sequential(Linear(G,128), Sigmoid, Linear(128,64), Sigmoid, Linear(64,1), Sigmoid)
+    (meta_discriminators.py:33-49), ``binary_cross_entropy(out, label, reduction='mean')`` (131-134),
+    ``torch.optim.Adam(lr=1e-3)`` with torch's defaults (103).  ``Pd``: state_dict of the Sequential
+    ('0.weight', '0.bias', '2.weight', ...), updated in place.  Returns loss and gradients."""
+    names = ["0.weight", "0.bias", "2.weight", "2.bias", "4.weight", "4.bias"]
+    for n in names:
+        Pd[n] = Pd[n].detach().requires_grad_(True)
+    a = xhat.detach()
+    for i in (0, 2, 4):
+        a = torch.sigmoid(a @ Pd[f"{i}.weight"].t() + Pd[f"{i}.bias"])
+    truth = torch.full_like(a, float(label))
+    loss = F.binary_cross_entropy(a, truth, reduction="mean")
+    grads = dict(zip(names, torch.autograd.grad(loss, [Pd[n] for n in names])))
+    for n in names:
+        t = opt.step.get(n, 0) + 1
+        m = opt.m.get(n, torch.zeros_like(Pd[n]))
+        v = opt.v.get(n, torch.zeros_like(Pd[n]))
+        p, m, v = adam_update(Pd[n].detach(), grads[n], m, v, t, lr, 0.0, (0.9, 0.999), 1e-8)
+        Pd[n], opt.m[n], opt.v[n], opt.step[n] = p, m, v, t
+    return {"loss": float(loss), "grads": grads}
+
+
+# --------------------------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md 8d) -- shared by tests and bench so both sides see the same bytes
 # --------------------------------------------------------------------------------------------
 

@@ -111,3 +111,31 @@ def test_oracle_fast_csr_path_agrees():
     # fp32 summation order differs between the two: compare against the tensor's scale
     assert (y0 - y1).abs().max() <= 1e-5 * y0.abs().max()
     assert (g0 - g1).abs().max() <= 1e-5 * g0.abs().max()
+
+
+def test_output_discriminator_restatement_matches_torch_modules():
+    """the oracle's output-discriminator step against the reference's own network definition executed by torch:
+    nn.Sequential(Linear, Sigmoid, Linear, Sigmoid, Linear, Sigmoid) + binary_cross_entropy(mean) + Adam(lr 1e-3)
+    (runners/meta_discriminators.py:33-49,103,131-134; the runner itself needs cluster data and a checkpoint, so
+    the pin is the architecture + loss + optimizer it names, run here for three steps on random reconstructions)"""
+    import torch.nn as nn
+    torch.manual_seed(3)
+    G, B = 300, 40
+    net = nn.Sequential(nn.Linear(G, 128), nn.Sigmoid(), nn.Linear(128, 64), nn.Sigmoid(), nn.Linear(64, 1), nn.Sigmoid())
+    Pd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    optim = torch.optim.Adam(net.parameters(), lr=0.001)
+    opt = O.OptState()
+    for t in range(3):
+        xhat = torch.relu(torch.randn(B, G, generator=torch.Generator().manual_seed(t)))
+        label = float(t % 2)
+        net.zero_grad()
+        loss = torch.nn.functional.binary_cross_entropy(net(xhat), torch.full((B, 1), label), reduction="mean")
+        loss.backward()
+        want_grads = {k: p.grad.clone() for k, p in net.named_parameters()}
+        optim.step()
+        got = O.output_discriminator_step(Pd, opt, xhat, label)
+        assert got["loss"] == pytest.approx(float(loss), rel=1e-6)
+        for k, g in want_grads.items():
+            assert torch.allclose(got["grads"][k], g, rtol=1e-5, atol=1e-8), k
+        for k, v in net.state_dict().items():
+            assert torch.allclose(Pd[k], v, rtol=1e-5, atol=1e-7), (t, k)
