@@ -45,14 +45,15 @@ class CMMVAEModel(BaseModel):
                  output_discriminator_lr: float = 1e-3, **kwargs):
         super().__init__(*args, **kwargs)
         self.module = module
-        # extension (BASELINE config 4, SURVEY 8f-4): per-species discriminators on the reconstruction, trained inside
-        # the step on the detached x-hat (mmvae_b200.modules.OutputDiscriminator); the reference only has the post-hoc
-        # runner (runners/meta_discriminators.py)
-        self.output_discriminators = torch.nn.ModuleDict(dict(output_discriminators or {}))
         self.output_discriminator_lr = float(output_discriminator_lr)
         self.automatic_optimization = False
         self.adversarial_criterion = torch.nn.CrossEntropyLoss(reduction="sum")
         self.init_weights()
+        # extension (BASELINE config 4, SURVEY 8f-4): per-species discriminators on the reconstruction, trained inside
+        # the step on the detached x-hat (mmvae_b200.modules.OutputDiscriminator); the reference only has the post-hoc
+        # runner (runners/meta_discriminators.py), whose networks live outside the LightningModule and therefore
+        # keep torch's default initialisation -- attached after init_weights() for the same reason
+        self.output_discriminators = torch.nn.ModuleDict(dict(output_discriminators or {}))
         self.adv_weight = adv_weight if adv_weight else 1.0   # 0/None -> 1.0, as in the reference
         self.autograd_config = autograd_config or AutogradConfig()
         self._engine: Optional[StepEngine] = None
