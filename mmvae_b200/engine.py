@@ -613,8 +613,7 @@ class StepEngine:
         self.timer_filter = None   # optional set of section names to time (an event record ends a PDL chain)
         self._seed = 0x5EED
         self.mid_tf32 = os.environ.get("CMMVAE_MID_TF32", "1") != "0"
-        self.spmm_tc = True                 # bf16 policy: expert-encoder SpMM on the tensor pipe ...
-        self.spmm_tc_min_density = 0.015    # ... when the batch is at least this dense (else gather kernel)
+        self.spmm_tc = True                 # bf16 policy: expert-encoder SpMM on the tensor pipe when spmm_picks_tensor() says so
         self.last = None
 
     # ------------------------------------------------------------------------------------ utilities
@@ -687,6 +686,17 @@ class StepEngine:
 
     def _tc(self, *dims) -> bool:
         return self.precision == "bf16" and all(d % 8 == 0 for d in dims)
+
+    @staticmethod
+    def spmm_picks_tensor(nnz: int, B: int, G: int, H: int = 1024) -> bool:
+        """which first-layer kernel family is faster for this batch (cost model fitted to the density x batch sweep,
+        profiles/r2_spmm_sweep.md, times in ms at G = 60 530, H = 1024 and scaled from there): the gather kernel
+        costs ~0.12 us per 1000 non-zeros with a 0.09 ms floor, the densified tensor-pipe product ~0.085 ms per 1024
+        cells plus index preparation and a small per-non-zero scatter term"""
+        scale = (G / 60530.0) * (H / 1024.0)
+        t_gather = max(0.09, 1.2e-7 * nnz * H / 1024.0)
+        t_tensor = 8.5e-5 * B * scale + 2e-8 * nnz + 0.035
+        return t_tensor < t_gather
 
     def _tf(self, *dims) -> bool:
         """small GEMMs of the middle chain: TF32 operands (fp32 activations / master weights) instead of bf16.
@@ -1382,7 +1392,7 @@ class StepEngine:
                                       self.ws("tp64", (B * ((G + 63) // 64 + 1),), torch.int32),
                                       self.ws_cap("packed", (cap + 3) // 4 * 4 + 4, torch.int32))
         else:
-            use_tc_spmm = tc_ok and nnz >= self.spmm_tc_min_density * B * G
+            use_tc_spmm = tc_ok and self.spmm_picks_tensor(nnz, B, G)
             if use_tc_spmm:
                 n_packed = (nnz + 3) // 4 * 4 + 4
                 tp = ops.csr_tile_ptr(crow, col, val, G, nnz,

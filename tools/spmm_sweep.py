@@ -96,7 +96,8 @@ def point(B, d, zipf, flush, Wt16, shard=1):
     r["bwd_tc"] = timed(lambda: ops.csr_linear_bwd_w_tc(packed, tp, Bc, Gs, dY16, dWt), flush)
     if shard == 1 and nnz <= 30_000_000:
         r["fwd_gather"] = timed(lambda: ops.csr_linear_fwd(crow, col, val, Gs, W, bias, out=Y), flush, n=4)
-    pick = "tensor" if nnz >= 0.015 * Bc * Gs or shard > 1 else "gather"
+    from mmvae_b200.engine import StepEngine
+    pick = "tensor" if (shard > 1 or StepEngine.spmm_picks_tensor(nnz, Bc, Gs, H)) else "gather"
     t_f = r["fwd_tc"] if pick == "tensor" else r.get("fwd_gather", r["fwd_tc"])
     roof_f = max(t_hbm_f, t_tensor) if pick == "tensor" else max(t_hbm_f, t_fma)
     r.update(pick=pick, t_hbm_f=t_hbm_f, t_tensor=t_tensor, t_fma=t_fma,
