@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from mmvae_b200 import ops
-from oracle.cmmvae_oracle import synth_csr
+from mmvae_b200.synth import synth_csr
 B, G, H = int(os.environ.get("PB", 1024)), 60530, 1024
 crow, col, val = synth_csr(B, G, 0.05, 1)
 crow, col, val = (torch.from_numpy(a).cuda() for a in (crow, col, val))
@@ -18,7 +18,7 @@ Y = torch.empty(B, H, device="cuda"); dWt = torch.empty(G, H, device="cuda")
 ldd = (G + 63) // 64 * 64
 dl = torch.zeros(B, ldd, device="cuda", dtype=torch.bfloat16); ls = torch.zeros(1, dtype=torch.float64, device="cuda")
 dW = torch.empty(G, H, device="cuda"); dh = torch.empty(B, H, device="cuda")
-n_adam = 125_080_192
+n_adam = 125_080_192 if B <= 1024 else 1024
 pa, ga, ma, va = (torch.zeros(n_adam, device="cuda") for _ in range(4))
 p16a = torch.zeros(n_adam, device="cuda", dtype=torch.bfloat16); nsq = torch.ones(1, dtype=torch.float64, device="cuda")
 Wg = torch.empty(G, H, device="cuda")
