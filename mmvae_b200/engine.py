@@ -694,7 +694,7 @@ class StepEngine:
         costs ~0.12 us per 1000 non-zeros with a 0.09 ms floor, the densified tensor-pipe product ~0.085 ms per 1024
         cells plus index preparation and a small per-non-zero scatter term"""
         scale = (G / 60530.0) * (H / 1024.0)
-        t_gather = max(0.09, 1.2e-7 * nnz * H / 1024.0)
+        t_gather = max(0.09, 1.2e-7 * nnz * H / 1024.0 * (1.0 + 256.0 / max(B, 1)))   # (one CTA per cell: small batches under-fill)
         t_tensor = 8.5e-5 * B * scale + 2e-8 * nnz + 0.035
         return t_tensor < t_gather
 
