@@ -37,7 +37,8 @@ struct DecSmem {
   static constexpr int kOutOff = DSTAGES * kStageBytes;                     // 4 x [128 rows][128 B] bf16, SW128
   static constexpr int kStagingOff = kOutOff + 4 * DBM * 128;               // float [8][512]
   static constexpr int kBarOff = kStagingOff + 8 * 32 * kDecEpiWarps * 4;   // + 16 KB
-  static constexpr int kTotal = kBarOff + 256;
+  static constexpr int kBiasOff = kBarOff + 256;          // float [2][256]: the tile's output biases, double buffered
+  static constexpr int kTotal = kBiasOff + 2 * DBN * 4;
 };
 
 struct DecParams {
@@ -60,6 +61,7 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
   extern __shared__ __align__(1024) uint8_t smem[];   // 128B-swizzled tiles need 1024-byte alignment
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   float* staging = reinterpret_cast<float*>(smem + DecSmem::kStagingOff);
+  float* bias_s = reinterpret_cast<float*>(smem + DecSmem::kBiasOff);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + DecSmem::kBarOff);
   uint64_t* empty_bar = full_bar + DSTAGES;
   uint64_t* tmem_full = empty_bar + DSTAGES;   // [2]
@@ -202,6 +204,10 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
       const int g0 = n0 + w * 64;            // first gene of this thread's window
       fetch(t + gridDim.x, np0, ncnt, necol, neval);
 
+      // the window's 64 output biases go to shared memory once per tile (the per-chunk global loads in the drain
+      // loop were its largest stall); two buffers: a warp is at most one tile ahead of its window group
+      float* bias_w = bias_s + (it & 1) * DBN + w * 64;
+      if (gt < 64) bias_w[gt] = (g0 + gt < p.G) ? __ldg(p.bout + g0 + gt) : 0.f;
       // the window's output tile (shared by the 4 warps of this window) must have been read by the previous
       // tile's TMA store before it is overwritten
       if (gt == 0) tma_store_wait_read();
@@ -213,17 +219,12 @@ decoder_mse_fused_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_c
       for (int c = 0; c < 8; ++c) {          // eight 8-column sub-chunks of the window (one 16-byte bf16 chunk each)
         uint32_t r[8];
         tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * DBN + w * 64 + c * 8), r);
-        const int gc = g0 + c * 8;
         float bias[8];
-        if (gc + 8 <= p.G) {
-#pragma unroll
-          for (int j = 0; j < 8; j += 2) {   // G is only guaranteed even-aligned here: 8-byte loads
-            const float2 t2 = __ldg(reinterpret_cast<const float2*>(p.bout + gc + j));
-            bias[j] = t2.x; bias[j + 1] = t2.y;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) bias[j] = (gc + j < p.G) ? __ldg(p.bout + gc + j) : 0.f;
+        {
+          const float4 b0 = *reinterpret_cast<const float4*>(bias_w + c * 8);       // same address for the whole warp
+          const float4 b1 = *reinterpret_cast<const float4*>(bias_w + c * 8 + 4);
+          bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
+          bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
         }
         tmem_ld_wait();
         // dense part: xhat = relu(acc + bias), staged in this thread's smem column (conflict free)
