@@ -28,8 +28,9 @@ def launches(path, dst):
         tot += v
     with open(dst, "w") as f:
         f.write(f"# ncu launch list ({tag}): `ncu --metrics gpu__time_duration.sum --clock-control none` over\n"
-                f"# `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (config 2, B=1024); {len(data)} launches = "
-                f"the whole process: set-up + 12 training steps (3 warm-up, 2 timed, 2 breakdown, 3+2 end to end), "
+                f"# `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-torch-baseline --no-parity-check` (config 2, "
+                f"B=1024); {len(data)} launches = the whole process: set-up + training steps of the warm-up, timed, breakdown "
+                f"and end-to-end legs (the end-to-end leg captures its two CUDA graphs, whose replays ncu lists kernel by kernel), "
                 f"{tot:.1f} us total device time (cold-cache, serialised: compare SHARES)\n\n")
         f.write("| share | total us | launches | kernel |\n|---|---|---|---|\n")
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -68,7 +69,9 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if os.path.exists(os.path.join(GP, "launches.csv")):
         launches(os.path.join(GP, "launches.csv"), os.path.join(OUT, f"{tag}_launch_list.md"))
-    for name, title in (("topk.ncu-rep", "top kernels at the bench shape (B=1024, G=60530, H=1024, 5% nnz)"),):
+    for name, title in (("topk.ncu-rep", "top kernels at the bench shape (B=1024, G=60530, H=1024, 5% nnz)"),
+                        ("dec4096.ncu-rep", "fused decoder at B=4096 (BASELINE config 3 batch), G=60530, H=1024"),
+                        ("dec8192.ncu-rep", "fused decoder at B=8192 (BASELINE config 4 batch), G=60530, H=1024")):
         p = os.path.join(GP, name)
         if os.path.exists(p):
             raw(p, os.path.join(OUT, f"{tag}_ncu_{name.split('.')[0]}.md"), title)
