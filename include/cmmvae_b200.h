@@ -260,13 +260,17 @@ int cmmvae_decoder_mse_fused_blocks(const void* h, int ldh, const void* Wout, in
                                     int loss_rows, void* workspace, void* stream);
 /* copy src[nbytes] (16-byte multiple) into dst_slots[i] on every rank i, then store `step` to peer_flags[i]
  * (system-scope release; peer_flags == NULL: no flags, for all but the last part of a multi-part push).
- * `ticket`: zeroed device uint32 owned by the caller (last-block detection). */
+ * `ticket`: zeroed device uint32 owned by the caller (last-block detection).  step_dev (device uint32, optional, in
+ * all three flag functions): the step number is read from device memory instead, so that the launch can be replayed
+ * from a captured CUDA graph. */
 int cmmvae_peer_push(const void* src, long long nbytes, void* const* dst_slots, void* const* peer_flags,
-                     int n_peers, unsigned int step, unsigned int* ticket, void* stream);
+                     int n_peers, unsigned int step, const unsigned int* step_dev, unsigned int* ticket, void* stream);
 /* flags only: after a kernel whose epilogue already stored to the peers (the routed kernels above) */
-int cmmvae_peer_signal(void* const* peer_flags, int n_peers, unsigned int step, void* stream);
+int cmmvae_peer_signal(void* const* peer_flags, int n_peers, unsigned int step, const unsigned int* step_dev,
+                       void* stream);
 /* block the stream until local_flags[0..n_peers) (uint32, this rank's memory) have all reached `step` */
-int cmmvae_peer_wait(const void* local_flags, int n_peers, unsigned int step, void* stream);
+int cmmvae_peer_wait(const void* local_flags, int n_peers, unsigned int step, const unsigned int* step_dev,
+                     void* stream);
 /* out[i] = sum_s slabs[s * slab_stride + i] (+ bias[i % H]), i < n; f32 and/or bf16 output */
 int cmmvae_slab_sum(const float* slabs, int n_slabs, long long slab_stride, long long n, const float* bias, int H,
                     float* out_f32, void* out_bf16, void* stream);

@@ -37,8 +37,10 @@ __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* addr) {
 // block to finish (device-scope ticket) raises this rank's flag on every peer
 __global__ void __launch_bounds__(256) peer_push_kernel(const uint4* __restrict__ src, long long n16, PeerPtrs dst,
                                                         PeerPtrs flags, int n_peers, uint32_t step,
-                                                        unsigned int* __restrict__ ticket) {
+                                                        unsigned int* __restrict__ ticket,
+                                                        const uint32_t* __restrict__ step_dev) {
   pdl_sync();
+  if (step_dev) step = *step_dev;    // step number kept in device memory (the launch is replayed from a CUDA graph)
   uint4* out = reinterpret_cast<uint4*>(dst.p[blockIdx.y]);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x)
     out[i] = __ldg(src + i);
@@ -55,8 +57,9 @@ __global__ void __launch_bounds__(256) peer_push_kernel(const uint4* __restrict_
   }
 }
 
-__global__ void peer_signal_kernel(PeerPtrs flags, int n_peers, uint32_t step) {
+__global__ void peer_signal_kernel(PeerPtrs flags, int n_peers, uint32_t step, const uint32_t* __restrict__ step_dev) {
   pdl_sync();   // returns once the producer grid has completed and its (peer) stores are visible
+  if (step_dev) step = *step_dev;
   __threadfence_system();
   if (threadIdx.x < n_peers) st_release_sys_u32(reinterpret_cast<uint32_t*>(flags.p[threadIdx.x]), step);
 }
@@ -65,8 +68,10 @@ __global__ void peer_signal_kernel(PeerPtrs flags, int n_peers, uint32_t step) {
 // moved onto the SMs while this kernel spins (and then blocked in griddepcontrol.wait) could hold the registers /
 // shared memory that a producer kernel of ANOTHER stream of this GPU -- the one a peer is waiting for -- needs:
 // a distributed deadlock.  Successors therefore launch only once the flags have arrived.
-__global__ void peer_wait_kernel(const uint32_t* __restrict__ local_flags, int n_peers, uint32_t step) {
+__global__ void peer_wait_kernel(const uint32_t* __restrict__ local_flags, int n_peers, uint32_t step,
+                                 const uint32_t* __restrict__ step_dev) {
   pdl_wait();
+  if (step_dev) step = *step_dev;
   if (threadIdx.x < n_peers) {
     // flags only grow; (int) difference keeps the comparison valid across a 2^32 wrap
     while ((int)(ld_acquire_sys_u32(local_flags + threadIdx.x) - step) < 0) __nanosleep(100);
@@ -230,7 +235,8 @@ static int fill_ptrs(PeerPtrs& out, void* const* ptrs, int n, const char* what) 
 }
 
 extern "C" int cmmvae_peer_push(const void* src, long long nbytes, void* const* dst_slots, void* const* peer_flags,
-                                int n_peers, unsigned int step, unsigned int* ticket, void* stream) {
+                                int n_peers, unsigned int step, const unsigned int* step_dev, unsigned int* ticket,
+                                void* stream) {
   CMMVAE_REQUIRE(nbytes >= 0 && nbytes % 16 == 0 && ((uintptr_t)src & 15) == 0 && ticket,
                  "peer_push: 16-byte aligned source and size");
   PeerPtrs d, f;
@@ -245,21 +251,24 @@ extern "C" int cmmvae_peer_push(const void* src, long long nbytes, void* const* 
   long long want = (n16 + 255) / 256;
   const int chunks = (int)(want < 1 ? 1 : (want > 32 ? 32 : want));   // a few CTAs per peer saturate the links
   launch_pdl(peer_push_kernel, dim3(chunks, n_peers), dim3(256), 0, (cudaStream_t)stream, (const uint4*)src, n16, d, f,
-             n_peers, (uint32_t)step, ticket);
+             n_peers, (uint32_t)step, ticket, (const uint32_t*)step_dev);
   return check_launch("peer_push");
 }
 
-extern "C" int cmmvae_peer_signal(void* const* peer_flags, int n_peers, unsigned int step, void* stream) {
+extern "C" int cmmvae_peer_signal(void* const* peer_flags, int n_peers, unsigned int step,
+                                  const unsigned int* step_dev, void* stream) {
   PeerPtrs f;
   if (int rc = fill_ptrs(f, peer_flags, n_peers, "peer_signal")) return rc;
-  launch_pdl(peer_signal_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, f, n_peers, (uint32_t)step);
+  launch_pdl(peer_signal_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, f, n_peers, (uint32_t)step,
+             (const uint32_t*)step_dev);
   return check_launch("peer_signal");
 }
 
-extern "C" int cmmvae_peer_wait(const void* local_flags, int n_peers, unsigned int step, void* stream) {
+extern "C" int cmmvae_peer_wait(const void* local_flags, int n_peers, unsigned int step, const unsigned int* step_dev,
+                                void* stream) {
   CMMVAE_REQUIRE(local_flags && n_peers >= 1 && n_peers <= kMaxPeers, "peer_wait: bad arguments");
   launch_pdl(peer_wait_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, (const uint32_t*)local_flags, n_peers,
-             (uint32_t)step);
+             (uint32_t)step, (const uint32_t*)step_dev);
   return check_launch("peer_wait");
 }
 

@@ -119,6 +119,8 @@ class FlatGroup:
         self.step_count = 0
         self.applied = False    # set by the fused step after its own clip+Adam launch; consumed by FlatAdam.step()
         self.bc_dev: Optional[torch.Tensor] = None   # device float[2] with this step's Adam bias corrections (graph mode)
+        self.dyn_active = False                      # the engine is in graph mode: read bc_dev instead of step_count
+        self._bg_snap = None
         self.master_dirty = False
         self._vec_range: Optional[tuple] = None
         self._deferred: Optional[torch.cuda.Event] = None   # output-layer update in flight on the background stream
@@ -224,7 +226,7 @@ class FlatGroup:
         if advance:
             self.advance()               # (rows owned by other ranks are now stale in this rank's fp32 buffer)
         hyper = (self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.step_count)
-        bc = self.bc_dev
+        bc = self.bc_dev if self.dyn_active else None
         if self.sharded:
             todo = list(self.ranges)
             bg = todo.pop(len(self.shard_blocks) - 2) if (background is not None and self.bg_range is not None) else None
@@ -244,6 +246,16 @@ class FlatGroup:
             return None
         lo, hi, mv = bg
         n = hi - lo
+        if bc is not None:
+            # graph mode: the scalar block and the bias corrections sit at fixed addresses that the NEXT step's first
+            # graph rewrites while this background update may still be running -- it reads private copies instead
+            # (rewritten only after join_background() of the next step)
+            if self._bg_snap is None:
+                self._bg_snap = (torch.zeros(1, dtype=torch.float64, device=self.p.device),
+                                 torch.zeros(2, dtype=torch.float32, device=self.p.device))
+            self._bg_snap[0].copy_(norm_sq)
+            self._bg_snap[1].copy_(bc)
+            norm_sq, bc = self._bg_snap
 
         def launch_background():
             first_done = torch.cuda.Event()
@@ -762,7 +774,7 @@ class StepEngine:
             p = lp.p_drop if training else 0.0
             mask = masks.get(tag) if (masks and p > 0) else None
             sb = None
-            if p > 0 and mask is None and self._dyn is not None:
+            if p > 0 and mask is None and self._gmode is not None:
                 # graph mode: per-step seed in device memory + a per-layer salt (the launch itself is replayed)
                 seed, sb = (hash(tag) & 0xFFFFFFF) * 0x9E3779B1, self._dyn["seed"]
             else:
@@ -1033,11 +1045,13 @@ class StepEngine:
         self._csr_pushed[key] = step
         return None
 
-    def _dp_prepare(self, gexp: FlatGroup, enc0: LayerPlan, crow, col, val, nnz: int, B: int, G: int, Hd: int):
-        """start of a data-parallel step: the pieces of every rank's batch that fall into this rank's gene shard
-        (all-to-all, normally prefetched) -> row ranges, window pointer table and packed records over the received
-        slabs, in place"""
-        N, r = self.world, self.rank
+    def _sd(self):
+        """graph mode: the device word holding this step's number (flag value of every exchange); else None"""
+        return self._dyn["step"] if (self._gmode is not None and self._dyn is not None) else None
+
+    def _dp_host_prepare(self, gexp: FlatGroup, enc0: LayerPlan, crow, col, val, nnz: int, B: int, G: int, Hd: int):
+        """host half of the start of a data-parallel step: step number / buffer parity, and -- unless the batch was
+        prefetched -- the all-to-all of its records (launched here, i.e. outside a captured graph)"""
         if self._dp is None:
             self._dp_setup(B, getattr(self, "_dp_force_nnz", nnz), enc0.N, Hd)
         d = self._dp
@@ -1057,9 +1071,22 @@ class StepEngine:
                 self._dp_step += 1
                 step = self._dp_step
             self._dp_push_csr(crow, col, val, nnz, step, per)
+        d["host"] = (step, per)
+        return step, per
+
+    def _dp_prepare(self, gexp: FlatGroup, enc0: LayerPlan, crow, col, val, nnz: int, B: int, G: int, Hd: int):
+        """start of a data-parallel step: the pieces of every rank's batch that fall into this rank's gene shard
+        (all-to-all, normally prefetched) -> row ranges, window pointer table and packed records over the received
+        slabs, in place"""
+        N, r = self.world, self.rank
+        if self._gmode is not None and self._gmode.get("dp_host") is not None:
+            step, per = self._gmode["dp_host"]       # graph mode: the host half already ran (outside the capture)
+        else:
+            step, per = self._dp_host_prepare(gexp, enc0, crow, col, val, nnz, B, G, Hd)
+        d = self._dp
         par = step & 1
         NB = N * B
-        ops.peer_wait(self.comm.local_flags(f"csr{par}"), N, step)
+        ops.peer_wait(self.comm.local_flags(f"csr{par}"), N, step, step_dev=self._sd())
         # the N received slabs are used in place: row ranges over one array spanning all slabs, window pointers
         # and packed records on top of it -- nothing is copied
         buf = d["csr"][par].local
@@ -1088,9 +1115,9 @@ class StepEngine:
         ops.csr_linear_fwd_tc_routed(dpm["tp"][1], dpm["tp"][0], dpm["NB"], dpm["per"], W16,
                                      [p + r * S * B * H1 * 4 for p in d["Yin"].ptr], B, S, B * H1)
         self._t1(ev)
-        ops.peer_signal(self.comm.flag_ptrs("Y"), step)
+        ops.peer_signal(self.comm.flag_ptrs("Y"), step, step_dev=self._sd())
         ev = self._t0("dp_wait_Y")
-        ops.peer_wait(self.comm.local_flags("Y"), N, step)
+        ops.peer_wait(self.comm.local_flags("Y"), N, step, step_dev=self._sd())
         self._t1(ev)
         Y = self.ws("enc0.y32", (B, H1))
         ops.slab_sum(d["Yin"].local.view(torch.float32), N * S, B * H1, B * H1, out32=Y, bias=lp.b, H=H1)
@@ -1110,12 +1137,13 @@ class StepEngine:
         # came after that): the CSR buffer of the other parity may be refilled for the next step from here on --
         # i.e. the prefetch of the next batch overlaps the tensor-bound decoder / dWout / dh kernels, not the
         # latency-bound chain of small kernels before them
-        d["safe"] = torch.cuda.Event()
-        d["safe"].record()
+        if not (self._gmode is not None and self._gmode["graphs"] is not None):   # (captured: recorded by the replay)
+            d["safe"] = torch.cuda.Event()
+            d["safe"].record()
         ops.peer_push(h16, B * Hd * 2, [p + r * B * Hd * 2 for p in d["hall"].ptr], self.comm.flag_ptrs("h"), step,
-                      self.comm.ticket)
+                      self.comm.ticket, step_dev=self._sd())
         ev = self._t0("dp_wait_h")
-        ops.peer_wait(self.comm.local_flags("h"), N, step)
+        ops.peer_wait(self.comm.local_flags("h"), N, step, step_dev=self._sd())
         self._t1(ev)
         h_all = d["hall"].local.view(torch.bfloat16).view(NB, Hd)
         W16 = gexp.own_rows(out.lin.weight, gexp.p16)
@@ -1146,9 +1174,9 @@ class StepEngine:
         ev = self._t0("dh_gemm")
         ops.gemm_routed(dl, 0, W16, 1, NB, Hd, per, Hd, [p + r * B * Hd * 4 for p in d["dhin"].ptr], B)
         self._t1(ev)
-        ops.peer_signal(self.comm.flag_ptrs("dh"), step)
+        ops.peer_signal(self.comm.flag_ptrs("dh"), step, step_dev=self._sd())
         ev = self._t0("dp_wait_dh")
-        ops.peer_wait(self.comm.local_flags("dh"), N, step)
+        ops.peer_wait(self.comm.local_flags("dh"), N, step, step_dev=self._sd())
         self._t1(ev)
         dh = self.ws("dh", (B, Hd))
         ops.slab_sum(d["dhin"].local.view(torch.float32), N, B * Hd, B * Hd, out32=dh)
@@ -1159,12 +1187,12 @@ class StepEngine:
         d, N, r, step = self._dp, self.world, self.rank, dpm["step"]
         gexp, H1, per = lp.group, lp.N, dpm["per"]
         ops.peer_push(dY16, B * H1 * 2, [p + r * B * H1 * 2 for p in d["dYall"].ptr], self.comm.flag_ptrs("dY"), step,
-                      self.comm.ticket)
+                      self.comm.ticket, step_dev=self._sd())
         # everything but dW1 is final now: the small (replicated) gradients travel while dW1 is computed
         gvae = self.groups["vae"]
         self._dp_allreduce_start(dpm, gexp, gexp.tail_lo, gexp.n)
         self._dp_allreduce_start(dpm, gvae, 0, gvae.n)
-        ops.peer_wait(self.comm.local_flags("dY"), N, step)
+        ops.peer_wait(self.comm.local_flags("dY"), N, step, step_dev=self._sd())
         dY_all = d["dYall"].local.view(torch.bfloat16).view(dpm["NB"], H1)
         gW = gexp.own_rows(lp.lin.weight, gexp.g)
         if gW.shape[0] != per:
@@ -1179,13 +1207,13 @@ class StepEngine:
         n = _ceil(hi - lo, 4)
         buf = self._dp_tail(group, n)
         ops.peer_push(group.g[lo:lo + n], n * 4, [p + self.rank * n * 4 for p in buf.ptr],
-                      self.comm.flag_ptrs(f"tail/{group.name}"), dpm["step"], self.comm.ticket)
+                      self.comm.flag_ptrs(f"tail/{group.name}"), dpm["step"], self.comm.ticket, step_dev=self._sd())
 
     def _dp_allreduce_finish(self, dpm, group: FlatGroup, lo: int, hi: int):
         """g[lo:hi] <- sum over ranks"""
         n = _ceil(hi - lo, 4)
         buf = self._dp_tail(group, n)
-        ops.peer_wait(self.comm.local_flags(f"tail/{group.name}"), self.world, dpm["step"])
+        ops.peer_wait(self.comm.local_flags(f"tail/{group.name}"), self.world, dpm["step"], step_dev=self._sd())
         ops.slab_sum(buf.local.view(torch.float32), self.world, n, n, out32=group.g[lo:lo + n])
 
     def _dp_finish_scalars(self, dpm, sc, s_norm_expert):
@@ -1197,8 +1225,8 @@ class StepEngine:
         mine[:N].copy_(dpm["loss_part"])
         mine[N:N + 1].copy_(dpm["shard_ssq"])
         ops.peer_push(mine, SC * 8, [p + r * SC * 8 for p in d["scal"].ptr], self.comm.flag_ptrs("scal"), step,
-                      self.comm.ticket)
-        ops.peer_wait(self.comm.local_flags("scal"), N, step)
+                      self.comm.ticket, step_dev=self._sd())
+        ops.peer_wait(self.comm.local_flags("scal"), N, step, step_dev=self._sd())
         ops.dp_scalars(d["scal"].local.view(torch.float64), N, SC, r, sc[0:1], s_norm_expert)
 
     # ----------------------------------------------------------------------------------------- step
@@ -1216,7 +1244,7 @@ class StepEngine:
             cur = torch.cuda.current_stream()
             self._hp.wait_stream(cur)
             with torch.cuda.stream(self._hp), ops.stream_scope(self._hp):
-                graphable = (self.use_graph and self.comm is None and masks is None and self.timers is None
+                graphable = (self.use_graph and masks is None and self.timers is None
                              and self.precision == "bf16" and not L._mask_queue)
                 if graphable:
                     rec = self._graph_step(expert_id, crow, col, val, nnz, kl_weight, eps, labels, nnz_cap)
@@ -1228,12 +1256,18 @@ class StepEngine:
             return self._train_step(expert_id, crow, col, val, nnz, kl_weight, eps, labels, masks)
 
     # ------------------------------------------------------------------------------------ graph mode
+    def _set_gmode(self, mode):
+        self._gmode = mode
+        for g in self.groups.values():
+            g.dyn_active = mode is not None
+
     def _ensure_dyn(self):
         if self._dyn is None:
             names = list(self.groups)
             nbytes = _ceil(16 + 8 * len(names), 16)
             dev = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
             self._dyn = dict(dev=dev, seed=dev[0:8].view(torch.int64), klw=dev[8:12].view(torch.float32),
+                             step=dev[12:16].view(torch.int32),
                              host=[torch.zeros(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(8)],
                              copied=[None] * 8, slot=0, index={n: i for i, n in enumerate(names)}, labels={},
                              inputs={})
@@ -1241,7 +1275,7 @@ class StepEngine:
                 self.groups[n].bc_dev = dev[16 + 8 * i:24 + 8 * i].view(torch.float32)
         return self._dyn
 
-    def _write_dyn(self, kl_weight: float):
+    def _write_dyn(self, kl_weight: float, dp_step: int = 0):
         """this step's scalars -> pinned block -> device block (one small async copy, stream-ordered before the step)"""
         d = self._dyn
         k = d["slot"]
@@ -1252,6 +1286,7 @@ class StepEngine:
         h[0:8].view(torch.int64)[0] = self._next_seed()
         f = h[8:].view(torch.float32)
         f[0] = float(kl_weight)
+        h[12:16].view(torch.int32)[0] = dp_step & 0x7FFFFFFF
         for n, i in d["index"].items():
             bc1, bc2 = self.groups[n].bias_corrections()
             f[2 + 2 * i], f[3 + 2 * i] = bc1, bc2
@@ -1285,36 +1320,49 @@ class StepEngine:
             stepped.append(self.odisc[expert_id]["group"])
         for g in stepped:
             g.advance()
-        self._write_dyn(kl_weight)
-        # the batch is copied to fixed addresses first (25 MB device-to-device, a few microseconds): ONE graph pair per
-        # (expert, cell count) serves every batch, wherever it was staged
         Bp1 = crow.numel()
-        gin = d["inputs"].get((expert_id, Bp1))
-        if gin is None or gin["cap"] < nnz:
-            cap = max(int(nnz * 1.25) + 1024, int(nnz_cap or 0))
-            gin = d["inputs"][(expert_id, Bp1)] = dict(
-                cap=cap, crow=torch.empty(Bp1, dtype=torch.int32, device=self.device),
-                col=torch.empty(cap, dtype=torch.int32, device=self.device),
-                val=torch.empty(cap, dtype=torch.float32, device=self.device))
-            self._graphs.pop((expert_id, Bp1), None)       # captured against the old addresses
-        gin["crow"].copy_(crow, non_blocking=True)
-        gin["col"][:nnz].copy_(col, non_blocking=True)
-        gin["val"][:nnz].copy_(val, non_blocking=True)
-        crow, col, val, nnz_cap = gin["crow"], gin["col"][:nnz], gin["val"][:nnz], gin["cap"]
-        key = (expert_id, Bp1)
+        if self.comm is not None:
+            # data parallel: the batch is exchanged by gene shard OUTSIDE the graphs (prefetched under the previous
+            # step, or inline here); the captured launches read only the received slabs (fixed addresses, one pair of
+            # graphs per buffer parity) and take the step number -- the value every flag is raised to -- from the
+            # device block
+            enc0, out = self.enc_plan[expert_id][0], self.dec_plan[expert_id][-1]
+            gexp = self.groups[f"experts/{expert_id}"]
+            step, per = self._dp_host_prepare(gexp, enc0, crow, col, val, nnz, Bp1 - 1, enc0.K, out.K)
+            self._write_dyn(kl_weight, step)
+            key = (expert_id, Bp1, step & 1)
+            dp_host = (step, per)
+        else:
+            self._write_dyn(kl_weight)
+            # the batch is copied to fixed addresses first (25 MB device-to-device, a few microseconds): ONE graph
+            # pair per (expert, cell count) serves every batch, wherever it was staged
+            gin = d["inputs"].get((expert_id, Bp1))
+            if gin is None or gin["cap"] < nnz:
+                cap = max(int(nnz * 1.25) + 1024, int(nnz_cap or 0))
+                gin = d["inputs"][(expert_id, Bp1)] = dict(
+                    cap=cap, crow=torch.empty(Bp1, dtype=torch.int32, device=self.device),
+                    col=torch.empty(cap, dtype=torch.int32, device=self.device),
+                    val=torch.empty(cap, dtype=torch.float32, device=self.device))
+                self._graphs.pop((expert_id, Bp1), None)       # captured against the old addresses
+            gin["crow"].copy_(crow, non_blocking=True)
+            gin["col"][:nnz].copy_(col, non_blocking=True)
+            gin["val"][:nnz].copy_(val, non_blocking=True)
+            crow, col, val, nnz_cap = gin["crow"], gin["col"][:nnz], gin["val"][:nnz], gin["cap"]
+            key = (expert_id, Bp1)
+            dp_host = None
         e = self._graphs.get(key)
         if e is None:
             # first visit: eager, with the device-side scalars (allocates every workspace the capture will need)
-            self._gmode = dict(cap=nnz_cap, graphs=None)
+            self._set_gmode(dict(cap=nnz_cap, graphs=None, dp_host=dp_host))
             try:
                 rec = self._train_step(expert_id, crow, col, val, nnz, kl_weight, eps, labels, None)
             finally:
-                self._gmode = None
+                self._set_gmode(None)
             self._graphs[key] = dict()
             return rec
         if "gA" not in e:
             gA, gB = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            self._gmode = dict(cap=nnz_cap, graphs=(gA, gB), events={})
+            self._set_gmode(dict(cap=nnz_cap, graphs=(gA, gB), events={}, dp_host=dp_host))
             gexp = self.groups[f"experts/{expert_id}"]
             gexp.join_background()
             ops.set_pdl(False)    # plain graph nodes replay faster than nodes with programmatic edges (measured)
@@ -1324,11 +1372,15 @@ class StepEngine:
                 gB.capture_end()
                 events = self._gmode["events"]
             finally:
-                self._gmode = None
+                self._set_gmode(None)
                 ops.set_pdl(True)
             e.update(gA=gA, gB=gB, rec=rec, bg=rec.pop("launch_bg", None), gexp=gexp, events=events, replays=0)
         e["replays"] += 1
         e["gA"].replay()
+        if dp_host is not None:
+            # (see _dp_decoder) from here the CSR buffer of the other parity may be refilled for the next step
+            self._dp["safe"] = torch.cuda.Event()
+            self._dp["safe"].record()
         e["gexp"].join_background()     # the output layer's update of the previous step (background stream)
         e["gB"].replay()
         if e["bg"] is not None:
@@ -1527,7 +1579,7 @@ class StepEngine:
                 ops.axpy(dz, d_hidden[i], -1.0)                            # GRL: -alpha * grad, alpha = 1
         dML = self.ws("dML", (B, 2 * Z))
         dML16 = self.ws("dML16", (B, 2 * Z), torch.bfloat16) if bf else None
-        if self._dyn is not None:     # graph mode: the KL weight of this step lives in device memory
+        if self._gmode is not None:   # graph mode: the KL weight of this step lives in device memory
             ops.reparam_kl_bwd(ML, eps, dz, Z, self.var_eps, 1.0 / B, dML, dML16, kl_weight_dev=self._dyn["klw"])
         else:
             ops.reparam_kl_bwd(ML, eps, dz, Z, self.var_eps, float(kl_weight) / B, dML, dML16)

@@ -111,10 +111,17 @@ def tc_ok(*dims) -> bool:
 
 def csr_parts(x: torch.Tensor):
     """(crow int32, col int32, val f32, nnz) of a torch.sparse_csr batch, bit-preserving."""
-    crow = x.crow_indices().to(torch.int32)
-    col = x.col_indices().to(torch.int32)
-    val = x.values().to(torch.float32)
-    return crow.contiguous(), col.contiguous(), val.contiguous(), int(col.numel())
+    parts = getattr(x, "_cmmvae_parts", None)
+    if parts is None:
+        crow = x.crow_indices().to(torch.int32)
+        col = x.col_indices().to(torch.int32)
+        val = x.values().to(torch.float32)
+        parts = (crow.contiguous(), col.contiguous(), val.contiguous(), int(col.numel()))
+        try:      # the same arrays on every call: a batch announced with prefetch_batch is recognised by its addresses
+            x._cmmvae_parts = parts
+        except Exception:
+            pass
+    return parts
 
 
 def _scratch(H: int, device):

@@ -410,21 +410,23 @@ def decoder_mse_fused_blocks(h16, Wout16, bout, G: int, crow, col, val, dl16, lo
                                                  _stream()), "decoder_mse_fused_blocks")
 
 
-def peer_push(src, nbytes: int, dst_ptrs, flag_ptrs, step: int, ticket):
-    """src -> dst_ptrs[i] on every rank, then (flag_ptrs not None) raise the flags to ``step``"""
+def peer_push(src, nbytes: int, dst_ptrs, flag_ptrs, step: int, ticket, step_dev=None):
+    """src -> dst_ptrs[i] on every rank, then (flag_ptrs not None) raise the flags to ``step`` (``step_dev``: device
+    uint32 holding the step number instead -- graph replay)"""
     _check(lib().cmmvae_peer_push(_ptr(src), _c.c_longlong(nbytes), _ptr_array(dst_ptrs),
                                   _ptr_array(flag_ptrs) if flag_ptrs is not None else None,
-                                  len(dst_ptrs), _c.c_uint(step & 0xFFFFFFFF), _ptr(ticket), _stream()), "peer_push")
+                                  len(dst_ptrs), _c.c_uint(step & 0xFFFFFFFF), _ptr(step_dev), _ptr(ticket), _stream()),
+           "peer_push")
 
 
-def peer_signal(flag_ptrs, step: int):
-    _check(lib().cmmvae_peer_signal(_ptr_array(flag_ptrs), len(flag_ptrs), _c.c_uint(step & 0xFFFFFFFF), _stream()),
-           "peer_signal")
+def peer_signal(flag_ptrs, step: int, step_dev=None):
+    _check(lib().cmmvae_peer_signal(_ptr_array(flag_ptrs), len(flag_ptrs), _c.c_uint(step & 0xFFFFFFFF),
+                                    _ptr(step_dev), _stream()), "peer_signal")
 
 
-def peer_wait(local_flags, n_peers: int, step: int):
-    _check(lib().cmmvae_peer_wait(_ptr(local_flags), int(n_peers), _c.c_uint(step & 0xFFFFFFFF), _stream()),
-           "peer_wait")
+def peer_wait(local_flags, n_peers: int, step: int, step_dev=None):
+    _check(lib().cmmvae_peer_wait(_ptr(local_flags), int(n_peers), _c.c_uint(step & 0xFFFFFFFF), _ptr(step_dev),
+                                  _stream()), "peer_wait")
 
 
 def slab_sum(slabs, n_slabs: int, slab_stride: int, n: int, out32=None, out16=None, bias=None, H: int = 0):

@@ -55,13 +55,21 @@ def _inputs(d, rank, t=0):
     return crow, col, val, eps
 
 
-def _step(model, d, rank, t=0, device="cuda"):
-    from mmvae_b200 import layers as L
+def _batch(d, rank, t, device):
     crow, col, val, eps = _inputs(d, rank, t)
+    return (csr_batch(crow, col, val, d["G"], device), pd.DataFrame({"cell": np.arange(d["B"])}), "human"), eps
+
+
+def _step(model, d, rank, t=0, device="cuda", batch=None, after=None):
+    from mmvae_b200 import layers as L
+    batch, eps = batch or _batch(d, rank, t, device)
     L.inject_noise(eps.to(device))
     model.logged_metrics.clear()
-    batch = (csr_batch(crow, col, val, d["G"], device), pd.DataFrame({"cell": np.arange(d["B"])}), "human")
     model.training_step(batch, t)
+    if after is not None:
+        after()
+    if not model.sync_logging:
+        model.flush_logs()
     torch.cuda.synchronize()
     return {k.split("/")[0] if not k.startswith("grad_norms") else k: float(v) for k, v in model.logged_metrics.items()}
 
@@ -125,7 +133,7 @@ def test_forced_dp_route_single_process_equals_plain_step():
             assert rel_l2(grads[k].numpy(), g.numpy()) < 3e-2, (d["G"], k, rel_l2(grads[k].numpy(), g.numpy()))
 
 
-def _worker(rank, world, port, out, d, same_gpu, steps):
+def _worker(rank, world, port, out, d, same_gpu, steps, pipelined=None):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     os.environ.pop("CMMVAE_FORCE_DP", None)
@@ -144,9 +152,22 @@ def _worker(rank, world, port, out, d, same_gpu, steps):
         eng = model.engine()
         assert eng.comm is not None and eng.world == world
         res = []
+        if pipelined is not None:
+            # the training loop's mode: results trail by a step, the next batch's records are exchanged underneath
+            # the running step, and (pipelined == "graph") the step is replayed from CUDA graphs
+            model.sync_logging = False
+            model.use_cuda_graphs = pipelined == "graph"
+        nxt = None
         for t in range(steps):
-            logs = _step(model, d, rank, t, f"cuda:{dev}")
+            cur = nxt or _batch(d, rank, t, f"cuda:{dev}")
+            nxt = _batch(d, rank, t + 1, f"cuda:{dev}") if pipelined is not None and t + 1 < steps else None
+            # (step 2's successor is NOT announced: its records are exchanged at the start of step 3 instead)
+            pf = (lambda: model.prefetch_batch(nxt[0])) if nxt is not None and t != 2 else None
+            logs = _step(model, d, rank, t, f"cuda:{dev}", batch=cur, after=pf)
             res.append(logs)
+        if pipelined == "graph":
+            replays = sum(e.get("replays", 0) for e in eng._graphs.values())
+            assert replays >= steps - 4, (replays, list(eng._graphs))
         grads = _grads(model)                      # of the last step
         sd = {k[len("module."):]: v.detach().cpu() for k, v in model.state_dict().items()}   # gathers the rows
         # numpy arrays travel by value (torch tensors would travel as file descriptors of a process about to exit)
@@ -156,11 +177,12 @@ def _worker(rank, world, port, out, d, same_gpu, steps):
         dist.destroy_process_group()
 
 
-def _run_ranks(world, d, same_gpu, steps=1):
+def _run_ranks(world, d, same_gpu, steps=1, pipelined=None):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
-    port = 29600 + (os.getpid() * 7 + world + int(same_gpu)) % 2000
-    procs = [ctx.Process(target=_worker, args=(r, world, port, out, d, same_gpu, steps)) for r in range(world)]
+    _run_ranks.n = getattr(_run_ranks, "n", 0) + 1
+    port = 29600 + (os.getpid() * 7 + world + int(same_gpu) + 13 * _run_ranks.n) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out, d, same_gpu, steps, pipelined)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([out.get(timeout=600) for _ in procs], key=lambda t: t[0])
@@ -227,6 +249,30 @@ def _check_two_ranks(d, res, world=2):
 def test_two_ranks_sharing_one_gpu_over_cuda_ipc(d):
     res = _run_ranks(2, d, same_gpu=True)
     _check_two_ranks(d, res)
+
+
+def _compare_runs(a, b, steps):
+    for r in range(2):
+        for t in range(steps):
+            for k, tol in (("loss", 2e-3), ("recon_loss", 2e-3), ("kl_loss", 2e-2), ("grad_norms/expert_human", 5e-2)):
+                assert a[r][1][t][k] == pytest.approx(b[r][1][t][k], rel=tol), (r, t, k)
+        for k in ("experts.human.encoder.fc_layers.0.lin.weight", "experts.human.decoder.fc_layers.1.lin.weight",
+                  "vae.encoder.mean_encoder.weight"):
+            assert rel_l2(a[r][3][k], b[r][3][k]) < 2e-3, (r, k, rel_l2(a[r][3][k], b[r][3][k]))
+
+
+def test_two_ranks_graph_replay_equals_stream_launches():
+    """data parallel, pipelined mode: the step replayed from CUDA graphs (flag values read from the device block,
+    one graph pair per buffer parity, records prefetched or exchanged inline) walks the trajectory the
+    stream-launched step walks; after the run the replicas still agree bit for bit"""
+    steps = 8
+    eager = _run_ranks(2, DIMS, same_gpu=True, steps=steps, pipelined="stream")
+    graph = _run_ranks(2, DIMS, same_gpu=True, steps=steps, pipelined="graph")
+    _compare_runs(eager, graph, steps)
+    for k in graph[0][3]:
+        if "running" in k or k.endswith("num_batches_tracked"):
+            continue
+        assert np.array_equal(graph[0][3][k], graph[1][3][k]), k
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
