@@ -486,7 +486,7 @@ def main():
     # batch -> D2H read of the step's scalar block (one step late, so the copy never stalls the launch queue).
     import scipy.sparse as sp
     from mmvae_b200.feed import StagedCSRBatches
-    workers = max(1, min(6, (os.cpu_count() or 8) // world - 1))
+    workers = int(os.environ.get("BENCH_WORKERS", 0)) or max(1, min(6, (os.cpu_count() or 8) // world - 1))
 
     def chunk_source(s):
         chunk = sp.vstack([sp.csr_matrix((v, c, r), shape=(B, species[s])) for r, c, v in host[s]], format="csr")

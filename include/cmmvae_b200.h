@@ -308,6 +308,14 @@ long long cmmvae_host_slice_rows(const void* indptr, int indptr_width, const voi
                                  int32_t* crow_out, void* col_out, int col_u16, float* val_out);
 /* device: dst int32[n] = src uint16[n] (gene ids shipped narrow over PCIe, widened once they are in HBM) */
 int cmmvae_widen_u16_i32(const void* src_u16, int32_t* dst, long long n, void* stream);
+/* Zero-copy route for chunks that serve many batches (the reference cuts every ~100k-cell .npz chunk into
+ * consecutive row ranges, cellxgene_datapipe.py:169-193): page-lock the chunk's indices / data arrays IN PLACE
+ * once (cudaHostRegister), then every batch is two DMA transfers straight out of them -- no host packing.
+ * register / unregister: 0 on success, < 0 with cmmvae_last_error() set (e.g. the lock limit of the process). */
+int cmmvae_host_register(const void* host_ptr, long long nbytes);
+int cmmvae_host_unregister(const void* host_ptr);
+/* cudaMemcpyAsync host -> device on `stream` (asynchronous when the host range is page-locked) */
+int cmmvae_h2d_async(void* dst_dev, const void* src_host, long long nbytes, void* stream);
 
 #ifdef __cplusplus
 }

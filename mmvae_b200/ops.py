@@ -374,6 +374,23 @@ def host_slice_rows(indptr, indices, data, lo: int, hi: int, n_genes: int, crow_
     return int(n)
 
 
+def host_register(arr) -> None:
+    """page-lock a numpy array's memory in place (cmmvae_host_register); raises RuntimeError if the driver refuses"""
+    if lib().cmmvae_host_register(_c.c_void_p(arr.ctypes.data), _c.c_longlong(arr.nbytes)) != 0:
+        raise RuntimeError(lib().cmmvae_last_error().decode())
+
+
+def host_unregister(arr) -> None:
+    if lib().cmmvae_host_unregister(_c.c_void_p(arr.ctypes.data)) != 0:
+        raise RuntimeError(lib().cmmvae_last_error().decode())
+
+
+def h2d_async(dst: torch.Tensor, src, nbytes: int, stream=None) -> None:
+    """cudaMemcpyAsync of ``nbytes`` from a numpy array (view) into a device tensor, on ``stream``"""
+    st = _c.c_void_p(stream.cuda_stream) if stream is not None else _stream()
+    _check(lib().cmmvae_h2d_async(_ptr(dst), _c.c_void_p(src.ctypes.data), _c.c_longlong(nbytes), st), "h2d_async")
+
+
 # ------------------------------------------------------------------- data parallel over peer memory
 def _ptr_array(ptrs):
     arr = (_c.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
