@@ -505,12 +505,19 @@ def main():
         x, meta = next(iters[s])
         return x, meta, s
 
+    host_t = {"fetch": 0.0, "training_step": 0.0}     # host wall time per phase (diagnostic: is a leg host-bound?)
+
     def api_step(t):
+        t0 = time.perf_counter()
         batch = pending.pop(t, None) or fetch(t)
+        t1 = time.perf_counter()
         model.training_step(batch, t)
+        t2 = time.perf_counter()
         if world > 1:      # data parallel: hand the next batch over so its CSR exchange runs under this step
             pending[t + 1] = fetch(t + 1)
             model.prefetch_batch(pending[t + 1])
+        host_t["fetch"] += t1 - t0 + (time.perf_counter() - t2)
+        host_t["training_step"] += t2 - t1
         v = model.logged_metrics.get(f"loss/training/{batch[2]}")
         return float(v) if v is not None else None
 
@@ -520,10 +527,12 @@ def main():
     for t in range(w_api):
         api_step(t)
     barrier()
+    host_t.update(fetch=0.0, training_step=0.0)
     e0.record()
     loss = None
     for t in range(args.steps):
         loss = api_step(t + w_api)
+    host_main = {k: v * 1e3 / args.steps for k, v in host_t.items()}
     model.flush_logs()
     e1.record()
     barrier()
@@ -532,6 +541,41 @@ def main():
         tt = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
         e2e_ms = float(tt.item())
+    # the same leg with the chunks page-locked in place once (StagedCSRBatches(pin_chunks=True)): a batch is its
+    # rebased crow plus two DMA transfers out of the chunk's own arrays -- no host pass, no packing threads.  Reported
+    # next to the headline (which keeps the reference loader's pageable chunks), to show what the step sustains when
+    # the host's DRAM bandwidth is not spent on packing (it is what limits `e2e` at N=8)
+    pinned_leg = None
+    if os.environ.get("BENCH_PINNED_LEG", "1") == "1":
+        pfeeds = {s: StagedCSRBatches(chunk_source(s), B, device=dev, workers=0, ahead=4, pin_chunks=True)
+                  for s in names}
+        main_iters, iters = iters, {s: iter(f) for s, f in pfeeds.items()}
+        pending.clear()
+        for t in range(w_api):
+            api_step(t)
+        barrier()
+        host_t.update(fetch=0.0, training_step=0.0)
+        e0.record()
+        for t in range(args.steps):
+            api_step(t + w_api)
+        host_pinned = {k: v * 1e3 / args.steps for k, v in host_t.items()}
+        model.flush_logs()
+        e1.record()
+        barrier()
+        p_ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([p_ms], device=dev, dtype=torch.float64)
+            torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+            p_ms = float(tt.item())
+        pinned_leg = {"value": B * world / (p_ms / args.steps * 1e-3), "unit": "cells/s",
+                      "ms_per_step": p_ms / args.steps,
+                      "h2d_bytes_per_step": int(pfeeds[names[0]].stager.bytes_staged),
+                      "host_ms_per_step": host_pinned,
+                      "host_side": "chunks page-locked in place once (cudaHostRegister), int32 gene ids, no packing"}
+        pending.clear()
+        iters = main_iters
+        for f in pfeeds.values():
+            f.close()
     clocks = sampler.stop() if rank == 0 else None
     h2d = int(feeds[names[0]].stager.bytes_staged)
     narrow = bool(feeds[names[0]].stager.narrow)
@@ -601,6 +645,7 @@ def main():
         "config": config,
         "e2e": {"value": B * world / (e2e_ms / args.steps * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps, "last_loss": loss,
+                "host_ms_per_step": host_main,
                 "host_side": f"StagedCSRBatches over pageable scipy CSR chunks, {workers} packing threads inside the "
                              f"timed region, gene ids on the wire: {'uint16' if narrow else 'int32'}"},
         "gpu_launches": int(launches),
@@ -618,6 +663,8 @@ def main():
                  "fma_tflops": 2.0 * nnz * H1 / (t_spmm * 1e-3) / 1e12 if t_spmm > 0 else 0.0},
         "clocks": clocks,
     }
+    if pinned_leg is not None:
+        line["e2e"]["pinned_chunks"] = pinned_leg
     if parity is not None:
         line["parity_check"] = parity
     if also:

@@ -297,6 +297,12 @@ int cmmvae_csr_tile_ptr_rows(const int32_t* row_begin, const int32_t* row_end, c
 int cmmvae_dp_scalars(const double* slabs, int n_src, int stride, int rank, double* out_recon, double* out_norm,
                       void* stream);
 
+/* ---- parallel conditional layers without parameters (configs/model/human_only.yaml:53-79; ConditionalLayers.forward,
+ * components.py:617-631, with FCBlocks of zero layers, components.py:217-232): out[b, k*Z + j] = z[b, j] for
+ * k < n (fp32 and optionally bf16), and its backward dz[b, j] = sum_k dcat[b, k*Z + j] */
+int cmmvae_tile_cols(const float* z, int B, int Z, int n, float* out_f32, void* out_bf16, void* stream);
+int cmmvae_fold_cols(const float* dcat, int B, int Z, int n, float* dz, void* stream);
+
 /* ---- host -> HBM feed of CSR batches (batch format of cellxgene_datapipe.py:169-193) ---------
  * HOST function (all pointers are host pointers): rows [lo, hi) of a CSR chunk -- what scipy's chunk[lo:hi]
  * yields in SparseCSRMatrixBatcherDataPipe -- written into a (pinned) staging block: crow int32 rebased to 0,
@@ -314,6 +320,8 @@ int cmmvae_widen_u16_i32(const void* src_u16, int32_t* dst, long long n, void* s
  * register / unregister: 0 on success, < 0 with cmmvae_last_error() set (e.g. the lock limit of the process). */
 int cmmvae_host_register(const void* host_ptr, long long nbytes);
 int cmmvae_host_unregister(const void* host_ptr);
+/* device -> device copy by a kernel (16-byte aligned buffers): does not queue behind H2D transfers on a copy engine */
+int cmmvae_copy_bytes(void* dst, const void* src, long long nbytes, void* stream);
 /* cudaMemcpyAsync host -> device on `stream` (asynchronous when the host range is page-locked) */
 int cmmvae_h2d_async(void* dst_dev, const void* src_host, long long nbytes, void* stream);
 

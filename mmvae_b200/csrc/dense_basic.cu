@@ -591,6 +591,40 @@ __global__ void axpy_kernel(float* __restrict__ a, const float* __restrict__ b, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// parallel conditional layers without parameters (configs/model/human_only.yaml:53-79: conditional_config.layers =
+// [128] builds FCBlocks with NO layer, components.py:217-232, so every ConditionalLayer is the identity and
+// ConditionalLayers.forward, components.py:617-631, concatenates n copies of z):  zcat[b, k*Z + j] = z[b, j], and in
+// the backward pass dz[b, j] = sum_k dzcat[b, k*Z + j]
+// ---------------------------------------------------------------------------------------------
+__global__ void tile_cols_kernel(const float* __restrict__ z, int Z, int n, long long total, float* __restrict__ out32,
+                                 __nv_bfloat16* __restrict__ out16) {
+  pdl_sync();
+  const int W = Z * n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / W;
+    const int j = (int)(i - b * W) % Z;
+    const float v = z[b * Z + j];
+    out32[i] = v;
+    if (out16) out16[i] = __float2bfloat16(v);
+  }
+}
+
+__global__ void fold_cols_kernel(const float* __restrict__ dcat, int Z, int n, long long total,
+                                 float* __restrict__ dz) {
+  pdl_sync();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / Z;
+    const int j = (int)(i - b * Z);
+    const float* src = dcat + b * (long long)Z * n + j;
+    float acc = 0.f;
+    for (int k = 0; k < n; ++k) acc += src[(long long)k * Z];
+    dz[i] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // output discriminator (BASELINE config 4; reference MLP: runners/meta_discriminators.py:33-49,112-148)
 // ---------------------------------------------------------------------------------------------
 // The discriminator reads the reconstruction xhat = relu(logits), which the fused decoder never writes.  What it
@@ -907,6 +941,21 @@ extern "C" int cmmvae_axpy(float* a, const float* b, float alpha, long long n, v
   if (n <= 0) return 0;
   launch_pdl(axpy_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, a, b, alpha, n);
   return check_launch("axpy");
+}
+
+extern "C" int cmmvae_tile_cols(const float* z, int B, int Z, int n, float* out_f32, void* out_bf16, void* stream) {
+  CMMVAE_REQUIRE(z && out_f32 && B > 0 && Z > 0 && n > 0, "tile_cols: bad arguments");
+  const long long total = (long long)B * Z * n;
+  launch_pdl(tile_cols_kernel, dim3(ew_blocks(total)), dim3(256), 0, (cudaStream_t)stream, z, Z, n, total, out_f32,
+             (__nv_bfloat16*)out_bf16);
+  return check_launch("tile_cols");
+}
+
+extern "C" int cmmvae_fold_cols(const float* dcat, int B, int Z, int n, float* dz, void* stream) {
+  CMMVAE_REQUIRE(dcat && dz && B > 0 && Z > 0 && n > 0, "fold_cols: bad arguments");
+  const long long total = (long long)B * Z;
+  launch_pdl(fold_cols_kernel, dim3(ew_blocks(total)), dim3(256), 0, (cudaStream_t)stream, dcat, Z, n, total, dz);
+  return check_launch("fold_cols");
 }
 
 extern "C" int cmmvae_mask_vals_by_dl(const int32_t* crow, const int32_t* col, const float* val, int B,

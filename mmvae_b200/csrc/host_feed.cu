@@ -30,9 +30,32 @@ __global__ void widen_u16_i32_kernel(const uint16_t* __restrict__ src, int32_t* 
        i += (long long)gridDim.x * blockDim.x)
     dst[i] = src[i];
 }
+__global__ void copy_bytes_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long n16,
+                                  const unsigned char* __restrict__ src_tail, unsigned char* __restrict__ dst_tail,
+                                  int tail) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16;
+       i += (long long)gridDim.x * blockDim.x)
+    dst[i] = __ldg(src + i);
+  if (blockIdx.x == 0 && (int)threadIdx.x < tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
+}
 }  // namespace cmmvae
 
 using namespace cmmvae;
+
+// device -> device copy done by the SMs.  The graph-replayed step copies each staged batch to the fixed addresses its
+// graphs read; as cudaMemcpyAsync those copies queue on the same copy engines as the H2D transfers of the batches
+// staged ahead (0.3-0.5 ms each) and the step waits for them; as a kernel they take ~15 us and wait for nothing.
+extern "C" int cmmvae_copy_bytes(void* dst, const void* src, long long nbytes, void* stream) {
+  if (nbytes <= 0) return 0;
+  CMMVAE_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "copy_bytes: buffers must be 16-byte aligned");
+  const long long n16 = nbytes / 16;
+  const int tail = (int)(nbytes - n16 * 16);
+  long long want = (n16 + 255) / 256 + 1;
+  const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
+  copy_bytes_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)src, (uint4*)dst, n16, (const unsigned char*)src + n16 * 16, (unsigned char*)dst + n16 * 16, tail);
+  return check_launch("copy_bytes");
+}
 
 extern "C" int cmmvae_widen_u16_i32(const void* src_u16, int32_t* dst, long long n, void* stream) {
   if (n <= 0) return 0;

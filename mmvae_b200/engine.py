@@ -21,6 +21,7 @@ and exposed as a ``[hidden, genes]`` view.
 from __future__ import annotations
 
 import math
+import random
 import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
@@ -520,8 +521,23 @@ class StepEngine:
         self.adv_weight = adv_weight
         self.clip = clip or {"vae": 10.0, "expert": 10.0, "adversarial": 10.0}
         vae = module.vae
-        if getattr(vae, "conditionals", None):
-            raise UnsupportedTopology("conditional layers are outside the fused step (SURVEY.md 8f-1)")
+        # conditional layers.  The topology the reference ships (configs/model/human_only.yaml:53-79)
+        # configures them with ``layers: [latent]``: FCBlocks without a single layer (components.py:217-232), so every
+        # ConditionalLayer is the identity; "parallel" selection concatenates one copy of z per conditional
+        # (components.py:617-631) in front of the extra "concat" decoder layer (clvae.py:55-79).  That is what the
+        # fused step runs (n copies of z, folded again in the backward pass).  Conditional blocks WITH parameters
+        # (one Linear + LayerNorm per metadata value) stay on the module route.
+        self.cond_copies, self.cond_shuffle = 1, None
+        cond = getattr(vae, "conditionals", None)
+        if cond:
+            blocks = [m for m in cond.modules() if hasattr(m, "fc_layers")]
+            if any(len(b.fc_layers) for b in blocks):
+                raise UnsupportedTopology("conditional layers with parameters are outside the fused step "
+                                          "(SURVEY.md 8f-1); parameter-free ones (human_only.yaml) are fused")
+            if cond.is_parallel:
+                self.cond_copies = len(cond.selection_order)
+            if cond.shuffle_selection_order:
+                self.cond_shuffle = list(cond.selection_order)
         enc = vae.encoder
         if isinstance(enc.z_transformation, nn.Softmax):
             raise UnsupportedTopology("distribution='ln' is outside the fused step")
@@ -1229,6 +1245,23 @@ class StepEngine:
         ops.peer_wait(self.comm.local_flags("scal"), N, step, step_dev=self._sd())
         ops.dp_scalars(d["scal"].local.view(torch.float64), N, SC, r, sc[0:1], s_norm_expert)
 
+    def _after_reparameterize(self, z32, z16, B: int):
+        """CLVAE.after_reparameterize (clvae.py:89-111) for parameter-free conditional layers: identity, or -- parallel
+        selection -- one copy of z per conditional side by side"""
+        if self.cond_shuffle is not None:
+            # ConditionalLayers.forward draws a fresh order with Python's ``random`` on every call
+            # (components.py:598-600); identical copies make the order irrelevant, the draw keeps the host's
+            # generator where the reference leaves it
+            random.sample(self.cond_shuffle, len(self.cond_shuffle))
+        n = self.cond_copies
+        if n == 1:
+            return z32, z16
+        Z = z32.shape[1]
+        c32 = self.ws("zcat32", (B, n * Z))
+        c16 = self.ws("zcat16", (B, n * Z), torch.bfloat16) if z16 is not None else None
+        ops.tile_cols(z32, n, c32, c16)
+        return c32, c16
+
     # ----------------------------------------------------------------------------------------- step
     def train_step(self, expert_id: str, crow, col, val, nnz: int, kl_weight: float, eps=None,
                    labels: Optional[Dict[str, torch.Tensor]] = None, masks=None, nnz_cap: Optional[int] = None):
@@ -1344,9 +1377,16 @@ class StepEngine:
                     col=torch.empty(cap, dtype=torch.int32, device=self.device),
                     val=torch.empty(cap, dtype=torch.float32, device=self.device))
                 self._graphs.pop((expert_id, Bp1), None)       # captured against the old addresses
-            gin["crow"].copy_(crow, non_blocking=True)
-            gin["col"][:nnz].copy_(col, non_blocking=True)
-            gin["val"][:nnz].copy_(val, non_blocking=True)
+            # (by a kernel: a cudaMemcpyAsync would queue behind the H2D transfers of the batches staged ahead)
+            if (crow.data_ptr() | col.data_ptr() | val.data_ptr()) % 16 == 0 and crow.dtype == torch.int32 \
+                    and col.is_contiguous() and val.is_contiguous():
+                ops.copy_bytes(gin["crow"], crow, 4 * Bp1)
+                ops.copy_bytes(gin["col"], col, 4 * nnz)
+                ops.copy_bytes(gin["val"], val, 4 * nnz)
+            else:
+                gin["crow"].copy_(crow, non_blocking=True)
+                gin["col"][:nnz].copy_(col, non_blocking=True)
+                gin["val"][:nnz].copy_(val, non_blocking=True)
             crow, col, val, nnz_cap = gin["crow"], gin["col"][:nnz], gin["val"][:nnz], gin["cap"]
             key = (expert_id, Bp1)
             dp_host = None
@@ -1479,7 +1519,7 @@ class StepEngine:
         ops.reparam_kl_fwd(ML, eps, Z, self.var_eps, z32, z16, sc[1:4])
         if self.hidden_z:
             hidden.append(("z", 0, z32, z16))
-        x32, x16 = z32, z16
+        x32, x16 = self._after_reparameterize(z32, z16, B)
         for j, lp in enumerate(self.vaedec_plan):
             x32, x16, caches[("vdec", j)] = self._layer_fwd(f"vdec{j}", lp, x32, x16, B, masks=masks)
         for j, lp in enumerate(dec[:-1]):
@@ -1573,7 +1613,10 @@ class StepEngine:
             d = self._layer_bwd(f"dec{j}", dec[j], caches[("dec", j)], d, B)
         for j in reversed(range(len(self.vaedec_plan))):
             d = self._layer_bwd(f"vdec{j}", self.vaedec_plan[j], caches[("vdec", j)], d, B)
-        dz = d
+        if self.cond_copies > 1:      # backward of the concatenation: the copies' gradients add up
+            dz = ops.fold_cols(d, self.cond_copies, self.ws("dz_fold", (B, Z)))
+        else:
+            dz = d
         for i in range(n_adv):
             if hidden[i][0] == "z":
                 ops.axpy(dz, d_hidden[i], -1.0)                            # GRL: -alpha * grad, alpha = 1
@@ -1725,7 +1768,7 @@ class StepEngine:
         z32 = self.ws("z32", (B, Z))
         z16 = self.ws("z16", (B, Z), torch.bfloat16) if bf else None
         ops.reparam_kl_fwd(ML, eps, Z, self.var_eps, z32, z16, sc[1:4])
-        x32, x16 = z32, z16
+        x32, x16 = self._after_reparameterize(z32, z16, B)
         for j, lp in enumerate(self.vaedec_plan):
             x32, x16, _ = self._layer_fwd(f"vdec{j}", lp, x32, x16, B, training=False)
         for j, lp in enumerate(dec[:-1]):

@@ -25,6 +25,10 @@ consumer of that slot's previous occupant, so an in-flight step never sees its i
 of 8 bytes per non-zero over PCIe -- and a widening kernel on the copy stream restores the int32 ``col`` array
 in HBM right behind the copy (exact: ids are < 65 536), so consumers still see int32 / fp32.
 
+``StagedCSRBatches(..., pin_chunks=True)``: chunks that serve many batches (or many epochs) are page-locked IN
+PLACE once (``cmmvae_host_register``); a batch is then the rebased ``crow`` plus two DMA transfers straight out of
+the chunk's ``indices`` / ``data`` arrays -- no host pass over the non-zeros at all.
+
 ``StagedCSRBatches(..., workers=k)`` packs batches on ``k`` background threads with the native packer
 (``cmmvae_host_slice_rows``: no GIL, no intermediate arrays), several batches ahead of the consumer.
 """
@@ -97,6 +101,8 @@ class CSRStager:
         self.on_gpu = self.device.type == "cuda"
         if self.on_gpu and not torch.cuda.is_available():
             raise RuntimeError("CSRStager(device='cuda') needs a CUDA device")
+        if self.on_gpu and self.device.index is None:      # (worker threads select the device by index)
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.host = [torch.empty(self.nbytes, dtype=torch.uint8, pin_memory=self.on_gpu) for _ in range(depth)]
         self.dev = [torch.empty(self.nbytes, dtype=torch.uint8, device=self.device) for _ in range(depth)]
         # narrow blocks: the int32 col array the kernels read, widened on the device behind each copy
@@ -155,6 +161,37 @@ class CSRStager:
             if self.narrow:
                 from . import ops
                 ops.widen_u16_i32(self.dev[slot][o_col:], self.col32[slot], b.nnz, stream=self.stream)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self._copied[slot] = ev
+        return Ticket(slot, b.n_cells, int(n_genes), b.nnz, ev)
+
+    def commit_from_chunk(self, b: "Block", indices: np.ndarray, data: np.ndarray, a: int, n_genes: int) -> Ticket:
+        """ship a batch whose ``crow`` sits in the reserved block and whose ids / values are the page-locked chunk's
+        ``indices[a:a+nnz]`` (int32) / ``data[a:a+nnz]`` (fp32): three DMA transfers, no host copy.  Wide stager only"""
+        if self.narrow:
+            raise ValueError("commit_from_chunk ships int32 gene ids: use a stager with narrow_col=False")
+        if indices.dtype != np.int32 or data.dtype != np.float32:
+            raise ValueError("commit_from_chunk needs int32 indices and float32 data")
+        if int(b.crow[0]) != 0 or int(b.crow[-1]) != b.nnz:
+            raise ValueError("inconsistent CSR arrays (crow[0] must be 0, crow[-1] == len(col) == len(val))")
+        o_crow, o_col, o_val, _ = block_layout(self.max_cells, self.max_nnz, self.col_bytes)
+        n0 = _align(4 * (b.n_cells + 1))
+        self.bytes_staged = n0 + 8 * b.nnz
+        slot, d = b.slot, self.dev[b.slot]
+        if not self.on_gpu:
+            d[:n0].copy_(self.host[slot][:n0])
+            d[o_col:o_col + 4 * b.nnz].copy_(torch.from_numpy(indices[a:a + b.nnz].view(np.uint8)))
+            d[o_val:o_val + 4 * b.nnz].copy_(torch.from_numpy(data[a:a + b.nnz].view(np.uint8)))
+            return Ticket(slot, b.n_cells, int(n_genes), b.nnz, None)
+        from . import ops
+        with torch.cuda.stream(self.stream):
+            if self._consumed[slot] is not None:
+                self.stream.wait_event(self._consumed[slot])
+            d[:n0].copy_(self.host[slot][:n0], non_blocking=True)
+            if b.nnz:
+                ops.h2d_async(d[o_col:], indices[a:a + b.nnz], 4 * b.nnz, stream=self.stream)
+                ops.h2d_async(d[o_val:], data[a:a + b.nnz], 4 * b.nnz, stream=self.stream)
             ev = torch.cuda.Event()
             ev.record(self.stream)
         self._copied[slot] = ev
@@ -226,7 +263,8 @@ class StagedCSRBatches:
     the chunk has <= 65 536 genes)."""
 
     def __init__(self, source, batch_size: int, allow_partials: bool = False, device="cuda", depth: int = 3,
-                 workers: int = 0, ahead: Optional[int] = None, narrow_col: Optional[bool] = None):
+                 workers: int = 0, ahead: Optional[int] = None, narrow_col: Optional[bool] = None,
+                 pin_chunks: bool = False):
         if batch_size <= 0:
             raise ValueError("batch_size must be positive")
         self.workers = int(workers)
@@ -238,9 +276,44 @@ class StagedCSRBatches:
         self.device, self.depth, self.narrow_col = device, depth, narrow_col
         self.stager: Optional[CSRStager] = None
         self._pool = None
+        self.pin_chunks = bool(pin_chunks)
+        self._pinned = collections.OrderedDict()     # (addresses) -> (indices, data): page-locked chunks, LRU of 2
+        self.chunks_pinned = 0
 
-    def _ensure_capacity(self, nnz: int, n_genes: int):
-        narrow = self.narrow_col if self.narrow_col is not None else n_genes <= 65536
+    def _pin(self, chunk, n_genes: int) -> bool:
+        """page-lock the chunk's arrays on first sight (validating the gene ids once); False = pack it instead"""
+        ind, dat = chunk.indices, chunk.data
+        if not (self.pin_chunks and ind.dtype == np.int32 and dat.dtype == np.float32 and ind.size
+                and ind.flags.c_contiguous and dat.flags.c_contiguous and torch.device(self.device).type == "cuda"):
+            return False
+        key = (ind.ctypes.data, dat.ctypes.data, ind.size)
+        if key in self._pinned:
+            self._pinned.move_to_end(key)
+            return True
+        if int(ind.min()) < 0 or int(ind.max()) >= n_genes:
+            raise ValueError(f"gene id outside [0, {n_genes})")
+        from . import ops
+        while len(self._pinned) >= 2:
+            self._unpin(next(iter(self._pinned)))
+        ops.host_register(ind)
+        try:
+            ops.host_register(dat)
+        except RuntimeError:
+            ops.host_unregister(ind)
+            raise
+        self._pinned[key] = (ind, dat)      # (keeps the arrays alive while they are registered)
+        self.chunks_pinned += 1
+        return True
+
+    def _unpin(self, key):
+        from . import ops
+        ind, dat = self._pinned.pop(key)
+        torch.cuda.synchronize(self.device)      # transfers out of the chunk may still be in flight
+        ops.host_unregister(ind)
+        ops.host_unregister(dat)
+
+    def _ensure_capacity(self, nnz: int, n_genes: int, pinned: bool = False):
+        narrow = False if pinned else (self.narrow_col if self.narrow_col is not None else n_genes <= 65536)
         if self.stager is None or nnz > self.stager.max_nnz or narrow != self.stager.narrow:
             # a denser batch than any seen so far: new ring with head room (old blocks stay alive with the
             # tickets that reference them until their consumers are done)
@@ -286,14 +359,19 @@ class StagedCSRBatches:
             return st.get(tk), md
 
         for chunk, frame, lo, hi, n_genes in self._tasks():
-            nnz = int(chunk.indptr[hi]) - int(chunk.indptr[lo])
-            self._ensure_capacity(nnz, n_genes)
+            a = int(chunk.indptr[lo])
+            nnz = int(chunk.indptr[hi]) - a
+            pinned = self._pin(chunk, n_genes)
+            self._ensure_capacity(nnz, n_genes, pinned)
             if len(inflight) > self.ahead - 1:     # keep at most ``ahead`` batches staged in front of the consumer
                 yield hand_out()
             st = self.stager
             blk = st.reserve(hi - lo, nnz)         # slots are handed out in batch order, on this thread
             meta = frame.iloc[lo:hi].reset_index(drop=True) if frame is not None else None
-            if self._pool is not None:
+            if pinned:
+                np.subtract(chunk.indptr[lo:hi + 1], a, out=blk.crow, casting="unsafe")
+                tk = st.commit_from_chunk(blk, chunk.indices, chunk.data, a, n_genes)
+            elif self._pool is not None:
                 tk = self._pool.submit(self._pack, st, blk, chunk, lo, hi, n_genes, True)
             else:
                 tk = self._pack(st, blk, chunk, lo, hi, n_genes, False)
@@ -307,3 +385,5 @@ class StagedCSRBatches:
         if self._pool is not None:
             self._pool.shutdown(wait=True)
             self._pool = None
+        for key in list(self._pinned):
+            self._unpin(key)

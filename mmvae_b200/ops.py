@@ -352,6 +352,20 @@ def axpy(a, b, alpha):
     _check(lib().cmmvae_axpy(_ptr(a), _ptr(b), _c.c_float(alpha), _c.c_longlong(a.numel()), _stream()), "axpy")
 
 
+def tile_cols(z32, n: int, out32, out16=None):
+    """out[b, k*Z + j] = z[b, j], k < n (the concatenation of n parameter-free parallel conditional layers)"""
+    B, Z = z32.shape
+    _check(lib().cmmvae_tile_cols(_ptr(z32), B, Z, int(n), _ptr(out32), _ptr(out16), _stream()), "tile_cols")
+    return out32, out16
+
+
+def fold_cols(dcat, n: int, dz):
+    """dz[b, j] = sum_k dcat[b, k*Z + j] (backward of tile_cols)"""
+    B, Z = dz.shape
+    _check(lib().cmmvae_fold_cols(_ptr(dcat), B, Z, int(n), _ptr(dz), _stream()), "fold_cols")
+    return dz
+
+
 def widen_u16_i32(src_u16, dst_i32, n: int, stream=None):
     """dst int32[n] = src uint16[n] (gene ids travel narrow over PCIe; mmvae_b200.feed)"""
     st = _c.c_void_p(stream.cuda_stream) if stream is not None else _stream()
@@ -372,6 +386,11 @@ def host_slice_rows(indptr, indices, data, lo: int, hi: int, n_genes: int, crow_
     if n < 0:
         raise ValueError(f"host_slice_rows failed ({n}): {lib().cmmvae_last_error().decode()}")
     return int(n)
+
+
+def copy_bytes(dst: torch.Tensor, src: torch.Tensor, nbytes: int) -> None:
+    """device-to-device copy of ``nbytes`` by a kernel on the current stream (see cmmvae_copy_bytes)"""
+    _check(lib().cmmvae_copy_bytes(_ptr(dst), _ptr(src), _c.c_longlong(nbytes), _stream()), "copy_bytes")
 
 
 def host_register(arr) -> None:

@@ -84,6 +84,18 @@ class AdversarySpec:
 
 
 @dataclass
+class CondSpec:
+    """ConditionalLayers (components.py:467-631): per batch key one ConditionalLayer (components.py:317-413) holding
+    an FCBlock per metadata value -- here the one-layer block the shipped topology uses (human_only.yaml:61-68:
+    ``layers: [latent]`` -> Linear(latent, latent), components.py:115-116, + LayerNorm without affine, :277-278)."""
+    names: List[str]                          # conditionals in constructor order, "species" included
+    species_specific: List[str] = field(default_factory=list)   # batch keys whose layers sit under ModuleDict[species]
+    parallel: bool = True                     # selection_order == ["parallel"]: outputs concatenated (:617-631)
+    layer_norm: bool = True
+    relu: bool = False
+
+
+@dataclass
 class ModelSpec:
     experts: Dict[str, Dict[str, BlockSpec]]  # id -> {"encoder": BlockSpec, "decoder": BlockSpec}
     vae_encoder: BlockSpec
@@ -98,6 +110,7 @@ class ModelSpec:
     weight_decay: float = 1e-6
     betas: Sequence[float] = (0.9, 0.999)
     adam_eps: float = 1e-8
+    conditionals: Optional["CondSpec"] = None   # CLVAE.conditionals (clvae.py:42-87)
 
 
 # --------------------------------------------------------------------------------------------
@@ -328,9 +341,41 @@ def apply_group_step(P, grads: Dict[str, torch.Tensor], opt: OptState, spec: Mod
 # --------------------------------------------------------------------------------------------
 
 
+def conditional_layers(cs: CondSpec, P, x, keys: Dict[str, List[str]], species: str, order: List[str]):
+    """ConditionalLayers.forward (components.py:581-631) in the given ``order`` (the reference draws it with
+    ``random.sample`` per call when the selection is parallel or unordered, :598-600) with ConditionalLayer.forward
+    (components.py:369-413: rows grouped by their metadata value, each group through that value's block, results
+    written back in the original row order).  ``keys``: batch key -> formatted condition key of every row."""
+    def block(h, prefix):
+        h = h @ P[f"{prefix}.fc_layers.0.lin.weight"].t() + P[f"{prefix}.fc_layers.0.lin.bias"]
+        if cs.layer_norm:
+            h = torch.nn.functional.layer_norm(h, h.shape[-1:])
+        return torch.relu(h) if cs.relu else h
+
+    branches = []
+    for bk in order:
+        if bk == "species":
+            y = block(x, f"vae.conditionals.layers.species.{species}")
+        else:
+            base = f"vae.conditionals.layers.{bk}" + (f".{species}" if bk in cs.species_specific else "")
+            groups: Dict[str, List[int]] = {}
+            for i, k in enumerate(keys[bk]):
+                groups.setdefault(k, []).append(i)
+            y = torch.zeros(x.shape[0], P[f"{base}.conditions.{keys[bk][0]}.fc_layers.0.lin.weight"].shape[0])
+            for k, rows in groups.items():
+                idx = torch.tensor(rows)
+                y = y.index_copy(0, idx, block(x.index_select(0, idx), f"{base}.conditions.{k}"))
+        if cs.parallel:
+            branches.append(y)
+        else:
+            x = y
+    return torch.cat(branches, dim=1) if branches else x
+
+
 def forward(spec: ModelSpec, P, expert_id, csr, n_genes, eps_noise, training, new_buffers,
-            dropout_masks=None):
-    """CMMVAE.forward (cmmvae.py:85-113) + BaseVAE.forward (vae.py:98-102), no conditionals."""
+            dropout_masks=None, cond=None):
+    """CMMVAE.forward (cmmvae.py:85-113) + BaseVAE.forward (vae.py:98-102).  ``cond`` (with ``spec.conditionals``):
+    dict(keys=..., order=...) for CLVAE.after_reparameterize (clvae.py:89-111)."""
     ex = spec.experts[expert_id]
     s, _ = fcblock(None, ex["encoder"], f"experts.{expert_id}.encoder", P, training, new_buffers,
                    dropout_masks, csr=csr)
@@ -338,9 +383,12 @@ def forward(spec: ModelSpec, P, expert_id, csr, n_genes, eps_noise, training, ne
     mu, sigma, z = latent_head(q, P, "vae.encoder", eps_noise, spec.var_eps)
     if spec.hidden_z:
         hidden = hidden + [z]
-    d, _ = fcblock(z, spec.vae_decoder, "vae.decoder", P, training, new_buffers, dropout_masks)
+    zc = z
+    if spec.conditionals is not None:
+        zc = conditional_layers(spec.conditionals, P, z, cond["keys"], expert_id, cond["order"])
+    d, _ = fcblock(zc, spec.vae_decoder, "vae.decoder", P, training, new_buffers, dropout_masks)
     xhat, _ = fcblock(d, ex["decoder"], f"experts.{expert_id}.decoder", P, training, new_buffers, dropout_masks)
-    return mu, sigma, z, xhat, hidden
+    return mu, sigma, zc, xhat, hidden      # (vae.py:98-102 returns z AFTER after_reparameterize)
 
 
 def elbo(mu, sigma, x_dense, xhat, kl_weight):
@@ -368,7 +416,7 @@ def adversary_losses(spec: ModelSpec, P, hidden, labels, detach, new_buffers):
 
 def train_step(spec: ModelSpec, P: Dict[str, torch.Tensor], opt: Dict[str, OptState], expert_id: str,
                crow, col, val, eps_noise, kl_weight: float, labels: Optional[Dict[str, torch.Tensor]] = None,
-               dropout_masks=None, return_grads: bool = True):
+               dropout_masks=None, return_grads: bool = True, cond=None):
     """One CMMVAEModel.training_step (cmmvae_model.py:138-217) on state ``P`` (updated in place).
 
     Returns a dict: logs (exact reference keys, untagged), grads (pre-clip), z.
@@ -385,7 +433,7 @@ def train_step(spec: ModelSpec, P: Dict[str, torch.Tensor], opt: Dict[str, OptSt
         P[n] = P[n].detach().requires_grad_(True)
 
     mu, sigma, z, xhat, hidden = forward(spec, P, expert_id, csr, n_genes, eps_noise, True, new_buffers,
-                                         dropout_masks)
+                                         dropout_masks, cond=cond)
     ld = elbo(mu, sigma, x_dense, xhat, kl_weight)
     logs["recon_loss"] = float(ld["recon_loss"])
     logs["kl_loss"] = float(ld["kl_loss"])
@@ -445,12 +493,13 @@ def train_step(spec: ModelSpec, P: Dict[str, torch.Tensor], opt: Dict[str, OptSt
     return {"logs": logs, "grads": grads_out, "z": z.detach(), "mu": mu.detach(), "sigma": sigma.detach()}
 
 
-def eval_step(spec: ModelSpec, P, expert_id, crow, col, val, eps_noise, kl_weight):
+def eval_step(spec: ModelSpec, P, expert_id, crow, col, val, eps_noise, kl_weight, cond=None):
     """CMMVAEModel.validation_step (cmmvae_model.py:219-245): eval-mode forward + ELBO."""
     n_genes = spec.experts[expert_id]["encoder"].layers[0]
     x_dense = csr_to_dense(crow, col, val, n_genes)
     with torch.no_grad():
-        mu, sigma, z, xhat, hidden = forward(spec, P, expert_id, (crow, col, val), n_genes, eps_noise, False, {})
+        mu, sigma, z, xhat, hidden = forward(spec, P, expert_id, (crow, col, val), n_genes, eps_noise, False, {},
+                                             cond=cond)
         ld = elbo(mu, sigma, x_dense, xhat, kl_weight)
     return {"logs": {k: float(v) for k, v in ld.items()}, "z": z, "xhat": xhat, "mu": mu, "sigma": sigma}
 

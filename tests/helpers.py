@@ -8,6 +8,7 @@ from oracle import cmmvae_oracle as O
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CONDITIONS = {"assay": 5, "dataset_id": 11}
+COND_NAMES = ("assay", "dataset_id", "species")      # conditional layers of the human_conditional case
 
 
 class GoldenCase:
@@ -47,11 +48,30 @@ class GoldenCase:
         if self.with_adv:
             for enc in ([d["Hv"], 24, 16], [d["Z"], 16]):
                 advs.append(O.AdversarySpec(O.BlockSpec.make(enc), dict(CONDITIONS)))
+        # make_golden.py: conditionals = [assay (shared), dataset_id (per species), species], parallel selection
+        n_cond = len(COND_NAMES) if self.conditional else 1
+        dec = [d["Z"], d["Hv"], d["H2"]]
         return O.ModelSpec(
             experts=experts,
             vae_encoder=O.BlockSpec.make([d["H2"], d["Hv"]], bn=True, return_hidden=True),
-            vae_decoder=O.BlockSpec.make([d["Z"], d["Hv"], d["H2"]]),
-            latent_dim=d["Z"], hidden_z=self.with_adv, adversarials=advs, adv_weight=self.adv_weight)
+            vae_decoder=O.BlockSpec.make(([n_cond * d["Z"]] if n_cond > 1 else []) + dec),
+            latent_dim=d["Z"], hidden_z=self.with_adv, adversarials=advs, adv_weight=self.adv_weight,
+            conditionals=O.CondSpec(names=list(COND_NAMES), species_specific=["dataset_id"])
+            if self.conditional else None)
+
+    def cond(self, s, seed):
+        """what the reference's ConditionalLayers.forward saw for step record ``s``: the formatted condition key of
+        every row and the order it drew after ``random.seed(seed)`` (make_golden.py)"""
+        import random
+        if not self.conditional:
+            return None
+        random.seed(seed)
+        order = random.sample(list(COND_NAMES), len(COND_NAMES))
+        if "labels" in s:
+            keys = {c: [f"{c}_{int(i)}" for i in s["labels"][c]] for c in CONDITIONS}
+        else:       # the validation record: every row carries value 0 (make_golden.py)
+            keys = {c: [f"{c}_0"] * self.dims["B"] for c in CONDITIONS}
+        return dict(keys=keys, order=order)
 
     def step(self, t):
         p = f"step{t}/" if t != "val" else "val/"

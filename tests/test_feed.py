@@ -246,3 +246,52 @@ def test_staged_batches_narrow_columns_and_worker_threads(workers):
         assert x.col_indices().dtype == torch.int32
         np.testing.assert_array_equal(x.values().numpy().view(np.uint32), ref.data.view(np.uint32))
         assert list(meta["cell"]) == list(fref["cell"])
+
+
+@pytest.mark.gpu
+def test_pinned_chunks_route_ships_the_same_batches_without_a_host_pass():
+    """pin_chunks=True: every chunk is page-locked in place once and its batches are DMA'd straight out of the
+    chunk's own indices / data arrays -- same tensors as scipy's chunk[lo:hi], bit for bit, over chunk changes"""
+    from mmvae_b200.feed import StagedCSRBatches
+    bs = 16
+    chunks = _chunks(4, [64, 48, 80, 32], G=911)
+    feed = StagedCSRBatches(chunks, bs, device="cuda", pin_chunks=True)
+    n = 0
+    it = iter(feed)
+    for m, frame in chunks:
+        for i in range(0, m.shape[0], bs):
+            b = m[i:i + bs]
+            x, meta = next(it)
+            torch.cuda.synchronize()
+            n += 1
+            assert x.is_cuda and tuple(x.shape) == b.shape
+            np.testing.assert_array_equal(x.crow_indices().cpu().numpy(), b.indptr)
+            np.testing.assert_array_equal(x.col_indices().cpu().numpy(), b.indices)
+            np.testing.assert_array_equal(x.values().cpu().numpy().view(np.uint32), b.data.view(np.uint32))
+            assert meta.equals(frame.iloc[i:i + bs].reset_index(drop=True))
+    assert next(it, None) is None and n == 14
+    assert feed.chunks_pinned == 4 and len(feed._pinned) == 2        # LRU of two registered chunks
+    feed.close()
+    assert not feed._pinned
+    bad = _chunks(1, [32], G=911)
+    bad[0][0].indices[5] = 911
+    with pytest.raises(ValueError, match="gene id"):
+        next(iter(StagedCSRBatches(bad, bs, device="cuda", pin_chunks=True)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [0, 1, 7, 8, 4099, 1 << 20])
+def test_device_feed_kernels_widen_and_copy(n):
+    """cmmvae_widen_u16_i32 (narrow gene ids -> int32 in HBM) and cmmvae_copy_bytes (kernel copy to the fixed
+    addresses the step's graphs read), all lengths incl. the non-multiple-of-16-byte tails"""
+    from mmvae_b200 import ops
+    g = torch.Generator().manual_seed(n)
+    src = torch.randint(0, 65536, (n + 8,), generator=g, dtype=torch.int32)
+    u16 = src.to(torch.uint16).cuda()
+    out = torch.full((n + 8,), -1, dtype=torch.int32, device="cuda")
+    ops.widen_u16_i32(u16, out, n)
+    assert torch.equal(out[:n].cpu(), src[:n]) and bool((out[n:] == -1).all())
+    a = torch.randint(0, 256, (4 * n + 19,), generator=g, dtype=torch.uint8).cuda()
+    b = torch.zeros_like(a)
+    ops.copy_bytes(b, a, 4 * n + 3)
+    assert torch.equal(b[:4 * n + 3], a[:4 * n + 3]) and not bool(b[4 * n + 3:].any())

@@ -7,7 +7,7 @@ import torch
 from helpers import GoldenCase, rel_l2, untag
 from oracle import cmmvae_oracle as O
 
-CASES = ["core_human", "two_species_adv"]
+CASES = ["core_human", "two_species_adv", "human_conditional"]
 
 
 def bias_feeds_batchnorm(name, state):
@@ -22,7 +22,7 @@ def test_oracle_reproduces_reference_training(name):
     for t in range(gc.n_steps):
         s = gc.step(t)
         out = O.train_step(spec, P, opt, s["species"], s["crow"], s["col"], s["val"], s["eps"], s["kl_weight"],
-                           labels=s["labels"] if gc.with_adv else None)
+                           labels=s["labels"] if gc.with_adv else None, cond=gc.cond(s, 4242 + t))
         ref_logs = untag(s["logs"], s["species"])
         assert set(ref_logs) == set(out["logs"]), (sorted(ref_logs), sorted(out["logs"]))
         for k, v in ref_logs.items():
@@ -56,7 +56,7 @@ def test_oracle_reproduces_reference_validation(name):
     gc = GoldenCase(name)
     s = gc.step("val")
     out = O.eval_step(gc.spec(), gc.state("final"), s["species"], s["crow"], s["col"], s["val"], s["eps"],
-                      kl_weight=untag(s["logs"], s["species"], "validation")["kl_weight"])
+                      kl_weight=untag(s["logs"], s["species"], "validation")["kl_weight"], cond=gc.cond(s, 777))
     ref = untag(s["logs"], s["species"], "validation")
     for k in ("loss", "recon_loss", "kl_loss"):
         assert out["logs"][k] == pytest.approx(ref[k], rel=1e-5)

@@ -1,0 +1,6 @@
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/t_all.log 2>&1
+grep -E "passed|failed|^E  |^FAILED" gpurun_out/t_all.log | cut -c1-300 | head -30
+BENCH_WATCHDOG=400 timeout 500 python bench.py 2>gpurun_out/bench1_err.log | tee gpurun_out/bench_r2_1.json | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('N', d['n_gpus'], {k:round(d[k],3) for k in ('value','ms_per_step')}, 'e2e', {k:v for k,v in d['e2e'].items() if k!='host_side'}); print(d['roofline']); print(d.get('cpu_baseline')); print(d.get('torch_cuda_baseline')); print(d.get('parity_check',{}).get('rel_err'))"
+grep -E "Error|Traceback" -A8 gpurun_out/bench1_err.log | head -30
