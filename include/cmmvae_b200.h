@@ -297,10 +297,35 @@ int cmmvae_csr_tile_ptr_rows(const int32_t* row_begin, const int32_t* row_end, c
 int cmmvae_dp_scalars(const double* slabs, int n_src, int stride, int rank, double* out_recon, double* out_norm,
                       void* stream);
 
-/* ---- parallel conditional layers without parameters (configs/model/human_only.yaml:53-79; ConditionalLayers.forward,
- * components.py:617-631, with FCBlocks of zero layers, components.py:217-232): out[b, k*Z + j] = z[b, j] for
- * k < n (fp32 and optionally bf16), and its backward dz[b, j] = sum_k dcat[b, k*Z + j] */
-int cmmvae_tile_cols(const float* z, int B, int Z, int n, float* out_f32, void* out_bf16, void* stream);
+/* ---- conditional layers on the latent ------------------------------------------------------
+ * ConditionalLayer.forward (components.py:369-413) sends every cell through the FCBlock of its metadata value;
+ * ConditionalLayers.forward (components.py:581-631) chains the batch keys or concatenates their outputs.  Blocks are
+ * the shipped one-layer kind (configs/model/human_only.yaml:61-68): Linear(Zin, Zout) [+ LayerNorm without affine,
+ * eps 1e-5] [+ ReLU].  All blocks live in one parameter bank: slot s at params + s * slot_stride = [W (Zout x Zin,
+ * torch layout) | b (Zout)]; grads / m / v alike.  The host sorts the rows of the batch by value:
+ *   tiles  int32[n_tiles][4] = (slot, start into rows, count <= 32, index c of the batch key)
+ *   rows   int32: cell indices, grouped as the tiles say
+ * fwd:  out[row, out_col[c] + j] = act(LN(x[row, :] W_s^T + b_s)) (fp32, optional bf16 copy), pre = LN output,
+ *       rstd[c * B + row]
+ * bwd:  grads (pre-zeroed for the slots present) += dW_s, db_s;  dx[row, dx_col[c] + k] = (dy W_s)[row, k]
+ * zero_grads / sumsq / adam run over the slots PRESENT in the batch only: torch.optim.Adam skips parameters whose
+ * grad is None (unused modules after zero_grad(set_to_none=True)), so every slot carries its own step count
+ * (steps[slot], advanced by cond_adam); sumsq ADDS the present slots' share to the group's clip norm. */
+int cmmvae_cond_fwd(const float* params, long long slot_stride, int Zin, int Zout, const int32_t* tiles, int n_tiles,
+                    const int32_t* rows, const float* x, int ldx, float* out, void* out_bf16, float* pre, int ldo,
+                    const int32_t* out_col, float* rstd, int B, int layer_norm, int relu, void* stream);
+int cmmvae_cond_bwd(const float* params, float* grads, long long slot_stride, int Zin, int Zout, const int32_t* tiles,
+                    int n_tiles, const int32_t* rows, const float* x, int ldx, const float* dout, const float* pre,
+                    int ldo, const int32_t* out_col, const float* rstd, int B, float* dx, int lddx,
+                    const int32_t* dx_col, int layer_norm, int relu, void* stream);
+int cmmvae_cond_zero_grads(float* grads, long long slot_stride, const int32_t* present, int n_present, void* stream);
+int cmmvae_cond_sumsq(const float* grads, long long slot_stride, const int32_t* present, int n_present, double* out,
+                      void* stream);
+int cmmvae_cond_adam(float* params, const float* grads, float* m, float* v, long long slot_stride,
+                     const int32_t* present, int n_present, int32_t* steps, const double* norm_sq, float max_norm,
+                     float grad_scale, float lr, double beta1, double beta2, float eps, float weight_decay,
+                     void* stream);
+/* dz[b, j] = sum_k dcat[b, k*Z + j]: the gradients of the n parallel branches, which all read z, add up */
 int cmmvae_fold_cols(const float* dcat, int B, int Z, int n, float* dz, void* stream);
 
 /* ---- host -> HBM feed of CSR batches (batch format of cellxgene_datapipe.py:169-193) ---------

@@ -591,25 +591,9 @@ __global__ void axpy_kernel(float* __restrict__ a, const float* __restrict__ b, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// parallel conditional layers without parameters (configs/model/human_only.yaml:53-79: conditional_config.layers =
-// [128] builds FCBlocks with NO layer, components.py:217-232, so every ConditionalLayer is the identity and
-// ConditionalLayers.forward, components.py:617-631, concatenates n copies of z):  zcat[b, k*Z + j] = z[b, j], and in
-// the backward pass dz[b, j] = sum_k dzcat[b, k*Z + j]
+// parallel conditional layers (ConditionalLayers.forward, components.py:617-631): every branch reads z, so in the
+// backward pass dz[b, j] = sum_k dcat[b, k*Z + j] over the branches' input gradients
 // ---------------------------------------------------------------------------------------------
-__global__ void tile_cols_kernel(const float* __restrict__ z, int Z, int n, long long total, float* __restrict__ out32,
-                                 __nv_bfloat16* __restrict__ out16) {
-  pdl_sync();
-  const int W = Z * n;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long b = i / W;
-    const int j = (int)(i - b * W) % Z;
-    const float v = z[b * Z + j];
-    out32[i] = v;
-    if (out16) out16[i] = __float2bfloat16(v);
-  }
-}
-
 __global__ void fold_cols_kernel(const float* __restrict__ dcat, int Z, int n, long long total,
                                  float* __restrict__ dz) {
   pdl_sync();
@@ -941,14 +925,6 @@ extern "C" int cmmvae_axpy(float* a, const float* b, float alpha, long long n, v
   if (n <= 0) return 0;
   launch_pdl(axpy_kernel, dim3(ew_blocks(n)), dim3(256), 0, (cudaStream_t)stream, a, b, alpha, n);
   return check_launch("axpy");
-}
-
-extern "C" int cmmvae_tile_cols(const float* z, int B, int Z, int n, float* out_f32, void* out_bf16, void* stream) {
-  CMMVAE_REQUIRE(z && out_f32 && B > 0 && Z > 0 && n > 0, "tile_cols: bad arguments");
-  const long long total = (long long)B * Z * n;
-  launch_pdl(tile_cols_kernel, dim3(ew_blocks(total)), dim3(256), 0, (cudaStream_t)stream, z, Z, n, total, out_f32,
-             (__nv_bfloat16*)out_bf16);
-  return check_launch("tile_cols");
 }
 
 extern "C" int cmmvae_fold_cols(const float* dcat, int B, int Z, int n, float* dz, void* stream) {

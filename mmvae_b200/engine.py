@@ -345,10 +345,14 @@ class FlatAdam(torch.optim.Optimizer):
     ``state_dict`` / ``load_state_dict`` speak torch.optim.Adam's format (``step``, ``exp_avg``,
     ``exp_avg_sq`` per parameter, in the parameter's logical shape), so checkpoints resume with their moments."""
 
-    def __init__(self, group: FlatGroup):
+    def __init__(self, group: FlatGroup, bank=None):
+        """``bank``: a ``mmvae_b200.conditional.CondBank`` stepped with this group (the conditional layers belong to
+        the VAE's optimizer, cmmvae_model.py:311); its parameters follow the group's, each slot with its own step"""
         self.flat = group
+        self.bank = bank
         self._max_norm = None
-        super().__init__(group.params, dict(lr=group.lr, weight_decay=group.wd, betas=group.betas, eps=group.eps))
+        super().__init__(group.params + (bank.params if bank is not None else []),
+                         dict(lr=group.lr, weight_decay=group.wd, betas=group.betas, eps=group.eps))
 
     def set_clip(self, max_norm: Optional[float]):
         self._max_norm = max_norm
@@ -360,6 +364,9 @@ class FlatAdam(torch.optim.Optimizer):
             return
         if self.flat.world > 1:
             raise NotImplementedError("with torch.distributed the exchange + step run inside training_step")
+        if self.bank is not None:
+            raise NotImplementedError("conditional layers are stepped inside training_step (values present in the "
+                                      "batch only)")
         ns = torch.zeros(1, dtype=torch.float64, device=self.flat.p.device)
         self.flat.grad_norm_sq(ns)
         self.flat.clip_adam(ns, self._max_norm)
@@ -378,8 +385,12 @@ class FlatAdam(torch.optim.Optimizer):
             for i, p in enumerate(g.params):
                 state[i] = {"step": torch.tensor(float(g.step_count)),
                             "exp_avg": g.logical(p, m_full).clone(), "exp_avg_sq": g.logical(p, v_full).clone()}
+        n_all = len(g.params)
+        if self.bank is not None:
+            state.update(self.bank.state_entries(len(g.params)))
+            n_all += len(self.bank.params)
         pg = dict(self.param_groups[0])
-        pg["params"] = list(range(len(g.params)))
+        pg["params"] = list(range(n_all))
         return {"state": state, "param_groups": [pg]}
 
     def load_state_dict(self, sd):
@@ -400,6 +411,8 @@ class FlatAdam(torch.optim.Optimizer):
             raise ValueError(f"FlatAdam steps a whole group together; checkpoint holds steps {sorted(steps)}")
         g.step_count = steps.pop() if steps else 0
         g.store_moments(m_full, v_full)
+        if self.bank is not None:
+            self.bank.load_state_entries(state, len(g.params))
         for k, v in (sd.get("param_groups") or [{}])[0].items():
             if k in ("lr", "weight_decay", "betas", "eps"):
                 self.param_groups[0][k] = v
@@ -521,28 +534,24 @@ class StepEngine:
         self.adv_weight = adv_weight
         self.clip = clip or {"vae": 10.0, "expert": 10.0, "adversarial": 10.0}
         vae = module.vae
-        # conditional layers.  The topology the reference ships (configs/model/human_only.yaml:53-79)
-        # configures them with ``layers: [latent]``: FCBlocks without a single layer (components.py:217-232), so every
-        # ConditionalLayer is the identity; "parallel" selection concatenates one copy of z per conditional
-        # (components.py:617-631) in front of the extra "concat" decoder layer (clvae.py:55-79).  That is what the
-        # fused step runs (n copies of z, folded again in the backward pass).  Conditional blocks WITH parameters
-        # (one Linear + LayerNorm per metadata value) stay on the module route.
-        self.cond_copies, self.cond_shuffle = 1, None
-        cond = getattr(vae, "conditionals", None)
-        if cond:
-            blocks = [m for m in cond.modules() if hasattr(m, "fc_layers")]
-            if any(len(b.fc_layers) for b in blocks):
-                raise UnsupportedTopology("conditional layers with parameters are outside the fused step "
-                                          "(SURVEY.md 8f-1); parameter-free ones (human_only.yaml) are fused")
-            if cond.is_parallel:
-                self.cond_copies = len(cond.selection_order)
-            if cond.shuffle_selection_order:
-                self.cond_shuffle = list(cond.selection_order)
+        # conditional layers on z: one Linear [+ LayerNorm] block per metadata value, run by
+        # mmvae_b200.conditional.CondBank (grouped by value on the host, one launch per direction, Adam on the
+        # values present in the batch only).  Built below, once the module sits on the device.
+        cond = getattr(vae, "conditionals", None) or None
+        if cond is not None and self.comm is not None:
+            raise UnsupportedTopology("conditional layers are not part of the data-parallel route (SURVEY.md 8f-1)")
+        self.cond = None
         enc = vae.encoder
         if isinstance(enc.z_transformation, nn.Softmax):
             raise UnsupportedTopology("distribution='ln' is outside the fused step")
         module.to(self.device)   # buffers (BN running stats) and not-yet-flattened params
         dev = self.device
+        if cond is not None:
+            from .conditional import CondBank, CondUnsupported
+            try:
+                self.cond = CondBank(cond, dev)
+            except CondUnsupported as why:
+                raise UnsupportedTopology(str(why))
         # ---- optimizer groups as flat buffers (order mirrors configure_optimizers) ----
         self.groups: Dict[str, FlatGroup] = {}
         self.enc_plan: Dict[str, List[LayerPlan]] = {}
@@ -571,6 +580,7 @@ class StepEngine:
         chains.append([(enc.mean_encoder.bias, False), (enc.var_encoder.bias, False)])
         chains += _block_chains(vae.decoder)
         listed = {id(p) for c in chains for p, _ in c}
+        listed |= {id(p) for p in (self.cond.params if self.cond else [])}
         extra = [p for p in vae.parameters() if id(p) not in listed]
         if extra:
             raise UnsupportedTopology("VAE has parameters outside encoder/decoder")
@@ -1246,29 +1256,24 @@ class StepEngine:
         ops.dp_scalars(d["scal"].local.view(torch.float64), N, SC, r, sc[0:1], s_norm_expert)
 
     def _after_reparameterize(self, z32, z16, B: int):
-        """CLVAE.after_reparameterize (clvae.py:89-111) for parameter-free conditional layers: identity, or -- parallel
-        selection -- one copy of z per conditional side by side"""
-        if self.cond_shuffle is not None:
-            # ConditionalLayers.forward draws a fresh order with Python's ``random`` on every call
-            # (components.py:598-600); identical copies make the order irrelevant, the draw keeps the host's
-            # generator where the reference leaves it
-            random.sample(self.cond_shuffle, len(self.cond_shuffle))
-        n = self.cond_copies
-        if n == 1:
+        """CLVAE.after_reparameterize (clvae.py:89-111): identity, or the conditional layers (whose host plan for
+        this batch was made at the start of the step)"""
+        if self.cond is None:
             return z32, z16
-        Z = z32.shape[1]
-        c32 = self.ws("zcat32", (B, n * Z))
-        c16 = self.ws("zcat16", (B, n * Z), torch.bfloat16) if z16 is not None else None
-        ops.tile_cols(z32, n, c32, c16)
-        return c32, c16
+        return self.cond.forward(z32, self.ws, z16 is not None)
 
     # ----------------------------------------------------------------------------------------- step
     def train_step(self, expert_id: str, crow, col, val, nnz: int, kl_weight: float, eps=None,
-                   labels: Optional[Dict[str, torch.Tensor]] = None, masks=None, nnz_cap: Optional[int] = None):
+                   labels: Optional[Dict[str, torch.Tensor]] = None, masks=None, nnz_cap: Optional[int] = None,
+                   metadata=None):
         """One optimisation step on a CSR batch already resident on the device (no host sync).
         Returns the step record (device scalar block etc.) for ``scalars()``.  With ``use_graph`` (pipelined mode,
         single process) the step is replayed from captured CUDA graphs; ``nnz_cap`` (optional) = the densest batch
         to size the graph's input buffers for."""
+        if self.cond is not None:
+            if metadata is None:
+                raise ValueError("conditional layers need the batch's metadata")
+            self.cond.make_plan(metadata, expert_id, crow.numel() - 1)    # host: rows grouped by value, one H2D copy
         if self.pipeline_optimizer:
             if self._hp is None:
                 lo_pri, hi_pri = torch.cuda.Stream.priority_range()
@@ -1277,7 +1282,7 @@ class StepEngine:
             cur = torch.cuda.current_stream()
             self._hp.wait_stream(cur)
             with torch.cuda.stream(self._hp), ops.stream_scope(self._hp):
-                graphable = (self.use_graph and masks is None and self.timers is None
+                graphable = (self.use_graph and masks is None and self.timers is None and self.cond is None
                              and self.precision == "bf16" and not L._mask_queue)
                 if graphable:
                     rec = self._graph_step(expert_id, crow, col, val, nnz, kl_weight, eps, labels, nnz_cap)
@@ -1520,6 +1525,7 @@ class StepEngine:
         if self.hidden_z:
             hidden.append(("z", 0, z32, z16))
         x32, x16 = self._after_reparameterize(z32, z16, B)
+        z_out = x32
         for j, lp in enumerate(self.vaedec_plan):
             x32, x16, caches[("vdec", j)] = self._layer_fwd(f"vdec{j}", lp, x32, x16, B, masks=masks)
         for j, lp in enumerate(dec[:-1]):
@@ -1613,10 +1619,7 @@ class StepEngine:
             d = self._layer_bwd(f"dec{j}", dec[j], caches[("dec", j)], d, B)
         for j in reversed(range(len(self.vaedec_plan))):
             d = self._layer_bwd(f"vdec{j}", self.vaedec_plan[j], caches[("vdec", j)], d, B)
-        if self.cond_copies > 1:      # backward of the concatenation: the copies' gradients add up
-            dz = ops.fold_cols(d, self.cond_copies, self.ws("dz_fold", (B, Z)))
-        else:
-            dz = d
+        dz = self.cond.backward(d, self.ws) if self.cond is not None else d
         for i in range(n_adv):
             if hidden[i][0] == "z":
                 ops.axpy(dz, d_hidden[i], -1.0)                            # GRL: -alpha * grad, alpha = 1
@@ -1679,15 +1682,19 @@ class StepEngine:
             sc[-2:].copy_(dpm["info"])
         else:
             gvae.grad_norm_sq(s_norm(0))
+            if self.cond is not None:       # same optimizer as the VAE (cmmvae_model.py:311): one clip norm
+                self.cond.add_norm_sq(s_norm(0))
             gexp.grad_norm_sq(s_norm(1), skip=[enc[0].lin.weight, out.lin.weight] if fuse_norm else None)
         bg = self._bg if self.pipeline_optimizer else None
         gvae.clip_adam(s_norm(0), self.clip.get("vae"), gscale, advance=self._gmode is None)
+        if self.cond is not None:
+            self.cond.clip_adam(s_norm(0), self.clip.get("vae"), gscale)
         launch_bg = gexp.clip_adam(s_norm(1), self.clip.get("expert"), gscale, background=bg,
                                    defer_background=capturing, advance=self._gmode is None)
         self._t1(ev)
 
         self.last = dict(sc=sc, B=B, Z=Z, kl_weight=float(kl_weight), expert_id=expert_id, n_adv=n_adv,
-                         gscale=gscale, ce_base=ce_base, z=z32, dl=dl, dp=dpm is not None,
+                         gscale=gscale, ce_base=ce_base, z=z_out, dl=dl, dp=dpm is not None,
                          od_slot=od_slot if od is not None else None)
         if launch_bg is not None:
             self.last["launch_bg"] = launch_bg
@@ -1744,12 +1751,16 @@ class StepEngine:
 
     # ------------------------------------------------------------------------------- eval forward
     @torch.no_grad()
-    def eval_step(self, expert_id: str, crow, col, val, eps=None, kl_weight: float = 1.0):
+    def eval_step(self, expert_id: str, crow, col, val, eps=None, kl_weight: float = 1.0, metadata=None):
         """validation_step arithmetic (cmmvae_model.py:219-245): eval-mode forward + ELBO on the fused
         decoder path.  Returns the scalar record (use ``scalars``-like host read via ``eval_scalars``)."""
         enc, dec = self.enc_plan[expert_id], self.dec_plan[expert_id]
         B, G, Z = crow.numel() - 1, enc[0].K, self.Z
         bf = self.precision == "bf16"
+        if self.cond is not None:
+            if metadata is None:
+                raise ValueError("conditional layers need the batch's metadata")
+            self.cond.make_plan(metadata, expert_id, B)
         self.groups[f"experts/{expert_id}"].sync_master()   # joins a background update; data parallel: gathers the rows
         sc = torch.zeros(4, dtype=torch.float64, device=self.device)
         x32 = x16 = None
@@ -1769,6 +1780,7 @@ class StepEngine:
         z16 = self.ws("z16", (B, Z), torch.bfloat16) if bf else None
         ops.reparam_kl_fwd(ML, eps, Z, self.var_eps, z32, z16, sc[1:4])
         x32, x16 = self._after_reparameterize(z32, z16, B)
+        z_out = x32          # (vae.py:98-102 returns z AFTER after_reparameterize)
         for j, lp in enumerate(self.vaedec_plan):
             x32, x16, _ = self._layer_fwd(f"vdec{j}", lp, x32, x16, B, training=False)
         for j, lp in enumerate(dec[:-1]):
@@ -1785,4 +1797,4 @@ class StepEngine:
         s = sc.cpu().tolist()
         kl = s[1] / B
         return {"loss": s[0] + kl_weight * kl, "recon_loss": s[0], "kl_loss": kl, "kl_weight": kl_weight,
-                "z": z32}
+                "z": z_out}

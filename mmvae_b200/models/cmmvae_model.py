@@ -64,6 +64,9 @@ class CMMVAEModel(BaseModel):
         # pipelined mode + batches from mmvae_b200.feed (fixed addresses per ring slot): the step is replayed from
         # captured CUDA graphs
         self.use_cuda_graphs = True
+        # False: train through the module route (the same kernels under autograd) even when the fused engine
+        # covers the topology
+        self.use_fused_engine = True
         self._pending_log = None
         self._label_ring = {}    # (n conditions, B) -> [pinned blocks, events of their last copy, next slot]
 
@@ -80,8 +83,12 @@ class CMMVAEModel(BaseModel):
         return float(val)
 
     def engine(self) -> Optional[StepEngine]:
-        """The fused step engine, or None when the topology is outside it (conditional layers, LayerNorm,
-        non-ReLU activations): those models train through the module route (same kernels under autograd)."""
+        """The fused step engine, or None when the topology is outside it (LayerNorm / non-ReLU activations in the
+        main blocks, conditional blocks other than Linear [+ LayerNorm] [+ ReLU]): those models train through the
+        module route (same kernels under autograd)."""
+        if self._engine is None and not self.use_fused_engine:
+            self._engine = False
+            self._module_route_reason = "use_fused_engine is off"
         if self._engine is None:
             ac = self.autograd_config
             clip = {"vae": self._clip_val(ac.vae_gradient_clip), "expert": self._clip_val(ac.expert_gradient_clip),
@@ -104,7 +111,7 @@ class CMMVAEModel(BaseModel):
         if eng is None:
             return self._configure_optimizers_module_route()
         optim_dict = {"experts": {eid: FlatAdam(eng.groups[f"experts/{eid}"]) for eid in self.module.experts.keys()},
-                      "vae": FlatAdam(eng.groups["vae"])}
+                      "vae": FlatAdam(eng.groups["vae"], bank=eng.cond)}
         if len(self.module.adversarials):
             optim_dict["adversarials"] = {i: FlatAdam(eng.groups[f"adversarials/{i}"])
                                           for i in range(1, len(self.module.adversarials) + 1)}
@@ -288,7 +295,8 @@ class CMMVAEModel(BaseModel):
         eng.pipeline_optimizer = not self.sync_logging    # pipelined mode: results (logs, output-layer update) trail
         eng.use_graph = eng.pipeline_optimizer and self.use_cuda_graphs
         rec = eng.train_step(expert_id, crow, col, val, nnz, self.kl_annealing_fn.kl_weight, labels=labels,
-                             nnz_cap=getattr(x, "_cmmvae_cap", None))
+                             nnz_cap=getattr(x, "_cmmvae_cap", None),
+                             metadata=metadata if eng.cond is not None else None)
         self._mark_stepped(expert_id, rec["n_adv"])
         self.kl_annealing_fn.step()
         if self.sync_logging:
@@ -340,7 +348,8 @@ class CMMVAEModel(BaseModel):
                 loss_dict = self.module.vae.elbo(qz, pz, x, xhats[expert_id], self.kl_annealing_fn.kl_weight)
         else:
             crow, col, val, _ = self._csr(x)
-            out = self.engine().eval_step(expert_id, crow, col, val, kl_weight=self.kl_annealing_fn.kl_weight)
+            out = self.engine().eval_step(expert_id, crow, col, val, kl_weight=self.kl_annealing_fn.kl_weight,
+                                          metadata=metadata)
             loss_dict = {k: out[k] for k in (RK.LOSS, RK.RECON_LOSS, RK.KL_LOSS, RK.KL_WEIGHT)}
         self.auto_log(loss_dict, tags=[self.stage_name, expert_id])
         if self.trainer.validating:

@@ -352,18 +352,42 @@ def axpy(a, b, alpha):
     _check(lib().cmmvae_axpy(_ptr(a), _ptr(b), _c.c_float(alpha), _c.c_longlong(a.numel()), _stream()), "axpy")
 
 
-def tile_cols(z32, n: int, out32, out16=None):
-    """out[b, k*Z + j] = z[b, j], k < n (the concatenation of n parameter-free parallel conditional layers)"""
-    B, Z = z32.shape
-    _check(lib().cmmvae_tile_cols(_ptr(z32), B, Z, int(n), _ptr(out32), _ptr(out16), _stream()), "tile_cols")
-    return out32, out16
-
-
 def fold_cols(dcat, n: int, dz):
     """dz[b, j] = sum_k dcat[b, k*Z + j] (backward of tile_cols)"""
     B, Z = dz.shape
     _check(lib().cmmvae_fold_cols(_ptr(dcat), B, Z, int(n), _ptr(dz), _stream()), "fold_cols")
     return dz
+
+
+def cond_fwd(params, S, Zin, Zout, tiles, n_tiles, rows, x, ldx, out, out16, pre, ldo, out_col, rstd, B, layer_norm, relu):
+    _check(lib().cmmvae_cond_fwd(_ptr(params), _c.c_longlong(S), Zin, Zout, _ptr(tiles), int(n_tiles), _ptr(rows), _ptr(x),
+                                 int(ldx), _ptr(out), _ptr(out16), _ptr(pre), int(ldo), _ptr(out_col), _ptr(rstd), int(B),
+                                 int(layer_norm), int(relu), _stream()), "cond_fwd")
+
+
+def cond_bwd(params, grads, S, Zin, Zout, tiles, n_tiles, rows, x, ldx, dout, pre, ldo, out_col, rstd, B, dx, lddx,
+             dx_col, layer_norm, relu):
+    _check(lib().cmmvae_cond_bwd(_ptr(params), _ptr(grads), _c.c_longlong(S), Zin, Zout, _ptr(tiles), int(n_tiles),
+                                 _ptr(rows), _ptr(x), int(ldx), _ptr(dout), _ptr(pre), int(ldo), _ptr(out_col),
+                                 _ptr(rstd), int(B), _ptr(dx), int(lddx), _ptr(dx_col), int(layer_norm), int(relu),
+                                 _stream()), "cond_bwd")
+
+
+def cond_zero_grads(grads, S, present, n_present):
+    _check(lib().cmmvae_cond_zero_grads(_ptr(grads), _c.c_longlong(S), _ptr(present), int(n_present), _stream()),
+           "cond_zero_grads")
+
+
+def cond_sumsq(grads, S, present, n_present, out):
+    _check(lib().cmmvae_cond_sumsq(_ptr(grads), _c.c_longlong(S), _ptr(present), int(n_present), _ptr(out), _stream()),
+           "cond_sumsq")
+
+
+def cond_adam(params, grads, m, v, S, present, n_present, steps, norm_sq, max_norm, grad_scale, lr, b1, b2, eps, wd):
+    _check(lib().cmmvae_cond_adam(_ptr(params), _ptr(grads), _ptr(m), _ptr(v), _c.c_longlong(S), _ptr(present),
+                                  int(n_present), _ptr(steps), _ptr(norm_sq), _c.c_float(max_norm or 0.0),
+                                  _c.c_float(grad_scale), _c.c_float(lr), _c.c_double(b1), _c.c_double(b2),
+                                  _c.c_float(eps), _c.c_float(wd), _stream()), "cond_adam")
 
 
 def widen_u16_i32(src_u16, dst_i32, n: int, stream=None):

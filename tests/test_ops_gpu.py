@@ -485,3 +485,86 @@ def test_torch_custom_ops_reach_the_kernels(ops):
     ML, eps = torch.randn(32, 16, generator=g).cuda(), torch.randn(32, 8, generator=g).cuda()
     z, sums = torch.ops.cmmvae.reparam_kl_fwd(ML, eps, 1e-4)
     assert rel(z, ML[:, :8] + eps * torch.sqrt(torch.exp(ML[:, 8:]) + 1e-4)) < 1e-6 and sums.shape == (3,)
+
+
+@pytest.mark.parametrize("parallel,relu,layer_norm", [(True, False, True), (False, True, True), (True, True, False)])
+def test_conditional_bank_matches_torch_modules(tmp_path, parallel, relu, layer_norm):
+    """mmvae_b200.conditional.CondBank + csrc/conditional.cu against the module route (ConditionalLayers.forward,
+    components.py:581-631, under autograd) at a batch where values own several 32-row tiles: outputs, input
+    gradient, the gradients of the values present (others untouched), and per-value Adam steps over 3 batches
+    against torch.optim.Adam on the same modules"""
+    import random
+    import pandas as pd
+    from helpers import rel_l2
+    from mmvae_b200.conditional import CondBank
+    from mmvae_b200.modules.base import FCBlockConfig
+    from mmvae_b200.modules.base.components import ConditionalLayers
+    import copy, os
+    from mmvae_b200 import layers as L
+    torch.manual_seed(5)
+    Z, B = 64, 200
+    L.set_precision("fp32")      # (the module route's Linear layers follow the precision policy)
+    try:
+        _conditional_bank_case(tmp_path, parallel, relu, layer_norm, Z, B)
+    finally:
+        L.set_precision("bf16")
+
+
+def _conditional_bank_case(tmp_path, parallel, relu, layer_norm, Z, B):
+    import copy, os, random
+    import pandas as pd
+    from helpers import rel_l2
+    from mmvae_b200.conditional import CondBank
+    from mmvae_b200.modules.base import FCBlockConfig
+    from mmvae_b200.modules.base.components import ConditionalLayers
+    os.makedirs(tmp_path / "shared"); os.makedirs(tmp_path / "human"); os.makedirs(tmp_path / "mouse")
+    pd.DataFrame([f"a.{i}" for i in range(3)]).to_csv(tmp_path / "shared" / "unique_expression_assay.csv", header=False, index=False)
+    for sp in ("human", "mouse"):
+        pd.DataFrame([f"d_{i}" for i in range(40)]).to_csv(tmp_path / sp / "unique_expression_donor.csv", header=False, index=False)
+    cfg = FCBlockConfig(layers=[Z], use_layer_norm=layer_norm, activation_fn=torch.nn.ReLU if relu else None)
+    ref = ConditionalLayers(str(tmp_path), ["assay", "donor", "species"], cfg,
+                            selection_order=["parallel"] if parallel else ["donor", "species", "assay"]).cuda()
+    mine = copy.deepcopy(ref)
+    bank = CondBank(mine, "cuda", lr=5e-3, weight_decay=1e-6)
+    opt = torch.optim.Adam(ref.parameters(), lr=5e-3, weight_decay=1e-6)
+    ws = {}
+    def wsf(name, shape, dtype=torch.float32):
+        return ws.setdefault((name, tuple(shape), dtype), torch.empty(shape, dtype=dtype, device="cuda"))
+    rng = np.random.default_rng(0)
+    for t in range(3):
+        meta = pd.DataFrame({"assay": [f"a.{i}" for i in rng.integers(0, 3, B)],
+                             "donor": [f"d_{i}" for i in rng.integers(0, 12 + 10 * t, B)]})
+        z = torch.randn(B, Z, device="cuda", requires_grad=True)
+        random.seed(10 + t)
+        opt.zero_grad(set_to_none=True)
+        y_ref = ref(z, meta, "human")
+        wgt = torch.randn_like(y_ref)
+        (y_ref * wgt).sum().backward()
+        random.seed(10 + t)
+        bank.make_plan(meta, "human", B)
+        y, y16 = bank.forward(z.detach(), wsf, True)
+        assert torch.allclose(y, y_ref, rtol=1e-3, atol=2e-4), float((y - y_ref).abs().max())
+        assert torch.allclose(y16.float(), y_ref, rtol=1e-2, atol=1e-2)
+        dz = bank.backward(wgt.contiguous(), wsf)
+        assert torch.allclose(dz, z.grad, rtol=1e-3, atol=1e-4), float((dz - z.grad).abs().max())
+        present = set(bank.plan["present"].cpu().tolist())
+        for s_, ((n_, p_ref), p_mine) in enumerate(zip(ref.named_parameters(), bank.params)):
+            if p_ref.grad is None:
+                assert s_ // 2 not in present, n_
+            else:
+                assert s_ // 2 in present, n_
+                assert rel_l2(p_mine.grad.cpu().numpy(), p_ref.grad.cpu().numpy()) < 2e-4 or \
+                    float((p_mine.grad - p_ref.grad).abs().max()) < 1e-4, n_
+        ns = torch.zeros(1, dtype=torch.float64, device="cuda")
+        bank.add_norm_sq(ns)
+        want = torch.nn.utils.clip_grad_norm_(ref.parameters(), 10.0)
+        assert float(ns.sqrt()) == pytest.approx(float(want), rel=1e-4)
+        opt.step()
+        bank.clip_adam(ns, 10.0)
+    for (n_, p_ref), p_mine in zip(ref.named_parameters(), bank.params):
+        if n_.endswith("lin.bias") and layer_norm:
+            continue      # shift-invariant under LayerNorm: its gradient is rounding noise that Adam normalises
+        assert rel_l2(p_mine.detach().cpu().numpy(), p_ref.detach().cpu().numpy()) < 1e-4, n_
+    steps = bank.steps.cpu().tolist()
+    for s_, (n_, p_ref) in enumerate(list(ref.named_parameters())[::2]):
+        assert steps[s_] == int(opt.state[p_ref]["step"]) if p_ref in opt.state else steps[s_] == 0, n_

@@ -258,11 +258,13 @@ def test_bf16_step_matches_oracle_midsize(with_adv, dims, tmp_path):
             g.refresh_shadow()
 
 
-def test_conditional_layers_module_route_matches_reference(tmp_path):
-    """the topology of configs/model/human_only.yaml (parallel conditional layers on z, concat
-    layer, two GRL adversaries) is outside the fused engine; it trains through the module route (same
-    kernels under autograd, LayerNorm as a stock module).  Checked against the unmodified reference's
-    training_step / validation_step outputs (fp32 path)."""
+@pytest.mark.parametrize("route", ["fused", "module"])
+def test_conditional_layers_match_reference(tmp_path, route):
+    """the topology of configs/model/human_only.yaml (parallel conditional layers on z -- one Linear +
+    LayerNorm per metadata value, shared / per species / species block --, concat layer, two GRL adversaries)
+    against the unmodified reference's training_step / validation_step outputs (fp32 path): through the fused
+    engine (rows grouped by value, one launch per direction, Adam on the values present in the batch only) and
+    through the module route (same kernels under autograd, LayerNorm as a stock module)."""
     import random
     from mmvae_b200 import layers as L
     from mmvae_b200.modules.base import KLAnnealingFn
@@ -273,7 +275,12 @@ def test_conditional_layers_module_route_matches_reference(tmp_path):
         model = build_b200_model(gc, tmp_path, kl_fn=KLAnnealingFn(0.5))
         model.load_state_dict({f"module.{k}": v for k, v in gc.state("init").items()}, strict=True)
         model.cuda().train()
-        assert model.engine() is None and "conditional" in model._module_route_reason
+        model.use_fused_engine = route == "fused"
+        if route == "fused":
+            model.configure_optimizers()
+            assert model.engine() is not None and model.engine().cond is not None
+        else:
+            assert model.engine() is None
         for t in range(gc.n_steps):
             s = gc.step(t)
             L.inject_noise(s["eps"].cuda())
@@ -294,10 +301,35 @@ def test_conditional_layers_module_route_matches_reference(tmp_path):
                 assert int(a) == int(v)
             elif bias_feeds_batchnorm(k, final) or k.endswith("bn.running_mean"):
                 continue
-            elif ".conditions." in k and k.endswith(".lin.bias"):
+            elif ".conditionals." in k and k.endswith(".lin.bias"):
                 continue   # bias feeding LayerNorm(no affine): shift-invariant, gradient is rounding noise too
             else:
                 assert rel_l2(a, v.numpy()) < 2e-3, (k, rel_l2(a, v.numpy()))
+        # validation step (eval mode) on the trained weights
+        s = gc.step("val")
+        L.inject_noise(s["eps"].cuda())
+        meta = pd.DataFrame({c: [f"{c}_0"] * gc.dims["B"] for c in CONDITIONS})
+        model.eval()
+        model.trainer.set_stage("validating")
+        model.load_state_dict({f"module.{k}": v for k, v in final.items()})    # (independent of training drift)
+        model.logged_metrics.clear()
+        random.seed(777)
+        model.validation_step((csr_batch(s["crow"], s["col"], s["val"], gc.genes["human"]), meta, "human"))
+        got = {k: float(v) for k, v in model.logged_metrics.items()}
+        for k, v in s["logs"].items():
+            assert got[k] == pytest.approx(v, rel=2e-3), k
+        if route == "fused":
+            # optimizer state in torch.optim.Adam's format: a value that was never drawn has no entry, every other
+            # one carries ITS OWN step count
+            sd = model.get_optimizers()["vae"].state_dict()
+            eng = model.engine()
+            n_dense = len(eng.groups["vae"].params)
+            steps = eng.cond.steps.cpu().tolist()
+            assert 0 < min(t for t in steps if t) <= max(steps) == gc.n_steps
+            for slot, t in enumerate(steps):
+                for j in (0, 1):
+                    e = sd["state"].get(n_dense + 2 * slot + j)
+                    assert (e is None) == (t == 0) and (e is None or int(e["step"]) == t)
     finally:
         L.set_precision("bf16")
 
