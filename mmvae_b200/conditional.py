@@ -57,6 +57,8 @@ class CondBank:
         p0 = dict(first.fc_layers[0].named_children())
         self.layer_norm, self.relu = "ln" in p0, "af" in p0
         self.Zin, self.Zout = p0["lin"].in_features, p0["lin"].out_features
+        if self.Zin % 4 or self.Zout % 4:
+            raise CondUnsupported("conditional block widths must be multiples of 4 in the fused step")
         if not self.parallel and self.Zin != self.Zout:
             raise CondUnsupported("chained conditional layers need square blocks")
         if (self.Zin + self.Zout) * ROWS * 4 > 200 * 1024:
@@ -91,6 +93,7 @@ class CondBank:
                 self.kind[bk] = "shared"
                 self.tables[(bk, None)] = self._table(f"layers.{bk}", layer)
                 continue
+            self.kind[bk] = "block"       # (an empty ModuleDict fails at lookup time, as the reference's does)
             for sp, sub in layer.items():
                 if hasattr(sub, "conditions"):
                     self.kind[bk] = "per_species"
@@ -107,45 +110,75 @@ class CondBank:
     def _table(self, path: str, layer) -> tuple:
         keys = list(layer.conditions.keys())
         slots = np.array([self.slot_of_path[f"{path}.conditions.{k}"] for k in keys], dtype=np.int32)
-        return pd.Index(keys), slots
+        return {k: i for i, k in enumerate(keys)}, slots
+
+    @staticmethod
+    def _lookup(tab, values) -> np.ndarray:
+        """slot of every metadata value.  The reference formats each value with ``str(v).replace(".", "_")``
+        (components.py:355-365, 391-396); values that already are keys are found directly, only the rest is
+        formatted"""
+        d = tab[0]
+        try:          # (a C-level map over a dict: 4x faster than pd.Index.get_indexer on object keys)
+            idx = np.fromiter(map(d.__getitem__, values), dtype=np.int64, count=len(values))
+        except KeyError:
+            idx = np.fromiter((d[str(v).replace(".", "_")] for v in values), dtype=np.int64, count=len(values))
+        return tab[1][idx]
 
     # --------------------------------------------------------------------------------------------- host plan
-    def make_plan(self, metadata: pd.DataFrame, species: Optional[str], B: int) -> dict:
-        """sort the batch by condition value (host, vectorised) and ship tiles / row lists / present slots"""
-        order = random.sample(self.names, len(self.names)) if self.shuffle else list(self.names)   # components.py:598-602
+    def host_plan(self, metadata: pd.DataFrame, species: Optional[str], B: int):
+        """(pure host work) rows of the batch grouped by condition value: tiles, row lists, tile range per key"""
         n_c = len(self.names)
-        tiles, rows_all, ranges = [], [], []
+        slots = np.empty((n_c, B), dtype=np.int64)
         for c, bk in enumerate(self.names):
             kind = self.kind[bk]
             if kind != "shared" and species is None:
                 raise RuntimeError(f"'species' must be set to access non-shared conditional layer for batch_key '{bk}'")
             if kind == "block":
-                slots = np.full(B, self.block_slot[(bk, species)], dtype=np.int32)
-            else:
-                tab = self.tables[(bk, None if kind == "shared" else species)]
-                keys = metadata[bk].astype(str)
-                if keys.str.contains(".", regex=False).any():
-                    keys = keys.str.replace(".", "_", regex=False)        # format_condition_key (components.py:355-365)
-                codes = tab[0].get_indexer(keys)
+                if (bk, species) not in self.block_slot:
+                    raise KeyError(species)
+                slots[c] = self.block_slot[(bk, species)]
+                continue
+            tab = self.tables[(bk, None if kind == "shared" else species)]
+            col = metadata[bk]
+            if isinstance(col.dtype, pd.CategoricalDtype):      # look the categories up, not the rows
+                codes = col.cat.codes.to_numpy()
                 if (codes < 0).any():
-                    raise KeyError(str(keys[codes < 0].iloc[0]))
-                slots = tab[1][codes]
-            perm = np.argsort(slots, kind="stable").astype(np.int32)
-            ss = slots[perm]
-            uniq, start, cnt = np.unique(ss, return_index=True, return_counts=True)
-            nch = (cnt + ROWS - 1) // ROWS
-            within = np.arange(int(nch.sum())) - np.repeat(np.cumsum(nch) - nch, nch)
-            t = np.empty((int(nch.sum()), 4), dtype=np.int32)
-            t[:, 0] = np.repeat(uniq, nch)
-            t[:, 1] = np.repeat(start, nch) + ROWS * within + c * B
-            t[:, 2] = np.minimum(ROWS, np.repeat(cnt, nch) - ROWS * within)
-            t[:, 3] = c
-            ranges.append((sum(len(x) for x in tiles), len(t)))
-            tiles.append(t)
-            rows_all.append(perm)
-        tiles = np.concatenate(tiles)
-        rows = np.concatenate(rows_all)
-        present = np.unique(tiles[:, 0]).astype(np.int32)
+                    raise KeyError("nan")
+                slots[c] = self._lookup(tab, col.cat.categories.to_numpy())[codes]
+            else:
+                slots[c] = self._lookup(tab, col.to_numpy())
+        # slots are unique across batch keys: ONE stable sort of all (key, row) pairs groups everything
+        flat = slots.reshape(-1)
+        perm = np.argsort(flat, kind="stable")
+        ss = flat[perm]
+        start = np.flatnonzero(np.concatenate(([True], ss[1:] != ss[:-1])))
+        cnt = np.diff(np.concatenate((start, [flat.size])))
+        nch = (cnt + ROWS - 1) // ROWS
+        n_t = int(nch.sum())
+        rep = np.repeat(np.arange(start.size), nch)                  # group of every tile
+        within = np.arange(n_t) - np.repeat(np.cumsum(nch) - nch, nch)
+        cond_of = (perm[start] // B).astype(np.int32)                # batch key index of every group
+        tiles = np.empty((n_t, 4), dtype=np.int32)
+        tiles[:, 0] = ss[start][rep]
+        tiles[:, 1] = start[rep] + ROWS * within
+        tiles[:, 2] = np.minimum(ROWS, cnt[rep] - ROWS * within)
+        tiles[:, 3] = cond_of[rep] | ((nch == 1)[rep].astype(np.int32) << 16)     # bit 16: the slot's only tile
+        rows = (perm % B).astype(np.int32)
+        present = ss[start].astype(np.int32)
+        multi = present[nch > 1]            # slots that several tiles ADD into (single tiles overwrite their slot)
+        # tile range of every batch key (chained selection launches them one after the other)
+        tc = cond_of[rep]
+        edge = np.flatnonzero(np.concatenate(([True], tc[1:] != tc[:-1])))
+        ranges = [None] * n_c
+        for lo, hi in zip(edge, np.concatenate((edge[1:], [n_t]))):
+            ranges[int(tc[lo])] = (int(lo), int(hi - lo))
+        return tiles, rows, present, ranges, multi
+
+    def make_plan(self, metadata: pd.DataFrame, species: Optional[str], B: int) -> dict:
+        """sort the batch by condition value (host, vectorised) and ship tiles / row lists / present slots"""
+        order = random.sample(self.names, len(self.names)) if self.shuffle else list(self.names)   # components.py:598-602
+        n_c = len(self.names)
+        tiles, rows, present, ranges, multi = self.host_plan(metadata, species, B)
         pos = {bk: i for i, bk in enumerate(order)}
         if self.parallel:
             out_col = np.array([pos[bk] * self.Zout for bk in self.names], dtype=np.int32)
@@ -153,8 +186,8 @@ class CondBank:
         else:
             out_col = np.zeros(n_c, dtype=np.int32)
             dx_col = np.zeros(n_c, dtype=np.int32)
-        # one pinned block, one copy: [tiles | rows | present | out_col | dx_col]
-        parts = [tiles.reshape(-1), rows, present, out_col, dx_col]
+        # one pinned block, one copy: [tiles | rows | present | out_col | dx_col | multi]
+        parts = [tiles.reshape(-1), rows, present, out_col, dx_col, multi]
         sizes = [(p.size + 3) // 4 * 4 for p in parts]
         total = sum(sizes)
         i = self._pin_i
@@ -178,7 +211,8 @@ class CondBank:
         self._pin_ev[i] = ev
         view = lambda k: dev[offs[k]:offs[k] + parts[k].size]   # noqa: E731
         self.plan = dict(order=order, n_tiles=len(tiles), tiles=view(0), rows=view(1), present=view(2),
-                         n_present=int(present.size), out_col=view(3), dx_col=view(4), ranges=ranges, B=B,
+                         n_present=int(present.size), out_col=view(3), dx_col=view(4), multi=view(5),
+                         n_multi=int(multi.size), ranges=ranges, B=B,
                          index={bk: c for c, bk in enumerate(self.names)})
         return self.plan
 
@@ -219,7 +253,7 @@ class CondBank:
         pl, B = self.plan, self.plan["B"]
         n_c = len(self.names)
         rstd = ws("cond.rstd", (n_c, B))
-        ops.cond_zero_grads(self.g, self.S, pl["present"], pl["n_present"])
+        ops.cond_zero_grads(self.g, self.S, pl["multi"], pl["n_multi"])
         if self.parallel:
             W = n_c * self.Zout
             dxc = ws("cond.dx", (B, n_c * self.Zin))

@@ -17,74 +17,165 @@ namespace cmmvae {
 constexpr int kCondRows = 32;       // rows per tile
 constexpr int kCondThreads = 128;
 
-// dynamic smem: xsT[Zin][32] | ysT[Zout][32]   (row index fastest: one LDS.128 = 4 rows of one column)
+// one torch.optim.Adam update (same arithmetic as clip_adam_kernel in dense_basic.cu)
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float gscale, float lr, float b1,
+                                         float b2, float eps, float wd, float bc1, float inv_sqrt_bc2) {
+  g = g * gscale;
+  g = fmaf(wd, p, g);
+  m = m + (g - m) * (1.f - b1);
+  v = v * b2 + (1.f - b2) * g * g;
+  const float denom = sqrtf(v) * inv_sqrt_bc2 + eps;
+  p = p - (lr / bc1) * (m / denom);
+}
+
+// Tile kernels.  A block of 128 threads = 4 warps owns one tile (<= 32 rows of one slot).  Register tiling: thread
+// (tx = lane, ty = warp) computes rows 8 ty .. 8 ty + 7 x columns {tx, tx + 32, tx + 64, tx + 96} of a 32 x 128 output
+// block; operands sit in shared memory row-major with a pitch of P = K + 4 floats (K <= 128 per pass), which makes
+// the lanes' 16-byte reads of four consecutive k conflict free (pitch = 4 mod 32 words) and every global row a
+// 512-byte coalesced load.  Warps whose 8 rows lie beyond the tile's row count skip the arithmetic: most tiles of a
+// many-valued key (donor_id) hold one or two cells.
+constexpr int kCondK = 128;              // K handled per pass
+constexpr int kCondP = kCondK + 4;       // shared-memory pitch
+
+// one row piece of 4 floats at column k (global), zero beyond K; 16-byte load when the row pitch allows it
+__device__ __forceinline__ float4 cond_load4(const float* __restrict__ s, int k, int K, bool vec) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (vec && k + 3 < K) return __ldg(reinterpret_cast<const float4*>(s));
+  if (k < K) v.x = __ldg(s);
+  if (k + 1 < K) v.y = __ldg(s + 1);
+  if (k + 2 < K) v.z = __ldg(s + 2);
+  if (k + 3 < K) v.w = __ldg(s + 3);
+  return v;
+}
+
+// rows x K block of a row-major global matrix (ld) -> smem [rows][kCondP].  Eight independent 512-byte row loads
+// are issued per warp before the first one is stored (a load-store pair per iteration would serialise on the
+// memory latency: 32 round trips per block).
+__device__ __forceinline__ void cond_stage_rows(float* __restrict__ dst, const float* __restrict__ src, long long ld,
+                                                int n_rows, int k0, int K, int warp, int lane) {
+  const bool vec = (ld & 3) == 0;
+  const int k = 4 * lane;
+  for (int r0 = warp; r0 < n_rows; r0 += 8 * (kCondThreads / 32)) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int r = r0 + u * (kCondThreads / 32);
+      v[u] = r < n_rows ? cond_load4(src + (long long)r * ld + k0 + k, k0 + k, K, vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int r = r0 + u * (kCondThreads / 32);
+      if (r < n_rows) *reinterpret_cast<float4*>(dst + r * kCondP + k) = v[u];
+    }
+  }
+}
+
+// gathered rows of x (row list in row_s, -1 = none) -> smem [32][kCondP]: a warp's 8 rows are loaded together
+__device__ __forceinline__ void cond_stage_x(float* __restrict__ dst, const float* __restrict__ x, long long ldx,
+                                             const int* row_s, int k0, int K, int warp, int lane,
+                                             int pitch = kCondP, bool pad_chunk = true) {
+  const bool vec = ((ldx | k0) & 3) == 0;
+  const int k = 4 * lane;
+  float4 v[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int row = row_s[warp + u * (kCondThreads / 32)];
+    v[u] = row >= 0 ? cond_load4(x + (long long)row * ldx + k0 + k, k0 + k, K, vec) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (!pad_chunk && k0 + k >= K) return;      // (pitch K + 4: nothing exists beyond column K + 3)
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    *reinterpret_cast<float4*>(dst + (warp + u * (kCondThreads / 32)) * pitch + k0 + k) = v[u];
+}
+
+// acc[i][c] += sum_k A[8 ty + i][k] * Bm[tx + 32 c][k]   (A, Bm: smem [.][kCondP], K = kCondK)
+__device__ __forceinline__ void cond_mma_nt(float (&acc)[8][4], const float* __restrict__ A,
+                                            const float* __restrict__ Bm, int ty, int tx) {
+#pragma unroll 2
+  for (int k = 0; k < kCondK; k += 4) {
+    float4 b[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) b[c] = *reinterpret_cast<const float4*>(Bm + (tx + 32 * c) * kCondP + k);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 a = *reinterpret_cast<const float4*>(A + (8 * ty + i) * kCondP + k);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        acc[i][c] = fmaf(a.x, b[c].x, acc[i][c]);
+        acc[i][c] = fmaf(a.y, b[c].y, acc[i][c]);
+        acc[i][c] = fmaf(a.z, b[c].z, acc[i][c]);
+        acc[i][c] = fmaf(a.w, b[c].w, acc[i][c]);
+      }
+    }
+  }
+}
+
+// dynamic smem: xs[32][P] | Ws[128][P] (reused as ys[32][P] per 128-column block of the output)
 __global__ void __launch_bounds__(kCondThreads)
 cond_fwd_kernel(const float* __restrict__ params, long long S, int Zin, int Zout, const int4* __restrict__ tiles,
                 const int* __restrict__ rows, const float* __restrict__ x, int ldx, float* __restrict__ out,
                 __nv_bfloat16* __restrict__ out16, float* __restrict__ pre, int ldo, const int* __restrict__ ooff,
                 float* __restrict__ rstd, int B, int layer_norm, int relu) {
-  extern __shared__ float smem[];
-  float* xsT = smem;
-  float* ysT = smem + (size_t)Zin * kCondRows;
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem;
+  float* Ws = smem + kCondRows * kCondP;
+  float* ys = Ws + kCondThreads * kCondP;            // [32][Zout + 4]: the whole output row block for LayerNorm
   __shared__ int row_s[kCondRows];
   pdl_sync();
   const int4 t = tiles[blockIdx.x];
-  const int slot = t.x, start = t.y, count = t.z, cond = t.w;
+  const int slot = t.x, start = t.y, count = t.z, cond = t.w & 0xFFFF;
   const float* W = params + (long long)slot * S;
   const float* bias = W + (long long)Zout * Zin;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
+  const int PY = Zout + 4;
   if (tid < kCondRows) row_s[tid] = tid < count ? rows[start + tid] : -1;
-  __syncthreads();
-  for (int i = tid; i < Zin * kCondRows; i += kCondThreads) {
-    const int r = i / Zin, k = i - r * Zin;            // coalesced along k
-    const int row = row_s[r];
-    xsT[k * kCondRows + r] = row >= 0 ? x[(long long)row * ldx + k] : 0.f;
-  }
-  __syncthreads();
-  for (int j = tid; j < Zout; j += kCondThreads) {
-    float acc[kCondRows];
-    const float bj = bias[j];
+  const bool active = 8 * ty < count;
+  for (int j0 = 0; j0 < Zout; j0 += kCondThreads) {
+    float acc[8][4];
 #pragma unroll
-    for (int r = 0; r < kCondRows; ++r) acc[r] = bj;
-    const float* Wj = W + (long long)j * Zin;
-    for (int k = 0; k < Zin; ++k) {
-      const float w = __ldg(Wj + k);
-      const float4* xr = reinterpret_cast<const float4*>(xsT + k * kCondRows);
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int q = 0; q < kCondRows / 4; ++q) {
-        const float4 v = xr[q];
-        acc[4 * q] = fmaf(w, v.x, acc[4 * q]);
-        acc[4 * q + 1] = fmaf(w, v.y, acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(w, v.z, acc[4 * q + 2]);
-        acc[4 * q + 3] = fmaf(w, v.w, acc[4 * q + 3]);
-      }
+      for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+    for (int k0 = 0; k0 < Zin; k0 += kCondK) {
+      __syncthreads();
+      cond_stage_x(xs - k0, x, ldx, row_s, k0, Zin, ty, tx);      // (chunk k0 lands at columns 0..127)
+      cond_stage_rows(Ws, W + (long long)j0 * Zin, Zin, min(kCondThreads, Zout - j0), k0, Zin, ty, tx);
+      __syncthreads();
+      if (active) cond_mma_nt(acc, xs, Ws, ty, tx);
     }
 #pragma unroll
-    for (int r = 0; r < kCondRows; ++r) ysT[j * kCondRows + r] = acc[r];
+    for (int c = 0; c < 4; ++c) {
+      const int j = j0 + tx + 32 * c;
+      if (j < Zout) {
+        const float bj = bias[j];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ys[(8 * ty + i) * PY + j] = acc[i][c] + bj;
+      }
+    }
   }
   __syncthreads();
   // LayerNorm (no affine, eps 1e-5, biased variance) + activation: one warp per row
-  const int warp = tid >> 5, lane = tid & 31;
   const int col0 = ooff[cond];
-  for (int r = warp; r < count; r += kCondThreads / 32) {
+  for (int r = ty; r < count; r += kCondThreads / 32) {
     const int row = row_s[r];
+    const float* y = ys + r * PY;
     float mean = 0.f, rs = 1.f;
     if (layer_norm) {
       float s = 0.f;
-      for (int j = lane; j < Zout; j += 32) s += ysT[j * kCondRows + r];
+      for (int j = tx; j < Zout; j += 32) s += y[j];
       s = warp_sum(s);
       mean = s / (float)Zout;
       float q = 0.f;
-      for (int j = lane; j < Zout; j += 32) {
-        const float d = ysT[j * kCondRows + r] - mean;
+      for (int j = tx; j < Zout; j += 32) {
+        const float d = y[j] - mean;
         q = fmaf(d, d, q);
       }
       q = warp_sum(q);
       rs = rsqrtf(q / (float)Zout + 1e-5f);
-      if (lane == 0) rstd[(long long)cond * B + row] = rs;
+      if (tx == 0) rstd[(long long)cond * B + row] = rs;
     }
-    for (int j = lane; j < Zout; j += 32) {
-      const float h = (ysT[j * kCondRows + r] - mean) * rs;
+    for (int j = tx; j < Zout; j += 32) {
+      const float h = (y[j] - mean) * rs;
       const float o = relu ? fmaxf(h, 0.f) : h;
       const long long at = (long long)row * ldo + col0 + j;
       pre[at] = h;
@@ -94,105 +185,200 @@ cond_fwd_kernel(const float* __restrict__ params, long long S, int Zin, int Zout
   }
 }
 
-// dynamic smem: xs[32][Zin] (row major: thread k reads a column into registers) | dysT[Zout][32]
+// dynamic smem: xs[32][Zin + 4] | dys[32][Zout + 4] | Ws[128][P]
+// (Zin, Zout <= 128 per pass of the two products; wider blocks loop over 128-wide pieces)
 __global__ void __launch_bounds__(kCondThreads)
 cond_bwd_kernel(const float* __restrict__ params, float* __restrict__ grads, long long S, int Zin, int Zout,
                 const int4* __restrict__ tiles, const int* __restrict__ rows, const float* __restrict__ x, int ldx,
                 const float* __restrict__ dout, const float* __restrict__ pre, int ldo,
                 const int* __restrict__ ooff, const float* __restrict__ rstd, int B, float* __restrict__ dx,
                 int lddx, const int* __restrict__ dxoff, int layer_norm, int relu) {
-  extern __shared__ float smem[];
-  float* xs = smem;
-  float* dysT = smem + (size_t)Zin * kCondRows;
+  extern __shared__ __align__(16) float smem[];
+  const int PX = Zin + 4, PY = Zout + 4;
+  float* xs = smem;                           // [32][PX]   gathered inputs
+  float* dys = xs + kCondRows * PX;           // [32][PY]   dy
+  float* Ws = dys + kCondRows * PY;           // [128][kCondP]  transposed W piece
   __shared__ int row_s[kCondRows];
   pdl_sync();
   const int4 t = tiles[blockIdx.x];
-  const int slot = t.x, start = t.y, count = t.z, cond = t.w;
+  const int slot = t.x, start = t.y, count = t.z, cond = t.w & 0xFFFF;
+  const bool sole = (t.w >> 16) != 0;     // the only tile of its slot: plain stores instead of atomic adds
   const float* W = params + (long long)slot * S;
   float* gW = grads + (long long)slot * S;
   float* gb = gW + (long long)Zout * Zin;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
   if (tid < kCondRows) row_s[tid] = tid < count ? rows[start + tid] : -1;
   __syncthreads();
-  for (int i = tid; i < Zin * kCondRows; i += kCondThreads) {
-    const int r = i / Zin, k = i - r * Zin;
-    const int row = row_s[r];
-    xs[r * Zin + k] = row >= 0 ? x[(long long)row * ldx + k] : 0.f;
-  }
+  for (int k0 = 0; k0 < Zin; k0 += kCondK) cond_stage_x(xs, x, ldx, row_s, k0, Zin, ty, tx, PX, false);
   // dy of the tile's rows (LayerNorm backward without affine: dy = rstd (g - mean(g) - h mean(g h)))
   const int col0 = ooff[cond];
-  for (int r = warp; r < kCondRows; r += kCondThreads / 32) {
-    const int row = row_s[r];
-    if (row < 0) {
-      for (int j = lane; j < Zout; j += 32) dysT[j * kCondRows + r] = 0.f;
-      continue;
+  if (Zout <= 128) {
+    // a warp's 8 rows at once: all loads of the rows' LayerNorm outputs and output gradients are in flight together
+    float h[8][4], g[8][4], rs[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int row = row_s[ty + 4 * u];
+      rs[u] = (row >= 0 && layer_norm) ? rstd[(long long)cond * B + row] : 1.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = tx + 32 * c;
+        const bool ok = row >= 0 && j < Zout;
+        const long long at = (long long)(row >= 0 ? row : 0) * ldo + col0 + j;
+        h[u][c] = ok ? pre[at] : 0.f;
+        g[u][c] = ok ? dout[at] : 0.f;
+      }
     }
-    const long long at = (long long)row * ldo + col0;
-    float m1 = 0.f, m2 = 0.f, rs = 1.f;
-    if (layer_norm) {
-      for (int j = lane; j < Zout; j += 32) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (relu && h[u][c] <= 0.f) g[u][c] = 0.f;
+        m1 += g[u][c];
+        m2 = fmaf(g[u][c], h[u][c], m2);
+      }
+      if (layer_norm) {
+        m1 = warp_sum(m1) / (float)Zout;
+        m2 = warp_sum(m2) / (float)Zout;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = tx + 32 * c;
+        if (j < Zout) dys[(ty + 4 * u) * PY + j] = layer_norm ? rs[u] * (g[u][c] - m1 - h[u][c] * m2) : g[u][c];
+      }
+    }
+  } else {
+    for (int r = ty; r < kCondRows; r += kCondThreads / 32) {
+      const int row = row_s[r];
+      if (row < 0) {
+        for (int j = tx; j < Zout; j += 32) dys[r * PY + j] = 0.f;
+        continue;
+      }
+      const long long at = (long long)row * ldo + col0;
+      float m1 = 0.f, m2 = 0.f, rs = 1.f;
+      if (layer_norm) {
+        for (int j = tx; j < Zout; j += 32) {
+          const float h = pre[at + j];
+          const float g = (relu && h <= 0.f) ? 0.f : dout[at + j];
+          m1 += g;
+          m2 = fmaf(g, h, m2);
+        }
+        m1 = warp_sum(m1) / (float)Zout;
+        m2 = warp_sum(m2) / (float)Zout;
+        rs = rstd[(long long)cond * B + row];
+      }
+      for (int j = tx; j < Zout; j += 32) {
         const float h = pre[at + j];
         const float g = (relu && h <= 0.f) ? 0.f : dout[at + j];
-        m1 += g;
-        m2 = fmaf(g, h, m2);
+        dys[r * PY + j] = layer_norm ? rs * (g - m1 - h * m2) : g;
       }
-      m1 = warp_sum(m1) / (float)Zout;
-      m2 = warp_sum(m2) / (float)Zout;
-      rs = rstd[(long long)cond * B + row];
-    }
-    for (int j = lane; j < Zout; j += 32) {
-      const float h = pre[at + j];
-      const float g = (relu && h <= 0.f) ? 0.f : dout[at + j];
-      dysT[j * kCondRows + r] = layer_norm ? rs * (g - m1 - h * m2) : g;
     }
   }
   __syncthreads();
-  // db_s[j] += sum_r dy[r][j]
+  // db_s[j] (+)= sum_r dy[r][j]
   for (int j = tid; j < Zout; j += kCondThreads) {
     float s = 0.f;
-#pragma unroll
-    for (int r = 0; r < kCondRows; ++r) s += dysT[j * kCondRows + r];
-    atomicAdd(gb + j, s);
+    for (int r = 0; r < count; ++r) s += dys[r * PY + j];
+    if (sole) gb[j] = s; else atomicAdd(gb + j, s);
   }
+  // dW_s[j][k] (+)= sum_r dy[r][j] x[r][k]: thread = columns k in {tx + 32 c}, 8 rows j per pass; the loop over r
+  // stops at the tile's row count
+  for (int j0 = 8 * ty; j0 < Zout; j0 += 8 * (kCondThreads / 32)) {
+    for (int kb = 0; kb < Zin; kb += 128) {
+      float acc[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+      for (int r = 0; r < count; ++r) {
+        float xv[4], dv[8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int k = kb + tx + 32 * c;
+          xv[c] = k < Zin ? xs[r * PX + k] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dv[i] = (j0 + i) < Zout ? dys[r * PY + j0 + i] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[i][c] = fmaf(dv[i], xv[c], acc[i][c]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int j = j0 + i, k = kb + tx + 32 * c;
+          if (j < Zout && k < Zin) {
+            if (sole) gW[(long long)j * Zin + k] = acc[i][c]; else atomicAdd(gW + (long long)j * Zin + k, acc[i][c]);
+          }
+        }
+    }
+  }
+  // dx[r][k] = sum_j dy[r][j] W[j][k]: W^T pieces [128 k][128 j] staged as Ws[k][j] (a transposing copy: the global
+  // rows j are read coalesced, 4 k per lane, and scattered to 4 smem rows)
   const int xoff = dxoff[cond];
-  for (int k = tid; k < Zin; k += kCondThreads) {
-    // dx[r][k] = sum_j dy[r][j] W[j][k]   (W read coalesced along k)
-    float acc[kCondRows];
+  const bool active = 8 * ty < count;
+  for (int kb = 0; kb < Zin; kb += kCondThreads) {
+    float acc[8][4];
 #pragma unroll
-    for (int r = 0; r < kCondRows; ++r) acc[r] = 0.f;
-    for (int j = 0; j < Zout; ++j) {
-      const float w = __ldg(W + (long long)j * Zin + k);
-      const float4* dr = reinterpret_cast<const float4*>(dysT + j * kCondRows);
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int q = 0; q < kCondRows / 4; ++q) {
-        const float4 v = dr[q];
-        acc[4 * q] = fmaf(w, v.x, acc[4 * q]);
-        acc[4 * q + 1] = fmaf(w, v.y, acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(w, v.z, acc[4 * q + 2]);
-        acc[4 * q + 3] = fmaf(w, v.w, acc[4 * q + 3]);
+      for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+    for (int jb = 0; jb < Zout; jb += kCondK) {
+      __syncthreads();
+      for (int jj0 = ty; jj0 < kCondK; jj0 += 8 * (kCondThreads / 32)) {
+        float w[8][4];       // 32 independent loads in flight per thread before the first store
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = jb + jj0 + u * (kCondThreads / 32);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int k = kb + tx + 32 * c;   // coalesced along k
+            w[u][c] = (j < Zout && k < Zin) ? __ldg(W + (long long)j * Zin + k) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) Ws[(tx + 32 * c) * kCondP + jj0 + u * (kCondThreads / 32)] = w[u][c];
+      }
+      __syncthreads();
+      if (active) {
+        // acc[i][c] += sum_jj dys[8 ty + i][jb + jj] * Ws[tx + 32 c][jj]
+#pragma unroll 2
+        for (int jj = 0; jj < kCondK; jj += 4) {
+          if (jb + jj >= Zout) break;
+          float4 b[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) b[c] = *reinterpret_cast<const float4*>(Ws + (tx + 32 * c) * kCondP + jj);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float* dp = dys + (8 * ty + i) * PY + jb + jj;
+            const float a0 = dp[0], a1 = (jb + jj + 1 < Zout) ? dp[1] : 0.f, a2 = (jb + jj + 2 < Zout) ? dp[2] : 0.f,
+                        a3 = (jb + jj + 3 < Zout) ? dp[3] : 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              acc[i][c] = fmaf(a0, b[c].x, acc[i][c]);
+              acc[i][c] = fmaf(a1, b[c].y, acc[i][c]);
+              acc[i][c] = fmaf(a2, b[c].z, acc[i][c]);
+              acc[i][c] = fmaf(a3, b[c].w, acc[i][c]);
+            }
+          }
+        }
       }
     }
+    if (active) {
 #pragma unroll
-    for (int r = 0; r < kCondRows; ++r) {
-      const int row = row_s[r];
-      if (row >= 0) dx[(long long)row * lddx + xoff + k] = acc[r];
-    }
-    // dW_s[j][k] += sum_r dy[r][j] x[r][k]   (column k of the tile's inputs in registers)
-    float xr[kCondRows];
+      for (int i = 0; i < 8; ++i) {
+        const int row = row_s[8 * ty + i];
+        if (row < 0) continue;
 #pragma unroll
-    for (int r = 0; r < kCondRows; ++r) xr[r] = xs[r * Zin + k];
-    for (int j = 0; j < Zout; ++j) {
-      const float4* dr = reinterpret_cast<const float4*>(dysT + j * kCondRows);
-      float s = 0.f;
-#pragma unroll
-      for (int q = 0; q < kCondRows / 4; ++q) {
-        const float4 v = dr[q];
-        s = fmaf(v.x, xr[4 * q], s);
-        s = fmaf(v.y, xr[4 * q + 1], s);
-        s = fmaf(v.z, xr[4 * q + 2], s);
-        s = fmaf(v.w, xr[4 * q + 3], s);
+        for (int c = 0; c < 4; ++c) {
+          const int k = kb + tx + 32 * c;
+          if (k < Zin) dx[(long long)row * lddx + xoff + k] = acc[i][c];
+        }
       }
-      atomicAdd(gW + (long long)j * Zin + k, s);
     }
   }
 }
@@ -230,11 +416,16 @@ __global__ void cond_adam_kernel(float* __restrict__ params, const float* __rest
                                  float* __restrict__ v, long long S, const int* __restrict__ present,
                                  const int* __restrict__ steps, const double* __restrict__ norm_sq, float max_norm,
                                  float grad_scale, float lr, double b1, double b2, float eps, float wd) {
+  __shared__ float bc[2];
   pdl_sync();
   const int slot = present[blockIdx.x];
-  const double t = (double)(steps[slot] + 1);
-  const float bc1 = (float)(1.0 - pow(b1, t));
-  const float isb2 = (float)(1.0 / sqrt(1.0 - pow(b2, t)));
+  if (threadIdx.x == 0) {
+    const double t = (double)(steps[slot] + 1);
+    bc[0] = (float)(1.0 - pow(b1, t));
+    bc[1] = (float)(1.0 / sqrt(1.0 - pow(b2, t)));
+  }
+  __syncthreads();
+  const float bc1 = bc[0], isb2 = bc[1];
   float coef = 1.f;
   if (max_norm > 0.f && norm_sq) {
     const float total = (float)sqrt(*norm_sq) * fabsf(grad_scale);
@@ -243,15 +434,18 @@ __global__ void cond_adam_kernel(float* __restrict__ params, const float* __rest
   const float gs = coef * grad_scale;
   const float fb1 = (float)b1, fb2 = (float)b2;
   const long long base = (long long)slot * S;
-  for (long long i = blockIdx.y * (long long)blockDim.x + threadIdx.x; i < S; i += (long long)gridDim.y * blockDim.x) {
-    float p = params[base + i], mm = m[base + i], vv = v[base + i];
-    float g = grads[base + i] * gs;
-    g = fmaf(wd, p, g);
-    mm = mm + (g - mm) * (1.f - fb1);
-    vv = vv * fb2 + (1.f - fb2) * g * g;
-    const float denom = sqrtf(vv) * isb2 + eps;
-    p = p - (lr / bc1) * (mm / denom);
-    params[base + i] = p; m[base + i] = mm; v[base + i] = vv;
+  float4* p4 = reinterpret_cast<float4*>(params + base);
+  float4* m4 = reinterpret_cast<float4*>(m + base);
+  float4* v4 = reinterpret_cast<float4*>(v + base);
+  const float4* g4 = reinterpret_cast<const float4*>(grads + base);
+  for (long long i = blockIdx.y * (long long)blockDim.x + threadIdx.x; i < S / 4; i += (long long)gridDim.y * blockDim.x) {
+    float4 p = p4[i], mm = m4[i], vv = v4[i];
+    const float4 g = g4[i];
+    adam_one(p.x, g.x, mm.x, vv.x, gs, lr, fb1, fb2, eps, wd, bc1, isb2);
+    adam_one(p.y, g.y, mm.y, vv.y, gs, lr, fb1, fb2, eps, wd, bc1, isb2);
+    adam_one(p.z, g.z, mm.z, vv.z, gs, lr, fb1, fb2, eps, wd, bc1, isb2);
+    adam_one(p.w, g.w, mm.w, vv.w, gs, lr, fb1, fb2, eps, wd, bc1, isb2);
+    p4[i] = p; m4[i] = mm; v4[i] = vv;
   }
 }
 
@@ -264,7 +458,12 @@ __global__ void cond_step_inc_kernel(int* __restrict__ steps, const int* __restr
 
 using namespace cmmvae;
 
-static size_t cond_smem(int Zin, int Zout) { return (size_t)(Zin + Zout) * kCondRows * sizeof(float); }
+static size_t cond_smem_fwd(int Zin, int Zout) {
+  return (size_t)(kCondRows * kCondP + kCondThreads * kCondP + kCondRows * (Zout + 4)) * sizeof(float);
+}
+static size_t cond_smem_bwd(int Zin, int Zout) {
+  return (size_t)(kCondRows * (Zin + 4) + kCondRows * (Zout + 4) + kCondThreads * kCondP) * sizeof(float);
+}
 
 extern "C" int cmmvae_cond_fwd(const float* params, long long slot_stride, int Zin, int Zout, const int32_t* tiles,
                                int n_tiles, const int32_t* rows, const float* x, int ldx, float* out, void* out_bf16,
@@ -272,10 +471,11 @@ extern "C" int cmmvae_cond_fwd(const float* params, long long slot_stride, int Z
                                void* stream) {
   if (n_tiles <= 0) return 0;
   CMMVAE_REQUIRE(params && tiles && rows && x && out && pre && out_col && rstd, "cond_fwd: null pointer");
-  CMMVAE_REQUIRE(Zin > 0 && Zout > 0 && slot_stride % 4 == 0 && slot_stride >= (long long)Zout * Zin + Zout,
-                 "cond_fwd: bad sizes");
-  const size_t smem = cond_smem(Zin, Zout);
-  CMMVAE_REQUIRE(smem <= 200 * 1024, "cond_fwd: Zin + Zout must be <= 1600");
+  CMMVAE_REQUIRE(Zin > 0 && Zout > 0 && Zin % 4 == 0 && Zout % 4 == 0 && slot_stride % 4 == 0 &&
+                     slot_stride >= (long long)Zout * Zin + Zout,
+                 "cond_fwd: bad sizes (block widths must be multiples of 4)");
+  const size_t smem = cond_smem_fwd(Zin, Zout);
+  CMMVAE_REQUIRE(smem <= 200 * 1024, "cond_fwd: block too wide for the shared-memory tile");
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
     cudaFuncSetAttribute(cond_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -295,9 +495,10 @@ extern "C" int cmmvae_cond_bwd(const float* params, float* grads, long long slot
   if (n_tiles <= 0) return 0;
   CMMVAE_REQUIRE(params && grads && tiles && rows && x && dout && pre && out_col && rstd && dx && dx_col,
                  "cond_bwd: null pointer");
-  CMMVAE_REQUIRE(Zin > 0 && Zout > 0 && slot_stride % 4 == 0, "cond_bwd: bad sizes");
-  const size_t smem = cond_smem(Zin, Zout);
-  CMMVAE_REQUIRE(smem <= 200 * 1024, "cond_bwd: Zin + Zout must be <= 1600");
+  CMMVAE_REQUIRE(Zin > 0 && Zout > 0 && Zin % 4 == 0 && Zout % 4 == 0 && slot_stride % 4 == 0,
+                 "cond_bwd: bad sizes (block widths must be multiples of 4)");
+  const size_t smem = cond_smem_bwd(Zin, Zout);
+  CMMVAE_REQUIRE(smem <= 200 * 1024, "cond_bwd: block too wide for the shared-memory tile");
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
     cudaFuncSetAttribute(cond_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -335,7 +536,7 @@ extern "C" int cmmvae_cond_adam(float* params, const float* grads, float* m, flo
                                 float weight_decay, void* stream) {
   if (n_present <= 0) return 0;
   CMMVAE_REQUIRE(params && grads && m && v && present && steps, "cond_adam: null pointer");
-  const int chunks = (int)((slot_stride + 1023) / 1024);
+  const int chunks = (int)((slot_stride / 4 + 255) / 256);
   // (the betas travel as doubles: the bias corrections 1 - beta ** t are taken as Python takes them)
   launch_pdl(cond_adam_kernel, dim3(n_present, chunks < 64 ? chunks : 64), dim3(256), 0, (cudaStream_t)stream, params,
              grads, m, v, slot_stride, present, (const int*)steps, norm_sq, max_norm, grad_scale, lr, beta1, beta2,
