@@ -74,7 +74,7 @@ def synth_batches(n, B, G, density, seed):
     return [synth_csr(B, G, density, seed + i) for i in range(n)]
 
 
-def build_model(config: int, only=None):
+def build_model(config: int, only=None, discriminators: bool = True):
     from mmvae_b200.config import AutogradConfig, GradientClipConfig
     from mmvae_b200.models import CMMVAEModel
     from mmvae_b200.modules import CLVAE, CMMVAE
@@ -102,7 +102,7 @@ def build_model(config: int, only=None):
                 Adversarial(FCBlockConfig([Z, 64], activation_fn=relu), FCBlockConfig([64]), list(conds), tmp)]
     clip = lambda: GradientClipConfig(val=10, algorithm="norm")  # noqa: E731
     extra = {}
-    if config == 4:      # BASELINE configs[3]: "+ output discriminator" (one per species, trained inside the step)
+    if config == 4 and discriminators:      # BASELINE configs[3]: "+ output discriminator" (one per species, trained inside the step)
         from mmvae_b200.modules import create_discriminators
         extra["output_discriminators"] = create_discriminators(species)
     model = CMMVAEModel(CMMVAE(vae, experts, advs), adv_weight=1.0,
@@ -546,7 +546,7 @@ def main():
     # next to the headline (which keeps the reference loader's pageable chunks), to show what the step sustains when
     # the host's DRAM bandwidth is not spent on packing (it is what limits `e2e` at N=8)
     pinned_leg = None
-    if os.environ.get("BENCH_PINNED_LEG", "1") == "1":
+    if os.environ.get("BENCH_PINNED_LEG", "1" if world > 1 else "0") == "1":
         pfeeds = {s: StagedCSRBatches(chunk_source(s), B, device=dev, workers=0, ahead=4, pin_chunks=True)
                   for s in names}
         main_iters, iters = iters, {s: iter(f) for s, f in pfeeds.items()}

@@ -189,7 +189,9 @@ def test_config4_shape_step_scalars():
     import bench
     from mmvae_b200 import layers as L
     L.set_precision("bf16")
-    model, species, _ = bench.build_model(4, only=("human",))
+    # (the core step at config 4's shape; its output discriminator has its own parity test,
+    # tests/test_output_discriminator_gpu.py)
+    model, species, _ = bench.build_model(4, only=("human",), discriminators=False)
     d = bench.Dims(4)
     G, B = d.G_HUMAN, 8192
     spec = oracle_spec({"human": G}, d.H1, d.H2, d.HV, d.Z)
