@@ -495,7 +495,10 @@ def main():
         while True:            # an endless epoch over the (pageable) chunk
             yield chunk, frame
 
-    feeds = {s: StagedCSRBatches(chunk_source(s), B, device=dev, workers=workers) for s in names}
+    # (BENCH_MAIN_PINNED=1: diagnostic -- the headline leg itself on page-locked chunks)
+    main_kw = dict(workers=0, ahead=int(os.environ.get("BENCH_PINNED_AHEAD", 4)), pin_chunks=True) \
+        if os.environ.get("BENCH_MAIN_PINNED") == "1" else dict(workers=workers)
+    feeds = {s: StagedCSRBatches(chunk_source(s), B, device=dev, **main_kw) for s in names}
     iters = {s: iter(f) for s, f in feeds.items()}
 
     pending = {}
@@ -546,8 +549,9 @@ def main():
     # next to the headline (which keeps the reference loader's pageable chunks), to show what the step sustains when
     # the host's DRAM bandwidth is not spent on packing (it is what limits `e2e` at N=8)
     pinned_leg = None
-    if os.environ.get("BENCH_PINNED_LEG", "1" if world > 1 else "0") == "1":
-        pfeeds = {s: StagedCSRBatches(chunk_source(s), B, device=dev, workers=0, ahead=4, pin_chunks=True)
+    if os.environ.get("BENCH_PINNED_LEG", "0") == "1":     # (opt-in: a third leg lengthens the run into the power cap)
+        pfeeds = {s: StagedCSRBatches(chunk_source(s), B, device=dev, workers=0,
+                                      ahead=int(os.environ.get("BENCH_PINNED_AHEAD", 4)), pin_chunks=True)
                   for s in names}
         main_iters, iters = iters, {s: iter(f) for s, f in pfeeds.items()}
         pending.clear()
