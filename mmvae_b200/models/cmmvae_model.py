@@ -11,6 +11,7 @@ from __future__ import annotations
 
 from typing import Optional
 
+import collections
 import numpy as np
 import pandas as pd
 import torch
@@ -67,7 +68,11 @@ class CMMVAEModel(BaseModel):
         # False: train through the module route (the same kernels under autograd) even when the fused engine
         # covers the topology
         self.use_fused_engine = True
-        self._pending_log = None
+        self._pending_log = collections.deque()
+        # pipelined mode: how many steps the host may run ahead of the step whose scalars it logs.  With 1 the host
+        # waits for step t-1 right after enqueueing step t, so any host hiccup longer than the slack of one step
+        # stalls the GPU -- and, data parallel, every GPU (the ranks meet at the flags each step); 2 absorbs it
+        self.log_lag = 2
         self._label_ring = {}    # (n conditions, B) -> [pinned blocks, events of their last copy, next slot]
 
     # ------------------------------------------------------------------------------------ engine
@@ -302,9 +307,10 @@ class CMMVAEModel(BaseModel):
         if self.sync_logging:
             self._log_step(eng.scalars(rec), expert_id)
         else:
-            prev, self._pending_log = self._pending_log, (eng.scalars_async(rec), rec, expert_id)
-            if prev is not None:
-                self._log_step(eng.scalars(prev[1], host=prev[0]), prev[2])
+            self._pending_log.append((eng.scalars_async(rec), rec, expert_id))
+            while len(self._pending_log) > max(1, int(self.log_lag)):
+                host, prev, eid = self._pending_log.popleft()
+                self._log_step(eng.scalars(prev, host=host), eid)
 
     def prefetch_batch(self, batch) -> None:
         """Data parallel only (no-op otherwise): call right after ``training_step`` with the NEXT batch, so that
@@ -320,9 +326,8 @@ class CMMVAEModel(BaseModel):
 
     def flush_logs(self):
         """log the scalars of the last step when ``sync_logging`` is off"""
-        if self._pending_log is not None:
-            host, rec, expert_id = self._pending_log
-            self._pending_log = None
+        while self._pending_log:
+            host, rec, expert_id = self._pending_log.popleft()
             self._log_step(self.engine().scalars(rec, host=host), expert_id)
         if self._engine:
             self._engine.finish()
