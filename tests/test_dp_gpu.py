@@ -57,7 +57,11 @@ def _inputs(d, rank, t=0):
 
 def _batch(d, rank, t, device):
     crow, col, val, eps = _inputs(d, rank, t)
-    return (csr_batch(crow, col, val, d["G"], device), pd.DataFrame({"cell": np.arange(d["B"])}), "human"), eps
+    rng = np.random.default_rng(7000 + 10 * t + rank)
+    meta = pd.DataFrame({"cell": np.arange(d["B"]),
+                         "assay": [f"assay_{i}" for i in rng.integers(0, 5, d["B"])],
+                         "dataset_id": [f"dataset_id_{i}" for i in rng.integers(0, 11, d["B"])]})
+    return (csr_batch(crow, col, val, d["G"], device), meta, "human"), eps
 
 
 def _step(model, d, rank, t=0, device="cuda", batch=None, after=None):
@@ -146,11 +150,19 @@ def _worker(rank, world, port, out, d, same_gpu, steps, pipelined=None):
     try:
         from mmvae_b200 import layers as L
         L.set_precision("bf16")
-        model = _build(d)
+        if d.get("adv"):      # two GRL adversaries (their small groups are summed over ranks inside the step)
+            import tempfile
+            from test_graph_gpu import _model
+            model = _model(d["G"], True, tempfile.mkdtemp())
+        else:
+            model = _build(d)
         model.cuda().train()
         model.configure_optimizers()
         eng = model.engine()
         assert eng.comm is not None and eng.world == world
+        if d.get("adv"):
+            for g in eng.groups.values():
+                g.lr = 2e-4       # (free-running comparison of two launch modes: keep the trajectories close)
         res = []
         if pipelined is not None:
             # the training loop's mode: results trail by a step, the next batch's records are exchanged underneath
@@ -251,24 +263,29 @@ def test_two_ranks_sharing_one_gpu_over_cuda_ipc(d):
     _check_two_ranks(d, res)
 
 
-def _compare_runs(a, b, steps):
+def _compare_runs(a, b, steps, extra=()):
     for r in range(2):
         for t in range(steps):
-            for k, tol in (("loss", 2e-3), ("recon_loss", 2e-3), ("kl_loss", 2e-2), ("grad_norms/expert_human", 5e-2)):
+            for k, tol in (("loss", 2e-3), ("recon_loss", 2e-3), ("kl_loss", 2e-2), ("grad_norms/expert_human", 5e-2)) \
+                    + tuple(extra):
                 assert a[r][1][t][k] == pytest.approx(b[r][1][t][k], rel=tol), (r, t, k)
         for k in ("experts.human.encoder.fc_layers.0.lin.weight", "experts.human.decoder.fc_layers.1.lin.weight",
                   "vae.encoder.mean_encoder.weight"):
             assert rel_l2(a[r][3][k], b[r][3][k]) < 2e-3, (r, k, rel_l2(a[r][3][k], b[r][3][k]))
 
 
-def test_two_ranks_graph_replay_equals_stream_launches():
+@pytest.mark.parametrize("adv", [False, True], ids=["core", "adversaries"])
+def test_two_ranks_graph_replay_equals_stream_launches(adv):
     """data parallel, pipelined mode: the step replayed from CUDA graphs (flag values read from the device block,
-    one graph pair per buffer parity, records prefetched or exchanged inline) walks the trajectory the
-    stream-launched step walks; after the run the replicas still agree bit for bit"""
+    one graph pair per buffer parity, records prefetched or exchanged inline; with adversaries: their replicated
+    groups summed over ranks inside the graphs) walks the trajectory the stream-launched step walks; after the run
+    the replicas still agree bit for bit"""
     steps = 8
-    eager = _run_ranks(2, DIMS, same_gpu=True, steps=steps, pipelined="stream")
-    graph = _run_ranks(2, DIMS, same_gpu=True, steps=steps, pipelined="graph")
-    _compare_runs(eager, graph, steps)
+    d = dict(DIMS, adv=True, G=2000, Z=32, B=128) if adv else DIMS
+    eager = _run_ranks(2, d, same_gpu=True, steps=steps, pipelined="stream")
+    graph = _run_ranks(2, d, same_gpu=True, steps=steps, pipelined="graph")
+    extra = (("discriminator_1", 2e-2), ("generator_2", 2e-2)) if adv else ()
+    _compare_runs(eager, graph, steps, extra)
     for k in graph[0][3]:
         if "running" in k or k.endswith("num_batches_tracked"):
             continue
