@@ -300,3 +300,54 @@ def test_custom_op_layer_is_registered():
         assert hasattr(torch.ops.cmmvae, name), name
     with pytest.raises(NotImplementedError, match="CPU"):
         torch.ops.cmmvae.cast_bf16(torch.randn(4), torch.empty(4, dtype=torch.bfloat16))
+
+
+def test_conditional_host_plan_groups_rows_by_value():
+    """CondBank.host_plan (pure host): every (batch key, cell) pair lands in exactly one tile of the slot of ITS value
+    -- what ConditionalLayer.forward's dict of row lists does (components.py:388-411) --, tiles hold <= 32 rows,
+    single-tile slots are flagged, '.' in a value is formatted like the reference (components.py:355-365), unknown
+    values raise KeyError like the ModuleDict lookup, and a non-shared key without species raises RuntimeError"""
+    import numpy as np
+    from mmvae_b200.conditional import CondBank, ROWS
+    bank = CondBank.__new__(CondBank)
+    bank.names = ["assay", "donor", "species"]
+    bank.kind = {"assay": "shared", "donor": "per_species", "species": "block"}
+    bank.block_slot = {("species", "human"): 0, ("species", "mouse"): 1}
+    bank.tables = {("assay", None): ({f"a_{i}": i for i in range(3)}, np.arange(2, 5, dtype=np.int32)),
+                   ("donor", "human"): ({f"d{i}": i for i in range(50)}, np.arange(5, 55, dtype=np.int32)),
+                   ("donor", "mouse"): ({f"d{i}": i for i in range(7)}, np.arange(55, 62, dtype=np.int32))}
+    B = 150
+    rng = np.random.default_rng(3)
+    assay = [f"a.{i}" if i == 1 else f"a_{i}" for i in rng.integers(0, 3, B)]      # 'a.1' must resolve to key 'a_1'
+    donor = [f"d{i}" for i in rng.integers(0, 50, B)]
+    meta = pd.DataFrame({"assay": assay, "donor": pd.Categorical(donor)})
+    tiles, rows, present, ranges, multi = bank.host_plan(meta, "human", B)
+    want = {0: {0: set(range(B))}}                                       # key index -> slot -> rows
+    want[0] = {}
+    for b in range(B):
+        want[0].setdefault(2 + int(assay[b].replace(".", "_")[2:]), set()).add(b)
+    want[1] = {}
+    for b in range(B):
+        want[1].setdefault(5 + int(donor[b][1:]), set()).add(b)
+    want[2] = {0: set(range(B))}
+    got, n_tiles_of = {0: {}, 1: {}, 2: {}}, {}
+    for slot, start, count, w in tiles:
+        c, sole = int(w) & 0xFFFF, int(w) >> 16
+        assert 0 < count <= ROWS
+        got[c].setdefault(int(slot), []).extend(rows[start:start + count].tolist())
+        n_tiles_of[int(slot)] = n_tiles_of.get(int(slot), 0) + 1
+        assert sole in (0, 1)
+    for c in (0, 1, 2):
+        assert {s: set(r) for s, r in got[c].items()} == want[c]
+        assert all(len(r) == len(set(r)) for r in got[c].values())
+    for slot, start, count, w in tiles:
+        assert (int(w) >> 16) == int(n_tiles_of[int(slot)] == 1)
+    assert sorted(present.tolist()) == sorted(n_tiles_of) and set(multi.tolist()) == {s for s, n in n_tiles_of.items() if n > 1}
+    for c, (lo, n) in enumerate(ranges):                                 # contiguous tile range per key
+        assert all((int(t[3]) & 0xFFFF) == c for t in tiles[lo:lo + n]) and n == sum((int(t[3]) & 0xFFFF) == c for t in tiles)
+    with pytest.raises(KeyError):
+        bank.host_plan(pd.DataFrame({"assay": ["zzz"] * B, "donor": donor}), "human", B)
+    with pytest.raises(RuntimeError, match="species"):
+        bank.host_plan(meta, None, B)
+    with pytest.raises(KeyError):
+        bank.host_plan(meta, "rat", B)
