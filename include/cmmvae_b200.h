@@ -207,6 +207,10 @@ int cmmvae_axpy(float* a, const float* b, float alpha, long long n, void* stream
  * val[i] : 0; the two products then run on the GEMM / SpMM entry points above. */
 int cmmvae_mask_vals_by_dl(const int32_t* crow, const int32_t* col, const float* val, int B,
                            const void* dlogits_bf16, int ldd, float* val_masked, void* stream);
+/* the same over rows given as [row_begin[b], row_end[b]) (the data-parallel route's received slabs) */
+int cmmvae_mask_vals_by_dl_rows(const int32_t* row_begin, const int32_t* row_end, const int32_t* col,
+                                const float* val, int B, const void* dlogits_bf16, int ldd, float* val_masked,
+                                void* stream);
 int cmmvae_sigmoid_fwd(const float* x, long long n, float* out_f32, void* out_bf16, void* stream);
 /* dx = dout * out * (1 - out) */
 int cmmvae_sigmoid_bwd(const float* dout, const float* out, long long n, float* dx, void* dx_bf16, void* stream);

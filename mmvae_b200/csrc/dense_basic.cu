@@ -617,7 +617,9 @@ __global__ void fold_cols_kernel(const float* __restrict__ dcat, int Z, int n, l
 // (dlogits == 0 with xhat > 0 would need xhat == x exactly).  So  xhat W^T = 1/2 dlogits W^T + Xm W^T  with
 // Xm = the CSR batch restricted to entries whose dlogits is non-zero: a dense GEMM over the tensor that is
 // already in HBM plus a sparse product -- xhat itself is never materialised.  This kernel builds Xm's values.
-__global__ void __launch_bounds__(256) mask_vals_by_dl_kernel(const int32_t* __restrict__ crow,
+// (row b = entries [row_begin[b], row_end[b]); a crow array is row_begin = crow, row_end = crow + 1)
+__global__ void __launch_bounds__(256) mask_vals_by_dl_kernel(const int32_t* __restrict__ row_begin,
+                                                              const int32_t* __restrict__ row_end,
                                                               const int32_t* __restrict__ col,
                                                               const float* __restrict__ val, int B,
                                                               const __nv_bfloat16* __restrict__ dl, int ldd,
@@ -625,7 +627,7 @@ __global__ void __launch_bounds__(256) mask_vals_by_dl_kernel(const int32_t* __r
   pdl_sync();
   const int lane = threadIdx.x & 31;
   for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += (gridDim.x * blockDim.x) >> 5) {
-    const int s = crow[b], e = crow[b + 1];
+    const int s = row_begin[b], e = row_end[b];
     const __nv_bfloat16* row = dl + (size_t)b * ldd;
     for (int i = s + lane; i < e; i += 32) {
       const uint16_t bits = *reinterpret_cast<const uint16_t*>(row + __ldg(col + i));
@@ -939,9 +941,21 @@ extern "C" int cmmvae_mask_vals_by_dl(const int32_t* crow, const int32_t* col, c
   CMMVAE_REQUIRE(crow && col && val && dlogits_bf16 && val_masked && B > 0, "mask_vals_by_dl: bad arguments");
   long long want = ((long long)B * 32 + 255) / 256;
   const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
-  launch_pdl(mask_vals_by_dl_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, crow, col, val, B,
+  launch_pdl(mask_vals_by_dl_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, crow, crow + 1, col, val, B,
              (const __nv_bfloat16*)dlogits_bf16, ldd, val_masked);
   return check_launch("mask_vals_by_dl");
+}
+
+extern "C" int cmmvae_mask_vals_by_dl_rows(const int32_t* row_begin, const int32_t* row_end, const int32_t* col,
+                                           const float* val, int B, const void* dlogits_bf16, int ldd,
+                                           float* val_masked, void* stream) {
+  CMMVAE_REQUIRE(row_begin && row_end && col && val && dlogits_bf16 && val_masked && B > 0,
+                 "mask_vals_by_dl_rows: bad arguments");
+  long long want = ((long long)B * 32 + 255) / 256;
+  const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
+  launch_pdl(mask_vals_by_dl_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, row_begin, row_end, col, val, B,
+             (const __nv_bfloat16*)dlogits_bf16, ldd, val_masked);
+  return check_launch("mask_vals_by_dl_rows");
 }
 
 extern "C" int cmmvae_sigmoid_fwd(const float* x, long long n, float* out_f32, void* out_bf16, void* stream) {

@@ -627,8 +627,6 @@ class StepEngine:
         # ---- output discriminators on the reconstruction (BASELINE config 4) ----
         self.odisc: Dict[str, dict] = {}
         for sid, disc in (output_discriminators or {}).items():
-            if self.comm is not None:
-                raise UnsupportedTopology("output discriminators are not part of the data-parallel route yet")
             l1, l2, l3 = disc.linears
             disc.to(dev)
             # first-layer weight stored [genes, hidden] (like the expert encoder's): the operand layout of both the
@@ -636,9 +634,10 @@ class StepEngine:
             g = self.groups[f"output_discriminators/{sid}"] = FlatGroup(
                 f"output_discriminators/{sid}", [[(l1.bias, False)], [(l2.bias, False)], [(l3.bias, False)],
                                                  [(l2.weight, False)], [(l3.weight, False)]], dev,
-                lr=output_discriminator_lr, weight_decay=0.0, sharded=[(l1.weight, True)], background_last=False)
+                lr=output_discriminator_lr, weight_decay=0.0, sharded=[(l1.weight, True)], background_last=False,
+                world=self.world, rank=self.rank)
             ph = lambda p, buf=None, g=g: g.phys(p, buf)   # noqa: E731
-            self.odisc[sid] = dict(group=g, G=l1.in_features, H1=l1.out_features, H2=l2.out_features,
+            self.odisc[sid] = dict(l1=l1, group=g, G=l1.in_features, H1=l1.out_features, H2=l2.out_features,
                                    W1t16=ph(l1.weight, g.p16), gW1t=ph(l1.weight, g.g), b1=ph(l1.bias), gb1=ph(l1.bias, g.g),
                                    W2=ph(l2.weight), gW2=ph(l2.weight, g.g), b2=ph(l2.bias), gb2=ph(l2.bias, g.g),
                                    W3=ph(l3.weight), gW3=ph(l3.weight, g.g), b3=ph(l3.bias), gb3=ph(l3.bias, g.g))
@@ -971,6 +970,85 @@ class StepEngine:
         g.grad_norm_sq(norm_slot)
         g.clip_adam(norm_slot, None, 1.0, advance=self._gmode is None)
 
+    def _od_tail(self, od, a3, y, loss_slot, a1, B):
+        """layers 2-3 + BCE + their backward on this rank's cells; returns d(loss)/d(a1 pre-activation) fp32 / bf16"""
+        H1, H2 = od["H1"], od["H2"]
+        a2pre, a2 = self.ws("od.a2pre", (B, H2)), self.ws("od.a2", (B, H2))
+        ops.gemm(a1, 0, od["W2"], 0, B, H2, H1, bias=od["b2"], C32=a2pre, tf32=True)
+        ops.sigmoid_fwd(a2pre, a2)
+        ops.gemm(a2, 0, od["W3"], 0, B, 1, H2, bias=od["b3"], C32=a3, use_tc=False)
+        da3 = self.ws("od.da3", (B, 1))
+        ops.bce_sigmoid(a3, y, None, da3, loss_slot)
+        ops.colsum(da3, od["gb3"])
+        ops.gemm(da3, 1, a2, 1, 1, H2, B, C32=od["gW3"], use_tc=False)
+        da2 = self.ws("od.da2", (B, H2))
+        ops.gemm(da3, 0, od["W3"], 1, B, H2, 1, C32=da2, use_tc=False)
+        da2pre = self.ws("od.da2pre", (B, H2))
+        ops.sigmoid_bwd(da2, a2, da2pre)
+        ops.colsum(da2pre, od["gb2"])
+        ops.gemm(da2pre, 1, a1, 1, H2, H1, B, C32=od["gW2"], tf32=True)
+        da1 = self.ws("od.da1", (B, H1))
+        ops.gemm(da2pre, 0, od["W2"], 1, B, H1, H2, C32=da1, tf32=True)
+        da1pre, da1pre16 = self.ws("od.da1pre", (B, H1)), self.ws("od.da1pre16", (B, H1), torch.bfloat16)
+        ops.sigmoid_bwd(da1, a1, da1pre, da1pre16)
+        ops.colsum(da1pre, od["gb1"])
+        return da1pre, da1pre16
+
+    def _dp_output_disc_step(self, od, expert_id, dpm, dl, B, loss_slot, norm_slot):
+        """the output discriminator on the data-parallel route: its first layer [genes, 128] is sharded by genes like
+        the expert's.  Rank r holds dlogits and the batch for (all cells) x (its genes): the two halves of
+        xhat W1^T -- 1/2 dlogits W1[genes_r] and Xm[:, genes_r] W1[genes_r] -- are routed from the kernels' epilogues
+        to the cells' owners and summed there; layers 2-3 and the loss run on the owner's cells; d(a1) is gathered
+        on every rank for dW1[genes_r] = xhat[:, genes_r]^T d(a1); the small layers' gradients are summed like the
+        other replicated groups.  DDP semantics: the mean over ranks of the per-rank BCE(mean) gradients."""
+        from mmvae_b200.modules.output_discriminator import SPECIES_LABEL
+        d, N, r, step = self._dp, self.world, self.rank, dpm["step"]
+        g, H1, l1 = od["group"], od["H1"], od["l1"]
+        per, NB = dpm["per"], dpm["NB"]
+        y = SPECIES_LABEL.get(expert_id, 0.0)
+        if "od" not in d:       # collective (every rank steps the same species): symmetric buffers of the route
+            d["od"] = dict(s=self.comm.alloc("od.s", N * B * H1 * 4), g=self.comm.alloc("od.g", N * B * H1 * 4),
+                           da=self.comm.alloc("od.da", N * B * H1 * 2))
+        o = d["od"]
+        W16, gW = g.own_rows(l1.weight, g.p16), g.own_rows(l1.weight, g.g)
+        if W16.shape[0] != per:
+            raise RuntimeError("output discriminator on the data-parallel route needs more than one process")
+        n_rec = dpm["n_rec"]
+        val_m = ops.mask_vals_by_dl_rows(dpm["rbeg"], dpm["rend"], dpm["col"], dpm["val"], dl,
+                                         self.ws("od.dp.valm", (n_rec,)))
+        tpm = ops.csr_tile_ptr_rows(dpm["rbeg"], dpm["rend"], dpm["col"], val_m, NB, per, n_rec - 8,
+                                    self.ws("od.dp.tp64", (NB * ((per + 63) // 64 + 1),), torch.int32),
+                                    self.ws("od.dp.packed", (n_rec + 8,), torch.int32))
+        # ---- forward: both halves routed to the owners
+        ops.csr_linear_fwd_tc_routed(tpm[1], tpm[0], NB, per, W16, [p + r * B * H1 * 4 for p in o["s"].ptr], B)
+        ops.gemm_routed(dl, 0, W16, 1, NB, H1, per, H1, [p + r * B * H1 * 4 for p in o["g"].ptr], B)
+        ops.peer_signal(self.comm.flag_ptrs("od.fwd"), step, step_dev=self._sd())
+        ops.peer_wait(self.comm.local_flags("od.fwd"), N, step, step_dev=self._sd())
+        a1pre, half = self.ws("od.a1pre", (B, H1)), self.ws("od.half", (B, H1))
+        ops.slab_sum(o["s"].local.view(torch.float32), N, B * H1, B * H1, out32=a1pre, bias=od["b1"], H=H1)
+        ops.slab_sum(o["g"].local.view(torch.float32), N, B * H1, B * H1, out32=half)
+        ops.axpy(a1pre, half, 0.5)
+        a1 = self.ws("od.a1", (B, H1))
+        ops.sigmoid_fwd(a1pre, a1)
+        da1pre, da1pre16 = self._od_tail(od, self.ws("od.a3", (B, 1)), y, loss_slot, a1, B)
+        # ---- backward: d(a1) of every rank's cells on every rank, then this rank's gene rows of dW1
+        ops.peer_push(da1pre16, B * H1 * 2, [p + r * B * H1 * 2 for p in o["da"].ptr], self.comm.flag_ptrs("od.da"), step,
+                      self.comm.ticket, step_dev=self._sd())
+        self._dp_allreduce_start(dpm, g, g.tail_lo, g.n)
+        ops.peer_wait(self.comm.local_flags("od.da"), N, step, step_dev=self._sd())
+        da_all = o["da"].local.view(torch.bfloat16).view(NB, H1)
+        ssq = self.ws("od.dp.ssq", (1,), torch.float64)
+        ssq.zero_()
+        ops.csr_linear_bwd_w_tc(tpm[1], tpm[0], NB, per, da_all, gW)                   # Xm^T da1
+        halfw = self.ws("od.dp.halfw", (per, H1))
+        ops.gemm(dl, 1, da_all, 1, per, H1, NB, C32=halfw)                              # dlogits^T da1
+        ops.axpy(gW, halfw, 0.5)
+        ops.sumsq(gW, ssq)
+        self._dp_allreduce_finish(dpm, g, g.tail_lo, g.n)
+        ops.sumsq(g.g[g.tail_lo:g.n], norm_slot)
+        dpm["od_ssq"] = ssq          # (the other ranks' rows join the logged norm in the scalar exchange)
+        g.clip_adam(norm_slot, None, 1.0 / N, advance=self._gmode is None)
+
     # ------------------------------------------------------ data parallel over peer memory (gene shards)
     # Cells shard across ranks; the two gene-sized layers shard by GENES (SURVEY.md 7.8).  Rank r owns rows
     # [r * per, (r + 1) * per) of W1 (stored [genes, hidden]), Wout and bout -- values, gradients, Adam state -- and
@@ -1127,6 +1205,7 @@ class StepEngine:
         info = d["scratch"][par][3]
         g0, g1, crow_s = r * per, min(G, (r + 1) * per), None
         return dict(step=step, per=per, g0=g0, g1=g1, NB=NB, crow=crow_s, col=col_s, val=val_s, tp=tp, info=info,
+                    rbeg=rbeg, rend=rend, n_rec=n_rec,
                     shard_ssq=self.ws("dp.shard_ssq", (1,), torch.float64), loss_part=self.ws("dp.loss_part", (N,), torch.float64))
 
     def _dp_first_layer_fwd(self, dpm, gexp: FlatGroup, lp: LayerPlan, B: int):
@@ -1250,10 +1329,14 @@ class StepEngine:
         mine = self.ws("dp.scal_mine", (SC,), torch.float64, zero=True)
         mine[:N].copy_(dpm["loss_part"])
         mine[N:N + 1].copy_(dpm["shard_ssq"])
+        if "od_ssq" in dpm:
+            mine[N + 1:N + 2].copy_(dpm["od_ssq"])
         ops.peer_push(mine, SC * 8, [p + r * SC * 8 for p in d["scal"].ptr], self.comm.flag_ptrs("scal"), step,
                       self.comm.ticket, step_dev=self._sd())
         ops.peer_wait(self.comm.local_flags("scal"), N, step, step_dev=self._sd())
         ops.dp_scalars(d["scal"].local.view(torch.float64), N, SC, r, sc[0:1], s_norm_expert)
+        if "od_ssq" in dpm:      # (logged only: the discriminator's update is not clipped)
+            dpm["od_norm_slot"].add_(d["scal"].local.view(torch.float64).view(N, SC)[:, N + 1].sum())
 
     def _after_reparameterize(self, z32, z16, B: int):
         """CLVAE.after_reparameterize (clvae.py:89-111): identity, or the conditional layers (whose host plan for
@@ -1564,8 +1647,12 @@ class StepEngine:
         if od is not None:
             if not (fused and use_tc_spmm):
                 raise RuntimeError("the output discriminator runs on the fused bf16 decoder route only")
-            self._output_disc_step(od, expert_id, crow, col, val, nnz, tp, dl, B, G, sc[od_slot:od_slot + 1],
-                                   sc[od_slot + 1:od_slot + 2])
+            if dpm is not None:
+                dpm["od_norm_slot"] = sc[od_slot + 1:od_slot + 2]
+                self._dp_output_disc_step(od, expert_id, dpm, dl, B, sc[od_slot:od_slot + 1], sc[od_slot + 1:od_slot + 2])
+            else:
+                self._output_disc_step(od, expert_id, crow, col, val, nnz, tp, dl, B, G, sc[od_slot:od_slot + 1],
+                                       sc[od_slot + 1:od_slot + 2])
 
         # ---------------- adversaries: discriminator update, then generator pass ----------------
         d_hidden = {}
@@ -1746,7 +1833,7 @@ class StepEngine:
         out["loss"] = total
         if rec.get("od_slot") is not None:     # reference writer tags: meta_disc/md_<species> (meta_discriminators.py:165-167)
             out[f"meta_disc/md_{rec['expert_id']}"] = sc[rec["od_slot"]]
-            out[f"grad_norms/output_discriminator_{rec['expert_id']}"] = math.sqrt(sc[rec["od_slot"] + 1])
+            out[f"grad_norms/output_discriminator_{rec['expert_id']}"] = math.sqrt(sc[rec["od_slot"] + 1]) * rec["gscale"]
         return out
 
     # ------------------------------------------------------------------------------- eval forward

@@ -528,6 +528,12 @@ def mask_vals_by_dl(crow, col, val, dl16, val_m):
     return val_m
 
 
+def mask_vals_by_dl_rows(row_begin, row_end, col, val, dl16, val_m):
+    _check(lib().cmmvae_mask_vals_by_dl_rows(_ptr(row_begin), _ptr(row_end), _ptr(col), _ptr(val), row_begin.numel(),
+                                             _ptr(dl16), dl16.stride(0), _ptr(val_m), _stream()), "mask_vals_by_dl_rows")
+    return val_m
+
+
 def sigmoid_fwd(x, out32=None, out16=None):
     _check(lib().cmmvae_sigmoid_fwd(_ptr(x), _c.c_longlong(x.numel()), _ptr(out32), _ptr(out16), _stream()),
            "sigmoid_fwd")

@@ -25,7 +25,7 @@ DIMS = dict(G=3000, H1=256, H2=128, Hv=64, Z=32, B=160)
 TINY = dict(G=264, H1=64, H2=32, Hv=32, Z=16, B=24)      # 2 ranks: rank 1 owns 8 real gene rows + 248 rows of padding
 
 
-def _build(d, dropout=0.0):
+def _build(d, dropout=0.0, od=False):
     from mmvae_b200.config import AutogradConfig, GradientClipConfig
     from mmvae_b200.models import CMMVAEModel
     from mmvae_b200.modules import CLVAE, CMMVAE
@@ -38,8 +38,13 @@ def _build(d, dropout=0.0):
     vae = CLVAE(FCBlockConfig([d["H2"], d["Hv"]], use_batch_norm=True, activation_fn=relu, return_hidden=True),
                 FCBlockConfig([d["Z"], d["Hv"], d["H2"]], activation_fn=relu), latent_dim=d["Z"])
     clip = lambda: GradientClipConfig(val=10, algorithm="norm")  # noqa: E731
+    extra = {}
+    if od:
+        from mmvae_b200.modules import create_discriminators
+        torch.manual_seed(1)
+        extra["output_discriminators"] = create_discriminators({"human": d["G"]})
     return CMMVAEModel(CMMVAE(vae, experts, []), autograd_config=AutogradConfig(clip(), clip(), clip()),
-                       kl_annealing_fn=KLAnnealingFn(1.0))
+                       kl_annealing_fn=KLAnnealingFn(1.0), **extra)
 
 
 def _spec(d):
@@ -80,7 +85,8 @@ def _step(model, d, rank, t=0, device="cuda", batch=None, after=None):
 
 def _grads(model):
     """every parameter's gradient as left by the step (row-sharded ones: this rank's rows are valid, others 0)"""
-    return {n[len("module."):]: p.grad.detach().float().cpu().clone() for n, p in model.named_parameters()}
+    return {(n[len("module."):] if n.startswith("module.") else n): p.grad.detach().float().cpu().clone()
+            for n, p in model.named_parameters()}
 
 
 def _single_process_reference(d, world, steps=1):
@@ -88,7 +94,7 @@ def _single_process_reference(d, world, steps=1):
     from mmvae_b200 import layers as L
     L.set_precision("bf16")
     os.environ.pop("CMMVAE_FORCE_DP", None)
-    model = _build(d)
+    model = _build(d, od=bool(d.get("od")))
     init = {k: v.detach().clone() for k, v in model.state_dict().items()}
     model.cuda().train()
     model.configure_optimizers()
@@ -155,7 +161,7 @@ def _worker(rank, world, port, out, d, same_gpu, steps, pipelined=None):
             from test_graph_gpu import _model
             model = _model(d["G"], True, tempfile.mkdtemp())
         else:
-            model = _build(d)
+            model = _build(d, od=bool(d.get("od")))
         model.cuda().train()
         model.configure_optimizers()
         eng = model.engine()
@@ -181,7 +187,8 @@ def _worker(rank, world, port, out, d, same_gpu, steps, pipelined=None):
             replays = sum(e.get("replays", 0) for e in eng._graphs.values())
             assert replays >= steps - 4, (replays, list(eng._graphs))
         grads = _grads(model)                      # of the last step
-        sd = {k[len("module."):]: v.detach().cpu() for k, v in model.state_dict().items()}   # gathers the rows
+        sd = {(k[len("module."):] if k.startswith("module.") else k): v.detach().cpu()
+              for k, v in model.state_dict().items()}   # gathers the rows
         # numpy arrays travel by value (torch tensors would travel as file descriptors of a process about to exit)
         out.put((rank, res, {k: v.numpy() for k, v in grads.items()}, {k: v.numpy() for k, v in sd.items()}))
         dist.barrier()
@@ -255,6 +262,38 @@ def _check_two_ranks(d, res, world=2):
         ua, ub = torch.from_numpy(sd[k]).double().flatten() - p0, P[k].double().flatten() - p0
         cos = float((ua * ub).sum() / (ua.norm() * ub.norm()).clamp_min(1e-30))
         assert cos > 0.95, (k, cos)
+
+
+def test_two_ranks_output_discriminator_on_the_gene_sharded_route():
+    """BASELINE config 4 data parallel: the discriminator's first layer is sharded by genes like the expert's; the
+    two halves of xhat W1^T are routed to the cells' owners, d(a1) is gathered for the rows of dW1.  Per-rank loss =
+    the single-process loss on that rank's batch; gradients = the SUM over ranks of the single-process gradients
+    (own gene rows of W1 / replicated small layers); replicas agree bit for bit after the step."""
+    d = dict(DIMS, od=True)
+    world = 2
+    res = _run_ranks(world, d, same_gpu=True)
+    init, ref = _single_process_reference(d, world)
+    per = (-(-d["G"] // world) + 127) // 128 * 128
+    pre = "output_discriminators.human."
+    names = [k for k in ref[0][1] if k.startswith(pre)]
+    assert len(names) == 6
+    for r in range(world):
+        _, logs, grads, sd = res[r]
+        assert logs[0]["meta_disc"] == pytest.approx(ref[r][0]["meta_disc"], rel=2e-3), r
+        assert logs[0]["loss"] == pytest.approx(ref[r][0]["loss"], rel=2e-5), r
+        for k in names:
+            a, b = torch.from_numpy(grads[k]), sum(ref[q][1][k] for q in range(world))
+            if k == pre + "0.weight":      # [128, G]: gene axis is dim 1; this rank's genes
+                lo, hi = r * per, min(d["G"], (r + 1) * per)
+                a, b = a[:, lo:hi], b[:, lo:hi]
+            assert rel_l2(a.numpy(), b.numpy()) < 3e-2, (r, k, rel_l2(a.numpy(), b.numpy()))
+    for k in res[0][3]:
+        if "running" in k or k.endswith("num_batches_tracked"):
+            continue
+        assert np.array_equal(res[0][3][k], res[1][3][k]), k
+    # the discriminator moved (Adam at lr 1e-3 on the mean gradient)
+    k = pre + "2.weight"
+    assert not np.array_equal(res[0][3][k], init[k].numpy())
 
 
 @pytest.mark.parametrize("d", [DIMS, TINY], ids=["mid", "tiny-padding-shard"])
