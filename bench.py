@@ -370,9 +370,10 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
-    if os.environ.get("BENCH_WATCHDOG"):      # debugging aid: dump every thread's stack if the run stalls
-        import faulthandler
-        faulthandler.dump_traceback_later(int(os.environ["BENCH_WATCHDOG"]), exit=True)
+    # a stalled run (e.g. a rank that died while its peers spin on its flags) ends itself instead of holding the GPUs:
+    # every thread's stack is dumped and the process exits (the normal run takes 1-3 minutes)
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("BENCH_WATCHDOG", 1500)), exit=True)
     same_gpu = os.environ.get("BENCH_SAME_GPU") == "1"     # debugging aid: all ranks share GPU 0 (CUDA IPC, gloo)
     if same_gpu:
         local_rank = 0
