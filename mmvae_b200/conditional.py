@@ -103,6 +103,7 @@ class CondBank:
                     self.block_slot[(bk, sp)] = self.slot_of_path[f"layers.{bk}.{sp}"]
         self._pinned = [None] * 4
         self._pin_ev = [None] * 4
+        self._used_ev = [None] * 4      # recorded behind the last kernel that reads a plan's device arrays
         self._pin_i = 0
         self.plan: Optional[dict] = None
         self.applied_present = 0
@@ -192,8 +193,9 @@ class CondBank:
         total = sum(sizes)
         i = self._pin_i
         self._pin_i = (i + 1) % len(self._pinned)
-        if self._pin_ev[i] is not None:
-            self._pin_ev[i].synchronize()
+        for ev in (self._pin_ev[i], self._used_ev[i]):      # the block's last copy has left, its last reader is done
+            if ev is not None:
+                ev.synchronize()
         if self._pinned[i] is None or self._pinned[i][0].numel() < total:
             cap = max(total * 2, 4096)
             self._pinned[i] = (torch.empty(cap, dtype=torch.int32, pin_memory=True),
@@ -212,7 +214,7 @@ class CondBank:
         view = lambda k: dev[offs[k]:offs[k] + parts[k].size]   # noqa: E731
         self.plan = dict(order=order, n_tiles=len(tiles), tiles=view(0), rows=view(1), present=view(2),
                          n_present=int(present.size), out_col=view(3), dx_col=view(4), multi=view(5),
-                         n_multi=int(multi.size), ranges=ranges, B=B,
+                         n_multi=int(multi.size), ranges=ranges, B=B, ring_slot=i,
                          index={bk: c for c, bk in enumerate(self.names)})
         return self.plan
 
@@ -230,6 +232,7 @@ class CondBank:
             ops.cond_fwd(self.p, self.S, self.Zin, self.Zout, pl["tiles"], pl["n_tiles"], pl["rows"], z32,
                          z32.shape[1], out, out16, pre, W, pl["out_col"], rstd, B, self.layer_norm, self.relu)
             pl["x"] = z32
+            self._mark_used()
             return out, out16
         cur = z32
         pl["stage_in"] = {}
@@ -246,6 +249,7 @@ class CondBank:
                          self.layer_norm, self.relu)
             pl["stage_in"][bk] = cur
             cur = out
+        self._mark_used()
         return cur, out16
 
     def backward(self, dout: torch.Tensor, ws) -> torch.Tensor:
@@ -273,6 +277,11 @@ class CondBank:
             d = dx
         return d
 
+    def _mark_used(self):
+        ev = torch.cuda.Event()
+        ev.record()
+        self._used_ev[self.plan["ring_slot"]] = ev
+
     def add_norm_sq(self, out: torch.Tensor):
         pl = self.plan
         ops.cond_sumsq(self.g, self.S, pl["present"], pl["n_present"], out)
@@ -281,6 +290,7 @@ class CondBank:
         pl = self.plan
         ops.cond_adam(self.p, self.g, self.m, self.v, self.S, pl["present"], pl["n_present"], self.steps, norm_sq,
                       max_norm, grad_scale, self.lr, self.betas[0], self.betas[1], self.eps, self.wd)
+        self._mark_used()
 
     # ------------------------------------------------------------------------------- torch.optim.Adam state
     def state_entries(self, first_index: int) -> dict:
