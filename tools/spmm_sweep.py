@@ -149,17 +149,20 @@ def dp_sweep(args):
     rows = []
     step = 0
     for B in args.batches:
-        Yin = comm.alloc(f"Y{B}", world * B * H * 4)
+        # as in the step engine (_dp_setup): with few cell tiles the product is also cut along the genes, one slab each
+        units = ((world * B + 127) // 128) * ((H + 255) // 256)
+        S = max(1, min(4, 148 // units))
+        Yin = comm.alloc(f"Y{B}", world * S * B * H * 4)
         for d in args.densities:
             crow, col, val = gpu_csr(world * B, d, 7, rank * per, min(G, (rank + 1) * per))
             nnz = int(col.numel())
             tp, packed = ops.csr_tile_ptr(crow, col, val, per, nnz)
-            route = [p + rank * B * H * 4 for p in Yin.ptr]
+            route = [p + rank * S * B * H * 4 for p in Yin.ptr]
 
             def run():
                 nonlocal step
                 step += 1
-                ops.csr_linear_fwd_tc_routed(packed, tp, world * B, per, W, route, B, 1, 0)
+                ops.csr_linear_fwd_tc_routed(packed, tp, world * B, per, W, route, B, S, B * H)
                 ops.peer_signal(comm.flag_ptrs("Y"), step)
                 ops.peer_wait(comm.local_flags("Y"), world, step)
             dist.barrier()
@@ -169,8 +172,8 @@ def dp_sweep(args):
             t = float(tt)
             fwd_bytes = nnz * 8 + (world * B + 1) * 4 + per * H * 2 + world * B * H * 4
             t_tensor = 2.0 * world * B * per * H / TENSOR
-            rows.append(dict(B=B, d=d, world=world, nnz=nnz, ms=t * 1e3, tensor_frac=t_tensor / t,
-                             hbm_frac=fwd_bytes / HBM / t, nvlink_gbs=(world - 1) * B * H * 4 / t / 1e9))
+            rows.append(dict(B=B, d=d, world=world, S=S, nnz=nnz, ms=t * 1e3, tensor_frac=t_tensor / t,
+                             hbm_frac=fwd_bytes / HBM / t, nvlink_gbs=(world - 1) * S * B * H * 4 / t / 1e9))
             if rank == 0:
                 print(json.dumps(rows[-1]), flush=True)
     if rank == 0:
@@ -178,10 +181,12 @@ def dp_sweep(args):
         with open(out, "w") as f:
             f.write(f"# Routed first-layer product on {world} GPUs (gene-sharded data-parallel route)\n\nPer rank: {world} x B cells "
                     f"x {per} genes, H={H}; partial sums stored into the owners' buffers over NVLink by the epilogue, then "
-                    "flag round trip; max over ranks, median of 6, L2 flushed.\n\n| B per rank | d | nnz in shard | ms | "
-                    "issued / tensor peak | HBM frac | NVLink out GB/s per rank |\n|---|---|---|---|---|---|---|\n")
+                    "flag round trip; max over ranks, median of 6, L2 flushed (cold weights: inside a step the kernel runs "
+                    "~0.1 ms faster, `kernels_ms.csr_linear_fwd` of bench.py).  `S` = gene pieces per rank (own slab each) "
+                    "when there are fewer cell tiles than SMs.\n\n| B per rank | d | S | nnz in shard | ms | "
+                    "issued / tensor peak | HBM frac | NVLink out GB/s per rank |\n|---|---|---|---|---|---|---|---|\n")
             for r in rows:
-                f.write(f"| {r['B']} | {r['d']:.0%} | {r['nnz']} | {r['ms']:.3f} | {r['tensor_frac']:.2f} | "
+                f.write(f"| {r['B']} | {r['d']:.0%} | {r['S']} | {r['nnz']} | {r['ms']:.3f} | {r['tensor_frac']:.2f} | "
                         f"{r['hbm_frac']:.3f} | {r['nvlink_gbs']:.0f} |\n")
         print("wrote", out)
     dist.barrier()
