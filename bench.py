@@ -532,11 +532,20 @@ def main():
         api_step(t)
     barrier()
     host_t.update(fetch=0.0, training_step=0.0)
+    prof = None
+    if os.environ.get("BENCH_PROFILE") == "1" and rank == 0:      # debugging aid: where does the host loop spend its time?
+        import cProfile
+        prof = cProfile.Profile()
+        prof.enable()
     e0.record()
     loss = None
     for t in range(args.steps):
         loss = api_step(t + w_api)
     host_main = {k: v * 1e3 / args.steps for k, v in host_t.items()}
+    if prof is not None:
+        import pstats
+        prof.disable()
+        pstats.Stats(prof, stream=sys.stderr).sort_stats("tottime").print_stats(35)
     model.flush_logs()
     e1.record()
     barrier()

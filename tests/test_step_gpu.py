@@ -334,6 +334,34 @@ def test_conditional_layers_match_reference(tmp_path, route):
         L.set_precision("bf16")
 
 
+def test_conditional_layers_bf16_policy_tracks_reference(tmp_path):
+    """the same golden run under the default bf16 policy (bf16 operands in the main GEMMs; the conditional blocks
+    themselves stay fp32): every logged scalar of the three steps within the bf16 tolerances"""
+    import random
+    from mmvae_b200 import layers as L
+    from mmvae_b200.modules.base import KLAnnealingFn
+    L.set_precision("bf16")
+    gc = GoldenCase("human_conditional")
+    model = build_b200_model(gc, tmp_path, kl_fn=KLAnnealingFn(0.5))
+    model.load_state_dict({f"module.{k}": v for k, v in gc.state("init").items()}, strict=True)
+    model.cuda().train()
+    model.configure_optimizers()
+    assert model.engine().cond is not None
+    for t in range(gc.n_steps):
+        s = gc.step(t)
+        L.inject_noise(s["eps"].cuda())
+        meta = pd.DataFrame({c: [f"{c}_{int(i)}" for i in s["labels"][c]] for c in CONDITIONS})
+        model.logged_metrics.clear()
+        random.seed(4242 + t)
+        model.training_step((csr_batch(s["crow"], s["col"], s["val"], gc.genes["human"]), meta, "human"), t)
+        got = {k: float(v) for k, v in model.logged_metrics.items()}
+        assert set(got) == set(s["logs"])
+        for k, v in s["logs"].items():
+            tol = 6e-2 if k.startswith("grad_norms") else (3e-2 if "kl_loss" in k or "adversarial" in k else 5e-3)
+            # ("Mean" = the mean of mu, a small number near zero: absolute tolerance)
+            assert got[k] == pytest.approx(v, rel=tol, abs=5e-3 if k.startswith("Mean") else 1e-4), (t, k, got[k], v)
+
+
 def test_pipelined_optimizer_gives_the_same_training_run(tmp_path):
     """sync_logging=False turns on the pipelined mode: the step runs on a high-priority stream, the output
     layer's clip+Adam on a background stream underneath the next forward pass, logs arrive one step late.
