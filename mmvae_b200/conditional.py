@@ -106,7 +106,6 @@ class CondBank:
         self._used_ev = [None] * 4      # recorded behind the last kernel that reads a plan's device arrays
         self._pin_i = 0
         self.plan: Optional[dict] = None
-        self.applied_present = 0
 
     def _table(self, path: str, layer) -> tuple:
         keys = list(layer.conditions.keys())

@@ -21,9 +21,8 @@ and exposed as a ``[hidden, genes]`` view.
 from __future__ import annotations
 
 import math
-import random
 import os
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional
 
 import torch
