@@ -253,6 +253,10 @@ class CMMVAEModel(BaseModel):
         through autograd Functions, optimisers are stock Adam; order of operations as in the reference
         (cmmvae_model.py:138-217): discriminator update first, then the generator loss through the GRL."""
         x, metadata, expert_id = batch
+        from mmvae_b200 import dp
+        if dp.world_size() > 1:      # no gradient exchange on this route: replicas would silently drift apart
+            raise RuntimeError("this topology trains through the module route (" + str(getattr(self, "_module_route_reason", "")) +
+                               "), which is single-process; the data-parallel step needs the fused engine")
         opts = self.get_optimizers()
         vae_opt, expert_opt = opts["vae"], opts["experts"][expert_id]
         adv_opts = opts.get("adversarials") or {}

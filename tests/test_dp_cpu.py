@@ -200,3 +200,49 @@ def test_single_process_helpers():
     assert dp.world_size() == 1 and dp.rank() == 0
     assert dp.allreduce_sum_(torch.ones(3)) is None
     assert dp.chunk_bounds(10, [0, 4, 4, 10, 12]) == [(0, 4), (4, 10)]
+
+
+def _worker_module_route_guard(rank, world, port, out):
+    """a topology that trains through the module route has no gradient exchange: with more than one process its
+    training_step must refuse to run instead of letting the replicas drift apart"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import pandas as pd
+        from mmvae_b200.config import AutogradConfig, GradientClipConfig
+        from mmvae_b200.models import CMMVAEModel
+        from mmvae_b200.modules import CLVAE, CMMVAE
+        from mmvae_b200.modules.base import Expert, Experts, FCBlockConfig, KLAnnealingFn
+        relu = torch.nn.ReLU
+        experts = Experts([Expert("human", FCBlockConfig([40, 16, 8], use_batch_norm=True, activation_fn=relu),
+                                  FCBlockConfig([8, 16, 40], activation_fn=relu))])
+        vae = CLVAE(FCBlockConfig([8, 8], use_batch_norm=True, activation_fn=relu), FCBlockConfig([4, 8, 8], activation_fn=relu),
+                    latent_dim=4)
+        clip = lambda: GradientClipConfig(val=10, algorithm="norm")  # noqa: E731
+        model = CMMVAEModel(CMMVAE(vae, experts, []), autograd_config=AutogradConfig(clip(), clip(), clip()),
+                            kl_annealing_fn=KLAnnealingFn(1.0))
+        model.use_fused_engine = False
+        assert model.engine() is None
+        x = torch.eye(4, 40).to_sparse_csr()
+        try:
+            model.training_step((x, pd.DataFrame({"cell": range(4)}), "human"), 0)
+            out.put((rank, "no error"))
+        except RuntimeError as e:
+            out.put((rank, "ok" if "single-process" in str(e) else repr(e)))
+    except Exception as e:  # noqa: BLE001
+        out.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_module_route_refuses_to_run_data_parallel():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29500 + (os.getpid() + 1511) % 2000
+    procs = [ctx.Process(target=_worker_module_route_guard, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
