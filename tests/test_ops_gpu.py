@@ -487,8 +487,10 @@ def test_torch_custom_ops_reach_the_kernels(ops):
     assert rel(z, ML[:, :8] + eps * torch.sqrt(torch.exp(ML[:, 8:]) + 1e-4)) < 1e-6 and sums.shape == (3,)
 
 
-@pytest.mark.parametrize("parallel,relu,layer_norm", [(True, False, True), (False, True, True), (True, True, False)])
-def test_conditional_bank_matches_torch_modules(tmp_path, parallel, relu, layer_norm):
+@pytest.mark.parametrize("parallel,relu,layer_norm,Z", [(True, False, True, 64), (False, True, True, 64),
+                                                         (True, True, False, 64), (True, False, True, 160),
+                                                         (False, False, True, 36)])
+def test_conditional_bank_matches_torch_modules(tmp_path, parallel, relu, layer_norm, Z):
     """mmvae_b200.conditional.CondBank + csrc/conditional.cu against the module route (ConditionalLayers.forward,
     components.py:581-631, under autograd) at a batch where values own several 32-row tiles: outputs, input
     gradient, the gradients of the values present (others untouched), and per-value Adam steps over 3 batches
@@ -502,7 +504,7 @@ def test_conditional_bank_matches_torch_modules(tmp_path, parallel, relu, layer_
     import copy, os
     from mmvae_b200 import layers as L
     torch.manual_seed(5)
-    Z, B = 64, 200
+    B = 200                      # (Z = 160: blocks wider than one 128-column pass of the tile kernels; 36: narrower)
     L.set_precision("fp32")      # (the module route's Linear layers follow the precision policy)
     try:
         _conditional_bank_case(tmp_path, parallel, relu, layer_norm, Z, B)
