@@ -36,6 +36,21 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert isinstance(lib.cmmvae_last_error(), bytes)
 
 
+def test_every_exported_entry_point_is_declared_in_the_header():
+    """the other direction: the library exports no `cmmvae_*` function that include/cmmvae_b200.h does not declare
+    (the header is the contract a reference-side binding is written against)"""
+    import shutil
+    import subprocess
+    nm = shutil.which("nm")
+    if nm is None:
+        pytest.skip("nm not available")
+    out = subprocess.run([nm, "-D", "--defined-only", _lib.build_library()], capture_output=True, text=True, check=True)
+    exported = {line.split()[-1] for line in out.stdout.splitlines() if line.split() and line.split()[-1].startswith("cmmvae_")}
+    declared = set(_lib.exported_symbols_in_header())
+    assert exported - declared == set(), sorted(exported - declared)
+    assert declared - exported == set(), sorted(declared - exported)
+
+
 def test_argument_validation_happens_before_any_launch():
     lib = _lib.load()
     lib.cmmvae_last_error.restype = ctypes.c_char_p
